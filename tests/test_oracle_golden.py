@@ -1,0 +1,168 @@
+"""Pins oracle/ against the reference: golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py), its known-answer vector, and its tests 1-5 restated
+(/root/reference/src/validate_implementation.py:20-187).  CPU only."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bc_oracle as O
+from tests import _golden as G
+
+CASES = list(G.forward_cases())
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_forward_restatement_matches_reference_bitwise(case):
+    """Same library calls in the same order -> bit-identical to the recorded reference output."""
+    c, x, bias, y_ref, y_cached_ref = G.load_case(case)
+    y = O.bc_forward_torch(c, x, bias)
+    assert y.dtype == case["y_dtype"] and y.shape == y_ref.shape
+    assert torch.equal(y, y_ref)
+    yc = O.bc_forward_cached_torch(O.CachedSpectrum(c), x, bias)
+    assert torch.equal(yc, y_cached_ref)
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["store_c"] and c["dtype"] == torch.float32],
+                         ids=lambda c: c["name"])
+def test_dense64_and_c_oracles_agree_with_reference(case):
+    """The two FFT-free oracles (numpy fp64 dense weight, plain-C direct convolution) agree with the
+    recorded reference output to fp32 round-off: max|d| <= 1e-5 * max|y| (reference tolerance, test 5)."""
+    c, x, bias, y_ref, _ = G.load_case(case)
+    y64 = O.bc_forward_dense64(c, x, bias)
+    scale = max(1e-30, float(np.abs(y64).max()))
+    assert np.abs(y64 - y_ref.double().numpy()).max() <= 1e-5 * scale
+    lib = _c_oracle()
+    p, q, B = c.shape
+    x2 = np.ascontiguousarray(x.double().numpy().reshape(-1, q * B))
+    yc = np.empty((x2.shape[0], p * B), dtype=np.float64)
+    b64 = None if bias is None else np.ascontiguousarray(bias.double().numpy())
+    rc = lib.bc_oracle_forward_f64(np.ascontiguousarray(c.numpy()).ctypes.data_as(ctypes.c_void_p), p, q, B,
+                                   x2.ctypes.data_as(ctypes.c_void_p), x2.shape[0],
+                                   None if b64 is None else b64.ctypes.data_as(ctypes.c_void_p),
+                                   yc.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    assert np.abs(yc - y64.reshape(yc.shape)).max() <= 1e-12 * scale
+
+
+def _c_oracle():
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "libbc_oracle.so")
+    if not os.path.exists(path):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.dirname(path)])
+    lib = ctypes.CDLL(path)
+    lib.bc_oracle_forward_f64.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bc_oracle_project_f64.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    return lib
+
+
+def test_primitive_matches_reference():
+    v = G.vectors()
+    for row in v["prim_meta"]:
+        key, n, dt = str(row).split("|")
+        c, x, y = G.t(v[f"{key}/c"]), G.t(v[f"{key}/x"], G.DT[dt]), G.t(v[f"{key}/y"], G.DT[dt])
+        assert torch.equal(O.circulant_matvec_fft(c, x), y)
+
+
+def test_projections_match_reference():
+    v = G.vectors()
+    lib = _c_oracle()
+    for row in v["proj_meta"]:
+        key, B, dt = str(row).split("|")
+        W = G.t(v[f"{key}/W"], G.DT[dt])
+        ref = G.t(v[f"{key}/loss_aware"], G.DT[dt])
+        assert torch.equal(O.project_loss_aware_loops(W), ref)
+        vec = O.project_loss_aware(W)
+        assert (vec.float() - ref.float()).abs().max() <= 4 * G.ulp(G.DT[dt]) * ref.float().abs().max()
+        assert torch.equal(O.project_diag(W, "diag"), G.t(v[f"{key}/diag"], G.DT[dt]))
+        assert torch.equal(O.project_diag(W, "diag_inv"), G.t(v[f"{key}/diag_inv"], G.DT[dt]))
+        if dt == "float32":
+            W64 = np.ascontiguousarray(W.double().numpy())
+            c64 = np.empty(int(B))
+            assert lib.bc_oracle_project_f64(W64.ctypes.data_as(ctypes.c_void_p), int(B),
+                                             c64.ctypes.data_as(ctypes.c_void_p)) == 0
+            assert np.abs(c64 - ref.double().numpy()).max() <= 1e-5 * np.abs(c64).max()
+    with pytest.raises(ValueError):
+        O.project_diag(torch.eye(4), "nope")
+
+
+def test_known_answer_vector():
+    """src/validate_implementation.py:47-78: projecting the circulant of c=[1..8] returns c (ratio std < 1e-5)."""
+    v = G.vectors()
+    c_true = torch.arange(1.0, 9.0)
+    idx = torch.arange(8)
+    C = c_true[(idx[:, None] - idx[None, :]) % 8]
+    assert torch.equal(C, G.t(v["known/C"]))
+    rec = O.project_loss_aware_loops(C)
+    assert torch.equal(rec, G.t(v["known/c_recovered"]))
+    assert (rec / c_true).std() < 1e-5
+    assert torch.equal(O.circulant_from_first_col(c_true), G.t(v["known/circ_from_first_col"]))
+    assert torch.equal(O.circulant_from_first_col(c_true), C)          # C[:,j] = roll(c,j)  <=>  C[i,j] = c[(i-j)%B]
+    assert np.array_equal(O.dense_bc_weight64(c_true.reshape(1, 1, 8)), C.double().numpy())
+
+
+def test_from_linear_matches_reference():
+    v = G.vectors()
+    for row in v["from_linear_meta"]:
+        key, inf, outf, B, dt, has_bias, c_dt = str(row).split("|")
+        W = G.t(v[f"{key}/W"], G.DT[dt])
+        c_ref = G.t(v[f"{key}/c"], torch.float32)
+        assert c_dt == "float32"
+        c = O.from_linear_c(W, int(B))
+        assert c.shape == c_ref.shape
+        assert (c - c_ref).abs().max() <= 4 * G.ulp(G.DT[dt]) * c_ref.abs().max()
+        if int(has_bias):
+            assert np.array_equal(v[f"{key}/lin_bias"].astype(np.float32), v[f"{key}/bc_bias"].astype(np.float32))
+
+
+def test_reference_validation_suite_restated():
+    """Tests 1, 3, 4, 5 of src/validate_implementation.py with its seed and tolerances."""
+    torch.manual_seed(42)
+    B = 64
+    c, x = torch.randn(B), torch.randn(B)
+    idx = torch.arange(B)
+    C = c[(idx[:, None] - idx[None, :]) % B]
+    assert ((C @ x) - O.circulant_matvec_fft(c, x)).norm() / (C @ x).norm() < 1e-5            # test 1
+    c_proj = O.project_loss_aware_loops(C)
+    assert ((C @ x) - O.circulant_matvec_fft(c_proj, x)).norm() / (C @ x).norm() < 1e-4       # test 3
+    W = torch.empty(128, 256).uniform_(-1, 1)
+    cfl = O.from_linear_c(W, 64)
+    assert cfl.shape == (2, 4, 64)
+    assert (cfl[0, 0] - O.project_loss_aware_loops(W[:64, :64])).abs().max() < 1e-5           # test 4
+    cc = torch.randn(2, 4, 32)
+    xx = torch.randn(4, 128)
+    y = O.bc_forward_torch(cc, xx)
+    yd = xx.double().numpy() @ O.dense_bc_weight64(cc).T
+    assert np.linalg.norm(yd - y.double().numpy()) / np.linalg.norm(yd) < 1e-4               # test 5
+
+
+def test_packed_spectrum_roundtrip():
+    rng = np.random.default_rng(0)
+    for B in (64, 128, 256):
+        c = rng.standard_normal((3, 2, B))
+        pk = O.packed_spectrum(c)
+        assert pk.shape == c.shape
+        F = O.unpack_spectrum(pk)
+        assert np.allclose(F, np.fft.rfft(c, axis=-1), atol=1e-12)
+        assert np.allclose(np.fft.irfft(F, n=B, axis=-1), c, atol=1e-12)
+
+
+def test_backward_oracle_matches_autograd_through_the_restated_forward():
+    torch.manual_seed(3)
+    c = torch.randn(2, 3, 64, dtype=torch.float64, requires_grad=True)
+    x = torch.randn(5, 192, dtype=torch.float64, requires_grad=True)
+    gy = torch.randn(5, 128, dtype=torch.float64)
+    W = c[:, :, (torch.arange(64)[:, None] - torch.arange(64)[None, :]) % 64].permute(0, 2, 1, 3).reshape(128, 192)
+    (x @ W.T).backward(gy)
+    gx, gc, gb = O.bc_backward_dense64(c.detach().numpy(), x.detach().numpy(), gy.numpy())
+    assert np.allclose(gx, x.grad.numpy(), atol=1e-10)
+    assert np.allclose(gc, c.grad.numpy(), atol=1e-10)
+    assert np.allclose(gb, gy.sum(0).numpy(), atol=1e-12)
+
+
+def test_unsupported_input_dim_raises():
+    with pytest.raises(ValueError, match="Unsupported input dim"):
+        O.bc_forward_torch(torch.zeros(1, 1, 64), torch.zeros(64))
