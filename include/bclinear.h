@@ -1,0 +1,131 @@
+/* bclinear.h -- C ABI of libbclinear.so: the block-circulant (BC) linear forward for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE path of Pinguhat/llama-fft: BlockCirculantLinear.forward
+ * (reference src/patch_llama_fft.py:226-275; cached-spectrum variant src/bench_all_in_one.py:179-231).
+ * The reference has no FFI of its own -- its seam is the Python module object -- so the entry points below
+ * are what a binding for that path needs: each one cites the reference lines it replaces.
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   B  block size, 64 | 128 | 256          q = in_features / B        p = out_features / B
+ *   c[j,i,:] is the first column of the circulant block mapping input block i to output block j,
+ *   C_{j,i}[r,s] = c[j,i,(r-s) mod B]                         (src/patch_llama_fft.py:152-154, :86-88)
+ *   y[n, jB:(j+1)B] = irfft( sum_i rfft(c[j,i]) * rfft(x[n, iB:(i+1)B]) )   (src/patch_llama_fft.py:252-263)
+ *
+ * Ownership and threading
+ *   Every pointer is caller-owned.  Device pointers unless the name says host.  The library never allocates,
+ *   frees or retains memory, keeps no mutable global state besides a thread-local error string, never syncs
+ *   the device (except the *_host convenience calls, which say so), and every launch goes to the stream that
+ *   is passed in (a cudaStream_t cast to void*; NULL = the legacy default stream).  All calls are CUDA-graph
+ *   capturable except the *_host ones.  Errors never abort or print: a negative bcl_status is returned and
+ *   bcl_last_error() describes it.  There is no CPU fallback and no other backend.
+ */
+#ifndef BCLINEAR_H_
+#define BCLINEAR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCL_ABI_VERSION 3
+
+typedef enum bcl_dtype { BCL_F32 = 0, BCL_F16 = 1, BCL_BF16 = 2 } bcl_dtype;
+
+/* Spectrum layouts in HBM (DESIGN.md "Data layout").
+ *   STREAM  [p][q][B] packed half-spectrum, frequency-contiguous: {Re F0, Re F_{B/2}, Re F1, Im F1, ...}.
+ *           Exactly the size of c.  Used by the bandwidth-bound small-N (decode) kernel.
+ *   GEMM    per-frequency real-embedded complex matrices for the tcgen05 prefill path (bf16 only):
+ *           [B/2][2p][2q] K-major tiles, see DESIGN.md. */
+typedef enum bcl_layout { BCL_LAYOUT_STREAM = 0, BCL_LAYOUT_GEMM = 1 } bcl_layout;
+
+typedef enum bcl_status {
+    BCL_OK = 0,
+    BCL_ERR_ARG = -1,        /* NULL pointer, negative size, unknown enum */
+    BCL_ERR_SHAPE = -2,      /* p, q, N out of range / in_features mismatch */
+    BCL_ERR_BLOCK = -3,      /* block size not in {64,128,256} */
+    BCL_ERR_ALIGN = -4,      /* pointer or row stride not 16-byte aligned */
+    BCL_ERR_DTYPE = -5,      /* unsupported dtype combination for this layout */
+    BCL_ERR_WORKSPACE = -6,  /* workspace too small */
+    BCL_ERR_CUDA = -7,       /* a CUDA runtime call failed; see bcl_last_error() */
+    BCL_ERR_UNSUPPORTED = -8 /* valid request this build has no kernel for (never a silent fallback) */
+} bcl_status;
+
+int bcl_abi_version(void);
+
+/* Thread-local, NUL-terminated description of the last failure on this thread ("" if none). */
+const char* bcl_last_error(void);
+
+/* ---- spectrum precompute: replaces Cf = rfft(c.to(float32)) --------------------------------------------
+ * reference: src/patch_llama_fft.py:256-257 (recomputed every forward) and the memoised
+ * _Cf_cache of src/bench_all_in_one.py:204-219.  c is the (p,q,B) float32 parameter, row-major. */
+size_t bcl_spectrum_bytes(int p, int q, int B, int spec_dtype, int layout);
+int bcl_precompute_spectrum(const float* c, int p, int q, int B,
+                            void* spec, int spec_dtype, int layout, void* stream);
+
+/* ---- forward: replaces steps 2-9 of BlockCirculantLinear.forward -----------------------------------------
+ * reference: src/patch_llama_fft.py:246-271 (reshape, fp32 up-cast, rfft, einsum, irfft, down-cast, bias).
+ *   x        (N, in) row-major, inner dimension contiguous, row stride in ELEMENTS
+ *   y        (N, out), dtype y_dtype.  Epilogue order is the reference's: y32 is rounded to x_dtype first
+ *            (:266), then the bias is added in the promoted dtype y_dtype (:270-271).  Without a bias
+ *            y_dtype must equal x_dtype.
+ *   bias     (out) or NULL
+ *   workspace  at least bcl_workspace_bytes(...) bytes, 256-byte aligned (may be NULL when that is 0)
+ * N == 0 is a no-op.  */
+size_t bcl_workspace_bytes(int64_t N, int p, int q, int B, int spec_dtype, int layout);
+int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
+                const void* spec, int spec_dtype, int layout, int p, int q, int B,
+                const void* bias, int bias_dtype,
+                void* y, int y_dtype, int64_t y_row_stride,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- grouped forward: many independent BC linears in ONE launch -------------------------------------------
+ * The reference calls one module at a time (HF LlamaMLP/LlamaAttention -> forward); at batch-1
+ * decode a single projection is 0.5-1.4 MB of spectrum, far below launch latency, so callers that hold
+ * several independent projections (q/k/v of one layer, gate/up, or a synthetic sweep over layers) submit
+ * them together.  All problems of a group share B, spec_dtype (STREAM layout) and have N <= 8.
+ * The plan (problem table + a byte-balanced partition of output block-rows over CTAs) is encoded on the
+ * host into caller memory; the caller copies it to the device once and replays it. */
+typedef struct bcl_problem {
+    const void* x;          /* (N, q*B)  */
+    const void* spec;       /* STREAM layout, p*q*B elements of spec_dtype */
+    const void* bias;       /* (p*B) or NULL */
+    void* y;                /* (N, p*B)  */
+    int64_t N;
+    int64_t x_row_stride;   /* elements */
+    int64_t y_row_stride;   /* elements */
+    int32_t p, q;
+    int32_t x_dtype, y_dtype, bias_dtype;
+    int32_t reserved;
+} bcl_problem;
+
+size_t bcl_group_plan_bytes(int count, int num_ctas);
+/* num_ctas: how many CTAs to partition over (e.g. 2 * SM count); returns BCL_OK and fills host_plan. */
+int bcl_group_plan_encode(const bcl_problem* problems, int count, int B, int spec_dtype, int num_ctas,
+                          void* host_plan, size_t host_plan_bytes);
+/* dev_plan = device copy of host_plan (same bytes).  host_plan is read for the launch geometry only. */
+int bcl_forward_grouped(const void* dev_plan, const void* host_plan, void* stream);
+
+/* ---- end-to-end convenience with HOST buffers (what bench.py's e2e figure times) --------------------------
+ * Copies x from (pinned) host memory to the caller's device staging buffers, runs bcl_forward, copies y
+ * back and synchronises the stream.  dev_x/dev_y are caller-owned device staging areas of N*in / N*out
+ * elements.  Not graph-capturable (it synchronises). */
+int bcl_forward_host(const void* host_x, int x_dtype, int64_t N,
+                     const void* spec, int spec_dtype, int layout, int p, int q, int B,
+                     const void* bias, int bias_dtype,
+                     void* host_y, int y_dtype,
+                     void* dev_x, void* dev_y, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- construction: replaces the Python p*q*B loops of from_linear ------------------------------------------
+ * reference: src/patch_llama_fft.py:201-219 + :110-128.  W is (p*B, q*B) row-major of dtype w_dtype;
+ * c[j,i,t] = alpha * mean_r W[jB+r, iB+(r-t) mod B], alpha as :124-126, arithmetic rounded to w_dtype the way
+ * the reference's per-block torch ops round, result stored as float32 (p,q,B). */
+int bcl_project_from_dense(const void* W, int w_dtype, int64_t w_row_stride, int p, int q, int B,
+                           float* c, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCLINEAR_H_ */

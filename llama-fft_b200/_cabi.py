@@ -1,0 +1,98 @@
+"""ctypes binding of libbclinear.so (include/bclinear.h).  No torch types cross this boundary: only raw
+pointers, sizes and enums.  There is no fallback: if the library is missing or a call fails, this raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbclinear.so")
+
+ABI_VERSION = 3
+F32, F16, BF16 = 0, 1, 2
+LAYOUT_STREAM, LAYOUT_GEMM = 0, 1
+
+DTYPE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+
+# every symbol include/bclinear.h declares (tests check the built library exports all of them)
+SYMBOLS = (
+    "bcl_abi_version", "bcl_last_error", "bcl_spectrum_bytes", "bcl_precompute_spectrum", "bcl_workspace_bytes",
+    "bcl_forward", "bcl_group_plan_bytes", "bcl_group_plan_encode", "bcl_forward_grouped", "bcl_forward_host",
+    "bcl_project_from_dense",
+)
+
+
+class BclError(RuntimeError):
+    pass
+
+
+class Problem(ctypes.Structure):
+    """struct bcl_problem"""
+    _fields_ = [("x", ctypes.c_void_p), ("spec", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("y", ctypes.c_void_p),
+                ("N", ctypes.c_int64), ("x_row_stride", ctypes.c_int64), ("y_row_stride", ctypes.c_int64),
+                ("p", ctypes.c_int32), ("q", ctypes.c_int32),
+                ("x_dtype", ctypes.c_int32), ("y_dtype", ctypes.c_int32), ("bias_dtype", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and type the library.  Raises loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built.  Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` or `make -C llama-fft_b200/csrc`.  "
+            "There is no CPU or torch.fft fallback for the BC-linear hot path.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+    L.bcl_abi_version.restype = i32
+    L.bcl_last_error.restype = ctypes.c_char_p
+    L.bcl_spectrum_bytes.restype = sz
+    L.bcl_spectrum_bytes.argtypes = [i32, i32, i32, i32, i32]
+    L.bcl_precompute_spectrum.argtypes = [vp, i32, i32, i32, vp, i32, i32, vp]
+    L.bcl_workspace_bytes.restype = sz
+    L.bcl_workspace_bytes.argtypes = [i64, i32, i32, i32, i32, i32]
+    L.bcl_forward.argtypes = [vp, i32, i64, i64, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32, i64, vp, sz, vp]
+    L.bcl_group_plan_bytes.restype = sz
+    L.bcl_group_plan_bytes.argtypes = [i32, i32]
+    L.bcl_group_plan_encode.argtypes = [ctypes.POINTER(Problem), i32, i32, i32, i32, vp, sz]
+    L.bcl_forward_grouped.argtypes = [vp, vp, vp]
+    L.bcl_forward_host.argtypes = [vp, i32, i64, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, vp, vp, sz, vp]
+    L.bcl_project_from_dense.argtypes = [vp, i32, i64, i32, i32, i32, vp, vp]
+    for name in SYMBOLS:
+        getattr(L, name)
+    if L.bcl_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH} has ABI {L.bcl_abi_version()}, this package needs {ABI_VERSION}: rebuild it")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    """Map a bcl_status to the exception the reference's Python would have raised."""
+    if rc == 0:
+        return
+    msg = lib().bcl_last_error().decode("utf-8", "replace")
+    text = f"{what}: {msg} (bcl_status {rc})"
+    if rc in (-1, -2, -3, -5):          # ARG, SHAPE, BLOCK, DTYPE
+        raise ValueError(text)
+    if rc == -8:
+        raise NotImplementedError(text)
+    raise BclError(text)
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} is on {t.device}: the BC-linear forward runs only as sm_100a CUDA kernels "
+            "(no CPU / torch.fft fallback).  Move the module and its input to a CUDA device.")

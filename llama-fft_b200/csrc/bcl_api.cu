@@ -1,0 +1,223 @@
+// bcl_api.cu -- the extern "C" surface declared in include/bclinear.h.  Argument validation, dispatch to the
+// kernel launchers, group-plan encoding.  No allocation, no global mutable state (thread-local error text only).
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <vector>
+#include "bcl_common.cuh"
+#include "bcl_kernels.h"
+
+namespace {
+
+thread_local char g_err[384] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(BCL_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+bool valid_B(int B) { return B == 64 || B == 128 || B == 256; }
+bool valid_dt(int dt) { return dt == BCL_F32 || dt == BCL_F16 || dt == BCL_BF16; }
+bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+// the reference's type promotion for y_flat + bias (src/patch_llama_fft.py:270-271)
+int promote(int a, int b) {
+    if (a == b) return a;
+    return BCL_F32;   // f32 with anything, and f16 + bf16, promote to f32 in PyTorch
+}
+
+int check_problem(const void* x, int x_dtype, int64_t N, int64_t xs, const void* spec, int p, int q, int B,
+                  const void* bias, int bias_dtype, const void* y, int y_dtype, int64_t ys) {
+    if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
+    if (p <= 0 || q <= 0 || N < 0) return fail(BCL_ERR_SHAPE, "bad shape p=%d q=%d N=%lld", p, q, (long long)N);
+    if (!valid_dt(x_dtype) || !valid_dt(y_dtype) || (bias && !valid_dt(bias_dtype))) return fail(BCL_ERR_DTYPE, "unknown dtype enum");
+    if (N == 0) return BCL_OK;
+    if (!x || !spec || !y) return fail(BCL_ERR_ARG, "NULL x/spec/y");
+    if (xs < (int64_t)q * B || ys < (int64_t)p * B) return fail(BCL_ERR_SHAPE, "row stride smaller than the feature dimension");
+    const int want = bias ? promote(x_dtype, bias_dtype) : x_dtype;
+    if (y_dtype != want) return fail(BCL_ERR_DTYPE, "y_dtype %d but the reference's promotion of x_dtype %d (+bias %d) gives %d", y_dtype, x_dtype, bias ? bias_dtype : -1, want);
+    if (!aligned(x, 16) || !aligned(y, 16) || !aligned(spec, 16) || (bias && !aligned(bias, 16)))
+        return fail(BCL_ERR_ALIGN, "x, y, spec and bias must be 16-byte aligned");
+    if ((xs * bcl::dtype_size(x_dtype)) % 16 || (ys * bcl::dtype_size(y_dtype)) % 16)
+        return fail(BCL_ERR_ALIGN, "row strides must be multiples of 16 bytes");
+    return BCL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bcl_abi_version(void) { return BCL_ABI_VERSION; }
+
+const char* bcl_last_error(void) { return g_err; }
+
+size_t bcl_spectrum_bytes(int p, int q, int B, int spec_dtype, int layout) {
+    if (!valid_B(B) || p <= 0 || q <= 0) return 0;
+    if (layout == BCL_LAYOUT_STREAM) {
+        if (spec_dtype != BCL_F32 && spec_dtype != BCL_BF16) return 0;
+        return (size_t)p * q * B * (spec_dtype == BCL_F32 ? 4 : 2);
+    }
+    return 0;
+}
+
+int bcl_precompute_spectrum(const float* c, int p, int q, int B, void* spec, int spec_dtype, int layout, void* stream) {
+    if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
+    if (p <= 0 || q <= 0) return fail(BCL_ERR_SHAPE, "bad shape p=%d q=%d", p, q);
+    if (!c || !spec) return fail(BCL_ERR_ARG, "NULL c/spec");
+    if (!aligned(c, 16) || !aligned(spec, 16)) return fail(BCL_ERR_ALIGN, "c and spec must be 16-byte aligned");
+    if (layout == BCL_LAYOUT_STREAM) {
+        if (spec_dtype != BCL_F32 && spec_dtype != BCL_BF16) return fail(BCL_ERR_DTYPE, "STREAM spectrum must be f32 or bf16");
+        cudaError_t e = bcl::launch_spectrum_stream(c, spec, p, q, B, spec_dtype, (cudaStream_t)stream);
+        return e == cudaSuccess ? BCL_OK : cuda_fail(e, "spectrum precompute launch");
+    }
+    return fail(BCL_ERR_UNSUPPORTED, "spectrum layout %d is not built", layout);
+}
+
+size_t bcl_workspace_bytes(int64_t N, int p, int q, int B, int spec_dtype, int layout) {
+    (void)N; (void)p; (void)q; (void)B; (void)spec_dtype;
+    if (layout == BCL_LAYOUT_STREAM) return 0;
+    return 0;
+}
+
+int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
+                const void* spec, int spec_dtype, int layout, int p, int q, int B,
+                const void* bias, int bias_dtype, void* y, int y_dtype, int64_t y_row_stride,
+                void* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace; (void)workspace_bytes;
+    int rc = check_problem(x, x_dtype, N, x_row_stride, spec, p, q, B, bias, bias_dtype, y, y_dtype, y_row_stride);
+    if (rc != BCL_OK || N == 0) return rc;
+    if (layout == BCL_LAYOUT_STREAM) {
+        if (spec_dtype != BCL_F32 && spec_dtype != BCL_BF16) return fail(BCL_ERR_DTYPE, "STREAM spectrum must be f32 or bf16");
+        if (N > 65535LL * 8) return fail(BCL_ERR_SHAPE, "N=%lld exceeds the stream kernel's grid limit; split the batch", (long long)N);
+        bcl::ProblemDev P{x, spec, bias, y, N, x_row_stride, y_row_stride, p, q, x_dtype, y_dtype, bias ? bias_dtype : BCL_F32, 0};
+        cudaError_t e = bcl::launch_stream_single(P, B, spec_dtype, (cudaStream_t)stream);
+        return e == cudaSuccess ? BCL_OK : cuda_fail(e, "stream forward launch");
+    }
+    return fail(BCL_ERR_UNSUPPORTED, "forward for spectrum layout %d is not built", layout);
+}
+
+size_t bcl_group_plan_bytes(int count, int num_ctas) {
+    if (count <= 0 || num_ctas <= 0) return 0;
+    // segments: every CTA boundary and every problem boundary can start one
+    size_t segs = (size_t)count + (size_t)num_ctas;
+    size_t b = sizeof(bcl::GroupPlanHeader);
+    b = (b + 15) & ~(size_t)15; b += (size_t)count * sizeof(bcl::ProblemDev);
+    b = (b + 15) & ~(size_t)15; b += ((size_t)num_ctas + 1) * sizeof(int);
+    b = (b + 15) & ~(size_t)15; b += segs * 16;
+    return (b + 255) & ~(size_t)255;
+}
+
+int bcl_group_plan_encode(const bcl_problem* problems, int count, int B, int spec_dtype, int num_ctas,
+                          void* host_plan, size_t host_plan_bytes) {
+    if (!problems || !host_plan || count <= 0 || num_ctas <= 0) return fail(BCL_ERR_ARG, "bad plan arguments");
+    if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
+    if (spec_dtype != BCL_F32 && spec_dtype != BCL_BF16) return fail(BCL_ERR_DTYPE, "STREAM spectrum must be f32 or bf16");
+    const size_t need = bcl_group_plan_bytes(count, num_ctas);
+    if (host_plan_bytes < need) return fail(BCL_ERR_WORKSPACE, "plan buffer %zu < %zu bytes", host_plan_bytes, need);
+    int64_t maxN = 0; int qmax = 0; int64_t total_w = 0;
+    for (int g = 0; g < count; ++g) {
+        const bcl_problem& P = problems[g];
+        int rc = check_problem(P.x, P.x_dtype, P.N, P.x_row_stride, P.spec, P.p, P.q, B, P.bias, P.bias_dtype, P.y, P.y_dtype, P.y_row_stride);
+        if (rc != BCL_OK) return rc;
+        if (P.N < 1 || P.N > 8) return fail(BCL_ERR_SHAPE, "grouped problems need 1 <= N <= 8 (problem %d has %lld)", g, (long long)P.N);
+        if (P.N > maxN) maxN = P.N;
+        if (P.q > qmax) qmax = P.q;
+        total_w += (int64_t)P.p * P.q;
+    }
+    int nt = 1; while (nt < maxN) nt *= 2;
+    if (bcl::stream_smem_bytes(B, nt, qmax, 8) > 200 * 1024)
+        return fail(BCL_ERR_UNSUPPORTED, "x spectrum tile (N=%d, q=%d, B=%d) exceeds shared memory; call bcl_forward per problem", nt, qmax, B);
+
+    unsigned char* base = reinterpret_cast<unsigned char*>(host_plan);
+    memset(base, 0, need);
+    bcl::GroupPlanHeader H{};
+    H.magic = bcl::kPlanMagic; H.count = count; H.num_ctas = num_ctas; H.B = B; H.spec_dtype = spec_dtype; H.nt = nt; H.qmax = qmax;
+    size_t off = sizeof(bcl::GroupPlanHeader);
+    off = (off + 15) & ~(size_t)15; H.off_problems = off; off += (size_t)count * sizeof(bcl::ProblemDev);
+    off = (off + 15) & ~(size_t)15; H.off_cta_ptr = off; off += ((size_t)num_ctas + 1) * sizeof(int);
+    off = (off + 15) & ~(size_t)15; H.off_segs = off;
+    H.total_bytes = need;
+
+    bcl::ProblemDev* pd = reinterpret_cast<bcl::ProblemDev*>(base + H.off_problems);
+    for (int g = 0; g < count; ++g) {
+        const bcl_problem& P = problems[g];
+        pd[g] = bcl::ProblemDev{P.x, P.spec, P.bias, P.y, P.N, P.x_row_stride, P.y_row_stride, P.p, P.q, P.x_dtype, P.y_dtype,
+                                P.bias ? P.bias_dtype : BCL_F32, 0};
+    }
+    // byte-balanced partition of the flattened (problem, row) sequence: CTA b owns the rows whose cumulative
+    // weight (q per row = bytes streamed) falls in [b, b+1) * total / num_ctas.
+    int* cta_ptr = reinterpret_cast<int*>(base + H.off_cta_ptr);
+    int* segs = reinterpret_cast<int*>(base + H.off_segs);
+    int nseg = 0, cta = 0;
+    int64_t cum = 0;
+    cta_ptr[0] = 0;
+    for (int g = 0; g < count; ++g) {
+        const int p = problems[g].p, q = problems[g].q;
+        int j = 0;
+        while (j < p) {
+            // rows of this problem that still belong to the current CTA
+            const int64_t limit = (total_w * (cta + 1) + num_ctas - 1) / num_ctas;   // ceil
+            int64_t room = limit - cum;
+            int take = (int)((room + q - 1) / q);
+            if (take < 1) take = 1;
+            if (take > p - j) take = p - j;
+            segs[4 * nseg + 0] = g; segs[4 * nseg + 1] = j; segs[4 * nseg + 2] = j + take; segs[4 * nseg + 3] = 0;
+            ++nseg;
+            j += take; cum += (int64_t)take * q;
+            while (cta < num_ctas - 1 && cum >= (total_w * (cta + 1) + num_ctas - 1) / num_ctas) { ++cta; cta_ptr[cta] = nseg; }
+        }
+    }
+    while (cta < num_ctas) { ++cta; cta_ptr[cta] = nseg; }
+    H.num_segs = nseg;
+    memcpy(base, &H, sizeof(H));
+    return BCL_OK;
+}
+
+int bcl_forward_grouped(const void* dev_plan, const void* host_plan, void* stream) {
+    if (!dev_plan || !host_plan) return fail(BCL_ERR_ARG, "NULL plan");
+    bcl::GroupPlanHeader H;
+    memcpy(&H, host_plan, sizeof(H));
+    if (H.magic != bcl::kPlanMagic) return fail(BCL_ERR_ARG, "host_plan was not written by bcl_group_plan_encode");
+    if (!aligned(dev_plan, 16)) return fail(BCL_ERR_ALIGN, "dev_plan must be 16-byte aligned");
+    cudaError_t e = bcl::launch_stream_grouped(H, dev_plan, (cudaStream_t)stream);
+    return e == cudaSuccess ? BCL_OK : cuda_fail(e, "grouped forward launch");
+}
+
+int bcl_forward_host(const void* host_x, int x_dtype, int64_t N,
+                     const void* spec, int spec_dtype, int layout, int p, int q, int B,
+                     const void* bias, int bias_dtype, void* host_y, int y_dtype,
+                     void* dev_x, void* dev_y, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!host_x || !host_y || !dev_x || !dev_y) return fail(BCL_ERR_ARG, "NULL host/device staging buffer");
+    if (!valid_B(B) || p <= 0 || q <= 0 || N < 0 || !valid_dt(x_dtype) || !valid_dt(y_dtype)) return fail(BCL_ERR_ARG, "bad arguments");
+    if (N == 0) return BCL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t xb = (size_t)N * q * B * bcl::dtype_size(x_dtype), yb = (size_t)N * p * B * bcl::dtype_size(y_dtype);
+    cudaError_t e = cudaMemcpyAsync(dev_x, host_x, xb, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "H2D copy of x");
+    int rc = bcl_forward(dev_x, x_dtype, N, (int64_t)q * B, spec, spec_dtype, layout, p, q, B, bias, bias_dtype,
+                         dev_y, y_dtype, (int64_t)p * B, workspace, workspace_bytes, stream);
+    if (rc != BCL_OK) return rc;
+    e = cudaMemcpyAsync(host_y, dev_y, yb, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(e, "D2H copy of y");
+    e = cudaStreamSynchronize(st);
+    return e == cudaSuccess ? BCL_OK : cuda_fail(e, "stream synchronize");
+}
+
+int bcl_project_from_dense(const void* W, int w_dtype, int64_t w_row_stride, int p, int q, int B, float* c, void* stream) {
+    if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
+    if (p <= 0 || q <= 0) return fail(BCL_ERR_SHAPE, "bad shape p=%d q=%d", p, q);
+    if (!W || !c) return fail(BCL_ERR_ARG, "NULL W/c");
+    if (!valid_dt(w_dtype)) return fail(BCL_ERR_DTYPE, "unknown dtype enum");
+    if (w_row_stride < (int64_t)q * B) return fail(BCL_ERR_SHAPE, "row stride smaller than in_features");
+    cudaError_t e = bcl::launch_project_from_dense(W, w_dtype, w_row_stride, p, q, B, c, (cudaStream_t)stream);
+    return e == cudaSuccess ? BCL_OK : cuda_fail(e, "projection launch");
+}
+
+}  // extern "C"

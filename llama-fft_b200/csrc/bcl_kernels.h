@@ -1,0 +1,42 @@
+// bcl_kernels.h -- internal interface between the C-ABI layer (bcl_api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace bcl {
+
+// Device-side view of one BC-linear problem (mirrors bcl_problem, plus nothing the host must keep alive).
+struct ProblemDev {
+    const void* x;
+    const void* spec;
+    const void* bias;
+    void* y;
+    int64_t N;
+    int64_t x_stride;   // elements
+    int64_t y_stride;   // elements
+    int32_t p, q;
+    int32_t x_dtype, y_dtype, bias_dtype;
+    int32_t pad;
+};
+
+// Header of an encoded group plan (host and device copies are byte-identical).
+struct GroupPlanHeader {
+    uint32_t magic;       // 'BCLG'
+    int32_t count;        // problems
+    int32_t num_ctas;
+    int32_t num_segs;
+    int32_t B, spec_dtype, nt, qmax;
+    uint64_t off_problems, off_cta_ptr, off_segs, total_bytes;
+};
+constexpr uint32_t kPlanMagic = 0x474c4342u;
+
+cudaError_t launch_spectrum_stream(const float* c, void* spec, int p, int q, int B, int spec_dtype, cudaStream_t st);
+cudaError_t launch_stream_single(const ProblemDev& P, int B, int spec_dtype, cudaStream_t st);
+cudaError_t launch_stream_grouped(const GroupPlanHeader& H, const void* dev_plan, cudaStream_t st);
+size_t stream_smem_bytes(int B, int nt, int q, int warps);
+int stream_pick_nt(int64_t N, int q, int B);
+
+cudaError_t launch_project_from_dense(const void* W, int w_dtype, int64_t w_stride, int p, int q, int B, float* c, cudaStream_t st);
+
+}  // namespace bcl

