@@ -1,0 +1,344 @@
+#!/usr/bin/env python3
+"""bench.py -- the BC-linear hot path on B200, measured the way BASELINE.json quotes it.
+
+Workload (config.workload = "llama2-7b-decode-b128", BASELINE.json configs[1]): one decode step of batch 1 through
+ALL 7 block-circulant projections (q,k,v,o 4096->4096; gate,up 4096->11008; down 11008->4096; B=128) of ALL 32
+layers of a Llama-2-7B-shaped model: 224 BC linears, 224 distinct random-init weight spectra (207 MB fp32 -- larger
+than the 126 MB L2, and two such sets alternate between steps), synthetic fp16 activations.
+A step is ONE launch of the grouped stream kernel (bcl_forward_grouped) over those 224 independent problems.
+
+    value            tokens/s, whole job (N GPUs decode N independent streams: data parallel, "weak")
+    roofline         algorithmic bytes of a step / CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+    e2e              same step through the host-buffer entry point: pinned x -> H2D -> launch -> D2H -> sync
+    cpu_baseline     the reference's CPU torch.fft path (oracle port, spectra cached as in its perf runs) on this box
+
+--impl reference times that CPU path itself (rank 0 only), same metric/unit/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LLAMA7B_LAYER = [("q_proj", 4096, 4096), ("k_proj", 4096, 4096), ("v_proj", 4096, 4096), ("o_proj", 4096, 4096),
+                 ("gate_proj", 4096, 11008), ("up_proj", 4096, 11008), ("down_proj", 11008, 4096)]
+N_LAYERS = 32
+B = 128
+METRIC = "bc_linear_decode_tokens_per_s"
+UNIT = "tokens/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def config(n_gpus, spec_dtype="float32", weight_sets=2):
+    return {"workload": "llama2-7b-decode-b128", "projections_per_step": len(LLAMA7B_LAYER) * N_LAYERS, "layers": N_LAYERS,
+            "block_size": B, "tokens_per_step_per_gpu": 1, "activation_dtype": "float16", "spectrum_dtype": spec_dtype,
+            "weights": "random-init c = randn*0.01 (reference init), %d distinct sets alternating" % weight_sets,
+            "l2_policy": "inputs larger than L2 (%.0f MB of spectra per step, %d sets alternate)" % (
+                algorithmic_bytes(spec_dtype)[1] / 1e6, weight_sets),
+            "parallelism": "dp%d" % n_gpus}
+
+
+def algorithmic_bytes(spec_dtype="float32", n=1):
+    """N*in*s_x + p*q*B*s_w + N*out*s_y per projection; returns (total, spectrum part) per step."""
+    sw = 4 if spec_dtype == "float32" else 2
+    tot = spec = 0
+    for _, inf, outf in LLAMA7B_LAYER:
+        spec += inf * outf // B * sw
+        tot += n * inf * 2 + inf * outf // B * sw + n * outf * 2
+    return tot * N_LAYERS, spec * N_LAYERS
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([s.strip() for s in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for nme, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the reference's own CPU path (torch.fft.rfft -> einsum -> irfft), restated in
+# oracle/bc_oracle.py (bit-identical to the reference on the golden vectors), spectra cached like its perf runs.
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, layers):
+    import torch
+    from oracle import bc_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    mods = []
+    for _ in range(layers):
+        for _, inf, outf in LLAMA7B_LAYER:
+            c = torch.randn(outf // B, inf // B, B, generator=g) * 0.01
+            mods.append((O.CachedSpectrum(c), torch.randn(1, 1, inf, generator=g)))      # fp32 on CPU, the reference's CPU default
+    def one_step():
+        with torch.inference_mode():
+            for spec, x in mods:
+                O.bc_forward_cached_torch(spec, x)
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / steps
+    return dt * (N_LAYERS / layers), torch.get_num_threads()          # seconds per full 32-layer token
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sec, cores = cpu_reference_steps(args.steps, max(args.warmup, 1), N_LAYERS)
+    val = 1.0 / sec
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config(args.gpus, weight_sets=1),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "every step = all 224 projections (32 layers x 7), batch 1, fp32, cached rfft(c); "
+                                       "reference CPU path restated in oracle/bc_oracle.py (torch.fft + einsum)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "decode_us_per_layer": sec * 1e6 / N_LAYERS, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import llama_fft_b200 as bc
+    from llama_fft_b200 import _cabi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the BC-linear path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.lib()
+
+    sdt = torch.float32 if args.spectrum == "float32" else torch.bfloat16
+    shapes = [(outf // B, inf // B) for _ in range(N_LAYERS) for (_, inf, outf) in LLAMA7B_LAYER]
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    def make_set():
+        specs = []
+        for (p, q) in shapes:
+            c = torch.randn(p, q, B, device=dev, generator=g) * 0.01
+            spec = torch.empty(p, q, B, device=dev, dtype=sdt)
+            _cabi.check(_cabi.lib().bcl_precompute_spectrum(c.data_ptr(), p, q, B, spec.data_ptr(), _cabi.DTYPE[sdt],
+                                                            _cabi.LAYOUT_STREAM, _cabi.stream_ptr(dev)), "bcl_precompute_spectrum")
+            specs.append(spec)
+        grp = bc.GroupedBCForward.from_packed(shapes, specs, 1, torch.float16, dev, num_ctas=args.ctas_per_sm * torch.cuda.get_device_properties(dev).multi_processor_count)
+        grp.x_all.copy_(torch.randn(grp.x_all.numel(), device=dev, generator=g).to(torch.float16))
+        return grp
+
+    groups = [make_set() for _ in range(args.weight_sets)]
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K steps, one grouped launch each ---------------------------------------------------
+    for i in range(args.warmup):
+        groups[i % len(groups)].run()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record(stream)
+        for i in range(args.steps):
+            groups[i % len(groups)].run()
+        ev1.record(stream)
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    launches = args.steps
+
+    # ---- end to end through the host-buffer entry point ------------------------------------------------------------
+    hx = [torch.randn(grp.x_all.numel()).to(torch.float16).pin_memory() for grp in groups]
+    hy = [torch.empty(grp.y_all.numel(), dtype=torch.float16).pin_memory() for grp in groups]
+    for i in range(min(args.warmup, 5)):
+        groups[i % len(groups)].run_host(hx[i % len(groups)], hy[i % len(groups)])
+    barrier()
+    e2e_steps = max(10, min(args.steps, 200))
+    ev0.record(stream)
+    for i in range(e2e_steps):
+        k = i % len(groups)
+        groups[k].run_host(hx[k], hy[k])
+    ev1.record(stream)
+    barrier()
+    t2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = t2.item() / e2e_steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- extra evidence at N=1 (not part of the timed value): other launch granularities, bf16 spectra --------------
+    detail = {}
+    if world == 1 and not args.no_detail:
+        detail = launch_granularity_detail(bc, _cabi, groups[0], shapes, dev, args)
+
+    peak, peak_src = peaks()
+    alg, spec_bytes = algorithmic_bytes(args.spectrum)
+    achieved = alg / (ms_step * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("stream_grouped_kernel_%s" % args.spectrum)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sec, cores = cpu_reference_steps(3, 1, 8)
+        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "3 timed passes over 8 of the 32 layers (56 projections, distinct weights), batch 1, fp32, cached rfft(c); "
+                         "per-token time scaled x4; reference CPU path restated in oracle/bc_oracle.py"}
+    line = {"metric": METRIC, "value": world * 1.0 / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config(world, args.spectrum, args.weight_sets),
+            "decode_us_per_layer": ms_step * 1e3 / N_LAYERS,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "stream_grouped_kernel<128,1,%s,8>" % ("float" if args.spectrum == "float32" else "bf16"),
+                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "e2e": {"value": world * 1.0 / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": groups[0].x_all.numel() * 2, "d2h_bytes_per_step": groups[0].y_all.numel() * 2},
+            "gpu_launches": launches, "clocks": clk.summary(), "detail": detail}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def launch_granularity_detail(bc, _cabi, grp_all, shapes, dev, args):
+    """How the same 224 projections fare at the launch granularities a real decoder allows."""
+    import torch
+    out = {}
+    stream = torch.cuda.current_stream(dev)
+    specs, xs = grp_all.specs, grp_all.xs
+
+    def time_graph(fn, reps=20):
+        s = torch.cuda.Stream(dev)
+        with torch.cuda.stream(s):
+            fn()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=s):
+                fn()
+            for _ in range(3):
+                graph.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s)
+            for _ in range(reps):
+                graph.replay()
+            e1.record(s)
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    L = _cabi.lib()
+    per_layer = [bc.GroupedBCForward(xs[7 * l:7 * l + 7], specs[7 * l:7 * l + 7]) for l in range(N_LAYERS)]
+    out["per_layer_grouped_graph_ms_per_step"] = time_graph(lambda: [gl.run() for gl in per_layer])
+    out["per_layer_grouped_launches_per_step"] = N_LAYERS
+    ys = [torch.empty(1, p * B, device=dev, dtype=torch.float16) for (p, q) in shapes]
+
+    def per_module():
+        st = torch.cuda.current_stream(dev).cuda_stream
+        for x, s, y, (p, q) in zip(xs, specs, ys, shapes):
+            L.bcl_forward(x.data_ptr(), _cabi.F16, 1, q * B, s.data_ptr(), _cabi.DTYPE[s.dtype], _cabi.LAYOUT_STREAM, p, q, B,
+                          None, 0, y.data_ptr(), _cabi.F16, p * B, None, 0, st)
+    out["per_module_graph_ms_per_step"] = time_graph(per_module)
+    out["per_module_launches_per_step"] = len(shapes)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per_module(); torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(5):
+        per_module()
+    e1.record(stream); torch.cuda.synchronize()
+    out["per_module_eager_ms_per_step"] = e0.elapsed_time(e1) / 5
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--spectrum", default="float32", choices=["float32", "bfloat16"])
+    ap.add_argument("--weight-sets", type=int, default=2)
+    ap.add_argument("--ctas-per-sm", type=int, default=2)
+    ap.add_argument("--no-detail", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -118,6 +118,12 @@ int bcl_forward_host(const void* host_x, int x_dtype, int64_t N,
                      void* host_y, int y_dtype,
                      void* dev_x, void* dev_y, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Grouped variant: all problems' x live back to back in one staging area (and all y in another), so a step is one
+ * H2D copy, one launch, one D2H copy, one synchronise. */
+int bcl_forward_grouped_host(const void* dev_plan, const void* host_plan,
+                             const void* host_x, void* dev_x, size_t x_bytes,
+                             void* host_y, const void* dev_y, size_t y_bytes, void* stream);
+
 /* ---- construction: replaces the Python p*q*B loops of from_linear ------------------------------------------
  * reference: src/patch_llama_fft.py:201-219 + :110-128.  W is (p*B, q*B) row-major of dtype w_dtype;
  * c[j,i,t] = alpha * mean_r W[jB+r, iB+(r-t) mod B], alpha as :124-126, arithmetic rounded to w_dtype the way

@@ -19,7 +19,7 @@ DTYPE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 # every symbol include/bclinear.h declares (tests check the built library exports all of them)
 SYMBOLS = (
     "bcl_abi_version", "bcl_last_error", "bcl_spectrum_bytes", "bcl_precompute_spectrum", "bcl_workspace_bytes",
-    "bcl_forward", "bcl_group_plan_bytes", "bcl_group_plan_encode", "bcl_forward_grouped", "bcl_forward_host",
+    "bcl_forward", "bcl_group_plan_bytes", "bcl_group_plan_encode", "bcl_forward_grouped", "bcl_forward_host", "bcl_forward_grouped_host",
     "bcl_project_from_dense",
 )
 
@@ -65,6 +65,7 @@ def lib() -> ctypes.CDLL:
     L.bcl_group_plan_encode.argtypes = [ctypes.POINTER(Problem), i32, i32, i32, i32, vp, sz]
     L.bcl_forward_grouped.argtypes = [vp, vp, vp]
     L.bcl_forward_host.argtypes = [vp, i32, i64, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, vp, vp, sz, vp]
+    L.bcl_forward_grouped_host.argtypes = [vp, vp, vp, vp, sz, vp, vp, sz, vp]
     L.bcl_project_from_dense.argtypes = [vp, i32, i64, i32, i32, i32, vp, vp]
     for name in SYMBOLS:
         getattr(L, name)

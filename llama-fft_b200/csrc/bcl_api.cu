@@ -210,6 +210,20 @@ int bcl_forward_host(const void* host_x, int x_dtype, int64_t N,
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "stream synchronize");
 }
 
+int bcl_forward_grouped_host(const void* dev_plan, const void* host_plan, const void* host_x, void* dev_x, size_t x_bytes,
+                             void* host_y, const void* dev_y, size_t y_bytes, void* stream) {
+    if (!host_x || !dev_x || !host_y || !dev_y) return fail(BCL_ERR_ARG, "NULL host/device staging buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(dev_x, host_x, x_bytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "H2D copy of x");
+    int rc = bcl_forward_grouped(dev_plan, host_plan, stream);
+    if (rc != BCL_OK) return rc;
+    e = cudaMemcpyAsync(host_y, dev_y, y_bytes, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(e, "D2H copy of y");
+    e = cudaStreamSynchronize(st);
+    return e == cudaSuccess ? BCL_OK : cuda_fail(e, "stream synchronize");
+}
+
 int bcl_project_from_dense(const void* W, int w_dtype, int64_t w_row_stride, int p, int q, int B, float* c, void* stream) {
     if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
     if (p <= 0 || q <= 0) return fail(BCL_ERR_SHAPE, "bad shape p=%d q=%d", p, q);

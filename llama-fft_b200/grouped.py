@@ -19,7 +19,8 @@ class GroupedBCForward:
     Output buffers are allocated here and written in place by every ``run()``."""
 
     def __init__(self, xs: Sequence[torch.Tensor], specs: Sequence[torch.Tensor],
-                 biases: Optional[Sequence[Optional[torch.Tensor]]] = None, *, num_ctas: Optional[int] = None):
+                 biases: Optional[Sequence[Optional[torch.Tensor]]] = None, *, num_ctas: Optional[int] = None,
+                 _y_packed=None):
         assert len(xs) == len(specs) and len(xs) > 0
         biases = list(biases) if biases is not None else [None] * len(xs)
         dev = xs[0].device
@@ -29,6 +30,9 @@ class GroupedBCForward:
         self.device, self.B = dev, B
         self.xs, self.specs, self.biases = list(xs), list(specs), biases
         self.ys = []
+        self.y_all = None
+        if _y_packed is not None:
+            self.y_all = torch.empty(_y_packed[0], device=dev, dtype=xs[0].dtype)
         probs = (_cabi.Problem * len(xs))()
         for g, (x, s, b) in enumerate(zip(xs, specs, biases)):
             assert x.device == dev and s.device == dev and x.dim() == 2 and s.dim() == 3
@@ -37,7 +41,11 @@ class GroupedBCForward:
             if x.shape[1] != q * B:
                 raise ValueError("in_features mismatch")
             y_dtype = x.dtype if b is None else torch.promote_types(x.dtype, b.dtype)
-            y = torch.empty(x.shape[0], p * B, device=dev, dtype=y_dtype)
+            if self.y_all is not None:
+                o = _y_packed[1][g]
+                y = self.y_all[o:o + x.shape[0] * p * B].view(x.shape[0], p * B)
+            else:
+                y = torch.empty(x.shape[0], p * B, device=dev, dtype=y_dtype)
             self.ys.append(y)
             probs[g] = _cabi.Problem(x.data_ptr(), s.data_ptr(), None if b is None else b.data_ptr(), y.data_ptr(),
                                      x.shape[0], x.stride(0), y.stride(0), p, q,
@@ -56,6 +64,35 @@ class GroupedBCForward:
         self.algorithmic_bytes = sum(x.numel() * x.element_size() + s.numel() * s.element_size() + y.numel() * y.element_size()
                                      + (0 if b is None else b.numel() * b.element_size())
                                      for x, s, y, b in zip(self.xs, self.specs, self.ys, self.biases))
+
+    @classmethod
+    def from_packed(cls, shapes, specs, N, x_dtype, device, **kw):
+        """Problems whose x (and y) live back to back in ONE staging buffer each, so a host round trip is one copy
+        per direction (``run_host``).  shapes[g] = (p, q); returns the instance with .x_all / .y_all set."""
+        B = specs[0].shape[-1]
+        esz = torch.empty(0, dtype=x_dtype).element_size()
+        align = 16 // esz
+        x_off, y_off, xo, yo = [], [], 0, 0
+        for (p, q) in shapes:
+            x_off.append(xo); y_off.append(yo)
+            xo += -(-N * q * B // align) * align
+            yo += -(-N * p * B // align) * align
+        x_all = torch.zeros(xo, device=device, dtype=x_dtype)
+        xs = [x_all[o:o + N * q * B].view(N, q * B) for o, (p, q) in zip(x_off, shapes)]
+        self = cls(xs, specs, None, _y_packed=(yo, y_off), **kw)
+        self.x_all = x_all
+        return self
+
+    def run_host(self, host_x: torch.Tensor, host_y: torch.Tensor):
+        """End-to-end step with HOST buffers: H2D(x_all) -> one grouped launch -> D2H(y_all) -> synchronise."""
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().bcl_forward_grouped_host(
+                self.dev_plan.data_ptr(), self.host_plan.data_ptr(),
+                host_x.data_ptr(), self.x_all.data_ptr(), self.x_all.numel() * self.x_all.element_size(),
+                host_y.data_ptr(), self.y_all.data_ptr(), self.y_all.numel() * self.y_all.element_size(),
+                _cabi.stream_ptr(self.device))
+        _cabi.check(rc, "bcl_forward_grouped_host")
+        return host_y
 
     def run(self):
         with torch.cuda.device(self.device):
