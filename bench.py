@@ -329,7 +329,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spectrum", default="float32", choices=["float32", "bfloat16"])
     ap.add_argument("--weight-sets", type=int, default=2)
-    ap.add_argument("--ctas-per-sm", type=int, default=2)
+    ap.add_argument("--ctas-per-sm", type=int, default=1)
     ap.add_argument("--no-detail", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

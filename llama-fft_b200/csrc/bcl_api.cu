@@ -2,6 +2,7 @@
 // kernel launchers, group-plan encoding.  No allocation, no global mutable state (thread-local error text only).
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cstdarg>
 #include <vector>
 #include "bcl_common.cuh"
@@ -132,13 +133,16 @@ int bcl_group_plan_encode(const bcl_problem* problems, int count, int B, int spe
         total_w += (int64_t)P.p * P.q;
     }
     int nt = 1; while (nt < maxN) nt *= 2;
-    if (bcl::stream_smem_bytes(B, nt, qmax, 8) > 200 * 1024)
+    const char* force = getenv("BCL_GROUP_VARIANT");                 // "plain" | "ws": A/B switch for profiling only
+    int variant = bcl::stream_ws_supported(B, spec_dtype, nt, qmax) ? 1 : 0;
+    if (force && !strcmp(force, "plain")) variant = 0;
+    if (variant == 0 && bcl::stream_smem_bytes(B, nt, qmax, 8) > 200 * 1024)
         return fail(BCL_ERR_UNSUPPORTED, "x spectrum tile (N=%d, q=%d, B=%d) exceeds shared memory; call bcl_forward per problem", nt, qmax, B);
 
     unsigned char* base = reinterpret_cast<unsigned char*>(host_plan);
     memset(base, 0, need);
     bcl::GroupPlanHeader H{};
-    H.magic = bcl::kPlanMagic; H.count = count; H.num_ctas = num_ctas; H.B = B; H.spec_dtype = spec_dtype; H.nt = nt; H.qmax = qmax;
+    H.magic = bcl::kPlanMagic; H.count = count; H.num_ctas = num_ctas; H.B = B; H.spec_dtype = spec_dtype; H.nt = nt; H.qmax = qmax; H.variant = variant;
     size_t off = sizeof(bcl::GroupPlanHeader);
     off = (off + 15) & ~(size_t)15; H.off_problems = off; off += (size_t)count * sizeof(bcl::ProblemDev);
     off = (off + 15) & ~(size_t)15; H.off_cta_ptr = off; off += ((size_t)num_ctas + 1) * sizeof(int);
@@ -186,7 +190,8 @@ int bcl_forward_grouped(const void* dev_plan, const void* host_plan, void* strea
     memcpy(&H, host_plan, sizeof(H));
     if (H.magic != bcl::kPlanMagic) return fail(BCL_ERR_ARG, "host_plan was not written by bcl_group_plan_encode");
     if (!aligned(dev_plan, 16)) return fail(BCL_ERR_ALIGN, "dev_plan must be 16-byte aligned");
-    cudaError_t e = bcl::launch_stream_grouped(H, dev_plan, (cudaStream_t)stream);
+    cudaError_t e = H.variant == 1 ? bcl::launch_stream_ws(H, dev_plan, (cudaStream_t)stream)
+                                   : bcl::launch_stream_grouped(H, dev_plan, (cudaStream_t)stream);
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "grouped forward launch");
 }
 

@@ -111,15 +111,15 @@ __device__ inline void load_spec(const SpecT* p, float (&v)[CW]) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Twiddles: tw[k] = exp(-2 pi i k / B), k = 0 .. B/2-1, evaluated in double on the device once per CTA
-// (exact to fp32 round-off; no fast-math sincos on the hot path).
+// Twiddles: tw[k] = exp(-2 pi i k / B), k = 0 .. B/2-1, evaluated once per CTA with sincospif (the accurate libm
+// routine, not the __sincosf fast path; k/B is a dyadic rational so the argument is exact).
 // ---------------------------------------------------------------------------------------------------------
 template <int B>
 __device__ inline void fill_twiddles(float2* tw, int tid, int nthreads) {
     for (int k = tid; k < B / 2; k += nthreads) {
-        double s, c;
-        sincospi(-2.0 * (double)k / (double)B, &s, &c);
-        tw[k] = make_float2((float)c, (float)s);
+        float s, c;
+        sincospif(-2.0f * (float)k / (float)B, &s, &c);
+        tw[k] = make_float2(c, s);
     }
 }
 

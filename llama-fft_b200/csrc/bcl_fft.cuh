@@ -1,0 +1,199 @@
+// bcl_fft.cuh -- register-resident real FFT / inverse real FFT of length-B blocks (B = 64, 128, 256) for sm_100a.
+//
+// Restates rfft / irfft of the reference (src/patch_llama_fft.py:252,257,263): forward unnormalised with
+// e^{-2 pi i k t / B}; inverse = (1/B) * sum, Im(DC) and Im(Nyquist) ignored (they do not exist in the packing).
+//
+// Design: a length-B real transform is a length-M = B/2 complex transform of z[m] = x[2m] + i x[2m+1] plus a
+// pairwise (k, M-k) pass.  The complex transform is a two-level Cooley-Tukey M = V * T:
+//     T lanes cooperate on one block, each lane holds V points in registers
+//     level 1: radix-V FFT entirely in registers (compile-time twiddles), then a twiddle by w_M^{t k1}
+//     transpose through a padded, bank-conflict-free shared scratch
+//     level 2: radix-T FFTs in registers
+// so a warp transforms G = 32 / T blocks at once with 3-4 __syncwarp()s and ~5x fewer instructions than a
+// one-warp-per-block radix-2 shared-memory FFT.   (B, V, T, G): (64, 8, 4, 8), (128, 8, 8, 4), (256, 16, 8, 4).
+#pragma once
+#include "bcl_common.cuh"
+
+namespace bcl {
+
+template <int B> struct FftCfg {
+    static constexpr int M = B / 2;
+    static constexpr int V = (M == 128) ? 16 : 8;       // points per lane
+    static constexpr int T = M / V;                     // lanes per block
+    static constexpr int G = 32 / T;                    // blocks per warp pass
+    static constexpr int OPT = V / T;                   // level-2 FFTs per lane
+    static constexpr int PITCH = T + 1;                 // padded row pitch of the transpose (float2 elements)
+    // float2 elements of scratch per block; the stride is chosen so consecutive blocks start 16 banks apart
+    static constexpr int GROUP_F2 = (M == 128) ? (V * PITCH + 8) : (V * PITCH);
+    static constexpr int WARP_SCRATCH_BYTES = G * GROUP_F2 * 8;
+    static constexpr int NPAIR = (M / 2) / T + 1;       // (k, M-k) pairs per lane in the real pass
+};
+
+__host__ __device__ constexpr int brev_n(int k, int n) {            // bit reversal of k in log2(n) bits
+    int r = 0;
+    for (int b = 1; b < n; b <<= 1) { r = (r << 1) | (k & 1); k >>= 1; }
+    return r;
+}
+
+// exp(-2 pi i k / 16), k = 0..7 (compile-time: every use is in a fully unrolled loop)
+__device__ __forceinline__ constexpr float tw16_re(int k) {
+    constexpr float t[8] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f, 0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
+    return t[k];
+}
+__device__ __forceinline__ constexpr float tw16_im(int k) {
+    constexpr float t[8] = {0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f, -1.f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f};
+    return t[k];
+}
+
+// In-register radix-2 DIF FFT of N points (N = 4, 8, 16), fully unrolled.  Output a[brev_n(k, N)] = X[k].
+template <int N, bool INV>
+__device__ __forceinline__ void fft_reg(float2 (&a)[N]) {
+#pragma unroll
+    for (int half = N / 2; half >= 1; half >>= 1) {
+#pragma unroll
+        for (int b = 0; b < N / 2; ++b) {
+            const int pos = b % half;
+            const int i0 = (b / half) * 2 * half + pos, i1 = i0 + half;
+            const int k16 = pos * (8 / half);                       // w_{2 half}^{pos} = w_16^{k16}
+            const float2 u = a[i0], v = a[i1];
+            a[i0] = make_float2(u.x + v.x, u.y + v.y);
+            const float dx = u.x - v.x, dy = u.y - v.y;
+            if (k16 == 0) a[i1] = make_float2(dx, dy);
+            else if (k16 == 4) a[i1] = INV ? make_float2(-dy, dx) : make_float2(dy, -dx);        // * (-i)  /  * (+i)
+            else {
+                const float wr = tw16_re(k16), wi = INV ? -tw16_im(k16) : tw16_im(k16);
+                a[i1] = make_float2(dx * wr - dy * wi, dx * wi + dy * wr);
+            }
+        }
+    }
+}
+
+// w_M^e = exp(-2 pi i e / M) for 0 <= e < M from the table tw[k] = exp(-2 pi i k / B), k < M  (w_M = w_B^2)
+template <int B>
+__device__ __forceinline__ float2 twiddle_m(const float2* tw, int e) {
+    constexpr int M = B / 2;
+    const int k = 2 * e;
+    float2 w = tw[k & (M - 1)];
+    if (k & M) { w.x = -w.x; w.y = -w.y; }
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Forward.  Lane t (0..T-1) of a block's group passes a[n1] = z[T*n1 + t] = (x[2(T n1 + t)], x[2(T n1 + t)+1]).
+// Writes the packed half-spectrum {Re X0, Re X_{B/2}, Re X1, Im X1, ...} to dst[0..B) (shared, linear) if active.
+// scr: this block's scratch (GROUP_F2 float2).  All 32 lanes must call (warp-level syncs inside).
+// ---------------------------------------------------------------------------------------------------------
+template <int B>
+__device__ __forceinline__ void group_rfft_packed(float2 (&a)[FftCfg<B>::V], float2* scr, float* dst, const float2* tw, int t, bool active) {
+    using C = FftCfg<B>;
+    constexpr int M = C::M, V = C::V, T = C::T, OPT = C::OPT, PITCH = C::PITCH;
+    fft_reg<V, false>(a);
+#pragma unroll
+    for (int k1 = 0; k1 < V; ++k1) {
+        float2 A = a[brev_n(k1, V)];
+        if (k1 > 0) A = cmul(A, twiddle_m<B>(tw, t * k1));
+        scr[k1 * PITCH + t] = A;
+    }
+    __syncwarp();
+    float2 zo[OPT][T];
+#pragma unroll
+    for (int j = 0; j < OPT; ++j) {
+        const int k1 = t * OPT + j;
+#pragma unroll
+        for (int n2 = 0; n2 < T; ++n2) zo[j][n2] = scr[k1 * PITCH + n2];
+        fft_reg<T, false>(zo[j]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < OPT; ++j) {
+        const int k1 = t * OPT + j;
+#pragma unroll
+        for (int k2 = 0; k2 < T; ++k2) scr[k1 + V * k2] = zo[j][brev_n(k2, T)];          // Z[k1 + V k2], natural order
+    }
+    __syncwarp();
+    // real pass: X[k] = (Zk + conj(Zm))/2 - (i/2) w^k (Zk - conj(Zm)),  X[M-k] = conj((Zk + conj(Zm))/2 + (i/2) w^k (Zk - conj(Zm)))
+#pragma unroll
+    for (int it = 0; it < C::NPAIR; ++it) {
+        const int k = t + T * it;
+        if (k <= M / 2 && active) {
+            const float2 zk = scr[k], zm = scr[(M - k) & (M - 1)];
+            if (k == 0) {
+                *reinterpret_cast<float2*>(dst) = make_float2(zk.x + zk.y, zk.x - zk.y);     // (DC, Nyquist)
+            } else {
+                const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                const float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
+                const float2 wd = cmul(tw[k], d);
+                *reinterpret_cast<float2*>(dst + 2 * k) = make_float2(e.x + wd.y, e.y - wd.x);
+                if (k != M - k) *reinterpret_cast<float2*>(dst + 2 * (M - k)) = make_float2(e.x - wd.y, -(e.y + wd.x));
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Inverse.  src[0..B): packed half-spectrum (shared, linear).  Returns, UNSCALED (caller multiplies by 1/B), for
+// j < OPT, k2 < T:   out[j*T + k2] = ( y[2m], y[2m+1] )  with  m = (t*OPT + j) + V*k2.
+// ---------------------------------------------------------------------------------------------------------
+template <int B>
+__device__ __forceinline__ void group_irfft_packed(const float* src, float2* scr, const float2* tw, int t, float2 (&out)[FftCfg<B>::V]) {
+    using C = FftCfg<B>;
+    constexpr int M = C::M, V = C::V, T = C::T, OPT = C::OPT, PITCH = C::PITCH;
+    // E = Xk + conj(Xm);  O = conj(w^k) (Xk - conj(Xm));  Z[k] = E + i O;  Z[M-k] = conj(E) + i conj(O)
+#pragma unroll
+    for (int it = 0; it < C::NPAIR; ++it) {
+        const int k = t + T * it;
+        if (k <= M / 2) {
+            float2 xk, xm;
+            if (k == 0) { const float2 p = *reinterpret_cast<const float2*>(src); xk = make_float2(p.x, 0.f); xm = make_float2(p.y, 0.f); }
+            else { xk = *reinterpret_cast<const float2*>(src + 2 * k); xm = *reinterpret_cast<const float2*>(src + 2 * (M - k)); }
+            const float2 e = make_float2(xk.x + xm.x, xk.y - xm.y);
+            const float2 d = make_float2(xk.x - xm.x, xk.y + xm.y);
+            const float2 o = cmulc(d, tw[k]);
+            scr[k] = make_float2(e.x - o.y, e.y + o.x);
+            if (k != 0 && k != M - k) scr[M - k] = make_float2(e.x + o.y, -e.y + o.x);
+        }
+    }
+    __syncwarp();
+    float2 a[V];
+#pragma unroll
+    for (int n1 = 0; n1 < V; ++n1) a[n1] = scr[T * n1 + t];
+    fft_reg<V, true>(a);
+    __syncwarp();
+#pragma unroll
+    for (int k1 = 0; k1 < V; ++k1) {
+        float2 A = a[brev_n(k1, V)];
+        if (k1 > 0) A = cmulc(A, twiddle_m<B>(tw, t * k1));
+        scr[k1 * PITCH + t] = A;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < OPT; ++j) {
+        const int k1 = t * OPT + j;
+        float2 b[T];
+#pragma unroll
+        for (int n2 = 0; n2 < T; ++n2) b[n2] = scr[k1 * PITCH + n2];
+        fft_reg<T, true>(b);
+#pragma unroll
+        for (int k2 = 0; k2 < T; ++k2) out[j * T + k2] = b[brev_n(k2, T)];
+    }
+    __syncwarp();
+}
+
+// time-domain element pair (2m, 2m+1) -> activation dtype helpers -------------------------------------------------
+__device__ __forceinline__ float2 load_act2(const void* base, int64_t elem_off, int dt) {
+    if (dt == BCL_F32) return *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(base) + elem_off);
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(base) + elem_off);
+    if (dt == BCL_F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+
+__device__ __forceinline__ void store_act2(void* base, int64_t elem_off, int dt, float2 v) {
+    if (dt == BCL_F32) { *reinterpret_cast<float2*>(reinterpret_cast<float*>(base) + elem_off) = v; return; }
+    uint32_t w;
+    if (dt == BCL_F16) { __half2 h = __floats2half2_rn(v.x, v.y); w = *reinterpret_cast<uint32_t*>(&h); }
+    else { __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y); w = *reinterpret_cast<uint32_t*>(&h); }
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(base) + elem_off) = w;
+}
+
+}  // namespace bcl

@@ -27,6 +27,8 @@ struct GroupPlanHeader {
     int32_t num_ctas;
     int32_t num_segs;
     int32_t B, spec_dtype, nt, qmax;
+    int32_t variant;      // 0 = plain CTA-cooperative kernel, 1 = warp-specialised TMA pipeline (one CTA per SM)
+    int32_t reserved;
     uint64_t off_problems, off_cta_ptr, off_segs, total_bytes;
 };
 constexpr uint32_t kPlanMagic = 0x474c4342u;
@@ -34,6 +36,8 @@ constexpr uint32_t kPlanMagic = 0x474c4342u;
 cudaError_t launch_spectrum_stream(const float* c, void* spec, int p, int q, int B, int spec_dtype, cudaStream_t st);
 cudaError_t launch_stream_single(const ProblemDev& P, int B, int spec_dtype, cudaStream_t st);
 cudaError_t launch_stream_grouped(const GroupPlanHeader& H, const void* dev_plan, cudaStream_t st);
+bool stream_ws_supported(int B, int spec_dtype, int nt, int qmax);
+cudaError_t launch_stream_ws(const GroupPlanHeader& H, const void* dev_plan, cudaStream_t st);
 size_t stream_smem_bytes(int B, int nt, int q, int warps);
 int stream_pick_nt(int64_t N, int q, int B);
 

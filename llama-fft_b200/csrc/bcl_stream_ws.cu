@@ -1,0 +1,346 @@
+// bcl_stream_ws.cu -- warp-specialised grouped stream kernel (the decode hot path on B200).
+//
+// One persistent CTA per SM walks its byte-balanced list of segments (problem, output block-rows [j0,j1)).  In the
+// STREAM layout the spectrum of a segment is ONE contiguous byte range, so the CTA's whole HBM stream is a sequence
+// of fixed-size chunks:
+//
+//   warp 0            TMA producer: cp.async.bulk (global -> shared, mbarrier complete_tx) of chunk after chunk into a
+//                     ring of S stages; runs ahead across segment boundaries, so HBM stays busy while the other warps
+//                     transform the next segment's x or finish rows.
+//   warps 1..NM       MAC warps: block k of the segment (row k/q, input block k%q) belongs to warp k mod NM; lane l
+//                     multiplies its packed reals of C_f[row,i] (from the ring) with X_f[i] (shared) into a per-row
+//                     partial spectrum in registers; when its row index advances it parks the partial in a
+//                     double-buffered group buffer and signals the finishers.  Before each segment the MAC warps
+//                     compute rfft(x) of the segment's problem into shared memory.
+//   warps NM+1..+NF   finishers: wait for a group of RG rows, sum the NM partials, inverse real FFT, 1/B scale,
+//                     round to x.dtype, + bias, store y (reference epilogue src/patch_llama_fft.py:263-271).
+//
+// All hand-offs are mbarriers (full/empty per ring stage, gfull/gempty per group buffer); the only block-wide
+// barrier is the one after setup.  Replaces steps 2-9 of the reference forward for up to hundreds of independent
+// projections per launch.
+#include <cstdlib>
+#include <cstdio>
+#include "bcl_stream_parts.cuh"
+
+namespace bcl {
+namespace ws {
+
+#ifndef BCL_WS_NM
+#define BCL_WS_NM 8
+#endif
+#ifndef BCL_WS_NF
+#define BCL_WS_NF 2
+#endif
+#ifndef BCL_WS_STAGE_KB
+#define BCL_WS_STAGE_KB 16
+#endif
+constexpr int NM = BCL_WS_NM;                // MAC warps
+constexpr int NF = BCL_WS_NF;                // finisher warps
+#ifndef BCL_WS_NX
+#define BCL_WS_NX 4
+#endif
+constexpr int NX = BCL_WS_NX;                // x-spectrum warps
+constexpr int THREADS = 32 * (1 + NM + NX + NF);
+constexpr int MAX_STAGES = 16;
+constexpr int PAIRS = 4;                     // rows per group buffer (one finisher warp inverse-transforms up to G = 32/T rows at once)
+// blocks per ring stage: 32 blocks of B=128 (16 KB fp32), 16 of B=256, 64 of B=64 -- always BPS = CB/NM blocks per MAC warp
+__host__ __device__ constexpr int stage_blocks(int B) { return 4096 / B; }
+
+__device__ inline uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ inline void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); }
+__device__ inline void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
+__device__ inline void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ inline bool mbar_try(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ inline void mbar_wait(uint64_t* b, uint32_t parity) {
+    const uint32_t addr = smem_u32(b);
+    if (mbar_try(addr, parity)) return;
+    while (!mbar_try(addr, parity)) __nanosleep(32);                // back off: waiting warps must not eat the issue slots of working ones
+}
+__device__ inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+#ifdef BCL_WS_TIMING
+__device__ inline long long clk() { long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c)); return c; }
+#define TSTART(v) long long v##_t0 = clk()
+#define TSTOP(v, acc) acc += clk() - v##_t0
+#define TPRINT(...) printf(__VA_ARGS__)
+#else
+__device__ inline long long clk() { return 0; }
+#define TSTART(v)
+#define TSTOP(v, acc)
+#define TPRINT(...)
+#endif
+
+struct Barriers {
+    uint64_t full[MAX_STAGES];      // ring stage filled by TMA            (1 arrival + tx bytes)
+    uint64_t empty[MAX_STAGES];     // ring stage released by the MAC warps (NM arrivals)
+    uint64_t gfull[2];              // group buffer complete                (NM arrivals)
+    uint64_t gempty[2];             // group buffer drained by a finisher   (1 arrival)
+    uint64_t xfull[2];              // x spectrum of a segment ready in shared memory     (NX arrivals; slot 0 used)
+    uint64_t xempty[2];             // every MAC warp copied its slice into registers      (NM arrivals)
+};
+
+// RS = ring stages per block-row = ceil(qmax / CB): compile-time so that each MAC warp's slice of the x spectrum
+// (RS * BPS blocks) can live in registers and the per-stage multiply is straight-line code.
+template <int B, typename SpecT, int RS>
+__global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev* __restrict__ problems, const int* __restrict__ cta_seg_ptr,
+                                                              const SegWork* __restrict__ segs, int S, int qmax, int dbg) {
+    using LM = LaneMap<B>;
+    using FC = FftCfg<B>;
+    constexpr int NT = 1;
+    constexpr int CH = LM::CH, CW = LM::CW;
+    constexpr int RG = PAIRS;                                        // rows per group buffer
+    constexpr int BLOCK_BYTES = B * (int)sizeof(SpecT);
+    constexpr int CB = stage_blocks(B);                              // blocks per ring stage
+    constexpr int BPS = CB / NM;                                     // blocks per MAC warp per stage
+    constexpr int STAGE_BYTES = CB * BLOCK_BYTES;
+    constexpr int NW = CW * (int)sizeof(SpecT) / 4;                  // 32-bit words per lane chunk of a spectrum block
+    static_assert(CB % NM == 0, "stage must split evenly over the MAC warps");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Barriers* bars = reinterpret_cast<Barriers*>(smem_raw);
+    float2* tw = reinterpret_cast<float2*>(smem_raw + 512);
+    unsigned char* ring = smem_raw + 512 + 1024;                     // tw needs B/2*8 <= 1024 bytes
+    float* part = reinterpret_cast<float*>(ring + (size_t)S * STAGE_BYTES);                         // [2][PAIRS][NM][B]
+    float2* fscr_all = reinterpret_cast<float2*>(part + 2 * PAIRS * NM * B);                        // FFT scratch of the NX + NF warps
+    float* xs = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(fscr_all) + (size_t)(NX + NF) * FC::WARP_SCRATCH_BYTES);   // [qmax][B]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], NM); }
+        for (int g = 0; g < 2; ++g) { mbar_init(&bars->gfull[g], NM); mbar_init(&bars->gempty[g], 1); }
+        mbar_init(&bars->xfull[0], NX); mbar_init(&bars->xempty[0], NM);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fill_twiddles<B>(tw, threadIdx.x, THREADS);
+    __syncthreads();
+
+    const int s0 = cta_seg_ptr[blockIdx.x], s1 = cta_seg_ptr[blockIdx.x + 1];
+    long long t_a = 0, t_b = 0, t_c = 0;
+    const long long t_all0 = clk();
+    (void)t_a; (void)t_b; (void)t_c; (void)t_all0; (void)dbg; (void)qmax;
+
+    if (warp == 0) {
+        // ===================== TMA producer: one bulk copy per (row, stage-of-row) =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0; int n = 0;
+            for (int s = s0; s < s1; ++s) {
+                const SegWork w = segs[s];
+                const ProblemDev* P = problems + w.g;
+                const int q = P->q;
+                const unsigned char* rowp = reinterpret_cast<const unsigned char*>(P->spec) + (size_t)w.j0 * q * BLOCK_BYTES;
+                for (int r = w.j0; r < w.j1; ++r, rowp += (size_t)q * BLOCK_BYTES) {
+#pragma unroll
+                    for (int cs = 0; cs < RS; ++cs) {
+                        if (cs * CB < q) {
+                            { TSTART(w); mbar_wait(&bars->empty[stage], ph ^ 1u); TSTOP(w, t_a); }
+                            const uint32_t bytes = (uint32_t)min(CB, q - cs * CB) * BLOCK_BYTES;
+                            mbar_arrive_expect_tx(&bars->full[stage], bytes);
+                            bulk_g2s(ring + (size_t)stage * STAGE_BYTES, rowp + (size_t)cs * STAGE_BYTES, bytes, &bars->full[stage]);
+                            if (++stage == S) { stage = 0; ph ^= 1u; }
+                            ++n;
+                        }
+                    }
+                }
+            }
+            if (blockIdx.x == 3) TPRINT("producer: total %lld wait_empty %lld chunks %d\n", clk() - t_all0, t_a, n);
+        }
+    } else if (warp <= NM) {
+        // ===================== MAC warps =====================
+        const int m = warp - 1;
+        int stage = 0; uint32_t ph = 0;
+        int gi = 0;
+        RowAcc<B, NT> acc;
+        for (int s = s0; s < s1; ++s) {
+            const SegWork w = segs[s];
+            const int q = problems[w.g].q;
+            const int rows = w.j1 - w.j0;
+            // my slice of this segment's x spectrum -> registers (blocks i = cs*CB + m + NM*u), then free the X buffer at once
+            float xr[RS][BPS][CH][CW];
+            { TSTART(x); mbar_wait(&bars->xfull[0], (uint32_t)(s - s0) & 1u); TSTOP(x, t_a); }
+#pragma unroll
+            for (int cs = 0; cs < RS; ++cs)
+#pragma unroll
+                for (int u = 0; u < BPS; ++u) {
+                    const int i = cs * CB + m + NM * u;
+#pragma unroll
+                    for (int ch = 0; ch < CH; ++ch) {
+                        if (i < q) {
+                            const float* xp = xs + (size_t)i * B + LM::offset(lane, ch);
+                            if constexpr (CW == 4) { float4 t = *reinterpret_cast<const float4*>(xp); xr[cs][u][ch][0] = t.x; xr[cs][u][ch][1] = t.y; xr[cs][u][ch][2] = t.z; xr[cs][u][ch][3] = t.w; }
+                            else { float2 t = *reinterpret_cast<const float2*>(xp); xr[cs][u][ch][0] = t.x; xr[cs][u][ch][1] = t.y; }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < CW; ++e) xr[cs][u][ch][e] = 0.f;
+                        }
+                    }
+                }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->xempty[0]);
+            for (int r = 0; r < rows; ++r) {
+                acc.clear();
+#pragma unroll
+                for (int cs = 0; cs < RS; ++cs) {
+                    if (cs * CB < q) {
+                        { TSTART(f); mbar_wait(&bars->full[stage], ph); TSTOP(f, t_b); }
+                        const SpecT* cbuf = reinterpret_cast<const SpecT*>(ring + (size_t)stage * STAGE_BYTES) + (size_t)m * B;
+                        RawChunk<SpecT, CW> raw[BPS][CH];
+#pragma unroll
+                        for (int u = 0; u < BPS; ++u) {               // all shared loads first: one latency, no branches
+                            if (cs * CB + m + NM * u < q) {
+#pragma unroll
+                                for (int ch = 0; ch < CH; ++ch) {
+                                    const uint32_t* src = reinterpret_cast<const uint32_t*>(cbuf + (size_t)(NM * u) * B + LM::offset(lane, ch));
+                                    if constexpr (NW == 4) { uint4 t = *reinterpret_cast<const uint4*>(src); raw[u][ch].w[0] = t.x; raw[u][ch].w[1] = t.y; raw[u][ch].w[2] = t.z; raw[u][ch].w[3] = t.w; }
+                                    else if constexpr (NW == 2) { uint2 t = *reinterpret_cast<const uint2*>(src); raw[u][ch].w[0] = t.x; raw[u][ch].w[1] = t.y; }
+                                    else { raw[u][ch].w[0] = *src; }
+                                }
+                            } else {
+#pragma unroll
+                                for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+                                    for (int e = 0; e < NW; ++e) raw[u][ch].w[e] = 0u;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < BPS; ++u) {
+#pragma unroll
+                            for (int ch = 0; ch < CH; ++ch) {
+                                float cv[CW];
+                                decode_raw<SpecT, CW>(raw[u][ch], cv);
+#pragma unroll
+                                for (int e = 0; e < CW; e += 2) {
+                                    const float cr = cv[e], ci = cv[e + 1], xre = xr[cs][u][ch][e], xim = xr[cs][u][ch][e + 1];
+                                    acc.a[0][ch][e] = fmaf(cr, xre, acc.a[0][ch][e]);
+                                    acc.a[0][ch][e] = fmaf(-ci, xim, acc.a[0][ch][e]);
+                                    acc.a[0][ch][e + 1] = fmaf(cr, xim, acc.a[0][ch][e + 1]);
+                                    acc.a[0][ch][e + 1] = fmaf(ci, xre, acc.a[0][ch][e + 1]);
+                                    if (ch == 0 && e == 0) {         // packed slot 0/1 of lane 0 is (DC, Nyquist)
+                                        acc.dc[0] = fmaf(cr, xre, acc.dc[0]);
+                                        acc.ny[0] = fmaf(ci, xim, acc.ny[0]);
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->empty[stage]);   // this warp no longer reads the stage
+                        if (++stage == S) { stage = 0; ph ^= 1u; }
+                    }
+                }
+                // park the row's partial spectrum in the group buffer; the last row of a group signals the finisher
+                const int slot = r % RG;
+                const int gb = gi & 1;
+                if (slot == 0) { TSTART(g); mbar_wait(&bars->gempty[gb], ((uint32_t)(gi >> 1) & 1u) ^ 1u); TSTOP(g, t_c); }
+                store_partial<B, NT, NM>(acc, part + (size_t)gb * PAIRS * NM * B, slot, m, lane);
+                if (slot == RG - 1 || r == rows - 1) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->gfull[gb]);
+                    ++gi;
+                }
+            }
+        }
+        if (blockIdx.x == 3 && lane == 0 && (m == 0 || m == NM - 1))
+            TPRINT("mac %d: total %lld wait_x %lld wait_full %lld wait_gempty %lld segs %d\n", m, clk() - t_all0, t_a, t_b, t_c, s1 - s0);
+    } else if (warp <= NM + NX) {
+        // ===================== X warps: rfft(x) of each segment into the X buffer, one segment ahead of the MAC warps ======
+        const int xw = warp - 1 - NM;
+        float2* fscr = fscr_all + (size_t)xw * (FC::WARP_SCRATCH_BYTES / 8);
+        for (int s = s0; s < s1; ++s) {
+            const ProblemDev P = problems[segs[s].g];
+            { TSTART(x); mbar_wait(&bars->xempty[0], ((uint32_t)(s - s0) & 1u) ^ 1u); TSTOP(x, t_a); }   // MAC warps copied the previous X out
+            { TSTART(y); load_x_spectrum<B, NT, NX>(P, 0, xs, tw, fscr, lane, xw); TSTOP(y, t_b); }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->xfull[0]);
+        }
+        if (blockIdx.x == 3 && lane == 0) TPRINT("xw %d: total %lld wait_xempty %lld fft %lld\n", xw, clk() - t_all0, t_a, t_b);
+    } else {
+        // ===================== finishers: one warp per group, alternating =====================
+        const int f = warp - 1 - NM - NX;
+        float2* fscr = fscr_all + (size_t)(NX + f) * (FC::WARP_SCRATCH_BYTES / 8);
+        int gi = 0;
+        for (int s = s0; s < s1; ++s) {
+            const SegWork w = segs[s];
+            const ProblemDev P = problems[w.g];
+            const int rows = w.j1 - w.j0;
+            for (int g0 = 0; g0 < rows; g0 += RG, ++gi) {
+                if (gi % NF != f) continue;
+                const int gb = gi & 1;
+                { TSTART(g); mbar_wait(&bars->gfull[gb], (uint32_t)(gi >> 1) & 1u); TSTOP(g, t_a); }
+                const int nr = min(RG, rows - g0);
+                TSTART(fin);
+                float* gpart = part + (size_t)gb * PAIRS * NM * B;
+                for (int p0 = 0; p0 < nr; p0 += FC::G)
+                    finish_pairs<B, NT, NM>(P, w.j0 + g0, 0, gpart + (size_t)p0 * NM * B, p0, min(FC::G, nr - p0), tw, fscr, lane);
+                TSTOP(fin, t_b);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->gempty[gb]);
+            }
+        }
+        if (blockIdx.x == 3 && lane == 0) TPRINT("fin %d: total %lld wait_gfull %lld finish %lld groups %d\n", f, clk() - t_all0, t_a, t_b, gi);
+    }
+}
+
+size_t smem_bytes(int B, int spec_bytes, int qmax, int S) {
+    const size_t fscr = B == 64 ? FftCfg<64>::WARP_SCRATCH_BYTES : (B == 128 ? FftCfg<128>::WARP_SCRATCH_BYTES : FftCfg<256>::WARP_SCRATCH_BYTES);
+    const size_t stage = (size_t)stage_blocks(B) * B * spec_bytes;
+    return 512 + 1024 + (size_t)S * stage + (size_t)2 * PAIRS * NM * B * 4 + (size_t)(NX + NF) * fscr + (size_t)qmax * B * 4;
+}
+
+// Number of ring stages that fit next to the fixed buffers (0 = this shape does not fit the warp-specialised kernel).
+int pick_stages(int B, int spec_dtype, int nt, int qmax) {
+    if (nt != 1) return 0;                                           // decode path: one token per problem
+    if (qmax > 4 * stage_blocks(B)) return 0;                        // x slice must fit the MAC warps' registers (RS <= 4)
+    const int sb = spec_dtype == BCL_F32 ? 4 : 2;
+    const size_t budget = 227 * 1024;
+    const size_t fixed = smem_bytes(B, sb, qmax, 0);
+    const size_t stage = (size_t)stage_blocks(B) * B * sb;
+    if (fixed + 3 * stage > budget) return 0;
+    int S = (int)((budget - fixed) / stage);
+    if (S > MAX_STAGES) S = MAX_STAGES;
+    return S;
+}
+
+template <int B, typename SpecT, int RS>
+static cudaError_t launch_t(const GroupPlanHeader& H, const unsigned char* d, cudaStream_t st) {
+    auto kern = stream_ws_kernel<B, SpecT, RS>;
+    const int S = pick_stages(B, H.spec_dtype, H.nt, H.qmax);
+    const size_t smem = smem_bytes(B, (int)sizeof(SpecT), H.qmax, S);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)H.num_ctas, THREADS, smem, st>>>(reinterpret_cast<const ProblemDev*>(d + H.off_problems), reinterpret_cast<const int*>(d + H.off_cta_ptr),
+                                                     reinterpret_cast<const SegWork*>(d + H.off_segs), S, H.qmax, 0);
+    return cudaGetLastError();
+}
+
+template <int B, typename SpecT>
+static cudaError_t launch_b(const GroupPlanHeader& H, const unsigned char* d, cudaStream_t st) {
+    const int rs = (H.qmax + stage_blocks(B) - 1) / stage_blocks(B);
+    switch (rs) {
+        case 1: return launch_t<B, SpecT, 1>(H, d, st);
+        case 2: return launch_t<B, SpecT, 2>(H, d, st);
+        case 3: return launch_t<B, SpecT, 3>(H, d, st);
+        default: return launch_t<B, SpecT, 4>(H, d, st);
+    }
+}
+
+}  // namespace ws
+
+bool stream_ws_supported(int B, int spec_dtype, int nt, int qmax) { return ws::pick_stages(B, spec_dtype, nt, qmax) >= 3; }
+
+cudaError_t launch_stream_ws(const GroupPlanHeader& H, const void* dev_plan, cudaStream_t st) {
+    const unsigned char* d = reinterpret_cast<const unsigned char*>(dev_plan);
+#define BCL_WS(BB) (H.spec_dtype == BCL_F32 ? ws::launch_b<BB, float>(H, d, st) : ws::launch_b<BB, __nv_bfloat16>(H, d, st))
+    switch (H.B) { case 64: return BCL_WS(64); case 128: return BCL_WS(128); default: return BCL_WS(256); }
+#undef BCL_WS
+}
+
+}  // namespace bcl

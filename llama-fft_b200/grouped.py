@@ -53,7 +53,7 @@ class GroupedBCForward:
         L = _cabi.lib()
         if num_ctas is None:
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            num_ctas = 2 * sms
+            num_ctas = sms           # the warp-specialised kernel runs one persistent CTA per SM
         self.num_ctas = int(num_ctas)
         nbytes = L.bcl_group_plan_bytes(len(xs), self.num_ctas)
         self.host_plan = torch.empty(nbytes, dtype=torch.uint8).pin_memory()

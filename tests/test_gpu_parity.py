@@ -248,7 +248,8 @@ def test_grouped_launch_equals_per_module_calls():
     torch.cuda.synchronize()
     with torch.no_grad():
         for m, x, y in zip(layers, xs, ys):
-            assert torch.equal(m(x), y)                                  # same arithmetic, same order
+            assert_close(y, m(x), 1e-5, torch.float16)                   # same math, different partial-sum order
+            assert_close(y, O.bc_forward_torch(m.c.detach().cpu(), x.cpu()), 1e-4, torch.float16)
     # with N = 3 tokens, a bias, and bf16 spectra
     layers = [make_layer(torch.randn(4, 6, 64, generator=g), torch.randn(256, generator=g), torch.bfloat16) for _ in range(5)]
     xs = [torch.randn(3, 384, generator=g).to(DEV) for _ in layers]
@@ -256,7 +257,8 @@ def test_grouped_launch_equals_per_module_calls():
     ys = grp.run()
     with torch.no_grad():
         for m, x, y in zip(layers, xs, ys):
-            assert torch.equal(m(x), y)
+            assert_close(y, m(x), 1e-5, torch.float32)
+            assert_close(y, O.bc_forward_torch(m.c.detach().cpu(), x.cpu(), m.bias.detach().cpu()), 1e-2, torch.float32)
 
 
 def test_host_buffer_entry_point():

@@ -65,10 +65,11 @@ def _encode(shapes, B, num_ctas, N=1):
 def _decode(blob):
     hdr = np.frombuffer(blob[:64], dtype=np.uint8)
     magic, count, num_ctas, num_segs, B, sdt, nt, qmax = np.frombuffer(hdr[:32].tobytes(), dtype=np.int32)
-    off_p, off_c, off_s, total = np.frombuffer(hdr[32:64].tobytes(), dtype=np.uint64)
+    variant = int(np.frombuffer(blob[32:36], dtype=np.int32)[0])
+    off_p, off_c, off_s, total = np.frombuffer(blob[40:72], dtype=np.uint64)
     cta_ptr = np.frombuffer(blob[int(off_c):int(off_c) + 4 * (num_ctas + 1)], dtype=np.int32)
     segs = np.frombuffer(blob[int(off_s):int(off_s) + 16 * num_segs], dtype=np.int32).reshape(-1, 4)
-    return dict(count=count, num_ctas=num_ctas, num_segs=num_segs, nt=nt, qmax=qmax), cta_ptr, segs
+    return dict(count=count, num_ctas=num_ctas, num_segs=num_segs, nt=nt, qmax=qmax, variant=variant), cta_ptr, segs
 
 
 def test_group_plan_covers_every_row_once_and_balances_bytes():
@@ -78,7 +79,7 @@ def test_group_plan_covers_every_row_once_and_balances_bytes():
     rc, blob = _encode(shapes, 128, 296)
     assert rc == 0
     H, cta_ptr, segs = _decode(blob)
-    assert H["count"] == len(shapes) and H["qmax"] == 86 and H["nt"] == 1
+    assert H["count"] == len(shapes) and H["qmax"] == 86 and H["nt"] == 1 and H["variant"] == 1
     assert cta_ptr[0] == 0 and cta_ptr[-1] == H["num_segs"] and np.all(np.diff(cta_ptr) >= 0)
     seen = {g: np.zeros(p, dtype=int) for g, (p, q) in enumerate(shapes)}
     for g, j0, j1, _ in segs:
