@@ -2,10 +2,7 @@
 //
 // * dtype-generic vector loads/stores for activations (fp32 / fp16 / bf16)
 // * the packed half-spectrum convention (DESIGN.md "Data layout")
-// * warp-level real FFT / inverse real FFT of one length-B block through a per-warp shared-memory scratch
-//
-// Math being restated: rfft / irfft of the reference (src/patch_llama_fft.py:252,257,263): forward unnormalised
-// with e^{-2 pi i k t / B}, inverse scaled by 1/B and ignoring Im(DC), Im(Nyquist).
+// * twiddle table and complex helpers (the FFT itself is in bcl_fft.cuh)
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -125,105 +122,5 @@ __device__ inline void fill_twiddles(float2* tw, int tid, int nthreads) {
 
 __device__ inline float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ inline float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a * conj(b)
-
-// In-place radix-2 decimation-in-frequency FFT of M = B/2 complex points held in shared memory by ONE warp.
-// Natural-order input, bit-reversed output.  INV selects e^{+...} twiddles.  Ends with __syncwarp().
-template <int B, bool INV>
-__device__ inline void warp_cfft_dif(float2* z, const float2* tw, int lane) {
-    constexpr int M = B / 2;
-    constexpr int LOGM = ilog2(M);
-#pragma unroll
-    for (int s = 0; s < LOGM; ++s) {
-        const int half = M >> (s + 1);
-#pragma unroll
-        for (int b = lane; b < M / 2; b += kWarp) {
-            const int pos = b & (half - 1);
-            const int i0 = ((b - pos) << 1) + pos;
-            const int i1 = i0 + half;
-            const float2 u = z[i0], v = z[i1];
-            const float2 w = tw[pos << (s + 1)];               // exp(-2 pi i pos / (2 half)) = tw_B[pos * B/(2 half)]
-            const float2 d = make_float2(u.x - v.x, u.y - v.y);
-            z[i0] = make_float2(u.x + v.x, u.y + v.y);
-            z[i1] = INV ? cmulc(d, w) : cmul(d, w);
-        }
-        __syncwarp();
-    }
-}
-
-template <int B> __device__ inline int brev(int k) { return (int)(__brev((unsigned)k) >> (32 - ilog2(B / 2))); }
-
-// Real FFT of one block, in place in shared memory, by one warp.
-//   in : buf[0..B) = time samples x[t]
-//   out: buf[0..B) = packed half-spectrum {Re X0, Re X_{B/2}, Re X1, Im X1, ..., Re X_{B/2-1}, Im X_{B/2-1}}
-template <int B>
-__device__ inline void warp_rfft_packed(float* buf, const float2* tw, int lane) {
-    constexpr int M = B / 2;
-    float2* z = reinterpret_cast<float2*>(buf);                // z[m] = x[2m] + i x[2m+1]
-    __syncwarp();
-    warp_cfft_dif<B, false>(z, tw, lane);
-    constexpr int KI = (M / 2) / kWarp + 1;
-    float2 zk[KI], zm[KI];
-#pragma unroll
-    for (int it = 0; it < KI; ++it) {
-        const int k = lane + it * kWarp;
-        if (k <= M / 2) { zk[it] = z[brev<B>(k)]; zm[it] = z[brev<B>((M - k) & (M - 1))]; }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < KI; ++it) {
-        const int k = lane + it * kWarp;
-        if (k > M / 2) continue;
-        if (k == 0) {
-            buf[0] = zk[it].x + zk[it].y;                       // DC
-            buf[1] = zk[it].x - zk[it].y;                       // Nyquist
-        } else {
-            // X[k] = (Zk + conj(Zm))/2 - (i/2) w^k (Zk - conj(Zm));  X[M-k] = conj((Zk + conj(Zm))/2 + (i/2) w^k (Zk - conj(Zm)))
-            const float2 e = make_float2(0.5f * (zk[it].x + zm[it].x), 0.5f * (zk[it].y - zm[it].y));
-            const float2 d = make_float2(0.5f * (zk[it].x - zm[it].x), 0.5f * (zk[it].y + zm[it].y));
-            const float2 wd = cmul(tw[k], d);                   // w^k * d
-            // -i * wd = (wd.y, -wd.x)
-            const float2 xk = make_float2(e.x + wd.y, e.y - wd.x);
-            const float2 xm = make_float2(e.x - wd.y, -(e.y + wd.x));
-            z[k] = xk;
-            if (k != M - k) z[M - k] = xm;
-        }
-    }
-    __syncwarp();
-}
-
-// Inverse real FFT of one block by one warp.
-//   in : buf[0..B) = packed half-spectrum of Y (imaginary parts of DC / Nyquist do not exist in this packing,
-//        which is exactly "irfft ignores them", src/patch_llama_fft.py:263)
-//   out: buf viewed as float2 z[]: y[2m] = z[brev(m)].x * (1/B), y[2m+1] = z[brev(m)].y * (1/B)   (caller scales)
-template <int B>
-__device__ inline void warp_irfft_packed(float* buf, const float2* tw, int lane) {
-    constexpr int M = B / 2;
-    float2* z = reinterpret_cast<float2*>(buf);
-    constexpr int KI = (M / 2) / kWarp + 1;
-    float2 xk[KI], xm[KI];
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < KI; ++it) {
-        const int k = lane + it * kWarp;
-        if (k <= M / 2) {
-            if (k == 0) { xk[it] = make_float2(buf[0], 0.f); xm[it] = make_float2(buf[1], 0.f); }
-            else { xk[it] = z[k]; xm[it] = z[M - k]; }
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < KI; ++it) {
-        const int k = lane + it * kWarp;
-        if (k > M / 2) continue;
-        // E = Xk + conj(Xm);  O = conj(w^k) (Xk - conj(Xm));  Z[k] = E + i O;  Z[M-k] = conj(E) + i conj(O)     (x2 scale kept, caller divides by B)
-        const float2 e = make_float2(xk[it].x + xm[it].x, xk[it].y - xm[it].y);
-        const float2 d = make_float2(xk[it].x - xm[it].x, xk[it].y + xm[it].y);
-        const float2 o = cmulc(d, tw[k]);                       // d * conj(w^k)
-        z[k] = make_float2(e.x - o.y, e.y + o.x);
-        if (k != 0 && k != M - k) z[M - k] = make_float2(e.x + o.y, -e.y + o.x);
-    }
-    __syncwarp();
-    warp_cfft_dif<B, true>(z, tw, lane);
-}
 
 }  // namespace bcl

@@ -29,13 +29,13 @@ namespace ws {
 #define BCL_WS_NM 8
 #endif
 #ifndef BCL_WS_NF
-#define BCL_WS_NF 2
+#define BCL_WS_NF 3
 #endif
 #ifndef BCL_WS_STAGE_KB
 #define BCL_WS_STAGE_KB 16
 #endif
 constexpr int NM = BCL_WS_NM;                // MAC warps
-constexpr int NF = BCL_WS_NF;                // finisher warps
+constexpr int NF = BCL_WS_NF;                // finisher warps == group buffers (finisher f owns buffer f, so it sees every phase of it)
 #ifndef BCL_WS_NX
 #define BCL_WS_NX 4
 #endif
@@ -83,8 +83,8 @@ __device__ inline long long clk() { return 0; }
 struct Barriers {
     uint64_t full[MAX_STAGES];      // ring stage filled by TMA            (1 arrival + tx bytes)
     uint64_t empty[MAX_STAGES];     // ring stage released by the MAC warps (NM arrivals)
-    uint64_t gfull[2];              // group buffer complete                (NM arrivals)
-    uint64_t gempty[2];             // group buffer drained by a finisher   (1 arrival)
+    uint64_t gfull[NF];             // group buffer complete                (NM arrivals)
+    uint64_t gempty[NF];            // group buffer drained by its finisher (1 arrival)
     uint64_t xfull[2];              // x spectrum of a segment ready in shared memory     (NX arrivals; slot 0 used)
     uint64_t xempty[2];             // every MAC warp copied its slice into registers      (NM arrivals)
 };
@@ -110,14 +110,14 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
     Barriers* bars = reinterpret_cast<Barriers*>(smem_raw);
     float2* tw = reinterpret_cast<float2*>(smem_raw + 512);
     unsigned char* ring = smem_raw + 512 + 1024;                     // tw needs B/2*8 <= 1024 bytes
-    float* part = reinterpret_cast<float*>(ring + (size_t)S * STAGE_BYTES);                         // [2][PAIRS][NM][B]
-    float2* fscr_all = reinterpret_cast<float2*>(part + 2 * PAIRS * NM * B);                        // FFT scratch of the NX + NF warps
+    float* part = reinterpret_cast<float*>(ring + (size_t)S * STAGE_BYTES);                         // [NF][PAIRS][NM][B]
+    float2* fscr_all = reinterpret_cast<float2*>(part + NF * PAIRS * NM * B);                       // FFT scratch of the NX + NF warps
     float* xs = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(fscr_all) + (size_t)(NX + NF) * FC::WARP_SCRATCH_BYTES);   // [qmax][B]
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], NM); }
-        for (int g = 0; g < 2; ++g) { mbar_init(&bars->gfull[g], NM); mbar_init(&bars->gempty[g], 1); }
+        for (int g = 0; g < NF; ++g) { mbar_init(&bars->gfull[g], NM); mbar_init(&bars->gempty[g], 1); }
         mbar_init(&bars->xfull[0], NX); mbar_init(&bars->xempty[0], NM);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
                 }
                 // park the row's partial spectrum in the group buffer; the last row of a group signals the finisher
                 const int slot = r % RG;
-                const int gb = gi & 1;
-                if (slot == 0) { TSTART(g); mbar_wait(&bars->gempty[gb], ((uint32_t)(gi >> 1) & 1u) ^ 1u); TSTOP(g, t_c); }
+                const int gb = gi % NF;
+                if (slot == 0) { TSTART(g); mbar_wait(&bars->gempty[gb], ((uint32_t)(gi / NF) & 1u) ^ 1u); TSTOP(g, t_c); }
                 store_partial<B, NT, NM>(acc, part + (size_t)gb * PAIRS * NM * B, slot, m, lane);
                 if (slot == RG - 1 || r == rows - 1) {
                     __syncwarp();
@@ -273,8 +273,8 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
             const int rows = w.j1 - w.j0;
             for (int g0 = 0; g0 < rows; g0 += RG, ++gi) {
                 if (gi % NF != f) continue;
-                const int gb = gi & 1;
-                { TSTART(g); mbar_wait(&bars->gfull[gb], (uint32_t)(gi >> 1) & 1u); TSTOP(g, t_a); }
+                const int gb = f;
+                { TSTART(g); mbar_wait(&bars->gfull[gb], (uint32_t)(gi / NF) & 1u); TSTOP(g, t_a); }
                 const int nr = min(RG, rows - g0);
                 TSTART(fin);
                 float* gpart = part + (size_t)gb * PAIRS * NM * B;
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
 size_t smem_bytes(int B, int spec_bytes, int qmax, int S) {
     const size_t fscr = B == 64 ? FftCfg<64>::WARP_SCRATCH_BYTES : (B == 128 ? FftCfg<128>::WARP_SCRATCH_BYTES : FftCfg<256>::WARP_SCRATCH_BYTES);
     const size_t stage = (size_t)stage_blocks(B) * B * spec_bytes;
-    return 512 + 1024 + (size_t)S * stage + (size_t)2 * PAIRS * NM * B * 4 + (size_t)(NX + NF) * fscr + (size_t)qmax * B * 4;
+    return 512 + 1024 + (size_t)S * stage + (size_t)NF * PAIRS * NM * B * 4 + (size_t)(NX + NF) * fscr + (size_t)qmax * B * 4;
 }
 
 // Number of ring stages that fit next to the fixed buffers (0 = this shape does not fit the warp-specialised kernel).
