@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BCL_ABI_VERSION 3
+#define BCL_ABI_VERSION 4
 
 typedef enum bcl_dtype { BCL_F32 = 0, BCL_F16 = 1, BCL_BF16 = 2 } bcl_dtype;
 
@@ -38,7 +38,8 @@ typedef enum bcl_dtype { BCL_F32 = 0, BCL_F16 = 1, BCL_BF16 = 2 } bcl_dtype;
  *   STREAM  [p][q][B] packed half-spectrum, frequency-contiguous: {Re F0, Re F_{B/2}, Re F1, Im F1, ...}.
  *           Exactly the size of c.  Used by the bandwidth-bound small-N (decode) kernel.
  *   GEMM    per-frequency real-embedded complex matrices for the tcgen05 prefill path (bf16 only):
- *           [B/2][2p][2q] K-major tiles, see DESIGN.md. */
+ *           Cmat[f][n][k], f < B/2 packed frequency slots, n = 2j+{re,im} < Np, k = 2i+{re,im} < Kp (K-major rows,
+ *           Np/Kp = 2p/2q rounded up to 16, zero padded); [[Cr,-Ci],[Ci,Cr]] per (j,i), slot 0 = diag(C_dc, C_ny). */
 typedef enum bcl_layout { BCL_LAYOUT_STREAM = 0, BCL_LAYOUT_GEMM = 1 } bcl_layout;
 
 typedef enum bcl_status {
@@ -72,7 +73,9 @@ int bcl_precompute_spectrum(const float* c, int p, int q, int B,
  *            (:266), then the bias is added in the promoted dtype y_dtype (:270-271).  Without a bias
  *            y_dtype must equal x_dtype.
  *   bias     (out) or NULL
- *   workspace  at least bcl_workspace_bytes(...) bytes, 256-byte aligned (may be NULL when that is 0)
+ *   workspace  at least bcl_workspace_bytes(...) bytes, 256-byte aligned (may be NULL when that is 0).  Layout GEMM
+ *            stages Xf/Yf of one token chunk there (a larger workspace means larger chunks); its first int is a
+ *            status word the call zeroes and the tcgen05 kernel sets non-zero if its pipeline ever stalls.
  * N == 0 is a no-op.  */
 size_t bcl_workspace_bytes(int64_t N, int p, int q, int B, int spec_dtype, int layout);
 int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
@@ -80,6 +83,17 @@ int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
                 const void* bias, int bias_dtype,
                 void* y, int y_dtype, int64_t y_row_stride,
                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- prefill stages (layout GEMM): the three steps bcl_forward chains per token chunk, exported so that each can be
+ * checked on its own against the reference step it replaces.  Intermediates are bf16, frequency-major:
+ *   Xf [B/2][N][Kp]   Xf[f][n][2i+{0,1}] = {Re,Im} rfft(x[n, iB:(i+1)B])[f]   (f = 0: {DC, Nyquist})   src/patch_llama_fft.py:252
+ *   Yf [B/2][N][Np]   Yf[f][n][2j+{0,1}] = sum_i Cf[j,i,f] * Xf[n,i,f]                                  src/patch_llama_fft.py:260
+ * bcl_prefill_gemm is the tcgen05 kernel: status (device int, zeroed by the caller) is set non-zero if its pipeline stalls. */
+void bcl_prefill_geometry(int p, int q, int B, int* F, int* Kp, int* Np);
+int bcl_prefill_rfft(const void* x, int x_dtype, int64_t N, int64_t x_row_stride, int q, int B, void* Xf, void* stream);
+int bcl_prefill_gemm(const void* Xf, const void* spec_gemm, void* Yf, int64_t N, int p, int q, int B, int* status, void* stream);
+int bcl_prefill_irfft(const void* Yf, int64_t N, int p, int B, int x_dtype, const void* bias, int bias_dtype,
+                      void* y, int y_dtype, int64_t y_row_stride, void* stream);
 
 /* ---- grouped forward: many independent BC linears in ONE launch -------------------------------------------
  * The reference calls one module at a time (HF LlamaMLP/LlamaAttention -> forward); at batch-1

@@ -10,7 +10,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BCL_LIB_PATH") or os.path.join(_HERE, "libbclinear.so")   # override: A/B builds when profiling
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 F32, F16, BF16 = 0, 1, 2
 LAYOUT_STREAM, LAYOUT_GEMM = 0, 1
 
@@ -21,6 +21,7 @@ SYMBOLS = (
     "bcl_abi_version", "bcl_last_error", "bcl_spectrum_bytes", "bcl_precompute_spectrum", "bcl_workspace_bytes",
     "bcl_forward", "bcl_group_plan_bytes", "bcl_group_plan_encode", "bcl_forward_grouped", "bcl_forward_host", "bcl_forward_grouped_host",
     "bcl_project_from_dense",
+    "bcl_prefill_geometry", "bcl_prefill_rfft", "bcl_prefill_gemm", "bcl_prefill_irfft",
 )
 
 
@@ -67,6 +68,12 @@ def lib() -> ctypes.CDLL:
     L.bcl_forward_host.argtypes = [vp, i32, i64, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, vp, vp, sz, vp]
     L.bcl_forward_grouped_host.argtypes = [vp, vp, vp, vp, sz, vp, vp, sz, vp]
     L.bcl_project_from_dense.argtypes = [vp, i32, i64, i32, i32, i32, vp, vp]
+    ip = ctypes.POINTER(ctypes.c_int)
+    L.bcl_prefill_geometry.restype = None
+    L.bcl_prefill_geometry.argtypes = [i32, i32, i32, ip, ip, ip]
+    L.bcl_prefill_rfft.argtypes = [vp, i32, i64, i64, i32, i32, vp, vp]
+    L.bcl_prefill_gemm.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, vp]
+    L.bcl_prefill_irfft.argtypes = [vp, i64, i32, i32, i32, vp, i32, vp, i32, i64, vp]
     for name in SYMBOLS:
         getattr(L, name)
     if L.bcl_abi_version() != ABI_VERSION:
@@ -86,6 +93,13 @@ def check(rc: int, what: str) -> None:
     if rc == -8:
         raise NotImplementedError(text)
     raise BclError(text)
+
+
+def prefill_geometry(p: int, q: int, B: int):
+    """(F, Kp, Np) of the GEMM layout: B/2 frequency slots, 2q and 2p rounded up to 16."""
+    F, Kp, Np = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    lib().bcl_prefill_geometry(p, q, B, ctypes.byref(F), ctypes.byref(Kp), ctypes.byref(Np))
+    return F.value, Kp.value, Np.value
 
 
 def stream_ptr(device) -> int:

@@ -65,6 +65,7 @@ size_t bcl_spectrum_bytes(int p, int q, int B, int spec_dtype, int layout) {
         if (spec_dtype != BCL_F32 && spec_dtype != BCL_BF16) return 0;
         return (size_t)p * q * B * (spec_dtype == BCL_F32 ? 4 : 2);
     }
+    if (layout == BCL_LAYOUT_GEMM) return spec_dtype == BCL_BF16 ? bcl::gemm_spectrum_bytes(p, q, B) : 0;
     return 0;
 }
 
@@ -78,12 +79,17 @@ int bcl_precompute_spectrum(const float* c, int p, int q, int B, void* spec, int
         cudaError_t e = bcl::launch_spectrum_stream(c, spec, p, q, B, spec_dtype, (cudaStream_t)stream);
         return e == cudaSuccess ? BCL_OK : cuda_fail(e, "spectrum precompute launch");
     }
-    return fail(BCL_ERR_UNSUPPORTED, "spectrum layout %d is not built", layout);
+    if (layout == BCL_LAYOUT_GEMM) {
+        if (spec_dtype != BCL_BF16) return fail(BCL_ERR_DTYPE, "GEMM spectrum must be bf16");
+        cudaError_t e = bcl::launch_spectrum_gemm(c, spec, p, q, B, (cudaStream_t)stream);
+        return e == cudaSuccess ? BCL_OK : cuda_fail(e, "GEMM spectrum precompute launch");
+    }
+    return fail(BCL_ERR_ARG, "unknown spectrum layout %d", layout);
 }
 
 size_t bcl_workspace_bytes(int64_t N, int p, int q, int B, int spec_dtype, int layout) {
-    (void)N; (void)p; (void)q; (void)B; (void)spec_dtype;
-    if (layout == BCL_LAYOUT_STREAM) return 0;
+    (void)spec_dtype;
+    if (layout == BCL_LAYOUT_GEMM && valid_B(B) && p > 0 && q > 0 && N > 0) return bcl::gemm_workspace_bytes(N, p, q, B);
     return 0;
 }
 
@@ -91,7 +97,6 @@ int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
                 const void* spec, int spec_dtype, int layout, int p, int q, int B,
                 const void* bias, int bias_dtype, void* y, int y_dtype, int64_t y_row_stride,
                 void* workspace, size_t workspace_bytes, void* stream) {
-    (void)workspace; (void)workspace_bytes;
     int rc = check_problem(x, x_dtype, N, x_row_stride, spec, p, q, B, bias, bias_dtype, y, y_dtype, y_row_stride);
     if (rc != BCL_OK || N == 0) return rc;
     if (layout == BCL_LAYOUT_STREAM) {
@@ -101,7 +106,63 @@ int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
         cudaError_t e = bcl::launch_stream_single(P, B, spec_dtype, (cudaStream_t)stream);
         return e == cudaSuccess ? BCL_OK : cuda_fail(e, "stream forward launch");
     }
-    return fail(BCL_ERR_UNSUPPORTED, "forward for spectrum layout %d is not built", layout);
+    if (layout == BCL_LAYOUT_GEMM) {
+        if (spec_dtype != BCL_BF16) return fail(BCL_ERR_DTYPE, "GEMM spectrum must be bf16");
+        if (N > (int64_t)1 << 30) return fail(BCL_ERR_SHAPE, "N=%lld too large; split the batch", (long long)N);
+        if (!workspace || !aligned(workspace, 256)) return fail(BCL_ERR_WORKSPACE, "GEMM layout needs a 256-byte aligned workspace");
+        if (bcl::gemm_chunk_tokens(N, p, q, B, workspace_bytes) < (N < 128 ? N : 128))
+            return fail(BCL_ERR_WORKSPACE, "workspace %zu bytes cannot stage one 128-token chunk (bcl_workspace_bytes gives %zu)", workspace_bytes,
+                        bcl::gemm_workspace_bytes(N, p, q, B));
+        bcl::ProblemDev P{x, spec, bias, y, N, x_row_stride, y_row_stride, p, q, x_dtype, y_dtype, bias ? bias_dtype : BCL_F32, 0};
+        cudaError_t e = bcl::launch_gemm_forward(P, B, spec, workspace, workspace_bytes, (cudaStream_t)stream);
+        return e == cudaSuccess ? BCL_OK : cuda_fail(e, "GEMM forward launch");
+    }
+    return fail(BCL_ERR_ARG, "unknown spectrum layout %d", layout);
+}
+
+void bcl_prefill_geometry(int p, int q, int B, int* F, int* Kp, int* Np) {
+    if (F) *F = B / 2;
+    if (Kp) *Kp = (2 * q + 15) / 16 * 16;
+    if (Np) *Np = (2 * p + 15) / 16 * 16;
+}
+
+int bcl_prefill_rfft(const void* x, int x_dtype, int64_t N, int64_t x_row_stride, int q, int B, void* Xf, void* stream) {
+    if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
+    if (q <= 0 || N < 0 || N > (int64_t)1 << 30) return fail(BCL_ERR_SHAPE, "bad shape q=%d N=%lld", q, (long long)N);
+    if (!valid_dt(x_dtype)) return fail(BCL_ERR_DTYPE, "unknown dtype enum");
+    if (N == 0) return BCL_OK;
+    if (!x || !Xf) return fail(BCL_ERR_ARG, "NULL x/Xf");
+    if (!aligned(x, 16) || !aligned(Xf, 16) || (x_row_stride * bcl::dtype_size(x_dtype)) % 16) return fail(BCL_ERR_ALIGN, "x, Xf and the row stride must be 16-byte aligned");
+    bcl::ProblemDev P{x, nullptr, nullptr, nullptr, N, x_row_stride, 0, 1, q, x_dtype, x_dtype, BCL_F32, 0};
+    cudaError_t e = bcl::launch_gemm_rfft(P, B, 0, (int)N, Xf, (cudaStream_t)stream);
+    return e == cudaSuccess ? BCL_OK : cuda_fail(e, "prefill rfft launch");
+}
+
+int bcl_prefill_gemm(const void* Xf, const void* spec_gemm, void* Yf, int64_t N, int p, int q, int B, int* status, void* stream) {
+    if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
+    if (p <= 0 || q <= 0 || N < 0 || N > (int64_t)1 << 30) return fail(BCL_ERR_SHAPE, "bad shape p=%d q=%d N=%lld", p, q, (long long)N);
+    if (N == 0) return BCL_OK;
+    if (!Xf || !spec_gemm || !Yf || !status) return fail(BCL_ERR_ARG, "NULL Xf/spec/Yf/status");
+    if (!aligned(Xf, 128) || !aligned(spec_gemm, 128) || !aligned(Yf, 16)) return fail(BCL_ERR_ALIGN, "Xf and spec must be 128-byte, Yf 16-byte aligned");
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = bcl::launch_gemm_mma(Xf, spec_gemm, Yf, status, p, q, B, (int)N, sms, (cudaStream_t)stream);
+    return e == cudaSuccess ? BCL_OK : cuda_fail(e, "prefill tcgen05 GEMM launch");
+}
+
+int bcl_prefill_irfft(const void* Yf, int64_t N, int p, int B, int x_dtype, const void* bias, int bias_dtype,
+                      void* y, int y_dtype, int64_t y_row_stride, void* stream) {
+    if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
+    if (p <= 0 || N < 0 || N > (int64_t)1 << 30) return fail(BCL_ERR_SHAPE, "bad shape p=%d N=%lld", p, (long long)N);
+    if (!valid_dt(x_dtype) || !valid_dt(y_dtype) || (bias && !valid_dt(bias_dtype))) return fail(BCL_ERR_DTYPE, "unknown dtype enum");
+    if (N == 0) return BCL_OK;
+    if (!Yf || !y) return fail(BCL_ERR_ARG, "NULL Yf/y");
+    const int want = bias ? promote(x_dtype, bias_dtype) : x_dtype;
+    if (y_dtype != want) return fail(BCL_ERR_DTYPE, "y_dtype %d but the reference's promotion gives %d", y_dtype, want);
+    if (!aligned(Yf, 16) || !aligned(y, 16) || (y_row_stride * bcl::dtype_size(y_dtype)) % 16) return fail(BCL_ERR_ALIGN, "Yf, y and the row stride must be 16-byte aligned");
+    bcl::ProblemDev P{nullptr, nullptr, bias, y, N, 0, y_row_stride, p, 1, x_dtype, y_dtype, bias ? bias_dtype : BCL_F32, 0};
+    cudaError_t e = bcl::launch_gemm_irfft(P, B, 0, (int)N, Yf, (cudaStream_t)stream);
+    return e == cudaSuccess ? BCL_OK : cuda_fail(e, "prefill irfft launch");
 }
 
 size_t bcl_group_plan_bytes(int count, int num_ctas) {

@@ -41,6 +41,16 @@ cudaError_t launch_stream_ws(const GroupPlanHeader& H, const void* dev_plan, cud
 size_t stream_smem_bytes(int B, int nt, int q, int warps);
 int stream_pick_nt(int64_t N, int q, int B);
 
+// prefill path (bcl_gemm.cu): GEMM-layout spectrum, the three stages, and the chunked forward that chains them
+size_t gemm_spectrum_bytes(int p, int q, int B);
+size_t gemm_workspace_bytes(int64_t N, int p, int q, int B);
+int64_t gemm_chunk_tokens(int64_t N, int p, int q, int B, size_t workspace_bytes);
+cudaError_t launch_spectrum_gemm(const float* c, void* spec, int p, int q, int B, cudaStream_t st);
+cudaError_t launch_gemm_rfft(const ProblemDev& P, int B, int64_t n_begin, int nc, void* Xf, cudaStream_t st);
+cudaError_t launch_gemm_mma(const void* Xf, const void* Cmat, void* Yf, int* status, int p, int q, int B, int nc, int max_ctas, cudaStream_t st);
+cudaError_t launch_gemm_irfft(const ProblemDev& P, int B, int64_t n_begin, int nc, const void* Yf, cudaStream_t st);
+cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* Cmat, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 cudaError_t launch_project_from_dense(const void* W, int w_dtype, int64_t w_stride, int p, int q, int B, float* c, cudaStream_t st);
 
 }  // namespace bcl

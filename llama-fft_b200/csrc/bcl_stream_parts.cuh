@@ -50,7 +50,7 @@ __device__ __forceinline__ void convert_x_raw(const XRaw<V>& r, int dt, float2 (
     }
 }
 
-template <int B, int NT, int NWARPS>
+template <int B, int NT, int NWARPS, int PITCH = B>
 __device__ inline void load_x_spectrum(const ProblemDev& P, int64_t n0, float* xs, const float2* tw, float2* fscr, int lane, int warp) {
     using C = FftCfg<B>;
     const int q = P.q;
@@ -77,7 +77,7 @@ __device__ inline void load_x_spectrum(const ProblemDev& P, int64_t n0, float* x
         }
         float2 a[C::V];
         convert_x_raw<C::V>(cur, P.x_dtype, a);
-        group_rfft_packed<B>(a, scr, xs + (size_t)idx * B, tw, t, active);
+        group_rfft_packed<B>(a, scr, xs + (size_t)idx * PITCH, tw, t, active);
         if (!more) break;
         cur = nxt; base = nbase; idx = idx2; n = n2; i = i2; active = act2;
     }
@@ -194,6 +194,32 @@ __device__ inline void store_partial(RowAcc<B, NT>& acc, float* part, int r, int
     }
 }
 
+// The reference epilogue for one output block (src/patch_llama_fft.py:263-271): lane t of the block's T-lane group holds
+// the UNSCALED inverse-FFT samples out[] (layout of group_irfft_packed); scale by 1/B, round to x.dtype FIRST (:266), then
+// add the bias in the promoted dtype (:270-271), store y[n, j*B ...].
+template <int B>
+__device__ __forceinline__ void store_block_epilogue(const ProblemDev& P, int64_t n, int j, int t, const float2 (&out)[FftCfg<B>::V]) {
+    using C = FftCfg<B>;
+    const float inv_b = 1.0f / (float)B;
+    const int64_t colbase = (int64_t)j * B;
+#pragma unroll
+    for (int jj = 0; jj < C::OPT; ++jj) {
+#pragma unroll
+        for (int k2 = 0; k2 < C::T; ++k2) {
+            const int m = (t * C::OPT + jj) + C::V * k2;
+            const int64_t col = colbase + 2 * m;
+            float2 v = out[jj * C::T + k2];
+            v.x = round_to(v.x * inv_b, P.x_dtype);             // y32.to(x.dtype) first (:266)
+            v.y = round_to(v.y * inv_b, P.x_dtype);
+            if (P.bias != nullptr) {                            // then + bias in the promoted dtype (:270-271)
+                const float2 bv = load_act2(P.bias, col, P.bias_dtype);
+                v.x += bv.x; v.y += bv.y;
+            }
+            store_act2(P.y, n * P.y_stride + col, P.y_dtype, v);
+        }
+    }
+}
+
 // One warp finishes up to G = 32/T (row, token) pairs at once: sum the NPART partial spectra of each pair (all lanes,
 // natural lane layout), then every T-lane group runs the inverse real FFT of one pair, applies the reference epilogue
 // (src/patch_llama_fft.py:263-271: 1/B scale, round to x.dtype, + bias in the promoted dtype) and stores y.
@@ -233,26 +259,7 @@ __device__ inline void finish_pairs(const ProblemDev& P, int j_first, int64_t n0
     float2 out[C::V];
     group_irfft_packed<B>(part + (size_t)pg * NPART * B, fscr + g * C::GROUP_F2, tw, t, out);
     const int slot_row = (pair0 + pg) / NT, n = (pair0 + pg) - slot_row * NT;
-    if (g < npairs && n0 + n < P.N) {
-        const float inv_b = 1.0f / (float)B;
-        const int64_t colbase = (int64_t)(j_first + slot_row) * B;
-#pragma unroll
-        for (int jj = 0; jj < C::OPT; ++jj) {
-#pragma unroll
-            for (int k2 = 0; k2 < C::T; ++k2) {
-                const int m = (t * C::OPT + jj) + C::V * k2;
-                const int64_t col = colbase + 2 * m;
-                float2 v = out[jj * C::T + k2];
-                v.x = round_to(v.x * inv_b, P.x_dtype);             // y32.to(x.dtype) first (:266)
-                v.y = round_to(v.y * inv_b, P.x_dtype);
-                if (P.bias != nullptr) {                            // then + bias in the promoted dtype (:270-271)
-                    const float2 bv = load_act2(P.bias, col, P.bias_dtype);
-                    v.x += bv.x; v.y += bv.y;
-                }
-                store_act2(P.y, (n0 + n) * P.y_stride + col, P.y_dtype, v);
-            }
-        }
-    }
+    if (g < npairs && n0 + n < P.N) store_block_epilogue<B>(P, n0 + n, j_first + slot_row, t, out);
     __syncwarp();
 }
 

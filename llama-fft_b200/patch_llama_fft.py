@@ -25,6 +25,8 @@ MODEL_PATH = os.environ.get("LLAMA_FFT_MODEL_PATH", "Llama-2-7b-hf")
 BLOCK_SIZE = 256
 NUM_LAYERS_TO_PATCH = 1
 
+PREFILL_MIN_TOKENS = int(os.environ.get("BCL_PREFILL_MIN_TOKENS", "256"))   # bf16-spectrum layers switch to the tcgen05 path from here
+
 MLP_TARGETS = ("gate_proj", "up_proj", "down_proj")
 ATTN_TARGETS = ("q_proj", "k_proj", "v_proj", "o_proj")
 
@@ -115,7 +117,8 @@ class BlockCirculantLinear(nn.Module):
         if spectrum_dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("spectrum_dtype must be torch.float32 or torch.bfloat16")
         self.spectrum_dtype = spectrum_dtype
-        self._spec: Optional[torch.Tensor] = None
+        self._spec: Optional[torch.Tensor] = None          # STREAM layout (decode / small N)
+        self._spec_gemm: Optional[torch.Tensor] = None     # GEMM layout (tcgen05 prefill path)
         self._spec_key = None
 
     def extra_repr(self) -> str:
@@ -140,27 +143,45 @@ class BlockCirculantLinear(nn.Module):
         c = self.c
         return (c.data_ptr(), c._version, str(c.device), c.dtype, self.spectrum_dtype)
 
-    def build_spectrum(self, *, force: bool = False) -> torch.Tensor:
-        """rfft(c) in the STREAM layout on c's device (replaces reference :256-257 / the _Cf_cache of
-        src/bench_all_in_one.py:204-219).  Re-used until c is written to (its version counter moves), moved, or
-        re-typed -- so load_bc_params / optimizer steps invalidate it, which the reference's cache key does not."""
+    def build_spectrum(self, *, force: bool = False, layout: int = _cabi.LAYOUT_STREAM) -> torch.Tensor:
+        """rfft(c) on c's device (replaces reference :256-257 / the _Cf_cache of src/bench_all_in_one.py:204-219), in the
+        STREAM layout (decode kernel) or the GEMM layout (tcgen05 prefill kernels, bf16 only).  Re-used until c is
+        written to (its version counter moves), moved, or re-typed -- so load_bc_params / optimizer steps invalidate
+        it, which the reference's cache key does not."""
         key = self._spectrum_key()
-        if not force and self._spec is not None and self._spec_key == key:
-            return self._spec
+        if self._spec_key != key:
+            self._spec, self._spec_gemm, self._spec_key = None, None, key
+        cached = self._spec if layout == _cabi.LAYOUT_STREAM else self._spec_gemm
+        if not force and cached is not None:
+            return cached
         c = self.c.detach()
         _cabi.require_cuda(c, "BlockCirculantLinear.c")
         c32 = c.to(torch.float32).contiguous()
-        spec = torch.empty(self.out_blocks, self.in_blocks, self.block_size, device=c.device, dtype=self.spectrum_dtype)
+        L = _cabi.lib()
+        if layout == _cabi.LAYOUT_STREAM:
+            spec = torch.empty(self.out_blocks, self.in_blocks, self.block_size, device=c.device, dtype=self.spectrum_dtype)
+        else:
+            if self.spectrum_dtype != torch.bfloat16:
+                raise ValueError("the GEMM (tcgen05 prefill) spectrum layout is bf16 only")
+            F, Kp, Np = _cabi.prefill_geometry(self.out_blocks, self.in_blocks, self.block_size)
+            spec = torch.empty(F, Np, Kp, device=c.device, dtype=torch.bfloat16)
         with torch.cuda.device(c.device):
-            rc = _cabi.lib().bcl_precompute_spectrum(c32.data_ptr(), self.out_blocks, self.in_blocks, self.block_size,
-                                                     spec.data_ptr(), _cabi.DTYPE[self.spectrum_dtype], _cabi.LAYOUT_STREAM,
-                                                     _cabi.stream_ptr(c.device))
+            rc = L.bcl_precompute_spectrum(c32.data_ptr(), self.out_blocks, self.in_blocks, self.block_size,
+                                           spec.data_ptr(), _cabi.DTYPE[self.spectrum_dtype], layout,
+                                           _cabi.stream_ptr(c.device))
         _cabi.check(rc, "bcl_precompute_spectrum")
-        self._spec, self._spec_key = spec, key
+        if layout == _cabi.LAYOUT_STREAM:
+            self._spec = spec
+        else:
+            self._spec_gemm = spec
         return spec
 
     def drop_spectrum(self) -> None:
-        self._spec, self._spec_key = None, None
+        self._spec, self._spec_gemm, self._spec_key = None, None, None
+
+    def _use_prefill_path(self, n_tokens: int) -> bool:
+        """bf16 spectra and enough tokens to fill 128-row MMA tiles -> tcgen05 per-frequency GEMM path."""
+        return self.spectrum_dtype == torch.bfloat16 and n_tokens >= PREFILL_MIN_TOKENS and self.block_size in (64, 128, 256)
 
     # -- forward --------------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -188,15 +209,30 @@ class BlockCirculantLinear(nn.Module):
         else:
             # reference rule (src/bench_all_in_one.py:212-219): a cached spectrum is served only in eval/no-grad
             reuse = (not self.training) and (not torch.is_grad_enabled())
-            spec = self.build_spectrum(force=not reuse)
-            y_flat = bc_forward(x_flat, spec, self.bias, self.out_blocks, self.in_blocks, self.block_size)
+            layout = _cabi.LAYOUT_GEMM if self._use_prefill_path(x_flat.shape[0]) else _cabi.LAYOUT_STREAM
+            spec = self.build_spectrum(force=not reuse, layout=layout)
+            y_flat = bc_forward(x_flat, spec, self.bias, self.out_blocks, self.in_blocks, self.block_size, layout=layout)
         if lead is not None:
             return y_flat.view(lead[0], lead[1], self.out_features)
         return y_flat
 
 
+_workspaces: Dict[str, torch.Tensor] = {}
+
+
+def prefill_workspace(device, nbytes: int) -> torch.Tensor:
+    """Per-device staging buffer of the GEMM-layout path (Xf/Yf of one token chunk); grows, never shrinks.  Kernels of
+    one stream run in order, so one buffer per device serves every layer."""
+    key = str(device)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, device=device, dtype=torch.uint8)
+        _workspaces[key] = ws
+    return ws
+
+
 def bc_forward(x_flat: torch.Tensor, spec: torch.Tensor, bias: Optional[torch.Tensor], p: int, q: int, B: int,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, *, layout: int = _cabi.LAYOUT_STREAM) -> torch.Tensor:
     """One ``bcl_forward`` call: (N,in) -> (N,out).  Output dtype follows the reference: x.dtype, or the PyTorch
     promotion of x.dtype and bias.dtype when a bias is present (reference :266-271)."""
     if x_flat.stride(-1) != 1 or (x_flat.stride(0) * x_flat.element_size()) % 16 or x_flat.data_ptr() % 16:
@@ -207,14 +243,24 @@ def bc_forward(x_flat: torch.Tensor, spec: torch.Tensor, bias: Optional[torch.Te
         raise TypeError(f"unsupported bias/output dtype {y_dtype}")
     y = out if out is not None else torch.empty(N, p * B, device=x_flat.device, dtype=y_dtype)
     L = _cabi.lib()
-    layout = _cabi.LAYOUT_STREAM
+    ws_ptr, ws_bytes = None, 0
+    if layout == _cabi.LAYOUT_GEMM and N > 0:
+        ws_bytes = L.bcl_workspace_bytes(N, p, q, B, _cabi.DTYPE[spec.dtype], layout)
+        ws = prefill_workspace(x_flat.device, ws_bytes)
+        ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
     with torch.cuda.device(x_flat.device):
         rc = L.bcl_forward(x_flat.data_ptr(), _cabi.DTYPE[x_flat.dtype], N, x_flat.stride(0),
                            spec.data_ptr(), _cabi.DTYPE[spec.dtype], layout, p, q, B,
                            None if bias is None else bias.data_ptr(), 0 if bias is None else _cabi.DTYPE[bias.dtype],
-                           y.data_ptr(), _cabi.DTYPE[y_dtype], y.stride(0), None, 0, _cabi.stream_ptr(x_flat.device))
+                           y.data_ptr(), _cabi.DTYPE[y_dtype], y.stride(0), ws_ptr, ws_bytes, _cabi.stream_ptr(x_flat.device))
     _cabi.check(rc, "bcl_forward")
     return y
+
+
+def prefill_status(device) -> int:
+    """Status word of the last GEMM-layout forward on `device` (0 = the tcgen05 pipeline never stalled).  Synchronises."""
+    ws = _workspaces.get(str(device))
+    return 0 if ws is None else int(ws[:4].view(torch.int32).item())
 
 
 # ---------------------------------------------------------------------------------------------------------
