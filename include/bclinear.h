@@ -30,16 +30,17 @@
 extern "C" {
 #endif
 
-#define BCL_ABI_VERSION 4
+#define BCL_ABI_VERSION 5
 
 typedef enum bcl_dtype { BCL_F32 = 0, BCL_F16 = 1, BCL_BF16 = 2 } bcl_dtype;
 
 /* Spectrum layouts in HBM (DESIGN.md "Data layout").
  *   STREAM  [p][q][B] packed half-spectrum, frequency-contiguous: {Re F0, Re F_{B/2}, Re F1, Im F1, ...}.
  *           Exactly the size of c.  Used by the bandwidth-bound small-N (decode) kernel.
- *   GEMM    per-frequency real-embedded complex matrices for the tcgen05 prefill path (bf16 only):
+ *   GEMM    the tcgen05 prefill path's buffer (bf16 only): per-frequency real-embedded complex matrices
  *           Cmat[f][n][k], f < B/2 packed frequency slots, n = 2j+{re,im} < Np, k = 2i+{re,im} < Kp (K-major rows,
- *           Np/Kp = 2p/2q rounded up to 16, zero padded); [[Cr,-Ci],[Ci,Cr]] per (j,i), slot 0 = diag(C_dc, C_ny). */
+ *           Np = 2p rounded up to 64, Kp = 2q rounded up to 16, zero padded); [[Cr,-Ci],[Ci,Cr]] per (j,i), slot 0 =
+ *           diag(C_dc, C_ny); followed by the forward (fp16, bf16) and inverse (bf16) B x B DFT matrices. */
 typedef enum bcl_layout { BCL_LAYOUT_STREAM = 0, BCL_LAYOUT_GEMM = 1 } bcl_layout;
 
 typedef enum bcl_status {
@@ -85,15 +86,18 @@ int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- prefill stages (layout GEMM): the three steps bcl_forward chains per token chunk, exported so that each can be
- * checked on its own against the reference step it replaces.  Intermediates are bf16, frequency-major:
- *   Xf [B/2][N][Kp]   Xf[f][n][2i+{0,1}] = {Re,Im} rfft(x[n, iB:(i+1)B])[f]   (f = 0: {DC, Nyquist})   src/patch_llama_fft.py:252
- *   Yf [B/2][N][Np]   Yf[f][n][2j+{0,1}] = sum_i Cf[j,i,f] * Xf[n,i,f]                                  src/patch_llama_fft.py:260
- * bcl_prefill_gemm is the tcgen05 kernel: status (device int, zeroed by the caller) is set non-zero if its pipeline stalls. */
-void bcl_prefill_geometry(int p, int q, int B, int* F, int* Kp, int* Np);
-int bcl_prefill_rfft(const void* x, int x_dtype, int64_t N, int64_t x_row_stride, int q, int B, void* Xf, void* stream);
+ * checked on its own against the reference step it replaces.  Intermediates are bf16 in 16-byte chunks:
+ *   Xf [B/2][Kp/8][N][8]   Xf[f][kg][n][k0], k = 8 kg + k0 = 2i+{0,1} = {Re,Im} rfft(x[n, iB:(i+1)B])[f]  (f = 0: {DC, Nyquist})   src/patch_llama_fft.py:252
+ *   Yf [B/8][p][N][8]      Yf[fg][j][n][2 fl+{0,1}] = {Re,Im} sum_i Cf[j,i,f] * Xf[n,i,f],  f = 4 fg + fl                         src/patch_llama_fft.py:260
+ * spec_gemm is the GEMM-layout spectrum buffer of the layer (it also carries the DFT matrices of the tensor-core stages).
+ * impl: 0 = pick, 1 = CUDA-core register FFT, 2 = DFT as a tcgen05 GEMM (B <= 128, 16-bit activations; else BCL_ERR_UNSUPPORTED).
+ * status: device int zeroed by the caller; a tcgen05 kernel sets it non-zero if its pipeline ever stalls. */
+void bcl_prefill_geometry(int p, int q, int B, int* F, int* Kp, int* Np, size_t* wf16_off, size_t* wbf16_off, size_t* winv_off);
+int bcl_prefill_rfft(const void* x, int x_dtype, int64_t N, int64_t x_row_stride, int p, int q, int B, const void* spec_gemm, int impl,
+                     void* Xf, int* status, void* stream);
 int bcl_prefill_gemm(const void* Xf, const void* spec_gemm, void* Yf, int64_t N, int p, int q, int B, int* status, void* stream);
-int bcl_prefill_irfft(const void* Yf, int64_t N, int p, int B, int x_dtype, const void* bias, int bias_dtype,
-                      void* y, int y_dtype, int64_t y_row_stride, void* stream);
+int bcl_prefill_irfft(const void* Yf, int64_t N, int p, int q, int B, const void* spec_gemm, int impl, int x_dtype,
+                      const void* bias, int bias_dtype, void* y, int y_dtype, int64_t y_row_stride, int* status, void* stream);
 
 /* ---- grouped forward: many independent BC linears in ONE launch -------------------------------------------
  * The reference calls one module at a time (HF LlamaMLP/LlamaAttention -> forward); at batch-1

@@ -10,7 +10,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BCL_LIB_PATH") or os.path.join(_HERE, "libbclinear.so")   # override: A/B builds when profiling
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 F32, F16, BF16 = 0, 1, 2
 LAYOUT_STREAM, LAYOUT_GEMM = 0, 1
 
@@ -70,10 +70,11 @@ def lib() -> ctypes.CDLL:
     L.bcl_project_from_dense.argtypes = [vp, i32, i64, i32, i32, i32, vp, vp]
     ip = ctypes.POINTER(ctypes.c_int)
     L.bcl_prefill_geometry.restype = None
-    L.bcl_prefill_geometry.argtypes = [i32, i32, i32, ip, ip, ip]
-    L.bcl_prefill_rfft.argtypes = [vp, i32, i64, i64, i32, i32, vp, vp]
+    szp = ctypes.POINTER(ctypes.c_size_t)
+    L.bcl_prefill_geometry.argtypes = [i32, i32, i32, ip, ip, ip, szp, szp, szp]
+    L.bcl_prefill_rfft.argtypes = [vp, i32, i64, i64, i32, i32, i32, vp, i32, vp, vp, vp]
     L.bcl_prefill_gemm.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, vp]
-    L.bcl_prefill_irfft.argtypes = [vp, i64, i32, i32, i32, vp, i32, vp, i32, i64, vp]
+    L.bcl_prefill_irfft.argtypes = [vp, i64, i32, i32, i32, vp, i32, i32, vp, i32, vp, i32, i64, vp, vp]
     for name in SYMBOLS:
         getattr(L, name)
     if L.bcl_abi_version() != ABI_VERSION:
@@ -96,10 +97,17 @@ def check(rc: int, what: str) -> None:
 
 
 def prefill_geometry(p: int, q: int, B: int):
-    """(F, Kp, Np) of the GEMM layout: B/2 frequency slots, 2q and 2p rounded up to 16."""
+    """(F, Kp, Np) of the GEMM layout: B/2 frequency slots, 2q rounded up to 16, 2p rounded up to 64."""
     F, Kp, Np = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
-    lib().bcl_prefill_geometry(p, q, B, ctypes.byref(F), ctypes.byref(Kp), ctypes.byref(Np))
+    lib().bcl_prefill_geometry(p, q, B, ctypes.byref(F), ctypes.byref(Kp), ctypes.byref(Np), None, None, None)
     return F.value, Kp.value, Np.value
+
+
+def prefill_dft_offsets(p: int, q: int, B: int):
+    """Byte offsets of the (fp16 forward, bf16 forward, bf16 inverse) DFT matrices inside the GEMM-layout spectrum buffer."""
+    a, b, c = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+    lib().bcl_prefill_geometry(p, q, B, None, None, None, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    return a.value, b.value, c.value
 
 
 def stream_ptr(device) -> int:

@@ -7,6 +7,7 @@
 #include <vector>
 #include "bcl_common.cuh"
 #include "bcl_kernels.h"
+#include "bcl_gemm.cuh"
 
 namespace {
 
@@ -120,21 +121,30 @@ int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
     return fail(BCL_ERR_ARG, "unknown spectrum layout %d", layout);
 }
 
-void bcl_prefill_geometry(int p, int q, int B, int* F, int* Kp, int* Np) {
-    if (F) *F = B / 2;
-    if (Kp) *Kp = (2 * q + 15) / 16 * 16;
-    if (Np) *Np = (2 * p + 15) / 16 * 16;
+void bcl_prefill_geometry(int p, int q, int B, int* F, int* Kp, int* Np, size_t* wf16_off, size_t* wbf16_off, size_t* winv_off) {
+    const bcl::gemm::Geometry g = bcl::gemm::geometry(p, q, B);
+    if (F) *F = g.F;
+    if (Kp) *Kp = g.Kp;
+    if (Np) *Np = g.Np;
+    if (wf16_off) *wf16_off = g.wf16_off;
+    if (wbf16_off) *wbf16_off = g.wbf16_off;
+    if (winv_off) *winv_off = g.winv_off;
 }
 
-int bcl_prefill_rfft(const void* x, int x_dtype, int64_t N, int64_t x_row_stride, int q, int B, void* Xf, void* stream) {
+static int check_impl(int impl) { return (impl < 0 || impl > 2) ? fail(BCL_ERR_ARG, "impl must be 0 (auto), 1 (CUDA-core FFT) or 2 (tensor-core DFT)") : BCL_OK; }
+
+int bcl_prefill_rfft(const void* x, int x_dtype, int64_t N, int64_t x_row_stride, int p, int q, int B, const void* spec_gemm, int impl,
+                     void* Xf, int* status, void* stream) {
     if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
-    if (q <= 0 || N < 0 || N > (int64_t)1 << 30) return fail(BCL_ERR_SHAPE, "bad shape q=%d N=%lld", q, (long long)N);
+    if (p <= 0 || q <= 0 || N < 0 || N > (int64_t)1 << 30) return fail(BCL_ERR_SHAPE, "bad shape p=%d q=%d N=%lld", p, q, (long long)N);
     if (!valid_dt(x_dtype)) return fail(BCL_ERR_DTYPE, "unknown dtype enum");
+    if (check_impl(impl) != BCL_OK) return BCL_ERR_ARG;
     if (N == 0) return BCL_OK;
-    if (!x || !Xf) return fail(BCL_ERR_ARG, "NULL x/Xf");
-    if (!aligned(x, 16) || !aligned(Xf, 16) || (x_row_stride * bcl::dtype_size(x_dtype)) % 16) return fail(BCL_ERR_ALIGN, "x, Xf and the row stride must be 16-byte aligned");
-    bcl::ProblemDev P{x, nullptr, nullptr, nullptr, N, x_row_stride, 0, 1, q, x_dtype, x_dtype, BCL_F32, 0};
-    cudaError_t e = bcl::launch_gemm_rfft(P, B, 0, (int)N, Xf, (cudaStream_t)stream);
+    if (!x || !Xf || !status) return fail(BCL_ERR_ARG, "NULL x/Xf/status");
+    if (!aligned(x, 16) || !aligned(Xf, 128) || (x_row_stride * bcl::dtype_size(x_dtype)) % 16) return fail(BCL_ERR_ALIGN, "x (16 B), Xf (128 B) and the row stride (16 B) must be aligned");
+    bcl::ProblemDev P{x, nullptr, nullptr, nullptr, N, x_row_stride, 0, p, q, x_dtype, x_dtype, BCL_F32, 0};
+    cudaError_t e = bcl::launch_prefill_stage1(P, B, spec_gemm, 0, (int)N, Xf, status, impl, (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported) return fail(BCL_ERR_UNSUPPORTED, "tensor-core DFT needs B <= 128, 16-bit activations and the GEMM-layout spectrum buffer");
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "prefill rfft launch");
 }
 
@@ -143,25 +153,27 @@ int bcl_prefill_gemm(const void* Xf, const void* spec_gemm, void* Yf, int64_t N,
     if (p <= 0 || q <= 0 || N < 0 || N > (int64_t)1 << 30) return fail(BCL_ERR_SHAPE, "bad shape p=%d q=%d N=%lld", p, q, (long long)N);
     if (N == 0) return BCL_OK;
     if (!Xf || !spec_gemm || !Yf || !status) return fail(BCL_ERR_ARG, "NULL Xf/spec/Yf/status");
-    if (!aligned(Xf, 128) || !aligned(spec_gemm, 128) || !aligned(Yf, 16)) return fail(BCL_ERR_ALIGN, "Xf and spec must be 128-byte, Yf 16-byte aligned");
+    if (!aligned(Xf, 128) || !aligned(spec_gemm, 128) || !aligned(Yf, 128)) return fail(BCL_ERR_ALIGN, "Xf, spec and Yf must be 128-byte aligned");
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = bcl::launch_gemm_mma(Xf, spec_gemm, Yf, status, p, q, B, (int)N, sms, (cudaStream_t)stream);
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "prefill tcgen05 GEMM launch");
 }
 
-int bcl_prefill_irfft(const void* Yf, int64_t N, int p, int B, int x_dtype, const void* bias, int bias_dtype,
-                      void* y, int y_dtype, int64_t y_row_stride, void* stream) {
+int bcl_prefill_irfft(const void* Yf, int64_t N, int p, int q, int B, const void* spec_gemm, int impl, int x_dtype,
+                      const void* bias, int bias_dtype, void* y, int y_dtype, int64_t y_row_stride, int* status, void* stream) {
     if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
-    if (p <= 0 || N < 0 || N > (int64_t)1 << 30) return fail(BCL_ERR_SHAPE, "bad shape p=%d N=%lld", p, (long long)N);
+    if (p <= 0 || q <= 0 || N < 0 || N > (int64_t)1 << 30) return fail(BCL_ERR_SHAPE, "bad shape p=%d q=%d N=%lld", p, q, (long long)N);
     if (!valid_dt(x_dtype) || !valid_dt(y_dtype) || (bias && !valid_dt(bias_dtype))) return fail(BCL_ERR_DTYPE, "unknown dtype enum");
+    if (check_impl(impl) != BCL_OK) return BCL_ERR_ARG;
     if (N == 0) return BCL_OK;
-    if (!Yf || !y) return fail(BCL_ERR_ARG, "NULL Yf/y");
+    if (!Yf || !y || !status) return fail(BCL_ERR_ARG, "NULL Yf/y/status");
     const int want = bias ? promote(x_dtype, bias_dtype) : x_dtype;
     if (y_dtype != want) return fail(BCL_ERR_DTYPE, "y_dtype %d but the reference's promotion gives %d", y_dtype, want);
-    if (!aligned(Yf, 16) || !aligned(y, 16) || (y_row_stride * bcl::dtype_size(y_dtype)) % 16) return fail(BCL_ERR_ALIGN, "Yf, y and the row stride must be 16-byte aligned");
-    bcl::ProblemDev P{nullptr, nullptr, bias, y, N, 0, y_row_stride, p, 1, x_dtype, y_dtype, bias ? bias_dtype : BCL_F32, 0};
-    cudaError_t e = bcl::launch_gemm_irfft(P, B, 0, (int)N, Yf, (cudaStream_t)stream);
+    if (!aligned(Yf, 128) || !aligned(y, 16) || (y_row_stride * bcl::dtype_size(y_dtype)) % 16) return fail(BCL_ERR_ALIGN, "Yf (128 B), y (16 B) and the row stride (16 B) must be aligned");
+    bcl::ProblemDev P{nullptr, nullptr, bias, y, N, 0, y_row_stride, p, q, x_dtype, y_dtype, bias ? bias_dtype : BCL_F32, 0};
+    cudaError_t e = bcl::launch_prefill_stage3(P, B, spec_gemm, 0, (int)N, Yf, status, impl, (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported) return fail(BCL_ERR_UNSUPPORTED, "tensor-core inverse DFT needs B <= 128, 16-bit activations, y_dtype == x_dtype and the GEMM-layout spectrum buffer");
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "prefill irfft launch");
 }
 

@@ -7,46 +7,23 @@
 // it is one bf16 GEMM per frequency with K = 2q, N = 2p and fp32 accumulation -- tensor-core work.  The packed (DC,
 // Nyquist) slot of the half-spectrum is the same GEMM with the block-diagonal matrix [[C_dc, 0], [0, C_ny]].
 //
-// Three kernels per token chunk, staged through an L2-resident workspace:
-//   rfft_rows_kernel   x (N,in)  -> Xf  [F][N][Kp]  bf16   CUDA cores, register FFT core of bcl_fft.cuh    (:249-252)
-//   freq_gemm_kernel   Xf, Cmat  -> Yf  [F][N][Np]  bf16   tcgen05.mma, TMA-fed smem ring, TMEM accumulators (:260)
-//   irfft_rows_kernel  Yf        -> y (N,out)              CUDA cores + the reference epilogue             (:263-271)
-// with F = B/2 packed frequency slots, Kp = 2q and Np = 2p rounded up to 16, k = 2i+{re,im}, n = 2j+{re,im}.
-// GEMM-layout spectrum:  Cmat[f][n][k]  (K-major rows, zero padded), built once per parameter version by
-// spectrum_gemm_kernel (replaces rfft(c), :256-257).
-#include <cuda.h>
+// Three stages per token chunk, staged through an L2-resident workspace (layouts: bcl_gemm.cuh):
+//   stage 1  x (N,in) -> Xf      rfft (:249-252).  dft_fwd_tc_kernel (DFT as a tcgen05 GEMM, bcl_dft_tc.cu) for 16-bit
+//                                activations and B <= 128, else rfft_rows_kernel (CUDA cores, register FFT of bcl_fft.cuh)
+//   stage 2  Xf, Cmat -> Yf      freq_gemm_kernel: tcgen05.mma, TMA-fed smem ring, TMEM accumulators, TMA stores (:260)
+//   stage 3  Yf -> y (N,out)     irfft + the reference epilogue (:263-271): dft_inv_tc_kernel or irfft_rows_kernel
+// The GEMM-layout spectrum (Cmat + the DFT matrices) is built once per parameter version by spectrum_gemm_kernel /
+// dft_matrix_kernel (replaces rfft(c), :256-257).
 #include <mutex>
+#include <cstdlib>
 #include "bcl_stream_parts.cuh"
 #include "bcl_sm100.cuh"
+#include "bcl_gemm.cuh"
 
 namespace bcl {
 namespace gemm {
 
 using namespace sm100;
-
-constexpr int TILE_M = 128;          // tokens per MMA tile (UMMA M)
-constexpr int KATOM = 64;            // bf16 elements per 128-byte swizzle row
-constexpr int ACC_COLS = 256;        // TMEM columns reserved per accumulator (two accumulators: 512 columns)
-constexpr int EPI_PITCH = 144;       // bytes per staged output row (128 data + 16 pad: conflict-free 16-byte accesses)
-constexpr int GEMM_THREADS = 192;    // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-constexpr int MAX_STAGES = 8;
-
-struct Geometry {
-    int F, Kp, Np, Nn, n_chunks, k_atoms;
-};
-
-__host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
-__host__ inline Geometry geometry(int p, int q, int B) {
-    Geometry g;
-    g.F = B / 2;
-    g.Kp = round_up(2 * q, 16);
-    g.Np = round_up(2 * p, 16);
-    g.n_chunks = (g.Np + 255) / 256;
-    g.Nn = round_up((g.Np + g.n_chunks - 1) / g.n_chunks, 16);
-    g.k_atoms = (g.Kp + KATOM - 1) / KATOM;
-    return g;
-}
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -55,10 +32,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ float2 unpack_bf16(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
 
 // ---------------------------------------------------------------------------------------------------------
-// stage 1: rfft of NT tokens (all q input blocks) -> rows of the per-frequency A operand
+// CUDA-core stage 1: rfft of NT tokens (all q input blocks) -> 16-byte chunks of the per-frequency A operand
 // ---------------------------------------------------------------------------------------------------------
 template <int B, int NT, int WARPS> struct RowsSmem {
-    static constexpr int PITCH = B + 2;                                // floats per block: (2i + 2f) mod 32 banks -> conflict-free
+    static constexpr int PITCH = B + 2;                                // floats per block: spreads (block, frequency) over the banks
     static constexpr size_t tw_bytes = (size_t)(B / 2) * 8;
     static constexpr size_t fscr_bytes = (size_t)WARPS * FftCfg<B>::WARP_SCRATCH_BYTES;
     static size_t bytes(int blocks) { return tw_bytes + fscr_bytes + (size_t)NT * blocks * PITCH * 4; }
@@ -66,13 +43,13 @@ template <int B, int NT, int WARPS> struct RowsSmem {
 
 template <int B, int NT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) rfft_rows_kernel(const __grid_constant__ ProblemDev P, int64_t n_begin, int nc,
-                                                                __nv_bfloat16* __restrict__ Xf, int Kp) {
+                                                                __nv_bfloat16* __restrict__ Xf, int KG) {
     using SM = RowsSmem<B, NT, WARPS>;
     using C = FftCfg<B>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tw = reinterpret_cast<float2*>(smem_raw);
-    float2* fscr_all = reinterpret_cast<float2*>(smem_raw + SM::tw_bytes);
-    float* xs = reinterpret_cast<float*>(smem_raw + SM::tw_bytes + SM::fscr_bytes);
+    extern __shared__ __align__(16) unsigned char rows_smem[];
+    float2* tw = reinterpret_cast<float2*>(rows_smem);
+    float2* fscr_all = reinterpret_cast<float2*>(rows_smem + SM::tw_bytes);
+    float* xs = reinterpret_cast<float*>(rows_smem + SM::tw_bytes + SM::fscr_bytes);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     fill_twiddles<B>(tw, threadIdx.x, WARPS * 32);
     __syncthreads();
@@ -83,18 +60,24 @@ __global__ void __launch_bounds__(WARPS * 32) rfft_rows_kernel(const __grid_cons
     load_x_spectrum<B, NT, WARPS, SM::PITCH>(Pc, n_begin + t0, xs, tw, fscr_all + (size_t)warp * (C::WARP_SCRATCH_BYTES / 8), lane, warp);
     __syncthreads();
     constexpr int F = B / 2;
-    for (int row = warp; row < F * NT; row += WARPS) {                  // one warp writes one (f, token) row: Kp bf16, contiguous
-        const int n = row % NT, f = row / NT;
+    // one 16-byte chunk = (f, kg, token): input blocks 4kg .. 4kg+3, {re,im} each.  Tokens of a CTA are adjacent chunks.
+    const int nchunks = F * KG * NT;
+    for (int id = threadIdx.x; id < nchunks; id += WARPS * 32) {
+        const int n = id % NT;
+        const int kg = (id / NT) % KG;
+        const int f = id / (NT * KG);
         if (t0 + n >= nc) continue;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(Xf + ((size_t)f * nc + (t0 + n)) * Kp);
-        for (int i = lane; i < Kp / 2; i += 32) {
-            uint32_t w = 0u;
+        uint32_t w[4];
+#pragma unroll
+        for (int ib = 0; ib < 4; ++ib) {
+            const int i = 4 * kg + ib;
+            w[ib] = 0u;
             if (i < q) {
                 const float2 v = *reinterpret_cast<const float2*>(xs + ((size_t)n * q + i) * SM::PITCH + 2 * f);
-                w = pack_bf16(v.x, v.y);                                // f = 0: (DC, Nyquist), both real
+                w[ib] = pack_bf16(v.x, v.y);                            // f = 0: (DC, Nyquist), both real
             }
-            dst[i] = w;
         }
+        *reinterpret_cast<uint4*>(Xf + (((size_t)f * KG + kg) * nc + (t0 + n)) * 8) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -105,10 +88,10 @@ template <int B, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) spectrum_gemm_kernel(const float* __restrict__ c, int p, int q, __nv_bfloat16* __restrict__ Cmat, int Np, int Kp) {
     using SM = RowsSmem<B, 1, WARPS>;
     using C = FftCfg<B>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tw = reinterpret_cast<float2*>(smem_raw);
-    float2* fscr_all = reinterpret_cast<float2*>(smem_raw + SM::tw_bytes);
-    float* xs = reinterpret_cast<float*>(smem_raw + SM::tw_bytes + SM::fscr_bytes);
+    extern __shared__ __align__(16) unsigned char rows_smem[];
+    float2* tw = reinterpret_cast<float2*>(rows_smem);
+    float2* fscr_all = reinterpret_cast<float2*>(rows_smem + SM::tw_bytes);
+    float* xs = reinterpret_cast<float*>(rows_smem + SM::tw_bytes + SM::fscr_bytes);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = blockIdx.x;
     constexpr int F = B / 2;
@@ -136,13 +119,43 @@ __global__ void __launch_bounds__(WARPS * 32) spectrum_gemm_kernel(const float* 
     }
 }
 
+// DFT matrices for the tensor-core stages.  grid B, block B: thread (row a, column b).
+//   Wfwd[r][t]  r = 0: 1, r = 1: (-1)^t, r = 2f: cos(2 pi f t / B), r = 2f+1: -sin(2 pi f t / B)              (rfft, :252)
+//   Winv[t][r]  the transpose, times 1/B for r < 2 and 2/B otherwise                                          (irfft n=B, :263)
+__global__ void dft_matrix_kernel(int B, __half* __restrict__ wf16, __nv_bfloat16* __restrict__ wbf16, __nv_bfloat16* __restrict__ winv) {
+    const int a = blockIdx.x, b = threadIdx.x;
+    auto entry = [B](int r, int t) -> float {
+        if (r == 0) return 1.f;
+        if (r == 1) return (t & 1) ? -1.f : 1.f;
+        const int f = r >> 1;
+        const int m = (f * t) & (B - 1);                                // angle 2 pi m / B, m exact
+        float s, c;
+        sincospif(2.0f * (float)m / (float)B, &s, &c);
+        return (r & 1) ? -s : c;
+    };
+    const float fw = entry(a, b);                                       // Wfwd[a][b]
+    wf16[(size_t)a * B + b] = __float2half_rn(fw);
+    wbf16[(size_t)a * B + b] = __float2bfloat16_rn(fw);
+    const float iv = entry(b, a) * (b < 2 ? 1.0f : 2.0f) / (float)B;    // Winv[a = t][b = r]
+    winv[(size_t)a * B + b] = __float2bfloat16_rn(iv);
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// stage 2: batched per-frequency GEMM on tcgen05.   D[128 tokens x Nn] = A[128 x Kp] * B[Nn x Kp]^T
+// stage 2: batched per-frequency GEMM on tcgen05.  Work item = (frequency group of 4, 128-token tile, 64-column chunk):
+//   D_fl[128 tokens x 64] = A_f[128 x Kp] * B_f[64 x Kp]^T   for the 4 frequencies f = 4 fg + fl, 4 TMEM accumulators,
+//   then the epilogue interleaves the four accumulators into 16-byte chunks (j, token, {fl, re/im}) and TMA-stores them.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int GEMM_THREADS = 192;    // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int MAX_STAGES = 8;
+constexpr uint32_t A_STAGE_BYTES = TILE_M * KATOM * 2;       // [8 kg][128 tokens][16 B], no swizzle ("interleaved" K-major)
+constexpr uint32_t B_STAGE_BYTES = NCHUNK * KATOM * 2;       // 64 rows x 128 B, 128-byte swizzle
+constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr uint32_t EPI_BUF_BYTES = 8 * 32 * 16;              // [8 j][32 tokens][16 B]
+constexpr int SET_COLS = 4 * NCHUNK;                         // TMEM columns of one accumulator set (4 frequencies)
+
 struct GemmArgs {
-    __nv_bfloat16* Yf;
     int* status;
-    int ntok, F, Kp, Np, Nn, n_chunks, k_atoms, m_tiles, num_tiles, stages;
+    int ntok, p, KG, k_atoms, m_tiles, NCH, num_items, stages;
 };
 
 struct GemmBarriers {
@@ -152,21 +165,19 @@ struct GemmBarriers {
     uint32_t pad;
 };
 
-__device__ __forceinline__ void decode_tile(const GemmArgs& a, int tile, int& f, int& m, int& nc) {
-    nc = tile % a.n_chunks;
-    const int r = tile / a.n_chunks;
+__device__ __forceinline__ void decode_item(const GemmArgs& a, int item, int& fg, int& m, int& nch) {
+    nch = item % a.NCH;
+    const int r = item / a.NCH;
     m = r % a.m_tiles;
-    f = r / a.m_tiles;
+    fg = r / a.m_tiles;
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                                     const __grid_constant__ GemmArgs a) {
+                                                                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char gemm_smem[];
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(gemm_smem);
-    unsigned char* epi = gemm_smem + 512;                                         // 4 warps x 32 rows x EPI_PITCH
-    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem) + 512 + 4 * 32 * EPI_PITCH + 1023) & ~(uintptr_t)1023);
-    const uint32_t a_bytes = TILE_M * KATOM * 2, b_bytes = (uint32_t)a.Nn * KATOM * 2;
-    const uint32_t stage_bytes = a_bytes + b_bytes;                              // both multiples of 1024
+    unsigned char* epi = gemm_smem + 1024;                                       // 4 warps x 2 buffers x EPI_BUF_BYTES
+    unsigned char* ring = gemm_smem + 1024 + 4 * 2 * EPI_BUF_BYTES;               // stays 1024-byte aligned
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int S = a.stages;
 
@@ -175,8 +186,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 4); }
         fence_barrier_init();
     }
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
-    if (warp == 1) tmem_alloc(&bars->tmem_base, 2 * ACC_COLS);
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY); }
+    if (warp == 1) tmem_alloc(&bars->tmem_base, 2 * SET_COLS);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -186,120 +197,120 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-                int f, m, nc; decode_tile(a, tile, f, m, nc);
-                for (int ka = 0; ka < a.k_atoms; ++ka) {
-                    if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 1); goto done; }
-                    unsigned char* sa = ring + (size_t)stage * stage_bytes;
-                    mbar_arrive_expect_tx(&bars->full[stage], stage_bytes);
-                    tma_load_3d(sa, &tmA, ka * KATOM, m * TILE_M, f, &bars->full[stage]);
-                    tma_load_3d(sa + a_bytes, &tmB, ka * KATOM, nc * a.Nn, f, &bars->full[stage]);
-                    if (++stage == S) { stage = 0; ph ^= 1u; }
+            for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
+                int fg, m, nch; decode_item(a, item, fg, m, nch);
+                for (int fl = 0; fl < 4; ++fl) {
+                    for (int ka = 0; ka < a.k_atoms; ++ka) {
+                        if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 1); goto done; }
+                        unsigned char* sa = ring + (size_t)stage * STAGE_BYTES;
+                        mbar_arrive_expect_tx(&bars->full[stage], STAGE_BYTES);
+                        tma_load_4d(sa, &tmA, 0, m * TILE_M, ka * 8, 4 * fg + fl, &bars->full[stage]);
+                        tma_load_3d(sa + A_STAGE_BYTES, &tmB, ka * KATOM, nch * NCHUNK, 4 * fg + fl, &bars->full[stage]);
+                        if (++stage == S) { stage = 0; ph ^= 1u; }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(TILE_M, a.Nn);
+            const uint32_t idesc = umma_idesc_bf16(TILE_M, NCHUNK);
             int stage = 0; uint32_t ph = 0; int it = 0;
-            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1; const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-                if (!mbar_wait(&bars->tmem_empty[acc], acc_ph ^ 1u)) { atomicExch(a.status, 2); goto done; }   // epilogue drained this accumulator
+            for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
+                const int set = it & 1; const uint32_t set_ph = (uint32_t)(it >> 1) & 1u;
+                if (!mbar_wait(&bars->tmem_empty[set], set_ph ^ 1u)) { atomicExch(a.status, 2); goto done; }   // epilogue drained this set
                 tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_COLS;
-                for (int ka = 0; ka < a.k_atoms; ++ka) {
-                    if (!mbar_wait(&bars->full[stage], ph)) { atomicExch(a.status, 3); goto done; }
-                    tc_fence_after_sync();
-                    const uint32_t sa = smem_u32(ring + (size_t)stage * stage_bytes);
-                    const uint64_t adesc = umma_desc_k_sw128(sa), bdesc = umma_desc_k_sw128(sa + a_bytes);
-                    const int ks = min(KATOM / 16, (a.Kp - ka * KATOM) / 16);
-                    for (int kk = 0; kk < ks; ++kk)
-                        umma_bf16_ss(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (ka | kk) != 0 ? 1u : 0u);
-                    umma_commit(&bars->empty[stage]);                            // smem stage reusable once these MMAs retire
-                    if (++stage == S) { stage = 0; ph ^= 1u; }
+                for (int fl = 0; fl < 4; ++fl) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(set * SET_COLS + fl * NCHUNK);
+                    for (int ka = 0; ka < a.k_atoms; ++ka) {
+                        if (!mbar_wait(&bars->full[stage], ph)) { atomicExch(a.status, 3); goto done; }
+                        tc_fence_after_sync();
+                        const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE_BYTES);
+                        const uint64_t bdesc = umma_desc_k_sw128(sa + A_STAGE_BYTES);
+                        const int ks = min(4, (a.KG - ka * 8) / 2);
+                        for (int kk = 0; kk < ks; ++kk)                          // one k-step = 16 elements = 2 kg slabs of 2048 bytes
+                            umma_bf16_ss(d_tmem, umma_desc_k_nosw(sa + (uint32_t)kk * 4096u, 128u, 2048u), bdesc + (uint64_t)(2 * kk), idesc, (ka | kk) != 0 ? 1u : 0u);
+                        umma_commit(&bars->empty[stage]);                        // smem stage reusable once these MMAs retire
+                        if (++stage == S) { stage = 0; ph ^= 1u; }
+                    }
                 }
-                umma_commit(&bars->tmem_full[acc]);                              // accumulator complete -> epilogue
+                umma_commit(&bars->tmem_full[set]);                              // all 4 accumulators complete -> epilogue
             }
         }
     } else {
-        // ===================== epilogue warps: TMEM -> registers -> bf16 -> smem -> coalesced global rows =====================
+        // ===================== epilogue warps: TMEM -> registers -> bf16 chunks -> smem -> TMA store =====================
         const int quarter = warp & 3;                                            // TMEM lanes [32*quarter, +32) are this warp's
-        unsigned char* stg = epi + (size_t)(warp - 2) * 32 * EPI_PITCH;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-            int f, m, nc; decode_tile(a, tile, f, m, nc);
-            const int acc = it & 1; const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-            if (!__all_sync(0xffffffffu, mbar_wait(&bars->tmem_full[acc], acc_ph))) { atomicExch(a.status, 4); goto done; }   // warp-uniform outcome
+        unsigned char* stg = epi + (size_t)(warp - 2) * 2 * EPI_BUF_BYTES;
+        int it = 0, buf = 0;
+        for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
+            int fg, m, nch; decode_item(a, item, fg, m, nch);
+            const int set = it & 1; const uint32_t set_ph = (uint32_t)(it >> 1) & 1u;
+            if (!__all_sync(0xffffffffu, mbar_wait(&bars->tmem_full[set], set_ph))) { atomicExch(a.status, 4); goto done; }
             tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * ACC_COLS;
-            const int tok0 = m * TILE_M + quarter * 32;
-            for (int c0 = 0; c0 < a.Nn; c0 += 64) {
-                const int width = min(64, a.Nn - c0);                            // 16, 32, 48 or 64 columns (warp-uniform)
-                for (int h = 0; h < width; h += 32) {
-                    uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)lane * EPI_PITCH + h * 2);
-                    if (width - h >= 32) {
-                        uint32_t r[32];
-                        tmem_ld_32x32b_x32(taddr + (uint32_t)(c0 + h), r);
-                        tmem_ld_wait();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * SET_COLS);
+            const int jc_n = min(4, (a.p - nch * 32 + 7) / 8);                   // 8-block column groups with at least one real block
+            for (int jc = 0; jc < jc_n; ++jc) {
+                uint32_t r[4][16];
 #pragma unroll
-                        for (int v = 0; v < 4; ++v)
-                            dst[v] = make_uint4(pack_bf16(__uint_as_float(r[8 * v + 0]), __uint_as_float(r[8 * v + 1])), pack_bf16(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3])),
-                                                pack_bf16(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5])), pack_bf16(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7])));
-                    } else {
-                        uint32_t r[16];
-                        tmem_ld_32x32b_x16(taddr + (uint32_t)(c0 + h), r);
-                        tmem_ld_wait();
+                for (int fl = 0; fl < 4; ++fl) tmem_ld_32x32b_x16(taddr + (uint32_t)(fl * NCHUNK + jc * 16), r[fl]);
+                tmem_ld_wait();
+                if (jc == jc_n - 1) {                                            // accumulators fully read: hand the set back to the MMA warp
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->tmem_empty[set]);
+                }
+                if (lane == 0) tma_store_wait_read<1>();                         // the store that last read this buffer has finished
+                __syncwarp();
+                uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)buf * EPI_BUF_BYTES) + lane;
 #pragma unroll
-                        for (int v = 0; v < 2; ++v)
-                            dst[v] = make_uint4(pack_bf16(__uint_as_float(r[8 * v + 0]), __uint_as_float(r[8 * v + 1])), pack_bf16(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3])),
-                                                pack_bf16(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5])), pack_bf16(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7])));
-                    }
-                }
+                for (int jj = 0; jj < 8; ++jj)
+                    dst[jj * 32] = make_uint4(pack_bf16(__uint_as_float(r[0][2 * jj]), __uint_as_float(r[0][2 * jj + 1])),
+                                              pack_bf16(__uint_as_float(r[1][2 * jj]), __uint_as_float(r[1][2 * jj + 1])),
+                                              pack_bf16(__uint_as_float(r[2][2 * jj]), __uint_as_float(r[2][2 * jj + 1])),
+                                              pack_bf16(__uint_as_float(r[3][2 * jj]), __uint_as_float(r[3][2 * jj + 1])));
+                fence_proxy_async_smem();
                 __syncwarp();
-                const int nch = width / 8;                                       // 16-byte chunks per row
-                for (int id = lane; id < 32 * nch; id += 32) {
-                    const int r = id / nch, cc = id - r * nch;
-                    const int tok = tok0 + r, col = nc * a.Nn + c0 + cc * 8;
-                    if (tok < a.ntok && col < a.Np)
-                        *reinterpret_cast<uint4*>(a.Yf + ((size_t)f * a.ntok + tok) * a.Np + col) = *reinterpret_cast<const uint4*>(stg + (size_t)r * EPI_PITCH + cc * 16);
+                if (lane == 0) {
+                    tma_store_4d(&tmY, 0, m * TILE_M + quarter * 32, nch * 32 + jc * 8, fg, stg + (size_t)buf * EPI_BUF_BYTES);
+                    tma_store_commit();
                 }
-                __syncwarp();
+                buf ^= 1;
             }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
         }
+        if (lane == 0) tma_store_wait<0>();
     }
 done:
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * ACC_COLS);
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * SET_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// stage 3: gather a token's output spectra from the per-frequency rows, inverse rfft, reference epilogue
+// CUDA-core stage 3: gather a token's output spectra from the 16-byte chunks, inverse rfft, reference epilogue
 // ---------------------------------------------------------------------------------------------------------
 template <int B, int NT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) irfft_rows_kernel(const __grid_constant__ ProblemDev P, int64_t n_begin, int nc,
-                                                                 const __nv_bfloat16* __restrict__ Yf, int Np) {
+                                                                 const __nv_bfloat16* __restrict__ Yf) {
     using SM = RowsSmem<B, NT, WARPS>;
     using C = FftCfg<B>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tw = reinterpret_cast<float2*>(smem_raw);
-    float2* fscr_all = reinterpret_cast<float2*>(smem_raw + SM::tw_bytes);
-    float* ys = reinterpret_cast<float*>(smem_raw + SM::tw_bytes + SM::fscr_bytes);
+    extern __shared__ __align__(16) unsigned char rows_smem[];
+    float2* tw = reinterpret_cast<float2*>(rows_smem);
+    float2* fscr_all = reinterpret_cast<float2*>(rows_smem + SM::tw_bytes);
+    float* ys = reinterpret_cast<float*>(rows_smem + SM::tw_bytes + SM::fscr_bytes);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     fill_twiddles<B>(tw, threadIdx.x, WARPS * 32);
     const int p = P.p;
     const int t0 = blockIdx.x * NT;
-    constexpr int F = B / 2;
-    for (int row = warp; row < F * NT; row += WARPS) {                  // one warp reads one (f, token) row: Np bf16, contiguous
-        const int n = row % NT, f = row / NT;
+    constexpr int FG = B / 8;
+    const int nchunks = FG * p * NT;                                    // one 16-byte chunk = (fg, j, token): 4 frequencies x {re,im}
+    for (int id = threadIdx.x; id < nchunks; id += WARPS * 32) {
+        const int n = id % NT;
+        const int j = (id / NT) % p;
+        const int fg = id / (NT * p);
         if (t0 + n >= nc) continue;
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(Yf + ((size_t)f * nc + (t0 + n)) * Np);
-        for (int j = lane; j < p; j += 32)
-            *reinterpret_cast<float2*>(ys + ((size_t)n * p + j) * SM::PITCH + 2 * f) = unpack_bf16(__ldg(src + j));
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(Yf + (((size_t)fg * p + j) * nc + (t0 + n)) * 8));
+        float2* dst = reinterpret_cast<float2*>(ys + ((size_t)n * p + j) * SM::PITCH + 8 * fg);
+        dst[0] = unpack_bf16(w.x); dst[1] = unpack_bf16(w.y); dst[2] = unpack_bf16(w.z); dst[3] = unpack_bf16(w.w);
     }
     __syncthreads();
     float2* fscr = fscr_all + (size_t)warp * (C::WARP_SCRATCH_BYTES / 8);
@@ -333,25 +344,19 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// bf16 tensor [d2][d1][d0] (d0 contiguous), box 64 x box_rows x 1, 128-byte swizzle, zero fill out of bounds
-static bool make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box_rows) {
+bool make_tensor_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box, CUtensorMapSwizzle swz) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
-    cuuint64_t dims[3] = {d0, d1, d2};
-    cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
-    cuuint32_t box[3] = {KATOM, box_rows, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], es[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides[i];
+    return fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static size_t gemm_smem_bytes(int Nn, int stages) { return 512 + 4 * 32 * EPI_PITCH + 1024 + (size_t)stages * (TILE_M * KATOM * 2 + (size_t)Nn * KATOM * 2); }
-
-static int pick_gemm_stages(int Nn) {
-    int s = MAX_STAGES;
-    while (s > 2 && gemm_smem_bytes(Nn, s) > 220 * 1024) --s;
-    return s;
-}
+static size_t gemm_smem_bytes(int stages) { return 1024 + 4 * 2 * EPI_BUF_BYTES + (size_t)stages * STAGE_BYTES; }
 
 template <typename K> static cudaError_t set_smem(K kernel, size_t bytes) {
     if (bytes <= 48 * 1024) return cudaSuccess;
@@ -359,24 +364,24 @@ template <typename K> static cudaError_t set_smem(K kernel, size_t bytes) {
 }
 
 template <int B, int NT>
-static cudaError_t launch_rfft_rows_t(const ProblemDev& P, int64_t n_begin, int nc, void* Xf, int Kp, cudaStream_t st) {
+static cudaError_t launch_rfft_rows_t(const ProblemDev& P, int64_t n_begin, int nc, void* Xf, int KG, cudaStream_t st) {
     constexpr int WARPS = 8;
     auto kern = rfft_rows_kernel<B, NT, WARPS>;
     const size_t smem = RowsSmem<B, NT, WARPS>::bytes(P.q);
     cudaError_t e = set_smem(kern, smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)((nc + NT - 1) / NT), WARPS * 32, smem, st>>>(P, n_begin, nc, reinterpret_cast<__nv_bfloat16*>(Xf), Kp);
+    kern<<<(unsigned)((nc + NT - 1) / NT), WARPS * 32, smem, st>>>(P, n_begin, nc, reinterpret_cast<__nv_bfloat16*>(Xf), KG);
     return cudaGetLastError();
 }
 
 template <int B, int NT>
-static cudaError_t launch_irfft_rows_t(const ProblemDev& P, int64_t n_begin, int nc, const void* Yf, int Np, cudaStream_t st) {
+static cudaError_t launch_irfft_rows_t(const ProblemDev& P, int64_t n_begin, int nc, const void* Yf, cudaStream_t st) {
     constexpr int WARPS = 8;
     auto kern = irfft_rows_kernel<B, NT, WARPS>;
     const size_t smem = RowsSmem<B, NT, WARPS>::bytes(P.p);
     cudaError_t e = set_smem(kern, smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)((nc + NT - 1) / NT), WARPS * 32, smem, st>>>(P, n_begin, nc, reinterpret_cast<const __nv_bfloat16*>(Yf), Np);
+    kern<<<(unsigned)((nc + NT - 1) / NT), WARPS * 32, smem, st>>>(P, n_begin, nc, reinterpret_cast<const __nv_bfloat16*>(Yf));
     return cudaGetLastError();
 }
 
@@ -385,29 +390,34 @@ static int rows_nt(int blocks, int B) { return (size_t)2 * blocks * (B + 2) * 4 
 
 }  // namespace gemm
 
-size_t gemm_spectrum_bytes(int p, int q, int B) {
-    const gemm::Geometry g = gemm::geometry(p, q, B);
-    return (size_t)g.F * g.Np * g.Kp * 2;
-}
+size_t gemm_spectrum_bytes(int p, int q, int B) { return gemm::geometry(p, q, B).total_bytes; }
 
 // workspace = [256-byte status area | Xf chunk | Yf chunk]; chunk tokens chosen so both stay L2-resident
 static constexpr size_t kWsHeader = 256;
-static constexpr size_t kChunkBudget = 48u << 20;
 
-static size_t per_token_ws(const gemm::Geometry& g) { return (size_t)g.F * (g.Kp + g.Np) * 2; }
+static size_t chunk_budget() {
+    static size_t v = 0;
+    if (!v) {
+        const char* e = getenv("BCL_PREFILL_CHUNK_MB");
+        const long mb = e ? atol(e) : 0;
+        v = (size_t)(mb > 0 ? mb : 56) << 20;
+    }
+    return v;
+}
+
+static size_t per_token_ws(const gemm::Geometry& g) { return (size_t)g.F * (g.Kp + 2 * g.p) * 2; }
 
 int64_t gemm_chunk_tokens(int64_t N, int p, int q, int B, size_t workspace_bytes) {
     const gemm::Geometry g = gemm::geometry(p, q, B);
     if (workspace_bytes <= kWsHeader + 512) return 0;
     int64_t nc = (int64_t)((workspace_bytes - kWsHeader - 512) / per_token_ws(g));
     if (nc >= N) return N;
-    nc = nc / gemm::TILE_M * gemm::TILE_M;
-    return nc;
+    return nc / gemm::TILE_M * gemm::TILE_M;
 }
 
 size_t gemm_workspace_bytes(int64_t N, int p, int q, int B) {
     const gemm::Geometry g = gemm::geometry(p, q, B);
-    int64_t nc = (int64_t)(kChunkBudget / per_token_ws(g)) / gemm::TILE_M * gemm::TILE_M;
+    int64_t nc = (int64_t)(chunk_budget() / per_token_ws(g)) / gemm::TILE_M * gemm::TILE_M;
     if (nc < gemm::TILE_M) nc = gemm::TILE_M;
     if (nc > N) nc = N;
     return kWsHeader + 512 + (size_t)nc * per_token_ws(g);
@@ -416,6 +426,11 @@ size_t gemm_workspace_bytes(int64_t N, int p, int q, int B) {
 cudaError_t launch_spectrum_gemm(const float* c, void* spec, int p, int q, int B, cudaStream_t st) {
     const gemm::Geometry g = gemm::geometry(p, q, B);
     constexpr int WARPS = 8;
+    unsigned char* base = reinterpret_cast<unsigned char*>(spec);
+    gemm::dft_matrix_kernel<<<B, B, 0, st>>>(B, reinterpret_cast<__half*>(base + g.wf16_off), reinterpret_cast<__nv_bfloat16*>(base + g.wbf16_off),
+                                            reinterpret_cast<__nv_bfloat16*>(base + g.winv_off));
+    cudaError_t e0 = cudaGetLastError();
+    if (e0 != cudaSuccess) return e0;
 #define BCL_SG(BB)                                                                                                         \
     {                                                                                                                      \
         auto kern = gemm::spectrum_gemm_kernel<BB, WARPS>;                                                                  \
@@ -432,38 +447,52 @@ cudaError_t launch_spectrum_gemm(const float* c, void* spec, int p, int q, int B
 cudaError_t launch_gemm_rfft(const ProblemDev& P, int B, int64_t n_begin, int nc, void* Xf, cudaStream_t st) {
     const gemm::Geometry g = gemm::geometry(P.p, P.q, B);
     const int nt = gemm::rows_nt(P.q, B);
-#define BCL_R1(BB) (nt == 2 ? gemm::launch_rfft_rows_t<BB, 2>(P, n_begin, nc, Xf, g.Kp, st) : gemm::launch_rfft_rows_t<BB, 1>(P, n_begin, nc, Xf, g.Kp, st))
+#define BCL_R1(BB) (nt == 2 ? gemm::launch_rfft_rows_t<BB, 2>(P, n_begin, nc, Xf, g.KG, st) : gemm::launch_rfft_rows_t<BB, 1>(P, n_begin, nc, Xf, g.KG, st))
     switch (B) { case 64: return BCL_R1(64); case 128: return BCL_R1(128); default: return BCL_R1(256); }
 #undef BCL_R1
 }
 
 cudaError_t launch_gemm_irfft(const ProblemDev& P, int B, int64_t n_begin, int nc, const void* Yf, cudaStream_t st) {
-    const gemm::Geometry g = gemm::geometry(P.p, P.q, B);
     const int nt = gemm::rows_nt(P.p, B);
-#define BCL_R3(BB) (nt == 2 ? gemm::launch_irfft_rows_t<BB, 2>(P, n_begin, nc, Yf, g.Np, st) : gemm::launch_irfft_rows_t<BB, 1>(P, n_begin, nc, Yf, g.Np, st))
+#define BCL_R3(BB) (nt == 2 ? gemm::launch_irfft_rows_t<BB, 2>(P, n_begin, nc, Yf, st) : gemm::launch_irfft_rows_t<BB, 1>(P, n_begin, nc, Yf, st))
     switch (B) { case 64: return BCL_R3(64); case 128: return BCL_R3(128); default: return BCL_R3(256); }
 #undef BCL_R3
 }
 
-// Xf [F][nc][Kp], Cmat [F][Np][Kp] -> Yf [F][nc][Np].  status: device int, set non-zero if a pipeline wait timed out.
+// Xf [F][KG][nc][8], Cmat [F][Np][Kp] -> Yf [FG][p][nc][8].  status: device int, set non-zero if a pipeline wait timed out.
 cudaError_t launch_gemm_mma(const void* Xf, const void* Cmat, void* Yf, int* status, int p, int q, int B, int nc, int max_ctas, cudaStream_t st) {
     const gemm::Geometry g = gemm::geometry(p, q, B);
-    CUtensorMap tmA, tmB;
-    if (!gemm::make_map(&tmA, Xf, (uint64_t)g.Kp, (uint64_t)nc, (uint64_t)g.F, gemm::TILE_M)) return cudaErrorNotSupported;
-    if (!gemm::make_map(&tmB, Cmat, (uint64_t)g.Kp, (uint64_t)g.Np, (uint64_t)g.F, (uint32_t)g.Nn)) return cudaErrorNotSupported;
+    CUtensorMap tmA, tmB, tmY;
+    {
+        const uint64_t dims[4] = {8, (uint64_t)nc, (uint64_t)g.KG, (uint64_t)g.F};
+        const uint64_t strides[3] = {16, (uint64_t)nc * 16, (uint64_t)g.KG * nc * 16};
+        const uint32_t box[4] = {8, gemm::TILE_M, 8, 1};
+        if (!gemm::make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, Xf, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorNotSupported;
+    }
+    {
+        const uint64_t dims[3] = {(uint64_t)g.Kp, (uint64_t)g.Np, (uint64_t)g.F};
+        const uint64_t strides[2] = {(uint64_t)g.Kp * 2, (uint64_t)g.Kp * g.Np * 2};
+        const uint32_t box[3] = {gemm::KATOM, gemm::NCHUNK, 1};
+        if (!gemm::make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Cmat, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return cudaErrorNotSupported;
+    }
+    {
+        const uint64_t dims[4] = {8, (uint64_t)nc, (uint64_t)p, (uint64_t)g.FG};
+        const uint64_t strides[3] = {16, (uint64_t)nc * 16, (uint64_t)p * nc * 16};
+        const uint32_t box[4] = {8, 32, 8, 1};
+        if (!gemm::make_tensor_map(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, Yf, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorNotSupported;
+    }
     gemm::GemmArgs a{};
-    a.Yf = reinterpret_cast<__nv_bfloat16*>(Yf);
     a.status = status;
-    a.ntok = nc; a.F = g.F; a.Kp = g.Kp; a.Np = g.Np; a.Nn = g.Nn; a.n_chunks = g.n_chunks; a.k_atoms = g.k_atoms;
+    a.ntok = nc; a.p = p; a.KG = g.KG; a.k_atoms = (g.Kp + gemm::KATOM - 1) / gemm::KATOM; a.NCH = g.NCH;
     a.m_tiles = (nc + gemm::TILE_M - 1) / gemm::TILE_M;
-    a.num_tiles = a.m_tiles * g.F * g.n_chunks;
-    a.stages = gemm::pick_gemm_stages(g.Nn);
-    const size_t smem = gemm::gemm_smem_bytes(g.Nn, a.stages);
+    a.num_items = a.m_tiles * g.FG * g.NCH;
+    a.stages = gemm::MAX_STAGES;
+    const size_t smem = gemm::gemm_smem_bytes(a.stages);
     cudaError_t e = cudaFuncSetAttribute(gemm::freq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int grid = a.num_tiles < max_ctas ? a.num_tiles : max_ctas;
+    const int grid = a.num_items < max_ctas ? a.num_items : max_ctas;
     if (grid < 1) return cudaSuccess;
-    gemm::freq_gemm_kernel<<<(unsigned)grid, gemm::GEMM_THREADS, smem, st>>>(tmA, tmB, a);
+    gemm::freq_gemm_kernel<<<(unsigned)grid, gemm::GEMM_THREADS, smem, st>>>(tmA, tmB, tmY, a);
     return cudaGetLastError();
 }
 
@@ -473,22 +502,40 @@ static int sm_count() {
     return n > 0 ? n : 148;
 }
 
-cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* Cmat, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+// impl: 0 = pick (tensor-core DFT when supported), 1 = CUDA-core FFT kernels, 2 = tensor-core DFT kernels (error if unsupported)
+cudaError_t launch_prefill_stage1(const ProblemDev& P, int B, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, int impl, cudaStream_t st) {
+    const gemm::Geometry g = gemm::geometry(P.p, P.q, B);
+    const bool tc_ok = gemm::dft_tc_supported(B, P.x_dtype) && spec_gemm != nullptr;
+    if (impl == 2 && !tc_ok) return cudaErrorNotSupported;
+    if (impl != 1 && tc_ok) return gemm::launch_dft_fwd_tc(P, g, spec_gemm, n_begin, nc, Xf, status, sm_count(), st);
+    return launch_gemm_rfft(P, B, n_begin, nc, Xf, st);
+}
+
+cudaError_t launch_prefill_stage3(const ProblemDev& P, int B, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, int impl, cudaStream_t st) {
+    const gemm::Geometry g = gemm::geometry(P.p, P.q, B);
+    const bool tc_ok = gemm::dft_tc_supported(B, P.x_dtype) && P.y_dtype == P.x_dtype && spec_gemm != nullptr;
+    if (impl == 2 && !tc_ok) return cudaErrorNotSupported;
+    if (impl != 1 && tc_ok) return gemm::launch_dft_inv_tc(P, g, spec_gemm, n_begin, nc, Yf, status, sm_count(), st);
+    return launch_gemm_irfft(P, B, n_begin, nc, Yf, st);
+}
+
+cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gemm, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     const gemm::Geometry g = gemm::geometry(P.p, P.q, B);
     const int64_t ncmax = gemm_chunk_tokens(P.N, P.p, P.q, B, workspace_bytes);
     if (ncmax < 1) return cudaErrorInvalidValue;
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     int* status = reinterpret_cast<int*>(ws);
     unsigned char* Xf = ws + kWsHeader;
-    unsigned char* Yf = Xf + (((size_t)g.F * ncmax * g.Kp * 2 + 255) & ~(size_t)255);
+    unsigned char* Yf = Xf + ((gemm::xf_bytes(g, ncmax) + 255) & ~(size_t)255);
     cudaError_t e = cudaMemsetAsync(status, 0, kWsHeader, st);
     if (e != cudaSuccess) return e;
+    static const int impl = getenv("BCL_PREFILL_DFT") ? atoi(getenv("BCL_PREFILL_DFT")) : 0;       // A/B switch for profiling only
     const int ctas = sm_count();
     for (int64_t n0 = 0; n0 < P.N; n0 += ncmax) {
         const int nc = (int)((P.N - n0 < ncmax) ? (P.N - n0) : ncmax);
-        if ((e = launch_gemm_rfft(P, B, n0, nc, Xf, st)) != cudaSuccess) return e;
-        if ((e = launch_gemm_mma(Xf, Cmat, Yf, status, P.p, P.q, B, nc, ctas, st)) != cudaSuccess) return e;
-        if ((e = launch_gemm_irfft(P, B, n0, nc, Yf, st)) != cudaSuccess) return e;
+        if ((e = launch_prefill_stage1(P, B, spec_gemm, n0, nc, Xf, status, impl, st)) != cudaSuccess) return e;
+        if ((e = launch_gemm_mma(Xf, spec_gemm, Yf, status, P.p, P.q, B, nc, ctas, st)) != cudaSuccess) return e;
+        if ((e = launch_prefill_stage3(P, B, spec_gemm, n0, nc, Yf, status, impl, st)) != cudaSuccess) return e;
     }
     return cudaSuccess;
 }

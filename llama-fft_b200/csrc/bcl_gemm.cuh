@@ -1,0 +1,66 @@
+// bcl_gemm.cuh -- geometry and intermediate layouts of the prefill (large-N) path, shared by bcl_gemm.cu (per-frequency
+// tcgen05 GEMM, CUDA-core FFT stages, spectrum precompute, chunked chaining) and bcl_dft_tc.cu (DFT-as-GEMM stages).
+//
+// Everything between the stages is bf16 and laid out so that BOTH the producer's stores and the consumer's TMA loads are
+// runs of whole 16-byte chunks:
+//   Xf  [F][KG][ntok][8]      Xf[f][kg][n][k0],  k = 8 kg + k0 = 2 i + {re,im}          (A operand of the frequency GEMM)
+//   Yf  [FG][p][ntok][8]      Yf[fg][j][n][2 fl + {re,im}],  f = 4 fg + fl               (A operand of the inverse DFT)
+//   GEMM-layout spectrum buffer:
+//     Cmat [F][Np][Kp]        K-major rows, n = 2 j + {re,im} (Np = 2p rounded up to 64), k as above (Kp = 2q rounded up to 16)
+//     Wfwd fp16, Wfwd bf16    [B][B]  row r = packed spectrum real (0: DC, 1: Nyquist, 2f: Re, 2f+1: Im), column t   (forward DFT)
+//     Winv bf16               [B][B]  row t, column r, 1/B scaling folded in                                          (inverse DFT)
+// F = B/2 packed frequency slots, FG = F/4, KG = Kp/8.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "bcl_kernels.h"
+
+namespace bcl {
+namespace gemm {
+
+constexpr int TILE_M = 128;          // tokens per MMA tile (UMMA M)
+constexpr int KATOM = 64;            // 16-bit elements per 128-byte swizzle row
+constexpr int NCHUNK = 64;           // columns (= 32 output blocks) of one frequency-GEMM tile
+
+struct Geometry {
+    int B, p, q;
+    int F, FG, Kp, KG, Np, NCH;
+    size_t cmat_bytes, wf16_off, wbf16_off, winv_off, total_bytes;
+};
+
+__host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+__host__ inline Geometry geometry(int p, int q, int B) {
+    Geometry g;
+    g.B = B; g.p = p; g.q = q;
+    g.F = B / 2;
+    g.FG = g.F / 4;
+    g.Kp = round_up(2 * q, 16);
+    g.KG = g.Kp / 8;
+    g.Np = round_up(2 * p, NCHUNK);
+    g.NCH = g.Np / NCHUNK;
+    g.cmat_bytes = ((size_t)g.F * g.Np * g.Kp * 2 + 1023) & ~(size_t)1023;
+    g.wf16_off = g.cmat_bytes;
+    g.wbf16_off = g.wf16_off + (size_t)B * B * 2;
+    g.winv_off = g.wbf16_off + (size_t)B * B * 2;
+    g.total_bytes = g.winv_off + (size_t)B * B * 2;
+    return g;
+}
+
+inline size_t xf_bytes(const Geometry& g, int64_t ntok) { return (size_t)g.F * g.Kp * ntok * 2; }
+inline size_t yf_bytes(const Geometry& g, int64_t ntok) { return (size_t)g.F * 2 * g.p * ntok * 2; }
+
+// Tensor-map helper (cuTensorMapEncodeTiled through the runtime's driver entry point; no libcuda link dependency).
+// dims/strides innermost first; strides[i] = byte stride of dimension i+1.
+bool make_tensor_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box, CUtensorMapSwizzle swz);
+
+// DFT-as-GEMM stages on tcgen05 (bcl_dft_tc.cu).  B in {64, 128}; 16-bit activations.
+bool dft_tc_supported(int B, int act_dtype);
+cudaError_t launch_dft_fwd_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, int max_ctas, cudaStream_t st);
+cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, int max_ctas, cudaStream_t st);
+
+}  // namespace gemm
+}  // namespace bcl

@@ -49,6 +49,8 @@ cudaError_t launch_spectrum_gemm(const float* c, void* spec, int p, int q, int B
 cudaError_t launch_gemm_rfft(const ProblemDev& P, int B, int64_t n_begin, int nc, void* Xf, cudaStream_t st);
 cudaError_t launch_gemm_mma(const void* Xf, const void* Cmat, void* Yf, int* status, int p, int q, int B, int nc, int max_ctas, cudaStream_t st);
 cudaError_t launch_gemm_irfft(const ProblemDev& P, int B, int64_t n_begin, int nc, const void* Yf, cudaStream_t st);
+cudaError_t launch_prefill_stage1(const ProblemDev& P, int B, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, int impl, cudaStream_t st);
+cudaError_t launch_prefill_stage3(const ProblemDev& P, int B, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, int impl, cudaStream_t st);
 cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* Cmat, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 cudaError_t launch_project_from_dense(const void* W, int w_dtype, int64_t w_stride, int p, int q, int B, float* c, cudaStream_t st);

@@ -31,7 +31,7 @@ __device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
 // Bounded wait: a protocol bug must surface as an error flag, never as a hung GPU (a hung box is a lost lease).
 // Returns false when the phase has not completed after ~2 s; callers then set the kernel's status word and bail out.
 __device__ __forceinline__ uint64_t global_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-__device__ __noinline__ bool mbar_wait_slow(uint32_t addr, uint32_t parity) {
+static __device__ __noinline__ bool mbar_wait_slow(uint32_t addr, uint32_t parity) {
     const uint64_t t0 = global_ns();
 #pragma unroll 1
     for (uint32_t spin = 0;; ++spin) {
@@ -62,6 +62,29 @@ __device__ __forceinline__ void tma_load_3d(void* dst_smem, const void* tmap, in
                  ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
                  : "memory");
 }
+
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+                 : "memory");
+}
+// Tiled stores shared -> global (bulk async-group completion).  Writes outside the tensor's bounds are dropped.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, const void* src_smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(src_smem)) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, int c0, int c1, int c2, int c3, const void* src_smem) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(src_smem)) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- TMEM ---------------------------------------------------------------------------------------------------------
 // One full warp allocates `ncols` (power of two >= 32) columns; the base address lands in *slot (shared memory).
@@ -112,10 +135,25 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// K-major operand WITHOUT swizzle ("interleaved" canonical layout): core matrices of 8 rows x 16 bytes stored contiguously
+// (128 bytes); sbo = byte distance between consecutive 8-row groups, lbo = byte distance between the two core matrices
+// that are adjacent along K.  One UMMA_K (16 x 16-bit) spans two core matrices, so a k-step advances the start by 2*lbo.
+__device__ __forceinline__ uint64_t umma_desc_k_nosw(uint32_t smem_addr, uint32_t sbo, uint32_t lbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
 // Instruction descriptor, kind::f16: D fp32 (bits 4-5 = 1), A and B bf16 (bits 7-9, 10-12 = 1), both K-major
 // (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// same with A and B both fp16 (format code 0) or both bf16 (format code 1)
+__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, int is_bf16) {
+    return (1u << 4) | ((uint32_t)is_bf16 << 7) | ((uint32_t)is_bf16 << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread on behalf of the CTA.
 __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {

@@ -163,8 +163,8 @@ class BlockCirculantLinear(nn.Module):
         else:
             if self.spectrum_dtype != torch.bfloat16:
                 raise ValueError("the GEMM (tcgen05 prefill) spectrum layout is bf16 only")
-            F, Kp, Np = _cabi.prefill_geometry(self.out_blocks, self.in_blocks, self.block_size)
-            spec = torch.empty(F, Np, Kp, device=c.device, dtype=torch.bfloat16)
+            nbytes = L.bcl_spectrum_bytes(self.out_blocks, self.in_blocks, self.block_size, _cabi.BF16, layout)
+            spec = torch.empty(nbytes, device=c.device, dtype=torch.uint8)      # Cmat + DFT matrices (include/bclinear.h)
         with torch.cuda.device(c.device):
             rc = L.bcl_precompute_spectrum(c32.data_ptr(), self.out_blocks, self.in_blocks, self.block_size,
                                            spec.data_ptr(), _cabi.DTYPE[self.spectrum_dtype], layout,
@@ -244,13 +244,14 @@ def bc_forward(x_flat: torch.Tensor, spec: torch.Tensor, bias: Optional[torch.Te
     y = out if out is not None else torch.empty(N, p * B, device=x_flat.device, dtype=y_dtype)
     L = _cabi.lib()
     ws_ptr, ws_bytes = None, 0
+    spec_dt = _cabi.BF16 if layout == _cabi.LAYOUT_GEMM else _cabi.DTYPE[spec.dtype]
     if layout == _cabi.LAYOUT_GEMM and N > 0:
-        ws_bytes = L.bcl_workspace_bytes(N, p, q, B, _cabi.DTYPE[spec.dtype], layout)
+        ws_bytes = L.bcl_workspace_bytes(N, p, q, B, spec_dt, layout)
         ws = prefill_workspace(x_flat.device, ws_bytes)
         ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
     with torch.cuda.device(x_flat.device):
         rc = L.bcl_forward(x_flat.data_ptr(), _cabi.DTYPE[x_flat.dtype], N, x_flat.stride(0),
-                           spec.data_ptr(), _cabi.DTYPE[spec.dtype], layout, p, q, B,
+                           spec.data_ptr(), spec_dt, layout, p, q, B,
                            None if bias is None else bias.data_ptr(), 0 if bias is None else _cabi.DTYPE[bias.dtype],
                            y.data_ptr(), _cabi.DTYPE[y_dtype], y.stride(0), ws_ptr, ws_bytes, _cabi.stream_ptr(x_flat.device))
     _cabi.check(rc, "bcl_forward")

@@ -9,7 +9,7 @@ import torch
 
 import llama_fft_b200 as bc
 from llama_fft_b200 import _cabi
-from llama_fft_b200 import patch_llama_fft as P
+from llama_fft_b200.patch_llama_fft import bc_forward, prefill_status
 from oracle import bc_oracle as O
 from tests import _golden as G
 
@@ -39,10 +39,22 @@ def assert_close(y, y_ref, tol, io_dtype=torch.float32, mag=None):
     assert not bool(torch.as_tensor(bad).any()), f"max rel err {(yd - rd).abs().max().item() / scale:.3e} (tol {tol})"
 
 
+def geom(p, q, B):
+    F, Kp, Np = _cabi.prefill_geometry(p, q, B)
+    return F, Kp, Np, Kp // 8, F // 4
+
+
+def gemm_spec(m):
+    """(whole GEMM-layout buffer, its Cmat part viewed as (F, Np, Kp) bf16)."""
+    buf = m.build_spectrum(layout=_cabi.LAYOUT_GEMM)
+    F, Kp, Np, _, _ = geom(m.out_blocks, m.in_blocks, m.block_size)
+    return buf, buf[:F * Np * Kp * 2].view(BF).view(F, Np, Kp)
+
+
 def ref_cmat(c):
     """The GEMM-layout spectrum from torch.fft.rfft(c) (reference :256-257), fp64: [F][Np][Kp]."""
     p, q, B = c.shape
-    F, Kp, Np = _cabi.prefill_geometry(p, q, B)
+    F, Kp, Np, _, _ = geom(p, q, B)
     Cf = torch.fft.rfft(c.double(), dim=-1)                      # (p,q,B/2+1)
     M = torch.zeros(F, Np, Kp, dtype=torch.float64)
     cr, ci = Cf.real[..., :F].permute(2, 0, 1), Cf.imag[..., :F].permute(2, 0, 1)     # (F,p,q)
@@ -56,8 +68,30 @@ def ref_cmat(c):
     return M
 
 
+def xf_natural(Xf_chunks):
+    """stage layout [F][KG][N][8] -> [F][N][Kp]"""
+    F, KG, N, _ = Xf_chunks.shape
+    return Xf_chunks.permute(0, 2, 1, 3).reshape(F, N, KG * 8)
+
+
+def xf_chunks(Xf_nat):
+    F, N, Kp = Xf_nat.shape
+    return Xf_nat.reshape(F, N, Kp // 8, 8).permute(0, 2, 1, 3).contiguous()
+
+
+def yf_natural(Yf_chunks):
+    """stage layout [FG][p][N][8] (8 = 4 frequencies x {re,im}) -> [F][N][2p]"""
+    FG, p, N, _ = Yf_chunks.shape
+    return Yf_chunks.reshape(FG, p, N, 4, 2).permute(0, 3, 2, 1, 4).reshape(FG * 4, N, 2 * p)
+
+
+def yf_chunks(Yf_nat, p):
+    F, N, _ = Yf_nat.shape
+    return Yf_nat[:, :, :2 * p].reshape(F // 4, 4, N, p, 2).permute(0, 3, 2, 1, 4).reshape(F // 4, p, N, 8).contiguous()
+
+
 def ref_xf(x, q, B, Kp):
-    """rfft(x) (reference :252) in the stage layout [F][N][Kp], fp64."""
+    """rfft(x) (reference :252), natural layout [F][N][Kp], fp64."""
     N = x.shape[0]
     F = B // 2
     Xf = torch.fft.rfft(x.double().view(N, q, B), dim=-1)       # (N,q,F+1)
@@ -68,33 +102,68 @@ def ref_xf(x, q, B, Kp):
     return out
 
 
+def new_status():
+    return torch.zeros(1, device=DEV, dtype=torch.int32)
+
+
 @pytest.mark.parametrize("p,q,B", [(3, 5, 64), (32, 32, 128), (86, 32, 128), (4, 9, 256)])
 def test_gemm_layout_spectrum_matches_rfft(p, q, B):
     g = torch.Generator().manual_seed(p * 100 + q + B)
     c = torch.randn(p, q, B, generator=g)
     m = make_layer(c)
-    spec = m.build_spectrum(layout=_cabi.LAYOUT_GEMM)
-    F, Kp, Np = _cabi.prefill_geometry(p, q, B)
-    assert spec.shape == (F, Np, Kp) and spec.dtype == BF
+    buf, spec = gemm_spec(m)
+    assert buf.numel() == _cabi.lib().bcl_spectrum_bytes(p, q, B, _cabi.BF16, _cabi.LAYOUT_GEMM)
     ref = ref_cmat(c)
     got = spec.double().cpu()
     assert (got - ref).abs().max() <= 2.0 ** -8 * ref.abs().max()
     assert (got[:, 2 * p:, :] == 0).all() and (got[:, :, 2 * q:] == 0).all()         # zero padding is what the MMA multiplies
+    # the DFT matrices behind Cmat: forward rows = packed spectrum reals, inverse = its scaled transpose
+    o16, obf, oinv = _cabi.prefill_dft_offsets(p, q, B)
+    wf = buf[o16:o16 + B * B * 2].view(torch.float16).view(B, B).double().cpu()
+    wb = buf[obf:obf + B * B * 2].view(BF).view(B, B).double().cpu()
+    wi = buf[oinv:oinv + B * B * 2].view(BF).view(B, B).double().cpu()
+    eye = torch.eye(B, dtype=torch.float64)
+    Fm = torch.fft.rfft(eye, dim=-1)                              # row t: spectrum of e_t
+    Wref = torch.zeros(B, B, dtype=torch.float64)
+    Wref[0], Wref[1] = Fm.real[:, 0], Fm.real[:, B // 2]
+    Wref[2::2], Wref[3::2] = Fm.real[:, 1:B // 2].T, Fm.imag[:, 1:B // 2].T
+    assert (wf - Wref).abs().max() <= 2.0 ** -11 and (wb - Wref).abs().max() <= 2.0 ** -8
+    assert ((wi @ Wref) - eye).abs().max() <= 2e-2                # Winv * Wfwd = I up to bf16 rounding of both
 
 
-@pytest.mark.parametrize("q,B,N,dtype", [(5, 64, 7, torch.float32), (32, 128, 200, torch.float16), (86, 128, 33, torch.bfloat16), (9, 256, 130, torch.float32)])
-def test_stage_rfft_rows(q, B, N, dtype):
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("q,B,N,dtype", [(5, 64, 7, torch.float32), (32, 128, 200, torch.float16), (86, 128, 33, torch.bfloat16),
+                                         (9, 256, 130, torch.float32), (5, 64, 300, torch.float16), (32, 128, 1024, torch.bfloat16)])
+def test_stage_rfft(q, B, N, dtype, impl):
+    if impl == 2 and (B == 256 or dtype == torch.float32):
+        pytest.skip("tensor-core DFT covers B <= 128 with 16-bit activations")
     g = torch.Generator().manual_seed(q + B + N)
     x = torch.randn(N, q * B, generator=g).to(dtype)
-    F, Kp, _ = _cabi.prefill_geometry(1, q, B)
-    Xf = torch.full((F, N, Kp), float("nan"), device=DEV, dtype=BF)
+    p = 3
+    m = make_layer(torch.randn(p, q, B, generator=g))
+    buf, _ = gemm_spec(m)
+    F, Kp, Np, KG, FG = geom(p, q, B)
+    Xf = torch.full((F, KG, N, 8), float("nan"), device=DEV, dtype=BF)
     xd = x.to(DEV)
-    rc = _cabi.lib().bcl_prefill_rfft(xd.data_ptr(), _cabi.DTYPE[dtype], N, xd.stride(0), q, B, Xf.data_ptr(), _cabi.stream_ptr(DEV))
+    st = new_status()
+    rc = _cabi.lib().bcl_prefill_rfft(xd.data_ptr(), _cabi.DTYPE[dtype], N, xd.stride(0), p, q, B, buf.data_ptr(), impl,
+                                      Xf.data_ptr(), st.data_ptr(), _cabi.stream_ptr(DEV))
     _cabi.check(rc, "bcl_prefill_rfft")
+    torch.cuda.synchronize()
+    assert st.item() == 0
     ref = ref_xf(x, q, B, Kp)
-    got = Xf.double().cpu()
+    got = xf_natural(Xf).double().cpu()
     assert torch.isfinite(got).all()
-    assert (got - ref).abs().max() <= 2.0 ** -8 * ref.abs().max()
+    # impl 2 multiplies by a 16-bit DFT matrix (fp16: 2^-11, bf16: 2^-8 per coefficient) before the bf16 rounding of Xf
+    tol = 2.0 ** -8 if impl == 1 else (2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -8 + 2.0 ** -10)
+    assert (got - ref).abs().max() <= tol * ref.abs().max()
+
+
+def test_stage_rfft_tc_rejects_unsupported():
+    x = torch.zeros(8, 512, device=DEV)
+    Xf = torch.zeros(128, 4, 8, 8, device=DEV, dtype=BF)
+    rc = _cabi.lib().bcl_prefill_rfft(x.data_ptr(), _cabi.F32, 8, 512, 2, 2, 256, None, 2, Xf.data_ptr(), new_status().data_ptr(), _cabi.stream_ptr(DEV))
+    assert rc == -8
 
 
 @pytest.mark.parametrize("p,q,B,N", [(32, 32, 128, 128), (32, 32, 128, 300), (86, 32, 128, 256), (32, 86, 128, 129), (3, 5, 64, 40),
@@ -102,42 +171,49 @@ def test_stage_rfft_rows(q, B, N, dtype):
 def test_stage_tcgen05_gemm(p, q, B, N):
     """Yf[f] = Xf[f] @ Cmat[f]^T per frequency, bf16 operands, fp32 accumulate (the einsum of reference :260)."""
     g = torch.Generator().manual_seed(p + q + B + N)
-    F, Kp, Np = _cabi.prefill_geometry(p, q, B)
+    F, Kp, Np, KG, FG = geom(p, q, B)
     Xf = torch.zeros(F, N, Kp)
     Xf[:, :, :2 * q] = torch.randn(F, N, 2 * q, generator=g)
     Cm = torch.zeros(F, Np, Kp)
     Cm[:, :2 * p, :2 * q] = torch.randn(F, 2 * p, 2 * q, generator=g)
-    Xd, Cd = Xf.to(DEV, BF), Cm.to(DEV, BF)
-    Yf = torch.full((F, N, Np), float("nan"), device=DEV, dtype=BF)
-    status = torch.zeros(1, device=DEV, dtype=torch.int32)
+    Xd, Cd = xf_chunks(Xf).to(DEV, BF), Cm.to(DEV, BF)
+    Yf = torch.full((FG, p, N, 8), float("nan"), device=DEV, dtype=BF)
+    status = new_status()
     rc = _cabi.lib().bcl_prefill_gemm(Xd.data_ptr(), Cd.data_ptr(), Yf.data_ptr(), N, p, q, B, status.data_ptr(), _cabi.stream_ptr(DEV))
     _cabi.check(rc, "bcl_prefill_gemm")
     torch.cuda.synchronize()
     assert status.item() == 0, f"tcgen05 pipeline stalled (status {status.item()})"
-    ref = torch.einsum("fnk,fmk->fnm", Xd.double().cpu(), Cd.double().cpu())
-    got = Yf.double().cpu()
+    ref = torch.einsum("fnk,fmk->fnm", xf_natural(Xd).double().cpu(), Cd.double().cpu())[:, :, :2 * p]
+    got = yf_natural(Yf).double().cpu()
     assert torch.isfinite(got).all()
     err = (got - ref).abs()
     assert (err <= 2.0 ** -8 * ref.abs() + 1e-3 * ref.abs().max()).all(), f"max err {err.max().item():.3e} of {ref.abs().max().item():.3e}"
 
 
+@pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("p,B,N,dtype,bias_dt", [(5, 64, 7, torch.float32, None), (32, 128, 200, torch.float16, torch.float16),
-                                                 (86, 128, 33, torch.bfloat16, None), (9, 256, 130, torch.float16, torch.float32)])
-def test_stage_irfft_rows(p, B, N, dtype, bias_dt):
+                                                 (86, 128, 33, torch.bfloat16, None), (9, 256, 130, torch.float16, torch.float32),
+                                                 (5, 64, 300, torch.bfloat16, torch.bfloat16), (32, 128, 1024, torch.float16, None)])
+def test_stage_irfft(p, B, N, dtype, bias_dt, impl):
+    if impl == 2 and (B == 256 or dtype == torch.float32 or (bias_dt is not None and bias_dt != dtype)):
+        pytest.skip("tensor-core inverse DFT covers B <= 128, 16-bit activations, output dtype == activation dtype")
     g = torch.Generator().manual_seed(p + B + N)
-    F, _, Np = _cabi.prefill_geometry(p, 1, B)
+    q = 2
+    m = make_layer(torch.randn(p, q, B, generator=g))
+    buf, _ = gemm_spec(m)
+    F, Kp, Np, KG, FG = geom(p, q, B)
     Yc = torch.fft.rfft(torch.randn(N, p, B, generator=g).double(), dim=-1)            # a valid half-spectrum per block
-    Yf = torch.zeros(F, N, Np)
-    Yf[:, :, 0:2 * p:2] = Yc.real[..., :F].permute(2, 0, 1).float()
-    Yf[:, :, 1:2 * p:2] = Yc.imag[..., :F].permute(2, 0, 1).float()
-    Yf[0, :, 1:2 * p:2] = Yc.real[..., F].float()
-    Yd = Yf.to(DEV, BF)
+    Yn = torch.zeros(F, N, 2 * p)
+    Yn[:, :, 0::2] = Yc.real[..., :F].permute(2, 0, 1).float()
+    Yn[:, :, 1::2] = Yc.imag[..., :F].permute(2, 0, 1).float()
+    Yn[0, :, 1::2] = Yc.real[..., F].float()
+    Yd = yf_chunks(Yn, p).to(DEV, BF)
     # reference on the SAME bf16-rounded spectrum: irfft (:263), round to x.dtype (:266), + bias in the promoted dtype (:270-271)
-    Yb = Yd.double().cpu()
+    Yb = yf_natural(Yd).double().cpu()
     spec = torch.zeros(N, p, F + 1, dtype=torch.complex128)
-    spec.real[..., :F] = Yb[:, :, 0:2 * p:2].permute(1, 2, 0)
-    spec.imag[..., 1:F] = Yb[1:, :, 1:2 * p:2].permute(1, 2, 0)
-    spec.real[..., F] = Yb[0, :, 1:2 * p:2]
+    spec.real[..., :F] = Yb[:, :, 0::2].permute(1, 2, 0)
+    spec.imag[..., 1:F] = Yb[1:, :, 1::2].permute(1, 2, 0)
+    spec.real[..., F] = Yb[0, :, 1::2]
     y32 = torch.fft.irfft(spec, n=B, dim=-1).float().reshape(N, p * B)
     bias = None if bias_dt is None else torch.randn(p * B, generator=g).to(bias_dt)
     y_ref = y32.to(dtype)
@@ -145,11 +221,15 @@ def test_stage_irfft_rows(p, B, N, dtype, bias_dt):
         y_ref = y_ref + bias
     y = torch.empty(N, p * B, device=DEV, dtype=y_ref.dtype)
     bd = None if bias is None else bias.to(DEV)
-    rc = _cabi.lib().bcl_prefill_irfft(Yd.data_ptr(), N, p, B, _cabi.DTYPE[dtype], None if bd is None else bd.data_ptr(),
+    st = new_status()
+    rc = _cabi.lib().bcl_prefill_irfft(Yd.data_ptr(), N, p, q, B, buf.data_ptr(), impl, _cabi.DTYPE[dtype], None if bd is None else bd.data_ptr(),
                                        0 if bd is None else _cabi.DTYPE[bias_dt], y.data_ptr(), _cabi.DTYPE[y_ref.dtype], y.stride(0),
-                                       _cabi.stream_ptr(DEV))
+                                       st.data_ptr(), _cabi.stream_ptr(DEV))
     _cabi.check(rc, "bcl_prefill_irfft")
-    assert_close(y, y_ref, 1e-5, dtype, mag=y32.abs() + (0 if bias is None else bias.float().abs()))
+    torch.cuda.synchronize()
+    assert st.item() == 0
+    tol = 1e-5 if impl == 1 else 6e-3                          # impl 2: bf16 inverse DFT matrix (2^-9 per coefficient, B terms)
+    assert_close(y, y_ref, tol, dtype, mag=y32.abs() + (0 if bias is None else bias.float().abs()))
 
 
 SHAPES = [(4096, 4096, 128), (4096, 11008, 128), (11008, 4096, 128), (4096, 4096, 64), (4096, 4096, 256), (1024, 512, 64)]
@@ -165,7 +245,7 @@ def test_prefill_forward_vs_oracle(inf, outf, B, N):
     assert m._use_prefill_path(N)
     with torch.no_grad():
         y = m(x.to(DEV))
-    assert P.prefill_status(DEV) == 0
+    assert prefill_status(DEV) == 0
     assert_close(y, O.bc_forward_torch(c, x), 1e-2)
 
 
@@ -180,7 +260,7 @@ def test_prefill_forward_3d_16bit_io_and_bias(dtype, bias_dt):
         y = m(x.to(DEV))
     y_ref = O.bc_forward_torch(c, x, bias)
     assert y.shape == (4, 600, 4096) and y.dtype == y_ref.dtype
-    assert P.prefill_status(DEV) == 0
+    assert prefill_status(DEV) == 0
     mag = None if bias is None else O.bc_forward_torch(c, x).float().abs() + bias.float().abs()
     assert_close(y, y_ref, 1e-2, dtype, mag=mag)
 
@@ -194,7 +274,7 @@ def test_prefill_matches_stream_kernel_with_same_spectrum_dtype():
     with torch.no_grad():
         y_gemm = m(x.to(DEV))
         spec = m.build_spectrum()
-        y_stream = P.bc_forward(x.to(DEV), spec, None, 86, 32, 128)
+        y_stream = bc_forward(x.to(DEV), spec, None, 86, 32, 128)
     assert_close(y_gemm, y_stream, 1e-2)
 
 

@@ -12,7 +12,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import llama_fft_b200 as bc  # noqa: E402
 from llama_fft_b200 import _cabi  # noqa: E402
-from llama_fft_b200 import patch_llama_fft as P  # noqa: E402
+from llama_fft_b200.patch_llama_fft import bc_forward, prefill_status  # noqa: E402
 
 DEV = torch.device("cuda:0")
 
@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--block", type=int, default=128)
     ap.add_argument("--shapes", default="4096x4096,4096x11008,11008x4096")
+    ap.add_argument("--stage-tokens", type=int, default=2048)
     ap.add_argument("--skip-torch", action="store_true")
     ap.add_argument("--skip-stream", action="store_true")
     args = ap.parse_args()
@@ -61,26 +62,27 @@ def main():
         spec_s = layer.build_spectrum()
 
         def gemm_path(i):
-            P.bc_forward(xs[i % nbuf], spec_g, None, p, q, B, out=ys[i % nbuf], layout=_cabi.LAYOUT_GEMM)
+            bc_forward(xs[i % nbuf], spec_g, None, p, q, B, out=ys[i % nbuf], layout=_cabi.LAYOUT_GEMM)
         row["gemm_path_us"] = timeit(gemm_path, args.reps)
-        row["gemm_path_status"] = P.prefill_status(DEV)
+        row["gemm_path_status"] = prefill_status(DEV)
         row["gemm_path_hbm_frac"] = row["t_hbm_us"] / row["gemm_path_us"]
         row["gemm_path_Mtok_s"] = N / row["gemm_path_us"]
 
         # stages alone on one 2048-token chunk (what the chunk loop runs)
-        nc = min(N, 2048)
+        nc = min(N, args.stage_tokens)
         F, Kp, Np = _cabi.prefill_geometry(p, q, B)
-        Xf = torch.empty(F, nc, Kp, device=DEV, dtype=torch.bfloat16)
-        Yf = torch.empty(F, nc, Np, device=DEV, dtype=torch.bfloat16)
+        Xf = torch.empty(F, Kp // 8, nc, 8, device=DEV, dtype=torch.bfloat16)
+        Yf = torch.empty(F // 4, p, nc, 8, device=DEV, dtype=torch.bfloat16)
         status = torch.zeros(1, device=DEV, dtype=torch.int32)
         st = _cabi.stream_ptr(DEV)
-        row["stage_rfft_us_2048"] = timeit(lambda i: L.bcl_prefill_rfft(xs[i % nbuf].data_ptr(), _cabi.F16, nc, inf, q, B, Xf.data_ptr(), st), args.reps)
-        row["stage_gemm_us_2048"] = timeit(lambda i: L.bcl_prefill_gemm(Xf.data_ptr(), spec_g.data_ptr(), Yf.data_ptr(), nc, p, q, B, status.data_ptr(), st), args.reps)
-        row["stage_irfft_us_2048"] = timeit(lambda i: L.bcl_prefill_irfft(Yf.data_ptr(), nc, p, B, _cabi.F16, None, 0, ys[i % nbuf].data_ptr(), _cabi.F16, outf, st), args.reps)
+        row["stage_tokens"] = nc
+        row["stage_rfft_us"] = timeit(lambda i: L.bcl_prefill_rfft(xs[i % nbuf].data_ptr(), _cabi.F16, nc, inf, p, q, B, spec_g.data_ptr(), 0, Xf.data_ptr(), status.data_ptr(), st), args.reps)
+        row["stage_gemm_us"] = timeit(lambda i: L.bcl_prefill_gemm(Xf.data_ptr(), spec_g.data_ptr(), Yf.data_ptr(), nc, p, q, B, status.data_ptr(), st), args.reps)
+        row["stage_irfft_us"] = timeit(lambda i: L.bcl_prefill_irfft(Yf.data_ptr(), nc, p, q, B, spec_g.data_ptr(), 0, _cabi.F16, None, 0, ys[i % nbuf].data_ptr(), _cabi.F16, outf, status.data_ptr(), st), args.reps)
 
         if not args.skip_stream:
             def stream_path(i):
-                P.bc_forward(xs[i % nbuf], spec_s, None, p, q, B, out=ys[i % nbuf])
+                bc_forward(xs[i % nbuf], spec_s, None, p, q, B, out=ys[i % nbuf])
             row["stream_kernel_bf16spec_us"] = timeit(stream_path, max(2, args.reps // 3), warm=1)
         if not args.skip_torch:
             c32 = layer.c.detach().float()
