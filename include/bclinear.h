@@ -87,8 +87,9 @@ int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
 
 /* ---- prefill stages (layout GEMM): the three steps bcl_forward chains per token chunk, exported so that each can be
  * checked on its own against the reference step it replaces.  Intermediates are bf16 in 16-byte chunks:
- *   Xf [B/2][Kp/8][N][8]   Xf[f][kg][n][k0], k = 8 kg + k0 = 2i+{0,1} = {Re,Im} rfft(x[n, iB:(i+1)B])[f]  (f = 0: {DC, Nyquist})   src/patch_llama_fft.py:252
- *   Yf [B/8][p][N][8]      Yf[fg][j][n][2 fl+{0,1}] = {Re,Im} sum_i Cf[j,i,f] * Xf[n,i,f],  f = 4 fg + fl                         src/patch_llama_fft.py:260
+ *   Xf [B/2][Kp/8][Nt][8]  Xf[f][kg][n][k0], k = 8 kg + k0 = 2i+{0,1} = {Re,Im} rfft(x[n, iB:(i+1)B])[f]  (f = 0: {DC, Nyquist})   src/patch_llama_fft.py:252
+ *   Yf [B/8][p][Nt][8]     Yf[fg][j][n][2 fl+{0,1}] = {Re,Im} sum_i Cf[j,i,f] * Xf[n,i,f],  f = 4 fg + fl                         src/patch_llama_fft.py:260
+ * with the token pitch Nt = N rounded up to 32 (rows N..Nt-1 are padding the kernels may write).
  * spec_gemm is the GEMM-layout spectrum buffer of the layer (it also carries the DFT matrices of the tensor-core stages).
  * impl: 0 = pick, 1 = CUDA-core register FFT, 2 = DFT as a tcgen05 GEMM (B <= 128, 16-bit activations; else BCL_ERR_UNSUPPORTED).
  * status: device int zeroed by the caller; a tcgen05 kernel sets it non-zero if its pipeline ever stalls. */

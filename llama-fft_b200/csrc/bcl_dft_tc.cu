@@ -23,6 +23,10 @@ using namespace sm100;
 
 constexpr int DFT_THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int DFT_MAX_STAGES = 6;
+#ifndef BCL_EPI_NBUF
+#define BCL_EPI_NBUF 4
+#endif
+constexpr int DFT_NBUF = BCL_EPI_NBUF;   // staging buffers per epilogue warp: TMA stores in flight
 constexpr uint32_t DFT_EPI_BUF = 4096;   // fwd: [8 f][32 tokens][16 B];  inv: [32 tokens][128 B] swizzled
 
 struct DftBarriers {
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_fwd_tc_kernel(const __grid
     extern __shared__ __align__(1024) unsigned char dft_smem[];
     DftBarriers* bars = reinterpret_cast<DftBarriers*>(dft_smem);
     unsigned char* epi = dft_smem + 1024;                    // 4 warps x 2 x DFT_EPI_BUF
-    unsigned char* wsm = dft_smem + 1024 + 4 * 2 * DFT_EPI_BUF;
+    unsigned char* wsm = dft_smem + 1024 + 4 * DFT_NBUF * DFT_EPI_BUF;
     unsigned char* ring = wsm + ATOMS * W_ATOM;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int S = a.stages;
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_fwd_tc_kernel(const __grid
         }
     } else {
         const int quarter = warp & 3;
-        unsigned char* stg = epi + (size_t)(warp - 2) * 2 * DFT_EPI_BUF;
+        unsigned char* stg = epi + (size_t)(warp - 2) * DFT_NBUF * DFT_EPI_BUF;
         int it = 0, buf = 0;
         for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
             const int kg = item % a.groups, m = item / a.groups;
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_fwd_tc_kernel(const __grid
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->tmem_empty[0]);
                 }
-                if (lane == 0) tma_store_wait_read<1>();
+                if (lane == 0) tma_store_wait_read<DFT_NBUF - 1>();
                 __syncwarp();
                 uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)buf * DFT_EPI_BUF) + lane;
 #pragma unroll
@@ -156,10 +160,10 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_fwd_tc_kernel(const __grid
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_4d(&tmXf, 0, m * TILE_M + quarter * 32, kg, fc * 8, stg + (size_t)buf * DFT_EPI_BUF);
+                    tma_store_4d(&tmXf, 0, m * (TILE_M / TOK_GROUP) + quarter, kg, fc * 8, stg + (size_t)buf * DFT_EPI_BUF);
                     tma_store_commit();
                 }
-                buf ^= 1;
+                if (++buf == DFT_NBUF) buf = 0;
             }
         }
         if (lane == 0) tma_store_wait<0>();
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_kernel(const __grid
     extern __shared__ __align__(1024) unsigned char dft_smem[];
     DftBarriers* bars = reinterpret_cast<DftBarriers*>(dft_smem);
     unsigned char* epi = dft_smem + 1024;
-    unsigned char* wsm = dft_smem + 1024 + 4 * 2 * DFT_EPI_BUF;
+    unsigned char* wsm = dft_smem + 1024 + 4 * DFT_NBUF * DFT_EPI_BUF;
     unsigned char* ring = wsm + ATOMS * W_ATOM;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int S = a.stages;
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_kernel(const __grid
                 const int j = item % a.groups, m = item / a.groups;
                 if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 21); goto done; }
                 mbar_arrive_expect_tx(&bars->full[stage], STAGE);
-                tma_load_4d(ring + (size_t)stage * STAGE, &tmYf, 0, m * TILE_M, j, 0, &bars->full[stage]);
+                tma_load_4d(ring + (size_t)stage * STAGE, &tmYf, 0, m * (TILE_M / TOK_GROUP), j, 0, &bars->full[stage]);
                 if (++stage == S) { stage = 0; ph ^= 1u; }
             }
         }
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_kernel(const __grid
         }
     } else {
         const int quarter = warp & 3;
-        unsigned char* stg = epi + (size_t)(warp - 2) * 2 * DFT_EPI_BUF;
+        unsigned char* stg = epi + (size_t)(warp - 2) * DFT_NBUF * DFT_EPI_BUF;
         int it = 0, buf = 0;
         for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
             const int j = item % a.groups, m = item / a.groups;
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_kernel(const __grid
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
                 }
-                if (lane == 0) tma_store_wait_read<1>();
+                if (lane == 0) tma_store_wait_read<DFT_NBUF - 1>();
                 __syncwarp();
                 unsigned char* row = stg + (size_t)buf * DFT_EPI_BUF + (size_t)lane * 128;
                 const int col0 = j * B + h * 64;
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_kernel(const __grid
                     tma_store_2d(&tmOut, col0, (int)(a.n_begin + (int64_t)m * TILE_M + quarter * 32), stg + (size_t)buf * DFT_EPI_BUF);
                     tma_store_commit();
                 }
-                buf ^= 1;
+                if (++buf == DFT_NBUF) buf = 0;
             }
         }
         if (lane == 0) tma_store_wait<0>();
@@ -302,7 +306,7 @@ done:
 bool dft_tc_supported(int B, int act_dtype) { return (B == 64 || B == 128) && (act_dtype == BCL_F16 || act_dtype == BCL_BF16); }
 
 static size_t dft_smem_bytes(int B, uint32_t stage_bytes, int stages) {
-    return 1024 + 4 * 2 * DFT_EPI_BUF + (size_t)(B / KATOM) * B * 128 + (size_t)stages * stage_bytes;
+    return 1024 + 4 * DFT_NBUF * DFT_EPI_BUF + (size_t)(B / KATOM) * B * 128 + (size_t)stages * stage_bytes;
 }
 static int dft_pick_stages(int B, uint32_t stage_bytes) {
     int s = DFT_MAX_STAGES;
@@ -330,12 +334,7 @@ cudaError_t launch_dft_fwd_tc(const ProblemDev& P, const Geometry& g, const void
     }
     const unsigned char* sb = reinterpret_cast<const unsigned char*>(spec_gemm);
     if (!map_w(&tmW, sb + (bf ? g.wbf16_off : g.wf16_off), B, adt)) return cudaErrorNotSupported;
-    {
-        const uint64_t dims[4] = {8, (uint64_t)nc, (uint64_t)g.KG, (uint64_t)g.F};
-        const uint64_t strides[3] = {16, (uint64_t)nc * 16, (uint64_t)g.KG * nc * 16};
-        const uint32_t box[4] = {8, 32, 1, 8};
-        if (!make_tensor_map(&tmXf, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, Xf, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorNotSupported;
-    }
+    if (!make_chunk_map(&tmXf, Xf, nc, g.KG, g.F, 1, 1, 8)) return cudaErrorNotSupported;
     DftArgs a{};
     a.status = status; a.bias = nullptr; a.n_begin = n_begin; a.nc = nc;
     a.m_tiles = (nc + TILE_M - 1) / TILE_M; a.groups = g.KG; a.num_items = a.m_tiles * g.KG; a.act_bf16 = bf ? 1 : 0;
@@ -360,12 +359,7 @@ cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void
     const bool bf = P.x_dtype == BCL_BF16;
     const CUtensorMapDataType adt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUtensorMap tmYf, tmW, tmOut;
-    {
-        const uint64_t dims[4] = {8, (uint64_t)nc, (uint64_t)g.p, (uint64_t)g.FG};
-        const uint64_t strides[3] = {16, (uint64_t)nc * 16, (uint64_t)g.p * nc * 16};
-        const uint32_t box[4] = {8, TILE_M, 1, (uint32_t)g.FG};
-        if (!make_tensor_map(&tmYf, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, Yf, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorNotSupported;
-    }
+    if (!make_chunk_map(&tmYf, Yf, nc, g.p, g.FG, TILE_M / TOK_GROUP, 1, (uint32_t)g.FG)) return cudaErrorNotSupported;
     const unsigned char* sb = reinterpret_cast<const unsigned char*>(spec_gemm);
     if (!map_w(&tmW, sb + g.winv_off, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return cudaErrorNotSupported;
     {

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(WARPS * 32) rfft_rows_kernel(const __grid_cons
     load_x_spectrum<B, NT, WARPS, SM::PITCH>(Pc, n_begin + t0, xs, tw, fscr_all + (size_t)warp * (C::WARP_SCRATCH_BYTES / 8), lane, warp);
     __syncthreads();
     constexpr int F = B / 2;
+    const size_t ntp = (size_t)token_pitch(nc);
     // one 16-byte chunk = (f, kg, token): input blocks 4kg .. 4kg+3, {re,im} each.  Tokens of a CTA are adjacent chunks.
     const int nchunks = F * KG * NT;
     for (int id = threadIdx.x; id < nchunks; id += WARPS * 32) {
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(WARPS * 32) rfft_rows_kernel(const __grid_cons
                 w[ib] = pack_bf16(v.x, v.y);                            // f = 0: (DC, Nyquist), both real
             }
         }
-        *reinterpret_cast<uint4*>(Xf + (((size_t)f * KG + kg) * nc + (t0 + n)) * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(Xf + (((size_t)f * KG + kg) * ntp + (t0 + n)) * 8) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -147,6 +148,10 @@ __global__ void dft_matrix_kernel(int B, __half* __restrict__ wf16, __nv_bfloat1
 // ---------------------------------------------------------------------------------------------------------
 constexpr int GEMM_THREADS = 192;    // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int MAX_STAGES = 8;
+#ifndef BCL_EPI_NBUF
+#define BCL_EPI_NBUF 4
+#endif
+constexpr int EPI_NBUF = BCL_EPI_NBUF;                       // staging buffers per epilogue warp: TMA stores in flight
 constexpr uint32_t A_STAGE_BYTES = TILE_M * KATOM * 2;       // [8 kg][128 tokens][16 B], no swizzle ("interleaved" K-major)
 constexpr uint32_t B_STAGE_BYTES = NCHUNK * KATOM * 2;       // 64 rows x 128 B, 128-byte swizzle
 constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -176,8 +181,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
                                                                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char gemm_smem[];
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(gemm_smem);
-    unsigned char* epi = gemm_smem + 1024;                                       // 4 warps x 2 buffers x EPI_BUF_BYTES
-    unsigned char* ring = gemm_smem + 1024 + 4 * 2 * EPI_BUF_BYTES;               // stays 1024-byte aligned
+    unsigned char* epi = gemm_smem + 1024;                                       // 4 warps x EPI_NBUF buffers x EPI_BUF_BYTES
+    unsigned char* ring = gemm_smem + 1024 + 4 * EPI_NBUF * EPI_BUF_BYTES;               // stays 1024-byte aligned
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int S = a.stages;
 
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
                         if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 1); goto done; }
                         unsigned char* sa = ring + (size_t)stage * STAGE_BYTES;
                         mbar_arrive_expect_tx(&bars->full[stage], STAGE_BYTES);
-                        tma_load_4d(sa, &tmA, 0, m * TILE_M, ka * 8, 4 * fg + fl, &bars->full[stage]);
+                        tma_load_4d(sa, &tmA, 0, m * (TILE_M / TOK_GROUP), ka * 8, 4 * fg + fl, &bars->full[stage]);
                         tma_load_3d(sa + A_STAGE_BYTES, &tmB, ka * KATOM, nch * NCHUNK, 4 * fg + fl, &bars->full[stage]);
                         if (++stage == S) { stage = 0; ph ^= 1u; }
                     }
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
     } else {
         // ===================== epilogue warps: TMEM -> registers -> bf16 chunks -> smem -> TMA store =====================
         const int quarter = warp & 3;                                            // TMEM lanes [32*quarter, +32) are this warp's
-        unsigned char* stg = epi + (size_t)(warp - 2) * 2 * EPI_BUF_BYTES;
+        unsigned char* stg = epi + (size_t)(warp - 2) * EPI_NBUF * EPI_BUF_BYTES;
         int it = 0, buf = 0;
         for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
             int fg, m, nch; decode_item(a, item, fg, m, nch);
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->tmem_empty[set]);
                 }
-                if (lane == 0) tma_store_wait_read<1>();                         // the store that last read this buffer has finished
+                if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();              // the store that last read this buffer has finished
                 __syncwarp();
                 uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)buf * EPI_BUF_BYTES) + lane;
 #pragma unroll
@@ -271,10 +276,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_4d(&tmY, 0, m * TILE_M + quarter * 32, nch * 32 + jc * 8, fg, stg + (size_t)buf * EPI_BUF_BYTES);
+                    tma_store_4d(&tmY, 0, m * (TILE_M / TOK_GROUP) + quarter, nch * 32 + jc * 8, fg, stg + (size_t)buf * EPI_BUF_BYTES);
                     tma_store_commit();
                 }
-                buf ^= 1;
+                if (++buf == EPI_NBUF) buf = 0;
             }
         }
         if (lane == 0) tma_store_wait<0>();
@@ -302,13 +307,14 @@ __global__ void __launch_bounds__(WARPS * 32) irfft_rows_kernel(const __grid_con
     const int p = P.p;
     const int t0 = blockIdx.x * NT;
     constexpr int FG = B / 8;
+    const size_t ntp = (size_t)token_pitch(nc);
     const int nchunks = FG * p * NT;                                    // one 16-byte chunk = (fg, j, token): 4 frequencies x {re,im}
     for (int id = threadIdx.x; id < nchunks; id += WARPS * 32) {
         const int n = id % NT;
         const int j = (id / NT) % p;
         const int fg = id / (NT * p);
         if (t0 + n >= nc) continue;
-        const uint4 w = __ldg(reinterpret_cast<const uint4*>(Yf + (((size_t)fg * p + j) * nc + (t0 + n)) * 8));
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(Yf + (((size_t)fg * p + j) * ntp + (t0 + n)) * 8));
         float2* dst = reinterpret_cast<float2*>(ys + ((size_t)n * p + j) * SM::PITCH + 8 * fg);
         dst[0] = unpack_bf16(w.x); dst[1] = unpack_bf16(w.y); dst[2] = unpack_bf16(w.z); dst[3] = unpack_bf16(w.w);
     }
@@ -356,7 +362,20 @@ bool make_tensor_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const voi
               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static size_t gemm_smem_bytes(int stages) { return 1024 + 4 * 2 * EPI_BUF_BYTES + (size_t)stages * STAGE_BYTES; }
+bool make_chunk_map(CUtensorMap* m, const void* base, int64_t ntok, int slabs, int outer, uint32_t box_groups, uint32_t box_slabs, uint32_t box_outer) {
+    const uint64_t ntp = (uint64_t)token_pitch(ntok);
+    const uint64_t dims[4] = {(uint64_t)TOK_GROUP * 8, ntp / TOK_GROUP, (uint64_t)slabs, (uint64_t)outer};
+    const uint64_t strides[3] = {(uint64_t)TOK_GROUP * 16, ntp * 16, (uint64_t)slabs * ntp * 16};
+    const uint32_t box[4] = {TOK_GROUP * 8, box_groups, box_slabs, box_outer};
+    return make_tensor_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+static size_t gemm_smem_bytes(int stages) { return 1024 + 4 * EPI_NBUF * EPI_BUF_BYTES + (size_t)stages * STAGE_BYTES; }
+static int gemm_pick_stages() {
+    int s = MAX_STAGES;
+    while (s > 2 && gemm_smem_bytes(s) > 225 * 1024) --s;
+    return s;
+}
 
 template <typename K> static cudaError_t set_smem(K kernel, size_t bytes) {
     if (bytes <= 48 * 1024) return cudaSuccess;
@@ -411,7 +430,7 @@ int64_t gemm_chunk_tokens(int64_t N, int p, int q, int B, size_t workspace_bytes
     const gemm::Geometry g = gemm::geometry(p, q, B);
     if (workspace_bytes <= kWsHeader + 512) return 0;
     int64_t nc = (int64_t)((workspace_bytes - kWsHeader - 512) / per_token_ws(g));
-    if (nc >= N) return N;
+    if (nc >= gemm::token_pitch(N)) return N;
     return nc / gemm::TILE_M * gemm::TILE_M;
 }
 
@@ -419,7 +438,7 @@ size_t gemm_workspace_bytes(int64_t N, int p, int q, int B) {
     const gemm::Geometry g = gemm::geometry(p, q, B);
     int64_t nc = (int64_t)(chunk_budget() / per_token_ws(g)) / gemm::TILE_M * gemm::TILE_M;
     if (nc < gemm::TILE_M) nc = gemm::TILE_M;
-    if (nc > N) nc = N;
+    if (nc > N) nc = gemm::token_pitch(N);
     return kWsHeader + 512 + (size_t)nc * per_token_ws(g);
 }
 
@@ -459,34 +478,24 @@ cudaError_t launch_gemm_irfft(const ProblemDev& P, int B, int64_t n_begin, int n
 #undef BCL_R3
 }
 
-// Xf [F][KG][nc][8], Cmat [F][Np][Kp] -> Yf [FG][p][nc][8].  status: device int, set non-zero if a pipeline wait timed out.
+// Xf [F][KG][ntp][8], Cmat [F][Np][Kp] -> Yf [FG][p][ntp][8] (ntp = nc rounded up to 32).  status: device int, set non-zero if a pipeline wait timed out.
 cudaError_t launch_gemm_mma(const void* Xf, const void* Cmat, void* Yf, int* status, int p, int q, int B, int nc, int max_ctas, cudaStream_t st) {
     const gemm::Geometry g = gemm::geometry(p, q, B);
     CUtensorMap tmA, tmB, tmY;
-    {
-        const uint64_t dims[4] = {8, (uint64_t)nc, (uint64_t)g.KG, (uint64_t)g.F};
-        const uint64_t strides[3] = {16, (uint64_t)nc * 16, (uint64_t)g.KG * nc * 16};
-        const uint32_t box[4] = {8, gemm::TILE_M, 8, 1};
-        if (!gemm::make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, Xf, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorNotSupported;
-    }
+    if (!gemm::make_chunk_map(&tmA, Xf, nc, g.KG, g.F, gemm::TILE_M / gemm::TOK_GROUP, 8, 1)) return cudaErrorNotSupported;
     {
         const uint64_t dims[3] = {(uint64_t)g.Kp, (uint64_t)g.Np, (uint64_t)g.F};
         const uint64_t strides[2] = {(uint64_t)g.Kp * 2, (uint64_t)g.Kp * g.Np * 2};
         const uint32_t box[3] = {gemm::KATOM, gemm::NCHUNK, 1};
         if (!gemm::make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Cmat, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return cudaErrorNotSupported;
     }
-    {
-        const uint64_t dims[4] = {8, (uint64_t)nc, (uint64_t)p, (uint64_t)g.FG};
-        const uint64_t strides[3] = {16, (uint64_t)nc * 16, (uint64_t)p * nc * 16};
-        const uint32_t box[4] = {8, 32, 8, 1};
-        if (!gemm::make_tensor_map(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, Yf, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorNotSupported;
-    }
+    if (!gemm::make_chunk_map(&tmY, Yf, nc, p, g.FG, 1, 8, 1)) return cudaErrorNotSupported;
     gemm::GemmArgs a{};
     a.status = status;
     a.ntok = nc; a.p = p; a.KG = g.KG; a.k_atoms = (g.Kp + gemm::KATOM - 1) / gemm::KATOM; a.NCH = g.NCH;
     a.m_tiles = (nc + gemm::TILE_M - 1) / gemm::TILE_M;
     a.num_items = a.m_tiles * g.FG * g.NCH;
-    a.stages = gemm::MAX_STAGES;
+    a.stages = gemm::gemm_pick_stages();
     const size_t smem = gemm::gemm_smem_bytes(a.stages);
     cudaError_t e = cudaFuncSetAttribute(gemm::freq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

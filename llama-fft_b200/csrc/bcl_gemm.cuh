@@ -3,8 +3,11 @@
 //
 // Everything between the stages is bf16 and laid out so that BOTH the producer's stores and the consumer's TMA loads are
 // runs of whole 16-byte chunks:
-//   Xf  [F][KG][ntok][8]      Xf[f][kg][n][k0],  k = 8 kg + k0 = 2 i + {re,im}          (A operand of the frequency GEMM)
-//   Yf  [FG][p][ntok][8]      Yf[fg][j][n][2 fl + {re,im}],  f = 4 fg + fl               (A operand of the inverse DFT)
+//   Xf  [F][KG][ntp][8]       Xf[f][kg][n][k0],  k = 8 kg + k0 = 2 i + {re,im}          (A operand of the frequency GEMM)
+//   Yf  [FG][p][ntp][8]       Yf[fg][j][n][2 fl + {re,im}],  f = 4 fg + fl               (A operand of the inverse DFT)
+// ntp = tokens of the chunk rounded up to 32 (token_pitch): consecutive tokens of one (f,kg) / (fg,j) slab are contiguous,
+// so every TMA box row is 32 tokens x 16 B = 512 contiguous bytes (TMA moves about one box row per clock: 16-byte rows
+// capped all three kernels at ~27 GB/s per SM, profiles/r1_prefill_notes.md).
 //   GEMM-layout spectrum buffer:
 //     Cmat [F][Np][Kp]        K-major rows, n = 2 j + {re,im} (Np = 2p rounded up to 64), k as above (Kp = 2q rounded up to 16)
 //     Wfwd fp16, Wfwd bf16    [B][B]  row r = packed spectrum real (0: DC, 1: Nyquist, 2f: Re, 2f+1: Im), column t   (forward DFT)
@@ -49,8 +52,12 @@ __host__ inline Geometry geometry(int p, int q, int B) {
     return g;
 }
 
-inline size_t xf_bytes(const Geometry& g, int64_t ntok) { return (size_t)g.F * g.Kp * ntok * 2; }
-inline size_t yf_bytes(const Geometry& g, int64_t ntok) { return (size_t)g.F * 2 * g.p * ntok * 2; }
+constexpr int TOK_GROUP = 32;        // tokens per TMA box row of the chunked layouts
+__host__ __device__ inline int64_t token_pitch(int64_t ntok) { return (ntok + TOK_GROUP - 1) / TOK_GROUP * TOK_GROUP; }
+inline size_t xf_bytes(const Geometry& g, int64_t ntok) { return (size_t)g.F * g.Kp * token_pitch(ntok) * 2; }
+inline size_t yf_bytes(const Geometry& g, int64_t ntok) { return (size_t)g.F * 2 * g.p * token_pitch(ntok) * 2; }
+// tensor maps over the chunked layouts: dims (256 elements = 32 tokens x 8, token groups, slabs (kg or j), f or fg)
+bool make_chunk_map(CUtensorMap* m, const void* base, int64_t ntok, int slabs, int outer, uint32_t box_groups, uint32_t box_slabs, uint32_t box_outer);
 
 // Tensor-map helper (cuTensorMapEncodeTiled through the runtime's driver entry point; no libcuda link dependency).
 // dims/strides innermost first; strides[i] = byte stride of dimension i+1.

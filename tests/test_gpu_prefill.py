@@ -102,6 +102,17 @@ def ref_xf(x, q, B, Kp):
     return out
 
 
+def pitch(N):
+    return (N + 31) // 32 * 32                                  # token pitch of the stage layouts (include/bclinear.h)
+
+
+def pad_tokens(t, N):
+    """(.., .., N, 8) -> (.., .., pitch(N), 8), zero padded"""
+    out = torch.zeros(t.shape[0], t.shape[1], pitch(N), 8, dtype=t.dtype, device=t.device)
+    out[:, :, :N] = t
+    return out
+
+
 def new_status():
     return torch.zeros(1, device=DEV, dtype=torch.int32)
 
@@ -143,7 +154,7 @@ def test_stage_rfft(q, B, N, dtype, impl):
     m = make_layer(torch.randn(p, q, B, generator=g))
     buf, _ = gemm_spec(m)
     F, Kp, Np, KG, FG = geom(p, q, B)
-    Xf = torch.full((F, KG, N, 8), float("nan"), device=DEV, dtype=BF)
+    Xf = torch.full((F, KG, pitch(N), 8), float("nan"), device=DEV, dtype=BF)
     xd = x.to(DEV)
     st = new_status()
     rc = _cabi.lib().bcl_prefill_rfft(xd.data_ptr(), _cabi.DTYPE[dtype], N, xd.stride(0), p, q, B, buf.data_ptr(), impl,
@@ -152,7 +163,7 @@ def test_stage_rfft(q, B, N, dtype, impl):
     torch.cuda.synchronize()
     assert st.item() == 0
     ref = ref_xf(x, q, B, Kp)
-    got = xf_natural(Xf).double().cpu()
+    got = xf_natural(Xf[:, :, :N]).double().cpu()
     assert torch.isfinite(got).all()
     # impl 2 multiplies by a 16-bit DFT matrix (fp16: 2^-11, bf16: 2^-8 per coefficient) before the bf16 rounding of Xf
     tol = 2.0 ** -8 if impl == 1 else (2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -8 + 2.0 ** -10)
@@ -176,15 +187,15 @@ def test_stage_tcgen05_gemm(p, q, B, N):
     Xf[:, :, :2 * q] = torch.randn(F, N, 2 * q, generator=g)
     Cm = torch.zeros(F, Np, Kp)
     Cm[:, :2 * p, :2 * q] = torch.randn(F, 2 * p, 2 * q, generator=g)
-    Xd, Cd = xf_chunks(Xf).to(DEV, BF), Cm.to(DEV, BF)
-    Yf = torch.full((FG, p, N, 8), float("nan"), device=DEV, dtype=BF)
+    Xd, Cd = pad_tokens(xf_chunks(Xf), N).to(DEV, BF), Cm.to(DEV, BF)
+    Yf = torch.full((FG, p, pitch(N), 8), float("nan"), device=DEV, dtype=BF)
     status = new_status()
     rc = _cabi.lib().bcl_prefill_gemm(Xd.data_ptr(), Cd.data_ptr(), Yf.data_ptr(), N, p, q, B, status.data_ptr(), _cabi.stream_ptr(DEV))
     _cabi.check(rc, "bcl_prefill_gemm")
     torch.cuda.synchronize()
     assert status.item() == 0, f"tcgen05 pipeline stalled (status {status.item()})"
-    ref = torch.einsum("fnk,fmk->fnm", xf_natural(Xd).double().cpu(), Cd.double().cpu())[:, :, :2 * p]
-    got = yf_natural(Yf).double().cpu()
+    ref = torch.einsum("fnk,fmk->fnm", xf_natural(Xd[:, :, :N]).double().cpu(), Cd.double().cpu())[:, :, :2 * p]
+    got = yf_natural(Yf[:, :, :N]).double().cpu()
     assert torch.isfinite(got).all()
     err = (got - ref).abs()
     assert (err <= 2.0 ** -8 * ref.abs() + 1e-3 * ref.abs().max()).all(), f"max err {err.max().item():.3e} of {ref.abs().max().item():.3e}"
@@ -207,9 +218,9 @@ def test_stage_irfft(p, B, N, dtype, bias_dt, impl):
     Yn[:, :, 0::2] = Yc.real[..., :F].permute(2, 0, 1).float()
     Yn[:, :, 1::2] = Yc.imag[..., :F].permute(2, 0, 1).float()
     Yn[0, :, 1::2] = Yc.real[..., F].float()
-    Yd = yf_chunks(Yn, p).to(DEV, BF)
+    Yd = pad_tokens(yf_chunks(Yn, p), N).to(DEV, BF)
     # reference on the SAME bf16-rounded spectrum: irfft (:263), round to x.dtype (:266), + bias in the promoted dtype (:270-271)
-    Yb = yf_natural(Yd).double().cpu()
+    Yb = yf_natural(Yd[:, :, :N]).double().cpu()
     spec = torch.zeros(N, p, F + 1, dtype=torch.complex128)
     spec.real[..., :F] = Yb[:, :, 0::2].permute(1, 2, 0)
     spec.imag[..., 1:F] = Yb[1:, :, 1::2].permute(1, 2, 0)

@@ -71,8 +71,8 @@ def main():
         # stages alone on one 2048-token chunk (what the chunk loop runs)
         nc = min(N, args.stage_tokens)
         F, Kp, Np = _cabi.prefill_geometry(p, q, B)
-        Xf = torch.empty(F, Kp // 8, nc, 8, device=DEV, dtype=torch.bfloat16)
-        Yf = torch.empty(F // 4, p, nc, 8, device=DEV, dtype=torch.bfloat16)
+        Xf = torch.empty(F, Kp // 8, (nc + 31) // 32 * 32, 8, device=DEV, dtype=torch.bfloat16)
+        Yf = torch.empty(F // 4, p, (nc + 31) // 32 * 32, 8, device=DEV, dtype=torch.bfloat16)
         status = torch.zeros(1, device=DEV, dtype=torch.int32)
         st = _cabi.stream_ptr(DEV)
         row["stage_tokens"] = nc

@@ -45,8 +45,8 @@ def main():
     for n in (int(v) for v in a.tokens.split(",")):
         x = torch.randn(n, inf, device=DEV).half()
         y = torch.empty(n, outf, device=DEV, dtype=torch.float16)
-        Xf = torch.empty(F, Kp // 8, n, 8, device=DEV, dtype=torch.bfloat16)
-        Yf = torch.empty(F // 4, p, n, 8, device=DEV, dtype=torch.bfloat16)
+        Xf = torch.empty(F, Kp // 8, (n + 31) // 32 * 32, 8, device=DEV, dtype=torch.bfloat16)
+        Yf = torch.empty(F // 4, p, (n + 31) // 32 * 32, 8, device=DEV, dtype=torch.bfloat16)
         r = {"shape": a.shape, "tokens": n}
         r["rfft_us"], r["rfft_host_us"] = ev_time(lambda: L.bcl_prefill_rfft(x.data_ptr(), _cabi.F16, n, inf, p, q, B, spec.data_ptr(), a.impl, Xf.data_ptr(), status.data_ptr(), st), a.reps)
         r["gemm_us"], r["gemm_host_us"] = ev_time(lambda: L.bcl_prefill_gemm(Xf.data_ptr(), spec.data_ptr(), Yf.data_ptr(), n, p, q, B, status.data_ptr(), st), a.reps)
