@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BCL_ABI_VERSION 5
+#define BCL_ABI_VERSION 6
 
 typedef enum bcl_dtype { BCL_F32 = 0, BCL_F16 = 1, BCL_BF16 = 2 } bcl_dtype;
 
@@ -84,6 +84,17 @@ int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
                 const void* bias, int bias_dtype,
                 void* y, int y_dtype, int64_t y_row_stride,
                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- forward with several destinations: the fused gather of output-block-row sharding ---------------------------
+ * Same as bcl_forward, but the epilogue stores y to every one of y_dsts[0 .. n_dst) (1 <= n_dst <= 8; same shape, row
+ * stride and dtype).  With peer-mapped pointers (symmetric memory over NVLink) a rank that owns block-rows [j0, j1) of a
+ * sharded layer writes its slice y[:, j0*B : j1*B] straight into every peer's full y: no collective afterwards.
+ * The reference has no distributed path; see llama-fft_b200/sharded.py. */
+int bcl_forward_bcast(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
+                      const void* spec, int spec_dtype, int layout, int p, int q, int B,
+                      const void* bias, int bias_dtype,
+                      void* const* y_dsts, int n_dst, int y_dtype, int64_t y_row_stride,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- prefill stages (layout GEMM): the three steps bcl_forward chains per token chunk, exported so that each can be
  * checked on its own against the reference step it replaces.  Intermediates are bf16 in 16-byte chunks:

@@ -94,16 +94,22 @@ size_t bcl_workspace_bytes(int64_t N, int p, int q, int B, int spec_dtype, int l
     return 0;
 }
 
-int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
-                const void* spec, int spec_dtype, int layout, int p, int q, int B,
-                const void* bias, int bias_dtype, void* y, int y_dtype, int64_t y_row_stride,
-                void* workspace, size_t workspace_bytes, void* stream) {
+static int forward_impl(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
+                        const void* spec, int spec_dtype, int layout, int p, int q, int B,
+                        const void* bias, int bias_dtype, void* const* y_dsts, int n_dst, int y_dtype, int64_t y_row_stride,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_dst < 1 || n_dst > 1 + bcl::kMaxExtraDst || !y_dsts) return fail(BCL_ERR_ARG, "need 1..%d destinations", 1 + bcl::kMaxExtraDst);
+    void* y = y_dsts[0];
     int rc = check_problem(x, x_dtype, N, x_row_stride, spec, p, q, B, bias, bias_dtype, y, y_dtype, y_row_stride);
     if (rc != BCL_OK || N == 0) return rc;
+    bcl::ProblemDev P{x, spec, bias, y, N, x_row_stride, y_row_stride, p, q, x_dtype, y_dtype, bias ? bias_dtype : BCL_F32, n_dst - 1, {}};
+    for (int e = 1; e < n_dst; ++e) {
+        if (!y_dsts[e] || !aligned(y_dsts[e], 16)) return fail(BCL_ERR_ALIGN, "destination %d is NULL or not 16-byte aligned", e);
+        P.y_extra[e - 1] = y_dsts[e];
+    }
     if (layout == BCL_LAYOUT_STREAM) {
         if (spec_dtype != BCL_F32 && spec_dtype != BCL_BF16) return fail(BCL_ERR_DTYPE, "STREAM spectrum must be f32 or bf16");
         if (N > 65535LL * 8) return fail(BCL_ERR_SHAPE, "N=%lld exceeds the stream kernel's grid limit; split the batch", (long long)N);
-        bcl::ProblemDev P{x, spec, bias, y, N, x_row_stride, y_row_stride, p, q, x_dtype, y_dtype, bias ? bias_dtype : BCL_F32, 0};
         cudaError_t e = bcl::launch_stream_single(P, B, spec_dtype, (cudaStream_t)stream);
         return e == cudaSuccess ? BCL_OK : cuda_fail(e, "stream forward launch");
     }
@@ -114,11 +120,27 @@ int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
         if (bcl::gemm_chunk_tokens(N, p, q, B, workspace_bytes) < (N < 128 ? N : 128))
             return fail(BCL_ERR_WORKSPACE, "workspace %zu bytes cannot stage one 128-token chunk (bcl_workspace_bytes gives %zu)", workspace_bytes,
                         bcl::gemm_workspace_bytes(N, p, q, B));
-        bcl::ProblemDev P{x, spec, bias, y, N, x_row_stride, y_row_stride, p, q, x_dtype, y_dtype, bias ? bias_dtype : BCL_F32, 0};
         cudaError_t e = bcl::launch_gemm_forward(P, B, spec, workspace, workspace_bytes, (cudaStream_t)stream);
         return e == cudaSuccess ? BCL_OK : cuda_fail(e, "GEMM forward launch");
     }
     return fail(BCL_ERR_ARG, "unknown spectrum layout %d", layout);
+}
+
+int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
+                const void* spec, int spec_dtype, int layout, int p, int q, int B,
+                const void* bias, int bias_dtype, void* y, int y_dtype, int64_t y_row_stride,
+                void* workspace, size_t workspace_bytes, void* stream) {
+    void* dst[1] = {y};
+    return forward_impl(x, x_dtype, N, x_row_stride, spec, spec_dtype, layout, p, q, B, bias, bias_dtype, dst, 1, y_dtype, y_row_stride,
+                        workspace, workspace_bytes, stream);
+}
+
+int bcl_forward_bcast(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
+                      const void* spec, int spec_dtype, int layout, int p, int q, int B,
+                      const void* bias, int bias_dtype, void* const* y_dsts, int n_dst, int y_dtype, int64_t y_row_stride,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    return forward_impl(x, x_dtype, N, x_row_stride, spec, spec_dtype, layout, p, q, B, bias, bias_dtype, y_dsts, n_dst, y_dtype, y_row_stride,
+                        workspace, workspace_bytes, stream);
 }
 
 void bcl_prefill_geometry(int p, int q, int B, int* F, int* Kp, int* Np, size_t* wf16_off, size_t* wbf16_off, size_t* winv_off) {
@@ -226,7 +248,7 @@ int bcl_group_plan_encode(const bcl_problem* problems, int count, int B, int spe
     for (int g = 0; g < count; ++g) {
         const bcl_problem& P = problems[g];
         pd[g] = bcl::ProblemDev{P.x, P.spec, P.bias, P.y, P.N, P.x_row_stride, P.y_row_stride, P.p, P.q, P.x_dtype, P.y_dtype,
-                                P.bias ? P.bias_dtype : BCL_F32, 0};
+                                P.bias ? P.bias_dtype : BCL_F32, 0, {}};
     }
     // byte-balanced partition of the flattened (problem, row) sequence: CTA b owns the rows whose cumulative
     // weight (q per row = bytes streamed) falls in [b, b+1) * total / num_ctas.

@@ -411,7 +411,10 @@ static int rows_nt(int blocks, int B) { return (size_t)2 * blocks * (B + 2) * 4 
 
 size_t gemm_spectrum_bytes(int p, int q, int B) { return gemm::geometry(p, q, B).total_bytes; }
 
-// workspace = [256-byte status area | Xf chunk | Yf chunk]; chunk tokens chosen so both stay L2-resident
+// workspace = [256-byte status area | Xf chunk | Yf chunk].  Measured on B200 (profiles/r1_prefill_notes.md): three
+// full-size passes through HBM (no chunking, 16384 tokens: 157 us for 4096->4096) beat L2-resident 2048-3072-token chunks
+// (228 us), because each per-chunk launch pays ~5 us of fixed cost (TMEM alloc, DFT-matrix load, pipeline fill, tail) for
+// ~3 us of data movement.  So the default budget only chunks very large batches; BCL_PREFILL_CHUNK_MB overrides it.
 static constexpr size_t kWsHeader = 256;
 
 static size_t chunk_budget() {
@@ -419,7 +422,7 @@ static size_t chunk_budget() {
     if (!v) {
         const char* e = getenv("BCL_PREFILL_CHUNK_MB");
         const long mb = e ? atol(e) : 0;
-        v = (size_t)(mb > 0 ? mb : 56) << 20;
+        v = (size_t)(mb > 0 ? mb : 1024) << 20;
     }
     return v;
 }
@@ -522,7 +525,7 @@ cudaError_t launch_prefill_stage1(const ProblemDev& P, int B, const void* spec_g
 
 cudaError_t launch_prefill_stage3(const ProblemDev& P, int B, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, int impl, cudaStream_t st) {
     const gemm::Geometry g = gemm::geometry(P.p, P.q, B);
-    const bool tc_ok = gemm::dft_tc_supported(B, P.x_dtype) && P.y_dtype == P.x_dtype && spec_gemm != nullptr;
+    const bool tc_ok = gemm::dft_tc_supported(B, P.x_dtype) && P.y_dtype == P.x_dtype && spec_gemm != nullptr && P.n_extra == 0;   // peer destinations: plain stores
     if (impl == 2 && !tc_ok) return cudaErrorNotSupported;
     if (impl != 1 && tc_ok) return gemm::launch_dft_inv_tc(P, g, spec_gemm, n_begin, nc, Yf, status, sm_count(), st);
     return launch_gemm_irfft(P, B, n_begin, nc, Yf, st);

@@ -17,8 +17,10 @@ struct ProblemDev {
     int64_t y_stride;   // elements
     int32_t p, q;
     int32_t x_dtype, y_dtype, bias_dtype;
-    int32_t pad;
+    int32_t n_extra;        // additional destinations of y (same shape / stride / dtype), e.g. peer GPUs' buffers
+    void* y_extra[7];
 };
+constexpr int kMaxExtraDst = 7;
 
 // Header of an encoded group plan (host and device copies are byte-identical).
 struct GroupPlanHeader {

@@ -216,6 +216,7 @@ __device__ __forceinline__ void store_block_epilogue(const ProblemDev& P, int64_
                 v.x += bv.x; v.y += bv.y;
             }
             store_act2(P.y, n * P.y_stride + col, P.y_dtype, v);
+            for (int e = 0; e < P.n_extra; ++e) store_act2(P.y_extra[e], n * P.y_stride + col, P.y_dtype, v);   // fused gather: peers' copies
         }
     }
 }

@@ -1,0 +1,156 @@
+"""Output-block-row sharding of a BC linear across the GPUs of one box (BASELINE.json configs[4]).
+
+The reference has no distributed code.  The BC forward shards naturally along output block-rows: rank g holds
+c[j0_g:j1_g] (and its spectrum), sees the full x (N, in), computes y[:, j0_g*B : j1_g*B] with the same sm_100a kernels as
+the unsharded layer, and the slices meet in ONE exchange step:
+
+    exchange="nccl"   torch.distributed all_gather_into_tensor over NCCL / NVLink, then a column interleave
+    exchange="p2p"    every rank's kernels store their slice straight into EVERY peer's y buffer (symmetric memory,
+                      NVLink peer stores): the gather is fused into the producing kernels, no collective afterwards
+
+Block-rows are split as evenly as possible; when p is not divisible by the world size the NCCL path pads the slices to the
+largest one (70B k/v: p = 4 on 8 ranks leaves ranks idle; ``shard_rows`` reports empty ranges for them).
+One process per GPU (torchrun); data-parallel replicas need none of this.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .patch_llama_fft import BlockCirculantLinear
+
+
+def shard_rows(p: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced split of the p output block-rows: the first p % world ranks get one extra row."""
+    base, extra = divmod(p, world)
+    out, j = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((j, j + n))
+        j += n
+    return out
+
+
+def gather_columns(y_local: torch.Tensor, ranges: List[Tuple[int, int]], B: int, group=None) -> torch.Tensor:
+    """All-gather column slices: y_local is (N, (j1-j0)*B) on every rank -> (N, p*B) everywhere.
+    Slices are padded to the widest one so that the collective is a plain all_gather_into_tensor."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    N = y_local.shape[0]
+    wmax = max(j1 - j0 for j0, j1 in ranges) * B
+    send = y_local
+    if y_local.shape[1] != wmax:
+        send = y_local.new_zeros(N, wmax)
+        send[:, :y_local.shape[1]] = y_local
+    recv = y_local.new_empty(world, N, wmax)
+    dist.all_gather_into_tensor(recv.view(world * N, wmax), send.contiguous(), group=group)
+    p = ranges[-1][1]
+    y = y_local.new_empty(N, p * B)
+    for r, (j0, j1) in enumerate(ranges):
+        if j1 > j0:
+            y[:, j0 * B:j1 * B] = recv[r, :, :(j1 - j0) * B]
+    assert ranges[rank][1] - ranges[rank][0] == y_local.shape[1] // B
+    return y
+
+
+class ShardedBlockCirculantLinear(nn.Module):
+    """Rank-local shard of a BlockCirculantLinear (same parameters c / bias, restricted to this rank's block-rows)."""
+
+    def __init__(self, full: BlockCirculantLinear, group=None, *, exchange: str = "nccl"):
+        super().__init__()
+        if exchange not in ("nccl", "p2p"):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        self.group = group
+        self.exchange = exchange
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.in_features, self.out_features, self.block_size = full.in_features, full.out_features, full.block_size
+        self.ranges = shard_rows(full.out_blocks, self.world)
+        j0, j1 = self.ranges[self.rank]
+        self.j0, self.j1 = j0, j1
+        B = full.block_size
+        self.local: Optional[BlockCirculantLinear] = None
+        if j1 > j0:
+            loc = BlockCirculantLinear(full.in_features, (j1 - j0) * B, block_size=B, bias=full.bias is not None,
+                                       spectrum_dtype=full.spectrum_dtype).to(full.c.device)
+            with torch.no_grad():
+                loc.c.copy_(full.c[j0:j1])
+                if full.bias is not None:
+                    loc.bias.data = full.bias.detach()[j0 * B:j1 * B].clone()
+            self.local = loc.eval() if not full.training else loc
+        self._symm = None       # (N, dtype) -> (symmetric y buffer, peer views) for exchange="p2p"
+
+    # -- p2p: y lives in symmetric memory; each rank's kernels write their slice into every peer's copy ------------
+    def _symmetric_y(self, N: int, dtype: torch.dtype, device):
+        key = (N, dtype)
+        if self._symm is not None and self._symm[0] == key:
+            return self._symm[1], self._symm[2]
+        import torch.distributed._symmetric_memory as symm_mem
+        y = symm_mem.empty(N, self.out_features, dtype=dtype, device=device)
+        hdl = symm_mem.rendezvous(y, self.group if self.group is not None else dist.group.WORLD)
+        peers = [hdl.get_buffer(r, (N, self.out_features), dtype) for r in range(self.world)]
+        self._symm = (key, y, peers, hdl)
+        return y, peers
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        lead = None
+        if x.dim() == 3:
+            lead = x.shape[:2]
+            x = x.reshape(-1, x.shape[-1])
+        elif x.dim() != 2:
+            raise ValueError("Unsupported input dim")
+        B = self.block_size
+        N = x.shape[0]
+        if self.exchange == "nccl":
+            if self.local is not None:
+                y_loc = self.local(x)
+            else:
+                y_loc = x.new_empty(N, 0)
+            y = gather_columns(y_loc, self.ranges, B, self.group)
+        else:
+            y_dtype = x.dtype if (self.local is None or self.local.bias is None) else torch.promote_types(x.dtype, self.local.bias.dtype)
+            y, peers = self._symmetric_y(N, y_dtype, x.device)
+            hdl = self._symm[3]
+            hdl.barrier()                                   # peers finished reading the previous contents
+            if self.local is not None:                      # ONE forward whose epilogue stores into every rank's y
+                bc_forward_bcast(self.local, x, [pv[:, self.j0 * B:self.j1 * B] for pv in peers])
+            hdl.barrier()                                   # every slice of every peer has landed
+        if lead is not None:
+            return y.view(lead[0], lead[1], self.out_features)
+        return y
+
+
+def bc_forward_bcast(layer: BlockCirculantLinear, x: torch.Tensor, dsts: List[torch.Tensor]) -> None:
+    """``bcl_forward_bcast``: one forward of `layer`, result stored to every tensor of `dsts` (same shape/strides/dtype;
+    views into peer-mapped symmetric buffers for the sharded layer)."""
+    import ctypes
+    from . import _cabi
+    from .patch_llama_fft import prefill_workspace
+    if x.stride(-1) != 1 or (x.stride(0) * x.element_size()) % 16 or x.data_ptr() % 16:
+        x = x.contiguous()
+    N = x.shape[0]
+    p, q, B = layer.out_blocks, layer.in_blocks, layer.block_size
+    layout = _cabi.LAYOUT_GEMM if layer._use_prefill_path(N) else _cabi.LAYOUT_STREAM
+    spec = layer.build_spectrum(layout=layout)
+    spec_dt = _cabi.BF16 if layout == _cabi.LAYOUT_GEMM else _cabi.DTYPE[spec.dtype]
+    d0 = dsts[0]
+    assert all(d.shape == (N, p * B) and d.dtype == d0.dtype and d.stride() == d0.stride() for d in dsts)
+    L = _cabi.lib()
+    ws_ptr, ws_bytes = None, 0
+    if layout == _cabi.LAYOUT_GEMM and N > 0:
+        ws = prefill_workspace(x.device, L.bcl_workspace_bytes(N, p, q, B, spec_dt, layout))
+        ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
+    ptrs = (ctypes.c_void_p * len(dsts))(*[d.data_ptr() for d in dsts])
+    bias = layer.bias
+    with torch.cuda.device(x.device):
+        rc = L.bcl_forward_bcast(x.data_ptr(), _cabi.DTYPE[x.dtype], N, x.stride(0), spec.data_ptr(), spec_dt, layout, p, q, B,
+                                 None if bias is None else bias.data_ptr(), 0 if bias is None else _cabi.DTYPE[bias.dtype],
+                                 ptrs, len(dsts), _cabi.DTYPE[d0.dtype], d0.stride(0), ws_ptr, ws_bytes, _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "bcl_forward_bcast")
+
+
+def shard_bc_linear(layer: BlockCirculantLinear, group=None, *, exchange: str = "nccl") -> ShardedBlockCirculantLinear:
+    return ShardedBlockCirculantLinear(layer, group, exchange=exchange)

@@ -334,3 +334,27 @@ def test_gemm_layout_rejects_fp32_spectrum_and_tiny_workspace():
     rc = L.bcl_forward(x.data_ptr(), _cabi.F32, 256, 512, spec.data_ptr(), _cabi.BF16, _cabi.LAYOUT_GEMM, 4, 4, 128, None, 0,
                        y.data_ptr(), _cabi.F32, 512, ws.data_ptr(), ws.numel(), _cabi.stream_ptr(DEV))
     assert rc == -6
+
+
+@pytest.mark.parametrize("N,dtype,sdt", [(1, torch.float16, torch.float32), (5, torch.float32, torch.bfloat16), (300, torch.float16, BF), (300, torch.float32, BF)])
+def test_forward_bcast_writes_every_destination(N, dtype, sdt):
+    """bcl_forward_bcast (the fused gather of sharded layers): one forward, identical results in all destinations --
+    stream kernel (N small), tensor-core path (16-bit I/O falls back to plain stores for peers) and CUDA-core stage 3."""
+    from llama_fft_b200.sharded import bc_forward_bcast
+    g = torch.Generator().manual_seed(N)
+    c = torch.randn(6, 4, 128, generator=g) * 0.05
+    m = bc.BlockCirculantLinear(512, 768, block_size=128, bias=True, spectrum_dtype=sdt)
+    with torch.no_grad():
+        m.c.copy_(c)
+        m.bias.normal_(0, 0.1, generator=g)
+    m = m.to(DEV).eval()
+    x = torch.randn(N, 512, generator=g).to(dtype).to(DEV)
+    with torch.no_grad():
+        y_ref = m(x)
+    big = [torch.full((N, 2048), 7.0, device=DEV, dtype=y_ref.dtype) for _ in range(3)]       # slices of wider buffers, like peers' y
+    dsts = [b[:, 256:1024] for b in big]
+    bc_forward_bcast(m, x, dsts)
+    torch.cuda.synchronize()
+    for b, d in zip(big, dsts):
+        assert_close(d, y_ref, 1e-2 if (sdt == BF and N >= 256) else 1e-6, dtype)
+        assert (b[:, :256] == 7.0).all() and (b[:, 1024:] == 7.0).all()
