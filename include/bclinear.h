@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BCL_ABI_VERSION 6
+#define BCL_ABI_VERSION 7
 
 typedef enum bcl_dtype { BCL_F32 = 0, BCL_F16 = 1, BCL_BF16 = 2 } bcl_dtype;
 
@@ -153,6 +153,18 @@ int bcl_forward_host(const void* host_x, int x_dtype, int64_t N,
 int bcl_forward_grouped_host(const void* dev_plan, const void* host_plan,
                              const void* host_x, void* dev_x, size_t x_bytes,
                              void* host_y, const void* dev_y, size_t y_bytes, void* stream);
+
+/* ---- gradients for calibration -----------------------------------------------------------------------------------
+ * reference: torch autograd through BlockCirculantLinear.forward (src/patch_llama_fft.py:226-275), used by the KL
+ * calibration loop (src/calibrate_bc.py:281-294).  All arithmetic fp32.
+ *   dx  = bcl_forward(gy, spectrum of ct) with ct = bcl_conj_transpose(c):  ct[i,j,t] = c[j,i,(-t) mod B]   (q x p blocks)
+ *   dc[j,i,t] = sum_n sum_r gy[n,j,r] * x[n,i,(r-t) mod B]                   bcl_backward_weights (dc (p,q,B) fp32;
+ *               accumulate != 0 adds to dc, e.g. over token chunks); workspace >= bcl_backward_workspace_bytes(N,p,q,B)
+ *   dbias = sum_n gy[n]  is a plain reduction left to the caller. */
+int bcl_conj_transpose(const float* c, int p, int q, int B, float* ct, void* stream);
+size_t bcl_backward_workspace_bytes(int64_t N, int p, int q, int B);
+int bcl_backward_weights(const void* x, int x_dtype, int64_t x_row_stride, const void* gy, int gy_dtype, int64_t gy_row_stride,
+                         int64_t N, int p, int q, int B, float* dc, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- construction: replaces the Python p*q*B loops of from_linear ------------------------------------------
  * reference: src/patch_llama_fft.py:201-219 + :110-128.  W is (p*B, q*B) row-major of dtype w_dtype;

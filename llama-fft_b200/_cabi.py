@@ -10,7 +10,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BCL_LIB_PATH") or os.path.join(_HERE, "libbclinear.so")   # override: A/B builds when profiling
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 F32, F16, BF16 = 0, 1, 2
 LAYOUT_STREAM, LAYOUT_GEMM = 0, 1
 
@@ -21,7 +21,7 @@ SYMBOLS = (
     "bcl_abi_version", "bcl_last_error", "bcl_spectrum_bytes", "bcl_precompute_spectrum", "bcl_workspace_bytes",
     "bcl_forward", "bcl_group_plan_bytes", "bcl_group_plan_encode", "bcl_forward_grouped", "bcl_forward_host", "bcl_forward_grouped_host",
     "bcl_project_from_dense",
-    "bcl_forward_bcast", "bcl_prefill_geometry", "bcl_prefill_rfft", "bcl_prefill_gemm", "bcl_prefill_irfft",
+    "bcl_forward_bcast", "bcl_conj_transpose", "bcl_backward_workspace_bytes", "bcl_backward_weights", "bcl_prefill_geometry", "bcl_prefill_rfft", "bcl_prefill_gemm", "bcl_prefill_irfft",
 )
 
 
@@ -62,6 +62,10 @@ def lib() -> ctypes.CDLL:
     L.bcl_workspace_bytes.argtypes = [i64, i32, i32, i32, i32, i32]
     L.bcl_forward.argtypes = [vp, i32, i64, i64, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32, i64, vp, sz, vp]
     L.bcl_forward_bcast.argtypes = [vp, i32, i64, i64, vp, i32, i32, i32, i32, i32, vp, i32, ctypes.POINTER(vp), i32, i32, i64, vp, sz, vp]
+    L.bcl_conj_transpose.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.bcl_backward_workspace_bytes.restype = sz
+    L.bcl_backward_workspace_bytes.argtypes = [i64, i32, i32, i32]
+    L.bcl_backward_weights.argtypes = [vp, i32, i64, vp, i32, i64, i64, i32, i32, i32, vp, i32, vp, sz, vp]
     L.bcl_group_plan_bytes.restype = sz
     L.bcl_group_plan_bytes.argtypes = [i32, i32]
     L.bcl_group_plan_encode.argtypes = [ctypes.POINTER(Problem), i32, i32, i32, i32, vp, sz]

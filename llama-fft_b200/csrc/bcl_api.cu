@@ -324,6 +324,39 @@ int bcl_forward_grouped_host(const void* dev_plan, const void* host_plan, const 
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "stream synchronize");
 }
 
+int bcl_conj_transpose(const float* c, int p, int q, int B, float* ct, void* stream) {
+    if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
+    if (p <= 0 || q <= 0) return fail(BCL_ERR_SHAPE, "bad shape p=%d q=%d", p, q);
+    if (!c || !ct || c == ct) return fail(BCL_ERR_ARG, "NULL or aliased c/ct");
+    cudaError_t e = bcl::launch_conj_transpose(c, p, q, B, ct, (cudaStream_t)stream);
+    return e == cudaSuccess ? BCL_OK : cuda_fail(e, "conj-transpose launch");
+}
+
+size_t bcl_backward_workspace_bytes(int64_t N, int p, int q, int B) {
+    if (!valid_B(B) || p <= 0 || q <= 0 || N <= 0) return 0;
+    return bcl::backward_workspace_bytes(N, p, q, B);
+}
+
+int bcl_backward_weights(const void* x, int x_dtype, int64_t x_row_stride, const void* gy, int gy_dtype, int64_t gy_row_stride,
+                         int64_t N, int p, int q, int B, float* dc, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
+    if (p <= 0 || q <= 0 || N < 0) return fail(BCL_ERR_SHAPE, "bad shape p=%d q=%d N=%lld", p, q, (long long)N);
+    if (!valid_dt(x_dtype) || !valid_dt(gy_dtype)) return fail(BCL_ERR_DTYPE, "unknown dtype enum");
+    if (!dc) return fail(BCL_ERR_ARG, "NULL dc");
+    if (N == 0) {
+        if (!accumulate) { cudaError_t e = cudaMemsetAsync(dc, 0, (size_t)p * q * B * 4, (cudaStream_t)stream); if (e != cudaSuccess) return cuda_fail(e, "memset dc"); }
+        return BCL_OK;
+    }
+    if (!x || !gy || !workspace) return fail(BCL_ERR_ARG, "NULL x/gy/workspace");
+    if (x_row_stride < (int64_t)q * B || gy_row_stride < (int64_t)p * B) return fail(BCL_ERR_SHAPE, "row stride smaller than the feature dimension");
+    if (!aligned(x, 16) || !aligned(gy, 16) || !aligned(dc, 16) || !aligned(workspace, 256) || (x_row_stride * bcl::dtype_size(x_dtype)) % 16 ||
+        (gy_row_stride * bcl::dtype_size(gy_dtype)) % 16)
+        return fail(BCL_ERR_ALIGN, "x, gy, dc (16 B), workspace (256 B) and row strides (16 B) must be aligned");
+    if (workspace_bytes < bcl::backward_workspace_bytes(N, p, q, B)) return fail(BCL_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, bcl::backward_workspace_bytes(N, p, q, B));
+    cudaError_t e = bcl::launch_backward_weights(x, x_dtype, x_row_stride, gy, gy_dtype, gy_row_stride, N, p, q, B, dc, accumulate, workspace, (cudaStream_t)stream);
+    return e == cudaSuccess ? BCL_OK : cuda_fail(e, "weight-gradient launch");
+}
+
 int bcl_project_from_dense(const void* W, int w_dtype, int64_t w_row_stride, int p, int q, int B, float* c, void* stream) {
     if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
     if (p <= 0 || q <= 0) return fail(BCL_ERR_SHAPE, "bad shape p=%d q=%d", p, q);

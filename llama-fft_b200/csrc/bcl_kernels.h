@@ -55,6 +55,12 @@ cudaError_t launch_prefill_stage1(const ProblemDev& P, int B, const void* spec_g
 cudaError_t launch_prefill_stage3(const ProblemDev& P, int B, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, int impl, cudaStream_t st);
 cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* Cmat, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+// calibration gradients (bcl_backward.cu)
+size_t backward_workspace_bytes(int64_t N, int p, int q, int B);
+cudaError_t launch_conj_transpose(const float* c, int p, int q, int B, float* ct, cudaStream_t st);
+cudaError_t launch_backward_weights(const void* x, int x_dtype, int64_t x_stride, const void* gy, int gy_dtype, int64_t gy_stride, int64_t N, int p, int q,
+                                    int B, float* dc, int accumulate, void* workspace, cudaStream_t st);
+
 cudaError_t launch_project_from_dense(const void* W, int w_dtype, int64_t w_stride, int p, int q, int B, float* c, cudaStream_t st);
 
 }  // namespace bcl
