@@ -115,7 +115,9 @@ class ClockSampler:
 # CPU reference arm / cpu_baseline: the reference's own CPU path (torch.fft.rfft -> einsum -> irfft), restated in
 # oracle/bc_oracle.py (bit-identical to the reference on the golden vectors), spectra cached like its perf runs.
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(steps, warmup, layers):
+def cpu_reference_steps(steps, warmup, layers, budget_s=None):
+    """Times the reference CPU path on `layers` of the 32 layers per step (distinct weights), scaled to a full token.
+    Stops early once budget_s seconds of timed work are spent (at least 2 steps).  Returns (s per token, threads, steps run)."""
     import torch
     from oracle import bc_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
@@ -131,25 +133,33 @@ def cpu_reference_steps(steps, warmup, layers):
                 O.bc_forward_cached_torch(spec, x)
     for _ in range(warmup):
         one_step()
+    done = 0
     t0 = time.perf_counter()
-    for _ in range(steps):
+    while done < steps:
         one_step()
-    dt = (time.perf_counter() - t0) / steps
-    return dt * (N_LAYERS / layers), torch.get_num_threads()          # seconds per full 32-layer token
+        done += 1
+        if budget_s is not None and done >= 2 and time.perf_counter() - t0 > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / done
+    return dt * (N_LAYERS / layers), torch.get_num_threads(), done          # seconds per full 32-layer token
 
 
 def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path (oracle port: it is pure Python + torch, there is
+    nothing to compile) on this box's host cores.  Each step is a bounded sample -- 4 of the 32 layers, 28 projections with
+    distinct weights, scaled x8 -- and the run stops after ~40 s of timed work however large --steps is."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sec, cores = cpu_reference_steps(args.steps, max(args.warmup, 1), N_LAYERS)
+    layers = 4
+    sec, cores, done = cpu_reference_steps(args.steps, min(max(args.warmup, 1), 3), layers, budget_s=40.0)
     val = 1.0 / sec
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    sample = ("each step = %d of the 32 layers (%d projections, distinct weights), batch 1, fp32, cached rfft(c), per-token time scaled x%d; "
+              "%d steps timed (40 s budget); reference CPU path restated in oracle/bc_oracle.py (torch.fft + einsum)" % (layers, 7 * layers, N_LAYERS // layers, done))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config(args.gpus, weight_sets=1),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "every step = all 224 projections (32 layers x 7), batch 1, fp32, cached rfft(c); "
-                                       "reference CPU path restated in oracle/bc_oracle.py (torch.fft + einsum)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "decode_us_per_layer": sec * 1e6 / N_LAYERS, "gpu_launches": 0}
     print(json.dumps(line))
@@ -243,6 +253,10 @@ def run_ours(args):
     detail = {}
     if world == 1 and not args.no_detail:
         detail = launch_granularity_detail(bc, _cabi, groups[0], shapes, dev, args)
+        try:
+            detail["prefill"] = prefill_detail(bc, _cabi, dev)
+        except Exception as e:                      # noqa: BLE001 -- evidence only; never hides the headline line
+            detail["prefill"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     peak, peak_src = peaks()
     alg, spec_bytes = algorithmic_bytes(args.spectrum)
@@ -254,10 +268,10 @@ def run_ours(args):
             traffic = json.load(f).get("stream_ws_kernel_%s" % args.spectrum)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        sec, cores = cpu_reference_steps(3, 1, 8)
+        sec, cores, done = cpu_reference_steps(6, 1, 4, budget_s=20.0)
         cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "3 timed passes over 8 of the 32 layers (56 projections, distinct weights), batch 1, fp32, cached rfft(c); "
-                         "per-token time scaled x4; reference CPU path restated in oracle/bc_oracle.py"}
+               "sample": "%d timed passes over 4 of the 32 layers (28 projections, distinct weights), batch 1, fp32, cached rfft(c); "
+                         "per-token time scaled x8; reference CPU path restated in oracle/bc_oracle.py" % done}
     line = {"metric": METRIC, "value": world * 1.0 / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config(world, args.spectrum, args.weight_sets),
@@ -320,6 +334,90 @@ def launch_granularity_detail(bc, _cabi, grp_all, shapes, dev, args):
         per_module()
     e1.record(stream); torch.cuda.synchronize()
     out["per_module_eager_ms_per_step"] = e0.elapsed_time(e1) / 5
+    return out
+
+
+PREFILL_TOKENS = 8 * 2048          # BASELINE.json configs[2]: 2048-token prefill x batch 8
+
+
+def prefill_algorithmic_bytes(n=PREFILL_TOKENS):
+    """SURVEY 8(d) with fp16 activations and bf16 spectra, one decoder layer (7 projections)."""
+    return sum(n * inf * 2 + inf * outf // B * 2 + n * outf * 2 for _, inf, outf in LLAMA7B_LAYER)
+
+
+def prefill_algorithmic_flops(n=PREFILL_TOKENS):
+    """4 N p q (B-1) per projection (complex MACs of the per-frequency contraction; DFT flops excluded)."""
+    return sum(4 * n * (outf // B) * (inf // B) * (B - 1) for _, inf, outf in LLAMA7B_LAYER)
+
+
+def time_prefill_layer(bc, _cabi, dev, reps, n=PREFILL_TOKENS, through_host=False):
+    """One decoder layer's 7 BC projections (bf16 spectra -> tcgen05 prefill path) on n tokens of synthetic fp16
+    activations; inputs rotate over two buffer sets (each larger than L2).  Returns (us per layer, per-shape us, status)."""
+    import torch
+    from llama_fft_b200.patch_llama_fft import bc_forward, prefill_status
+    torch.manual_seed(0)
+    layers = {}
+    for name, inf, outf in LLAMA7B_LAYER:
+        if (inf, outf) not in layers:
+            m = bc.BlockCirculantLinear(inf, outf, block_size=B, bias=False, spectrum_dtype=torch.bfloat16).to(dev).eval()
+            layers[(inf, outf)] = (m, m.build_spectrum(layout=_cabi.LAYOUT_GEMM))
+    xs = {d: [torch.randn(n, d, device=dev).half() for _ in range(2)] for d in (4096, 11008)}
+    ys = {d: [torch.empty(n, d, device=dev, dtype=torch.float16) for _ in range(2)] for d in (4096, 11008)}
+    hx = hy = None
+    if through_host:
+        hx = {d: torch.randn(n, d).half().pin_memory() for d in (4096, 11008)}
+        hy = {d: torch.empty(n, d, dtype=torch.float16).pin_memory() for d in (4096, 11008)}
+    stream = torch.cuda.current_stream(dev)
+
+    def one(i, inf, outf):
+        m, spec = layers[(inf, outf)]
+        x, y = xs[inf][i & 1], ys[outf][i & 1]
+        if through_host:
+            x.copy_(hx[inf], non_blocking=True)
+        bc_forward(x, spec, None, outf // B, inf // B, B, out=y, layout=_cabi.LAYOUT_GEMM)
+        if through_host:
+            hy[outf].copy_(y, non_blocking=True)
+            stream.synchronize()
+
+    per_shape = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for (inf, outf) in layers:
+        for i in range(3):
+            one(i, inf, outf)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for i in range(reps):
+            one(i, inf, outf)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        per_shape["%dx%d" % (inf, outf)] = e0.elapsed_time(e1) / reps * 1e3
+    e0.record(stream)
+    for i in range(reps):
+        for _, inf, outf in LLAMA7B_LAYER:
+            one(i, inf, outf)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3, per_shape, prefill_status(dev)
+
+
+def prefill_detail(bc, _cabi, dev, reps=5):
+    import torch
+    us, per_shape, status = time_prefill_layer(bc, _cabi, dev, reps)
+    peak, _ = peaks()
+    alg, fl = prefill_algorithmic_bytes(), prefill_algorithmic_flops()
+    tpeak = 1685.0
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tpeak = float(json.load(f)["bf16_tflops"])
+    except Exception:
+        pass
+    out = {"workload": "llama2-7b-prefill-b128: 7 projections of one layer, %d tokens, fp16 activations, bf16 spectra (tcgen05 path)" % PREFILL_TOKENS,
+           "us_per_layer": us, "tokens_per_s": PREFILL_TOKENS / (us * 1e-6), "us_per_projection_shape": per_shape,
+           "algorithmic_bytes_per_layer": alg, "hbm_frac_of_measured_peak": alg / (us * 1e-6) / 1e9 / peak,
+           "algorithmic_tflops": fl / (us * 1e-6) / 1e12, "tensor_frac_of_measured_bf16_peak": fl / (us * 1e-6) / 1e12 / tpeak,
+           "pipeline_status": status}
+    del us
+    torch.cuda.empty_cache()
     return out
 
 
