@@ -68,6 +68,9 @@ __device__ inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t b
                  : "memory");
 }
 
+__device__ inline void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ inline void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 #ifdef BCL_WS_TIMING
 __device__ inline long long clk() { long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c)); return c; }
 #define TSTART(v) long long v##_t0 = clk()
@@ -123,6 +126,11 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
     }
     fill_twiddles<B>(tw, threadIdx.x, THREADS);
     __syncthreads();
+    // Programmatic dependent launch: let the NEXT grid in the stream start on every SM this grid leaves (no launch bubble,
+    // early finishers pick up the next step at once).  The plan, the problem table and the spectra are constants of the
+    // stream; activations are not: the warps that read x or write y call pdl_wait() first (full completion + visibility
+    // of the previous grid).
+    pdl_launch_dependents();
 
     const int s0 = cta_seg_ptr[blockIdx.x], s1 = cta_seg_ptr[blockIdx.x + 1];
     long long t_a = 0, t_b = 0, t_c = 0;
@@ -254,6 +262,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
         // ===================== X warps: rfft(x) of each segment into the X buffer, one segment ahead of the MAC warps ======
         const int xw = warp - 1 - NM;
         float2* fscr = fscr_all + (size_t)xw * (FC::WARP_SCRATCH_BYTES / 8);
+        pdl_wait();                                                      // x may have been written by the previous grid
         for (int s = s0; s < s1; ++s) {
             const ProblemDev P = problems[segs[s].g];
             { TSTART(x); mbar_wait(&bars->xempty[0], ((uint32_t)(s - s0) & 1u) ^ 1u); TSTOP(x, t_a); }   // MAC warps copied the previous X out
@@ -266,6 +275,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
         // ===================== finishers: one warp per group, alternating =====================
         const int f = warp - 1 - NM - NX;
         float2* fscr = fscr_all + (size_t)(NX + f) * (FC::WARP_SCRATCH_BYTES / 8);
+        pdl_wait();                                                      // y may still be read by the previous grid
         int gi = 0;
         for (int s = s0; s < s1; ++s) {
             const SegWork w = segs[s];
@@ -309,6 +319,11 @@ int pick_stages(int B, int spec_dtype, int nt, int qmax) {
     return S;
 }
 
+static bool pdl_enabled() {                                             // BCL_PDL=0: A/B switch for profiling only
+    static const bool on = !(getenv("BCL_PDL") && getenv("BCL_PDL")[0] == '0');
+    return on;
+}
+
 template <int B, typename SpecT, int RS>
 static cudaError_t launch_t(const GroupPlanHeader& H, const unsigned char* d, cudaStream_t st) {
     auto kern = stream_ws_kernel<B, SpecT, RS>;
@@ -316,8 +331,23 @@ static cudaError_t launch_t(const GroupPlanHeader& H, const unsigned char* d, cu
     const size_t smem = smem_bytes(B, (int)sizeof(SpecT), H.qmax, S);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)H.num_ctas, THREADS, smem, st>>>(reinterpret_cast<const ProblemDev*>(d + H.off_problems), reinterpret_cast<const int*>(d + H.off_cta_ptr),
-                                                     reinterpret_cast<const SegWork*>(d + H.off_segs), S, H.qmax, 0);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)H.num_ctas);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    const ProblemDev* probs = reinterpret_cast<const ProblemDev*>(d + H.off_problems);
+    const int* cta_ptr = reinterpret_cast<const int*>(d + H.off_cta_ptr);
+    const SegWork* segs = reinterpret_cast<const SegWork*>(d + H.off_segs);
+    int qmax = H.qmax, dbg = 0, S_ = S;
+    void* args[] = {(void*)&probs, (void*)&cta_ptr, (void*)&segs, (void*)&S_, (void*)&qmax, (void*)&dbg};
+    e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kern), args);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
