@@ -21,10 +21,11 @@ namespace gemm {
 
 using namespace sm100;
 
-constexpr int DFT_THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int DFT_EPI_WARPS = 8;     // two per TMEM lane quarter (one epilogue warp per SMSP is latency-bound)
+constexpr int DFT_THREADS = 32 * (2 + DFT_EPI_WARPS);   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr int DFT_MAX_STAGES = 6;
 #ifndef BCL_EPI_NBUF
-#define BCL_EPI_NBUF 4
+#define BCL_EPI_NBUF 2
 #endif
 constexpr int DFT_NBUF = BCL_EPI_NBUF;   // staging buffers per epilogue warp: TMA stores in flight
 constexpr uint32_t DFT_EPI_BUF = 4096;   // fwd: [8 f][32 tokens][16 B];  inv: [32 tokens][128 B] swizzled
@@ -68,14 +69,14 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_fwd_tc_kernel(const __grid
     extern __shared__ __align__(1024) unsigned char dft_smem[];
     DftBarriers* bars = reinterpret_cast<DftBarriers*>(dft_smem);
     unsigned char* epi = dft_smem + 1024;                    // 4 warps x 2 x DFT_EPI_BUF
-    unsigned char* wsm = dft_smem + 1024 + 4 * DFT_NBUF * DFT_EPI_BUF;
+    unsigned char* wsm = dft_smem + 1024 + DFT_EPI_WARPS * DFT_NBUF * DFT_EPI_BUF;
     unsigned char* ring = wsm + ATOMS * W_ATOM;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int S = a.stages;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        mbar_init(&bars->tmem_full[0], 1); mbar_init(&bars->tmem_empty[0], 4);
+        mbar_init(&bars->tmem_full[0], 1); mbar_init(&bars->tmem_empty[0], DFT_EPI_WARPS);
         mbar_init(&bars->wfull, 1);
         fence_barrier_init();
     }
@@ -138,12 +139,13 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_fwd_tc_kernel(const __grid
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
             constexpr int FC = B / 16;                                           // chunks of 8 frequencies (16 accumulator columns)
-            for (int fc = 0; fc < FC; ++fc) {
+            const int fc0 = ((warp - 2) >> 2) * (FC / 2), fc1 = fc0 + FC / 2;     // this warp's half of them
+            for (int fc = fc0; fc < fc1; ++fc) {
                 uint32_t r[4][16];
 #pragma unroll
                 for (int ib = 0; ib < 4; ++ib) tmem_ld_32x32b_x16(taddr + (uint32_t)(ib * B + fc * 16), r[ib]);
                 tmem_ld_wait();
-                if (fc == FC - 1) {
+                if (fc == fc1 - 1) {
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->tmem_empty[0]);
@@ -174,6 +176,30 @@ done:
     if (warp == 1) tmem_dealloc(tmem_base, 4 * B >= 32 ? 4 * B : 32);
 }
 
+// One token's 64 outputs (fp32 accumulators, 1/B already folded into Winv) -> 8 swizzled 16-byte chunks of the store tile.
+// Reference epilogue: round to x.dtype (:266), then + bias in that dtype (:270-271).
+template <bool BF16, bool HAS_BIAS>
+__device__ __forceinline__ void store_row(unsigned char* row, int lane, const uint32_t (&r)[64], const void* bias, int col0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float v0 = __uint_as_float(r[8 * c + 2 * e]), v1 = __uint_as_float(r[8 * c + 2 * e + 1]);
+            if constexpr (HAS_BIAS) {
+                const uint32_t bw = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(bias) + col0 + 8 * c + 2 * e));
+                float b0, b1;
+                if constexpr (BF16) { b0 = __uint_as_float(bw << 16); b1 = __uint_as_float(bw & 0xffff0000u); }
+                else { const float2 bf = __half22float2(*reinterpret_cast<const __half2*>(&bw)); b0 = bf.x; b1 = bf.y; }
+                v0 = round_to(v0, BF16 ? BCL_BF16 : BCL_F16) + b0;
+                v1 = round_to(v1, BF16 ? BCL_BF16 : BCL_F16) + b1;
+            }
+            w[e] = pack16(v0, v1, BF16 ? 1 : 0);
+        }
+        *reinterpret_cast<uint4*>(row + ((c ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 // =========================================================================================================
 // inverse: Yf -> y
 // =========================================================================================================
@@ -188,14 +214,14 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_kernel(const __grid
     extern __shared__ __align__(1024) unsigned char dft_smem[];
     DftBarriers* bars = reinterpret_cast<DftBarriers*>(dft_smem);
     unsigned char* epi = dft_smem + 1024;
-    unsigned char* wsm = dft_smem + 1024 + 4 * DFT_NBUF * DFT_EPI_BUF;
+    unsigned char* wsm = dft_smem + 1024 + DFT_EPI_WARPS * DFT_NBUF * DFT_EPI_BUF;
     unsigned char* ring = wsm + ATOMS * W_ATOM;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int S = a.stages;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        for (int i = 0; i < NACC; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 4); }
+        for (int i = 0; i < NACC; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], DFT_EPI_WARPS); }
         mbar_init(&bars->wfull, 1);
         fence_barrier_init();
     }
@@ -249,13 +275,18 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_kernel(const __grid
             if (!__all_sync(0xffffffffu, mbar_wait(&bars->tmem_full[acc], acc_ph))) { atomicExch(a.status, 25); goto done; }
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * B);
-#pragma unroll
-            for (int h = 0; h < ATOMS; ++h) {                                    // 64 output columns = one 128-byte row of the store tile
+            const int wh = (warp - 2) >> 2;                                      // second warp of the lane quarter?
+            const int h0 = (ATOMS == 2) ? wh : 0, h1 = (ATOMS == 2) ? wh + 1 : (wh == 0 ? 1 : 0);
+            if (h0 >= h1) {                                                      // B = 64: one half only, the partner warp just releases
+                tc_fence_before_sync();
+                if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+            }
+            for (int h = h0; h < h1; ++h) {                                      // 64 output columns = one 128-byte row of the store tile
                 uint32_t r[64];
                 tmem_ld_32x32b_x32(taddr + (uint32_t)(h * 64), *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
                 tmem_ld_32x32b_x32(taddr + (uint32_t)(h * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
                 tmem_ld_wait();
-                if (h == ATOMS - 1) {
+                if (h == h1 - 1) {
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
@@ -264,24 +295,13 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_kernel(const __grid
                 __syncwarp();
                 unsigned char* row = stg + (size_t)buf * DFT_EPI_BUF + (size_t)lane * 128;
                 const int col0 = j * B + h * 64;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {                                    // 16-byte chunk c of this token's row, 128-byte swizzle
-                    uint32_t w[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float v0 = __uint_as_float(r[8 * c + 2 * e]), v1 = __uint_as_float(r[8 * c + 2 * e + 1]);    // 1/B is folded into Winv
-                        if (a.bias != nullptr) {                                // round to x.dtype first (:266), then + bias in that dtype (:270-271)
-                            const int dt = a.act_bf16 ? BCL_BF16 : BCL_F16;
-                            const uint32_t bw = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(a.bias) + col0 + 8 * c + 2 * e));
-                            float b0, b1;
-                            if (a.act_bf16) { b0 = __uint_as_float(bw << 16); b1 = __uint_as_float(bw & 0xffff0000u); }
-                            else { const float2 bf = __half22float2(*reinterpret_cast<const __half2*>(&bw)); b0 = bf.x; b1 = bf.y; }
-                            v0 = round_to(v0, dt) + b0;
-                            v1 = round_to(v1, dt) + b1;
-                        }
-                        w[e] = pack16(v0, v1, a.act_bf16);
-                    }
-                    *reinterpret_cast<uint4*>(row + ((c ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                // 16-byte chunks of this token's row, 128-byte swizzle; the dtype / bias variants are separate straight-line code
+                if (a.bias == nullptr) {
+                    if (a.act_bf16) store_row<true, false>(row, lane, r, nullptr, 0);
+                    else store_row<false, false>(row, lane, r, nullptr, 0);
+                } else {
+                    if (a.act_bf16) store_row<true, true>(row, lane, r, a.bias, col0);
+                    else store_row<false, true>(row, lane, r, a.bias, col0);
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -306,7 +326,7 @@ done:
 bool dft_tc_supported(int B, int act_dtype) { return (B == 64 || B == 128) && (act_dtype == BCL_F16 || act_dtype == BCL_BF16); }
 
 static size_t dft_smem_bytes(int B, uint32_t stage_bytes, int stages) {
-    return 1024 + 4 * DFT_NBUF * DFT_EPI_BUF + (size_t)(B / KATOM) * B * 128 + (size_t)stages * stage_bytes;
+    return 1024 + DFT_EPI_WARPS * DFT_NBUF * DFT_EPI_BUF + (size_t)(B / KATOM) * B * 128 + (size_t)stages * stage_bytes;
 }
 static int dft_pick_stages(int B, uint32_t stage_bytes) {
     int s = DFT_MAX_STAGES;

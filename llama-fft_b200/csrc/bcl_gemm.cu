@@ -146,10 +146,11 @@ __global__ void dft_matrix_kernel(int B, __half* __restrict__ wf16, __nv_bfloat1
 //   D_fl[128 tokens x 64] = A_f[128 x Kp] * B_f[64 x Kp]^T   for the 4 frequencies f = 4 fg + fl, 4 TMEM accumulators,
 //   then the epilogue interleaves the four accumulators into 16-byte chunks (j, token, {fl, re/im}) and TMA-stores them.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int GEMM_THREADS = 192;    // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int EPI_WARPS = 8;         // two per TMEM lane quarter: one epilogue warp per SMSP is latency-bound (profiles/r1_prefill_notes.md)
+constexpr int GEMM_THREADS = 32 * (2 + EPI_WARPS);   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr int MAX_STAGES = 8;
 #ifndef BCL_EPI_NBUF
-#define BCL_EPI_NBUF 4
+#define BCL_EPI_NBUF 2
 #endif
 constexpr int EPI_NBUF = BCL_EPI_NBUF;                       // staging buffers per epilogue warp: TMA stores in flight
 constexpr uint32_t A_STAGE_BYTES = TILE_M * KATOM * 2;       // [8 kg][128 tokens][16 B], no swizzle ("interleaved" K-major)
@@ -181,14 +182,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
                                                                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char gemm_smem[];
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(gemm_smem);
-    unsigned char* epi = gemm_smem + 1024;                                       // 4 warps x EPI_NBUF buffers x EPI_BUF_BYTES
-    unsigned char* ring = gemm_smem + 1024 + 4 * EPI_NBUF * EPI_BUF_BYTES;               // stays 1024-byte aligned
+    unsigned char* epi = gemm_smem + 1024;                                       // EPI_WARPS x EPI_NBUF buffers x EPI_BUF_BYTES
+    unsigned char* ring = gemm_smem + 1024 + EPI_WARPS * EPI_NBUF * EPI_BUF_BYTES;               // stays 1024-byte aligned
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int S = a.stages;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY); }
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
     } else {
         // ===================== epilogue warps: TMEM -> registers -> bf16 chunks -> smem -> TMA store =====================
         const int quarter = warp & 3;                                            // TMEM lanes [32*quarter, +32) are this warp's
+        const int half = (warp - 2) >> 2;                                        // which two of the four 8-block column groups
         unsigned char* stg = epi + (size_t)(warp - 2) * EPI_NBUF * EPI_BUF_BYTES;
         int it = 0, buf = 0;
         for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
@@ -254,12 +256,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * SET_COLS);
             const int jc_n = min(4, (a.p - nch * 32 + 7) / 8);                   // 8-block column groups with at least one real block
-            for (int jc = 0; jc < jc_n; ++jc) {
+            const int jc0 = half * 2, jc1 = min(jc_n, jc0 + 2);
+            if (jc0 >= jc1) {                                                    // nothing to read: hand the set back at once
+                tc_fence_before_sync();
+                if (lane == 0) mbar_arrive(&bars->tmem_empty[set]);
+            }
+            for (int jc = jc0; jc < jc1; ++jc) {
                 uint32_t r[4][16];
 #pragma unroll
                 for (int fl = 0; fl < 4; ++fl) tmem_ld_32x32b_x16(taddr + (uint32_t)(fl * NCHUNK + jc * 16), r[fl]);
                 tmem_ld_wait();
-                if (jc == jc_n - 1) {                                            // accumulators fully read: hand the set back to the MMA warp
+                if (jc == jc1 - 1) {                                             // this warp's columns are read: hand the set back to the MMA warp
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->tmem_empty[set]);
@@ -370,7 +377,7 @@ bool make_chunk_map(CUtensorMap* m, const void* base, int64_t ntok, int slabs, i
     return make_tensor_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
-static size_t gemm_smem_bytes(int stages) { return 1024 + 4 * EPI_NBUF * EPI_BUF_BYTES + (size_t)stages * STAGE_BYTES; }
+static size_t gemm_smem_bytes(int stages) { return 1024 + EPI_WARPS * EPI_NBUF * EPI_BUF_BYTES + (size_t)stages * STAGE_BYTES; }
 static int gemm_pick_stages() {
     int s = MAX_STAGES;
     while (s > 2 && gemm_smem_bytes(s) > 225 * 1024) --s;
