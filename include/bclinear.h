@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BCL_ABI_VERSION 7
+#define BCL_ABI_VERSION 8
 
 typedef enum bcl_dtype { BCL_F32 = 0, BCL_F16 = 1, BCL_BF16 = 2 } bcl_dtype;
 
@@ -153,6 +153,19 @@ int bcl_forward_host(const void* host_x, int x_dtype, int64_t N,
 int bcl_forward_grouped_host(const void* dev_plan, const void* host_plan,
                              const void* host_x, void* dev_x, size_t x_bytes,
                              void* host_y, const void* dev_y, size_t y_bytes, void* stream);
+
+/* Pipelined variant for a stream of steps: step k's H2D copy, kernel and D2H copy run on three streams, so the copies
+ * of neighbouring steps overlap the kernel (PCIe is full duplex) and a step costs max(H2D, kernel, D2H) instead of their sum.
+ * A "slot" is one set of staging buffers (host_x, dev_x, dev_y, host_y) plus three events; use >= 2 slots round-robin.
+ * The call only enqueues (no synchronisation): it records ev_in_done / ev_compute_done / ev_out_done for this slot and, when
+ * slot_used_before != 0, first waits on the slot's previous ev_compute_done (dev_x free) and ev_out_done (dev_y free).
+ * host_y of the slot is valid once ev_out_done has completed (cudaEventSynchronize); the caller must not touch host_x /
+ * host_y of a slot that is still in flight.  Streams and events are caller-owned (cudaStream_t / cudaEvent_t as void*). */
+int bcl_forward_grouped_host_pipelined(const void* dev_plan, const void* host_plan,
+                                       const void* host_x, void* dev_x, size_t x_bytes,
+                                       void* host_y, const void* dev_y, size_t y_bytes,
+                                       void* stream_in, void* stream_compute, void* stream_out,
+                                       void* ev_in_done, void* ev_compute_done, void* ev_out_done, int slot_used_before);
 
 /* ---- gradients for calibration -----------------------------------------------------------------------------------
  * reference: torch autograd through BlockCirculantLinear.forward (src/patch_llama_fft.py:226-275), used by the KL

@@ -18,7 +18,7 @@ from .patch_llama_fft import (  # noqa: F401
     enable_cfft_cache, disable_cfft_cache,
 )
 from .fft_utils import circulant_matvec_fft  # noqa: F401
-from .grouped import GroupedBCForward  # noqa: F401
+from .grouped import GroupedBCForward, HostPipe  # noqa: F401
 from .sharded import ShardedBlockCirculantLinear, shard_bc_linear, shard_rows, gather_columns  # noqa: F401
 
 __version__ = "0.1.0"

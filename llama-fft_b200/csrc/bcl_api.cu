@@ -324,6 +324,30 @@ int bcl_forward_grouped_host(const void* dev_plan, const void* host_plan, const 
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "stream synchronize");
 }
 
+int bcl_forward_grouped_host_pipelined(const void* dev_plan, const void* host_plan, const void* host_x, void* dev_x, size_t x_bytes,
+                                       void* host_y, const void* dev_y, size_t y_bytes, void* stream_in, void* stream_compute, void* stream_out,
+                                       void* ev_in_done, void* ev_compute_done, void* ev_out_done, int slot_used_before) {
+    if (!host_x || !dev_x || !host_y || !dev_y) return fail(BCL_ERR_ARG, "NULL host/device staging buffer");
+    if (!ev_in_done || !ev_compute_done || !ev_out_done) return fail(BCL_ERR_ARG, "NULL event");
+    cudaStream_t si = (cudaStream_t)stream_in, sc = (cudaStream_t)stream_compute, so = (cudaStream_t)stream_out;
+    cudaEvent_t ei = (cudaEvent_t)ev_in_done, ec = (cudaEvent_t)ev_compute_done, eo = (cudaEvent_t)ev_out_done;
+    cudaError_t e;
+#define BCL_TRY(call, what) if ((e = (call)) != cudaSuccess) return cuda_fail(e, what)
+    if (slot_used_before) BCL_TRY(cudaStreamWaitEvent(si, ec, 0), "wait: previous kernel of this slot still reads dev_x");
+    BCL_TRY(cudaMemcpyAsync(dev_x, host_x, x_bytes, cudaMemcpyHostToDevice, si), "H2D copy of x");
+    BCL_TRY(cudaEventRecord(ei, si), "record H2D done");
+    BCL_TRY(cudaStreamWaitEvent(sc, ei, 0), "wait: H2D");
+    if (slot_used_before) BCL_TRY(cudaStreamWaitEvent(sc, eo, 0), "wait: previous D2H of this slot still reads dev_y");
+    int rc = bcl_forward_grouped(dev_plan, host_plan, stream_compute);
+    if (rc != BCL_OK) return rc;
+    BCL_TRY(cudaEventRecord(ec, sc), "record kernel done");
+    BCL_TRY(cudaStreamWaitEvent(so, ec, 0), "wait: kernel");
+    BCL_TRY(cudaMemcpyAsync(host_y, dev_y, y_bytes, cudaMemcpyDeviceToHost, so), "D2H copy of y");
+    BCL_TRY(cudaEventRecord(eo, so), "record D2H done");
+#undef BCL_TRY
+    return BCL_OK;
+}
+
 int bcl_conj_transpose(const float* c, int p, int q, int B, float* ct, void* stream) {
     if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
     if (p <= 0 || q <= 0) return fail(BCL_ERR_SHAPE, "bad shape p=%d q=%d", p, q);

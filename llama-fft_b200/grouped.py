@@ -94,9 +94,48 @@ class GroupedBCForward:
         _cabi.check(rc, "bcl_forward_grouped_host")
         return host_y
 
+    def submit_host(self, host_x: torch.Tensor, host_y: torch.Tensor, pipe: "HostPipe") -> None:
+        """Pipelined end-to-end step (``bcl_forward_grouped_host_pipelined``): enqueue H2D(x) / kernel / D2H(y) on the pipe's three
+        streams with this group as the slot; returns without waiting.  Call ``wait_host()`` before reading host_y or
+        resubmitting this group."""
+        if not hasattr(self, "_slot_events"):
+            self._slot_events = [torch.cuda.Event() for _ in range(3)]
+            for ev in self._slot_events:
+                ev.record(pipe.compute)                       # materialise the cudaEvent_t handles
+            self._slot_used = False
+        ei, ec, eo = self._slot_events
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().bcl_forward_grouped_host_pipelined(
+                self.dev_plan.data_ptr(), self.host_plan.data_ptr(),
+                host_x.data_ptr(), self.x_all.data_ptr(), self.x_all.numel() * self.x_all.element_size(),
+                host_y.data_ptr(), self.y_all.data_ptr(), self.y_all.numel() * self.y_all.element_size(),
+                pipe.h2d.cuda_stream, pipe.compute.cuda_stream, pipe.d2h.cuda_stream,
+                ei.cuda_event, ec.cuda_event, eo.cuda_event, 1 if self._slot_used else 0)
+        _cabi.check(rc, "bcl_forward_grouped_host_pipelined")
+        self._slot_used = True
+
+    def wait_host(self) -> None:
+        """Block until this group's last submitted step has delivered host_y."""
+        if getattr(self, "_slot_used", False):
+            self._slot_events[2].synchronize()
+
     def run(self):
         with torch.cuda.device(self.device):
             rc = _cabi.lib().bcl_forward_grouped(self.dev_plan.data_ptr(), self.host_plan.data_ptr(),
                                                  _cabi.stream_ptr(self.device))
         _cabi.check(rc, "bcl_forward_grouped")
         return self.ys
+
+
+class HostPipe:
+    """The three streams of the pipelined host entry point (H2D copies, kernels, D2H copies)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.h2d = torch.cuda.Stream(device)
+        self.compute = torch.cuda.Stream(device)
+        self.d2h = torch.cuda.Stream(device)
+
+    def synchronize(self) -> None:
+        for s in (self.h2d, self.compute, self.d2h):
+            s.synchronize()

@@ -323,3 +323,35 @@ def test_hypothesis_small_shapes():
         assert_close(y, O.bc_forward_torch(c, x, b), 1e-4, dt)
 
     run()
+
+
+def test_pipelined_host_entry_matches_serial_host_entry():
+    """bcl_forward_grouped_host_pipelined (3 streams, 2 slots) delivers the same bytes as the synchronous host call."""
+    g = torch.Generator().manual_seed(21)
+    shapes = [(4, 3), (2, 5), (3, 3)]
+    slots, hxs, hys = [], [], []
+    for s in range(2):
+        specs = []
+        for (p, q) in shapes:
+            m = make_layer(torch.randn(p, q, 128, generator=g) * 0.1, None)
+            specs.append(m.build_spectrum())
+        grp = bc.GroupedBCForward.from_packed(shapes, specs, 1, torch.float16, torch.device(DEV))
+        slots.append(grp)
+        hxs.append(torch.randn(grp.x_all.numel(), generator=g).half().pin_memory())
+        hys.append(torch.zeros(grp.y_all.numel(), dtype=torch.float16).pin_memory())
+    ref = []
+    for grp, hx in zip(slots, hxs):
+        out = torch.zeros(grp.y_all.numel(), dtype=torch.float16).pin_memory()
+        grp.run_host(hx, out)
+        ref.append(out.clone())
+    pipe = bc.HostPipe(torch.device(DEV))
+    for it in range(7):                                     # slots are reused: exercises the dev_x / dev_y hazards
+        k = it % 2
+        slots[k].wait_host()
+        if it >= 2:
+            assert torch.equal(hys[k], ref[k])
+            hys[k].zero_()
+        slots[k].submit_host(hxs[k], hys[k], pipe)
+    for k in range(2):
+        slots[k].wait_host()
+        assert torch.equal(hys[k], ref[k])
