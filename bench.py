@@ -231,13 +231,18 @@ def run_ours(args):
     # C ABI's pipelined host call (bcl_forward_grouped_host_pipelined): three streams, the weight sets double as staging
     # slots, so copies of neighbouring steps overlap the kernel.  The host consumes (waits for) a slot's previous result
     # before resubmitting it, so at most len(groups) steps are in flight and every result reaches the host inside the region.
-    hx = [torch.randn(grp.x_all.numel()).to(torch.float16).pin_memory() for grp in groups]
-    hy = [torch.empty(grp.y_all.numel(), dtype=torch.float16).pin_memory() for grp in groups]
+    n_slots = 4                                               # staging slots (own x/y buffers + plan); slot j streams weight set j % sets
+    slots = list(groups)
+    while len(slots) < n_slots:
+        src = groups[len(slots) % len(groups)]
+        slots.append(bc.GroupedBCForward.from_packed(shapes, src.specs, 1, torch.float16, dev, num_ctas=src.num_ctas))
+    hx = [torch.randn(grp.x_all.numel()).to(torch.float16).pin_memory() for grp in slots]
+    hy = [torch.empty(grp.y_all.numel(), dtype=torch.float16).pin_memory() for grp in slots]
     pipe = bc.HostPipe(dev)
-    for i in range(min(args.warmup, 6)):
-        k = i % len(groups)
-        groups[k].wait_host()
-        groups[k].submit_host(hx[k], hy[k], pipe)
+    for i in range(min(args.warmup, 8)):
+        k = i % n_slots
+        slots[k].wait_host()
+        slots[k].submit_host(hx[k], hy[k], pipe)
     pipe.synchronize()
     barrier()
     e2e_steps = max(10, min(args.steps, 2000))
@@ -245,9 +250,9 @@ def run_ours(args):
     for s in (pipe.h2d, pipe.compute, pipe.d2h):
         s.wait_event(ev0)
     for i in range(e2e_steps):
-        k = i % len(groups)
-        groups[k].wait_host()
-        groups[k].submit_host(hx[k], hy[k], pipe)
+        k = i % n_slots
+        slots[k].wait_host()
+        slots[k].submit_host(hx[k], hy[k], pipe)
     for s in (pipe.h2d, pipe.compute, pipe.d2h):
         fin = torch.cuda.Event()
         fin.record(s)
@@ -258,6 +263,19 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_ms = t2.item() / e2e_steps
+    # PCIe copies alone (what bounds a pipelined step): 20 back-to-back copies each way
+    ev0.record(stream)
+    for _ in range(20):
+        slots[0].x_all.copy_(hx[0], non_blocking=True)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    h2d_us = ev0.elapsed_time(ev1) / 20 * 1e3
+    ev0.record(stream)
+    for _ in range(20):
+        hy[0].copy_(slots[0].y_all, non_blocking=True)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    d2h_us = ev0.elapsed_time(ev1) / 20 * 1e3
     # the same step without overlap (one stream, synchronise per step), for the record
     for i in range(3):
         groups[i % len(groups)].run_host(hx[i % len(groups)], hy[i % len(groups)])
@@ -309,7 +327,8 @@ def run_ours(args):
             "e2e": {"value": world * 1.0 / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": groups[0].x_all.numel() * 2, "d2h_bytes_per_step": groups[0].y_all.numel() * 2,
                     "how": "bcl_forward_grouped_host_pipelined: pinned x -> H2D -> grouped launch -> D2H -> pinned y every step, 3 streams, "
-                           "%d staging slots in flight; unpipelined (bcl_forward_grouped_host, sync per step): %.4f ms/step" % (len(groups), e2e_serial_ms)},
+                           "%d staging slots in flight; copies alone: H2D %.1f us, D2H %.1f us per step; unpipelined (bcl_forward_grouped_host, sync per step): "
+                           "%.4f ms/step" % (n_slots, h2d_us, d2h_us, e2e_serial_ms)},
             "gpu_launches": launches, "clocks": clk.summary(), "detail": detail}
     print(json.dumps(line))
     if world > 1:
