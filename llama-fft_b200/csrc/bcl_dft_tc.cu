@@ -86,11 +86,13 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_fwd_tc_kernel(const __grid
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         if (lane == 0) {
             mbar_arrive_expect_tx(&bars->wfull, ATOMS * W_ATOM);                 // the DFT matrix: resident for the whole kernel
             for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + at * W_ATOM, &tmW, at * KATOM, 0, &bars->wfull);
+            pdl_wait();                                                          // x may come from the previous kernel
             int stage = 0; uint32_t ph = 0;
             for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
                 const int kg = item % a.groups, m = item / a.groups;
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_fwd_tc_kernel(const __grid
                     unsigned char* sa = ring + (size_t)stage * STAGE;
                     mbar_arrive_expect_tx(&bars->full[stage], STAGE);
                     for (int at = 0; at < ATOMS; ++at)                           // columns past in_features are zero-filled
-                        tma_load_2d(sa + at * A_ATOM, &tmX, (4 * kg + ib) * B + at * KATOM, (int)(a.n_begin + (int64_t)m * TILE_M), &bars->full[stage]);
+                        tma_load_2d_hint(sa + at * A_ATOM, &tmX, (4 * kg + ib) * B + at * KATOM, (int)(a.n_begin + (int64_t)m * TILE_M), &bars->full[stage], L2_EVICT_FIRST);
                     if (++stage == S) { stage = 0; ph ^= 1u; }
                 }
             }
@@ -132,6 +134,7 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_fwd_tc_kernel(const __grid
     } else {
         const int quarter = warp & 3;
         unsigned char* stg = epi + (size_t)(warp - 2) * DFT_NBUF * DFT_EPI_BUF;
+        pdl_wait();                                                              // Xf may still be read by the previous kernel
         int it = 0, buf = 0;
         for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
             const int kg = item % a.groups, m = item / a.groups;
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_fwd_tc_kernel(const __grid
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_4d(&tmXf, 0, m * (TILE_M / TOK_GROUP) + quarter, kg, fc * 8, stg + (size_t)buf * DFT_EPI_BUF);
+                    tma_store_4d_hint(&tmXf, 0, m * (TILE_M / TOK_GROUP) + quarter, kg, fc * 8, stg + (size_t)buf * DFT_EPI_BUF, L2_EVICT_LAST);
                     tma_store_commit();
                 }
                 if (++buf == DFT_NBUF) buf = 0;
@@ -231,17 +234,19 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_kernel(const __grid
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         if (lane == 0) {
             mbar_arrive_expect_tx(&bars->wfull, ATOMS * W_ATOM);
             for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + at * W_ATOM, &tmW, at * KATOM, 0, &bars->wfull);
+            pdl_wait();                                                          // Yf comes from the previous kernel
             int stage = 0; uint32_t ph = 0;
             for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
                 const int j = item % a.groups, m = item / a.groups;
                 if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 21); goto done; }
                 mbar_arrive_expect_tx(&bars->full[stage], STAGE);
-                tma_load_4d(ring + (size_t)stage * STAGE, &tmYf, 0, m * (TILE_M / TOK_GROUP), j, 0, &bars->full[stage]);
+                tma_load_4d_hint(ring + (size_t)stage * STAGE, &tmYf, 0, m * (TILE_M / TOK_GROUP), j, 0, &bars->full[stage], L2_EVICT_FIRST);
                 if (++stage == S) { stage = 0; ph ^= 1u; }
             }
         }
@@ -268,6 +273,7 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_kernel(const __grid
     } else {
         const int quarter = warp & 3;
         unsigned char* stg = epi + (size_t)(warp - 2) * DFT_NBUF * DFT_EPI_BUF;
+        pdl_wait();                                                              // y may still be read by the previous kernel
         int it = 0, buf = 0;
         for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
             const int j = item % a.groups, m = item / a.groups;
@@ -366,10 +372,10 @@ cudaError_t launch_dft_fwd_tc(const ProblemDev& P, const Geometry& g, const void
     cudaError_t e;
     if (B == 128) {
         if ((e = cudaFuncSetAttribute(dft_fwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        dft_fwd_tc_kernel<128><<<(unsigned)grid, DFT_THREADS, smem, st>>>(tmX, tmW, tmXf, a);
+        return launch_pdl(dft_fwd_tc_kernel<128>, (unsigned)grid, DFT_THREADS, smem, st, tmX, tmW, tmXf, a);
     } else {
         if ((e = cudaFuncSetAttribute(dft_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        dft_fwd_tc_kernel<64><<<(unsigned)grid, DFT_THREADS, smem, st>>>(tmX, tmW, tmXf, a);
+        return launch_pdl(dft_fwd_tc_kernel<64>, (unsigned)grid, DFT_THREADS, smem, st, tmX, tmW, tmXf, a);
     }
     return cudaGetLastError();
 }
@@ -399,10 +405,10 @@ cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void
     cudaError_t e;
     if (B == 128) {
         if ((e = cudaFuncSetAttribute(dft_inv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        dft_inv_tc_kernel<128><<<(unsigned)grid, DFT_THREADS, smem, st>>>(tmYf, tmW, tmOut, a);
+        return launch_pdl(dft_inv_tc_kernel<128>, (unsigned)grid, DFT_THREADS, smem, st, tmYf, tmW, tmOut, a);
     } else {
         if ((e = cudaFuncSetAttribute(dft_inv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        dft_inv_tc_kernel<64><<<(unsigned)grid, DFT_THREADS, smem, st>>>(tmYf, tmW, tmOut, a);
+        return launch_pdl(dft_inv_tc_kernel<64>, (unsigned)grid, DFT_THREADS, smem, st, tmYf, tmW, tmOut, a);
     }
     return cudaGetLastError();
 }

@@ -161,7 +161,7 @@ constexpr int SET_COLS = 4 * NCHUNK;                         // TMEM columns of 
 
 struct GemmArgs {
     int* status;
-    int ntok, p, KG, k_atoms, m_tiles, NCH, num_items, stages;
+    int ntok, p, KG, FG, k_atoms, m_tiles, NCH, num_items, stages;
 };
 
 struct GemmBarriers {
@@ -171,11 +171,13 @@ struct GemmBarriers {
     uint32_t pad;
 };
 
+// Token tiles are walked from the LAST one down: the rfft stage wrote Xf in ascending tile order, so its most recent
+// ~100 MB are still in L2 when this kernel starts; the inverse stage then walks up again and finds this kernel's last Yf.
 __device__ __forceinline__ void decode_item(const GemmArgs& a, int item, int& fg, int& m, int& nch) {
     nch = item % a.NCH;
     const int r = item / a.NCH;
-    m = r % a.m_tiles;
-    fg = r / a.m_tiles;
+    fg = r % a.FG;
+    m = a.m_tiles - 1 - r / a.FG;
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -198,10 +200,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            pdl_wait();                                                          // Xf comes from the previous kernel
             int stage = 0; uint32_t ph = 0;
             for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
                 int fg, m, nch; decode_item(a, item, fg, m, nch);
@@ -210,8 +214,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
                         if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 1); goto done; }
                         unsigned char* sa = ring + (size_t)stage * STAGE_BYTES;
                         mbar_arrive_expect_tx(&bars->full[stage], STAGE_BYTES);
-                        tma_load_4d(sa, &tmA, 0, m * (TILE_M / TOK_GROUP), ka * 8, 4 * fg + fl, &bars->full[stage]);
-                        tma_load_3d(sa + A_STAGE_BYTES, &tmB, ka * KATOM, nch * NCHUNK, 4 * fg + fl, &bars->full[stage]);
+                        tma_load_4d_hint(sa, &tmA, 0, m * (TILE_M / TOK_GROUP), ka * 8, 4 * fg + fl, &bars->full[stage], L2_EVICT_FIRST);   // read once
+                        tma_load_3d_hint(sa + A_STAGE_BYTES, &tmB, ka * KATOM, nch * NCHUNK, 4 * fg + fl, &bars->full[stage], L2_EVICT_LAST);   // re-read by every tile
                         if (++stage == S) { stage = 0; ph ^= 1u; }
                     }
                 }
@@ -248,6 +252,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
         const int quarter = warp & 3;                                            // TMEM lanes [32*quarter, +32) are this warp's
         const int half = (warp - 2) >> 2;                                        // which two of the four 8-block column groups
         unsigned char* stg = epi + (size_t)(warp - 2) * EPI_NBUF * EPI_BUF_BYTES;
+        pdl_wait();                                                              // Yf may still be read by the previous kernel
         int it = 0, buf = 0;
         for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
             int fg, m, nch; decode_item(a, item, fg, m, nch);
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_4d(&tmY, 0, m * (TILE_M / TOK_GROUP) + quarter, nch * 32 + jc * 8, fg, stg + (size_t)buf * EPI_BUF_BYTES);
+                    tma_store_4d_hint(&tmY, 0, m * (TILE_M / TOK_GROUP) + quarter, nch * 32 + jc * 8, fg, stg + (size_t)buf * EPI_BUF_BYTES, L2_EVICT_LAST);   // the next stage reads it
                     tma_store_commit();
                 }
                 if (++buf == EPI_NBUF) buf = 0;
@@ -502,7 +507,7 @@ cudaError_t launch_gemm_mma(const void* Xf, const void* Cmat, void* Yf, int* sta
     if (!gemm::make_chunk_map(&tmY, Yf, nc, p, g.FG, 1, 8, 1)) return cudaErrorNotSupported;
     gemm::GemmArgs a{};
     a.status = status;
-    a.ntok = nc; a.p = p; a.KG = g.KG; a.k_atoms = (g.Kp + gemm::KATOM - 1) / gemm::KATOM; a.NCH = g.NCH;
+    a.ntok = nc; a.p = p; a.KG = g.KG; a.FG = g.FG; a.k_atoms = (g.Kp + gemm::KATOM - 1) / gemm::KATOM; a.NCH = g.NCH;
     a.m_tiles = (nc + gemm::TILE_M - 1) / gemm::TILE_M;
     a.num_items = a.m_tiles * g.FG * g.NCH;
     a.stages = gemm::gemm_pick_stages();
@@ -511,8 +516,7 @@ cudaError_t launch_gemm_mma(const void* Xf, const void* Cmat, void* Yf, int* sta
     if (e != cudaSuccess) return e;
     const int grid = a.num_items < max_ctas ? a.num_items : max_ctas;
     if (grid < 1) return cudaSuccess;
-    gemm::freq_gemm_kernel<<<(unsigned)grid, gemm::GEMM_THREADS, smem, st>>>(tmA, tmB, tmY, a);
-    return cudaGetLastError();
+    return gemm::launch_pdl(gemm::freq_gemm_kernel, (unsigned)grid, gemm::GEMM_THREADS, smem, st, tmA, tmB, tmY, a);
 }
 
 static int sm_count() {

@@ -47,6 +47,12 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* b, uint32_t parity) {
     return mbar_wait_slow(addr, parity);
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// launch_dependents: the next grid of the stream may start on SMs this grid has left.  wait: block until the previous
+// grid has completed and its memory is visible -- call before the first access to anything it may have produced or still read.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- proxies / fences ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -72,6 +78,33 @@ __device__ __forceinline__ void tma_load_4d(void* dst_smem, const void* tmap, in
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                  ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
                  : "memory");
+}
+// L2 eviction-priority hints (the fixed createpolicy encodings): streamed-once data must not push out what the next stage re-reads.
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* dst_smem, const void* tmap, int c0, int c1, int c2, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_hint(void* dst_smem, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+                 ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const void* tmap, int c0, int c1, const void* src_smem, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(src_smem)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_hint(const void* tmap, int c0, int c1, int c2, int c3, const void* src_smem, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3, %4}], [%5], %6;"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(src_smem)), "l"(policy) : "memory");
 }
 // Tiled stores shared -> global (bulk async-group completion).  Writes outside the tensor's bounds are dropped.
 __device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, const void* src_smem) {
