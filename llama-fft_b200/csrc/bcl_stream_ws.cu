@@ -168,13 +168,24 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
         int stage = 0; uint32_t ph = 0;
         int gi = 0;
         RowAcc<B, NT> acc;
+        if (s0 < s1) {
+            // First segment: nothing to multiply yet, so the MAC warps help the X warps with rfft(x) (all NM + NX warps, one
+            // pass for q <= 48 instead of three): the start-up latency during which the ring is full and HBM idles.
+            // Scratch: the (still unused) group buffers.
+            pdl_wait();                                                  // x may have been written by the previous grid
+            const ProblemDev P0 = problems[segs[s0].g];
+            TSTART(x0);
+            load_x_spectrum<B, NT, NM + NX>(P0, 0, xs, tw, reinterpret_cast<float2*>(part) + (size_t)m * (FC::WARP_SCRATCH_BYTES / 8), lane, m);
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * (NM + NX)) : "memory");
+            TSTOP(x0, t_a);
+        }
         for (int s = s0; s < s1; ++s) {
             const SegWork w = segs[s];
             const int q = problems[w.g].q;
             const int rows = w.j1 - w.j0;
             // my slice of this segment's x spectrum -> registers (blocks i = cs*CB + m + NM*u), then free the X buffer at once
             float xr[RS][BPS][CH][CW];
-            { TSTART(x); mbar_wait(&bars->xfull[0], (uint32_t)(s - s0) & 1u); TSTOP(x, t_a); }
+            if (s > s0) { TSTART(x); mbar_wait(&bars->xfull[0], (uint32_t)(s - s0 - 1) & 1u); TSTOP(x, t_a); }
 #pragma unroll
             for (int cs = 0; cs < RS; ++cs)
 #pragma unroll
@@ -263,7 +274,14 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
         const int xw = warp - 1 - NM;
         float2* fscr = fscr_all + (size_t)xw * (FC::WARP_SCRATCH_BYTES / 8);
         pdl_wait();                                                      // x may have been written by the previous grid
-        for (int s = s0; s < s1; ++s) {
+        if (s0 < s1) {                                                   // first segment: together with the MAC warps (see there)
+            const ProblemDev P0 = problems[segs[s0].g];
+            TSTART(y0);
+            load_x_spectrum<B, NT, NM + NX>(P0, 0, xs, tw, fscr, lane, NM + xw);
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * (NM + NX)) : "memory");
+            TSTOP(y0, t_b);
+        }
+        for (int s = s0 + 1; s < s1; ++s) {
             const ProblemDev P = problems[segs[s].g];
             { TSTART(x); mbar_wait(&bars->xempty[0], ((uint32_t)(s - s0) & 1u) ^ 1u); TSTOP(x, t_a); }   // MAC warps copied the previous X out
             { TSTART(y); load_x_spectrum<B, NT, NX>(P, 0, xs, tw, fscr, lane, xw); TSTOP(y, t_b); }
