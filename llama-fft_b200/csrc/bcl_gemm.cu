@@ -19,6 +19,7 @@
 #include "bcl_stream_parts.cuh"
 #include "bcl_sm100.cuh"
 #include "bcl_gemm.cuh"
+#include "bcl_prefill_bodies.cuh"
 
 namespace bcl {
 namespace gemm {
@@ -142,164 +143,12 @@ __global__ void dft_matrix_kernel(int B, __half* __restrict__ wf16, __nv_bfloat1
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// stage 2: batched per-frequency GEMM on tcgen05.  Work item = (frequency group of 4, 128-token tile, 64-column chunk):
-//   D_fl[128 tokens x 64] = A_f[128 x Kp] * B_f[64 x Kp]^T   for the 4 frequencies f = 4 fg + fl, 4 TMEM accumulators,
-//   then the epilogue interleaves the four accumulators into 16-byte chunks (j, token, {fl, re/im}) and TMA-stores them.
+// stage 2 stand-alone: the per-frequency tcgen05 GEMM (body: bcl_prefill_bodies.cuh)
 // ---------------------------------------------------------------------------------------------------------
-constexpr int EPI_WARPS = 8;         // two per TMEM lane quarter: one epilogue warp per SMSP is latency-bound (profiles/r1_prefill_notes.md)
-constexpr int GEMM_THREADS = 32 * (2 + EPI_WARPS);   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
-constexpr int MAX_STAGES = 8;
-#ifndef BCL_EPI_NBUF
-#define BCL_EPI_NBUF 2
-#endif
-constexpr int EPI_NBUF = BCL_EPI_NBUF;                       // staging buffers per epilogue warp: TMA stores in flight
-constexpr uint32_t A_STAGE_BYTES = TILE_M * KATOM * 2;       // [8 kg][128 tokens][16 B], no swizzle ("interleaved" K-major)
-constexpr uint32_t B_STAGE_BYTES = NCHUNK * KATOM * 2;       // 64 rows x 128 B, 128-byte swizzle
-constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr uint32_t EPI_BUF_BYTES = 8 * 32 * 16;              // [8 j][32 tokens][16 B]
-constexpr int SET_COLS = 4 * NCHUNK;                         // TMEM columns of one accumulator set (4 frequencies)
-
-struct GemmArgs {
-    int* status;
-    int ntok, p, KG, FG, k_atoms, m_tiles, NCH, num_items, stages;
-};
-
-struct GemmBarriers {
-    uint64_t full[MAX_STAGES], empty[MAX_STAGES];
-    uint64_t tmem_full[2], tmem_empty[2];
-    uint32_t tmem_base;
-    uint32_t pad;
-};
-
-// Token tiles are walked from the LAST one down: the rfft stage wrote Xf in ascending tile order, so its most recent
-// ~100 MB are still in L2 when this kernel starts; the inverse stage then walks up again and finds this kernel's last Yf.
-__device__ __forceinline__ void decode_item(const GemmArgs& a, int item, int& fg, int& m, int& nch) {
-    nch = item % a.NCH;
-    const int r = item / a.NCH;
-    fg = r % a.FG;
-    m = a.m_tiles - 1 - r / a.FG;
-}
-
 __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char gemm_smem[];
-    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(gemm_smem);
-    unsigned char* epi = gemm_smem + 1024;                                       // EPI_WARPS x EPI_NBUF buffers x EPI_BUF_BYTES
-    unsigned char* ring = gemm_smem + 1024 + EPI_WARPS * EPI_NBUF * EPI_BUF_BYTES;               // stays 1024-byte aligned
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int S = a.stages;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], EPI_WARPS); }
-        fence_barrier_init();
-    }
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY); }
-    if (warp == 1) tmem_alloc(&bars->tmem_base, 2 * SET_COLS);
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = bars->tmem_base;
-    pdl_launch_dependents();
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            pdl_wait();                                                          // Xf comes from the previous kernel
-            int stage = 0; uint32_t ph = 0;
-            for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
-                int fg, m, nch; decode_item(a, item, fg, m, nch);
-                for (int fl = 0; fl < 4; ++fl) {
-                    for (int ka = 0; ka < a.k_atoms; ++ka) {
-                        if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 1); goto done; }
-                        unsigned char* sa = ring + (size_t)stage * STAGE_BYTES;
-                        mbar_arrive_expect_tx(&bars->full[stage], STAGE_BYTES);
-                        tma_load_4d_hint(sa, &tmA, 0, m * (TILE_M / TOK_GROUP), ka * 8, 4 * fg + fl, &bars->full[stage], L2_EVICT_FIRST);   // read once
-                        tma_load_3d_hint(sa + A_STAGE_BYTES, &tmB, ka * KATOM, nch * NCHUNK, 4 * fg + fl, &bars->full[stage], L2_EVICT_LAST);   // re-read by every tile
-                        if (++stage == S) { stage = 0; ph ^= 1u; }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(TILE_M, NCHUNK);
-            int stage = 0; uint32_t ph = 0; int it = 0;
-            for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
-                const int set = it & 1; const uint32_t set_ph = (uint32_t)(it >> 1) & 1u;
-                if (!mbar_wait(&bars->tmem_empty[set], set_ph ^ 1u)) { atomicExch(a.status, 2); goto done; }   // epilogue drained this set
-                tc_fence_after_sync();
-                for (int fl = 0; fl < 4; ++fl) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(set * SET_COLS + fl * NCHUNK);
-                    for (int ka = 0; ka < a.k_atoms; ++ka) {
-                        if (!mbar_wait(&bars->full[stage], ph)) { atomicExch(a.status, 3); goto done; }
-                        tc_fence_after_sync();
-                        const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE_BYTES);
-                        const uint64_t bdesc = umma_desc_k_sw128(sa + A_STAGE_BYTES);
-                        const int ks = min(4, (a.KG - ka * 8) / 2);
-                        for (int kk = 0; kk < ks; ++kk)                          // one k-step = 16 elements = 2 kg slabs of 2048 bytes
-                            umma_bf16_ss(d_tmem, umma_desc_k_nosw(sa + (uint32_t)kk * 4096u, 128u, 2048u), bdesc + (uint64_t)(2 * kk), idesc, (ka | kk) != 0 ? 1u : 0u);
-                        umma_commit(&bars->empty[stage]);                        // smem stage reusable once these MMAs retire
-                        if (++stage == S) { stage = 0; ph ^= 1u; }
-                    }
-                }
-                umma_commit(&bars->tmem_full[set]);                              // all 4 accumulators complete -> epilogue
-            }
-        }
-    } else {
-        // ===================== epilogue warps: TMEM -> registers -> bf16 chunks -> smem -> TMA store =====================
-        const int quarter = warp & 3;                                            // TMEM lanes [32*quarter, +32) are this warp's
-        const int half = (warp - 2) >> 2;                                        // which two of the four 8-block column groups
-        unsigned char* stg = epi + (size_t)(warp - 2) * EPI_NBUF * EPI_BUF_BYTES;
-        pdl_wait();                                                              // Yf may still be read by the previous kernel
-        int it = 0, buf = 0;
-        for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
-            int fg, m, nch; decode_item(a, item, fg, m, nch);
-            const int set = it & 1; const uint32_t set_ph = (uint32_t)(it >> 1) & 1u;
-            if (!__all_sync(0xffffffffu, mbar_wait(&bars->tmem_full[set], set_ph))) { atomicExch(a.status, 4); goto done; }
-            tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * SET_COLS);
-            const int jc_n = min(4, (a.p - nch * 32 + 7) / 8);                   // 8-block column groups with at least one real block
-            const int jc0 = half * 2, jc1 = min(jc_n, jc0 + 2);
-            if (jc0 >= jc1) {                                                    // nothing to read: hand the set back at once
-                tc_fence_before_sync();
-                if (lane == 0) mbar_arrive(&bars->tmem_empty[set]);
-            }
-            for (int jc = jc0; jc < jc1; ++jc) {
-                uint32_t r[4][16];
-#pragma unroll
-                for (int fl = 0; fl < 4; ++fl) tmem_ld_32x32b_x16(taddr + (uint32_t)(fl * NCHUNK + jc * 16), r[fl]);
-                tmem_ld_wait();
-                if (jc == jc1 - 1) {                                             // this warp's columns are read: hand the set back to the MMA warp
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->tmem_empty[set]);
-                }
-                if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();              // the store that last read this buffer has finished
-                __syncwarp();
-                uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)buf * EPI_BUF_BYTES) + lane;
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                    dst[jj * 32] = make_uint4(pack_bf16(__uint_as_float(r[0][2 * jj]), __uint_as_float(r[0][2 * jj + 1])),
-                                              pack_bf16(__uint_as_float(r[1][2 * jj]), __uint_as_float(r[1][2 * jj + 1])),
-                                              pack_bf16(__uint_as_float(r[2][2 * jj]), __uint_as_float(r[2][2 * jj + 1])),
-                                              pack_bf16(__uint_as_float(r[3][2 * jj]), __uint_as_float(r[3][2 * jj + 1])));
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_4d_hint(&tmY, 0, m * (TILE_M / TOK_GROUP) + quarter, nch * 32 + jc * 8, fg, stg + (size_t)buf * EPI_BUF_BYTES, L2_EVICT_LAST);   // the next stage reads it
-                    tma_store_commit();
-                }
-                if (++buf == EPI_NBUF) buf = 0;
-            }
-        }
-        if (lane == 0) tma_store_wait<0>();
-    }
-done:
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * SET_COLS);
+    freq_gemm_body(gemm_smem, tmA, tmB, tmY, a, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -389,6 +238,28 @@ static int gemm_pick_stages() {
     return s;
 }
 
+// Xf [F][KG][ntp][8], Cmat [F][Np][Kp] -> Yf [FG][p][ntp][8] (ntp = nc rounded up to 32)
+bool prep_gemm(const void* Xf, const void* Cmat, void* Yf, int* status, const Geometry& g, int nc, StageLaunch<GemmArgs>& L) {
+    if (!make_chunk_map(&L.tm_in, Xf, nc, g.KG, g.F, TILE_M / TOK_GROUP, 8, 1)) return false;
+    {
+        const uint64_t dims[3] = {(uint64_t)g.Kp, (uint64_t)g.Np, (uint64_t)g.F};
+        const uint64_t strides[2] = {(uint64_t)g.Kp * 2, (uint64_t)g.Kp * g.Np * 2};
+        const uint32_t box[3] = {KATOM, NCHUNK, 1};
+        if (!make_tensor_map(&L.tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Cmat, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
+    }
+    if (!make_chunk_map(&L.tm_out, Yf, nc, g.p, g.FG, 1, 8, 1)) return false;
+    GemmArgs& a = L.a;
+    a = GemmArgs{};
+    a.status = status;
+    a.ntok = nc; a.p = g.p; a.KG = g.KG; a.FG = g.FG; a.k_atoms = (g.Kp + KATOM - 1) / KATOM; a.NCH = g.NCH;
+    a.m_tiles = (nc + TILE_M - 1) / TILE_M;
+    a.num_items = a.m_tiles * g.FG * g.NCH;
+    a.stages = gemm_pick_stages();
+    L.smem = gemm_smem_bytes(a.stages);
+    a.trace = trace_ptr(2);
+    return true;
+}
+
 template <typename K> static cudaError_t set_smem(K kernel, size_t bytes) {
     if (bytes <= 48 * 1024) return cudaSuccess;
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -441,10 +312,13 @@ static size_t chunk_budget() {
 
 static size_t per_token_ws(const gemm::Geometry& g) { return (size_t)g.F * (g.Kp + 2 * g.p) * 2; }
 
+// workspace = [256-byte status area | tile counters of the fused launch | Xf | Yf]
+static size_t ws_fixed(int64_t N) { return kWsHeader + gemm::fused_counter_bytes(N) + 512; }
+
 int64_t gemm_chunk_tokens(int64_t N, int p, int q, int B, size_t workspace_bytes) {
     const gemm::Geometry g = gemm::geometry(p, q, B);
-    if (workspace_bytes <= kWsHeader + 512) return 0;
-    int64_t nc = (int64_t)((workspace_bytes - kWsHeader - 512) / per_token_ws(g));
+    if (workspace_bytes <= ws_fixed(N)) return 0;
+    int64_t nc = (int64_t)((workspace_bytes - ws_fixed(N)) / per_token_ws(g));
     if (nc >= gemm::token_pitch(N)) return N;
     return nc / gemm::TILE_M * gemm::TILE_M;
 }
@@ -454,7 +328,7 @@ size_t gemm_workspace_bytes(int64_t N, int p, int q, int B) {
     int64_t nc = (int64_t)(chunk_budget() / per_token_ws(g)) / gemm::TILE_M * gemm::TILE_M;
     if (nc < gemm::TILE_M) nc = gemm::TILE_M;
     if (nc > N) nc = gemm::token_pitch(N);
-    return kWsHeader + 512 + (size_t)nc * per_token_ws(g);
+    return ws_fixed(N) + (size_t)nc * per_token_ws(g);
 }
 
 cudaError_t launch_spectrum_gemm(const float* c, void* spec, int p, int q, int B, cudaStream_t st) {
@@ -493,30 +367,16 @@ cudaError_t launch_gemm_irfft(const ProblemDev& P, int B, int64_t n_begin, int n
 #undef BCL_R3
 }
 
-// Xf [F][KG][ntp][8], Cmat [F][Np][Kp] -> Yf [FG][p][ntp][8] (ntp = nc rounded up to 32).  status: device int, set non-zero if a pipeline wait timed out.
+// status: device int, set non-zero if a pipeline wait timed out.
 cudaError_t launch_gemm_mma(const void* Xf, const void* Cmat, void* Yf, int* status, int p, int q, int B, int nc, int max_ctas, cudaStream_t st) {
     const gemm::Geometry g = gemm::geometry(p, q, B);
-    CUtensorMap tmA, tmB, tmY;
-    if (!gemm::make_chunk_map(&tmA, Xf, nc, g.KG, g.F, gemm::TILE_M / gemm::TOK_GROUP, 8, 1)) return cudaErrorNotSupported;
-    {
-        const uint64_t dims[3] = {(uint64_t)g.Kp, (uint64_t)g.Np, (uint64_t)g.F};
-        const uint64_t strides[2] = {(uint64_t)g.Kp * 2, (uint64_t)g.Kp * g.Np * 2};
-        const uint32_t box[3] = {gemm::KATOM, gemm::NCHUNK, 1};
-        if (!gemm::make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Cmat, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return cudaErrorNotSupported;
-    }
-    if (!gemm::make_chunk_map(&tmY, Yf, nc, p, g.FG, 1, 8, 1)) return cudaErrorNotSupported;
-    gemm::GemmArgs a{};
-    a.status = status;
-    a.ntok = nc; a.p = p; a.KG = g.KG; a.FG = g.FG; a.k_atoms = (g.Kp + gemm::KATOM - 1) / gemm::KATOM; a.NCH = g.NCH;
-    a.m_tiles = (nc + gemm::TILE_M - 1) / gemm::TILE_M;
-    a.num_items = a.m_tiles * g.FG * g.NCH;
-    a.stages = gemm::gemm_pick_stages();
-    const size_t smem = gemm::gemm_smem_bytes(a.stages);
-    cudaError_t e = cudaFuncSetAttribute(gemm::freq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gemm::StageLaunch<gemm::GemmArgs> L;
+    if (!gemm::prep_gemm(Xf, Cmat, Yf, status, g, nc, L)) return cudaErrorNotSupported;
+    cudaError_t e = cudaFuncSetAttribute(gemm::freq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     if (e != cudaSuccess) return e;
-    const int grid = a.num_items < max_ctas ? a.num_items : max_ctas;
+    const int grid = L.a.num_items < max_ctas ? L.a.num_items : max_ctas;
     if (grid < 1) return cudaSuccess;
-    return gemm::launch_pdl(gemm::freq_gemm_kernel, (unsigned)grid, gemm::GEMM_THREADS, smem, st, tmA, tmB, tmY, a);
+    return gemm::launch_pdl(gemm::freq_gemm_kernel, (unsigned)grid, gemm::GEMM_THREADS, L.smem, st, L.tm_in, L.tm_w, L.tm_out, L.a);
 }
 
 static int sm_count() {
@@ -548,12 +408,24 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
     if (ncmax < 1) return cudaErrorInvalidValue;
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     int* status = reinterpret_cast<int*>(ws);
-    unsigned char* Xf = ws + kWsHeader;
+    const size_t ctr_bytes = gemm::fused_counter_bytes(P.N);
+    unsigned char* Xf = ws + kWsHeader + ctr_bytes;
     unsigned char* Yf = Xf + ((gemm::xf_bytes(g, ncmax) + 255) & ~(size_t)255);
+    static const int impl = getenv("BCL_PREFILL_DFT") ? atoi(getenv("BCL_PREFILL_DFT")) : 0;       // A/B switch for profiling only
+    // Single-launch pipeline (bcl_prefill_fused.cu): opt-in.  Measured 155-165 us against 140 us for the three launches
+    // (4096->4096, 16384 tokens): every stage's epilogue already runs near the TMEM read rate, so splitting the SMs three ways
+    // costs what the saved HBM passes gain (profiles/r1_prefill_notes.md).  BCL_FUSED_MIN_TILES=<tiles> enables it.
+    static const int fused_min_tiles = getenv("BCL_FUSED_MIN_TILES") ? atoi(getenv("BCL_FUSED_MIN_TILES")) : 0;    // <= 0: never
+    const int ctas = sm_count();
+    const bool tc_ok = impl != 1 && spec_gemm != nullptr && gemm::dft_tc_supported(B, P.x_dtype) && P.y_dtype == P.x_dtype && P.n_extra == 0;
+    if (tc_ok && ncmax >= P.N && fused_min_tiles > 0 && (P.N + gemm::TILE_M - 1) / gemm::TILE_M >= fused_min_tiles && ctas >= 12) {
+        // one launch: the three stages pipelined tile by tile over L2-resident Xf / Yf (bcl_prefill_fused.cu)
+        cudaError_t e = cudaMemsetAsync(ws, 0, kWsHeader + ctr_bytes, st);
+        if (e != cudaSuccess) return e;
+        return gemm::launch_prefill_fused(P, g, spec_gemm, Xf, Yf, status, reinterpret_cast<int*>(ws + kWsHeader), ctas, st);
+    }
     cudaError_t e = cudaMemsetAsync(status, 0, kWsHeader, st);
     if (e != cudaSuccess) return e;
-    static const int impl = getenv("BCL_PREFILL_DFT") ? atoi(getenv("BCL_PREFILL_DFT")) : 0;       // A/B switch for profiling only
-    const int ctas = sm_count();
     for (int64_t n0 = 0; n0 < P.N; n0 += ncmax) {
         const int nc = (int)((P.N - n0 < ncmax) ? (P.N - n0) : ncmax);
         if ((e = launch_prefill_stage1(P, B, spec_gemm, n0, nc, Xf, status, impl, st)) != cudaSuccess) return e;

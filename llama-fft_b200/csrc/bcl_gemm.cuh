@@ -85,5 +85,11 @@ bool dft_tc_supported(int B, int act_dtype);
 cudaError_t launch_dft_fwd_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, int max_ctas, cudaStream_t st);
 cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, int max_ctas, cudaStream_t st);
 
+// Single-launch pipeline of the three tensor-core stages over L2-resident intermediates (bcl_prefill_fused.cu).
+// counters: 3 * ceil(N/128) ints, zeroed in stream order before the launch; Xf / Yf sized for all N tokens.
+size_t fused_counter_bytes(int64_t N);
+cudaError_t launch_prefill_fused(const ProblemDev& P, const Geometry& g, const void* spec_gemm, void* Xf, void* Yf, int* status, int* counters, int ctas,
+                                 cudaStream_t st);
+
 }  // namespace gemm
 }  // namespace bcl

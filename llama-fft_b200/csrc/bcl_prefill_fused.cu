@@ -1,0 +1,112 @@
+// bcl_prefill_fused.cu -- the whole prefill forward (rfft -> per-frequency GEMM -> irfft + epilogue) as ONE launch.
+//
+// reference: src/patch_llama_fft.py:246-271 (the forward), src/bench_all_in_one.py:179-231 (cached spectrum).
+// Three separate stage kernels move every intermediate through HBM: x -> Xf -> Yf -> y is three full read+write passes
+// (profiles/r1_prefill_notes.md: 151 us for 4096->4096 at 16384 tokens, each stage at ~80 % of the HBM copy peak).  Here the
+// 148 persistent CTAs of one grid are split into three groups, one per stage, that work on the SAME token tiles a few
+// tiles apart: the forward-DFT CTAs publish tile m of Xf (per-tile completion counter in global memory, release/acquire
+// + async-proxy fences around the TMA stores / loads), the GEMM CTAs pick it up while it is still in L2 and publish Yf,
+// the inverse-DFT CTAs finish the tile.  Only x is read from and y written to HBM; Xf and Yf live in the 126 MB L2.
+// A lag limit (back-pressure counter) keeps a fast group from running ahead of its consumer and spilling the intermediates.
+// The group sizes follow the per-stage bytes over the measured L2-resident per-SM rates (BCL_FUSED_SPLIT overrides).
+#include <cstdlib>
+#include <cstdio>
+#include "bcl_prefill_bodies.cuh"
+
+namespace bcl {
+namespace gemm {
+
+constexpr int FUSED_THREADS = DFT_THREADS + 32;          // + the signaller warp (SIG_WARP)
+static_assert(FUSED_THREADS == 32 * (SIG_WARP + 1), "signaller = last warp");
+
+template <int B>
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+prefill_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWf, const __grid_constant__ CUtensorMap tmXfS,
+                     const __grid_constant__ CUtensorMap tmXfL, const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmYfS,
+                     const __grid_constant__ CUtensorMap tmYfL, const __grid_constant__ CUtensorMap tmWi, const __grid_constant__ CUtensorMap tmOut,
+                     const __grid_constant__ DftArgs a1, const __grid_constant__ GemmArgs a2, const __grid_constant__ DftArgs a3, const int n1, const int n2) {
+    extern __shared__ __align__(1024) unsigned char fused_smem[];
+    const int b = (int)blockIdx.x;
+    if (b < n1) dft_fwd_body<B>(fused_smem, tmX, tmWf, tmXfS, a1, b, n1);
+    else if (b < n1 + n2) freq_gemm_body(fused_smem, tmXfL, tmC, tmYfS, a2, b - n1, n2);
+    else dft_inv_body<B>(fused_smem, tmYfL, tmWi, tmOut, a3, b - n1 - n2, (int)gridDim.x - n1 - n2);
+}
+
+static_assert(DFT_THREADS == GEMM_THREADS, "the three stage bodies share one block shape");
+
+size_t fused_counter_bytes(int64_t N) {
+    const size_t tiles = (size_t)((N + TILE_M - 1) / TILE_M);
+    return (3 * tiles * sizeof(int) + 255) & ~(size_t)255;
+}
+
+static bool env_ints(const char* name, int* out, int n) {
+    const char* e = getenv(name);
+    if (!e) return false;
+    for (int i = 0; i < n; ++i) {
+        char* end = nullptr;
+        out[i] = (int)strtol(e, &end, 10);
+        if (end == e) return false;
+        e = (*end == ',') ? end + 1 : end;
+    }
+    return true;
+}
+
+// CTAs per stage: proportional to the stage's L2-side bytes per token over its per-SM rate (GB/s per SM on L2-resident data,
+// measured with each stage alone under CUDA-graph replay: gpurun_out/graph_scan.log -> profiles/r2 notes).
+void fused_split(const Geometry& g, int ctas, int* n1, int* n2, int* n3) {
+    int ov[2];
+    if (env_ints("BCL_FUSED_SPLIT", ov, 2) && ov[0] > 0 && ov[1] > 0 && ov[0] + ov[1] < ctas) {
+        *n1 = ov[0]; *n2 = ov[1]; *n3 = ctas - ov[0] - ov[1];
+        return;
+    }
+    const double in_b = (double)g.q * g.B * 2, xf_b = (double)g.F * g.Kp * 2, yf_b = (double)g.F * 2 * g.p * 2, out_b = (double)g.p * g.B * 2;
+    const double t1 = (in_b + xf_b) / 50.0, t2 = (xf_b + yf_b) / 54.0, t3 = (yf_b + out_b) / 82.0;
+    const double tot = t1 + t2 + t3;
+    int a = (int)(ctas * t1 / tot + 0.5), b = (int)(ctas * t2 / tot + 0.5);
+    if (a < 1) a = 1;
+    if (b < 1) b = 1;
+    if (a + b > ctas - 1) b = ctas - 1 - a;
+    *n1 = a; *n2 = b; *n3 = ctas - a - b;
+}
+
+// counters: [done1 | done2 | done3], m_tiles ints each, zeroed by the caller (stream-ordered) before this launch
+cudaError_t launch_prefill_fused(const ProblemDev& P, const Geometry& g, const void* spec_gemm, void* Xf, void* Yf, int* status, int* counters, int ctas,
+                                 cudaStream_t st) {
+    const int nc = (int)P.N;
+    StageLaunch<DftArgs> L1, L3;
+    StageLaunch<GemmArgs> L2;
+    if (!prep_dft_fwd(P, g, spec_gemm, 0, nc, Xf, status, L1)) return cudaErrorNotSupported;
+    if (!prep_gemm(Xf, spec_gemm, Yf, status, g, nc, L2)) return cudaErrorNotSupported;
+    if (!prep_dft_inv(P, g, spec_gemm, 0, nc, Yf, status, L3)) return cudaErrorNotSupported;
+    const int m_tiles = L1.a.m_tiles;
+    int* done1 = counters;
+    int* done2 = counters + m_tiles;
+    int* done3 = counters + 2 * m_tiles;
+    // keep roughly 48 MB of Xf + Yf in flight between a producer group and its consumer
+    int lag = (int)((48.0 * 1024 * 1024) / ((double)TILE_M * g.F * (g.Kp + 2 * g.p) * 2));
+    int ov[1];
+    if (env_ints("BCL_FUSED_LAG", ov, 1)) lag = ov[0];
+    if (lag < 4 && lag != 0) lag = 4;
+    int ch[3] = {2, 2, 4};                                          // consecutive items per round: one poll / one signal per run of a tile
+    int chov[3];
+    if (env_ints("BCL_FUSED_CHUNK", chov, 3)) { ch[0] = chov[0]; ch[1] = chov[1]; ch[2] = chov[2]; }
+    L1.a.deps = StageDeps{nullptr, done1, lag > 0 ? done2 : nullptr, 0, g.FG * g.NCH * EPI_WARPS, lag, 1, ch[0]};
+    L2.a.deps = StageDeps{done1, done2, lag > 0 ? done3 : nullptr, g.KG * DFT_EPI_WARPS, g.p * DFT_EPI_WARPS, lag, 1, ch[1]};
+    L3.a.deps = StageDeps{done2, lag > 0 ? done3 : nullptr, nullptr, g.FG * g.NCH * EPI_WARPS, 0, 0, 1, ch[2]};
+    int n1, n2, n3;
+    fused_split(g, ctas, &n1, &n2, &n3);
+    size_t smem = L1.smem > L2.smem ? L1.smem : L2.smem;
+    if (L3.smem > smem) smem = L3.smem;
+    cudaError_t e;
+    if (g.B == 128) {
+        if ((e = cudaFuncSetAttribute(prefill_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        return launch_pdl(prefill_fused_kernel<128>, (unsigned)ctas, FUSED_THREADS, smem, st, L1.tm_in, L1.tm_w, L1.tm_out, L2.tm_in, L2.tm_w, L2.tm_out,
+                          L3.tm_in, L3.tm_w, L3.tm_out, L1.a, L2.a, L3.a, n1, n2);
+    }
+    if ((e = cudaFuncSetAttribute(prefill_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    return launch_pdl(prefill_fused_kernel<64>, (unsigned)ctas, FUSED_THREADS, smem, st, L1.tm_in, L1.tm_w, L1.tm_out, L2.tm_in, L2.tm_w, L2.tm_out,
+                      L3.tm_in, L3.tm_w, L3.tm_out, L1.a, L2.a, L3.a, n1, n2);
+}
+
+}  // namespace gemm
+}  // namespace bcl

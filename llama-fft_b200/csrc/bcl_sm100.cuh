@@ -28,6 +28,13 @@ __device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
                  : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
     return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a system-dependent time; test_wait returns at once).
+__device__ __forceinline__ bool mbar_test(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as an error flag, never as a hung GPU (a hung box is a lost lease).
 // Returns false when the phase has not completed after ~2 s; callers then set the kernel's status word and bail out.
 __device__ __forceinline__ uint64_t global_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -35,8 +42,8 @@ static __device__ __noinline__ bool mbar_wait_slow(uint32_t addr, uint32_t parit
     const uint64_t t0 = global_ns();
 #pragma unroll 1
     for (uint32_t spin = 0;; ++spin) {
-        if (mbar_try(addr, parity)) return true;
-        __nanosleep(64);
+        if (mbar_try(addr, parity)) return true;                        // try_wait suspends in hardware for a bounded time
+        if (spin >= 256u) __nanosleep(64);                              // long waits only: stop competing for issue slots
         if ((spin & 1023u) == 1023u && global_ns() - t0 > 2000000000ull) return false;
     }
 }
