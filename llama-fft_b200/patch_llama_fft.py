@@ -120,6 +120,7 @@ class BlockCirculantLinear(nn.Module):
         self._spec: Optional[torch.Tensor] = None          # STREAM layout (decode / small N)
         self._spec_gemm: Optional[torch.Tensor] = None     # GEMM layout (tcgen05 prefill path)
         self._spec_key = None
+        self._shared_group = None                          # shared_input.SharedInputGroup when fused with siblings (q/k/v, gate/up)
 
     def extra_repr(self) -> str:
         return (f"in_features={self.in_features}, out_features={self.out_features}, block_size={self.block_size}, "
@@ -209,6 +210,10 @@ class BlockCirculantLinear(nn.Module):
         else:
             # reference rule (src/bench_all_in_one.py:212-219): a cached spectrum is served only in eval/no-grad
             reuse = (not self.training) and (not torch.is_grad_enabled())
+            if reuse and self._shared_group is not None:
+                # siblings reading the same activation (q/k/v, gate/up): one fused forward, this layer's column slice
+                y_flat = self._shared_group.member_forward(self, x_flat)
+                return y_flat.view(lead[0], lead[1], self.out_features) if lead is not None else y_flat
             layout = _cabi.LAYOUT_GEMM if self._use_prefill_path(x_flat.shape[0]) else _cabi.LAYOUT_STREAM
             spec = self.build_spectrum(force=not reuse, layout=layout)
             y_flat = bc_forward(x_flat, spec, self.bias, self.out_blocks, self.in_blocks, self.block_size, layout=layout)

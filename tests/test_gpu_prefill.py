@@ -358,3 +358,57 @@ def test_forward_bcast_writes_every_destination(N, dtype, sdt):
     for b, d in zip(big, dsts):
         assert_close(d, y_ref, 1e-2 if (sdt == BF and N >= 256) else 1e-6, dtype)
         assert (b[:, :256] == 7.0).all() and (b[:, 1024:] == 7.0).all()
+
+
+_FUSED_CHILD = r"""
+import sys, torch
+import llama_fft_b200 as bc
+from llama_fft_b200.patch_llama_fft import prefill_status
+inf, outf, B, N, dt, has_bias, out = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5], int(sys.argv[6]), sys.argv[7]
+dtype = {"f16": torch.float16, "bf16": torch.bfloat16}[dt]
+g = torch.Generator().manual_seed(inf + outf + B + N)
+c = torch.randn(outf // B, inf // B, B, generator=g) * 0.01
+x = torch.randn(N, inf, generator=g).to(dtype)
+m = bc.BlockCirculantLinear(inf, outf, block_size=B, bias=bool(has_bias), spectrum_dtype=torch.bfloat16)
+with torch.no_grad():
+    m.c.copy_(c)
+    if has_bias:
+        m.bias.copy_(torch.randn(outf, generator=g) * 0.1)
+m = m.to("cuda:0").eval()
+if has_bias:
+    m.bias.data = m.bias.data.to(dtype)               # same dtype as the activations: the tensor-core inverse stage adds it
+with torch.no_grad():
+    y = m(x.to("cuda:0"))
+    y2 = m(x.to("cuda:0"))
+torch.cuda.synchronize()
+assert prefill_status("cuda:0") == 0, prefill_status("cuda:0")
+assert torch.equal(y, y2)
+torch.save(y.cpu(), out)
+"""
+
+
+@pytest.mark.parametrize("inf,outf,B,N,dt,has_bias", [(4096, 4096, 128, 2048 + 77, "f16", 0), (4096, 11008, 128, 1500, "bf16", 1),
+                                                      (11008, 4096, 128, 1024, "f16", 0), (1024, 512, 64, 3000, "f16", 1)])
+def test_prefill_fused_single_launch_matches_three_launch_chain(tmp_path, inf, outf, B, N, dt, has_bias):
+    """The opt-in single-launch pipeline (bcl_prefill_fused.cu, BCL_FUSED_MIN_TILES) runs the same MMAs on the same tiles as the
+    three stage launches, only handed over through per-tile counters: its output must be BIT-identical to the chain's, and
+    within the bf16-spectrum tolerance of the oracle.  The switch is read once per process, hence the child process."""
+    import os
+    import subprocess
+    import sys
+    outs = {}
+    for tag, tiles in (("chain", "0"), ("fused", "4")):
+        out = str(tmp_path / f"{tag}.pt")
+        env = dict(os.environ, BCL_FUSED_MIN_TILES=tiles, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        r = subprocess.run([sys.executable, "-c", _FUSED_CHILD, str(inf), str(outf), str(B), str(N), dt, str(has_bias), out],
+                           env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = torch.load(out)
+    assert torch.equal(outs["chain"], outs["fused"])
+    dtype = {"f16": torch.float16, "bf16": torch.bfloat16}[dt]
+    g = torch.Generator().manual_seed(inf + outf + B + N)
+    c = torch.randn(outf // B, inf // B, B, generator=g) * 0.01
+    x = torch.randn(N, inf, generator=g).to(dtype)
+    rows = torch.tensor([0, 1, 127, 128, N // 2, N - 2, N - 1])
+    if not has_bias:
+        assert_close(outs["fused"][rows], O.bc_forward_torch(c, x[rows].float()), 1e-2, dtype)

@@ -252,3 +252,25 @@ def test_patch_api_on_a_random_init_llama():
     W = ref.model.layers[2].mlp.gate_proj.weight.data
     got = model.model.layers[2].mlp.gate_proj.c.detach()
     assert (got - O.from_linear_c(W, 64)).abs().max() <= 1e-6 * got.abs().max()
+
+
+def test_shared_input_groups_attach_without_changing_the_module_tree():
+    """fuse_shared_inputs: q/k/v and gate/up of every patched layer form one group each; the members stay the
+    model's modules (state-dict keys, checkpoint I/O unchanged) and unfuse detaches the groups again."""
+    model = _tiny_llama(layers=2)
+    bc.patch_llama_fft(model, block_size=64)
+    keys = sorted(model.state_dict().keys())
+    assert bc.fuse_shared_inputs(model) == 2 * 2
+    assert sorted(model.state_dict().keys()) == keys
+    attn, mlp = model.model.layers[1].self_attn, model.model.layers[1].mlp
+    g = attn.q_proj._shared_group
+    assert g is attn.k_proj._shared_group is attn.v_proj._shared_group and attn.o_proj._shared_group is None
+    assert g.out_blocks == 3 * (128 // 64) and g.offsets == [0, 128, 256, 384]
+    assert mlp.gate_proj._shared_group is mlp.up_proj._shared_group and mlp.down_proj._shared_group is None
+    assert mlp.gate_proj._shared_group.offsets == [0, 256, 512]
+    with pytest.raises(ValueError, match="share"):
+        bc.SharedInputGroup([attn.q_proj, mlp.down_proj])
+    with pytest.raises(RuntimeError):                                # still no CPU path: the fused call fails as loudly as a single layer
+        with torch.no_grad():
+            attn.q_proj(torch.randn(3, 128))
+    assert bc.unfuse_shared_inputs(model) == 4 and attn.q_proj._shared_group is None
