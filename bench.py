@@ -447,6 +447,41 @@ def time_prefill_layer(bc, _cabi, dev, reps, n=PREFILL_TOKENS, through_host=Fals
     return e0.elapsed_time(e1) / reps * 1e3, per_shape, prefill_status(dev)
 
 
+def time_prefill_layer_shared_input(bc, _cabi, dev, reps, n=PREFILL_TOKENS):
+    """Same layer, same tokens, with q/k/v and gate/up fused into one BC forward each (llama-fft_b200/shared_input.py):
+    4 launches-chains instead of 7, one forward-DFT pass of x per group.  The algorithmic bytes of the fused layer are smaller
+    (x is read once per group), so the roofline fraction is quoted against its own figure."""
+    import torch
+    from llama_fft_b200.patch_llama_fft import prefill_status
+    torch.manual_seed(0)
+
+    def mk(inf, outf):
+        return bc.BlockCirculantLinear(inf, outf, block_size=B, bias=False, spectrum_dtype=torch.bfloat16).to(dev).eval()
+    qkv = bc.SharedInputGroup([mk(4096, 4096) for _ in range(3)])
+    gu = bc.SharedInputGroup([mk(4096, 11008) for _ in range(2)])
+    o, down = mk(4096, 4096), mk(11008, 4096)
+    xs = {d: [torch.randn(n, d, device=dev).half() for _ in range(2)] for d in (4096, 11008)}
+
+    def layer(i):
+        with torch.no_grad():
+            qkv.forward_all(xs[4096][i & 1])
+            o(xs[4096][i & 1])
+            gu.forward_all(xs[4096][i & 1])
+            down(xs[11008][i & 1])
+    for i in range(3):
+        layer(i)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(reps):
+        layer(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    alg = sum(n * inf * 2 + inf * outf // B * 2 + n * outf * 2 for inf, outf in ((4096, 3 * 4096), (4096, 4096), (4096, 2 * 11008), (11008, 4096)))
+    return e0.elapsed_time(e1) / reps * 1e3, alg, prefill_status(dev)
+
+
 def prefill_detail(bc, _cabi, dev, reps=5):
     import torch
     us, per_shape, status = time_prefill_layer(bc, _cabi, dev, reps)
@@ -463,7 +498,14 @@ def prefill_detail(bc, _cabi, dev, reps=5):
            "algorithmic_bytes_per_layer": alg, "hbm_frac_of_measured_peak": alg / (us * 1e-6) / 1e9 / peak,
            "algorithmic_tflops": fl / (us * 1e-6) / 1e12, "tensor_frac_of_measured_bf16_peak": fl / (us * 1e-6) / 1e12 / tpeak,
            "pipeline_status": status}
-    del us
+    torch.cuda.empty_cache()
+    try:
+        us2, alg2, status2 = time_prefill_layer_shared_input(bc, _cabi, dev, reps)
+        out["shared_input_fusion"] = {"what": "q/k/v and gate/up each as one BC forward over stacked block-rows (bit-identical outputs)",
+                                      "us_per_layer": us2, "tokens_per_s": PREFILL_TOKENS / (us2 * 1e-6), "algorithmic_bytes_per_layer": alg2,
+                                      "hbm_frac_of_measured_peak": alg2 / (us2 * 1e-6) / 1e9 / peak, "pipeline_status": status2}
+    except Exception as e:                                               # noqa: BLE001
+        out["shared_input_fusion"] = {"error": "%s: %s" % (type(e).__name__, e)}
     torch.cuda.empty_cache()
     return out
 

@@ -66,7 +66,8 @@ size_t bcl_spectrum_bytes(int p, int q, int B, int spec_dtype, int layout) {
         if (spec_dtype != BCL_F32 && spec_dtype != BCL_BF16) return 0;
         return (size_t)p * q * B * (spec_dtype == BCL_F32 ? 4 : 2);
     }
-    if (layout == BCL_LAYOUT_GEMM) return spec_dtype == BCL_BF16 ? bcl::gemm_spectrum_bytes(p, q, B) : 0;
+    if (layout == BCL_LAYOUT_GEMM)                                  // f32 = the split (hi, lo) bf16 layout of the fp32-accurate tensor path
+        return (spec_dtype == BCL_BF16 || spec_dtype == BCL_F32) ? bcl::gemm_spectrum_bytes(p, q, B, spec_dtype == BCL_F32) : 0;
     return 0;
 }
 
@@ -81,16 +82,16 @@ int bcl_precompute_spectrum(const float* c, int p, int q, int B, void* spec, int
         return e == cudaSuccess ? BCL_OK : cuda_fail(e, "spectrum precompute launch");
     }
     if (layout == BCL_LAYOUT_GEMM) {
-        if (spec_dtype != BCL_BF16) return fail(BCL_ERR_DTYPE, "GEMM spectrum must be bf16");
-        cudaError_t e = bcl::launch_spectrum_gemm(c, spec, p, q, B, (cudaStream_t)stream);
+        if (spec_dtype != BCL_BF16 && spec_dtype != BCL_F32) return fail(BCL_ERR_DTYPE, "GEMM spectrum must be bf16 or f32 (split bf16 pairs)");
+        cudaError_t e = bcl::launch_spectrum_gemm(c, spec, p, q, B, spec_dtype == BCL_F32, (cudaStream_t)stream);
         return e == cudaSuccess ? BCL_OK : cuda_fail(e, "GEMM spectrum precompute launch");
     }
     return fail(BCL_ERR_ARG, "unknown spectrum layout %d", layout);
 }
 
 size_t bcl_workspace_bytes(int64_t N, int p, int q, int B, int spec_dtype, int layout) {
-    (void)spec_dtype;
-    if (layout == BCL_LAYOUT_GEMM && valid_B(B) && p > 0 && q > 0 && N > 0) return bcl::gemm_workspace_bytes(N, p, q, B);
+    if (layout == BCL_LAYOUT_GEMM && valid_B(B) && p > 0 && q > 0 && N > 0 && (spec_dtype == BCL_BF16 || spec_dtype == BCL_F32))
+        return bcl::gemm_workspace_bytes(N, p, q, B, spec_dtype == BCL_F32);
     return 0;
 }
 
@@ -114,13 +115,14 @@ static int forward_impl(const void* x, int x_dtype, int64_t N, int64_t x_row_str
         return e == cudaSuccess ? BCL_OK : cuda_fail(e, "stream forward launch");
     }
     if (layout == BCL_LAYOUT_GEMM) {
-        if (spec_dtype != BCL_BF16) return fail(BCL_ERR_DTYPE, "GEMM spectrum must be bf16");
+        if (spec_dtype != BCL_BF16 && spec_dtype != BCL_F32) return fail(BCL_ERR_DTYPE, "GEMM spectrum must be bf16 or f32 (split bf16 pairs)");
+        const int split = spec_dtype == BCL_F32;
         if (N > (int64_t)1 << 30) return fail(BCL_ERR_SHAPE, "N=%lld too large; split the batch", (long long)N);
         if (!workspace || !aligned(workspace, 256)) return fail(BCL_ERR_WORKSPACE, "GEMM layout needs a 256-byte aligned workspace");
-        if (bcl::gemm_chunk_tokens(N, p, q, B, workspace_bytes) < (N < 128 ? N : 128))
+        if (bcl::gemm_chunk_tokens(N, p, q, B, workspace_bytes, split) < (N < 128 ? N : 128))
             return fail(BCL_ERR_WORKSPACE, "workspace %zu bytes cannot stage one 128-token chunk (bcl_workspace_bytes gives %zu)", workspace_bytes,
-                        bcl::gemm_workspace_bytes(N, p, q, B));
-        cudaError_t e = bcl::launch_gemm_forward(P, B, spec, workspace, workspace_bytes, (cudaStream_t)stream);
+                        bcl::gemm_workspace_bytes(N, p, q, B, split));
+        cudaError_t e = bcl::launch_gemm_forward(P, B, spec, workspace, workspace_bytes, split, (cudaStream_t)stream);
         return e == cudaSuccess ? BCL_OK : cuda_fail(e, "GEMM forward launch");
     }
     return fail(BCL_ERR_ARG, "unknown spectrum layout %d", layout);
@@ -178,7 +180,7 @@ int bcl_prefill_gemm(const void* Xf, const void* spec_gemm, void* Yf, int64_t N,
     if (!aligned(Xf, 128) || !aligned(spec_gemm, 128) || !aligned(Yf, 128)) return fail(BCL_ERR_ALIGN, "Xf, spec and Yf must be 128-byte aligned");
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = bcl::launch_gemm_mma(Xf, spec_gemm, Yf, status, p, q, B, (int)N, sms, (cudaStream_t)stream);
+    cudaError_t e = bcl::launch_gemm_mma(Xf, nullptr, spec_gemm, Yf, nullptr, status, p, q, B, (int)N, sms, (cudaStream_t)stream);
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "prefill tcgen05 GEMM launch");
 }
 

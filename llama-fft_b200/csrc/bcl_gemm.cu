@@ -30,6 +30,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// (hi, lo) split of two floats: hi = bf16(v), lo = bf16(v - hi); hi + lo reproduces v to ~2^-17 relative
+__device__ __forceinline__ void split_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    __nv_bfloat162 h; h.x = ha; h.y = hb;
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = pack_bf16(a - __bfloat162float(ha), b - __bfloat162float(hb));
+}
 __device__ __forceinline__ float2 unpack_bf16(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -44,7 +51,7 @@ template <int B, int NT, int WARPS> struct RowsSmem {
 
 template <int B, int NT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) rfft_rows_kernel(const __grid_constant__ ProblemDev P, int64_t n_begin, int nc,
-                                                                __nv_bfloat16* __restrict__ Xf, int KG) {
+                                                                __nv_bfloat16* __restrict__ Xf, __nv_bfloat16* __restrict__ Xf_lo, int KG) {
     using SM = RowsSmem<B, NT, WARPS>;
     using C = FftCfg<B>;
     extern __shared__ __align__(16) unsigned char rows_smem[];
@@ -69,17 +76,19 @@ __global__ void __launch_bounds__(WARPS * 32) rfft_rows_kernel(const __grid_cons
         const int kg = (id / NT) % KG;
         const int f = id / (NT * KG);
         if (t0 + n >= nc) continue;
-        uint32_t w[4];
+        uint32_t w[4], wl[4];
 #pragma unroll
         for (int ib = 0; ib < 4; ++ib) {
             const int i = 4 * kg + ib;
-            w[ib] = 0u;
+            w[ib] = 0u; wl[ib] = 0u;
             if (i < q) {
                 const float2 v = *reinterpret_cast<const float2*>(xs + ((size_t)n * q + i) * SM::PITCH + 2 * f);
-                w[ib] = pack_bf16(v.x, v.y);                            // f = 0: (DC, Nyquist), both real
+                split_bf16(v.x, v.y, w[ib], wl[ib]);                    // f = 0: (DC, Nyquist), both real
             }
         }
-        *reinterpret_cast<uint4*>(Xf + (((size_t)f * KG + kg) * ntp + (t0 + n)) * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        const size_t off = (((size_t)f * KG + kg) * ntp + (t0 + n)) * 8;
+        *reinterpret_cast<uint4*>(Xf + off) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (Xf_lo != nullptr) *reinterpret_cast<uint4*>(Xf_lo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
     }
 }
 
@@ -87,7 +96,8 @@ __global__ void __launch_bounds__(WARPS * 32) rfft_rows_kernel(const __grid_cons
 // GEMM-layout spectrum: c (p,q,B) fp32 -> Cmat[F][Np][Kp] bf16.  One CTA per output block j (rows 2j, 2j+1 of every f).
 // ---------------------------------------------------------------------------------------------------------
 template <int B, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) spectrum_gemm_kernel(const float* __restrict__ c, int p, int q, __nv_bfloat16* __restrict__ Cmat, int Np, int Kp) {
+__global__ void __launch_bounds__(WARPS * 32) spectrum_gemm_kernel(const float* __restrict__ c, int p, int q, __nv_bfloat16* __restrict__ Cmat,
+                                                                   __nv_bfloat16* __restrict__ Cmat_lo, int Np, int Kp) {
     using SM = RowsSmem<B, 1, WARPS>;
     using C = FftCfg<B>;
     extern __shared__ __align__(16) unsigned char rows_smem[];
@@ -108,15 +118,17 @@ __global__ void __launch_bounds__(WARPS * 32) spectrum_gemm_kernel(const float* 
     for (int f = warp; f < F; f += WARPS) {
         uint32_t* row_re = reinterpret_cast<uint32_t*>(Cmat + ((size_t)f * Np + 2 * j) * Kp);       // n = 2j  : Yr
         uint32_t* row_im = row_re + Kp / 2;                                                         // n = 2j+1: Yi
+        const size_t lo_shift = Cmat_lo != nullptr ? (size_t)(Cmat_lo - Cmat) / 2 : 0;                // in 32-bit words
         for (int i = lane; i < Kp / 2; i += 32) {
-            uint32_t wr = 0u, wi = 0u;
+            uint32_t wr = 0u, wi = 0u, lr = 0u, li = 0u;
             if (j < p && i < q) {
                 const float2 v = *reinterpret_cast<const float2*>(xs + (size_t)i * SM::PITCH + 2 * f);
-                if (f == 0) { wr = pack_bf16(v.x, 0.f); wi = pack_bf16(0.f, v.y); }                  // [[C_dc, 0], [0, C_ny]]
-                else { wr = pack_bf16(v.x, -v.y); wi = pack_bf16(v.y, v.x); }                        // Yr = Xr Cr - Xi Ci ; Yi = Xr Ci + Xi Cr
+                if (f == 0) { split_bf16(v.x, 0.f, wr, lr); split_bf16(0.f, v.y, wi, li); }          // [[C_dc, 0], [0, C_ny]]
+                else { split_bf16(v.x, -v.y, wr, lr); split_bf16(v.y, v.x, wi, li); }                // Yr = Xr Cr - Xi Ci ; Yi = Xr Ci + Xi Cr
             }
             row_re[i] = wr;
             row_im[i] = wi;
+            if (Cmat_lo != nullptr) { row_re[i + lo_shift] = lr; row_im[i + lo_shift] = li; }
         }
     }
 }
@@ -148,7 +160,14 @@ __global__ void dft_matrix_kernel(int B, __half* __restrict__ wf16, __nv_bfloat1
 __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char gemm_smem[];
-    freq_gemm_body(gemm_smem, tmA, tmB, tmY, a, (int)blockIdx.x, (int)gridDim.x);
+    freq_gemm_body<false>(gemm_smem, tmA, tmB, tmY, nullptr, a, (int)blockIdx.x, (int)gridDim.x);
+}
+// fp32-accurate variant: (hi, lo) bf16 operands, three MMAs per k-step (bcl_gemm.cuh: geometry(..., split = 1))
+__global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                                           const __grid_constant__ CUtensorMap tmY, const __grid_constant__ GemmLoMaps lo,
+                                                                           const __grid_constant__ GemmArgs a) {
+    extern __shared__ __align__(1024) unsigned char gemm_smem[];
+    freq_gemm_body<true>(gemm_smem, tmA, tmB, tmY, &lo, a, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -156,7 +175,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) freq_gemm_kernel(const __grid
 // ---------------------------------------------------------------------------------------------------------
 template <int B, int NT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) irfft_rows_kernel(const __grid_constant__ ProblemDev P, int64_t n_begin, int nc,
-                                                                 const __nv_bfloat16* __restrict__ Yf) {
+                                                                 const __nv_bfloat16* __restrict__ Yf, const __nv_bfloat16* __restrict__ Yf_lo) {
     using SM = RowsSmem<B, NT, WARPS>;
     using C = FftCfg<B>;
     extern __shared__ __align__(16) unsigned char rows_smem[];
@@ -175,9 +194,16 @@ __global__ void __launch_bounds__(WARPS * 32) irfft_rows_kernel(const __grid_con
         const int j = (id / NT) % p;
         const int fg = id / (NT * p);
         if (t0 + n >= nc) continue;
-        const uint4 w = __ldg(reinterpret_cast<const uint4*>(Yf + (((size_t)fg * p + j) * ntp + (t0 + n)) * 8));
+        const size_t off = (((size_t)fg * p + j) * ntp + (t0 + n)) * 8;
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(Yf + off));
         float2* dst = reinterpret_cast<float2*>(ys + ((size_t)n * p + j) * SM::PITCH + 8 * fg);
         dst[0] = unpack_bf16(w.x); dst[1] = unpack_bf16(w.y); dst[2] = unpack_bf16(w.z); dst[3] = unpack_bf16(w.w);
+        if (Yf_lo != nullptr) {                                         // split layout: value = hi + lo
+            const uint4 l = __ldg(reinterpret_cast<const uint4*>(Yf_lo + off));
+            const float2 l0 = unpack_bf16(l.x), l1 = unpack_bf16(l.y), l2 = unpack_bf16(l.z), l3 = unpack_bf16(l.w);
+            dst[0].x += l0.x; dst[0].y += l0.y; dst[1].x += l1.x; dst[1].y += l1.y;
+            dst[2].x += l2.x; dst[2].y += l2.y; dst[3].x += l3.x; dst[3].y += l3.y;
+        }
     }
     __syncthreads();
     float2* fscr = fscr_all + (size_t)warp * (C::WARP_SCRATCH_BYTES / 8);
@@ -231,22 +257,32 @@ bool make_chunk_map(CUtensorMap* m, const void* base, int64_t ntok, int slabs, i
     return make_tensor_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
-static size_t gemm_smem_bytes(int stages) { return 1024 + EPI_WARPS * EPI_NBUF * EPI_BUF_BYTES + (size_t)stages * STAGE_BYTES; }
-static int gemm_pick_stages() {
+static size_t gemm_smem_bytes(int stages, int split) { return 1024 + EPI_WARPS * EPI_NBUF * EPI_BUF_BYTES + (size_t)stages * STAGE_BYTES * (split ? 2 : 1); }
+static int gemm_pick_stages(int split) {
     int s = MAX_STAGES;
-    while (s > 2 && gemm_smem_bytes(s) > 225 * 1024) --s;
+    while (s > 2 && gemm_smem_bytes(s, split) > 225 * 1024) --s;
     return s;
 }
 
 // Xf [F][KG][ntp][8], Cmat [F][Np][Kp] -> Yf [FG][p][ntp][8] (ntp = nc rounded up to 32)
-bool prep_gemm(const void* Xf, const void* Cmat, void* Yf, int* status, const Geometry& g, int nc, StageLaunch<GemmArgs>& L) {
+// split layout (lo != nullptr): Xf_lo / Yf_lo follow Xf / Yf at lo_stride_x / lo_stride_y bytes, Cmat_lo at g.cmat_lo_off
+static bool map_cmat(CUtensorMap* m, const void* Cmat, const Geometry& g) {
+    const uint64_t dims[3] = {(uint64_t)g.Kp, (uint64_t)g.Np, (uint64_t)g.F};
+    const uint64_t strides[2] = {(uint64_t)g.Kp * 2, (uint64_t)g.Kp * g.Np * 2};
+    const uint32_t box[3] = {KATOM, NCHUNK, 1};
+    return make_tensor_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Cmat, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+bool prep_gemm_lo(const void* Xf_lo, const void* Cmat, void* Yf_lo, const Geometry& g, int nc, GemmLoMaps* lo) {
+    if (!make_chunk_map(&lo->A, Xf_lo, nc, g.KG, g.F, TILE_M / TOK_GROUP, 8, 1)) return false;
+    if (!map_cmat(&lo->B, reinterpret_cast<const unsigned char*>(Cmat) + g.cmat_lo_off, g)) return false;
+    return make_chunk_map(&lo->Y, Yf_lo, nc, g.p, g.FG, 1, 8, 1);
+}
+
+bool prep_gemm(const void* Xf, const void* Cmat, void* Yf, int* status, const Geometry& g, int nc, StageLaunch<GemmArgs>& L, GemmLoMaps* lo) {
+    (void)lo;
     if (!make_chunk_map(&L.tm_in, Xf, nc, g.KG, g.F, TILE_M / TOK_GROUP, 8, 1)) return false;
-    {
-        const uint64_t dims[3] = {(uint64_t)g.Kp, (uint64_t)g.Np, (uint64_t)g.F};
-        const uint64_t strides[2] = {(uint64_t)g.Kp * 2, (uint64_t)g.Kp * g.Np * 2};
-        const uint32_t box[3] = {KATOM, NCHUNK, 1};
-        if (!make_tensor_map(&L.tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Cmat, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
-    }
+    if (!map_cmat(&L.tm_w, Cmat, g)) return false;
     if (!make_chunk_map(&L.tm_out, Yf, nc, g.p, g.FG, 1, 8, 1)) return false;
     GemmArgs& a = L.a;
     a = GemmArgs{};
@@ -254,8 +290,8 @@ bool prep_gemm(const void* Xf, const void* Cmat, void* Yf, int* status, const Ge
     a.ntok = nc; a.p = g.p; a.KG = g.KG; a.FG = g.FG; a.k_atoms = (g.Kp + KATOM - 1) / KATOM; a.NCH = g.NCH;
     a.m_tiles = (nc + TILE_M - 1) / TILE_M;
     a.num_items = a.m_tiles * g.FG * g.NCH;
-    a.stages = gemm_pick_stages();
-    L.smem = gemm_smem_bytes(a.stages);
+    a.stages = gemm_pick_stages(g.split);
+    L.smem = gemm_smem_bytes(a.stages, g.split);
     a.trace = trace_ptr(2);
     return true;
 }
@@ -266,24 +302,24 @@ template <typename K> static cudaError_t set_smem(K kernel, size_t bytes) {
 }
 
 template <int B, int NT>
-static cudaError_t launch_rfft_rows_t(const ProblemDev& P, int64_t n_begin, int nc, void* Xf, int KG, cudaStream_t st) {
+static cudaError_t launch_rfft_rows_t(const ProblemDev& P, int64_t n_begin, int nc, void* Xf, void* Xf_lo, int KG, cudaStream_t st) {
     constexpr int WARPS = 8;
     auto kern = rfft_rows_kernel<B, NT, WARPS>;
     const size_t smem = RowsSmem<B, NT, WARPS>::bytes(P.q);
     cudaError_t e = set_smem(kern, smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)((nc + NT - 1) / NT), WARPS * 32, smem, st>>>(P, n_begin, nc, reinterpret_cast<__nv_bfloat16*>(Xf), KG);
+    kern<<<(unsigned)((nc + NT - 1) / NT), WARPS * 32, smem, st>>>(P, n_begin, nc, reinterpret_cast<__nv_bfloat16*>(Xf), reinterpret_cast<__nv_bfloat16*>(Xf_lo), KG);
     return cudaGetLastError();
 }
 
 template <int B, int NT>
-static cudaError_t launch_irfft_rows_t(const ProblemDev& P, int64_t n_begin, int nc, const void* Yf, cudaStream_t st) {
+static cudaError_t launch_irfft_rows_t(const ProblemDev& P, int64_t n_begin, int nc, const void* Yf, const void* Yf_lo, cudaStream_t st) {
     constexpr int WARPS = 8;
     auto kern = irfft_rows_kernel<B, NT, WARPS>;
     const size_t smem = RowsSmem<B, NT, WARPS>::bytes(P.p);
     cudaError_t e = set_smem(kern, smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)((nc + NT - 1) / NT), WARPS * 32, smem, st>>>(P, n_begin, nc, reinterpret_cast<const __nv_bfloat16*>(Yf));
+    kern<<<(unsigned)((nc + NT - 1) / NT), WARPS * 32, smem, st>>>(P, n_begin, nc, reinterpret_cast<const __nv_bfloat16*>(Yf), reinterpret_cast<const __nv_bfloat16*>(Yf_lo));
     return cudaGetLastError();
 }
 
@@ -292,7 +328,7 @@ static int rows_nt(int blocks, int B) { return (size_t)2 * blocks * (B + 2) * 4 
 
 }  // namespace gemm
 
-size_t gemm_spectrum_bytes(int p, int q, int B) { return gemm::geometry(p, q, B).total_bytes; }
+size_t gemm_spectrum_bytes(int p, int q, int B, int split) { return gemm::geometry(p, q, B, split).total_bytes; }
 
 // workspace = [256-byte status area | Xf chunk | Yf chunk].  Measured on B200 (profiles/r1_prefill_notes.md): three
 // full-size passes through HBM (no chunking, 16384 tokens: 157 us for 4096->4096) beat L2-resident 2048-3072-token chunks
@@ -310,29 +346,29 @@ static size_t chunk_budget() {
     return v;
 }
 
-static size_t per_token_ws(const gemm::Geometry& g) { return (size_t)g.F * (g.Kp + 2 * g.p) * 2; }
+static size_t per_token_ws(const gemm::Geometry& g) { return (size_t)g.F * (g.Kp + 2 * g.p) * 2 * (g.split ? 2 : 1); }   // split: (hi, lo) pairs
 
 // workspace = [256-byte status area | tile counters of the fused launch | Xf | Yf]
 static size_t ws_fixed(int64_t N) { return kWsHeader + gemm::fused_counter_bytes(N) + 512; }
 
-int64_t gemm_chunk_tokens(int64_t N, int p, int q, int B, size_t workspace_bytes) {
-    const gemm::Geometry g = gemm::geometry(p, q, B);
+int64_t gemm_chunk_tokens(int64_t N, int p, int q, int B, size_t workspace_bytes, int split) {
+    const gemm::Geometry g = gemm::geometry(p, q, B, split);
     if (workspace_bytes <= ws_fixed(N)) return 0;
     int64_t nc = (int64_t)((workspace_bytes - ws_fixed(N)) / per_token_ws(g));
     if (nc >= gemm::token_pitch(N)) return N;
     return nc / gemm::TILE_M * gemm::TILE_M;
 }
 
-size_t gemm_workspace_bytes(int64_t N, int p, int q, int B) {
-    const gemm::Geometry g = gemm::geometry(p, q, B);
+size_t gemm_workspace_bytes(int64_t N, int p, int q, int B, int split) {
+    const gemm::Geometry g = gemm::geometry(p, q, B, split);
     int64_t nc = (int64_t)(chunk_budget() / per_token_ws(g)) / gemm::TILE_M * gemm::TILE_M;
     if (nc < gemm::TILE_M) nc = gemm::TILE_M;
     if (nc > N) nc = gemm::token_pitch(N);
     return ws_fixed(N) + (size_t)nc * per_token_ws(g);
 }
 
-cudaError_t launch_spectrum_gemm(const float* c, void* spec, int p, int q, int B, cudaStream_t st) {
-    const gemm::Geometry g = gemm::geometry(p, q, B);
+cudaError_t launch_spectrum_gemm(const float* c, void* spec, int p, int q, int B, int split, cudaStream_t st) {
+    const gemm::Geometry g = gemm::geometry(p, q, B, split);
     constexpr int WARPS = 8;
     unsigned char* base = reinterpret_cast<unsigned char*>(spec);
     gemm::dft_matrix_kernel<<<B, B, 0, st>>>(B, reinterpret_cast<__half*>(base + g.wf16_off), reinterpret_cast<__nv_bfloat16*>(base + g.wbf16_off),
@@ -345,37 +381,48 @@ cudaError_t launch_spectrum_gemm(const float* c, void* spec, int p, int q, int B
         const size_t smem = gemm::RowsSmem<BB, 1, WARPS>::bytes(q);                                                         \
         cudaError_t e = gemm::set_smem(kern, smem);                                                                         \
         if (e != cudaSuccess) return e;                                                                                    \
-        kern<<<(unsigned)(g.Np / 2), WARPS * 32, smem, st>>>(c, p, q, reinterpret_cast<__nv_bfloat16*>(spec), g.Np, g.Kp); \
+        kern<<<(unsigned)(g.Np / 2), WARPS * 32, smem, st>>>(c, p, q, reinterpret_cast<__nv_bfloat16*>(spec),                \
+                                                              split ? reinterpret_cast<__nv_bfloat16*>(base + g.cmat_lo_off) : nullptr, g.Np, g.Kp); \
         return cudaGetLastError();                                                                                         \
     }
     switch (B) { case 64: BCL_SG(64) case 128: BCL_SG(128) default: BCL_SG(256) }
 #undef BCL_SG
 }
 
-cudaError_t launch_gemm_rfft(const ProblemDev& P, int B, int64_t n_begin, int nc, void* Xf, cudaStream_t st) {
+cudaError_t launch_gemm_rfft(const ProblemDev& P, int B, int64_t n_begin, int nc, void* Xf, void* Xf_lo, cudaStream_t st) {
     const gemm::Geometry g = gemm::geometry(P.p, P.q, B);
     const int nt = gemm::rows_nt(P.q, B);
-#define BCL_R1(BB) (nt == 2 ? gemm::launch_rfft_rows_t<BB, 2>(P, n_begin, nc, Xf, g.KG, st) : gemm::launch_rfft_rows_t<BB, 1>(P, n_begin, nc, Xf, g.KG, st))
+#define BCL_R1(BB) (nt == 2 ? gemm::launch_rfft_rows_t<BB, 2>(P, n_begin, nc, Xf, Xf_lo, g.KG, st) : gemm::launch_rfft_rows_t<BB, 1>(P, n_begin, nc, Xf, Xf_lo, g.KG, st))
     switch (B) { case 64: return BCL_R1(64); case 128: return BCL_R1(128); default: return BCL_R1(256); }
 #undef BCL_R1
 }
 
-cudaError_t launch_gemm_irfft(const ProblemDev& P, int B, int64_t n_begin, int nc, const void* Yf, cudaStream_t st) {
+cudaError_t launch_gemm_irfft(const ProblemDev& P, int B, int64_t n_begin, int nc, const void* Yf, const void* Yf_lo, cudaStream_t st) {
     const int nt = gemm::rows_nt(P.p, B);
-#define BCL_R3(BB) (nt == 2 ? gemm::launch_irfft_rows_t<BB, 2>(P, n_begin, nc, Yf, st) : gemm::launch_irfft_rows_t<BB, 1>(P, n_begin, nc, Yf, st))
+#define BCL_R3(BB) (nt == 2 ? gemm::launch_irfft_rows_t<BB, 2>(P, n_begin, nc, Yf, Yf_lo, st) : gemm::launch_irfft_rows_t<BB, 1>(P, n_begin, nc, Yf, Yf_lo, st))
     switch (B) { case 64: return BCL_R3(64); case 128: return BCL_R3(128); default: return BCL_R3(256); }
 #undef BCL_R3
 }
 
 // status: device int, set non-zero if a pipeline wait timed out.
-cudaError_t launch_gemm_mma(const void* Xf, const void* Cmat, void* Yf, int* status, int p, int q, int B, int nc, int max_ctas, cudaStream_t st) {
-    const gemm::Geometry g = gemm::geometry(p, q, B);
+// Xf_lo / Yf_lo != NULL: split layout (Cmat then carries Cmat_lo at geometry(.., split = 1).cmat_lo_off)
+cudaError_t launch_gemm_mma(const void* Xf, const void* Xf_lo, const void* Cmat, void* Yf, void* Yf_lo, int* status, int p, int q, int B, int nc, int max_ctas,
+                            cudaStream_t st) {
+    const int split = (Xf_lo != nullptr && Yf_lo != nullptr) ? 1 : 0;
+    const gemm::Geometry g = gemm::geometry(p, q, B, split);
     gemm::StageLaunch<gemm::GemmArgs> L;
     if (!gemm::prep_gemm(Xf, Cmat, Yf, status, g, nc, L)) return cudaErrorNotSupported;
-    cudaError_t e = cudaFuncSetAttribute(gemm::freq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
-    if (e != cudaSuccess) return e;
     const int grid = L.a.num_items < max_ctas ? L.a.num_items : max_ctas;
     if (grid < 1) return cudaSuccess;
+    if (split) {
+        gemm::GemmLoMaps lo;
+        if (!gemm::prep_gemm_lo(Xf_lo, Cmat, Yf_lo, g, nc, &lo)) return cudaErrorNotSupported;
+        cudaError_t e = cudaFuncSetAttribute(gemm::freq_gemm_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+        if (e != cudaSuccess) return e;
+        return gemm::launch_pdl(gemm::freq_gemm_split_kernel, (unsigned)grid, gemm::GEMM_THREADS, L.smem, st, L.tm_in, L.tm_w, L.tm_out, lo, L.a);
+    }
+    cudaError_t e = cudaFuncSetAttribute(gemm::freq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) return e;
     return gemm::launch_pdl(gemm::freq_gemm_kernel, (unsigned)grid, gemm::GEMM_THREADS, L.smem, st, L.tm_in, L.tm_w, L.tm_out, L.a);
 }
 
@@ -391,7 +438,7 @@ cudaError_t launch_prefill_stage1(const ProblemDev& P, int B, const void* spec_g
     const bool tc_ok = gemm::dft_tc_supported(B, P.x_dtype) && spec_gemm != nullptr;
     if (impl == 2 && !tc_ok) return cudaErrorNotSupported;
     if (impl != 1 && tc_ok) return gemm::launch_dft_fwd_tc(P, g, spec_gemm, n_begin, nc, Xf, status, sm_count(), st);
-    return launch_gemm_rfft(P, B, n_begin, nc, Xf, st);
+    return launch_gemm_rfft(P, B, n_begin, nc, Xf, nullptr, st);
 }
 
 cudaError_t launch_prefill_stage3(const ProblemDev& P, int B, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, int impl, cudaStream_t st) {
@@ -399,18 +446,34 @@ cudaError_t launch_prefill_stage3(const ProblemDev& P, int B, const void* spec_g
     const bool tc_ok = gemm::dft_tc_supported(B, P.x_dtype) && P.y_dtype == P.x_dtype && spec_gemm != nullptr && P.n_extra == 0;   // peer destinations: plain stores
     if (impl == 2 && !tc_ok) return cudaErrorNotSupported;
     if (impl != 1 && tc_ok) return gemm::launch_dft_inv_tc(P, g, spec_gemm, n_begin, nc, Yf, status, sm_count(), st);
-    return launch_gemm_irfft(P, B, n_begin, nc, Yf, st);
+    return launch_gemm_irfft(P, B, n_begin, nc, Yf, nullptr, st);
 }
 
-cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gemm, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    const gemm::Geometry g = gemm::geometry(P.p, P.q, B);
-    const int64_t ncmax = gemm_chunk_tokens(P.N, P.p, P.q, B, workspace_bytes);
+// split = 1: fp32-accurate chain (fp32 spectra): CUDA-core fp32 rfft -> (hi, lo) Xf -> split tcgen05 GEMM -> (hi, lo) Yf -> CUDA-core irfft
+cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gemm, void* workspace, size_t workspace_bytes, int split, cudaStream_t st) {
+    const gemm::Geometry g = gemm::geometry(P.p, P.q, B, split);
+    const int64_t ncmax = gemm_chunk_tokens(P.N, P.p, P.q, B, workspace_bytes, split);
     if (ncmax < 1) return cudaErrorInvalidValue;
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     int* status = reinterpret_cast<int*>(ws);
     const size_t ctr_bytes = gemm::fused_counter_bytes(P.N);
+    const size_t xfb = (gemm::xf_bytes(g, ncmax) + 255) & ~(size_t)255, yfb = (gemm::yf_bytes(g, ncmax) + 255) & ~(size_t)255;
     unsigned char* Xf = ws + kWsHeader + ctr_bytes;
-    unsigned char* Yf = Xf + ((gemm::xf_bytes(g, ncmax) + 255) & ~(size_t)255);
+    unsigned char* Yf = Xf + xfb * (split ? 2 : 1);
+    if (split) {
+        unsigned char* Xf_lo = Xf + xfb;
+        unsigned char* Yf_lo = Yf + yfb;
+        cudaError_t e = cudaMemsetAsync(status, 0, kWsHeader, st);
+        if (e != cudaSuccess) return e;
+        const int ctas = sm_count();
+        for (int64_t n0 = 0; n0 < P.N; n0 += ncmax) {
+            const int nc = (int)((P.N - n0 < ncmax) ? (P.N - n0) : ncmax);
+            if ((e = launch_gemm_rfft(P, B, n0, nc, Xf, Xf_lo, st)) != cudaSuccess) return e;
+            if ((e = launch_gemm_mma(Xf, Xf_lo, spec_gemm, Yf, Yf_lo, status, P.p, P.q, B, nc, ctas, st)) != cudaSuccess) return e;
+            if ((e = launch_gemm_irfft(P, B, n0, nc, Yf, Yf_lo, st)) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     static const int impl = getenv("BCL_PREFILL_DFT") ? atoi(getenv("BCL_PREFILL_DFT")) : 0;       // A/B switch for profiling only
     // Single-launch pipeline (bcl_prefill_fused.cu): opt-in.  Measured 155-165 us against 140 us for the three launches
     // (4096->4096, 16384 tokens): every stage's epilogue already runs near the TMEM read rate, so splitting the SMs three ways
@@ -429,7 +492,7 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
     for (int64_t n0 = 0; n0 < P.N; n0 += ncmax) {
         const int nc = (int)((P.N - n0 < ncmax) ? (P.N - n0) : ncmax);
         if ((e = launch_prefill_stage1(P, B, spec_gemm, n0, nc, Xf, status, impl, st)) != cudaSuccess) return e;
-        if ((e = launch_gemm_mma(Xf, spec_gemm, Yf, status, P.p, P.q, B, nc, ctas, st)) != cudaSuccess) return e;
+        if ((e = launch_gemm_mma(Xf, nullptr, spec_gemm, Yf, nullptr, status, P.p, P.q, B, nc, ctas, st)) != cudaSuccess) return e;
         if ((e = launch_prefill_stage3(P, B, spec_gemm, n0, nc, Yf, status, impl, st)) != cudaSuccess) return e;
     }
     return cudaSuccess;

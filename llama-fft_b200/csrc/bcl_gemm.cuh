@@ -28,16 +28,21 @@ constexpr int KATOM = 64;            // 16-bit elements per 128-byte swizzle row
 constexpr int NCHUNK = 64;           // columns (= 32 output blocks) of one frequency-GEMM tile
 
 struct Geometry {
-    int B, p, q;
+    int B, p, q, split;
     int F, FG, Kp, KG, Np, NCH;
-    size_t cmat_bytes, wf16_off, wbf16_off, winv_off, total_bytes;
+    // byte offsets inside the GEMM-layout spectrum buffer; Cmat_lo exists only in the split (fp32-accurate) layout
+    size_t cmat_bytes, cmat_lo_off, wf16_off, wbf16_off, winv_off, total_bytes;
 };
 
 __host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-__host__ inline Geometry geometry(int p, int q, int B) {
+// split = 1 (fp32 spectra on the tensor cores): every bf16 operand of the frequency GEMM is a (hi, lo) pair, v = hi + lo to
+// ~2^-17, and A*B is evaluated as Ahi*Bhi + Ahi*Blo + Alo*Bhi with fp32 accumulation -- the 1e-4 parity class of the
+// reference's complex64 contraction (src/patch_llama_fft.py:260).  Xf / Yf are (hi, lo) pairs too (lo buffer right after
+// hi); the rfft / irfft stages then run on the CUDA cores in fp32 (register FFT of bcl_fft.cuh).
+__host__ inline Geometry geometry(int p, int q, int B, int split = 0) {
     Geometry g;
-    g.B = B; g.p = p; g.q = q;
+    g.B = B; g.p = p; g.q = q; g.split = split;
     g.F = B / 2;
     g.FG = g.F / 4;
     g.Kp = round_up(2 * q, 16);
@@ -45,7 +50,8 @@ __host__ inline Geometry geometry(int p, int q, int B) {
     g.Np = round_up(2 * p, NCHUNK);
     g.NCH = g.Np / NCHUNK;
     g.cmat_bytes = ((size_t)g.F * g.Np * g.Kp * 2 + 1023) & ~(size_t)1023;
-    g.wf16_off = g.cmat_bytes;
+    g.cmat_lo_off = g.cmat_bytes;
+    g.wf16_off = g.cmat_bytes * (split ? 2 : 1);
     g.wbf16_off = g.wf16_off + (size_t)B * B * 2;
     g.winv_off = g.wbf16_off + (size_t)B * B * 2;
     g.total_bytes = g.winv_off + (size_t)B * B * 2;

@@ -44,16 +44,18 @@ size_t stream_smem_bytes(int B, int nt, int q, int warps);
 int stream_pick_nt(int64_t N, int q, int B);
 
 // prefill path (bcl_gemm.cu): GEMM-layout spectrum, the three stages, and the chunked forward that chains them
-size_t gemm_spectrum_bytes(int p, int q, int B);
-size_t gemm_workspace_bytes(int64_t N, int p, int q, int B);
-int64_t gemm_chunk_tokens(int64_t N, int p, int q, int B, size_t workspace_bytes);
-cudaError_t launch_spectrum_gemm(const float* c, void* spec, int p, int q, int B, cudaStream_t st);
-cudaError_t launch_gemm_rfft(const ProblemDev& P, int B, int64_t n_begin, int nc, void* Xf, cudaStream_t st);
-cudaError_t launch_gemm_mma(const void* Xf, const void* Cmat, void* Yf, int* status, int p, int q, int B, int nc, int max_ctas, cudaStream_t st);
-cudaError_t launch_gemm_irfft(const ProblemDev& P, int B, int64_t n_begin, int nc, const void* Yf, cudaStream_t st);
+// split = 1: the fp32-accurate variant (fp32 spectra): (hi, lo) bf16 pairs for Cmat / Xf / Yf, three MMAs per k-step
+size_t gemm_spectrum_bytes(int p, int q, int B, int split);
+size_t gemm_workspace_bytes(int64_t N, int p, int q, int B, int split);
+int64_t gemm_chunk_tokens(int64_t N, int p, int q, int B, size_t workspace_bytes, int split);
+cudaError_t launch_spectrum_gemm(const float* c, void* spec, int p, int q, int B, int split, cudaStream_t st);
+cudaError_t launch_gemm_rfft(const ProblemDev& P, int B, int64_t n_begin, int nc, void* Xf, void* Xf_lo, cudaStream_t st);
+cudaError_t launch_gemm_mma(const void* Xf, const void* Xf_lo, const void* Cmat, void* Yf, void* Yf_lo, int* status, int p, int q, int B, int nc, int max_ctas,
+                            cudaStream_t st);
+cudaError_t launch_gemm_irfft(const ProblemDev& P, int B, int64_t n_begin, int nc, const void* Yf, const void* Yf_lo, cudaStream_t st);
 cudaError_t launch_prefill_stage1(const ProblemDev& P, int B, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, int impl, cudaStream_t st);
 cudaError_t launch_prefill_stage3(const ProblemDev& P, int B, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, int impl, cudaStream_t st);
-cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* Cmat, void* workspace, size_t workspace_bytes, cudaStream_t st);
+cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* Cmat, void* workspace, size_t workspace_bytes, int split, cudaStream_t st);
 
 // calibration gradients (bcl_backward.cu)
 size_t backward_workspace_bytes(int64_t N, int p, int q, int B);

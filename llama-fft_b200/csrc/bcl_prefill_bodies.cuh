@@ -194,8 +194,20 @@ __device__ __forceinline__ void decode_item(const GemmArgs& a, int item, int& fg
     m = a.deps.ascending ? r / a.FG : a.m_tiles - 1 - r / a.FG;
 }
 
+// (hi, lo) split of two floats: hi = bf16(v), lo = bf16(v - hi)
+__device__ __forceinline__ void split_bf(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    __nv_bfloat162 h; h.x = ha; h.y = hb;
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = pack_bf(a - __bfloat162float(ha), b - __bfloat162float(hb));
+}
+struct GemmLoMaps { CUtensorMap A, B, Y; };      // the lo halves of the split layout (bcl_gemm.cuh: geometry(..., split = 1))
+
+// SPLIT: operands are (hi, lo) bf16 pairs; D += Ahi*Bhi + Ahi*Blo + Alo*Bhi (fp32 accumulate), outputs stored as (hi, lo).
+template <bool SPLIT>
 __device__ __forceinline__ void freq_gemm_body(unsigned char* gemm_smem, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
-                                               const GemmArgs& a, const int first, const int stride) {
+                                               const GemmLoMaps* lo, const GemmArgs& a, const int first, const int stride) {
+    constexpr uint32_t STAGE = SPLIT ? 2 * STAGE_BYTES : STAGE_BYTES;            // [A hi | B hi | A lo | B lo]
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(gemm_smem);
     uint32_t* sig = reinterpret_cast<uint32_t*>(gemm_smem + 512);                // signaller queue (fused launch)
     unsigned char* epi = gemm_smem + 1024;                                       // EPI_WARPS x EPI_NBUF buffers x EPI_BUF_BYTES
@@ -210,7 +222,10 @@ __device__ __forceinline__ void freq_gemm_body(unsigned char* gemm_smem, const C
         for (int i = 0; i <= SIG_RING; ++i) sig[i] = 0u;
         fence_barrier_init();
     }
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY); }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY);
+        if constexpr (SPLIT) { tma_prefetch_desc(&lo->A); tma_prefetch_desc(&lo->B); tma_prefetch_desc(&lo->Y); }
+    }
     if (warp == 1) tmem_alloc(&bars->tmem_base, 2 * SET_COLS);
     tc_fence_before_sync();
     __syncthreads();
@@ -233,10 +248,14 @@ __device__ __forceinline__ void freq_gemm_body(unsigned char* gemm_smem, const C
                 for (int fl = 0; fl < 4; ++fl) {
                     for (int ka = 0; ka < a.k_atoms; ++ka) {
                         if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 1); goto done; }
-                        unsigned char* sa = ring + (size_t)stage * STAGE_BYTES;
-                        mbar_arrive_expect_tx(&bars->full[stage], STAGE_BYTES);
+                        unsigned char* sa = ring + (size_t)stage * STAGE;
+                        mbar_arrive_expect_tx(&bars->full[stage], STAGE);
                         tma_load_4d_hint(sa, &tmA, 0, m * (TILE_M / TOK_GROUP), ka * 8, 4 * fg + fl, &bars->full[stage], L2_EVICT_FIRST);   // read once
                         tma_load_3d_hint(sa + A_STAGE_BYTES, &tmB, ka * KATOM, nch * NCHUNK, 4 * fg + fl, &bars->full[stage], L2_EVICT_LAST);   // re-read by every tile
+                        if constexpr (SPLIT) {
+                            tma_load_4d_hint(sa + STAGE_BYTES, &lo->A, 0, m * (TILE_M / TOK_GROUP), ka * 8, 4 * fg + fl, &bars->full[stage], L2_EVICT_FIRST);
+                            tma_load_3d_hint(sa + STAGE_BYTES + A_STAGE_BYTES, &lo->B, ka * KATOM, nch * NCHUNK, 4 * fg + fl, &bars->full[stage], L2_EVICT_LAST);
+                        }
                         if (++stage == S) { stage = 0; ph ^= 1u; }
                     }
                 }
@@ -257,11 +276,18 @@ __device__ __forceinline__ void freq_gemm_body(unsigned char* gemm_smem, const C
                     for (int ka = 0; ka < a.k_atoms; ++ka) {
                         if (!mbar_wait(&bars->full[stage], ph)) { atomicExch(a.status, 3); goto done; }
                         tc_fence_after_sync();
-                        const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE_BYTES);
+                        const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE);
                         const uint64_t bdesc = umma_desc_k_sw128(sa + A_STAGE_BYTES);
                         const int ks = min(4, (a.KG - ka * 8) / 2);
-                        for (int kk = 0; kk < ks; ++kk)                          // one k-step = 16 elements = 2 kg slabs of 2048 bytes
-                            umma_bf16_ss(d_tmem, umma_desc_k_nosw(sa + (uint32_t)kk * 4096u, 128u, 2048u), bdesc + (uint64_t)(2 * kk), idesc, (ka | kk) != 0 ? 1u : 0u);
+                        for (int kk = 0; kk < ks; ++kk) {                        // one k-step = 16 elements = 2 kg slabs of 2048 bytes
+                            const uint64_t adesc = umma_desc_k_nosw(sa + (uint32_t)kk * 4096u, 128u, 2048u);
+                            umma_bf16_ss(d_tmem, adesc, bdesc + (uint64_t)(2 * kk), idesc, (ka | kk) != 0 ? 1u : 0u);
+                            if constexpr (SPLIT) {
+                                const uint64_t bdesc_lo = umma_desc_k_sw128(sa + STAGE_BYTES + A_STAGE_BYTES);
+                                umma_bf16_ss(d_tmem, adesc, bdesc_lo + (uint64_t)(2 * kk), idesc, 1u);
+                                umma_bf16_ss(d_tmem, umma_desc_k_nosw(sa + STAGE_BYTES + (uint32_t)kk * 4096u, 128u, 2048u), bdesc + (uint64_t)(2 * kk), idesc, 1u);
+                            }
+                        }
                         umma_commit(&bars->empty[stage]);                        // smem stage reusable once these MMAs retire
                         if (++stage == S) { stage = 0; ph ^= 1u; }
                     }
@@ -306,22 +332,46 @@ __device__ __forceinline__ void freq_gemm_body(unsigned char* gemm_smem, const C
                     if (lane == 0) mbar_arrive(&bars->tmem_empty[set]);
                     if (warp == 2 && lane == 0) BCL_TRACE(6, it);
                 }
-                if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();              // the store that last read this buffer has finished
-                __syncwarp();
-                uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)buf * EPI_BUF_BYTES) + lane;
+                const int tg = m * (TILE_M / TOK_GROUP) + quarter, j0 = nch * 32 + jc * 8;
+                if constexpr (!SPLIT) {
+                    if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();          // the store that last read this buffer has finished
+                    __syncwarp();
+                    uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)buf * EPI_BUF_BYTES) + lane;
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                    dst[jj * 32] = make_uint4(pack_bf(__uint_as_float(r[0][2 * jj]), __uint_as_float(r[0][2 * jj + 1])),
-                                              pack_bf(__uint_as_float(r[1][2 * jj]), __uint_as_float(r[1][2 * jj + 1])),
-                                              pack_bf(__uint_as_float(r[2][2 * jj]), __uint_as_float(r[2][2 * jj + 1])),
-                                              pack_bf(__uint_as_float(r[3][2 * jj]), __uint_as_float(r[3][2 * jj + 1])));
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_4d_hint(&tmY, 0, m * (TILE_M / TOK_GROUP) + quarter, nch * 32 + jc * 8, fg, stg + (size_t)buf * EPI_BUF_BYTES, L2_EVICT_LAST);   // the next stage reads it
-                    tma_store_commit();
+                    for (int jj = 0; jj < 8; ++jj)
+                        dst[jj * 32] = make_uint4(pack_bf(__uint_as_float(r[0][2 * jj]), __uint_as_float(r[0][2 * jj + 1])),
+                                                  pack_bf(__uint_as_float(r[1][2 * jj]), __uint_as_float(r[1][2 * jj + 1])),
+                                                  pack_bf(__uint_as_float(r[2][2 * jj]), __uint_as_float(r[2][2 * jj + 1])),
+                                                  pack_bf(__uint_as_float(r[3][2 * jj]), __uint_as_float(r[3][2 * jj + 1])));
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d_hint(&tmY, 0, tg, j0, fg, stg + (size_t)buf * EPI_BUF_BYTES, L2_EVICT_LAST);   // the next stage reads it
+                        tma_store_commit();
+                    }
+                    if (++buf == EPI_NBUF) buf = 0;
+                } else {
+                    static_assert(EPI_NBUF >= 2, "split epilogue: one staging buffer for hi, one for lo");
+                    if (lane == 0) tma_store_wait_read<0>();                     // both buffers (hi, lo) free again
+                    __syncwarp();
+                    uint4* dh = reinterpret_cast<uint4*>(stg) + lane;
+                    uint4* dl = reinterpret_cast<uint4*>(stg + EPI_BUF_BYTES) + lane;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        uint32_t hi[4], lw[4];
+#pragma unroll
+                        for (int fl = 0; fl < 4; ++fl) split_bf(__uint_as_float(r[fl][2 * jj]), __uint_as_float(r[fl][2 * jj + 1]), hi[fl], lw[fl]);
+                        dh[jj * 32] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        dl[jj * 32] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d_hint(&tmY, 0, tg, j0, fg, stg, L2_EVICT_LAST);
+                        tma_store_4d_hint(&lo->Y, 0, tg, j0, fg, stg + EPI_BUF_BYTES, L2_EVICT_LAST);
+                        tma_store_commit();
+                    }
                 }
-                if (++buf == EPI_NBUF) buf = 0;
             }
             if (warp == 2 && lane == 0) BCL_TRACE(7, it);
             if (a.deps.done_ctr != nullptr && lane == 0) done_trk.item_committed(sig, m, max(jc1 - jc0, 0));
@@ -698,7 +748,7 @@ template <typename Args> struct StageLaunch {
 };
 long long* trace_ptr(int stage);
 bool prep_dft_fwd(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, StageLaunch<DftArgs>& L);
-bool prep_gemm(const void* Xf, const void* Cmat, void* Yf, int* status, const Geometry& g, int nc, StageLaunch<GemmArgs>& L);
+bool prep_gemm(const void* Xf, const void* Cmat, void* Yf, int* status, const Geometry& g, int nc, StageLaunch<GemmArgs>& L, GemmLoMaps* lo = nullptr);
 bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L);
 
 }  // namespace gemm

@@ -26,6 +26,7 @@ BLOCK_SIZE = 256
 NUM_LAYERS_TO_PATCH = 1
 
 PREFILL_MIN_TOKENS = int(os.environ.get("BCL_PREFILL_MIN_TOKENS", "256"))   # bf16-spectrum layers switch to the tcgen05 path from here
+PREFILL_MIN_TOKENS_F32 = int(os.environ.get("BCL_PREFILL_MIN_TOKENS_F32", "256"))   # fp32 spectra: split-bf16 tcgen05 GEMM + fp32 FFT stages
 
 MLP_TARGETS = ("gate_proj", "up_proj", "down_proj")
 ATTN_TARGETS = ("q_proj", "k_proj", "v_proj", "o_proj")
@@ -146,7 +147,7 @@ class BlockCirculantLinear(nn.Module):
 
     def build_spectrum(self, *, force: bool = False, layout: int = _cabi.LAYOUT_STREAM) -> torch.Tensor:
         """rfft(c) on c's device (replaces reference :256-257 / the _Cf_cache of src/bench_all_in_one.py:204-219), in the
-        STREAM layout (decode kernel) or the GEMM layout (tcgen05 prefill kernels, bf16 only).  Re-used until c is
+        STREAM layout (decode kernel) or the GEMM layout (tcgen05 prefill kernels; fp32 spectra -> split bf16 pairs).  Re-used until c is
         written to (its version counter moves), moved, or re-typed -- so load_bc_params / optimizer steps invalidate
         it, which the reference's cache key does not."""
         key = self._spectrum_key()
@@ -162,9 +163,8 @@ class BlockCirculantLinear(nn.Module):
         if layout == _cabi.LAYOUT_STREAM:
             spec = torch.empty(self.out_blocks, self.in_blocks, self.block_size, device=c.device, dtype=self.spectrum_dtype)
         else:
-            if self.spectrum_dtype != torch.bfloat16:
-                raise ValueError("the GEMM (tcgen05 prefill) spectrum layout is bf16 only")
-            nbytes = L.bcl_spectrum_bytes(self.out_blocks, self.in_blocks, self.block_size, _cabi.BF16, layout)
+            # bf16: one bf16 matrix per frequency; fp32: (hi, lo) bf16 pairs, v = hi + lo to ~2^-17 (the 1e-4 parity class)
+            nbytes = L.bcl_spectrum_bytes(self.out_blocks, self.in_blocks, self.block_size, _cabi.DTYPE[self.spectrum_dtype], layout)
             spec = torch.empty(nbytes, device=c.device, dtype=torch.uint8)      # Cmat + DFT matrices (include/bclinear.h)
         with torch.cuda.device(c.device):
             rc = L.bcl_precompute_spectrum(c32.data_ptr(), self.out_blocks, self.in_blocks, self.block_size,
@@ -181,8 +181,10 @@ class BlockCirculantLinear(nn.Module):
         self._spec, self._spec_gemm, self._spec_key = None, None, None
 
     def _use_prefill_path(self, n_tokens: int) -> bool:
-        """bf16 spectra and enough tokens to fill 128-row MMA tiles -> tcgen05 per-frequency GEMM path."""
-        return self.spectrum_dtype == torch.bfloat16 and n_tokens >= PREFILL_MIN_TOKENS and self.block_size in (64, 128, 256)
+        """Enough tokens to fill 128-row MMA tiles -> tcgen05 per-frequency GEMM path (bf16 spectra: all three stages on the
+        tensor cores; fp32 spectra: split-bf16 GEMM between fp32 CUDA-core FFT stages)."""
+        floor = PREFILL_MIN_TOKENS if self.spectrum_dtype == torch.bfloat16 else PREFILL_MIN_TOKENS_F32
+        return n_tokens >= floor and self.block_size in (64, 128, 256)
 
     # -- forward --------------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -216,7 +218,8 @@ class BlockCirculantLinear(nn.Module):
                 return y_flat.view(lead[0], lead[1], self.out_features) if lead is not None else y_flat
             layout = _cabi.LAYOUT_GEMM if self._use_prefill_path(x_flat.shape[0]) else _cabi.LAYOUT_STREAM
             spec = self.build_spectrum(force=not reuse, layout=layout)
-            y_flat = bc_forward(x_flat, spec, self.bias, self.out_blocks, self.in_blocks, self.block_size, layout=layout)
+            y_flat = bc_forward(x_flat, spec, self.bias, self.out_blocks, self.in_blocks, self.block_size, layout=layout,
+                                spectrum_dtype=self.spectrum_dtype)
         if lead is not None:
             return y_flat.view(lead[0], lead[1], self.out_features)
         return y_flat
@@ -237,7 +240,8 @@ def prefill_workspace(device, nbytes: int) -> torch.Tensor:
 
 
 def bc_forward(x_flat: torch.Tensor, spec: torch.Tensor, bias: Optional[torch.Tensor], p: int, q: int, B: int,
-               out: Optional[torch.Tensor] = None, *, layout: int = _cabi.LAYOUT_STREAM) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, *, layout: int = _cabi.LAYOUT_STREAM,
+               spectrum_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """One ``bcl_forward`` call: (N,in) -> (N,out).  Output dtype follows the reference: x.dtype, or the PyTorch
     promotion of x.dtype and bias.dtype when a bias is present (reference :266-271)."""
     if x_flat.stride(-1) != 1 or (x_flat.stride(0) * x_flat.element_size()) % 16 or x_flat.data_ptr() % 16:
@@ -249,7 +253,10 @@ def bc_forward(x_flat: torch.Tensor, spec: torch.Tensor, bias: Optional[torch.Te
     y = out if out is not None else torch.empty(N, p * B, device=x_flat.device, dtype=y_dtype)
     L = _cabi.lib()
     ws_ptr, ws_bytes = None, 0
-    spec_dt = _cabi.BF16 if layout == _cabi.LAYOUT_GEMM else _cabi.DTYPE[spec.dtype]
+    if layout == _cabi.LAYOUT_GEMM:                      # an opaque byte buffer: bf16 matrices, or (hi, lo) bf16 pairs for fp32 spectra
+        spec_dt = _cabi.DTYPE[spectrum_dtype] if spectrum_dtype is not None else _cabi.BF16
+    else:
+        spec_dt = _cabi.DTYPE[spec.dtype]
     if layout == _cabi.LAYOUT_GEMM and N > 0:
         ws_bytes = L.bcl_workspace_bytes(N, p, q, B, spec_dt, layout)
         ws = prefill_workspace(x_flat.device, ws_bytes)

@@ -135,7 +135,7 @@ def bc_forward_bcast(layer: BlockCirculantLinear, x: torch.Tensor, dsts: List[to
     p, q, B = layer.out_blocks, layer.in_blocks, layer.block_size
     layout = _cabi.LAYOUT_GEMM if layer._use_prefill_path(N) else _cabi.LAYOUT_STREAM
     spec = layer.build_spectrum(layout=layout)
-    spec_dt = _cabi.BF16 if layout == _cabi.LAYOUT_GEMM else _cabi.DTYPE[spec.dtype]
+    spec_dt = _cabi.DTYPE[layer.spectrum_dtype] if layout == _cabi.LAYOUT_GEMM else _cabi.DTYPE[spec.dtype]
     d0 = dsts[0]
     assert all(d.shape == (N, p * B) and d.dtype == d0.dtype and d.stride() == d0.stride() for d in dsts)
     L = _cabi.lib()

@@ -79,7 +79,7 @@ class SharedInputGroup:
         if layout == _cabi.LAYOUT_STREAM:
             spec = torch.empty(self.out_blocks, self.in_blocks, self.block_size, device=c.device, dtype=m0.spectrum_dtype)
         else:
-            nbytes = L.bcl_spectrum_bytes(self.out_blocks, self.in_blocks, self.block_size, _cabi.BF16, layout)
+            nbytes = L.bcl_spectrum_bytes(self.out_blocks, self.in_blocks, self.block_size, _cabi.DTYPE[m0.spectrum_dtype], layout)
             spec = torch.empty(nbytes, device=c.device, dtype=torch.uint8)
         with torch.cuda.device(c.device):
             rc = L.bcl_precompute_spectrum(c.data_ptr(), self.out_blocks, self.in_blocks, self.block_size, spec.data_ptr(),
@@ -94,7 +94,8 @@ class SharedInputGroup:
         m0 = self.members[0]
         layout = _cabi.LAYOUT_GEMM if m0._use_prefill_path(x_flat.shape[0]) else _cabi.LAYOUT_STREAM
         spec = self.build_spectrum(layout)
-        return bc_forward(x_flat, spec, self._bias, self.out_blocks, self.in_blocks, self.block_size, layout=layout)
+        return bc_forward(x_flat, spec, self._bias, self.out_blocks, self.in_blocks, self.block_size, layout=layout,
+                          spectrum_dtype=m0.spectrum_dtype)
 
     @staticmethod
     def _x_key(x_flat: torch.Tensor):

@@ -321,14 +321,17 @@ def test_prefill_chunking_small_workspace_and_full_size_properties():
         assert torch.equal(m(x1), m(x1))                                                     # deterministic
 
 
-def test_gemm_layout_rejects_fp32_spectrum_and_tiny_workspace():
+def test_gemm_layout_rejects_bad_spectrum_dtype_and_tiny_workspace():
     L = _cabi.lib()
-    assert L.bcl_spectrum_bytes(4, 4, 128, _cabi.F32, _cabi.LAYOUT_GEMM) == 0
+    assert L.bcl_spectrum_bytes(4, 4, 128, _cabi.F16, _cabi.LAYOUT_GEMM) == 0
+    # fp32 = the split layout: Cmat twice (hi, lo), the DFT matrices once
+    assert (L.bcl_spectrum_bytes(4, 4, 128, _cabi.F32, _cabi.LAYOUT_GEMM) - L.bcl_spectrum_bytes(4, 4, 128, _cabi.BF16, _cabi.LAYOUT_GEMM)
+            == 64 * 64 * 16 * 2)
     x = torch.zeros(256, 512, device=DEV)
     spec = torch.zeros(L.bcl_spectrum_bytes(4, 4, 128, _cabi.BF16, _cabi.LAYOUT_GEMM), device=DEV, dtype=torch.uint8)
     y = torch.zeros(256, 512, device=DEV)
     ws = torch.zeros(1024, device=DEV, dtype=torch.uint8)
-    rc = L.bcl_forward(x.data_ptr(), _cabi.F32, 256, 512, spec.data_ptr(), _cabi.F32, _cabi.LAYOUT_GEMM, 4, 4, 128, None, 0,
+    rc = L.bcl_forward(x.data_ptr(), _cabi.F32, 256, 512, spec.data_ptr(), _cabi.F16, _cabi.LAYOUT_GEMM, 4, 4, 128, None, 0,
                        y.data_ptr(), _cabi.F32, 512, ws.data_ptr(), ws.numel(), _cabi.stream_ptr(DEV))
     assert rc == -5
     rc = L.bcl_forward(x.data_ptr(), _cabi.F32, 256, 512, spec.data_ptr(), _cabi.BF16, _cabi.LAYOUT_GEMM, 4, 4, 128, None, 0,
@@ -412,3 +415,89 @@ def test_prefill_fused_single_launch_matches_three_launch_chain(tmp_path, inf, o
     rows = torch.tensor([0, 1, 127, 128, N // 2, N - 2, N - 1])
     if not has_bias:
         assert_close(outs["fused"][rows], O.bc_forward_torch(c, x[rows].float()), 1e-2, dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fp32 spectra on the tensor cores: split (hi, lo) bf16 operands, three MMAs per k-step, fp32 CUDA-core FFT stages
+# (north star: max relative error <= 1e-4 for fp32 spectra)
+# ---------------------------------------------------------------------------------------------------------
+def make_layer_f32(c, bias=None):
+    p, q, B = c.shape
+    m = bc.BlockCirculantLinear(q * B, p * B, block_size=B, bias=bias is not None, spectrum_dtype=torch.float32)
+    with torch.no_grad():
+        m.c.copy_(c)
+        if bias is not None:
+            m.bias.data = bias.clone()
+    return m.to(DEV).eval()
+
+
+@pytest.mark.parametrize("inf,outf,B", SHAPES + [(8192, 1024, 256)])
+@pytest.mark.parametrize("N", [256, 333])
+def test_split_prefill_forward_fp32_class_vs_oracle(inf, outf, B, N):
+    g = torch.Generator().manual_seed(inf + outf + B + N + 1)
+    c = torch.randn(outf // B, inf // B, B, generator=g) * 0.01
+    x = torch.randn(N, inf, generator=g)
+    m = make_layer_f32(c)
+    assert m._use_prefill_path(N)
+    with torch.no_grad():
+        y = m(x.to(DEV))
+    assert prefill_status(DEV) == 0
+    assert_close(y, O.bc_forward_torch(c, x), 1e-4)
+
+
+def test_split_prefill_matches_fp64_dense_oracle_and_stream_kernel():
+    g = torch.Generator().manual_seed(77)
+    p, q, B, N = 5, 9, 64, 300
+    c = torch.randn(p, q, B, generator=g) * 0.05
+    bias = torch.randn(p * B, generator=g) * 0.1
+    x = torch.randn(N, q * B, generator=g)
+    m = make_layer_f32(c, bias)
+    with torch.no_grad():
+        y = m(x.to(DEV))
+        ys = bc_forward(x.to(DEV), m.build_spectrum(), m.bias, p, q, B)              # the CUDA-core stream kernel, fp32 spectrum
+    y_ref = torch.from_numpy(O.bc_forward_dense64(c, x, bias))
+    assert_close(y, y_ref, 1e-4)
+    assert_close(y, ys, 1e-4)
+
+
+@pytest.mark.parametrize("dtype,bias_dt", [(torch.float16, None), (torch.float16, torch.float32), (torch.bfloat16, torch.bfloat16)])
+def test_split_prefill_16bit_io_3d_and_bias(dtype, bias_dt):
+    g = torch.Generator().manual_seed(5)
+    p, q, B = 8, 16, 128
+    c = torch.randn(p, q, B, generator=g) * 0.01
+    bias = None if bias_dt is None else (torch.randn(p * B, generator=g) * 0.1).to(bias_dt)
+    x = torch.randn(3, 100, q * B, generator=g).to(dtype)
+    m = make_layer_f32(c, bias)
+    with torch.no_grad():
+        y = m(x.to(DEV))
+    y_ref = O.bc_forward_torch(c, x, bias)
+    assert y.shape == (3, 100, p * B) and y.dtype == y_ref.dtype
+    y32 = O.bc_forward_torch(c, x.float())
+    assert_close(y, y_ref, 1e-4, dtype, mag=y32.abs() + (0 if bias is None else bias.float().abs()))
+
+
+def test_split_prefill_chunked_workspace_full_size():
+    """N = 8 x 2048 + ragged tail through a workspace that forces several chunks; row subset against the oracle at 1e-4."""
+    g = torch.Generator().manual_seed(10)
+    p = q = 32
+    B = 128
+    c = torch.randn(p, q, B, generator=g) * 0.01
+    m = make_layer_f32(c)
+    spec = m.build_spectrum(layout=_cabi.LAYOUT_GEMM)
+    N = 16384 + 77
+    x = torch.randn(N, 4096, generator=g).to(DEV)
+    L = _cabi.lib()
+    full = L.bcl_workspace_bytes(N, p, q, B, _cabi.F32, _cabi.LAYOUT_GEMM)
+    per_tok = (B // 2) * (64 + 64) * 2 * 2
+    ws = torch.empty(4096 + 1000 * per_tok, device=DEV, dtype=torch.uint8)
+    assert ws.numel() < full
+    y = torch.empty(N, 4096, device=DEV)
+    rc = L.bcl_forward(x.data_ptr(), _cabi.F32, N, 4096, spec.data_ptr(), _cabi.F32, _cabi.LAYOUT_GEMM, p, q, B, None, 0,
+                       y.data_ptr(), _cabi.F32, 4096, ws.data_ptr(), ws.numel(), _cabi.stream_ptr(DEV))
+    _cabi.check(rc, "bcl_forward")
+    torch.cuda.synchronize()
+    assert int(ws[:4].view(torch.int32).item()) == 0
+    rows = torch.tensor([0, 127, 128, 895, 896, 897, 8000, 16383, 16384, N - 1])
+    assert_close(y[rows], O.bc_forward_torch(c, x[rows].cpu()), 1e-4)
+    with torch.no_grad():
+        assert torch.equal(m(x), y)                                                        # unchunked == chunked, deterministic
