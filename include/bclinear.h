@@ -30,17 +30,20 @@
 extern "C" {
 #endif
 
-#define BCL_ABI_VERSION 8
+#define BCL_ABI_VERSION 9
 
 typedef enum bcl_dtype { BCL_F32 = 0, BCL_F16 = 1, BCL_BF16 = 2 } bcl_dtype;
 
 /* Spectrum layouts in HBM (DESIGN.md "Data layout").
  *   STREAM  [p][q][B] packed half-spectrum, frequency-contiguous: {Re F0, Re F_{B/2}, Re F1, Im F1, ...}.
  *           Exactly the size of c.  Used by the bandwidth-bound small-N (decode) kernel.
- *   GEMM    the tcgen05 prefill path's buffer (bf16 only): per-frequency real-embedded complex matrices
+ *   GEMM    the tcgen05 prefill path's buffer: per-frequency real-embedded complex matrices
  *           Cmat[f][n][k], f < B/2 packed frequency slots, n = 2j+{re,im} < Np, k = 2i+{re,im} < Kp (K-major rows,
  *           Np = 2p rounded up to 64, Kp = 2q rounded up to 16, zero padded); [[Cr,-Ci],[Ci,Cr]] per (j,i), slot 0 =
- *           diag(C_dc, C_ny); followed by the forward (fp16, bf16) and inverse (bf16) B x B DFT matrices. */
+ *           diag(C_dc, C_ny); followed by the forward (fp16, bf16) and inverse (bf16) B x B DFT matrices.
+ *           spec_dtype BCL_BF16: one bf16 Cmat (parity class 1e-2).  spec_dtype BCL_F32: the SPLIT layout -- Cmat_hi then
+ *           Cmat_lo, bf16 each, value = hi + lo to ~2^-17; the frequency GEMM evaluates Ahi*Bhi + Ahi*Blo + Alo*Bhi with fp32
+ *           accumulation and the rfft / irfft stages run in fp32 (parity class 1e-4, the reference's complex64 contraction). */
 typedef enum bcl_layout { BCL_LAYOUT_STREAM = 0, BCL_LAYOUT_GEMM = 1 } bcl_layout;
 
 typedef enum bcl_status {

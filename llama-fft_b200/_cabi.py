@@ -10,7 +10,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BCL_LIB_PATH") or os.path.join(_HERE, "libbclinear.so")   # override: A/B builds when profiling
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 F32, F16, BF16 = 0, 1, 2
 LAYOUT_STREAM, LAYOUT_GEMM = 0, 1
 

@@ -27,13 +27,28 @@ template <int B>
 __global__ void __launch_bounds__(DFT_THREADS, 1) dft_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                                                      const __grid_constant__ CUtensorMap tmXf, const __grid_constant__ DftArgs a) {
     extern __shared__ __align__(1024) unsigned char dft_smem[];
-    dft_fwd_body<B>(dft_smem, tmX, tmW, tmXf, a, (int)blockIdx.x, (int)gridDim.x);
+    dft_fwd_body<B, false>(dft_smem, tmX, tmW, tmXf, nullptr, a, (int)blockIdx.x, (int)gridDim.x);
 }
 template <int B>
 __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_kernel(const __grid_constant__ CUtensorMap tmYf, const __grid_constant__ CUtensorMap tmW,
                                                                      const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ DftArgs a) {
     extern __shared__ __align__(1024) unsigned char dft_smem[];
-    dft_inv_body<B>(dft_smem, tmYf, tmW, tmOut, a, (int)blockIdx.x, (int)gridDim.x);
+    dft_inv_body<B, false>(dft_smem, tmYf, tmW, tmOut, nullptr, a, (int)blockIdx.x, (int)gridDim.x);
+}
+// fp32-accurate variants: (hi, lo) DFT matrices and (hi, lo) intermediates
+template <int B>
+__global__ void __launch_bounds__(DFT_THREADS, 1) dft_fwd_tc_split_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                                                                           const __grid_constant__ CUtensorMap tmXf, const __grid_constant__ DftLoMaps lo,
+                                                                           const __grid_constant__ DftArgs a) {
+    extern __shared__ __align__(1024) unsigned char dft_smem[];
+    dft_fwd_body<B, true>(dft_smem, tmX, tmW, tmXf, &lo, a, (int)blockIdx.x, (int)gridDim.x);
+}
+template <int B>
+__global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_split_kernel(const __grid_constant__ CUtensorMap tmYf, const __grid_constant__ CUtensorMap tmW,
+                                                                           const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ DftLoMaps lo,
+                                                                           const __grid_constant__ DftArgs a) {
+    extern __shared__ __align__(1024) unsigned char dft_smem[];
+    dft_inv_body<B, true>(dft_smem, tmYf, tmW, tmOut, &lo, a, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // =========================================================================================================
@@ -41,12 +56,13 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_kernel(const __grid
 // =========================================================================================================
 bool dft_tc_supported(int B, int act_dtype) { return (B == 64 || B == 128) && (act_dtype == BCL_F16 || act_dtype == BCL_BF16); }
 
-static size_t dft_smem_bytes(int B, uint32_t stage_bytes, int stages) {
-    return 1024 + DFT_EPI_WARPS * DFT_NBUF * DFT_EPI_BUF + (size_t)(B / KATOM) * B * 128 + (size_t)stages * stage_bytes;
+// nbuf: staging buffers per epilogue warp; wmats: resident DFT matrices (1, or 2 = hi + lo)
+static size_t dft_smem_bytes(int B, uint32_t stage_bytes, int stages, int nbuf = DFT_NBUF, int wmats = 1) {
+    return 1024 + DFT_EPI_WARPS * nbuf * DFT_EPI_BUF + (size_t)wmats * (B / KATOM) * B * 128 + (size_t)stages * stage_bytes;
 }
-static int dft_pick_stages(int B, uint32_t stage_bytes) {
+static int dft_pick_stages(int B, uint32_t stage_bytes, int nbuf = DFT_NBUF, int wmats = 1) {
     int s = DFT_MAX_STAGES;
-    while (s > 2 && dft_smem_bytes(B, stage_bytes, s) > 225 * 1024) --s;
+    while (s > 1 && dft_smem_bytes(B, stage_bytes, s, nbuf, wmats) > 225 * 1024) --s;
     return s;
 }
 
@@ -65,7 +81,9 @@ long long* trace_ptr(int stage) {
     return reinterpret_cast<long long*>(strtoull(tp, nullptr, 0));
 }
 
-bool prep_dft_fwd(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, StageLaunch<DftArgs>& L) {
+bool prep_dft_fwd(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, StageLaunch<DftArgs>& L,
+                  void* Xf_lo, DftLoMaps* lo) {
+    const bool split = lo != nullptr;
     const int B = g.B;
     const bool bf = P.x_dtype == BCL_BF16;
     const CUtensorMapDataType adt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -84,12 +102,18 @@ bool prep_dft_fwd(const ProblemDev& P, const Geometry& g, const void* spec_gemm,
     a.m_tiles = (nc + TILE_M - 1) / TILE_M; a.groups = g.KG; a.num_items = a.m_tiles * g.KG; a.act_bf16 = bf ? 1 : 0;
     a.trace = trace_ptr(1);
     const uint32_t stage_bytes = (uint32_t)(B / KATOM) * TILE_M * 128;
-    a.stages = dft_pick_stages(B, stage_bytes);
-    L.smem = dft_smem_bytes(B, stage_bytes, a.stages);
+    a.stages = dft_pick_stages(B, stage_bytes, DFT_NBUF, split ? 2 : 1);
+    L.smem = dft_smem_bytes(B, stage_bytes, a.stages, DFT_NBUF, split ? 2 : 1);
+    if (split) {
+        if (!map_w(&lo->W, sb + (bf ? g.wbf16_lo_off : g.wf16_lo_off), B, adt)) return false;
+        if (!make_chunk_map(&lo->IO, Xf_lo, nc, g.KG, g.F, 1, 1, 8)) return false;
+    }
     return true;
 }
 
-bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L) {
+bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L,
+                  const void* Yf_lo, DftLoMaps* lo) {
+    const bool split = lo != nullptr;
     const int B = g.B;
     const bool bf = P.x_dtype == BCL_BF16;
     const CUtensorMapDataType adt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -107,29 +131,45 @@ bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm,
     a.status = status; a.bias = P.bias; a.n_begin = n_begin; a.nc = nc;
     a.m_tiles = (nc + TILE_M - 1) / TILE_M; a.groups = g.p; a.num_items = a.m_tiles * g.p; a.act_bf16 = bf ? 1 : 0;
     a.trace = trace_ptr(3);
-    const uint32_t stage_bytes = (uint32_t)g.FG * 2048;
-    a.stages = dft_pick_stages(B, stage_bytes);
-    L.smem = dft_smem_bytes(B, stage_bytes, a.stages);
+    const uint32_t stage_bytes = (uint32_t)g.FG * 2048 * (split ? 2 : 1);
+    a.stages = dft_pick_stages(B, stage_bytes, split ? 1 : DFT_NBUF, split ? 2 : 1);
+    L.smem = dft_smem_bytes(B, stage_bytes, a.stages, split ? 1 : DFT_NBUF, split ? 2 : 1);
+    if (split) {
+        if (!map_w(&lo->W, sb + g.winv_lo_off, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return false;
+        if (!make_chunk_map(&lo->IO, Yf_lo, nc, g.p, g.FG, TILE_M / TOK_GROUP, 1, (uint32_t)g.FG)) return false;
+    }
     return true;
 }
 
-template <typename K>
-static cudaError_t launch_stage(K kernel, const StageLaunch<DftArgs>& L, int max_ctas, cudaStream_t st) {
+template <typename K, typename... Extra>
+static cudaError_t launch_stage(K kernel, const StageLaunch<DftArgs>& L, int max_ctas, cudaStream_t st, const Extra&... extra) {
     const int grid = L.a.num_items < max_ctas ? L.a.num_items : max_ctas;
     if (grid < 1) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     if (e != cudaSuccess) return e;
-    return launch_pdl(kernel, (unsigned)grid, DFT_THREADS, L.smem, st, L.tm_in, L.tm_w, L.tm_out, L.a);
+    return launch_pdl(kernel, (unsigned)grid, DFT_THREADS, L.smem, st, L.tm_in, L.tm_w, L.tm_out, extra..., L.a);
 }
 
-cudaError_t launch_dft_fwd_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, int max_ctas, cudaStream_t st) {
+cudaError_t launch_dft_fwd_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, void* Xf_lo, int* status, int max_ctas,
+                              cudaStream_t st) {
     StageLaunch<DftArgs> L;
+    if (g.split && Xf_lo != nullptr) {
+        DftLoMaps lo;
+        if (!prep_dft_fwd(P, g, spec_gemm, n_begin, nc, Xf, status, L, Xf_lo, &lo)) return cudaErrorNotSupported;
+        return g.B == 128 ? launch_stage(dft_fwd_tc_split_kernel<128>, L, max_ctas, st, lo) : launch_stage(dft_fwd_tc_split_kernel<64>, L, max_ctas, st, lo);
+    }
     if (!prep_dft_fwd(P, g, spec_gemm, n_begin, nc, Xf, status, L)) return cudaErrorNotSupported;
     return g.B == 128 ? launch_stage(dft_fwd_tc_kernel<128>, L, max_ctas, st) : launch_stage(dft_fwd_tc_kernel<64>, L, max_ctas, st);
 }
 
-cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, int max_ctas, cudaStream_t st) {
+cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, const void* Yf_lo, int* status,
+                              int max_ctas, cudaStream_t st) {
     StageLaunch<DftArgs> L;
+    if (g.split && Yf_lo != nullptr) {
+        DftLoMaps lo;
+        if (!prep_dft_inv(P, g, spec_gemm, n_begin, nc, Yf, status, L, Yf_lo, &lo)) return cudaErrorNotSupported;
+        return g.B == 128 ? launch_stage(dft_inv_tc_split_kernel<128>, L, max_ctas, st, lo) : launch_stage(dft_inv_tc_split_kernel<64>, L, max_ctas, st, lo);
+    }
     if (!prep_dft_inv(P, g, spec_gemm, n_begin, nc, Yf, status, L)) return cudaErrorNotSupported;
     return g.B == 128 ? launch_stage(dft_inv_tc_kernel<128>, L, max_ctas, st) : launch_stage(dft_inv_tc_kernel<64>, L, max_ctas, st);
 }

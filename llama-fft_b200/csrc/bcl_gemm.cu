@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(WARPS * 32) spectrum_gemm_kernel(const float* 
 // DFT matrices for the tensor-core stages.  grid B, block B: thread (row a, column b).
 //   Wfwd[r][t]  r = 0: 1, r = 1: (-1)^t, r = 2f: cos(2 pi f t / B), r = 2f+1: -sin(2 pi f t / B)              (rfft, :252)
 //   Winv[t][r]  the transpose, times 1/B for r < 2 and 2/B otherwise                                          (irfft n=B, :263)
-__global__ void dft_matrix_kernel(int B, __half* __restrict__ wf16, __nv_bfloat16* __restrict__ wbf16, __nv_bfloat16* __restrict__ winv) {
+__global__ void dft_matrix_kernel(int B, __half* __restrict__ wf16, __nv_bfloat16* __restrict__ wbf16, __nv_bfloat16* __restrict__ winv,
+                                  __half* __restrict__ wf16_lo, __nv_bfloat16* __restrict__ wbf16_lo, __nv_bfloat16* __restrict__ winv_lo) {
     const int a = blockIdx.x, b = threadIdx.x;
     auto entry = [B](int r, int t) -> float {
         if (r == 0) return 1.f;
@@ -147,11 +148,20 @@ __global__ void dft_matrix_kernel(int B, __half* __restrict__ wf16, __nv_bfloat1
         sincospif(2.0f * (float)m / (float)B, &s, &c);
         return (r & 1) ? -s : c;
     };
+    const size_t o = (size_t)a * B + b;
     const float fw = entry(a, b);                                       // Wfwd[a][b]
-    wf16[(size_t)a * B + b] = __float2half_rn(fw);
-    wbf16[(size_t)a * B + b] = __float2bfloat16_rn(fw);
+    const __half h16 = __float2half_rn(fw);
+    const __nv_bfloat16 hbf = __float2bfloat16_rn(fw);
+    wf16[o] = h16;
+    wbf16[o] = hbf;
     const float iv = entry(b, a) * (b < 2 ? 1.0f : 2.0f) / (float)B;    // Winv[a = t][b = r]
-    winv[(size_t)a * B + b] = __float2bfloat16_rn(iv);
+    const __nv_bfloat16 hiv = __float2bfloat16_rn(iv);
+    winv[o] = hiv;
+    if (wf16_lo != nullptr) {                                           // split layout: the rounding residues
+        wf16_lo[o] = __float2half_rn(fw - __half2float(h16));
+        wbf16_lo[o] = __float2bfloat16_rn(fw - __bfloat162float(hbf));
+        winv_lo[o] = __float2bfloat16_rn(iv - __bfloat162float(hiv));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -372,7 +382,10 @@ cudaError_t launch_spectrum_gemm(const float* c, void* spec, int p, int q, int B
     constexpr int WARPS = 8;
     unsigned char* base = reinterpret_cast<unsigned char*>(spec);
     gemm::dft_matrix_kernel<<<B, B, 0, st>>>(B, reinterpret_cast<__half*>(base + g.wf16_off), reinterpret_cast<__nv_bfloat16*>(base + g.wbf16_off),
-                                            reinterpret_cast<__nv_bfloat16*>(base + g.winv_off));
+                                            reinterpret_cast<__nv_bfloat16*>(base + g.winv_off),
+                                            split ? reinterpret_cast<__half*>(base + g.wf16_lo_off) : nullptr,
+                                            split ? reinterpret_cast<__nv_bfloat16*>(base + g.wbf16_lo_off) : nullptr,
+                                            split ? reinterpret_cast<__nv_bfloat16*>(base + g.winv_lo_off) : nullptr);
     cudaError_t e0 = cudaGetLastError();
     if (e0 != cudaSuccess) return e0;
 #define BCL_SG(BB)                                                                                                         \
@@ -437,7 +450,7 @@ cudaError_t launch_prefill_stage1(const ProblemDev& P, int B, const void* spec_g
     const gemm::Geometry g = gemm::geometry(P.p, P.q, B);
     const bool tc_ok = gemm::dft_tc_supported(B, P.x_dtype) && spec_gemm != nullptr;
     if (impl == 2 && !tc_ok) return cudaErrorNotSupported;
-    if (impl != 1 && tc_ok) return gemm::launch_dft_fwd_tc(P, g, spec_gemm, n_begin, nc, Xf, status, sm_count(), st);
+    if (impl != 1 && tc_ok) return gemm::launch_dft_fwd_tc(P, g, spec_gemm, n_begin, nc, Xf, nullptr, status, sm_count(), st);
     return launch_gemm_rfft(P, B, n_begin, nc, Xf, nullptr, st);
 }
 
@@ -445,7 +458,7 @@ cudaError_t launch_prefill_stage3(const ProblemDev& P, int B, const void* spec_g
     const gemm::Geometry g = gemm::geometry(P.p, P.q, B);
     const bool tc_ok = gemm::dft_tc_supported(B, P.x_dtype) && P.y_dtype == P.x_dtype && spec_gemm != nullptr && P.n_extra == 0;   // peer destinations: plain stores
     if (impl == 2 && !tc_ok) return cudaErrorNotSupported;
-    if (impl != 1 && tc_ok) return gemm::launch_dft_inv_tc(P, g, spec_gemm, n_begin, nc, Yf, status, sm_count(), st);
+    if (impl != 1 && tc_ok) return gemm::launch_dft_inv_tc(P, g, spec_gemm, n_begin, nc, Yf, nullptr, status, sm_count(), st);
     return launch_gemm_irfft(P, B, n_begin, nc, Yf, nullptr, st);
 }
 
@@ -466,11 +479,17 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
         cudaError_t e = cudaMemsetAsync(status, 0, kWsHeader, st);
         if (e != cudaSuccess) return e;
         const int ctas = sm_count();
+        static const int impl_s = getenv("BCL_PREFILL_DFT") ? atoi(getenv("BCL_PREFILL_DFT")) : 0;   // 1: force the CUDA-core FFT stages
+        // 16-bit activations, B <= 128: the DFT stages run on the tensor cores too, with (hi, lo) DFT matrices
+        const bool tc1 = impl_s != 1 && gemm::dft_tc_supported(B, P.x_dtype);
+        const bool tc3 = tc1 && P.y_dtype == P.x_dtype && P.n_extra == 0;
         for (int64_t n0 = 0; n0 < P.N; n0 += ncmax) {
             const int nc = (int)((P.N - n0 < ncmax) ? (P.N - n0) : ncmax);
-            if ((e = launch_gemm_rfft(P, B, n0, nc, Xf, Xf_lo, st)) != cudaSuccess) return e;
+            e = tc1 ? gemm::launch_dft_fwd_tc(P, g, spec_gemm, n0, nc, Xf, Xf_lo, status, ctas, st) : launch_gemm_rfft(P, B, n0, nc, Xf, Xf_lo, st);
+            if (e != cudaSuccess) return e;
             if ((e = launch_gemm_mma(Xf, Xf_lo, spec_gemm, Yf, Yf_lo, status, P.p, P.q, B, nc, ctas, st)) != cudaSuccess) return e;
-            if ((e = launch_gemm_irfft(P, B, n0, nc, Yf, Yf_lo, st)) != cudaSuccess) return e;
+            e = tc3 ? gemm::launch_dft_inv_tc(P, g, spec_gemm, n0, nc, Yf, Yf_lo, status, ctas, st) : launch_gemm_irfft(P, B, n0, nc, Yf, Yf_lo, st);
+            if (e != cudaSuccess) return e;
         }
         return cudaSuccess;
     }

@@ -30,8 +30,8 @@ constexpr int NCHUNK = 64;           // columns (= 32 output blocks) of one freq
 struct Geometry {
     int B, p, q, split;
     int F, FG, Kp, KG, Np, NCH;
-    // byte offsets inside the GEMM-layout spectrum buffer; Cmat_lo exists only in the split (fp32-accurate) layout
-    size_t cmat_bytes, cmat_lo_off, wf16_off, wbf16_off, winv_off, total_bytes;
+    // byte offsets inside the GEMM-layout spectrum buffer; the *_lo parts exist only in the split (fp32-accurate) layout
+    size_t cmat_bytes, cmat_lo_off, wf16_off, wbf16_off, winv_off, wf16_lo_off, wbf16_lo_off, winv_lo_off, total_bytes;
 };
 
 __host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -54,7 +54,10 @@ __host__ inline Geometry geometry(int p, int q, int B, int split = 0) {
     g.wf16_off = g.cmat_bytes * (split ? 2 : 1);
     g.wbf16_off = g.wf16_off + (size_t)B * B * 2;
     g.winv_off = g.wbf16_off + (size_t)B * B * 2;
-    g.total_bytes = g.winv_off + (size_t)B * B * 2;
+    g.wf16_lo_off = g.winv_off + (size_t)B * B * 2;                 // rounding residues of the three DFT matrices (split only)
+    g.wbf16_lo_off = g.wf16_lo_off + (size_t)B * B * 2;
+    g.winv_lo_off = g.wbf16_lo_off + (size_t)B * B * 2;
+    g.total_bytes = split ? g.winv_lo_off + (size_t)B * B * 2 : g.wf16_lo_off;
     return g;
 }
 
@@ -88,8 +91,11 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned 
 
 // DFT-as-GEMM stages on tcgen05 (bcl_dft_tc.cu).  B in {64, 128}; 16-bit activations.
 bool dft_tc_supported(int B, int act_dtype);
-cudaError_t launch_dft_fwd_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, int max_ctas, cudaStream_t st);
-cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, int max_ctas, cudaStream_t st);
+// g.split: Xf_lo / Yf_lo are the lo halves of the (hi, lo) intermediates (NULL otherwise)
+cudaError_t launch_dft_fwd_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, void* Xf_lo, int* status, int max_ctas,
+                              cudaStream_t st);
+cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, const void* Yf_lo, int* status,
+                              int max_ctas, cudaStream_t st);
 
 // Single-launch pipeline of the three tensor-core stages over L2-resident intermediates (bcl_prefill_fused.cu).
 // counters: 3 * ceil(N/128) ints, zeroed in stream order before the launch; Xf / Yf sized for all N tokens.

@@ -420,9 +420,13 @@ struct DftArgs {
 // =========================================================================================================
 // forward: x -> Xf
 // =========================================================================================================
-template <int B>
+struct DftLoMaps { CUtensorMap W, IO; };         // split layout: the lo DFT matrix, and Xf_lo (forward, store) / Yf_lo (inverse, load)
+
+// SPLIT (fp32 spectra): the activations are exact in their 16-bit format; W = Whi + Wlo (same format), two MMAs per k-step;
+// the fp32 accumulators leave as (hi, lo) bf16 pairs into Xf and Xf_lo.
+template <int B, bool SPLIT>
 __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmXf,
-                                             const DftArgs& a, const int first, const int stride) {
+                                             const DftLoMaps* lo, const DftArgs& a, const int first, const int stride) {
     constexpr int ATOMS = B / KATOM;                         // 128-byte K atoms per block (K = B time samples)
     constexpr uint32_t A_ATOM = TILE_M * 128;                // 128 tokens x 128 B
     constexpr uint32_t W_ATOM = B * 128;                     // B spectrum rows x 128 B
@@ -431,7 +435,7 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
     uint32_t* sig = reinterpret_cast<uint32_t*>(dft_smem + 512);                // signaller queue (fused launch)
     unsigned char* epi = dft_smem + 1024;                    // 4 warps x 2 x DFT_EPI_BUF
     unsigned char* wsm = dft_smem + 1024 + DFT_EPI_WARPS * DFT_NBUF * DFT_EPI_BUF;
-    unsigned char* ring = wsm + ATOMS * W_ATOM;
+    unsigned char* ring = wsm + (SPLIT ? 2 : 1) * ATOMS * W_ATOM;           // split: [W hi | W lo]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int S = a.stages;
     const int C = a.deps.chunk > 0 ? a.deps.chunk : 1;      // consecutive items per round
@@ -443,7 +447,10 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
         for (int i = 0; i <= SIG_RING; ++i) sig[i] = 0u;
         fence_barrier_init();
     }
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmXf); }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmXf);
+        if constexpr (SPLIT) { tma_prefetch_desc(&lo->W); tma_prefetch_desc(&lo->IO); }
+    }
     if (warp == 1) tmem_alloc(&bars->tmem_base, 4 * B >= 32 ? 4 * B : 32);
     tc_fence_before_sync();
     __syncthreads();
@@ -453,8 +460,10 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(&bars->wfull, ATOMS * W_ATOM);                 // the DFT matrix: resident for the whole kernel
+            mbar_arrive_expect_tx(&bars->wfull, (SPLIT ? 2 : 1) * ATOMS * W_ATOM);   // the DFT matrix: resident for the whole kernel
             for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + at * W_ATOM, &tmW, at * KATOM, 0, &bars->wfull);
+            if constexpr (SPLIT)
+                for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + (ATOMS + at) * W_ATOM, &lo->W, at * KATOM, 0, &bars->wfull);
             pdl_wait();                                                          // x may come from the previous kernel
             int stage = 0; uint32_t ph = 0; int m_ready = -1, pit = 0;
             for (int blk = first * C; blk < a.num_items; blk += stride * C) for (int item = blk; item < min(blk + C, a.num_items); ++item, ++pit) {
@@ -498,8 +507,12 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
                     for (int at = 0; at < ATOMS; ++at) {
                         const uint64_t adesc = umma_desc_k_sw128(sa + at * A_ATOM), bdesc = umma_desc_k_sw128(sw + at * W_ATOM);
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
+                        for (int kk = 0; kk < 4; ++kk) {
                             umma_bf16_ss(tmem_base + (uint32_t)(ib * B), adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (at | kk) != 0 ? 1u : 0u);
+                            if constexpr (SPLIT)
+                                umma_bf16_ss(tmem_base + (uint32_t)(ib * B), adesc + (uint64_t)(2 * kk),
+                                             umma_desc_k_sw128(sw + (ATOMS + at) * W_ATOM) + (uint64_t)(2 * kk), idesc, 1u);
+                        }
                     }
                     umma_commit(&bars->empty[stage]);
                     if (++stage == S) { stage = 0; ph ^= 1u; }
@@ -537,22 +550,45 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
                     if (lane == 0) mbar_arrive(&bars->tmem_empty[0]);
                     if (warp == 2 && lane == 0) BCL_TRACE(6, it);
                 }
-                if (lane == 0) tma_store_wait_read<DFT_NBUF - 1>();
-                __syncwarp();
-                uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)buf * DFT_EPI_BUF) + lane;
+                if constexpr (!SPLIT) {
+                    if (lane == 0) tma_store_wait_read<DFT_NBUF - 1>();
+                    __syncwarp();
+                    uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)buf * DFT_EPI_BUF) + lane;
 #pragma unroll
-                for (int fl = 0; fl < 8; ++fl)                                   // chunk (f = 8 fc + fl, kg, token) = {Re,Im} x 4 blocks
-                    dst[fl * 32] = make_uint4(pack_bf(__uint_as_float(r[0][2 * fl]), __uint_as_float(r[0][2 * fl + 1])),
-                                              pack_bf(__uint_as_float(r[1][2 * fl]), __uint_as_float(r[1][2 * fl + 1])),
-                                              pack_bf(__uint_as_float(r[2][2 * fl]), __uint_as_float(r[2][2 * fl + 1])),
-                                              pack_bf(__uint_as_float(r[3][2 * fl]), __uint_as_float(r[3][2 * fl + 1])));
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_4d_hint(&tmXf, 0, m * (TILE_M / TOK_GROUP) + quarter, kg, fc * 8, stg + (size_t)buf * DFT_EPI_BUF, L2_EVICT_LAST);
-                    tma_store_commit();
+                    for (int fl = 0; fl < 8; ++fl)                               // chunk (f = 8 fc + fl, kg, token) = {Re,Im} x 4 blocks
+                        dst[fl * 32] = make_uint4(pack_bf(__uint_as_float(r[0][2 * fl]), __uint_as_float(r[0][2 * fl + 1])),
+                                                  pack_bf(__uint_as_float(r[1][2 * fl]), __uint_as_float(r[1][2 * fl + 1])),
+                                                  pack_bf(__uint_as_float(r[2][2 * fl]), __uint_as_float(r[2][2 * fl + 1])),
+                                                  pack_bf(__uint_as_float(r[3][2 * fl]), __uint_as_float(r[3][2 * fl + 1])));
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d_hint(&tmXf, 0, m * (TILE_M / TOK_GROUP) + quarter, kg, fc * 8, stg + (size_t)buf * DFT_EPI_BUF, L2_EVICT_LAST);
+                        tma_store_commit();
+                    }
+                    if (++buf == DFT_NBUF) buf = 0;
+                } else {
+                    static_assert(DFT_NBUF >= 2, "split epilogue: one staging buffer for hi, one for lo");
+                    if (lane == 0) tma_store_wait_read<0>();                     // both buffers (hi, lo) free again
+                    __syncwarp();
+                    uint4* dh = reinterpret_cast<uint4*>(stg) + lane;
+                    uint4* dl = reinterpret_cast<uint4*>(stg + DFT_EPI_BUF) + lane;
+#pragma unroll
+                    for (int fl = 0; fl < 8; ++fl) {
+                        uint32_t hi[4], lw[4];
+#pragma unroll
+                        for (int ib = 0; ib < 4; ++ib) split_bf(__uint_as_float(r[ib][2 * fl]), __uint_as_float(r[ib][2 * fl + 1]), hi[ib], lw[ib]);
+                        dh[fl * 32] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        dl[fl * 32] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d_hint(&tmXf, 0, m * (TILE_M / TOK_GROUP) + quarter, kg, fc * 8, stg, L2_EVICT_LAST);
+                        tma_store_4d_hint(&lo->IO, 0, m * (TILE_M / TOK_GROUP) + quarter, kg, fc * 8, stg + DFT_EPI_BUF, L2_EVICT_LAST);
+                        tma_store_commit();
+                    }
                 }
-                if (++buf == DFT_NBUF) buf = 0;
             }
             if (warp == 2 && lane == 0) BCL_TRACE(7, it);
             if (a.deps.done_ctr != nullptr && lane == 0) done_trk.item_committed(sig, m, FC / 2);
@@ -595,19 +631,23 @@ __device__ __forceinline__ void store_row(unsigned char* row, int lane, const ui
 // =========================================================================================================
 // inverse: Yf -> y
 // =========================================================================================================
-template <int B>
+// SPLIT (fp32 spectra): Yf = Yhi + Ylo, Winv = Whi + Wlo (bf16 pairs); three MMAs per k-step (Yhi Whi + Yhi Wlo + Ylo Whi).
+// One staging buffer per epilogue warp instead of two, so that two 64 KB (hi, lo) stages fit next to the two DFT matrices.
+template <int B, bool SPLIT>
 __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUtensorMap& tmYf, const CUtensorMap& tmW, const CUtensorMap& tmOut,
-                                             const DftArgs& a, const int first, const int stride) {
+                                             const DftLoMaps* lo, const DftArgs& a, const int first, const int stride) {
     constexpr int ATOMS = B / KATOM;
     constexpr int FG = B / 8;
     constexpr uint32_t W_ATOM = B * 128;                     // B time rows x 128 B
-    constexpr uint32_t STAGE = FG * 2048;                    // [fg][128 tokens][16 B]
+    constexpr uint32_t STAGE_HALF = FG * 2048;               // [fg][128 tokens][16 B]
+    constexpr uint32_t STAGE = (SPLIT ? 2 : 1) * STAGE_HALF; // split: [Yf hi | Yf lo]
+    constexpr int NBUF = SPLIT ? 1 : DFT_NBUF;               // staging buffers per epilogue warp
     constexpr int NACC = 512 / B > 4 ? 4 : 512 / B;
     DftBarriers* bars = reinterpret_cast<DftBarriers*>(dft_smem);
     uint32_t* sig = reinterpret_cast<uint32_t*>(dft_smem + 512);                // signaller queue (fused launch)
     unsigned char* epi = dft_smem + 1024;
-    unsigned char* wsm = dft_smem + 1024 + DFT_EPI_WARPS * DFT_NBUF * DFT_EPI_BUF;
-    unsigned char* ring = wsm + ATOMS * W_ATOM;
+    unsigned char* wsm = dft_smem + 1024 + DFT_EPI_WARPS * NBUF * DFT_EPI_BUF;
+    unsigned char* ring = wsm + (SPLIT ? 2 : 1) * ATOMS * W_ATOM;           // split: [W hi | W lo]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int S = a.stages;
     const int C = a.deps.chunk > 0 ? a.deps.chunk : 1;      // consecutive items per round
@@ -619,7 +659,10 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
         for (int i = 0; i <= SIG_RING; ++i) sig[i] = 0u;
         fence_barrier_init();
     }
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmYf); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmOut); }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmYf); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmOut);
+        if constexpr (SPLIT) { tma_prefetch_desc(&lo->W); tma_prefetch_desc(&lo->IO); }
+    }
     if (warp == 1) tmem_alloc(&bars->tmem_base, NACC * B);
     tc_fence_before_sync();
     __syncthreads();
@@ -629,8 +672,10 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(&bars->wfull, ATOMS * W_ATOM);
+            mbar_arrive_expect_tx(&bars->wfull, (SPLIT ? 2 : 1) * ATOMS * W_ATOM);
             for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + at * W_ATOM, &tmW, at * KATOM, 0, &bars->wfull);
+            if constexpr (SPLIT)
+                for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + (ATOMS + at) * W_ATOM, &lo->W, at * KATOM, 0, &bars->wfull);
             pdl_wait();                                                          // Yf comes from the previous kernel
             int stage = 0; uint32_t ph = 0; int m_ready = -1, pit = 0;
             for (int blk = first * C; blk < a.num_items; blk += stride * C) for (int item = blk; item < min(blk + C, a.num_items); ++item, ++pit) {
@@ -643,6 +688,8 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
                 if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 21); goto done; }
                 mbar_arrive_expect_tx(&bars->full[stage], STAGE);
                 tma_load_4d_hint(ring + (size_t)stage * STAGE, &tmYf, 0, m * (TILE_M / TOK_GROUP), j, 0, &bars->full[stage], L2_EVICT_FIRST);
+                if constexpr (SPLIT)
+                    tma_load_4d_hint(ring + (size_t)stage * STAGE + STAGE_HALF, &lo->IO, 0, m * (TILE_M / TOK_GROUP), j, 0, &bars->full[stage], L2_EVICT_FIRST);
                 if (++stage == S) { stage = 0; ph ^= 1u; }
             }
         }
@@ -660,9 +707,15 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
                 BCL_TRACE(3, it);
                 const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE), sw = smem_u32(wsm);
 #pragma unroll
-                for (int kk = 0; kk < B / 16; ++kk)                              // K = B packed spectrum reals; one k-step = 2 fg slabs
-                    umma_bf16_ss(tmem_base + (uint32_t)(acc * B), umma_desc_k_nosw(sa + (uint32_t)kk * 4096u, 128u, 2048u),
-                                 umma_desc_k_sw128(sw + (kk / 4) * W_ATOM) + (uint64_t)(2 * (kk % 4)), idesc, kk != 0 ? 1u : 0u);
+                for (int kk = 0; kk < B / 16; ++kk) {                            // K = B packed spectrum reals; one k-step = 2 fg slabs
+                    const uint64_t adesc = umma_desc_k_nosw(sa + (uint32_t)kk * 4096u, 128u, 2048u);
+                    const uint64_t bdesc = umma_desc_k_sw128(sw + (kk / 4) * W_ATOM) + (uint64_t)(2 * (kk % 4));
+                    umma_bf16_ss(tmem_base + (uint32_t)(acc * B), adesc, bdesc, idesc, kk != 0 ? 1u : 0u);
+                    if constexpr (SPLIT) {
+                        umma_bf16_ss(tmem_base + (uint32_t)(acc * B), adesc, umma_desc_k_sw128(sw + (ATOMS + kk / 4) * W_ATOM) + (uint64_t)(2 * (kk % 4)), idesc, 1u);
+                        umma_bf16_ss(tmem_base + (uint32_t)(acc * B), umma_desc_k_nosw(sa + STAGE_HALF + (uint32_t)kk * 4096u, 128u, 2048u), bdesc, idesc, 1u);
+                    }
+                }
                 umma_commit(&bars->empty[stage]);
                 umma_commit(&bars->tmem_full[acc]);
                 BCL_TRACE(4, it);
@@ -673,7 +726,7 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
         if (lane == 0 && a.deps.done_ctr != nullptr) signaller_loop(sig, a.deps.done_ctr, DFT_EPI_WARPS);
     } else {
         const int quarter = warp & 3;
-        unsigned char* stg = epi + (size_t)(warp - 2) * DFT_NBUF * DFT_EPI_BUF;
+        unsigned char* stg = epi + (size_t)(warp - 2) * NBUF * DFT_EPI_BUF;
         pdl_wait();                                                              // y may still be read by the previous kernel
         int it = 0, buf = 0;
         DoneTracker done_trk;
@@ -703,7 +756,7 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
                     if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
                     if (warp == 2 && lane == 0) BCL_TRACE(6, it);
                 }
-                if (lane == 0) tma_store_wait_read<DFT_NBUF - 1>();
+                if (lane == 0) tma_store_wait_read<NBUF - 1>();
                 __syncwarp();
                 unsigned char* row = stg + (size_t)buf * DFT_EPI_BUF + (size_t)lane * 128;
                 const int col0 = j * B + h * 64;
@@ -721,7 +774,7 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
                     tma_store_2d(&tmOut, col0, (int)(a.n_begin + (int64_t)m * TILE_M + quarter * 32), stg + (size_t)buf * DFT_EPI_BUF);
                     tma_store_commit();
                 }
-                if (++buf == DFT_NBUF) buf = 0;
+                if (++buf == NBUF) buf = 0;
             }
             if (warp == 2 && lane == 0) BCL_TRACE(7, it);
             if (a.deps.done_ctr != nullptr && lane == 0) done_trk.item_committed(sig, m, max(h1 - h0, 0));
@@ -747,9 +800,11 @@ template <typename Args> struct StageLaunch {
     size_t smem;
 };
 long long* trace_ptr(int stage);
-bool prep_dft_fwd(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, StageLaunch<DftArgs>& L);
+bool prep_dft_fwd(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, StageLaunch<DftArgs>& L,
+                  void* Xf_lo = nullptr, DftLoMaps* lo = nullptr);
 bool prep_gemm(const void* Xf, const void* Cmat, void* Yf, int* status, const Geometry& g, int nc, StageLaunch<GemmArgs>& L, GemmLoMaps* lo = nullptr);
-bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L);
+bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L,
+                  const void* Yf_lo = nullptr, DftLoMaps* lo = nullptr);
 
 }  // namespace gemm
 }  // namespace bcl

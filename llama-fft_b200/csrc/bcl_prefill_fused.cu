@@ -27,9 +27,9 @@ prefill_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                      const __grid_constant__ DftArgs a1, const __grid_constant__ GemmArgs a2, const __grid_constant__ DftArgs a3, const int n1, const int n2) {
     extern __shared__ __align__(1024) unsigned char fused_smem[];
     const int b = (int)blockIdx.x;
-    if (b < n1) dft_fwd_body<B>(fused_smem, tmX, tmWf, tmXfS, a1, b, n1);
+    if (b < n1) dft_fwd_body<B, false>(fused_smem, tmX, tmWf, tmXfS, nullptr, a1, b, n1);
     else if (b < n1 + n2) freq_gemm_body<false>(fused_smem, tmXfL, tmC, tmYfS, nullptr, a2, b - n1, n2);
-    else dft_inv_body<B>(fused_smem, tmYfL, tmWi, tmOut, a3, b - n1 - n2, (int)gridDim.x - n1 - n2);
+    else dft_inv_body<B, false>(fused_smem, tmYfL, tmWi, tmOut, nullptr, a3, b - n1 - n2, (int)gridDim.x - n1 - n2);
 }
 
 static_assert(DFT_THREADS == GEMM_THREADS, "the three stage bodies share one block shape");

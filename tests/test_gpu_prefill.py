@@ -324,9 +324,9 @@ def test_prefill_chunking_small_workspace_and_full_size_properties():
 def test_gemm_layout_rejects_bad_spectrum_dtype_and_tiny_workspace():
     L = _cabi.lib()
     assert L.bcl_spectrum_bytes(4, 4, 128, _cabi.F16, _cabi.LAYOUT_GEMM) == 0
-    # fp32 = the split layout: Cmat twice (hi, lo), the DFT matrices once
+    # fp32 = the split layout: Cmat and the three DFT matrices twice (hi, lo)
     assert (L.bcl_spectrum_bytes(4, 4, 128, _cabi.F32, _cabi.LAYOUT_GEMM) - L.bcl_spectrum_bytes(4, 4, 128, _cabi.BF16, _cabi.LAYOUT_GEMM)
-            == 64 * 64 * 16 * 2)
+            == 64 * 64 * 16 * 2 + 3 * 128 * 128 * 2)
     x = torch.zeros(256, 512, device=DEV)
     spec = torch.zeros(L.bcl_spectrum_bytes(4, 4, 128, _cabi.BF16, _cabi.LAYOUT_GEMM), device=DEV, dtype=torch.uint8)
     y = torch.zeros(256, 512, device=DEV)
@@ -501,3 +501,24 @@ def test_split_prefill_chunked_workspace_full_size():
     assert_close(y[rows], O.bc_forward_torch(c, x[rows].cpu()), 1e-4)
     with torch.no_grad():
         assert torch.equal(m(x), y)                                                        # unchunked == chunked, deterministic
+
+
+@pytest.mark.parametrize("inf,outf,B", SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_split_prefill_16bit_activations_tensor_core_dft_stages(inf, outf, B, dtype):
+    """fp32 spectra + 16-bit activations (the reference's default Llama configuration, commands.txt:22): for B <= 128 all three
+    stages run on the tensor cores with (hi, lo) operands; the result must stay in the fp32-spectrum class (1e-4 + I/O rounding)
+    and agree with the CUDA-core FFT stages (BCL_PREFILL_DFT=1 equivalent: fp32 activations)."""
+    N = 300
+    g = torch.Generator().manual_seed(inf + outf + B + 3)
+    c = torch.randn(outf // B, inf // B, B, generator=g) * 0.01
+    x = torch.randn(N, inf, generator=g).to(dtype)
+    m = make_layer_f32(c)
+    with torch.no_grad():
+        y = m(x.to(DEV))
+        y32 = m(x.float().to(DEV))                                # fp32 activations: CUDA-core fp32 FFT stages + split GEMM
+    assert prefill_status(DEV) == 0
+    assert y.dtype == dtype
+    y_ref = O.bc_forward_torch(c, x.float())
+    assert_close(y32, y_ref, 1e-4)
+    assert_close(y, y_ref, 1e-4, dtype)

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--block", type=int, default=128)
     ap.add_argument("--shapes", default="4096x4096,4096x11008,11008x4096")
     ap.add_argument("--stage-tokens", type=int, default=2048)
+    ap.add_argument("--spectrum", default="bfloat16", choices=["bfloat16", "float32"], help="float32: the split-bf16 (fp32-accurate) GEMM chain")
     ap.add_argument("--skip-torch", action="store_true")
     ap.add_argument("--skip-stream", action="store_true")
     args = ap.parse_args()
@@ -52,22 +53,32 @@ def main():
         inf, outf = (int(v) for v in shp.split("x"))
         p, q = outf // B, inf // B
         torch.manual_seed(0)
-        layer = bc.BlockCirculantLinear(inf, outf, block_size=B, bias=False, spectrum_dtype=torch.bfloat16).to(DEV).eval()
+        sdt = torch.bfloat16 if args.spectrum == "bfloat16" else torch.float32
+        layer = bc.BlockCirculantLinear(inf, outf, block_size=B, bias=False, spectrum_dtype=sdt).to(DEV).eval()
         nbuf = 2
         xs = [torch.randn(N, inf, device=DEV).half() for _ in range(nbuf)]
         ys = [torch.empty(N, outf, device=DEV, dtype=torch.float16) for _ in range(nbuf)]
-        alg = N * inf * 2 + p * q * B * 2 + N * outf * 2
+        alg = N * inf * 2 + p * q * B * (2 if sdt == torch.bfloat16 else 4) + N * outf * 2
         row = {"shape": shp, "B": B, "tokens": N, "algorithmic_MB": alg / 1e6, "t_hbm_us": alg / peak / 1e3}
         spec_g = layer.build_spectrum(layout=_cabi.LAYOUT_GEMM)
         spec_s = layer.build_spectrum()
 
         def gemm_path(i):
-            bc_forward(xs[i % nbuf], spec_g, None, p, q, B, out=ys[i % nbuf], layout=_cabi.LAYOUT_GEMM)
+            bc_forward(xs[i % nbuf], spec_g, None, p, q, B, out=ys[i % nbuf], layout=_cabi.LAYOUT_GEMM, spectrum_dtype=sdt)
         row["gemm_path_us"] = timeit(gemm_path, args.reps)
         row["gemm_path_status"] = prefill_status(DEV)
         row["gemm_path_hbm_frac"] = row["t_hbm_us"] / row["gemm_path_us"]
         row["gemm_path_Mtok_s"] = N / row["gemm_path_us"]
 
+        row["spectrum"] = args.spectrum
+        if sdt != torch.bfloat16:
+            if not args.skip_stream:
+                row["stream_kernel_f32spec_us"] = timeit(lambda i: bc_forward(xs[i % nbuf], spec_s, None, p, q, B, out=ys[i % nbuf]), 3, warm=1)
+            print(json.dumps(row), flush=True)
+            out.append(row)
+            del xs, ys, layer
+            torch.cuda.empty_cache()
+            continue
         # stages alone on one 2048-token chunk (what the chunk loop runs)
         nc = min(N, args.stage_tokens)
         F, Kp, Np = _cabi.prefill_geometry(p, q, B)
