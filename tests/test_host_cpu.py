@@ -274,3 +274,40 @@ def test_shared_input_groups_attach_without_changing_the_module_tree():
         with torch.no_grad():
             attn.q_proj(torch.randn(3, 128))
     assert bc.unfuse_shared_inputs(model) == 4 and attn.q_proj._shared_group is None
+
+
+def test_bench_all_in_one_metric_helpers_cpu():
+    """Metric definitions of the unified bench (reference src/bench_all_in_one.py:112-120, :297-346) on a stand-in model."""
+    from llama_fft_b200 import bench_all_in_one as bai
+    torch.manual_seed(0)
+    s, t = torch.randn(3, 50), torch.randn(3, 50)
+    want = torch.nn.functional.kl_div(torch.log_softmax(s / 2, -1), torch.softmax(t / 2, -1), reduction="none").sum(-1)
+    assert torch.allclose(bai.softmax_kl(s, t, temperature=2.0), want, atol=1e-6)
+    toks = bai.byte_tokenize(["ab", "", "x" * 500], max_len=8, vocab_size=320)
+    assert [int(i.numel()) for i, _ in toks] == [2, 1, 8] and toks[0][0].tolist() == [3 + 97, 3 + 98]
+    batches = list(bai.iter_batches(toks, 2, pad_id=0))
+    assert batches[0][0].shape == (2, 2) and batches[0][2].tolist() == [1, 0] and batches[1][0].shape == (1, 8)
+
+    class Fake(torch.nn.Module):
+        def __init__(self, shift):
+            super().__init__()
+            self.emb = torch.nn.Embedding(320, 16)
+            self.head = torch.nn.Linear(16, 40)
+            self.shift = shift
+
+        def forward(self, input_ids, attention_mask=None):
+            class Out:
+                pass
+            o = Out()
+            o.logits = self.head(self.emb(input_ids)) + self.shift
+            return o
+    torch.manual_seed(1)
+    teacher = Fake(0.0)
+    cache = bai.compute_teacher_last_cache(teacher, toks, torch.device("cpu"))
+    same = bai.correctness_last_token(teacher, toks, cache, torch.device("cpu"), 1.0, 5)
+    assert same["last_mse"] == 0.0 and abs(same["last_kl"]) < 1e-6 and same["last_top1_acc"] == 1.0 and same["last_topk_overlap"] == 1.0
+    teacher.shift = 0.5                                  # a constant logit shift: MSE 0.25, distribution unchanged
+    moved = bai.correctness_last_token(teacher, toks, cache, torch.device("cpu"), 1.0, 5)
+    assert abs(moved["last_mse"] - 0.25) < 1e-5 and abs(moved["last_kl"]) < 1e-5 and moved["last_top1_acc"] == 1.0
+    perf = bai.perf_prefill(teacher, toks, torch.device("cpu"), 0, 2, 1, 2)
+    assert perf["prefill_tokens_per_s"] > 0 and set(perf) >= {"prefill_avg_ms", "prefill_tokens_per_s", "peak_mem_bytes"}
