@@ -15,7 +15,7 @@ from .patch_llama_fft import (  # noqa: F401
     BlockCirculantLinear, patch_mlp_with_block_circulant, patch_llama_fft,
     save_bc_params, load_bc_params,
     dense_block_to_circulant_column, dense_block_to_circulant_column_loss_aware, circulant_from_first_col,
-    enable_cfft_cache, disable_cfft_cache,
+    enable_cfft_cache, disable_cfft_cache, _detect_best_convention_for_layer, _get_submodule_by_name,
 )
 from .fft_utils import circulant_matvec_fft  # noqa: F401
 from .grouped import GroupedBCForward, HostPipe  # noqa: F401

@@ -53,6 +53,22 @@ def dense_block_to_circulant_column(W_block: torch.Tensor, *, convention: str = 
     return _wrapped_diagonals(src, +1).mean(-1)
 
 
+def _detect_best_convention_for_layer(W: torch.Tensor, block_size: int, *, num_probes: int = 3) -> str:
+    """Legacy sanity check (reference :17-44; its call sites are commented out there, :210/:218): which of the two legacy
+    projections of the top-left BxB block reproduces the dense matvec better on `num_probes` random vectors (seed 0, :30).
+    Returns "diag" or "diag_inv".  Construction-time host logic on W's device; the circulant product is formed explicitly."""
+    B = block_size
+    block = W[:B, :B].detach().to(dtype=torch.float32)
+    torch.manual_seed(0)
+    xs = torch.stack([torch.randn(B, device=block.device, dtype=torch.float32) for _ in range(num_probes)], dim=1)   # (B, probes)
+    y_dense = block @ xs
+
+    def score(convention: str) -> float:
+        C = circulant_from_first_col(dense_block_to_circulant_column(block, convention=convention).to(torch.float32))
+        return (y_dense - C @ xs).pow(2).mean(dim=0).sum().item() / float(num_probes)
+    return "diag" if score("diag") <= score("diag_inv") else "diag_inv"
+
+
 def dense_block_to_circulant_column_loss_aware(W_block: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
     """First column c of the circulant C[i,j] = c[(i-j)%B] closest to W in Frobenius norm, times the
     energy-matching scalar alpha = <W,C>/<C,C> (reference :82-128).  Accepts (..., B, B); arithmetic stays in

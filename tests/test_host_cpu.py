@@ -311,3 +311,35 @@ def test_bench_all_in_one_metric_helpers_cpu():
     assert abs(moved["last_mse"] - 0.25) < 1e-5 and abs(moved["last_kl"]) < 1e-5 and moved["last_top1_acc"] == 1.0
     perf = bai.perf_prefill(teacher, toks, torch.device("cpu"), 0, 2, 1, 2)
     assert perf["prefill_tokens_per_s"] > 0 and set(perf) >= {"prefill_avg_ms", "prefill_tokens_per_s", "peak_mem_bytes"}
+
+
+def test_legacy_convention_detector():
+    """reference src/patch_llama_fft.py:17-44.  "diag_inv" (c[k] = mean_i W[(i+k)%B, i]) is exact for every circulant block, a
+    transposed one included, so the detector must pick it there; on random blocks it must agree with a slow restatement."""
+    torch.manual_seed(3)
+    B = 32
+    c = torch.randn(B)
+    C = bc.circulant_from_first_col(c)
+    W = torch.randn(2 * B, 3 * B)
+    for blk in (C, C.t()):
+        W[:B, :B] = blk
+        assert bc._detect_best_convention_for_layer(W, B) == "diag_inv"
+    assert torch.allclose(bc.dense_block_to_circulant_column(C, convention="diag_inv"), c, atol=1e-6)
+    assert torch.allclose(bc.dense_block_to_circulant_column(C, convention="diag"), c[(-torch.arange(B)) % B], atol=1e-6)
+
+    def slow(Wb):
+        torch.manual_seed(0)
+        xs = [torch.randn(B) for _ in range(3)]
+        errs = {}
+        for conv in ("diag", "diag_inv"):
+            col = torch.stack([torch.stack([Wb[i, (i + k) % B] if conv == "diag" else Wb[(i + k) % B, i] for i in range(B)]).mean() for k in range(B)])
+            Cm = torch.stack([torch.stack([col[(i - j) % B] for j in range(B)]) for i in range(B)])
+            errs[conv] = sum(((Wb @ x) - (Cm @ x)).pow(2).mean().item() for x in xs) / 3.0
+        return "diag" if errs["diag"] <= errs["diag_inv"] else "diag_inv"
+    seen = set()
+    for seed in range(6):
+        Wr = torch.randn(B, B, generator=torch.Generator().manual_seed(seed))
+        got = bc._detect_best_convention_for_layer(Wr, B)
+        assert got == slow(Wr)
+        seen.add(got)
+    assert seen <= {"diag", "diag_inv"}
