@@ -75,10 +75,15 @@ static bool map_w(CUtensorMap* m, const void* w, int B, CUtensorMapDataType dt) 
 
 // debug only: BCL_TRACE_PTR=<device address of 512 int64> BCL_TRACE_STAGE=<1|2|3>
 long long* trace_ptr(int stage) {
+#ifdef BCL_ENABLE_TRACE
     const char* tp = getenv("BCL_TRACE_PTR");
     const char* ts = getenv("BCL_TRACE_STAGE");
     if (!tp || (ts ? atoi(ts) : 1) != stage) return nullptr;
     return reinterpret_cast<long long*>(strtoull(tp, nullptr, 0));
+#else
+    (void)stage;
+    return nullptr;
+#endif
 }
 
 bool prep_dft_fwd(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, StageLaunch<DftArgs>& L,

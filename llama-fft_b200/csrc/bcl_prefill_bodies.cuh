@@ -167,8 +167,13 @@ constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr uint32_t EPI_BUF_BYTES = 8 * 32 * 16;              // [8 j][32 tokens][16 B]
 constexpr int SET_COLS = 4 * NCHUNK;                         // TMEM columns of one accumulator set (4 frequencies)
 
-// debug only (BCL_TRACE_PTR): per-item clock64 stamps of one CTA, 8 slots per item, first 64 items
+// Debug builds only (make TRACE=1 -> -DBCL_ENABLE_TRACE; tools/trace_stages.py, tools/trace_fused.py): per-item clock64 stamps of
+// the first CTA of a stage, 8 slots per item, first 64 items, into the buffer named by BCL_TRACE_PTR.  Compiled out otherwise.
+#ifdef BCL_ENABLE_TRACE
 #define BCL_TRACE(slot, itv) do { if (a.trace != nullptr && first == 0 && (itv) < 64) a.trace[(itv) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define BCL_TRACE(slot, itv) do { (void)(itv); } while (0)
+#endif
 
 struct GemmArgs {
     int* status;

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
 """Debug: per-item clock64 stamps of the first CTA of each role inside the fused prefill launch (BCL_TRACE_PTR / BCL_TRACE_STAGE).
+   Needs a tracing build of the library: make -C llama-fft_b200/csrc clean && make -C llama-fft_b200/csrc TRACE=1
    python tools/trace_fused.py [tokens] [first_item_to_print]"""
 import os, sys
 import torch

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
 """Debug: per-item clock64 stamps of CTA 0 of each tcgen05 prefill stage (BCL_TRACE_PTR / BCL_TRACE_STAGE), as cycle offsets.
+   Needs a tracing build of the library: make -C llama-fft_b200/csrc clean && make -C llama-fft_b200/csrc TRACE=1
    python tools/trace_stages.py [tokens]"""
 import os, sys
 import torch
