@@ -8,8 +8,10 @@ and both gradients run on the same hand-written CUDA kernels (include/bclinear.h
     dc    = sum over tokens of the circular cross-correlation of gy and x       (bcl_backward_weights)
     dbias = gy.sum(0)
 
-In grad mode the spectrum is rebuilt on every call (reference rule, src/bench_all_in_one.py:212-219) and always fp32,
-whatever ``spectrum_dtype`` the layer serves inference with.  No CPU path: CPU tensors raise.
+In grad mode the spectrum is rebuilt on every call (reference rule, src/bench_all_in_one.py:212-219) and always in the fp32
+accuracy class, whatever ``spectrum_dtype`` the layer serves inference with: the CUDA-core stream kernel for a few tokens, the
+split-bf16 tensor-core chain (GEMM layout, spec_dtype f32) from ``PREFILL_MIN_TOKENS_F32`` tokens -- calibration batches are
+hundreds to thousands of tokens.  No CPU path: CPU tensors raise.
 """
 from __future__ import annotations
 
@@ -28,6 +30,20 @@ def _spectrum_f32(c32: torch.Tensor) -> torch.Tensor:
     return spec
 
 
+def _forward_f32(x_flat: torch.Tensor, c32: torch.Tensor, bias) -> torch.Tensor:
+    """One fp32-class BC forward with a freshly built spectrum of c32 (p, q, B)."""
+    from .patch_llama_fft import bc_forward, PREFILL_MIN_TOKENS_F32
+    p, q, B = c32.shape
+    if x_flat.shape[0] >= PREFILL_MIN_TOKENS_F32:
+        L = _cabi.lib()
+        spec = torch.empty(L.bcl_spectrum_bytes(p, q, B, _cabi.F32, _cabi.LAYOUT_GEMM), device=c32.device, dtype=torch.uint8)
+        with torch.cuda.device(c32.device):
+            rc = L.bcl_precompute_spectrum(c32.data_ptr(), p, q, B, spec.data_ptr(), _cabi.F32, _cabi.LAYOUT_GEMM, _cabi.stream_ptr(c32.device))
+        _cabi.check(rc, "bcl_precompute_spectrum")
+        return bc_forward(x_flat, spec, bias, p, q, B, layout=_cabi.LAYOUT_GEMM, spectrum_dtype=torch.float32)
+    return bc_forward(x_flat, _spectrum_f32(c32), bias, p, q, B)
+
+
 def _aligned(t: torch.Tensor) -> torch.Tensor:
     if t.stride(-1) != 1 or (t.stride(0) * t.element_size()) % 16 or t.data_ptr() % 16:
         return t.contiguous()
@@ -37,18 +53,15 @@ def _aligned(t: torch.Tensor) -> torch.Tensor:
 class _BCLinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_flat, c, bias):
-        from .patch_llama_fft import bc_forward
         _cabi.require_cuda(c, "BlockCirculantLinear.c")
-        p, q, B = c.shape
         c32 = c.detach().to(torch.float32).contiguous()
-        y = bc_forward(x_flat.detach(), _spectrum_f32(c32), None if bias is None else bias.detach(), p, q, B)
+        y = _forward_f32(x_flat.detach(), c32, None if bias is None else bias.detach())
         ctx.save_for_backward(x_flat.detach(), c32)
         ctx.meta = (c.dtype, None if bias is None else bias.dtype, x_flat.dtype)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        from .patch_llama_fft import bc_forward
         x_flat, c32 = ctx.saved_tensors
         c_dtype, bias_dtype, x_dtype = ctx.meta
         p, q, B = c32.shape
@@ -62,7 +75,7 @@ class _BCLinearFn(torch.autograd.Function):
             ct = torch.empty(q, p, B, device=dev, dtype=torch.float32)
             with torch.cuda.device(dev):
                 _cabi.check(L.bcl_conj_transpose(c32.data_ptr(), p, q, B, ct.data_ptr(), _cabi.stream_ptr(dev)), "bcl_conj_transpose")
-            gx = bc_forward(g_act, _spectrum_f32(ct), None, q, p, B)         # (N, in) in x.dtype
+            gx = _forward_f32(g_act, ct, None)                               # (N, in) in x.dtype
         if ctx.needs_input_grad[1]:
             xa = _aligned(x_flat)
             dc = torch.empty(p, q, B, device=dev, dtype=torch.float32)

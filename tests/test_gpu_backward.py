@@ -17,7 +17,8 @@ def rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 
 
-@pytest.mark.parametrize("p,q,B,N", [(2, 3, 64, 5), (3, 2, 128, 7), (2, 2, 256, 3), (5, 7, 64, 33), (32, 32, 128, 16)])
+@pytest.mark.parametrize("p,q,B,N", [(2, 3, 64, 5), (3, 2, 128, 7), (2, 2, 256, 3), (5, 7, 64, 33), (32, 32, 128, 16),
+                                     (5, 7, 64, 300), (8, 6, 128, 517), (3, 4, 256, 260)])      # >= 256 tokens: split tensor-core chain
 @pytest.mark.parametrize("with_bias", [False, True])
 def test_gradients_match_autograd_of_reference_forward_fp32(p, q, B, N, with_bias):
     g = torch.Generator().manual_seed(p * 7 + q + B + N)
