@@ -54,11 +54,13 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_split_kernel(const 
 // =========================================================================================================
 // host side
 // =========================================================================================================
-bool dft_tc_supported(int B, int act_dtype) { return (B == 64 || B == 128) && (act_dtype == BCL_F16 || act_dtype == BCL_BF16); }
+bool dft_tc_supported(int B, int act_dtype) { return (B == 64 || B == 128 || B == 256) && (act_dtype == BCL_F16 || act_dtype == BCL_BF16); }
+static int dft_nb(int B) { return B == 256 ? 128 : B; }         // accumulator columns per block and launch (DftShape<B>::NB)
+static int dft_parts(int B) { return B == 256 ? 2 : 1; }         // K parts = smem stages per block (DftShape<B>::PARTS)
 
 // nbuf: staging buffers per epilogue warp; wmats: resident DFT matrices (1, or 2 = hi + lo)
 static size_t dft_smem_bytes(int B, uint32_t stage_bytes, int stages, int nbuf = DFT_NBUF, int wmats = 1) {
-    return 1024 + DFT_EPI_WARPS * nbuf * DFT_EPI_BUF + (size_t)wmats * (B / KATOM) * B * 128 + (size_t)stages * stage_bytes;
+    return 1024 + DFT_EPI_WARPS * nbuf * DFT_EPI_BUF + (size_t)wmats * (B / KATOM) * dft_nb(B) * 128 + (size_t)stages * stage_bytes;
 }
 static int dft_pick_stages(int B, uint32_t stage_bytes, int nbuf = DFT_NBUF, int wmats = 1) {
     int s = DFT_MAX_STAGES;
@@ -66,10 +68,10 @@ static int dft_pick_stages(int B, uint32_t stage_bytes, int nbuf = DFT_NBUF, int
     return s;
 }
 
-static bool map_w(CUtensorMap* m, const void* w, int B, CUtensorMapDataType dt) {                  // [B rows][B k], box 64 x B, 128-byte swizzle
+static bool map_w(CUtensorMap* m, const void* w, int B, CUtensorMapDataType dt) {                  // [B rows][B k], box 64 x NB rows, 128-byte swizzle
     const uint64_t dims[2] = {(uint64_t)B, (uint64_t)B};
     const uint64_t strides[1] = {(uint64_t)B * 2};
-    const uint32_t box[2] = {KATOM, (uint32_t)B};
+    const uint32_t box[2] = {KATOM, (uint32_t)dft_nb(B)};
     return make_tensor_map(m, dt, 2, w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -106,7 +108,7 @@ bool prep_dft_fwd(const ProblemDev& P, const Geometry& g, const void* spec_gemm,
     a.status = status; a.bias = nullptr; a.n_begin = n_begin; a.nc = nc;
     a.m_tiles = (nc + TILE_M - 1) / TILE_M; a.groups = g.KG; a.num_items = a.m_tiles * g.KG; a.act_bf16 = bf ? 1 : 0;
     a.trace = trace_ptr(1);
-    const uint32_t stage_bytes = (uint32_t)(B / KATOM) * TILE_M * 128;
+    const uint32_t stage_bytes = (uint32_t)(B / KATOM / dft_parts(B)) * TILE_M * 128;
     a.stages = dft_pick_stages(B, stage_bytes, DFT_NBUF, split ? 2 : 1);
     L.smem = dft_smem_bytes(B, stage_bytes, a.stages, DFT_NBUF, split ? 2 : 1);
     if (split) {
@@ -122,7 +124,7 @@ bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm,
     const int B = g.B;
     const bool bf = P.x_dtype == BCL_BF16;
     const CUtensorMapDataType adt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    if (!make_chunk_map(&L.tm_in, Yf, nc, g.p, g.FG, TILE_M / TOK_GROUP, 1, (uint32_t)g.FG)) return false;
+    if (!make_chunk_map(&L.tm_in, Yf, nc, g.p, g.FG, TILE_M / TOK_GROUP, 1, (uint32_t)(g.FG / dft_parts(B)))) return false;
     const unsigned char* sb = reinterpret_cast<const unsigned char*>(spec_gemm);
     if (!map_w(&L.tm_w, sb + g.winv_off, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return false;
     {
@@ -136,7 +138,7 @@ bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm,
     a.status = status; a.bias = P.bias; a.n_begin = n_begin; a.nc = nc;
     a.m_tiles = (nc + TILE_M - 1) / TILE_M; a.groups = g.p; a.num_items = a.m_tiles * g.p; a.act_bf16 = bf ? 1 : 0;
     a.trace = trace_ptr(3);
-    const uint32_t stage_bytes = (uint32_t)g.FG * 2048 * (split ? 2 : 1);
+    const uint32_t stage_bytes = (uint32_t)(g.FG / dft_parts(B)) * 2048 * (split ? 2 : 1);
     a.stages = dft_pick_stages(B, stage_bytes, split ? 1 : DFT_NBUF, split ? 2 : 1);
     L.smem = dft_smem_bytes(B, stage_bytes, a.stages, split ? 1 : DFT_NBUF, split ? 2 : 1);
     if (split) {
@@ -164,6 +166,14 @@ cudaError_t launch_dft_fwd_tc(const ProblemDev& P, const Geometry& g, const void
         return g.B == 128 ? launch_stage(dft_fwd_tc_split_kernel<128>, L, max_ctas, st, lo) : launch_stage(dft_fwd_tc_split_kernel<64>, L, max_ctas, st, lo);
     }
     if (!prep_dft_fwd(P, g, spec_gemm, n_begin, nc, Xf, status, L)) return cudaErrorNotSupported;
+    if (g.B == 256) {                                               // two launches: spectrum rows [0,128) and [128,256) (DftShape)
+        for (int half = 0; half < 2; ++half) {
+            L.a.half = half;
+            cudaError_t e = launch_stage(dft_fwd_tc_kernel<256>, L, max_ctas, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     return g.B == 128 ? launch_stage(dft_fwd_tc_kernel<128>, L, max_ctas, st) : launch_stage(dft_fwd_tc_kernel<64>, L, max_ctas, st);
 }
 
@@ -176,6 +186,14 @@ cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void
         return g.B == 128 ? launch_stage(dft_inv_tc_split_kernel<128>, L, max_ctas, st, lo) : launch_stage(dft_inv_tc_split_kernel<64>, L, max_ctas, st, lo);
     }
     if (!prep_dft_inv(P, g, spec_gemm, n_begin, nc, Yf, status, L)) return cudaErrorNotSupported;
+    if (g.B == 256) {                                               // two launches: output samples [0,128) and [128,256) of every block
+        for (int half = 0; half < 2; ++half) {
+            L.a.half = half;
+            cudaError_t e = launch_stage(dft_inv_tc_kernel<256>, L, max_ctas, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     return g.B == 128 ? launch_stage(dft_inv_tc_kernel<128>, L, max_ctas, st) : launch_stage(dft_inv_tc_kernel<64>, L, max_ctas, st);
 }
 

@@ -481,7 +481,7 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
         const int ctas = sm_count();
         static const int impl_s = getenv("BCL_PREFILL_DFT") ? atoi(getenv("BCL_PREFILL_DFT")) : 0;   // 1: force the CUDA-core FFT stages
         // 16-bit activations, B <= 128: the DFT stages run on the tensor cores too, with (hi, lo) DFT matrices
-        const bool tc1 = impl_s != 1 && gemm::dft_tc_supported(B, P.x_dtype);
+        const bool tc1 = impl_s != 1 && B <= 128 && gemm::dft_tc_supported(B, P.x_dtype);   // B = 256: the (hi, lo) DFT matrices do not fit
         const bool tc3 = tc1 && P.y_dtype == P.x_dtype && P.n_extra == 0;
         for (int64_t n0 = 0; n0 < P.N; n0 += ncmax) {
             const int nc = (int)((P.N - n0 < ncmax) ? (P.N - n0) : ncmax);
@@ -500,7 +500,7 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
     static const int fused_min_tiles = getenv("BCL_FUSED_MIN_TILES") ? atoi(getenv("BCL_FUSED_MIN_TILES")) : 0;    // <= 0: never
     const int ctas = sm_count();
     const bool tc_ok = impl != 1 && spec_gemm != nullptr && gemm::dft_tc_supported(B, P.x_dtype) && P.y_dtype == P.x_dtype && P.n_extra == 0;
-    if (tc_ok && ncmax >= P.N && fused_min_tiles > 0 && (P.N + gemm::TILE_M - 1) / gemm::TILE_M >= fused_min_tiles && ctas >= 12) {
+    if (tc_ok && B <= 128 && ncmax >= P.N && fused_min_tiles > 0 && (P.N + gemm::TILE_M - 1) / gemm::TILE_M >= fused_min_tiles && ctas >= 12) {
         // one launch: the three stages pipelined tile by tile over L2-resident Xf / Yf (bcl_prefill_fused.cu)
         cudaError_t e = cudaMemsetAsync(ws, 0, kWsHeader + ctr_bytes, st);
         if (e != cudaSuccess) return e;

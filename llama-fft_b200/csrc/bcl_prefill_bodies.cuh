@@ -416,8 +416,20 @@ struct DftArgs {
     int64_t n_begin;         // first token of the chunk (row coordinate into x / y)
     int nc, m_tiles, groups; // groups: KG (forward) or p (inverse)
     int num_items, stages, act_bf16;
+    int half;                // B = 256 only: which 128 spectrum rows (forward) / output samples (inverse) this launch computes
     StageDeps deps;
     long long* trace;
+};
+
+// B = 256 on the tensor cores: a 256 x 256 DFT matrix (128 KB) plus four 256-column accumulators do not fit, so a launch computes
+// HALF of the N dimension (128 spectrum rows / output samples, `DftArgs::half`) with the full K = 256 fed in two 128-wide parts
+// (one smem stage each), and the stage is launched twice.  The activations are read twice; the CUDA-core FFT stages this
+// replaces are instruction-bound at 3-5x the HBM time (profiles/r1_prefill_notes.md).
+template <int B> struct DftShape {
+    static constexpr int NB = B == 256 ? 128 : B;            // accumulator columns per block = MMA N
+    static constexpr int KATOMS = B / KATOM;                  // 128-byte K atoms over the whole K = B
+    static constexpr int PARTS = B == 256 ? 2 : 1;            // K parts = smem stages per block
+    static constexpr int APP = KATOMS / PARTS;                // atoms per part
 };
 
 
@@ -432,10 +444,13 @@ struct DftLoMaps { CUtensorMap W, IO; };         // split layout: the lo DFT mat
 template <int B, bool SPLIT>
 __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmXf,
                                              const DftLoMaps* lo, const DftArgs& a, const int first, const int stride) {
-    constexpr int ATOMS = B / KATOM;                         // 128-byte K atoms per block (K = B time samples)
+    using SH = DftShape<B>;
+    constexpr int NB = SH::NB, PARTS = SH::PARTS, APP = SH::APP;
+    constexpr int ATOMS = SH::KATOMS;                        // 128-byte K atoms per block (K = B time samples)
     constexpr uint32_t A_ATOM = TILE_M * 128;                // 128 tokens x 128 B
-    constexpr uint32_t W_ATOM = B * 128;                     // B spectrum rows x 128 B
-    constexpr uint32_t STAGE = ATOMS * A_ATOM;               // one input block of the tile
+    constexpr uint32_t W_ATOM = NB * 128;                    // NB spectrum rows x 128 B
+    constexpr uint32_t STAGE = APP * A_ATOM;                 // one K part of one input block of the tile
+    static_assert(!(SPLIT && B == 256), "B = 256 split: CUDA-core FFT stages");
     DftBarriers* bars = reinterpret_cast<DftBarriers*>(dft_smem);
     uint32_t* sig = reinterpret_cast<uint32_t*>(dft_smem + 512);                // signaller queue (fused launch)
     unsigned char* epi = dft_smem + 1024;                    // 4 warps x 2 x DFT_EPI_BUF
@@ -456,7 +471,7 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
         tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmXf);
         if constexpr (SPLIT) { tma_prefetch_desc(&lo->W); tma_prefetch_desc(&lo->IO); }
     }
-    if (warp == 1) tmem_alloc(&bars->tmem_base, 4 * B >= 32 ? 4 * B : 32);
+    if (warp == 1) tmem_alloc(&bars->tmem_base, 4 * NB);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -466,7 +481,7 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
     if (warp == 0) {
         if (lane == 0) {
             mbar_arrive_expect_tx(&bars->wfull, (SPLIT ? 2 : 1) * ATOMS * W_ATOM);   // the DFT matrix: resident for the whole kernel
-            for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + at * W_ATOM, &tmW, at * KATOM, 0, &bars->wfull);
+            for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + at * W_ATOM, &tmW, at * KATOM, a.half * NB, &bars->wfull);
             if constexpr (SPLIT)
                 for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + (ATOMS + at) * W_ATOM, &lo->W, at * KATOM, 0, &bars->wfull);
             pdl_wait();                                                          // x may come from the previous kernel
@@ -478,12 +493,14 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
                     m_ready = m;
                 }
                 BCL_TRACE(0, pit);
-                for (int ib = 0; ib < 4; ++ib) {
+                for (int ibp = 0; ibp < 4 * PARTS; ++ibp) {                      // (input block, K part)
+                    const int ib = ibp / PARTS, part = ibp % PARTS;
                     if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 11); goto done; }
                     unsigned char* sa = ring + (size_t)stage * STAGE;
                     mbar_arrive_expect_tx(&bars->full[stage], STAGE);
-                    for (int at = 0; at < ATOMS; ++at)                           // columns past in_features are zero-filled
-                        tma_load_2d_hint(sa + at * A_ATOM, &tmX, (4 * kg + ib) * B + at * KATOM, (int)(a.n_begin + (int64_t)m * TILE_M), &bars->full[stage], L2_EVICT_FIRST);
+                    for (int at = 0; at < APP; ++at)                             // columns past in_features are zero-filled
+                        tma_load_2d_hint(sa + at * A_ATOM, &tmX, (4 * kg + ib) * B + (part * APP + at) * KATOM, (int)(a.n_begin + (int64_t)m * TILE_M),
+                                         &bars->full[stage], L2_EVICT_FIRST);
                     if (++stage == S) { stage = 0; ph ^= 1u; }
                 }
                 BCL_TRACE(1, pit);
@@ -496,26 +513,27 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
             // smem stages held for both passes) starve the MMAs of prefetch depth; two block-pair sets with the first pair parked
             // in registers make the epilogue slower than the overlap gains.  The epilogue itself sits at the TMEM read rate
             // (64 B/clk/SM: 256 KB of fp32 accumulators per item = 4.1k cycles).
-            const uint32_t idesc = umma_idesc_16(TILE_M, B, a.act_bf16);
+            const uint32_t idesc = umma_idesc_16(TILE_M, NB, a.act_bf16);
             if (!mbar_wait(&bars->wfull, 0)) { atomicExch(a.status, 12); goto done; }
             int stage = 0; uint32_t ph = 0; int it = 0;
             for (int blk = first * C; blk < a.num_items; blk += stride * C) for (int item = blk; item < min(blk + C, a.num_items); ++item, ++it) {
                 if (!mbar_wait(&bars->tmem_empty[0], ((uint32_t)it & 1u) ^ 1u)) { atomicExch(a.status, 13); goto done; }
                 tc_fence_after_sync();
                 BCL_TRACE(2, it);
-                for (int ib = 0; ib < 4; ++ib) {
+                for (int ibp = 0; ibp < 4 * PARTS; ++ibp) {                      // (input block, K part)
+                    const int ib = ibp / PARTS, part = ibp % PARTS;
                     if (!mbar_wait(&bars->full[stage], ph)) { atomicExch(a.status, 14); goto done; }
                     tc_fence_after_sync();
-                    if (ib == 0) BCL_TRACE(3, it);
+                    if (ibp == 0) BCL_TRACE(3, it);
                     const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE), sw = smem_u32(wsm);
 #pragma unroll
-                    for (int at = 0; at < ATOMS; ++at) {
-                        const uint64_t adesc = umma_desc_k_sw128(sa + at * A_ATOM), bdesc = umma_desc_k_sw128(sw + at * W_ATOM);
+                    for (int at = 0; at < APP; ++at) {
+                        const uint64_t adesc = umma_desc_k_sw128(sa + at * A_ATOM), bdesc = umma_desc_k_sw128(sw + (part * APP + at) * W_ATOM);
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            umma_bf16_ss(tmem_base + (uint32_t)(ib * B), adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (at | kk) != 0 ? 1u : 0u);
+                            umma_bf16_ss(tmem_base + (uint32_t)(ib * NB), adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (part | at | kk) != 0 ? 1u : 0u);
                             if constexpr (SPLIT)
-                                umma_bf16_ss(tmem_base + (uint32_t)(ib * B), adesc + (uint64_t)(2 * kk),
+                                umma_bf16_ss(tmem_base + (uint32_t)(ib * NB), adesc + (uint64_t)(2 * kk),
                                              umma_desc_k_sw128(sw + (ATOMS + at) * W_ATOM) + (uint64_t)(2 * kk), idesc, 1u);
                         }
                     }
@@ -542,12 +560,12 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
             tc_fence_after_sync();
             if (warp == 2 && lane == 0) BCL_TRACE(5, it);
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-            constexpr int FC = B / 16;                                           // chunks of 8 frequencies (16 accumulator columns)
+            constexpr int FC = NB / 16;                                          // chunks of 8 frequencies (16 accumulator columns)
             const int fc0 = ((warp - 2) >> 2) * (FC / 2), fc1 = fc0 + FC / 2;     // this warp's half of them
             for (int fc = fc0; fc < fc1; ++fc) {
                 uint32_t r[4][16];
 #pragma unroll
-                for (int ib = 0; ib < 4; ++ib) tmem_ld_32x32b_x16(taddr + (uint32_t)(ib * B + fc * 16), r[ib]);
+                for (int ib = 0; ib < 4; ++ib) tmem_ld_32x32b_x16(taddr + (uint32_t)(ib * NB + fc * 16), r[ib]);
                 tmem_ld_wait();
                 if (fc == fc1 - 1) {
                     tc_fence_before_sync();
@@ -568,7 +586,7 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_4d_hint(&tmXf, 0, m * (TILE_M / TOK_GROUP) + quarter, kg, fc * 8, stg + (size_t)buf * DFT_EPI_BUF, L2_EVICT_LAST);
+                        tma_store_4d_hint(&tmXf, 0, m * (TILE_M / TOK_GROUP) + quarter, kg, (a.half * FC + fc) * 8, stg + (size_t)buf * DFT_EPI_BUF, L2_EVICT_LAST);
                         tma_store_commit();
                     }
                     if (++buf == DFT_NBUF) buf = 0;
@@ -589,8 +607,8 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_4d_hint(&tmXf, 0, m * (TILE_M / TOK_GROUP) + quarter, kg, fc * 8, stg, L2_EVICT_LAST);
-                        tma_store_4d_hint(&lo->IO, 0, m * (TILE_M / TOK_GROUP) + quarter, kg, fc * 8, stg + DFT_EPI_BUF, L2_EVICT_LAST);
+                        tma_store_4d_hint(&tmXf, 0, m * (TILE_M / TOK_GROUP) + quarter, kg, (a.half * FC + fc) * 8, stg, L2_EVICT_LAST);
+                        tma_store_4d_hint(&lo->IO, 0, m * (TILE_M / TOK_GROUP) + quarter, kg, (a.half * FC + fc) * 8, stg + DFT_EPI_BUF, L2_EVICT_LAST);
                         tma_store_commit();
                     }
                 }
@@ -606,7 +624,7 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
 done:
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 4 * B >= 32 ? 4 * B : 32);
+    if (warp == 1) tmem_dealloc(tmem_base, 4 * NB);
 }
 
 // One token's 64 outputs (fp32 accumulators, 1/B already folded into Winv) -> 8 swizzled 16-byte chunks of the store tile.
@@ -641,13 +659,18 @@ __device__ __forceinline__ void store_row(unsigned char* row, int lane, const ui
 template <int B, bool SPLIT>
 __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUtensorMap& tmYf, const CUtensorMap& tmW, const CUtensorMap& tmOut,
                                              const DftLoMaps* lo, const DftArgs& a, const int first, const int stride) {
-    constexpr int ATOMS = B / KATOM;
-    constexpr int FG = B / 8;
-    constexpr uint32_t W_ATOM = B * 128;                     // B time rows x 128 B
+    using SH = DftShape<B>;
+    constexpr int NB = SH::NB, PARTS = SH::PARTS;
+    constexpr int ATOMS = SH::KATOMS;                        // K atoms of the DFT matrix (K = B packed spectrum reals)
+    constexpr int OUT_ATOMS = NB / KATOM;                    // 64-column pieces of one block's output (of this launch's half)
+    constexpr int FG = B / 8 / PARTS;                        // 16-byte frequency slabs per K part = per smem stage
+    constexpr int KSTEPS = B / 16 / PARTS;                   // k-steps (16 reals) per part
+    constexpr uint32_t W_ATOM = NB * 128;                    // NB time rows x 128 B
     constexpr uint32_t STAGE_HALF = FG * 2048;               // [fg][128 tokens][16 B]
     constexpr uint32_t STAGE = (SPLIT ? 2 : 1) * STAGE_HALF; // split: [Yf hi | Yf lo]
     constexpr int NBUF = SPLIT ? 1 : DFT_NBUF;               // staging buffers per epilogue warp
-    constexpr int NACC = 512 / B > 4 ? 4 : 512 / B;
+    constexpr int NACC = 512 / NB > 4 ? 4 : 512 / NB;
+    static_assert(!(SPLIT && B == 256), "B = 256 split: CUDA-core FFT stages");
     DftBarriers* bars = reinterpret_cast<DftBarriers*>(dft_smem);
     uint32_t* sig = reinterpret_cast<uint32_t*>(dft_smem + 512);                // signaller queue (fused launch)
     unsigned char* epi = dft_smem + 1024;
@@ -668,7 +691,7 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
         tma_prefetch_desc(&tmYf); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmOut);
         if constexpr (SPLIT) { tma_prefetch_desc(&lo->W); tma_prefetch_desc(&lo->IO); }
     }
-    if (warp == 1) tmem_alloc(&bars->tmem_base, NACC * B);
+    if (warp == 1) tmem_alloc(&bars->tmem_base, NACC * NB);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -678,7 +701,7 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
     if (warp == 0) {
         if (lane == 0) {
             mbar_arrive_expect_tx(&bars->wfull, (SPLIT ? 2 : 1) * ATOMS * W_ATOM);
-            for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + at * W_ATOM, &tmW, at * KATOM, 0, &bars->wfull);
+            for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + at * W_ATOM, &tmW, at * KATOM, a.half * NB, &bars->wfull);
             if constexpr (SPLIT)
                 for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + (ATOMS + at) * W_ATOM, &lo->W, at * KATOM, 0, &bars->wfull);
             pdl_wait();                                                          // Yf comes from the previous kernel
@@ -690,41 +713,46 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
                     m_ready = m;
                 }
                 BCL_TRACE(0, pit);
-                if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 21); goto done; }
-                mbar_arrive_expect_tx(&bars->full[stage], STAGE);
-                tma_load_4d_hint(ring + (size_t)stage * STAGE, &tmYf, 0, m * (TILE_M / TOK_GROUP), j, 0, &bars->full[stage], L2_EVICT_FIRST);
-                if constexpr (SPLIT)
-                    tma_load_4d_hint(ring + (size_t)stage * STAGE + STAGE_HALF, &lo->IO, 0, m * (TILE_M / TOK_GROUP), j, 0, &bars->full[stage], L2_EVICT_FIRST);
-                if (++stage == S) { stage = 0; ph ^= 1u; }
+                for (int part = 0; part < PARTS; ++part) {
+                    if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 21); goto done; }
+                    mbar_arrive_expect_tx(&bars->full[stage], STAGE);
+                    tma_load_4d_hint(ring + (size_t)stage * STAGE, &tmYf, 0, m * (TILE_M / TOK_GROUP), j, part * FG, &bars->full[stage], L2_EVICT_FIRST);
+                    if constexpr (SPLIT)
+                        tma_load_4d_hint(ring + (size_t)stage * STAGE + STAGE_HALF, &lo->IO, 0, m * (TILE_M / TOK_GROUP), j, 0, &bars->full[stage], L2_EVICT_FIRST);
+                    if (++stage == S) { stage = 0; ph ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(TILE_M, B);
+            const uint32_t idesc = umma_idesc_bf16(TILE_M, NB);
             if (!mbar_wait(&bars->wfull, 0)) { atomicExch(a.status, 22); goto done; }
             int stage = 0; uint32_t ph = 0; int it = 0;
             for (int blk = first * C; blk < a.num_items; blk += stride * C) for (int item = blk; item < min(blk + C, a.num_items); ++item, ++it) {
                 const int acc = it % NACC; const uint32_t acc_ph = (uint32_t)(it / NACC) & 1u;
                 if (!mbar_wait(&bars->tmem_empty[acc], acc_ph ^ 1u)) { atomicExch(a.status, 23); goto done; }
                 BCL_TRACE(2, it);
-                if (!mbar_wait(&bars->full[stage], ph)) { atomicExch(a.status, 24); goto done; }
-                tc_fence_after_sync();
-                BCL_TRACE(3, it);
-                const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE), sw = smem_u32(wsm);
+                for (int part = 0; part < PARTS; ++part) {
+                    if (!mbar_wait(&bars->full[stage], ph)) { atomicExch(a.status, 24); goto done; }
+                    tc_fence_after_sync();
+                    if (part == 0) BCL_TRACE(3, it);
+                    const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE), sw = smem_u32(wsm);
 #pragma unroll
-                for (int kk = 0; kk < B / 16; ++kk) {                            // K = B packed spectrum reals; one k-step = 2 fg slabs
-                    const uint64_t adesc = umma_desc_k_nosw(sa + (uint32_t)kk * 4096u, 128u, 2048u);
-                    const uint64_t bdesc = umma_desc_k_sw128(sw + (kk / 4) * W_ATOM) + (uint64_t)(2 * (kk % 4));
-                    umma_bf16_ss(tmem_base + (uint32_t)(acc * B), adesc, bdesc, idesc, kk != 0 ? 1u : 0u);
-                    if constexpr (SPLIT) {
-                        umma_bf16_ss(tmem_base + (uint32_t)(acc * B), adesc, umma_desc_k_sw128(sw + (ATOMS + kk / 4) * W_ATOM) + (uint64_t)(2 * (kk % 4)), idesc, 1u);
-                        umma_bf16_ss(tmem_base + (uint32_t)(acc * B), umma_desc_k_nosw(sa + STAGE_HALF + (uint32_t)kk * 4096u, 128u, 2048u), bdesc, idesc, 1u);
+                    for (int kk = 0; kk < KSTEPS; ++kk) {                        // K = B packed spectrum reals; one k-step = 2 fg slabs
+                        const int kg = part * KSTEPS + kk;                       // k-step within the whole K
+                        const uint64_t adesc = umma_desc_k_nosw(sa + (uint32_t)kk * 4096u, 128u, 2048u);
+                        const uint64_t bdesc = umma_desc_k_sw128(sw + (kg / 4) * W_ATOM) + (uint64_t)(2 * (kg % 4));
+                        umma_bf16_ss(tmem_base + (uint32_t)(acc * NB), adesc, bdesc, idesc, (part | kk) != 0 ? 1u : 0u);
+                        if constexpr (SPLIT) {
+                            umma_bf16_ss(tmem_base + (uint32_t)(acc * NB), adesc, umma_desc_k_sw128(sw + (ATOMS + kg / 4) * W_ATOM) + (uint64_t)(2 * (kg % 4)), idesc, 1u);
+                            umma_bf16_ss(tmem_base + (uint32_t)(acc * NB), umma_desc_k_nosw(sa + STAGE_HALF + (uint32_t)kk * 4096u, 128u, 2048u), bdesc, idesc, 1u);
+                        }
                     }
+                    umma_commit(&bars->empty[stage]);
+                    if (++stage == S) { stage = 0; ph ^= 1u; }
                 }
-                umma_commit(&bars->empty[stage]);
                 umma_commit(&bars->tmem_full[acc]);
                 BCL_TRACE(4, it);
-                if (++stage == S) { stage = 0; ph ^= 1u; }
             }
         }
     } else if (warp == SIG_WARP) {
@@ -743,9 +771,9 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
             if (!__all_sync(0xffffffffu, mbar_wait(&bars->tmem_full[acc], acc_ph))) { atomicExch(a.status, 25); goto done; }
             tc_fence_after_sync();
             if (warp == 2 && lane == 0) BCL_TRACE(5, it);
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * B);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * NB);
             const int wh = (warp - 2) >> 2;                                      // second warp of the lane quarter?
-            const int h0 = (ATOMS == 2) ? wh : 0, h1 = (ATOMS == 2) ? wh + 1 : (wh == 0 ? 1 : 0);
+            const int h0 = (OUT_ATOMS == 2) ? wh : 0, h1 = (OUT_ATOMS == 2) ? wh + 1 : (wh == 0 ? 1 : 0);
             if (h0 >= h1) {                                                      // B = 64: one half only, the partner warp just releases
                 tc_fence_before_sync();
                 if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
@@ -764,7 +792,7 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
                 if (lane == 0) tma_store_wait_read<NBUF - 1>();
                 __syncwarp();
                 unsigned char* row = stg + (size_t)buf * DFT_EPI_BUF + (size_t)lane * 128;
-                const int col0 = j * B + h * 64;
+                const int col0 = j * B + a.half * NB + h * 64;
                 // 16-byte chunks of this token's row, 128-byte swizzle; the dtype / bias variants are separate straight-line code
                 if (a.bias == nullptr) {
                     if (a.act_bf16) store_row<true, false>(row, lane, r, nullptr, 0);
@@ -792,7 +820,7 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
 done:
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, NACC * B);
+    if (warp == 1) tmem_dealloc(tmem_base, NACC * NB);
 }
 
 

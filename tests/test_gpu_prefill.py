@@ -144,10 +144,11 @@ def test_gemm_layout_spectrum_matches_rfft(p, q, B):
 
 @pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("q,B,N,dtype", [(5, 64, 7, torch.float32), (32, 128, 200, torch.float16), (86, 128, 33, torch.bfloat16),
-                                         (9, 256, 130, torch.float32), (5, 64, 300, torch.float16), (32, 128, 1024, torch.bfloat16)])
+                                         (9, 256, 130, torch.float32), (5, 64, 300, torch.float16), (32, 128, 1024, torch.bfloat16),
+                                         (9, 256, 333, torch.float16), (32, 256, 200, torch.bfloat16)])
 def test_stage_rfft(q, B, N, dtype, impl):
-    if impl == 2 and (B == 256 or dtype == torch.float32):
-        pytest.skip("tensor-core DFT covers B <= 128 with 16-bit activations")
+    if impl == 2 and dtype == torch.float32:
+        pytest.skip("tensor-core DFT covers 16-bit activations")
     g = torch.Generator().manual_seed(q + B + N)
     x = torch.randn(N, q * B, generator=g).to(dtype)
     p = 3
@@ -174,7 +175,7 @@ def test_stage_rfft_tc_rejects_unsupported():
     x = torch.zeros(8, 512, device=DEV)
     Xf = torch.zeros(128, 4, 8, 8, device=DEV, dtype=BF)
     rc = _cabi.lib().bcl_prefill_rfft(x.data_ptr(), _cabi.F32, 8, 512, 2, 2, 256, None, 2, Xf.data_ptr(), new_status().data_ptr(), _cabi.stream_ptr(DEV))
-    assert rc == -8
+    assert rc == -8                                                # fp32 activations: no tensor-core DFT (NULL spectrum buffer too)
 
 
 @pytest.mark.parametrize("p,q,B,N", [(32, 32, 128, 128), (32, 32, 128, 300), (86, 32, 128, 256), (32, 86, 128, 129), (3, 5, 64, 40),
@@ -204,10 +205,11 @@ def test_stage_tcgen05_gemm(p, q, B, N):
 @pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("p,B,N,dtype,bias_dt", [(5, 64, 7, torch.float32, None), (32, 128, 200, torch.float16, torch.float16),
                                                  (86, 128, 33, torch.bfloat16, None), (9, 256, 130, torch.float16, torch.float32),
-                                                 (5, 64, 300, torch.bfloat16, torch.bfloat16), (32, 128, 1024, torch.float16, None)])
+                                                 (5, 64, 300, torch.bfloat16, torch.bfloat16), (32, 128, 1024, torch.float16, None),
+                                                 (9, 256, 333, torch.float16, torch.float16), (32, 256, 200, torch.bfloat16, None)])
 def test_stage_irfft(p, B, N, dtype, bias_dt, impl):
-    if impl == 2 and (B == 256 or dtype == torch.float32 or (bias_dt is not None and bias_dt != dtype)):
-        pytest.skip("tensor-core inverse DFT covers B <= 128, 16-bit activations, output dtype == activation dtype")
+    if impl == 2 and (dtype == torch.float32 or (bias_dt is not None and bias_dt != dtype)):
+        pytest.skip("tensor-core inverse DFT covers 16-bit activations with output dtype == activation dtype")
     g = torch.Generator().manual_seed(p + B + N)
     q = 2
     m = make_layer(torch.randn(p, q, B, generator=g))

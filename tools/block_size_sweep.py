@@ -83,7 +83,7 @@ def main():
             flops = 4 * N * p * q * (B - 1)
             print(json.dumps({"regime": "prefill", "dim": dim, "B": B, "tokens": N, "spectrum": "bfloat16", "us": round(us, 1),
                               "Mtok_s": round(N / us, 2), "algorithmic_MB": round(alg / 1e6, 1), "hbm_frac": round(alg / us / 1e3 / peak, 3),
-                              "algorithmic_TFLOPs": round(flops / us / 1e6, 1), "dft_stages": "tcgen05" if B <= 128 else "cuda-core fft",
+                              "algorithmic_TFLOPs": round(flops / us / 1e6, 1), "dft_stages": "tcgen05" if B <= 128 else "tcgen05, two half-N launches per stage",
                               "status": prefill_status(DEV)}), flush=True)
             del layer, spec, xs, ys
             torch.cuda.empty_cache()
