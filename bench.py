@@ -381,7 +381,66 @@ def launch_granularity_detail(bc, _cabi, grp_all, shapes, dev, args):
         per_module()
     e1.record(stream); torch.cuda.synchronize()
     out["per_module_eager_ms_per_step"] = e0.elapsed_time(e1) / 5
+    try:
+        out["dependent_chain"] = dependent_chain_detail(bc, _cabi, dev, time_graph)
+    except Exception as e:                                               # noqa: BLE001
+        out["dependent_chain"] = {"error": "%s: %s" % (type(e).__name__, e)}
     return out
+
+
+def dependent_chain_detail(bc, _cabi, dev, time_graph):
+    """What a real decoder can do: inside a layer the projections depend on each other (q/k/v -> o -> gate/up -> down), so a token
+    costs 4 DEPENDENT launches per layer with shared-input fusion (q/k/v and gate/up stacked), 7 without.  CUDA-graph replay of
+    32 layers with distinct weights (no L2 reuse), each launch reading the previous launch's output; next to it the dense fp16
+    nn.Linear chain of the same shapes on the same GPU (cuBLAS; weight-bandwidth bound at batch 1)."""
+    import torch
+    torch.manual_seed(0)
+    sdt = torch.float32
+
+    def mk(inf, outf):
+        return bc.BlockCirculantLinear(inf, outf, block_size=B, bias=False, spectrum_dtype=sdt).to(dev).eval()
+    layers = []
+    for _ in range(N_LAYERS):
+        qkv, o, gu, down = mk(4096, 3 * 4096), mk(4096, 4096), mk(4096, 2 * 11008), mk(11008, 4096)
+        for m in (qkv, o, gu, down):
+            m.build_spectrum()
+        layers.append((qkv, o, gu, down))
+    x0 = torch.randn(1, 4096, device=dev).half()
+
+    def bc_chain():
+        h = x0
+        with torch.no_grad():
+            for qkv, o, gu, down in layers:
+                a = qkv(h)[:, :4096]                      # stand-in for attention: any slice keeps the dependency
+                h = o(a.contiguous())
+                g = gu(h)
+                h = down(g[:, :11008].contiguous())
+        return h
+    bc_ms = time_graph(bc_chain, reps=10)
+    res = {"what": "32 layers x 4 dependent launches (fused q/k/v, o, fused gate/up, down), 1 token, fp32 spectra, CUDA-graph replay; the two "
+                   "slice copies per layer stand in for attention / the MLP activation",
+           "bc_ms_per_token": bc_ms, "bc_us_per_layer": bc_ms * 1e3 / N_LAYERS}
+    del layers
+    torch.cuda.empty_cache()
+    dense = []
+    for _ in range(N_LAYERS):
+        dense.append(tuple(torch.nn.Linear(i, o_, bias=False, device=dev, dtype=torch.float16) for i, o_ in
+                           ((4096, 3 * 4096), (4096, 4096), (4096, 2 * 11008), (11008, 4096))))
+
+    def dense_chain():
+        h = x0
+        with torch.no_grad():
+            for qkv, o, gu, down in dense:
+                a = qkv(h)[:, :4096]
+                h = o(a.contiguous())
+                g = gu(h)
+                h = down(g[:, :11008].contiguous())
+        return h
+    d_ms = time_graph(dense_chain, reps=10)
+    res.update({"dense_fp16_ms_per_token": d_ms, "dense_fp16_us_per_layer": d_ms * 1e3 / N_LAYERS, "speedup_vs_dense_fp16": d_ms / bc_ms})
+    del dense
+    torch.cuda.empty_cache()
+    return res
 
 
 PREFILL_TOKENS = 8 * 2048          # BASELINE.json configs[2]: 2048-token prefill x batch 8
