@@ -78,6 +78,9 @@ __device__ inline void run_segment(const ProblemDev& P, int j0, int j1, int64_t 
     const SpecT* spec = reinterpret_cast<const SpecT*>(P.spec) + (size_t)j0 * q * B;
     Batch<B, SpecT, UNROLL> bA, bB;
     if (T > 0) load_batch<B, SpecT, UNROLL, WARPS>(bA, spec, 0, q, warp, lane);   // in flight during the x FFT below
+    // Programmatic dependent launch: everything above (twiddles, the first spectrum batch: constants of the stream) overlaps the
+    // previous kernel's tail; x may be that kernel's output, and y may still be read by it, so wait here.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     load_x_spectrum<B, NT, WARPS>(P, n0, xs, tw, fscr, lane, warp);
     __syncthreads();
     RowAcc<B, NT> acc;
@@ -113,6 +116,7 @@ __device__ inline void run_segment(const ProblemDev& P, int j0, int j1, int64_t 
 template <int B, int NT, typename SpecT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, (NT <= 2 ? 2 : 1)) stream_single_kernel(const __grid_constant__ ProblemDev P, int rows_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the next kernel of the stream may start its prologue
     fill_twiddles<B>(reinterpret_cast<float2*>(smem_raw), threadIdx.x, WARPS * 32);
     __syncthreads();
     const int j0 = blockIdx.x * rows_per_cta;
@@ -186,7 +190,20 @@ static cudaError_t launch_single_t(const ProblemDev& P, cudaStream_t st) {
     int rows = (int)((P.p + want_p_ctas - 1) / want_p_ctas);
     if (rows < 1) rows = 1;
     dim3 grid((unsigned)((P.p + rows - 1) / rows), (unsigned)token_groups);
-    kern<<<grid, WARPS * 32, smem, st>>>(P, rows);
+    // launched with the programmatic-stream-serialization attribute: in a chain of dependent per-module launches (a decoder layer:
+    // q/k/v -> o -> gate/up -> down) the prologue of each kernel hides behind the tail of the previous one
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(WARPS * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, P, rows);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
