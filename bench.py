@@ -298,6 +298,10 @@ def run_ours(args):
     if world == 1 and not args.no_detail:
         detail = launch_granularity_detail(bc, _cabi, groups[0], shapes, dev, args)
         try:
+            detail["decode_bf16_spectra"] = bf16_decode_detail(bc, _cabi, dev, shapes, args)
+        except Exception as e:                      # noqa: BLE001
+            detail["decode_bf16_spectra"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        try:
             detail["prefill"] = prefill_detail(bc, _cabi, dev)
         except Exception as e:                      # noqa: BLE001 -- evidence only; never hides the headline line
             detail["prefill"] = {"error": "%s: %s" % (type(e).__name__, e)}
@@ -386,6 +390,41 @@ def launch_granularity_detail(bc, _cabi, grp_all, shapes, dev, args):
     except Exception as e:                                               # noqa: BLE001
         out["dependent_chain"] = {"error": "%s: %s" % (type(e).__name__, e)}
     return out
+
+
+def bf16_decode_detail(bc, _cabi, dev, shapes, args, steps=2000):
+    """The headline workload with bf16 spectra (half the bytes, parity class 1e-2): same grouped launch, two weight sets."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(4321)
+    groups = []
+    for _ in range(2):
+        specs = []
+        for (p, q) in shapes:
+            c = torch.randn(p, q, B, device=dev, generator=g) * 0.01
+            spec = torch.empty(p, q, B, device=dev, dtype=torch.bfloat16)
+            _cabi.check(_cabi.lib().bcl_precompute_spectrum(c.data_ptr(), p, q, B, spec.data_ptr(), _cabi.BF16, _cabi.LAYOUT_STREAM,
+                                                            _cabi.stream_ptr(dev)), "bcl_precompute_spectrum")
+            specs.append(spec)
+        grp = bc.GroupedBCForward.from_packed(shapes, specs, 1, torch.float16, dev, num_ctas=args.ctas_per_sm * torch.cuda.get_device_properties(dev).multi_processor_count)
+        grp.x_all.copy_(torch.randn(grp.x_all.numel(), device=dev, generator=g).to(torch.float16))
+        groups.append(grp)
+    for i in range(20):
+        groups[i & 1].run()
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        groups[i & 1].run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    alg, _ = algorithmic_bytes("bfloat16")
+    peak, _ = peaks()
+    del groups
+    torch.cuda.empty_cache()
+    return {"ms_per_step": ms, "tokens_per_s": 1.0 / (ms * 1e-3), "algorithmic_bytes_per_launch": alg, "hbm_frac_of_measured_peak": alg / (ms * 1e-3) / 1e9 / peak,
+            "note": "MAC-warp bound, not HBM bound: the per-row hand-offs cost the same whether a row is 16 KB (fp32) or 8 KB (bf16); profiles/r1_prefill_notes.md"}
 
 
 def dependent_chain_detail(bc, _cabi, dev, time_graph):
