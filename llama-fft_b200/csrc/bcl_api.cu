@@ -232,7 +232,9 @@ int bcl_group_plan_encode(const bcl_problem* problems, int count, int B, int spe
     int nt = 1; while (nt < maxN) nt *= 2;
     const char* force = getenv("BCL_GROUP_VARIANT");                 // "plain" | "ws": A/B switch for profiling only
     int variant = bcl::stream_ws_supported(B, spec_dtype, nt, qmax) ? 1 : 0;
+    if (variant == 1 && bcl::stream_rw_supported(B, spec_dtype, nt, qmax)) variant = 2;     // bf16 spectra: row-per-warp kernel
     if (force && !strcmp(force, "plain")) variant = 0;
+    if (force && !strcmp(force, "ws") && variant == 2) variant = 1;
     if (variant == 0 && bcl::stream_smem_bytes(B, nt, qmax, 8) > 200 * 1024)
         return fail(BCL_ERR_UNSUPPORTED, "x spectrum tile (N=%d, q=%d, B=%d) exceeds shared memory; call bcl_forward per problem", nt, qmax, B);
 
@@ -287,7 +289,8 @@ int bcl_forward_grouped(const void* dev_plan, const void* host_plan, void* strea
     memcpy(&H, host_plan, sizeof(H));
     if (H.magic != bcl::kPlanMagic) return fail(BCL_ERR_ARG, "host_plan was not written by bcl_group_plan_encode");
     if (!aligned(dev_plan, 16)) return fail(BCL_ERR_ALIGN, "dev_plan must be 16-byte aligned");
-    cudaError_t e = H.variant == 1 ? bcl::launch_stream_ws(H, dev_plan, (cudaStream_t)stream)
+    cudaError_t e = H.variant == 2 ? bcl::launch_stream_rw(H, dev_plan, (cudaStream_t)stream)
+                  : H.variant == 1 ? bcl::launch_stream_ws(H, dev_plan, (cudaStream_t)stream)
                                    : bcl::launch_stream_grouped(H, dev_plan, (cudaStream_t)stream);
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "grouped forward launch");
 }

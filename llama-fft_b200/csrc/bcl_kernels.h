@@ -29,7 +29,7 @@ struct GroupPlanHeader {
     int32_t num_ctas;
     int32_t num_segs;
     int32_t B, spec_dtype, nt, qmax;
-    int32_t variant;      // 0 = plain CTA-cooperative kernel, 1 = warp-specialised TMA pipeline (one CTA per SM)
+    int32_t variant;      // 0 = plain CTA-cooperative kernel, 1 = warp-specialised TMA pipeline (one CTA per SM), 2 = its row-per-warp form (bf16 spectra)
     int32_t reserved;
     uint64_t off_problems, off_cta_ptr, off_segs, total_bytes;
 };
@@ -40,6 +40,8 @@ cudaError_t launch_stream_single(const ProblemDev& P, int B, int spec_dtype, cud
 cudaError_t launch_stream_grouped(const GroupPlanHeader& H, const void* dev_plan, cudaStream_t st);
 bool stream_ws_supported(int B, int spec_dtype, int nt, int qmax);
 cudaError_t launch_stream_ws(const GroupPlanHeader& H, const void* dev_plan, cudaStream_t st);
+bool stream_rw_supported(int B, int spec_dtype, int nt, int qmax);
+cudaError_t launch_stream_rw(const GroupPlanHeader& H, const void* dev_plan, cudaStream_t st);
 size_t stream_smem_bytes(int B, int nt, int q, int warps);
 int stream_pick_nt(int64_t N, int q, int B);
 

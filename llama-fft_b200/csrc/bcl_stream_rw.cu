@@ -1,0 +1,319 @@
+// bcl_stream_rw.cu -- row-per-warp variant of the grouped decode kernel, for 16-bit (bf16) spectra.
+//
+// reference: the same forward as bcl_stream_ws.cu (src/patch_llama_fft.py:246-271, one token per problem).
+// In bcl_stream_ws.cu the eight MAC warps split every block-row eight ways (warp m owns input blocks i = m mod 8) and park eight
+// partial spectra per row; the per-row hand-offs (barrier wait, release, parking, the finisher's 8-way reduction) cost ~480
+// cycles per row and warp whether the row is 16 KB of fp32 or 8 KB of bf16 -- with bf16 spectra the MAC warps, not HBM, bound
+// the kernel (clock stamps: profiles/r1_prefill_notes.md).  Here a MAC warp multiplies a WHOLE row: lane l accumulates its
+// packed reals of all q blocks of C_f[row] (ring) times X_f (shared memory) in registers, parks ONE finished spectrum per row,
+// and the finisher only inverse-transforms.  Eight rows are in flight per CTA; the hand-offs per row drop eightfold.
+//   warp 0           TMA producer (identical ring protocol: one bulk copy per (row, stage-of-row))
+//   warps 1..8       row warps: rows r = m, m + 8, ... of the CTA's running row sequence
+//   warps 9..12      X warps: rfft(x) of the next segment into the other half of a double-buffered X buffer
+//   warps 13..15     finishers: inverse real FFT of 4 rows at once, 1/B, round to x.dtype, + bias, store y
+#include <cstdlib>
+#include "bcl_stream_parts.cuh"
+
+namespace bcl {
+namespace rw {
+
+constexpr int NM = 8, NX = 4, NF = 3, RG = 4;
+constexpr int THREADS = 32 * (1 + NM + NX + NF);
+constexpr int MAX_STAGES = 16;
+__host__ __device__ constexpr int stage_blocks(int B) { return 4096 / B; }       // same chunking as bcl_stream_ws.cu
+
+// The row warps drift apart (a warp's consecutive rows are NM rows = up to NM * nst ring chunks and two groups apart), so a warp
+// can be MORE than one phase ahead of a barrier -- and a parity wait cannot tell phase n+2 from phase n.  Wherever that can happen
+// the waiter first checks a sequence number in shared memory: `chunk_in[stage]` = the chunk the producer is filling / has filled
+// the stage with, `accepts[buf]` = the group the buffer may be parked into next.
+struct Barriers {
+    uint64_t full[MAX_STAGES];      // ring stage filled by TMA                      (1 arrival + tx bytes)
+    uint64_t empty[MAX_STAGES];     // ring stage released by the ONE row warp that owns it
+    uint64_t gfull[NF];             // group buffer complete                          (RG arrivals: one per row)
+    uint64_t xfull[2];              // x spectrum of a segment ready in X buffer k    (NX arrivals)
+    uint64_t xempty[2];             // every row warp is done with X buffer k          (NM arrivals)
+    volatile int chunk_in[MAX_STAGES];
+    volatile int accepts[NF];
+};
+static_assert(sizeof(Barriers) <= 512, "barrier block");
+
+__device__ inline uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ inline void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); }
+__device__ inline void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
+__device__ inline void mbar_arrive_n(uint64_t* b, uint32_t n) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(n) : "memory"); }
+__device__ inline void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ inline bool mbar_try(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ inline void mbar_wait(uint64_t* b, uint32_t parity) {
+    const uint32_t addr = smem_u32(b);
+    if (mbar_try(addr, parity)) return;
+    while (!mbar_try(addr, parity)) __nanosleep(32);
+}
+__device__ inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ inline void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ inline void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <int B, typename SpecT>
+__global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev* __restrict__ problems, const int* __restrict__ cta_seg_ptr,
+                                                              const SegWork* __restrict__ segs, int S, int qmax) {
+    using LM = LaneMap<B>;
+    using FC = FftCfg<B>;
+    constexpr int NT = 1;
+    constexpr int CH = LM::CH, CW = LM::CW;
+    constexpr int BLOCK_BYTES = B * (int)sizeof(SpecT);
+    constexpr int CB = stage_blocks(B);                              // blocks per ring stage
+    constexpr int STAGE_BYTES = CB * BLOCK_BYTES;
+    constexpr int NW = CW * (int)sizeof(SpecT) / 4;                  // 32-bit words per lane chunk of a spectrum block
+    constexpr int UB = 8;                                            // blocks multiplied per unrolled batch (loads first)
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Barriers* bars = reinterpret_cast<Barriers*>(smem_raw);
+    float2* tw = reinterpret_cast<float2*>(smem_raw + 512);
+    unsigned char* ring = smem_raw + 512 + 1024;
+    float* part = reinterpret_cast<float*>(ring + (size_t)S * STAGE_BYTES);                         // [NF][RG][B]: finished row spectra
+    float2* fscr_all = reinterpret_cast<float2*>(part + NF * RG * B);                               // FFT scratch of NM + NX + NF warps
+    float* xs_all = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(fscr_all) + (size_t)(NM + NX + NF) * FC::WARP_SCRATCH_BYTES);   // [2][qmax][B]
+    const size_t xs_stride = (size_t)qmax * B;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); bars->chunk_in[s] = -1; }
+        for (int g = 0; g < NF; ++g) { mbar_init(&bars->gfull[g], RG); bars->accepts[g] = g; }
+        for (int k = 0; k < 2; ++k) { mbar_init(&bars->xfull[k], NX); mbar_init(&bars->xempty[k], NM); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fill_twiddles<B>(tw, threadIdx.x, THREADS);
+    __syncthreads();
+    pdl_launch_dependents();                                         // see bcl_stream_ws.cu: spectra and plan are constants of the stream
+
+    const int s0 = cta_seg_ptr[blockIdx.x], s1 = cta_seg_ptr[blockIdx.x + 1];
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0; int idx = 0;
+            for (int s = s0; s < s1; ++s) {
+                const SegWork w = segs[s];
+                const ProblemDev* P = problems + w.g;
+                const int q = P->q;
+                const int nst = (q + CB - 1) / CB;
+                const unsigned char* rowp = reinterpret_cast<const unsigned char*>(P->spec) + (size_t)w.j0 * q * BLOCK_BYTES;
+                for (int r = w.j0; r < w.j1; ++r, rowp += (size_t)q * BLOCK_BYTES) {
+                    for (int cs = 0; cs < nst; ++cs, ++idx) {
+                        mbar_wait(&bars->empty[stage], ph ^ 1u);          // in order and one phase at a time: parity is enough here
+                        bars->chunk_in[stage] = idx;                     // from now on full[stage] is in this chunk's phase
+                        __threadfence_block();
+                        const uint32_t bytes = (uint32_t)min(CB, q - cs * CB) * BLOCK_BYTES;
+                        mbar_arrive_expect_tx(&bars->full[stage], bytes);
+                        bulk_g2s(ring + (size_t)stage * STAGE_BYTES, rowp + (size_t)cs * STAGE_BYTES, bytes, &bars->full[stage]);
+                        if (++stage == S) { stage = 0; ph ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp <= NM) {
+        // ===================== row warps =====================
+        const int m = warp - 1;
+        if (s0 < s1) {                                               // first segment: help with rfft(x) (start-up latency, HBM idles)
+            pdl_wait();
+            const ProblemDev P0 = problems[segs[s0].g];
+            load_x_spectrum<B, NT, NM + NX>(P0, 0, xs_all, tw, fscr_all + (size_t)m * (FC::WARP_SCRATCH_BYTES / 8), lane, m);
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * (NM + NX)) : "memory");
+        }
+        int chunk0 = 0;                                              // ring chunk index of the segment's first chunk (CTA-wide sequence)
+        int row0 = 0;                                                // running row index of the segment's first row
+        int grp0 = 0;                                                // running group index of the segment's first group
+        for (int s = s0; s < s1; ++s) {
+            const SegWork w = segs[s];
+            const int q = problems[w.g].q;
+            const int rows = w.j1 - w.j0;
+            const int nst = (q + CB - 1) / CB;
+            const int k = s - s0;
+            const float* xs = xs_all + (size_t)(k & 1) * xs_stride;
+            if (k > 0) mbar_wait(&bars->xfull[k & 1], (uint32_t)((k - 1) >> 1) & 1u);      // buffer 1: segments 1,3,..; buffer 0: 2,4,.. (0 was cooperative)
+            // my rows of this segment: (row0 + r) % NM == m
+            int r = (m - (row0 % NM) + NM) % NM;
+            for (; r < rows; r += NM) {
+                int idx = chunk0 + r * nst;
+                int stage = idx % S; uint32_t ph = (uint32_t)(idx / S) & 1u;
+                RowAcc<B, NT> acc;
+                acc.clear();
+                for (int cs = 0; cs < nst; ++cs, ++idx) {
+                    while (bars->chunk_in[stage] != idx) __nanosleep(20);   // my chunk's turn in this stage (see Barriers)
+                    mbar_wait(&bars->full[stage], ph);
+                    const SpecT* cbuf = reinterpret_cast<const SpecT*>(ring + (size_t)stage * STAGE_BYTES);
+                    const int nblk = min(CB, q - cs * CB);
+                    const float* xrow = xs + (size_t)cs * CB * B;
+                    for (int u0 = 0; u0 < nblk; u0 += UB) {
+                        RawChunk<SpecT, CW> raw[UB][CH];
+                        float xv[UB][CH][CW];
+#pragma unroll
+                        for (int u = 0; u < UB; ++u) {                // all shared loads first: one latency per batch
+                            const bool on = u0 + u < nblk;
+#pragma unroll
+                            for (int ch = 0; ch < CH; ++ch) {
+                                if (on) {
+                                    const uint32_t* src = reinterpret_cast<const uint32_t*>(cbuf + (size_t)(u0 + u) * B + LM::offset(lane, ch));
+                                    if constexpr (NW == 4) { uint4 t = *reinterpret_cast<const uint4*>(src); raw[u][ch].w[0] = t.x; raw[u][ch].w[1] = t.y; raw[u][ch].w[2] = t.z; raw[u][ch].w[3] = t.w; }
+                                    else if constexpr (NW == 2) { uint2 t = *reinterpret_cast<const uint2*>(src); raw[u][ch].w[0] = t.x; raw[u][ch].w[1] = t.y; }
+                                    else { raw[u][ch].w[0] = *src; }
+                                    const float* xp = xrow + (size_t)(u0 + u) * B + LM::offset(lane, ch);
+                                    if constexpr (CW == 4) { float4 t = *reinterpret_cast<const float4*>(xp); xv[u][ch][0] = t.x; xv[u][ch][1] = t.y; xv[u][ch][2] = t.z; xv[u][ch][3] = t.w; }
+                                    else { float2 t = *reinterpret_cast<const float2*>(xp); xv[u][ch][0] = t.x; xv[u][ch][1] = t.y; }
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < NW; ++e) raw[u][ch].w[e] = 0u;
+#pragma unroll
+                                    for (int e = 0; e < CW; ++e) xv[u][ch][e] = 0.f;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < UB; ++u) {
+#pragma unroll
+                            for (int ch = 0; ch < CH; ++ch) {
+                                float cv[CW];
+                                decode_raw<SpecT, CW>(raw[u][ch], cv);
+#pragma unroll
+                                for (int e = 0; e < CW; e += 2) {
+                                    const float cr = cv[e], ci = cv[e + 1], xre = xv[u][ch][e], xim = xv[u][ch][e + 1];
+                                    acc.a[0][ch][e] = fmaf(cr, xre, acc.a[0][ch][e]);
+                                    acc.a[0][ch][e] = fmaf(-ci, xim, acc.a[0][ch][e]);
+                                    acc.a[0][ch][e + 1] = fmaf(cr, xim, acc.a[0][ch][e + 1]);
+                                    acc.a[0][ch][e + 1] = fmaf(ci, xre, acc.a[0][ch][e + 1]);
+                                    if (ch == 0 && e == 0) {         // packed slot 0/1 of lane 0 is (DC, Nyquist)
+                                        acc.dc[0] = fmaf(cr, xre, acc.dc[0]);
+                                        acc.ny[0] = fmaf(ci, xim, acc.ny[0]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->empty[stage]);   // the producer may refill this stage
+                    if (++stage == S) { stage = 0; ph ^= 1u; }
+                }
+                // park the finished row spectrum; the group's finisher starts when all its rows have arrived
+                const int gi = grp0 + r / RG;
+                const int gb = gi % NF;
+                while (bars->accepts[gb] != gi) __nanosleep(20);       // the finisher has drained the buffer's previous group
+                __threadfence_block();
+                store_partial<B, NT, 1>(acc, part + (size_t)gb * RG * B, r % RG, 0, lane);
+                __syncwarp();
+                if (lane == 0) {
+                    const int nr = min(RG, rows - (r / RG) * RG);    // rows of this (possibly ragged) group
+                    mbar_arrive_n(&bars->gfull[gb], (r % RG == nr - 1) ? (uint32_t)(1 + RG - nr) : 1u);   // its last row stands in for the missing ones
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->xempty[k & 1]);         // done reading this segment's X buffer
+            chunk0 += rows * nst;
+            row0 += rows;
+            grp0 += (rows + RG - 1) / RG;
+        }
+    } else if (warp <= NM + NX) {
+        // ===================== X warps: rfft(x) of each segment into the other X buffer, one segment ahead of the row warps ======
+        const int xw = warp - 1 - NM;
+        float2* fscr = fscr_all + (size_t)(NM + xw) * (FC::WARP_SCRATCH_BYTES / 8);
+        pdl_wait();                                                      // x may have been written by the previous grid
+        if (s0 < s1) {
+            const ProblemDev P0 = problems[segs[s0].g];
+            load_x_spectrum<B, NT, NM + NX>(P0, 0, xs_all, tw, fscr, lane, NM + xw);
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * (NM + NX)) : "memory");
+        }
+        for (int s = s0 + 1; s < s1; ++s) {
+            const ProblemDev P = problems[segs[s].g];
+            const int k = s - s0;
+            if (k >= 2) mbar_wait(&bars->xempty[k & 1], (uint32_t)((k - 2) >> 1) & 1u);     // the segment that used this buffer is finished
+            load_x_spectrum<B, NT, NX>(P, 0, xs_all + (size_t)(k & 1) * xs_stride, tw, fscr, lane, xw);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->xfull[k & 1]);
+        }
+    } else {
+        // ===================== finishers =====================
+        const int f = warp - 1 - NM - NX;
+        float2* fscr = fscr_all + (size_t)(NM + NX + f) * (FC::WARP_SCRATCH_BYTES / 8);
+        pdl_wait();                                                      // y may still be read by the previous grid
+        int gi = 0;
+        for (int s = s0; s < s1; ++s) {
+            const SegWork w = segs[s];
+            const ProblemDev P = problems[w.g];
+            const int rows = w.j1 - w.j0;
+            for (int g0 = 0; g0 < rows; g0 += RG, ++gi) {
+                if (gi % NF != f) continue;
+                mbar_wait(&bars->gfull[f], (uint32_t)(gi / NF) & 1u);
+                const int nr = min(RG, rows - g0);
+                float* gpart = part + (size_t)f * RG * B;
+                for (int p0 = 0; p0 < nr; p0 += FC::G)
+                    finish_pairs<B, NT, 1>(P, w.j0 + g0, 0, gpart + (size_t)p0 * B, p0, min(FC::G, nr - p0), tw, fscr, lane);
+                __syncwarp();
+                if (lane == 0) { __threadfence_block(); bars->accepts[f] = gi + NF; }     // the buffer takes group gi + NF next
+            }
+        }
+    }
+}
+
+size_t smem_bytes(int B, int spec_bytes, int qmax, int S) {
+    const size_t fscr = B == 64 ? FftCfg<64>::WARP_SCRATCH_BYTES : (B == 128 ? FftCfg<128>::WARP_SCRATCH_BYTES : FftCfg<256>::WARP_SCRATCH_BYTES);
+    const size_t stage = (size_t)stage_blocks(B) * B * spec_bytes;
+    return 512 + 1024 + (size_t)S * stage + (size_t)NF * RG * B * 4 + (size_t)(NM + NX + NF) * fscr + (size_t)2 * qmax * B * 4;
+}
+
+int pick_stages(int B, int spec_dtype, int nt, int qmax) {
+    if (nt != 1 || spec_dtype != BCL_BF16) return 0;                  // fp32 spectra are HBM-bound in bcl_stream_ws.cu already
+    const size_t budget = 227 * 1024;
+    const size_t fixed = smem_bytes(B, 2, qmax, 0);
+    const size_t stage = (size_t)stage_blocks(B) * B * 2;
+    if (fixed + (size_t)(NM + 1) * stage > budget) return 0;          // eight rows in flight + one stage of prefetch at least
+    int S = (int)((budget - fixed) / stage);
+    return S > MAX_STAGES ? MAX_STAGES : S;
+}
+
+template <int B>
+static cudaError_t launch_t(const GroupPlanHeader& H, const unsigned char* d, cudaStream_t st) {
+    auto kern = stream_rw_kernel<B, __nv_bfloat16>;
+    const int S = pick_stages(B, H.spec_dtype, H.nt, H.qmax);
+    const size_t smem = smem_bytes(B, 2, H.qmax, S);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)H.num_ctas);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const ProblemDev* probs = reinterpret_cast<const ProblemDev*>(d + H.off_problems);
+    const int* cta_ptr = reinterpret_cast<const int*>(d + H.off_cta_ptr);
+    const SegWork* segs = reinterpret_cast<const SegWork*>(d + H.off_segs);
+    e = cudaLaunchKernelEx(&cfg, kern, probs, cta_ptr, segs, S, (int)H.qmax);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+}  // namespace rw
+
+// BCL_DECODE_RW=0 keeps the split-q kernel of bcl_stream_ws.cu for bf16 spectra too (A/B switch for profiling)
+bool stream_rw_supported(int B, int spec_dtype, int nt, int qmax) {
+    static const bool on = !(getenv("BCL_DECODE_RW") && getenv("BCL_DECODE_RW")[0] == '0');
+    return on && rw::pick_stages(B, spec_dtype, nt, qmax) >= rw::NM + 1;
+}
+
+cudaError_t launch_stream_rw(const GroupPlanHeader& H, const void* dev_plan, cudaStream_t st) {
+    const unsigned char* d = reinterpret_cast<const unsigned char*>(dev_plan);
+    switch (H.B) { case 64: return rw::launch_t<64>(H, d, st); case 128: return rw::launch_t<128>(H, d, st); default: return rw::launch_t<256>(H, d, st); }
+}
+
+}  // namespace bcl

@@ -355,3 +355,35 @@ def test_pipelined_host_entry_matches_serial_host_entry():
     for k in range(2):
         slots[k].wait_host()
         assert torch.equal(hys[k], ref[k])
+
+
+@pytest.mark.parametrize("B,shapes,reps,num_ctas,bias", [
+    (128, [(32, 32)] * 4 + [(86, 32)] * 2 + [(32, 86)], 8, None, False),       # 56 problems over 148 CTAs: ring wraps, group-buffer reuse
+    (128, [(32, 32), (32, 86), (86, 32)], 4, 5, True),                         # few CTAs: many segments per CTA (X double buffer), bias
+    (64, [(16, 24), (40, 8), (9, 70)], 5, 9, False),
+    (256, [(8, 8), (12, 20), (20, 12)], 5, 11, True),
+])
+def test_grouped_decode_bf16_row_per_warp_kernel(B, shapes, reps, num_ctas, bias):
+    """bf16 spectra, one token per problem: the grouped launch runs the row-per-warp kernel (bcl_stream_rw.cu), whose row warps drift
+    apart (sequence-number guarded barriers).  Every problem must match its own per-module forward (same math, other summation
+    order) and the oracle in the bf16 class; a second launch of the same plan must be bit-identical (no ordering effects)."""
+    g = torch.Generator().manual_seed(B + len(shapes) + reps)
+    layers, xs = [], []
+    for _ in range(reps):
+        for (p, q) in shapes:
+            b = torch.randn(p * B, generator=g) * 0.1 if bias else None
+            layers.append(make_layer(torch.randn(p, q, B, generator=g) * 0.02, b, torch.bfloat16))
+            xs.append(torch.randn(1, q * B, generator=g).to(torch.float16).to(DEV))
+    specs = [m.build_spectrum() for m in layers]
+    kw = {} if num_ctas is None else {"num_ctas": num_ctas}
+    grp = bc.GroupedBCForward(xs, specs, [m.bias.detach() for m in layers] if bias else None, **kw)
+    ys = [y.clone() for y in grp.run()]
+    ys2 = grp.run()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for m, x, y, y2 in zip(layers, xs, ys, ys2):
+            assert torch.equal(y, y2)
+            # the spectrum product is rounded to x.dtype (fp16) BEFORE the bias is added (reference :266-271): another summation
+            # order may move that rounding by one fp16 ulp even when y itself is fp32 (fp32 bias)
+            assert_close(y, m(x), 1e-5, torch.float16)
+            assert_close(y, O.bc_forward_torch(m.c.detach().cpu(), x.cpu(), None if m.bias is None else m.bias.detach().cpu()), 1e-2, torch.float16)
