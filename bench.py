@@ -424,7 +424,7 @@ def bf16_decode_detail(bc, _cabi, dev, shapes, args, steps=2000):
     del groups
     torch.cuda.empty_cache()
     return {"ms_per_step": ms, "tokens_per_s": 1.0 / (ms * 1e-3), "algorithmic_bytes_per_launch": alg, "hbm_frac_of_measured_peak": alg / (ms * 1e-3) / 1e9 / peak,
-            "note": "MAC-warp bound, not HBM bound: the per-row hand-offs cost the same whether a row is 16 KB (fp32) or 8 KB (bf16); profiles/r1_prefill_notes.md"}
+            "note": "row-per-warp kernel (bcl_stream_rw.cu): with 8 KB rows the split-q kernel of the headline is bound by its per-row hand-offs, not by HBM; profiles/r1_prefill_notes.md"}
 
 
 def dependent_chain_detail(bc, _cabi, dev, time_graph):
