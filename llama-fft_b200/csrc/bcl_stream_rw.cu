@@ -17,7 +17,10 @@
 namespace bcl {
 namespace rw {
 
-constexpr int NM = 8, NX = 4, NF = 3, RG = 4;
+#ifndef BCL_RW_NF
+#define BCL_RW_NF 3
+#endif
+constexpr int NM = 8, NX = 4, NF = BCL_RW_NF, RG = 4;       // NF = 4 and 6 measured slower (32.9, 34.2 us vs 31.5 us: fewer registers, smaller ring)
 constexpr int THREADS = 32 * (1 + NM + NX + NF);
 constexpr int MAX_STAGES = 16;
 __host__ __device__ constexpr int stage_blocks(int B) { return 4096 / B; }       // same chunking as bcl_stream_ws.cu
@@ -145,8 +148,18 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
             for (; r < rows; r += NM) {
                 int idx = chunk0 + r * nst;
                 int stage = idx % S; uint32_t ph = (uint32_t)(idx / S) & 1u;
-                RowAcc<B, NT> acc;
-                acc.clear();
+                // Independent accumulator chains: the two products of every complex MAC go to separate sums (pos / neg) and even / odd
+                // blocks to separate sets, so consecutive FMAs never depend on each other (a single chain per packed real made the
+                // row warp issue one FMA per ~4-5 cycles: 2.3k cycles per row, clock stamps).
+                float sp[2][CH][CW], sn[2][CH][CW], sdc[2], sny[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    sdc[h] = 0.f; sny[h] = 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+                        for (int e = 0; e < CW; ++e) { sp[h][ch][e] = 0.f; sn[h][ch][e] = 0.f; }
+                }
                 for (int cs = 0; cs < nst; ++cs, ++idx) {
                     while (bars->chunk_in[stage] != idx) __nanosleep(20);   // my chunk's turn in this stage (see Barriers)
                     mbar_wait(&bars->full[stage], ph);
@@ -179,6 +192,8 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                         }
 #pragma unroll
                         for (int u = 0; u < UB; ++u) {
+                            constexpr int dummy = 0; (void)dummy;
+                            const int h = u & 1;
 #pragma unroll
                             for (int ch = 0; ch < CH; ++ch) {
                                 float cv[CW];
@@ -186,22 +201,30 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
 #pragma unroll
                                 for (int e = 0; e < CW; e += 2) {
                                     const float cr = cv[e], ci = cv[e + 1], xre = xv[u][ch][e], xim = xv[u][ch][e + 1];
-                                    acc.a[0][ch][e] = fmaf(cr, xre, acc.a[0][ch][e]);
-                                    acc.a[0][ch][e] = fmaf(-ci, xim, acc.a[0][ch][e]);
-                                    acc.a[0][ch][e + 1] = fmaf(cr, xim, acc.a[0][ch][e + 1]);
-                                    acc.a[0][ch][e + 1] = fmaf(ci, xre, acc.a[0][ch][e + 1]);
-                                    if (ch == 0 && e == 0) {         // packed slot 0/1 of lane 0 is (DC, Nyquist)
-                                        acc.dc[0] = fmaf(cr, xre, acc.dc[0]);
-                                        acc.ny[0] = fmaf(ci, xim, acc.ny[0]);
-                                    }
+                                    sp[h][ch][e] = fmaf(cr, xre, sp[h][ch][e]);             // Re: cr xre - ci xim
+                                    sn[h][ch][e] = fmaf(ci, xim, sn[h][ch][e]);
+                                    sp[h][ch][e + 1] = fmaf(cr, xim, sp[h][ch][e + 1]);     // Im: cr xim + ci xre
+                                    sn[h][ch][e + 1] = fmaf(ci, xre, sn[h][ch][e + 1]);
                                 }
                             }
+                            // packed slot 0/1 of lane 0 is (DC, Nyquist): real x real products, already in sp[..][0][0] and sn[..][0][0]
                         }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->empty[stage]);   // the producer may refill this stage
                     if (++stage == S) { stage = 0; ph ^= 1u; }
                 }
+                RowAcc<B, NT> acc;
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+                    for (int e = 0; e < CW; e += 2) {
+                        acc.a[0][ch][e] = (sp[0][ch][e] + sp[1][ch][e]) - (sn[0][ch][e] + sn[1][ch][e]);
+                        acc.a[0][ch][e + 1] = (sp[0][ch][e + 1] + sp[1][ch][e + 1]) + (sn[0][ch][e + 1] + sn[1][ch][e + 1]);
+                    }
+                acc.dc[0] = sp[0][0][0] + sp[1][0][0];               // lane 0: DC = sum C_dc X_dc (= the cr*xre sum of slot 0)
+                acc.ny[0] = sn[0][0][0] + sn[1][0][0];               //         Nyquist = sum C_ny X_ny (= the ci*xim sum of slot 0)
+                (void)sdc; (void)sny;
                 // park the finished row spectrum; the group's finisher starts when all its rows have arrived
                 const int gi = grp0 + r / RG;
                 const int gb = gi % NF;

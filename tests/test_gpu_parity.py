@@ -385,5 +385,6 @@ def test_grouped_decode_bf16_row_per_warp_kernel(B, shapes, reps, num_ctas, bias
             assert torch.equal(y, y2)
             # the spectrum product is rounded to x.dtype (fp16) BEFORE the bias is added (reference :266-271): another summation
             # order may move that rounding by one fp16 ulp even when y itself is fp32 (fp32 bias)
-            assert_close(y, m(x), 1e-5, torch.float16)
+            # (with a bias the flipped ulp belongs to the value before the bias was added, which |y| no longer bounds: absolute 1e-3)
+            assert_close(y, m(x), 1e-3 if bias else 1e-5, torch.float16)
             assert_close(y, O.bc_forward_torch(m.c.detach().cpu(), x.cpu(), None if m.bias is None else m.bias.detach().cpu()), 1e-2, torch.float16)
