@@ -117,7 +117,31 @@ def prefill_dft_offsets(p: int, q: int, B: int):
 
 
 def stream_ptr(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    """Raw cudaStream_t of torch's current stream on `device` (the private accessor skips the Stream object: ~0.5 us instead of ~6 us
+    per call, which matters when a decode step makes hundreds of per-module calls)."""
+    try:
+        dev = device if isinstance(device, torch.device) else torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        return torch._C._cuda_getCurrentRawStream(idx)
+    except AttributeError:                                    # accessor renamed in another torch version: the public route
+        return torch.cuda.current_stream(device).cuda_stream
+
+
+class on_device:
+    """`with on_device(t.device):` -- torch.cuda.device(...) only when the current device differs (the context manager costs ~4 us)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.ctx = None if idx == torch.cuda.current_device() else torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
 
 
 def require_cuda(t: torch.Tensor, what: str) -> None:

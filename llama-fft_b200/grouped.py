@@ -85,7 +85,7 @@ class GroupedBCForward:
 
     def run_host(self, host_x: torch.Tensor, host_y: torch.Tensor):
         """End-to-end step with HOST buffers: H2D(x_all) -> one grouped launch -> D2H(y_all) -> synchronise."""
-        with torch.cuda.device(self.device):
+        with _cabi.on_device(self.device):
             rc = _cabi.lib().bcl_forward_grouped_host(
                 self.dev_plan.data_ptr(), self.host_plan.data_ptr(),
                 host_x.data_ptr(), self.x_all.data_ptr(), self.x_all.numel() * self.x_all.element_size(),
@@ -104,7 +104,7 @@ class GroupedBCForward:
                 ev.record(pipe.compute)                       # materialise the cudaEvent_t handles
             self._slot_used = False
         ei, ec, eo = self._slot_events
-        with torch.cuda.device(self.device):
+        with _cabi.on_device(self.device):
             rc = _cabi.lib().bcl_forward_grouped_host_pipelined(
                 self.dev_plan.data_ptr(), self.host_plan.data_ptr(),
                 host_x.data_ptr(), self.x_all.data_ptr(), self.x_all.numel() * self.x_all.element_size(),
@@ -120,7 +120,7 @@ class GroupedBCForward:
             self._slot_events[2].synchronize()
 
     def run(self):
-        with torch.cuda.device(self.device):
+        with _cabi.on_device(self.device):
             rc = _cabi.lib().bcl_forward_grouped(self.dev_plan.data_ptr(), self.host_plan.data_ptr(),
                                                  _cabi.stream_ptr(self.device))
         _cabi.check(rc, "bcl_forward_grouped")

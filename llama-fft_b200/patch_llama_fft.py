@@ -159,7 +159,7 @@ class BlockCirculantLinear(nn.Module):
     # -- spectrum lifecycle ---------------------------------------------------------------------------------
     def _spectrum_key(self):
         c = self.c
-        return (c.data_ptr(), c._version, str(c.device), c.dtype, self.spectrum_dtype)
+        return (c.data_ptr(), c._version, c.device, c.dtype, self.spectrum_dtype)
 
     def build_spectrum(self, *, force: bool = False, layout: int = _cabi.LAYOUT_STREAM) -> torch.Tensor:
         """rfft(c) on c's device (replaces reference :256-257 / the _Cf_cache of src/bench_all_in_one.py:204-219), in the
@@ -277,7 +277,7 @@ def bc_forward(x_flat: torch.Tensor, spec: torch.Tensor, bias: Optional[torch.Te
         ws_bytes = L.bcl_workspace_bytes(N, p, q, B, spec_dt, layout)
         ws = prefill_workspace(x_flat.device, ws_bytes)
         ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
-    with torch.cuda.device(x_flat.device):
+    with _cabi.on_device(x_flat.device):
         rc = L.bcl_forward(x_flat.data_ptr(), _cabi.DTYPE[x_flat.dtype], N, x_flat.stride(0),
                            spec.data_ptr(), spec_dt, layout, p, q, B,
                            None if bias is None else bias.data_ptr(), 0 if bias is None else _cabi.DTYPE[bias.dtype],

@@ -145,7 +145,7 @@ def bc_forward_bcast(layer: BlockCirculantLinear, x: torch.Tensor, dsts: List[to
         ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
     ptrs = (ctypes.c_void_p * len(dsts))(*[d.data_ptr() for d in dsts])
     bias = layer.bias
-    with torch.cuda.device(x.device):
+    with _cabi.on_device(x.device):
         rc = L.bcl_forward_bcast(x.data_ptr(), _cabi.DTYPE[x.dtype], N, x.stride(0), spec.data_ptr(), spec_dt, layout, p, q, B,
                                  None if bias is None else bias.data_ptr(), 0 if bias is None else _cabi.DTYPE[bias.dtype],
                                  ptrs, len(dsts), _cabi.DTYPE[d0.dtype], d0.stride(0), ws_ptr, ws_bytes, _cabi.stream_ptr(x.device))
