@@ -151,10 +151,9 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                 // Independent accumulator chains: the two products of every complex MAC go to separate sums (pos / neg) and even / odd
                 // blocks to separate sets, so consecutive FMAs never depend on each other (a single chain per packed real made the
                 // row warp issue one FMA per ~4-5 cycles: 2.3k cycles per row, clock stamps).
-                float sp[2][CH][CW], sn[2][CH][CW], sdc[2], sny[2];
+                float sp[2][CH][CW], sn[2][CH][CW];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    sdc[h] = 0.f; sny[h] = 0.f;
 #pragma unroll
                     for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
@@ -192,7 +191,6 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                         }
 #pragma unroll
                         for (int u = 0; u < UB; ++u) {
-                            constexpr int dummy = 0; (void)dummy;
                             const int h = u & 1;
 #pragma unroll
                             for (int ch = 0; ch < CH; ++ch) {
@@ -224,7 +222,6 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                     }
                 acc.dc[0] = sp[0][0][0] + sp[1][0][0];               // lane 0: DC = sum C_dc X_dc (= the cr*xre sum of slot 0)
                 acc.ny[0] = sn[0][0][0] + sn[1][0][0];               //         Nyquist = sum C_ny X_ny (= the ci*xim sum of slot 0)
-                (void)sdc; (void)sny;
                 // park the finished row spectrum; the group's finisher starts when all its rows have arrived
                 const int gi = grp0 + r / RG;
                 const int gb = gi % NF;
