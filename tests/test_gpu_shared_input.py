@@ -91,7 +91,7 @@ def test_tiny_llama_logits_unchanged_by_fusion():
         ref = model(input_ids=ids).logits
         assert bc.fuse_shared_inputs(model) == 4                     # GQA: k/v are narrower than q, still one group
         got = model(input_ids=ids).logits
-        ids_long = torch.randint(0, 320, (2, 200), device=DEV)       # 400 tokens: no prefill path with fp32 spectra, still fused
+        ids_long = torch.randint(0, 320, (2, 200), device=DEV)       # 400 tokens: the split (fp32-spectrum) tensor-core chain, fused
         l1 = model(input_ids=ids_long).logits
         bc.unfuse_shared_inputs(model)
         l2 = model(input_ids=ids_long).logits
