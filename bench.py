@@ -179,6 +179,11 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the BC-linear path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE line, the JSON: anything a library writes to fd 1 meanwhile (NCCL prints its version banner there when
+    # NCCL_DEBUG is set) goes to stderr instead.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _cabi.lib()
@@ -334,7 +339,9 @@ def run_ours(args):
                            "%d staging slots in flight; copies alone: H2D %.1f us, D2H %.1f us per step; unpipelined (bcl_forward_grouped_host, sync per step): "
                            "%.4f ms/step" % (n_slots, h2d_us, d2h_us, e2e_serial_ms)},
             "gpu_launches": launches, "clocks": clk.summary(), "detail": detail}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
