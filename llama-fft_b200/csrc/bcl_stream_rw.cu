@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                         for (int e = 0; e < CW; ++e) { sp[h][ch][e] = 0.f; sn[h][ch][e] = 0.f; }
                 }
                 for (int cs = 0; cs < nst; ++cs, ++idx) {
-                    while (bars->chunk_in[stage] != idx) __nanosleep(20);   // my chunk's turn in this stage (see Barriers)
+                    while (bars->chunk_in[stage] != idx) __nanosleep(128);   // my chunk's turn in this stage (see Barriers)
                     mbar_wait(&bars->full[stage], ph);
                     const SpecT* cbuf = reinterpret_cast<const SpecT*>(ring + (size_t)stage * STAGE_BYTES);
                     const int nblk = min(CB, q - cs * CB);
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                 // park the finished row spectrum; the group's finisher starts when all its rows have arrived
                 const int gi = grp0 + r / RG;
                 const int gb = gi % NF;
-                while (bars->accepts[gb] != gi) __nanosleep(20);       // the finisher has drained the buffer's previous group
+                while (bars->accepts[gb] != gi) __nanosleep(128);      // the finisher has drained the buffer's previous group
                 __threadfence_block();
                 store_partial<B, NT, 1>(acc, part + (size_t)gb * RG * B, r % RG, 0, lane);
                 __syncwarp();
