@@ -462,6 +462,15 @@ cudaError_t launch_prefill_stage3(const ProblemDev& P, int B, const void* spec_g
     return launch_gemm_irfft(P, B, n_begin, nc, Yf, nullptr, st);
 }
 
+// BCL_PREFILL_CHAIN=1: the single-launch chain kernel (three stages, grid barriers in between) instead of three PDL-chained
+// launches per chunk.  Opt-in: bit-identical, but measured 1-4 us SLOWER (4096x4096: 26.9 / 34.1 / 142.1 us against 26.3 / 30.0 /
+// 140.3 us at 512 / 2048 / 16384 tokens): programmatic dependent launch already hides the launch transitions, and a grid barrier
+// waits for the slowest CTA of every stage.  It only saves host launch cost (one launch instead of three).
+static bool chain_enabled() {
+    static const bool on = getenv("BCL_PREFILL_CHAIN") && getenv("BCL_PREFILL_CHAIN")[0] == '1';
+    return on;
+}
+
 // split = 1: fp32-accurate chain (fp32 spectra): CUDA-core fp32 rfft -> (hi, lo) Xf -> split tcgen05 GEMM -> (hi, lo) Yf -> CUDA-core irfft
 cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gemm, void* workspace, size_t workspace_bytes, int split, cudaStream_t st) {
     const gemm::Geometry g = gemm::geometry(P.p, P.q, B, split);
@@ -485,6 +494,11 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
         const bool tc3 = tc1 && P.y_dtype == P.x_dtype && P.n_extra == 0;
         for (int64_t n0 = 0; n0 < P.N; n0 += ncmax) {
             const int nc = (int)((P.N - n0 < ncmax) ? (P.N - n0) : ncmax);
+            if (tc1 && tc3 && chain_enabled() && ctas >= 8) {                // all three stages on the tensor cores: one launch
+                if ((e = cudaMemsetAsync(ws + kWsHeader, 0, 256, st)) != cudaSuccess) return e;
+                if ((e = gemm::launch_prefill_chain(P, g, spec_gemm, n0, nc, Xf, Xf_lo, Yf, Yf_lo, status, reinterpret_cast<int*>(ws + kWsHeader), ctas, st)) != cudaSuccess) return e;
+                continue;
+            }
             e = tc1 ? gemm::launch_dft_fwd_tc(P, g, spec_gemm, n0, nc, Xf, Xf_lo, status, ctas, st) : launch_gemm_rfft(P, B, n0, nc, Xf, Xf_lo, st);
             if (e != cudaSuccess) return e;
             if ((e = launch_gemm_mma(Xf, Xf_lo, spec_gemm, Yf, Yf_lo, status, P.p, P.q, B, nc, ctas, st)) != cudaSuccess) return e;
@@ -510,6 +524,11 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
     if (e != cudaSuccess) return e;
     for (int64_t n0 = 0; n0 < P.N; n0 += ncmax) {
         const int nc = (int)((P.N - n0 < ncmax) ? (P.N - n0) : ncmax);
+        if (tc_ok && impl == 0 && chain_enabled() && ctas >= 8) {            // all three stages on the tensor cores: one launch
+            if ((e = cudaMemsetAsync(ws + kWsHeader, 0, 256, st)) != cudaSuccess) return e;
+            if ((e = gemm::launch_prefill_chain(P, g, spec_gemm, n0, nc, Xf, nullptr, Yf, nullptr, status, reinterpret_cast<int*>(ws + kWsHeader), ctas, st)) != cudaSuccess) return e;
+            continue;
+        }
         if ((e = launch_prefill_stage1(P, B, spec_gemm, n0, nc, Xf, status, impl, st)) != cudaSuccess) return e;
         if ((e = launch_gemm_mma(Xf, nullptr, spec_gemm, Yf, nullptr, status, P.p, P.q, B, nc, ctas, st)) != cudaSuccess) return e;
         if ((e = launch_prefill_stage3(P, B, spec_gemm, n0, nc, Yf, status, impl, st)) != cudaSuccess) return e;

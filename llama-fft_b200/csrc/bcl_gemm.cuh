@@ -100,6 +100,9 @@ cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void
 // Single-launch pipeline of the three tensor-core stages over L2-resident intermediates (bcl_prefill_fused.cu).
 // counters: 3 * ceil(N/128) ints, zeroed in stream order before the launch; Xf / Yf sized for all N tokens.
 size_t fused_counter_bytes(int64_t N);
+// The three tensor-core stages of one token chunk in ONE launch with grid barriers in between (bcl_prefill_fused.cu).
+cudaError_t launch_prefill_chain(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, void* Xf_lo, void* Yf,
+                                 void* Yf_lo, int* status, int* grid_ctr, int ctas, cudaStream_t st);
 cudaError_t launch_prefill_fused(const ProblemDev& P, const Geometry& g, const void* spec_gemm, void* Xf, void* Yf, int* status, int* counters, int ctas,
                                  cudaStream_t st);
 

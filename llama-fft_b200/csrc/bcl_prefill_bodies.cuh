@@ -53,6 +53,20 @@ __device__ __forceinline__ void ctr_signal(int* ctr, int count) {
     asm volatile("fence.proxy.async;" ::: "memory");
     asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(ctr), "r"(count) : "memory");
 }
+// Grid-wide barrier between the stages of the chain kernel (all CTAs co-resident: grid <= SM count, 1 CTA per SM).  Every CTA's bulk
+// stores have completed (the epilogue warps wait on their bulk groups before a stage body returns); the release / acquire pair plus
+// the async-proxy fences order them before the next stage's TMA loads on every SM.  `target` = CTAs x (barriers passed so far + 1).
+__device__ __forceinline__ bool grid_barrier(int* ctr, int target) {
+    __shared__ int ok;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(ctr), "r"(1) : "memory");
+        ok = ctr_wait(ctr, target) ? 1 : 0;
+    }
+    __syncthreads();
+    return ok != 0;
+}
 __device__ __forceinline__ bool deps_wait_tile(const StageDeps& d, int m) {
     if (d.wait_ctr != nullptr && !ctr_wait(d.wait_ctr + m, d.wait_target)) return false;
     if (d.lag_ctr != nullptr && m >= d.lag && !ctr_wait(d.lag_ctr + (m - d.lag), d.lag_target)) return false;
@@ -390,6 +404,10 @@ done:
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 2 * SET_COLS);
+    if (threadIdx.x == 0) {                                                      // the chain kernel re-initialises this memory for the next stage
+        for (int s = 0; s < S; ++s) { mbar_inval(&bars->full[s]); mbar_inval(&bars->empty[s]); }
+        for (int i = 0; i < 2; ++i) { mbar_inval(&bars->tmem_full[i]); mbar_inval(&bars->tmem_empty[i]); }
+    }
 }
 
 
@@ -625,6 +643,10 @@ done:
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 4 * NB);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_inval(&bars->full[s]); mbar_inval(&bars->empty[s]); }
+        mbar_inval(&bars->tmem_full[0]); mbar_inval(&bars->tmem_empty[0]); mbar_inval(&bars->wfull);
+    }
 }
 
 // One token's 64 outputs (fp32 accumulators, 1/B already folded into Winv) -> 8 swizzled 16-byte chunks of the store tile.
@@ -821,6 +843,11 @@ done:
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, NACC * NB);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_inval(&bars->full[s]); mbar_inval(&bars->empty[s]); }
+        for (int i = 0; i < NACC; ++i) { mbar_inval(&bars->tmem_full[i]); mbar_inval(&bars->tmem_empty[i]); }
+        mbar_inval(&bars->wfull);
+    }
 }
 
 
@@ -836,6 +863,7 @@ long long* trace_ptr(int stage);
 bool prep_dft_fwd(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, StageLaunch<DftArgs>& L,
                   void* Xf_lo = nullptr, DftLoMaps* lo = nullptr);
 bool prep_gemm(const void* Xf, const void* Cmat, void* Yf, int* status, const Geometry& g, int nc, StageLaunch<GemmArgs>& L, GemmLoMaps* lo = nullptr);
+bool prep_gemm_lo(const void* Xf_lo, const void* Cmat, void* Yf_lo, const Geometry& g, int nc, GemmLoMaps* lo);
 bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L,
                   const void* Yf_lo = nullptr, DftLoMaps* lo = nullptr);
 

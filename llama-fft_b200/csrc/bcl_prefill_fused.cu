@@ -34,6 +34,74 @@ prefill_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 
 static_assert(DFT_THREADS == GEMM_THREADS, "the three stage bodies share one block shape");
 
+// ---------------------------------------------------------------------------------------------------------
+// Chain kernel: the three stages one after the other in ONE launch, separated by grid-wide barriers (all CTAs co-resident).
+// Same work split as the three stand-alone launches (CTA b runs items b, b + grid, ... of every stage), same results bit for
+// bit; what it saves is two launch transitions per forward (drain, launch latency, TMEM / barrier set-up behind a cold start)
+// and two thirds of the host launch cost -- which is what bounds prefills of a few hundred to a few thousand tokens.
+// B = 256 runs both half-N passes of a DFT stage back to back (no barrier needed between them).
+// ---------------------------------------------------------------------------------------------------------
+struct ChainLo { DftLoMaps fwd; GemmLoMaps gemm; DftLoMaps inv; };      // lo halves of the split (fp32-spectrum) layout
+
+template <int B, bool SPLIT>
+__global__ void __launch_bounds__(DFT_THREADS, 1)
+prefill_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWf, const __grid_constant__ CUtensorMap tmXfS,
+                     const __grid_constant__ CUtensorMap tmXfL, const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmYfS,
+                     const __grid_constant__ CUtensorMap tmYfL, const __grid_constant__ CUtensorMap tmWi, const __grid_constant__ CUtensorMap tmOut,
+                     const __grid_constant__ ChainLo lo, const __grid_constant__ DftArgs a1, const __grid_constant__ GemmArgs a2,
+                     const __grid_constant__ DftArgs a3, int* grid_ctr) {
+    extern __shared__ __align__(1024) unsigned char chain_smem[];
+    const int b = (int)blockIdx.x, n = (int)gridDim.x;
+    constexpr int HALVES = B == 256 ? 2 : 1;
+    for (int h = 0; h < HALVES; ++h) {
+        DftArgs a = a1;
+        a.half = h;
+        dft_fwd_body<B, SPLIT>(chain_smem, tmX, tmWf, tmXfS, SPLIT ? &lo.fwd : nullptr, a, b, n);
+        __syncthreads();
+    }
+    if (!grid_barrier(grid_ctr, n)) { if (threadIdx.x == 0) atomicExch(a1.status, 31); return; }
+    freq_gemm_body<SPLIT>(chain_smem, tmXfL, tmC, tmYfS, SPLIT ? &lo.gemm : nullptr, a2, b, n);
+    if (!grid_barrier(grid_ctr, 2 * n)) { if (threadIdx.x == 0) atomicExch(a1.status, 32); return; }
+    for (int h = 0; h < HALVES; ++h) {
+        DftArgs a = a3;
+        a.half = h;
+        dft_inv_body<B, SPLIT>(chain_smem, tmYfL, tmWi, tmOut, SPLIT ? &lo.inv : nullptr, a, b, n);
+        __syncthreads();
+    }
+}
+
+template <int B, bool SPLIT>
+static cudaError_t launch_chain_t(const StageLaunch<DftArgs>& L1, const StageLaunch<GemmArgs>& L2, const StageLaunch<DftArgs>& L3, const ChainLo& lo,
+                                  int* grid_ctr, int ctas, cudaStream_t st) {
+    size_t smem = L1.smem > L2.smem ? L1.smem : L2.smem;
+    if (L3.smem > smem) smem = L3.smem;
+    auto kern = prefill_chain_kernel<B, SPLIT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return launch_pdl(kern, (unsigned)ctas, DFT_THREADS, smem, st, L1.tm_in, L1.tm_w, L1.tm_out, L2.tm_in, L2.tm_w, L2.tm_out, L3.tm_in, L3.tm_w, L3.tm_out, lo,
+                      L1.a, L2.a, L3.a, grid_ctr);
+}
+
+// One token chunk [n_begin, n_begin + nc) through all three tensor-core stages in one launch.  grid_ctr: one int, zeroed in stream
+// order before the launch.  Xf_lo / Yf_lo: the lo halves of the split layout (g.split), else NULL.
+cudaError_t launch_prefill_chain(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, void* Xf_lo, void* Yf,
+                                 void* Yf_lo, int* status, int* grid_ctr, int ctas, cudaStream_t st) {
+    StageLaunch<DftArgs> L1, L3;
+    StageLaunch<GemmArgs> L2;
+    ChainLo lo{};
+    const bool split = g.split != 0;
+    if (split && g.B > 128) return cudaErrorNotSupported;
+    if (!prep_dft_fwd(P, g, spec_gemm, n_begin, nc, Xf, status, L1, split ? Xf_lo : nullptr, split ? &lo.fwd : nullptr)) return cudaErrorNotSupported;
+    if (!prep_gemm(Xf, spec_gemm, Yf, status, g, nc, L2)) return cudaErrorNotSupported;
+    if (split && !prep_gemm_lo(Xf_lo, spec_gemm, Yf_lo, g, nc, &lo.gemm)) return cudaErrorNotSupported;
+    if (!prep_dft_inv(P, g, spec_gemm, n_begin, nc, Yf, status, L3, split ? Yf_lo : nullptr, split ? &lo.inv : nullptr)) return cudaErrorNotSupported;
+    switch (g.B) {
+        case 64: return split ? launch_chain_t<64, true>(L1, L2, L3, lo, grid_ctr, ctas, st) : launch_chain_t<64, false>(L1, L2, L3, lo, grid_ctr, ctas, st);
+        case 128: return split ? launch_chain_t<128, true>(L1, L2, L3, lo, grid_ctr, ctas, st) : launch_chain_t<128, false>(L1, L2, L3, lo, grid_ctr, ctas, st);
+        default: return launch_chain_t<256, false>(L1, L2, L3, lo, grid_ctr, ctas, st);
+    }
+}
+
 size_t fused_counter_bytes(int64_t N) {
     const size_t tiles = (size_t)((N + TILE_M - 1) / TILE_M);
     return (3 * tiles * sizeof(int) + 255) & ~(size_t)255;

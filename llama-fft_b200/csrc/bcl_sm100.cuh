@@ -15,6 +15,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
 }
+// Invalidate an mbarrier so that its shared-memory location may be initialised again (a CTA that runs several stages in turn).
+__device__ __forceinline__ void mbar_inval(uint64_t* b) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
@@ -129,8 +133,8 @@ template <int N> __device__ __forceinline__ void tma_store_wait() { asm volatile
 // ---- TMEM ---------------------------------------------------------------------------------------------------------
 // One full warp allocates `ncols` (power of two >= 32) columns; the base address lands in *slot (shared memory).
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    // (no relinquish_alloc_permit: the chain kernel allocates again for its next stage; one CTA per SM, nobody else is waiting)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");

@@ -524,3 +524,41 @@ def test_split_prefill_16bit_activations_tensor_core_dft_stages(inf, outf, B, dt
     y_ref = O.bc_forward_torch(c, x.float())
     assert_close(y32, y_ref, 1e-4)
     assert_close(y, y_ref, 1e-4, dtype)
+
+
+def test_prefill_chain_kernel_matches_three_launches(tmp_path):
+    """Opt-in single-launch chain kernel (BCL_PREFILL_CHAIN=1: three stages separated by grid barriers) against the default three
+    PDL-chained launches: bit-identical, bf16 and fp32 (split) spectra, B = 128 and the two-half B = 256 stages."""
+    import os
+    import subprocess
+    import sys
+    child = r"""
+import sys, torch
+import llama_fft_b200 as bc
+from llama_fft_b200.patch_llama_fft import prefill_status
+out = sys.argv[1]
+res = {}
+for (inf, outf, B, N, sdt) in [(4096, 4096, 128, 2048 + 77, torch.bfloat16), (1024, 2048, 128, 700, torch.float32), (1024, 512, 256, 900, torch.bfloat16)]:
+    g = torch.Generator().manual_seed(inf + outf + B + N)
+    m = bc.BlockCirculantLinear(inf, outf, block_size=B, bias=False, spectrum_dtype=sdt)
+    with torch.no_grad():
+        m.c.copy_(torch.randn(outf // B, inf // B, B, generator=g) * 0.01)
+    m = m.to("cuda:0").eval()
+    x = torch.randn(N, inf, generator=g).half().to("cuda:0")
+    with torch.no_grad():
+        y = m(x)
+    torch.cuda.synchronize()
+    assert prefill_status("cuda:0") == 0
+    res[f"{inf}x{outf}x{B}"] = y.cpu()
+torch.save(res, out)
+"""
+    outs = {}
+    for tag, flag in (("launches", "0"), ("chain", "1")):
+        out = str(tmp_path / f"{tag}.pt")
+        env = dict(os.environ, BCL_PREFILL_CHAIN=flag, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        r = subprocess.run([sys.executable, "-c", child, out], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = torch.load(out)
+    assert outs["launches"].keys() == outs["chain"].keys()
+    for k in outs["launches"]:
+        assert torch.equal(outs["launches"][k], outs["chain"][k]), k
