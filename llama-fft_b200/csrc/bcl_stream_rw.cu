@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
         // ===================== row warps =====================
         const int m = warp - 1;
         if (s0 < s1) {                                               // first segment: help with rfft(x) (start-up latency, HBM idles)
+            const ProblemDev P0 = problems[segs[s0].g];              // plan data: constant, fetched while the previous grid drains
             pdl_wait();
-            const ProblemDev P0 = problems[segs[s0].g];
             load_x_spectrum<B, NT, NM + NX>(P0, 0, xs_all, tw, fscr_all + (size_t)m * (FC::WARP_SCRATCH_BYTES / 8), lane, m);
             asm volatile("bar.sync 1, %0;" ::"r"(32 * (NM + NX)) : "memory");
         }
@@ -244,9 +244,10 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
         // ===================== X warps: rfft(x) of each segment into the other X buffer, one segment ahead of the row warps ======
         const int xw = warp - 1 - NM;
         float2* fscr = fscr_all + (size_t)(NM + xw) * (FC::WARP_SCRATCH_BYTES / 8);
+        ProblemDev P0{};
+        if (s0 < s1) P0 = problems[segs[s0].g];                          // plan data: constant, fetched while the previous grid drains
         pdl_wait();                                                      // x may have been written by the previous grid
         if (s0 < s1) {
-            const ProblemDev P0 = problems[segs[s0].g];
             load_x_spectrum<B, NT, NM + NX>(P0, 0, xs_all, tw, fscr, lane, NM + xw);
             asm volatile("bar.sync 1, %0;" ::"r"(32 * (NM + NX)) : "memory");
         }

@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
             // First segment: nothing to multiply yet, so the MAC warps help the X warps with rfft(x) (all NM + NX warps, one
             // pass for q <= 48 instead of three): the start-up latency during which the ring is full and HBM idles.
             // Scratch: the (still unused) group buffers.
+            const ProblemDev P0 = problems[segs[s0].g];                  // plan data: constant, fetched while the previous grid drains
             pdl_wait();                                                  // x may have been written by the previous grid
-            const ProblemDev P0 = problems[segs[s0].g];
             TSTART(x0);
             load_x_spectrum<B, NT, NM + NX>(P0, 0, xs, tw, reinterpret_cast<float2*>(part) + (size_t)m * (FC::WARP_SCRATCH_BYTES / 8), lane, m);
             asm volatile("bar.sync 1, %0;" ::"r"(32 * (NM + NX)) : "memory");
@@ -273,9 +273,10 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
         // ===================== X warps: rfft(x) of each segment into the X buffer, one segment ahead of the MAC warps ======
         const int xw = warp - 1 - NM;
         float2* fscr = fscr_all + (size_t)xw * (FC::WARP_SCRATCH_BYTES / 8);
+        ProblemDev P0{};
+        if (s0 < s1) P0 = problems[segs[s0].g];                          // plan data: constant, fetched while the previous grid drains
         pdl_wait();                                                      // x may have been written by the previous grid
         if (s0 < s1) {                                                   // first segment: together with the MAC warps (see there)
-            const ProblemDev P0 = problems[segs[s0].g];
             TSTART(y0);
             load_x_spectrum<B, NT, NM + NX>(P0, 0, xs, tw, fscr, lane, NM + xw);
             asm volatile("bar.sync 1, %0;" ::"r"(32 * (NM + NX)) : "memory");
