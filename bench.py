@@ -236,7 +236,7 @@ def run_ours(args):
     # C ABI's pipelined host call (bcl_forward_grouped_host_pipelined): three streams, the weight sets double as staging
     # slots, so copies of neighbouring steps overlap the kernel.  The host consumes (waits for) a slot's previous result
     # before resubmitting it, so at most len(groups) steps are in flight and every result reaches the host inside the region.
-    n_slots = 4                                               # staging slots (own x/y buffers + plan); slot j streams weight set j % sets
+    n_slots = 4                                               # staging slots (own x/y buffers + plan); slot j streams weight set j % sets (3: 75 us, 6-8: 57-61 us)
     slots = list(groups)
     while len(slots) < n_slots:
         src = groups[len(slots) % len(groups)]
