@@ -22,7 +22,10 @@ namespace rw {
 #endif
 constexpr int NM = 8, NX = 4, NF = BCL_RW_NF, RG = 4;       // NF = 4 and 6 measured slower (32.9, 34.2 us vs 31.5 us: fewer registers, smaller ring)
 constexpr int THREADS = 32 * (1 + NM + NX + NF);
-constexpr int MAX_STAGES = 16;
+#ifndef BCL_RW_MAX_STAGES
+#define BCL_RW_MAX_STAGES 16
+#endif
+constexpr int MAX_STAGES = BCL_RW_MAX_STAGES;
 __host__ __device__ constexpr int stage_blocks(int B) { return 4096 / B; }       // same chunking as bcl_stream_ws.cu
 
 // The row warps drift apart (a warp's consecutive rows are NM rows = up to NM * nst ring chunks and two groups apart), so a warp
@@ -65,6 +68,12 @@ __device__ inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t b
 __device__ inline void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ inline void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+__host__ __device__ inline size_t warp_scratch_bytes(int B) {
+    return B == 64 ? FftCfg<64>::WARP_SCRATCH_BYTES : (B == 128 ? FftCfg<128>::WARP_SCRATCH_BYTES : FftCfg<256>::WARP_SCRATCH_BYTES);
+}
+// the row warps' first-segment FFT scratch fits into X buffer 1
+__host__ __device__ inline bool scratch_aliases_x(int B, int qmax) { return (size_t)qmax * B * 4 >= (size_t)NM * warp_scratch_bytes(B); }
+
 template <int B, typename SpecT>
 __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev* __restrict__ problems, const int* __restrict__ cta_seg_ptr,
                                                               const SegWork* __restrict__ segs, int S, int qmax) {
@@ -83,9 +92,15 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
     float2* tw = reinterpret_cast<float2*>(smem_raw + 512);
     unsigned char* ring = smem_raw + 512 + 1024;
     float* part = reinterpret_cast<float*>(ring + (size_t)S * STAGE_BYTES);                         // [NF][RG][B]: finished row spectra
-    float2* fscr_all = reinterpret_cast<float2*>(part + NF * RG * B);                               // FFT scratch of NM + NX + NF warps
-    float* xs_all = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(fscr_all) + (size_t)(NM + NX + NF) * FC::WARP_SCRATCH_BYTES);   // [2][qmax][B]
+    // FFT scratch: the X warps and the finishers own theirs; the row warps only transform during the cooperative first segment, when X
+    // buffer 1 is still unused (the X warps write it after the bar.sync that ends that phase) -- so their scratch aliases it when it
+    // is large enough, which buys two more ring stages for Llama shapes (9 -> 12 stages was worth 3 us of 34: the ring is what
+    // bounds this kernel).
+    float2* fscr_all = reinterpret_cast<float2*>(part + NF * RG * B);                               // scratch of NX + NF warps (+ NM if not aliased)
+    const bool alias_scr = scratch_aliases_x(B, qmax);
+    float* xs_all = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(fscr_all) + (size_t)(NX + NF + (alias_scr ? 0 : NM)) * FC::WARP_SCRATCH_BYTES);   // [2][qmax][B]
     const size_t xs_stride = (size_t)qmax * B;
+    float2* row_scr = alias_scr ? reinterpret_cast<float2*>(xs_all + xs_stride) : fscr_all + (size_t)(NX + NF) * (FC::WARP_SCRATCH_BYTES / 8);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
@@ -129,7 +144,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
         if (s0 < s1) {                                               // first segment: help with rfft(x) (start-up latency, HBM idles)
             const ProblemDev P0 = problems[segs[s0].g];              // plan data: constant, fetched while the previous grid drains
             pdl_wait();
-            load_x_spectrum<B, NT, NM + NX>(P0, 0, xs_all, tw, fscr_all + (size_t)m * (FC::WARP_SCRATCH_BYTES / 8), lane, m);
+            load_x_spectrum<B, NT, NM + NX>(P0, 0, xs_all, tw, row_scr + (size_t)m * (FC::WARP_SCRATCH_BYTES / 8), lane, m);
             asm volatile("bar.sync 1, %0;" ::"r"(32 * (NM + NX)) : "memory");
         }
         int chunk0 = 0;                                              // ring chunk index of the segment's first chunk (CTA-wide sequence)
@@ -243,7 +258,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
     } else if (warp <= NM + NX) {
         // ===================== X warps: rfft(x) of each segment into the other X buffer, one segment ahead of the row warps ======
         const int xw = warp - 1 - NM;
-        float2* fscr = fscr_all + (size_t)(NM + xw) * (FC::WARP_SCRATCH_BYTES / 8);
+        float2* fscr = fscr_all + (size_t)xw * (FC::WARP_SCRATCH_BYTES / 8);
         ProblemDev P0{};
         if (s0 < s1) P0 = problems[segs[s0].g];                          // plan data: constant, fetched while the previous grid drains
         pdl_wait();                                                      // x may have been written by the previous grid
@@ -262,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
     } else {
         // ===================== finishers =====================
         const int f = warp - 1 - NM - NX;
-        float2* fscr = fscr_all + (size_t)(NM + NX + f) * (FC::WARP_SCRATCH_BYTES / 8);
+        float2* fscr = fscr_all + (size_t)(NX + f) * (FC::WARP_SCRATCH_BYTES / 8);
         pdl_wait();                                                      // y may still be read by the previous grid
         int gi = 0;
         for (int s = s0; s < s1; ++s) {
@@ -284,9 +299,10 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
 }
 
 size_t smem_bytes(int B, int spec_bytes, int qmax, int S) {
-    const size_t fscr = B == 64 ? FftCfg<64>::WARP_SCRATCH_BYTES : (B == 128 ? FftCfg<128>::WARP_SCRATCH_BYTES : FftCfg<256>::WARP_SCRATCH_BYTES);
+    const size_t fscr = warp_scratch_bytes(B);
     const size_t stage = (size_t)stage_blocks(B) * B * spec_bytes;
-    return 512 + 1024 + (size_t)S * stage + (size_t)NF * RG * B * 4 + (size_t)(NM + NX + NF) * fscr + (size_t)2 * qmax * B * 4;
+    const int scr_warps = NX + NF + (scratch_aliases_x(B, qmax) ? 0 : NM);
+    return 512 + 1024 + (size_t)S * stage + (size_t)NF * RG * B * 4 + (size_t)scr_warps * fscr + (size_t)2 * qmax * B * 4;
 }
 
 int pick_stages(int B, int spec_dtype, int nt, int qmax) {
