@@ -41,7 +41,10 @@ constexpr int NF = BCL_WS_NF;                // finisher warps == group buffers 
 #endif
 constexpr int NX = BCL_WS_NX;                // x-spectrum warps
 constexpr int THREADS = 32 * (1 + NM + NX + NF);
-constexpr int MAX_STAGES = 16;
+#ifndef BCL_WS_MAX_STAGES
+#define BCL_WS_MAX_STAGES 16
+#endif
+constexpr int MAX_STAGES = BCL_WS_MAX_STAGES;
 constexpr int PAIRS = 4;                     // rows per group buffer (one finisher warp inverse-transforms up to G = 32/T rows at once)
 // blocks per ring stage: 32 blocks of B=128 (16 KB fp32), 16 of B=256, 64 of B=64 -- always BPS = CB/NM blocks per MAC warp
 __host__ __device__ constexpr int stage_blocks(int B) { return 4096 / B; }
