@@ -128,8 +128,9 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                 for (int r = w.j0; r < w.j1; ++r, rowp += (size_t)q * BLOCK_BYTES) {
                     for (int cs = 0; cs < nst; ++cs, ++idx) {
                         mbar_wait(&bars->empty[stage], ph ^ 1u);          // in order and one phase at a time: parity is enough here
-                        bars->chunk_in[stage] = idx;                     // from now on full[stage] is in this chunk's phase
-                        __threadfence_block();
+                        bars->chunk_in[stage] = idx;                     // from now on full[stage] is in this chunk's phase (the store cannot pass the
+                                                                         // acquiring wait above; nothing else is ordered by it: no fence, the producer
+                                                                         // thread's ~300 cycles per copy are the scarce resource here)
                         const uint32_t bytes = (uint32_t)min(CB, q - cs * CB) * BLOCK_BYTES;
                         mbar_arrive_expect_tx(&bars->full[stage], bytes);
                         bulk_g2s(ring + (size_t)stage * STAGE_BYTES, rowp + (size_t)cs * STAGE_BYTES, bytes, &bars->full[stage]);
