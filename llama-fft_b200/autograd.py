@@ -10,7 +10,7 @@ and both gradients run on the same hand-written CUDA kernels (include/bclinear.h
 
 In grad mode the spectrum is rebuilt on every call (reference rule, src/bench_all_in_one.py:212-219) and always in the fp32
 accuracy class, whatever ``spectrum_dtype`` the layer serves inference with: the CUDA-core stream kernel for a few tokens, the
-split-bf16 tensor-core chain (GEMM layout, spec_dtype f32) from ``PREFILL_MIN_TOKENS_F32`` tokens -- calibration batches are
+split-bf16 tensor-core chain (GEMM layout, spec_dtype f32) from ``prefill_token_floor`` tokens -- calibration batches are
 hundreds to thousands of tokens.  No CPU path: CPU tensors raise.
 """
 from __future__ import annotations
@@ -32,9 +32,9 @@ def _spectrum_f32(c32: torch.Tensor) -> torch.Tensor:
 
 def _forward_f32(x_flat: torch.Tensor, c32: torch.Tensor, bias) -> torch.Tensor:
     """One fp32-class BC forward with a freshly built spectrum of c32 (p, q, B)."""
-    from .patch_llama_fft import bc_forward, PREFILL_MIN_TOKENS_F32
+    from .patch_llama_fft import bc_forward, prefill_token_floor
     p, q, B = c32.shape
-    if x_flat.shape[0] >= PREFILL_MIN_TOKENS_F32:
+    if x_flat.shape[0] >= prefill_token_floor(p, q, torch.float32):
         L = _cabi.lib()
         spec = torch.empty(L.bcl_spectrum_bytes(p, q, B, _cabi.F32, _cabi.LAYOUT_GEMM), device=c32.device, dtype=torch.uint8)
         with torch.cuda.device(c32.device):

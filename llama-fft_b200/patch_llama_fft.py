@@ -25,8 +25,24 @@ MODEL_PATH = os.environ.get("LLAMA_FFT_MODEL_PATH", "Llama-2-7b-hf")
 BLOCK_SIZE = 256
 NUM_LAYERS_TO_PATCH = 1
 
-PREFILL_MIN_TOKENS = int(os.environ.get("BCL_PREFILL_MIN_TOKENS", "256"))   # bf16-spectrum layers switch to the tcgen05 path from here
-PREFILL_MIN_TOKENS_F32 = int(os.environ.get("BCL_PREFILL_MIN_TOKENS_F32", "256"))   # fp32 spectra: split-bf16 tcgen05 GEMM + fp32 FFT stages
+# Where a layer switches from the CUDA-core stream kernel to the tcgen05 path.  Measured per-module on B200 (tools/prefill_vs_dense.py,
+# profiles/r1_prefill_notes.md): the stream kernel costs ~17 us + 1.05e-4 us per (token x block pair), the tensor-core chain a flat
+# ~24 us (bf16 spectra) / ~33 us (fp32 spectra, split operands) up to a few hundred tokens.  So the switch is on WORK, tokens x p x q:
+#   4096->4096 (1024 block pairs): from 64 / 156 tokens;  4096<->11008 (2752 pairs): from 24 / 58 tokens.
+# BCL_PREFILL_MIN_TOKENS / BCL_PREFILL_MIN_TOKENS_F32, when set, replace the rule by a fixed token floor.
+PREFILL_MIN_WORK = 65536            # tokens x p x q, bf16 spectra
+PREFILL_MIN_WORK_F32 = 160000       # fp32 spectra (split-bf16 tcgen05 GEMM + fp32-accurate DFT stages)
+PREFILL_MIN_TOKENS = int(os.environ["BCL_PREFILL_MIN_TOKENS"]) if "BCL_PREFILL_MIN_TOKENS" in os.environ else None
+PREFILL_MIN_TOKENS_F32 = int(os.environ["BCL_PREFILL_MIN_TOKENS_F32"]) if "BCL_PREFILL_MIN_TOKENS_F32" in os.environ else None
+
+
+def prefill_token_floor(p: int, q: int, spectrum_dtype: torch.dtype) -> int:
+    """Tokens per call from which a (p x q)-block layer takes the tensor-core path."""
+    fixed = PREFILL_MIN_TOKENS if spectrum_dtype == torch.bfloat16 else PREFILL_MIN_TOKENS_F32
+    if fixed is not None:
+        return fixed
+    work = PREFILL_MIN_WORK if spectrum_dtype == torch.bfloat16 else PREFILL_MIN_WORK_F32
+    return max(16, -(-work // (p * q)))
 
 MLP_TARGETS = ("gate_proj", "up_proj", "down_proj")
 ATTN_TARGETS = ("q_proj", "k_proj", "v_proj", "o_proj")
@@ -199,8 +215,7 @@ class BlockCirculantLinear(nn.Module):
     def _use_prefill_path(self, n_tokens: int) -> bool:
         """Enough tokens to fill 128-row MMA tiles -> tcgen05 per-frequency GEMM path (bf16 spectra: all three stages on the
         tensor cores; fp32 spectra: split-bf16 GEMM between fp32 CUDA-core FFT stages)."""
-        floor = PREFILL_MIN_TOKENS if self.spectrum_dtype == torch.bfloat16 else PREFILL_MIN_TOKENS_F32
-        return n_tokens >= floor and self.block_size in (64, 128, 256)
+        return n_tokens >= prefill_token_floor(self.out_blocks, self.in_blocks, self.spectrum_dtype) and self.block_size in (64, 128, 256)
 
     # -- forward --------------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -23,3 +23,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+# The tests use small layers; the library switches to the tensor-core path on WORK (tokens x p x q), which such layers only reach at
+# thousands of tokens.  Pin the fixed token floors (the documented override) so that "N >= 256" keeps meaning "tensor-core path" here,
+# in this process and in the child processes some tests start.  tests/test_host_cpu.py checks the work-based rule itself.
+import os  # noqa: E402
+
+os.environ.setdefault("BCL_PREFILL_MIN_TOKENS", "256")
+os.environ.setdefault("BCL_PREFILL_MIN_TOKENS_F32", "256")

@@ -90,12 +90,14 @@ def test_prefill_path_inside_the_model_matches_stream_path():
     model.load_state_dict(gold["state"], strict=True)
     model = model.to("cuda:0").half().eval()
     ids = gold["input_ids"].cuda()
+    old = P.PREFILL_MIN_TOKENS
     with torch.no_grad():
-        a = model(input_ids=ids).logits.float()
-        assert P.prefill_status("cuda:0") == 0
-        old = P.PREFILL_MIN_TOKENS
-        P.PREFILL_MIN_TOKENS = 1 << 30
         try:
+            P.PREFILL_MIN_TOKENS = 256                 # fixed floor: this tiny model's layers are below the work-based switch
+            assert model.model.layers[0].mlp.gate_proj._use_prefill_path(ids.numel())
+            a = model(input_ids=ids).logits.float()
+            assert P.prefill_status("cuda:0") == 0
+            P.PREFILL_MIN_TOKENS = 1 << 30
             b = model(input_ids=ids).logits.float()
         finally:
             P.PREFILL_MIN_TOKENS = old

@@ -343,3 +343,19 @@ def test_legacy_convention_detector():
         assert got == slow(Wr)
         seen.add(got)
     assert seen <= {"diag", "diag_inv"}
+
+
+def test_work_based_switch_to_the_tensor_core_path(monkeypatch):
+    """Without the BCL_PREFILL_MIN_TOKENS* overrides a layer takes the tcgen05 path from a token count that shrinks with its size
+    (stream kernel: ~17 us + 1.05e-4 us per token x block pair; tensor-core chain: flat ~24 / ~33 us)."""
+    import importlib
+    P = importlib.import_module("llama_fft_b200.patch_llama_fft")      # (the package attribute of that name is the function)
+    monkeypatch.setattr(P, "PREFILL_MIN_TOKENS", None)
+    monkeypatch.setattr(P, "PREFILL_MIN_TOKENS_F32", None)
+    assert P.prefill_token_floor(32, 32, torch.bfloat16) == 64 and P.prefill_token_floor(86, 32, torch.bfloat16) == 24
+    assert P.prefill_token_floor(32, 32, torch.float32) == 157 and P.prefill_token_floor(32, 86, torch.float32) == 59
+    assert P.prefill_token_floor(2, 2, torch.bfloat16) == 16384 and P.prefill_token_floor(500, 500, torch.bfloat16) == 16
+    m = bc.BlockCirculantLinear(4096, 4096, block_size=128, bias=False, spectrum_dtype=torch.bfloat16)
+    assert not m._use_prefill_path(63) and m._use_prefill_path(64)
+    monkeypatch.setattr(P, "PREFILL_MIN_TOKENS", 256)                      # the override is a plain token floor
+    assert not m._use_prefill_path(255) and m._use_prefill_path(256)
