@@ -152,7 +152,7 @@ template <typename K, typename... Extra>
 static cudaError_t launch_stage(K kernel, const StageLaunch<DftArgs>& L, int max_ctas, cudaStream_t st, const Extra&... extra) {
     const int grid = L.a.num_items < max_ctas ? L.a.num_items : max_ctas;
     if (grid < 1) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), L.smem);
     if (e != cudaSuccess) return e;
     return launch_pdl(kernel, (unsigned)grid, DFT_THREADS, L.smem, st, L.tm_in, L.tm_w, L.tm_out, extra..., L.a);
 }

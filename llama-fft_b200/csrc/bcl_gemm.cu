@@ -15,6 +15,8 @@
 // The GEMM-layout spectrum (Cmat + the DFT matrices) is built once per parameter version by spectrum_gemm_kernel /
 // dft_matrix_kernel (replaces rfft(c), :256-257).
 #include <mutex>
+#include <map>
+#include <utility>
 #include <cstdlib>
 #include "bcl_stream_parts.cuh"
 #include "bcl_sm100.cuh"
@@ -247,6 +249,21 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> granted;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = granted[std::make_pair(kernel, dev)];
+    if (have >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
+
 bool make_tensor_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
                      const uint32_t* box, CUtensorMapSwizzle swz) {
     EncodeTiledFn fn = encode_fn();
@@ -430,19 +447,24 @@ cudaError_t launch_gemm_mma(const void* Xf, const void* Xf_lo, const void* Cmat,
     if (split) {
         gemm::GemmLoMaps lo;
         if (!gemm::prep_gemm_lo(Xf_lo, Cmat, Yf_lo, g, nc, &lo)) return cudaErrorNotSupported;
-        cudaError_t e = cudaFuncSetAttribute(gemm::freq_gemm_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+        cudaError_t e = gemm::ensure_dynamic_smem(reinterpret_cast<const void*>(gemm::freq_gemm_split_kernel), L.smem);
         if (e != cudaSuccess) return e;
         return gemm::launch_pdl(gemm::freq_gemm_split_kernel, (unsigned)grid, gemm::GEMM_THREADS, L.smem, st, L.tm_in, L.tm_w, L.tm_out, lo, L.a);
     }
-    cudaError_t e = cudaFuncSetAttribute(gemm::freq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    cudaError_t e = gemm::ensure_dynamic_smem(reinterpret_cast<const void*>(gemm::freq_gemm_kernel), L.smem);
     if (e != cudaSuccess) return e;
     return gemm::launch_pdl(gemm::freq_gemm_kernel, (unsigned)grid, gemm::GEMM_THREADS, L.smem, st, L.tm_in, L.tm_w, L.tm_out, L.a);
 }
 
 static int sm_count() {
+    static int cached[64] = {0};                                       // per device; a race only repeats the query
     int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n > 0 ? n : 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return n;
+    if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cached[dev] = n;
+    return n;
 }
 
 // impl: 0 = pick (tensor-core DFT when supported), 1 = CUDA-core FFT kernels, 2 = tensor-core DFT kernels (error if unsupported)

@@ -73,6 +73,10 @@ bool make_chunk_map(CUtensorMap* m, const void* base, int64_t ntok, int slabs, i
 bool make_tensor_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
                      const uint32_t* box, CUtensorMapSwizzle swz);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of on every launch (~1-2 us of host time each;
+// a 256-token forward is three launches and host-bound).  Defined in bcl_gemm.cu.
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes);
+
 // Launch with the programmatic-stream-serialization attribute (PDL): the kernel's prologue overlaps the previous kernel's tail.
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {

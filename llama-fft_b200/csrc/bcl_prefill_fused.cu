@@ -76,7 +76,7 @@ static cudaError_t launch_chain_t(const StageLaunch<DftArgs>& L1, const StageLau
     size_t smem = L1.smem > L2.smem ? L1.smem : L2.smem;
     if (L3.smem > smem) smem = L3.smem;
     auto kern = prefill_chain_kernel<B, SPLIT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
     if (e != cudaSuccess) return e;
     return launch_pdl(kern, (unsigned)ctas, DFT_THREADS, smem, st, L1.tm_in, L1.tm_w, L1.tm_out, L2.tm_in, L2.tm_w, L2.tm_out, L3.tm_in, L3.tm_w, L3.tm_out, lo,
                       L1.a, L2.a, L3.a, grid_ctr);
