@@ -44,12 +44,13 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def config(n_gpus, spec_dtype="float32", weight_sets=2):
+def config(n_gpus, spec_dtype="float32"):
+    """The workload, in the same words for both arms (the driver compares the two `config` objects): per-arm facts (how many
+    weight sets rotate on the GPU, which dtype the CPU arm computes in) live in the arms' own top-level keys."""
     return {"workload": "llama2-7b-decode-b128", "projections_per_step": len(LLAMA7B_LAYER) * N_LAYERS, "layers": N_LAYERS,
-            "block_size": B, "tokens_per_step_per_gpu": 1, "activation_dtype": "float16", "spectrum_dtype": spec_dtype,
-            "weights": "random-init c = randn*0.01 (reference init), %d distinct sets alternating" % weight_sets,
-            "l2_policy": "inputs larger than L2 (%.0f MB of spectra per step, %d sets alternate)" % (
-                algorithmic_bytes(spec_dtype)[1] / 1e6, weight_sets),
+            "block_size": B, "tokens_per_step_per_gpu": 1, "spectrum_dtype": spec_dtype,
+            "weights": "random-init c = randn*0.01 (reference init), distinct per projection (224 matrices)",
+            "l2_policy": "inputs larger than L2 (%.0f MB of spectra per step, all distinct)" % (algorithmic_bytes(spec_dtype)[1] / 1e6),
             "parallelism": "dp%d" % n_gpus}
 
 
@@ -115,22 +116,44 @@ class ClockSampler:
 # CPU reference arm / cpu_baseline: the reference's own CPU path (torch.fft.rfft -> einsum -> irfft), restated in
 # oracle/bc_oracle.py (bit-identical to the reference on the golden vectors), spectra cached like its perf runs.
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(steps, warmup, layers, budget_s=None):
-    """Times the reference CPU path on `layers` of the 32 layers per step (distinct weights), scaled to a full token.
-    Stops early once budget_s seconds of timed work are spent (at least 2 steps).  Returns (s per token, threads, steps run)."""
+def cpu_reference_steps(steps, warmup, budget_s=None):
+    """One decode token through all 224 projections on the host cores, the way the reference's perf runs do it: its own
+    BlockCirculantLinear (src/patch_llama_fft.py:142-275) with enable_cfft_cache (src/bench_all_in_one.py:164-254), fp32, batch 1.
+    The modules are the UNMODIFIED reference imported from oracle/_ref/ (kind "reference"; staged by oracle/make_ref.py); without it
+    the oracle port of the same three torch calls is timed (kind "port").  All 32 layers, distinct weights (207 MB of c + the cached
+    complex spectra).  Stops once budget_s seconds of timed work are spent (at least 2 steps).
+    Returns (s per token, threads, steps run, kind)."""
     import torch
-    from oracle import bc_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(0)
+    from oracle import ref_loader
+    kind = "reference" if ref_loader.available() else "port"
     mods = []
-    for _ in range(layers):
-        for _, inf, outf in LLAMA7B_LAYER:
-            c = torch.randn(outf // B, inf // B, B, generator=g) * 0.01
-            mods.append((O.CachedSpectrum(c), torch.randn(1, 1, inf, generator=g)))      # fp32 on CPU, the reference's CPU default
+    if kind == "reference":
+        plf, bai = ref_loader.load("patch_llama_fft"), ref_loader.load("bench_all_in_one")
+        holder = torch.nn.ModuleList()
+        for _ in range(N_LAYERS):
+            for _, inf, outf in LLAMA7B_LAYER:
+                m = plf.BlockCirculantLinear(inf, outf, block_size=B, bias=False)
+                with torch.no_grad():
+                    m.c.copy_(torch.randn(outf // B, inf // B, B, generator=g) * 0.01)
+                holder.append(m)
+        holder.eval()
+        bai.enable_cfft_cache(holder)
+        mods = [(m, torch.randn(1, 1, m.in_features, generator=g)) for m in holder]
+        call = lambda m, x: m(x)                                                        # noqa: E731
+    else:
+        from oracle import bc_oracle as O
+        for _ in range(N_LAYERS):
+            for _, inf, outf in LLAMA7B_LAYER:
+                c = torch.randn(outf // B, inf // B, B, generator=g) * 0.01
+                mods.append((O.CachedSpectrum(c), torch.randn(1, 1, inf, generator=g)))  # fp32 on CPU, the reference's CPU default
+        call = O.bc_forward_cached_torch
+
     def one_step():
         with torch.inference_mode():
-            for spec, x in mods:
-                O.bc_forward_cached_torch(spec, x)
+            for m, x in mods:
+                call(m, x)
     for _ in range(warmup):
         one_step()
     done = 0
@@ -141,27 +164,30 @@ def cpu_reference_steps(steps, warmup, layers, budget_s=None):
         if budget_s is not None and done >= 2 and time.perf_counter() - t0 > budget_s:
             break
     dt = (time.perf_counter() - t0) / done
-    return dt * (N_LAYERS / layers), torch.get_num_threads(), done          # seconds per full 32-layer token
+    return dt, torch.get_num_threads(), done, kind          # seconds per full 32-layer token
+
+
+CPU_SAMPLE = ("%d timed passes over all 32 layers (224 projections, distinct weights), batch 1, fp32 activations, cached rfft(c) "
+              "(enable_cfft_cache, the reference's perf configuration); %s")
+CPU_KIND_TEXT = {"reference": "the UNMODIFIED reference modules from oracle/_ref (src/patch_llama_fft.py + src/bench_all_in_one.py)",
+                 "port": "oracle/_ref not staged: the oracle port of the reference's CPU path (oracle/bc_oracle.py, torch.fft + einsum)"}
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path (oracle port: it is pure Python + torch, there is
-    nothing to compile) on this box's host cores.  Each step is a bounded sample -- 4 of the 32 layers, 28 projections with
-    distinct weights, scaled x8 -- and the run stops after ~40 s of timed work however large --steps is."""
+    """Reference arm: the reference's own CPU implementation of the path on this box's host cores, all the threads torch will use.
+    A step is one full token (all 224 projections); the run stops after ~40 s of timed work however large --steps is."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    layers = 4
-    sec, cores, done = cpu_reference_steps(args.steps, min(max(args.warmup, 1), 3), layers, budget_s=40.0)
+    sec, cores, done, kind = cpu_reference_steps(args.steps, min(max(args.warmup, 1), 3), budget_s=40.0)
     val = 1.0 / sec
-    sample = ("each step = %d of the 32 layers (%d projections, distinct weights), batch 1, fp32, cached rfft(c), per-token time scaled x%d; "
-              "%d steps timed (40 s budget); reference CPU path restated in oracle/bc_oracle.py (torch.fft + einsum)" % (layers, 7 * layers, N_LAYERS // layers, done))
+    sample = CPU_SAMPLE % (done, CPU_KIND_TEXT[kind])
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config(args.gpus, weight_sets=1),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "dtype": "f32", "data": "synthetic", "config": config(args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "decode_us_per_layer": sec * 1e6 / N_LAYERS, "gpu_launches": 0}
+            "decode_us_per_layer": sec * 1e6 / N_LAYERS, "gpu_launches": 0, "activation_dtype": "float32"}
     print(json.dumps(line))
 
 
@@ -217,19 +243,24 @@ def run_ours(args):
     for i in range(args.warmup):
         groups[i % len(groups)].run()
     barrier()
+    # The timed region is REPEATS back-to-back blocks of exactly --steps steps, each block bracketed by its own CUDA-event pair on the
+    # launching stream, the whole region by barrier + synchronize; per block the max over ranks, then the MEDIAN block (a 20-step
+    # block is 0.8 ms: one event pair alone reads +-4 % from run to run).
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    blocks = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.repeats)]
     with ClockSampler(local) as clk:
-        ev0.record(stream)
-        for i in range(args.steps):
-            groups[i % len(groups)].run()
-        ev1.record(stream)
+        for (b0, b1) in blocks:
+            b0.record(stream)
+            for i in range(args.steps):
+                groups[i % len(groups)].run()
+            b1.record(stream)
         barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    t = torch.tensor([b0.elapsed_time(b1) for (b0, b1) in blocks], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = t.item() / args.steps
-    launches = args.steps
+    block_ms = sorted(t.tolist())
+    ms_step = block_ms[len(block_ms) // 2] / args.steps
+    launches = args.steps * args.repeats
 
     # ---- end to end through the host-buffer entry point ------------------------------------------------------------
     # Every step: H2D of that step's x from pinned memory, one grouped launch, D2H of its y to pinned memory, through the
@@ -310,27 +341,36 @@ def run_ours(args):
             detail["prefill"] = prefill_detail(bc, _cabi, dev)
         except Exception as e:                      # noqa: BLE001 -- evidence only; never hides the headline line
             detail["prefill"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        try:
+            detail["reference_cuda"] = reference_cuda_detail(dev)
+        except Exception as e:                      # noqa: BLE001
+            detail["reference_cuda"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     peak, peak_src = peaks()
     alg, spec_bytes = algorithmic_bytes(args.spectrum)
     achieved = alg / (ms_step * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get("stream_ws_kernel_%s" % args.spectrum)
+    # DRAM bytes per launch of the hot kernel cannot be read without a profiler: the figure is the one ncu --set full capture of
+    # this command committed under profiles/ (newest round first), and `traffic_source` says which file it came from.
+    traffic, traffic_src = None, None
+    for name in ("r2_traffic.json", "traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("stream_ws_kernel_%s" % args.spectrum)
+            if traffic is not None:
+                traffic_src = "profiles/" + name + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+                break
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        sec, cores, done = cpu_reference_steps(6, 1, 4, budget_s=20.0)
-        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d timed passes over 4 of the 32 layers (28 projections, distinct weights), batch 1, fp32, cached rfft(c); "
-                         "per-token time scaled x8; reference CPU path restated in oracle/bc_oracle.py" % done}
+        sec, cores, done, kind = cpu_reference_steps(50, 1, budget_s=15.0)
+        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": kind, "sample": CPU_SAMPLE % (done, CPU_KIND_TEXT[kind])}
     line = {"metric": METRIC, "value": world * 1.0 / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config(world, args.spectrum, args.weight_sets),
-            "decode_us_per_layer": ms_step * 1e3 / N_LAYERS,
+            "dtype": "f32", "data": "synthetic", "config": config(world, args.spectrum),
+            "decode_us_per_layer": ms_step * 1e3 / N_LAYERS, "activation_dtype": "float16", "weight_sets_alternating": args.weight_sets,
+            "timing": {"repeats": args.repeats, "steps_per_block": args.steps, "block_ms_sorted": block_ms, "reported": "median block / steps"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "bcl::ws::stream_ws_kernel<128,%s,3> (warp-specialised TMA/mbarrier pipeline, 1 CTA/SM)" % ("float" if args.spectrum == "float32" else "bf16"),
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "bcl::ws::stream_ws_kernel<128,%s,3> (warp-specialised TMA/mbarrier pipeline, 1 CTA/SM)" % ("float" if args.spectrum == "float32" else "bf16"),
                          "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": world * 1.0 / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
@@ -392,6 +432,17 @@ def launch_granularity_detail(bc, _cabi, grp_all, shapes, dev, args):
         per_module()
     e1.record(stream); torch.cuda.synchronize()
     out["per_module_eager_ms_per_step"] = e0.elapsed_time(e1) / 5
+    # the empty-kernel launch floor under the same graph replay: what 224 / 32 launches cost when they do nothing
+    def noops(n, pdl):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        for _ in range(n):
+            L.bcl_launch_noop(pdl, st)
+    floor_pdl = time_graph(lambda: noops(len(shapes), 1)) / len(shapes) * 1e3
+    floor_plain = time_graph(lambda: noops(len(shapes), 0)) / len(shapes) * 1e3
+    out["launch_floor"] = {"what": "CUDA-graph replay of %d empty kernels (1 CTA x 32 threads) back to back on one stream" % len(shapes),
+                           "empty_kernel_us_per_launch_pdl": floor_pdl, "empty_kernel_us_per_launch_plain": floor_plain,
+                           "per_module_us_per_launch": out["per_module_graph_ms_per_step"] * 1e3 / len(shapes),
+                           "per_layer_grouped_us_per_launch": out["per_layer_grouped_graph_ms_per_step"] * 1e3 / N_LAYERS}
     try:
         out["dependent_chain"] = dependent_chain_detail(bc, _cabi, dev, time_graph)
     except Exception as e:                                               # noqa: BLE001
@@ -399,7 +450,7 @@ def launch_granularity_detail(bc, _cabi, grp_all, shapes, dev, args):
     return out
 
 
-def bf16_decode_detail(bc, _cabi, dev, shapes, args, steps=2000):
+def bf16_decode_detail(bc, _cabi, dev, shapes, args, steps=1000):
     """The headline workload with bf16 spectra (half the bytes, parity class 1e-2): same grouped launch, two weight sets."""
     import torch
     g = torch.Generator(device=dev).manual_seed(4321)
@@ -490,6 +541,48 @@ def dependent_chain_detail(bc, _cabi, dev, time_graph):
 
 
 PREFILL_TOKENS = 8 * 2048          # BASELINE.json configs[2]: 2048-token prefill x batch 8
+
+
+def reference_cuda_detail(dev):
+    """The kernel-level bar of SURVEY 8(d) / BASELINE.md section 4: the UNMODIFIED reference module (oracle/_ref; torch.fft = cuFFT,
+    einsum = cuBLAS complex bmm) on the same B200 and the same shapes, as shipped (rfft(c) on every call, src/patch_llama_fft.py:256-257)
+    and with enable_cfft_cache (src/bench_all_in_one.py:164-254), at decode (1 token) and at the prefill size (16384 tokens).
+    fp16 activations, fp32 parameters -- the reference's Llama configuration (commands.txt:22)."""
+    import torch
+    from oracle import ref_loader
+    if not ref_loader.available():
+        return {"unavailable": "oracle/_ref not staged (python oracle/make_ref.py in the build container)"}
+    plf, bai = ref_loader.load("patch_llama_fft"), ref_loader.load("bench_all_in_one")
+    stream = torch.cuda.current_stream(dev)
+    out = {"what": "reference BlockCirculantLinear on cuda (torch.fft + einsum), us per call; layer = 4 x 4096->4096 + 2 x 4096->11008 + 11008->4096"}
+    torch.manual_seed(0)
+    for n, reps in ((1, 50), (PREFILL_TOKENS, 3)):
+        row = {}
+        for cached in (0, 1):
+            per = {}
+            for inf, outf in ((4096, 4096), (4096, 11008), (11008, 4096)):
+                m = plf.BlockCirculantLinear(inf, outf, block_size=B, bias=False).to(dev).eval()
+                holder = torch.nn.ModuleList([m])
+                if cached:
+                    bai.enable_cfft_cache(holder)
+                x = torch.randn(n, inf, device=dev).half()
+                with torch.inference_mode():
+                    for _ in range(3):
+                        m(x)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    for _ in range(reps):
+                        m(x)
+                    e1.record(stream)
+                    torch.cuda.synchronize()
+                per["%dx%d" % (inf, outf)] = e0.elapsed_time(e1) / reps * 1e3
+                del m, holder, x
+                torch.cuda.empty_cache()
+            per["layer_us"] = 4 * per["4096x4096"] + 2 * per["4096x11008"] + per["11008x4096"]
+            row["cached_rfft_c" if cached else "as_shipped"] = per
+        out["decode_1_token" if n == 1 else "prefill_%d_tokens" % n] = row
+    return out
 
 
 def prefill_algorithmic_bytes(n=PREFILL_TOKENS):
@@ -620,6 +713,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20000)
     ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--repeats", type=int, default=5, help="timed blocks of --steps steps; the median block is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spectrum", default="float32", choices=["float32", "bfloat16"])
     ap.add_argument("--weight-sets", type=int, default=2)

@@ -14,7 +14,9 @@
  *
  * Ownership and threading
  *   Every pointer is caller-owned.  Device pointers unless the name says host.  The library never allocates,
- *   frees or retains memory, keeps no mutable global state besides a thread-local error string, never syncs
+ *   frees or retains caller memory; its only mutable global state is a thread-local error string plus three mutex-guarded /
+ *   write-once caches of facts about the device (dynamic-shared-memory attributes already granted per (kernel, device), the SM
+ *   count per device, environment switches read once) -- nothing that depends on the data of a call.  It never syncs
  *   the device (except the *_host convenience calls, which say so), and every launch goes to the stream that
  *   is passed in (a cudaStream_t cast to void*; NULL = the legacy default stream).  All calls are CUDA-graph
  *   capturable except the *_host ones.  Errors never abort or print: a negative bcl_status is returned and
@@ -30,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BCL_ABI_VERSION 9
+#define BCL_ABI_VERSION 10
 
 typedef enum bcl_dtype { BCL_F32 = 0, BCL_F16 = 1, BCL_BF16 = 2 } bcl_dtype;
 
@@ -79,7 +81,8 @@ int bcl_precompute_spectrum(const float* c, int p, int q, int B,
  *   bias     (out) or NULL
  *   workspace  at least bcl_workspace_bytes(...) bytes, 256-byte aligned (may be NULL when that is 0).  Layout GEMM
  *            stages Xf/Yf of one token chunk there (a larger workspace means larger chunks); its first int is a
- *            status word the call zeroes and the tcgen05 kernel sets non-zero if its pipeline ever stalls.
+ *            status word the call zeroes and the tcgen05 kernels set non-zero if their pipeline ever stalls; its second
+ *            int is STICKY: the code of the first stall since the caller last zeroed it (zero it once after allocating).
  * N == 0 is a no-op.  */
 size_t bcl_workspace_bytes(int64_t N, int p, int q, int B, int spec_dtype, int layout);
 int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
@@ -188,6 +191,13 @@ int bcl_backward_weights(const void* x, int x_dtype, int64_t x_row_stride, const
  * the reference's per-block torch ops round, result stored as float32 (p,q,B). */
 int bcl_project_from_dense(const void* W, int w_dtype, int64_t w_row_stride, int p, int q, int B,
                            float* c, void* stream);
+
+/* ---- measurement aid ----------------------------------------------------------------------------------------------
+ * Launches an EMPTY kernel (1 CTA, 32 threads) on `stream`; pdl != 0 launches it with the programmatic-stream-serialization
+ * attribute the forward kernels use.  bench.py replays graphs of these to print the launch floor next to every
+ * launch-latency-bound figure ("report per-call latency next to the empty-kernel launch floor").
+ * No reference counterpart. */
+int bcl_launch_noop(int pdl, void* stream);
 
 #ifdef __cplusplus
 }

@@ -230,10 +230,13 @@ def main(argv=None):
             if ck and os.path.exists(ck):
                 load_bc_params(model, ck, strict_shapes=True)
                 row["calib_loaded"] = 1
+            model.eval()                                   # swapped-in layers follow the model's mode; the cached spectrum is eval-only
             row["cfft_cached_layers"] = enable_cfft_cache(model)
+            groups = []
             if args.fuse_shared_inputs:
                 from .shared_input import fuse_shared_inputs
                 row["shared_input_groups"] = fuse_shared_inputs(model)
+                groups = list({id(m._shared_group): m._shared_group for m in model.modules() if getattr(m, "_shared_group", None) is not None}.values())
         if B == 0:
             teacher_cache = compute_teacher_last_cache(model, tokenized, device)
         else:
@@ -242,6 +245,8 @@ def main(argv=None):
         if args.do_generate:
             row.update(perf_generate(model, tokenized, device, pad_id, args.batch_size, max(1, args.warmup // 2), max(1, args.runs // 2),
                                      args.max_new_tokens))
+        if B and args.fuse_shared_inputs:
+            row["shared_input_fused_calls"] = sum(g.fused_calls for g in groups)     # > 0: the fused path really served the forwards
         if B == 0:
             dense_row = row
         else:

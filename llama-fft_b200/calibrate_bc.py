@@ -36,10 +36,22 @@ def pick_input_device(m: nn.Module) -> torch.device:
     return next(m.parameters()).device
 
 
+def default_prompts_file() -> str:
+    """The reference defaults to ``prompts_100.txt`` next to the script (src/calibrate_bc.py:113).  Its prompt files are data of the
+    reference repo and are not shipped here: a copy placed next to this module is picked up, otherwise the synthetic prompt set that
+    ships with this repo (tools/prompts_synthetic.txt) is the default."""
+    here = Path(__file__).resolve()
+    for cand in (here.with_name("prompts_100.txt"), here.parent.parent / "tools" / "prompts_synthetic.txt"):
+        if cand.exists():
+            return str(cand)
+    return str(here.with_name("prompts_100.txt"))
+
+
 def load_texts(path: Path, limit: int) -> List[str]:
     path = Path(path)
     if not path.exists():
-        raise FileNotFoundError(f"Prompts file not found: {path}")
+        raise FileNotFoundError(f"Prompts file not found: {path} (pass --prompts_file; the reference's src/prompts_*.txt are not shipped "
+                                f"with this package, tools/prompts_synthetic.txt is)")
     lines = (ln.strip() for ln in path.read_text(encoding="utf-8").splitlines())
     texts = [ln for ln in lines if ln and not ln.startswith("#")][:limit]
     if not texts:
@@ -172,7 +184,7 @@ def _load_causal_lm(model_path: str, device: torch.device, dtype: torch.dtype):
 
 def build_parser() -> argparse.ArgumentParser:
     ap = argparse.ArgumentParser(description="Calibrate block-circulant layers against the dense teacher (B200 kernels).")
-    ap.add_argument("--prompts_file", type=str, default=str(Path(__file__).with_name("prompts_100.txt")))
+    ap.add_argument("--prompts_file", type=str, default=default_prompts_file())
     ap.add_argument("--limit", type=int, default=50)
     ap.add_argument("--block_sizes", type=str, default="64,128,256")
     ap.add_argument("--num_layers_to_patch", type=int, default=1)

@@ -52,9 +52,28 @@ int check_problem(const void* x, int x_dtype, int64_t N, int64_t xs, const void*
     return BCL_OK;
 }
 
+__global__ void noop_kernel() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 }  // namespace
 
 extern "C" {
+
+int bcl_launch_noop(int pdl, void* stream) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(32);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, noop_kernel);
+    return e == cudaSuccess ? BCL_OK : cuda_fail(e, "noop launch");
+}
 
 int bcl_abi_version(void) { return BCL_ABI_VERSION; }
 

@@ -507,7 +507,7 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
     if (split) {
         unsigned char* Xf_lo = Xf + xfb;
         unsigned char* Yf_lo = Yf + yfb;
-        cudaError_t e = cudaMemsetAsync(status, 0, kWsHeader, st);
+        cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int), st);
         if (e != cudaSuccess) return e;
         const int ctas = sm_count();
         static const int impl_s = getenv("BCL_PREFILL_DFT") ? atoi(getenv("BCL_PREFILL_DFT")) : 0;   // 1: force the CUDA-core FFT stages
@@ -538,11 +538,12 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
     const bool tc_ok = impl != 1 && spec_gemm != nullptr && gemm::dft_tc_supported(B, P.x_dtype) && P.y_dtype == P.x_dtype && P.n_extra == 0;
     if (tc_ok && B <= 128 && ncmax >= P.N && fused_min_tiles > 0 && (P.N + gemm::TILE_M - 1) / gemm::TILE_M >= fused_min_tiles && ctas >= 12) {
         // one launch: the three stages pipelined tile by tile over L2-resident Xf / Yf (bcl_prefill_fused.cu)
-        cudaError_t e = cudaMemsetAsync(ws, 0, kWsHeader + ctr_bytes, st);
+        cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int), st);                       // (status[1] is sticky: never cleared here)
+        if (e == cudaSuccess) e = cudaMemsetAsync(ws + kWsHeader, 0, ctr_bytes, st);
         if (e != cudaSuccess) return e;
         return gemm::launch_prefill_fused(P, g, spec_gemm, Xf, Yf, status, reinterpret_cast<int*>(ws + kWsHeader), ctas, st);
     }
-    cudaError_t e = cudaMemsetAsync(status, 0, kWsHeader, st);
+    cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     for (int64_t n0 = 0; n0 < P.N; n0 += ncmax) {
         const int nc = (int)((P.N - n0 < ncmax) ? (P.N - n0) : ncmax);

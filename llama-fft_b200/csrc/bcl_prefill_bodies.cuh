@@ -260,13 +260,13 @@ __device__ __forceinline__ void freq_gemm_body(unsigned char* gemm_smem, const C
             for (int blk = first * C; blk < a.num_items; blk += stride * C) for (int item = blk; item < min(blk + C, a.num_items); ++item, ++pit) {
                 int fg, m, nch; decode_item(a, item, fg, m, nch);
                 if (m != m_ready) {                                              // fused launch: Xf of this tile complete?
-                    if (!deps_wait_tile(a.deps, m)) { atomicExch(a.status, 5); goto done; }
+                    if (!deps_wait_tile(a.deps, m)) { set_status(a.status, 5); goto done; }
                     m_ready = m;
                 }
                 BCL_TRACE(0, pit);
                 for (int fl = 0; fl < 4; ++fl) {
                     for (int ka = 0; ka < a.k_atoms; ++ka) {
-                        if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 1); goto done; }
+                        if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { set_status(a.status, 1); goto done; }
                         unsigned char* sa = ring + (size_t)stage * STAGE;
                         mbar_arrive_expect_tx(&bars->full[stage], STAGE);
                         tma_load_4d_hint(sa, &tmA, 0, m * (TILE_M / TOK_GROUP), ka * 8, 4 * fg + fl, &bars->full[stage], L2_EVICT_FIRST);   // read once
@@ -287,13 +287,13 @@ __device__ __forceinline__ void freq_gemm_body(unsigned char* gemm_smem, const C
             int stage = 0; uint32_t ph = 0; int it = 0;
             for (int blk = first * C; blk < a.num_items; blk += stride * C) for (int item = blk; item < min(blk + C, a.num_items); ++item, ++it) {
                 const int set = it & 1; const uint32_t set_ph = (uint32_t)(it >> 1) & 1u;
-                if (!mbar_wait(&bars->tmem_empty[set], set_ph ^ 1u)) { atomicExch(a.status, 2); goto done; }   // epilogue drained this set
+                if (!mbar_wait(&bars->tmem_empty[set], set_ph ^ 1u)) { set_status(a.status, 2); goto done; }   // epilogue drained this set
                 tc_fence_after_sync();
                 BCL_TRACE(2, it);
                 for (int fl = 0; fl < 4; ++fl) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)(set * SET_COLS + fl * NCHUNK);
                     for (int ka = 0; ka < a.k_atoms; ++ka) {
-                        if (!mbar_wait(&bars->full[stage], ph)) { atomicExch(a.status, 3); goto done; }
+                        if (!mbar_wait(&bars->full[stage], ph)) { set_status(a.status, 3); goto done; }
                         tc_fence_after_sync();
                         const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE);
                         const uint64_t bdesc = umma_desc_k_sw128(sa + A_STAGE_BYTES);
@@ -330,7 +330,7 @@ __device__ __forceinline__ void freq_gemm_body(unsigned char* gemm_smem, const C
             const int set = it & 1; const uint32_t set_ph = (uint32_t)(it >> 1) & 1u;
             if (a.deps.done_ctr != nullptr && !__all_sync(0xffffffffu, epi_idle_poll(&bars->tmem_full[set], set_ph)) && lane == 0)
                 done_trk.flush(sig);                                 // about to idle: publish what is finished
-            if (!__all_sync(0xffffffffu, mbar_wait(&bars->tmem_full[set], set_ph))) { atomicExch(a.status, 4); goto done; }
+            if (!__all_sync(0xffffffffu, mbar_wait(&bars->tmem_full[set], set_ph))) { set_status(a.status, 4); goto done; }
             tc_fence_after_sync();
             if (warp == 2 && lane == 0) BCL_TRACE(5, it);
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * SET_COLS);
@@ -507,13 +507,13 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
             for (int blk = first * C; blk < a.num_items; blk += stride * C) for (int item = blk; item < min(blk + C, a.num_items); ++item, ++pit) {
                 const int kg = item % a.groups, m = item / a.groups;
                 if (m != m_ready) {                                              // fused launch: back-pressure from the frequency GEMM
-                    if (!deps_wait_tile(a.deps, m)) { atomicExch(a.status, 16); goto done; }
+                    if (!deps_wait_tile(a.deps, m)) { set_status(a.status, 16); goto done; }
                     m_ready = m;
                 }
                 BCL_TRACE(0, pit);
                 for (int ibp = 0; ibp < 4 * PARTS; ++ibp) {                      // (input block, K part)
                     const int ib = ibp / PARTS, part = ibp % PARTS;
-                    if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 11); goto done; }
+                    if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { set_status(a.status, 11); goto done; }
                     unsigned char* sa = ring + (size_t)stage * STAGE;
                     mbar_arrive_expect_tx(&bars->full[stage], STAGE);
                     for (int at = 0; at < APP; ++at)                             // columns past in_features are zero-filled
@@ -532,15 +532,15 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
             // in registers make the epilogue slower than the overlap gains.  The epilogue itself sits at the TMEM read rate
             // (64 B/clk/SM: 256 KB of fp32 accumulators per item = 4.1k cycles).
             const uint32_t idesc = umma_idesc_16(TILE_M, NB, a.act_bf16);
-            if (!mbar_wait(&bars->wfull, 0)) { atomicExch(a.status, 12); goto done; }
+            if (!mbar_wait(&bars->wfull, 0)) { set_status(a.status, 12); goto done; }
             int stage = 0; uint32_t ph = 0; int it = 0;
             for (int blk = first * C; blk < a.num_items; blk += stride * C) for (int item = blk; item < min(blk + C, a.num_items); ++item, ++it) {
-                if (!mbar_wait(&bars->tmem_empty[0], ((uint32_t)it & 1u) ^ 1u)) { atomicExch(a.status, 13); goto done; }
+                if (!mbar_wait(&bars->tmem_empty[0], ((uint32_t)it & 1u) ^ 1u)) { set_status(a.status, 13); goto done; }
                 tc_fence_after_sync();
                 BCL_TRACE(2, it);
                 for (int ibp = 0; ibp < 4 * PARTS; ++ibp) {                      // (input block, K part)
                     const int ib = ibp / PARTS, part = ibp % PARTS;
-                    if (!mbar_wait(&bars->full[stage], ph)) { atomicExch(a.status, 14); goto done; }
+                    if (!mbar_wait(&bars->full[stage], ph)) { set_status(a.status, 14); goto done; }
                     tc_fence_after_sync();
                     if (ibp == 0) BCL_TRACE(3, it);
                     const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE), sw = smem_u32(wsm);
@@ -574,7 +574,7 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
             const int kg = item % a.groups, m = item / a.groups;
             if (a.deps.done_ctr != nullptr && !__all_sync(0xffffffffu, epi_idle_poll(&bars->tmem_full[0], (uint32_t)it & 1u)) && lane == 0)
                 done_trk.flush(sig);                                             // about to idle: publish what is finished
-            if (!__all_sync(0xffffffffu, mbar_wait(&bars->tmem_full[0], (uint32_t)it & 1u))) { atomicExch(a.status, 15); goto done; }
+            if (!__all_sync(0xffffffffu, mbar_wait(&bars->tmem_full[0], (uint32_t)it & 1u))) { set_status(a.status, 15); goto done; }
             tc_fence_after_sync();
             if (warp == 2 && lane == 0) BCL_TRACE(5, it);
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -731,12 +731,12 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
             for (int blk = first * C; blk < a.num_items; blk += stride * C) for (int item = blk; item < min(blk + C, a.num_items); ++item, ++pit) {
                 const int j = item % a.groups, m = item / a.groups;
                 if (m != m_ready) {                                              // fused launch: Yf of this tile complete?
-                    if (!deps_wait_tile(a.deps, m)) { atomicExch(a.status, 26); goto done; }
+                    if (!deps_wait_tile(a.deps, m)) { set_status(a.status, 26); goto done; }
                     m_ready = m;
                 }
                 BCL_TRACE(0, pit);
                 for (int part = 0; part < PARTS; ++part) {
-                    if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { atomicExch(a.status, 21); goto done; }
+                    if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { set_status(a.status, 21); goto done; }
                     mbar_arrive_expect_tx(&bars->full[stage], STAGE);
                     tma_load_4d_hint(ring + (size_t)stage * STAGE, &tmYf, 0, m * (TILE_M / TOK_GROUP), j, part * FG, &bars->full[stage], L2_EVICT_FIRST);
                     if constexpr (SPLIT)
@@ -748,14 +748,14 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(TILE_M, NB);
-            if (!mbar_wait(&bars->wfull, 0)) { atomicExch(a.status, 22); goto done; }
+            if (!mbar_wait(&bars->wfull, 0)) { set_status(a.status, 22); goto done; }
             int stage = 0; uint32_t ph = 0; int it = 0;
             for (int blk = first * C; blk < a.num_items; blk += stride * C) for (int item = blk; item < min(blk + C, a.num_items); ++item, ++it) {
                 const int acc = it % NACC; const uint32_t acc_ph = (uint32_t)(it / NACC) & 1u;
-                if (!mbar_wait(&bars->tmem_empty[acc], acc_ph ^ 1u)) { atomicExch(a.status, 23); goto done; }
+                if (!mbar_wait(&bars->tmem_empty[acc], acc_ph ^ 1u)) { set_status(a.status, 23); goto done; }
                 BCL_TRACE(2, it);
                 for (int part = 0; part < PARTS; ++part) {
-                    if (!mbar_wait(&bars->full[stage], ph)) { atomicExch(a.status, 24); goto done; }
+                    if (!mbar_wait(&bars->full[stage], ph)) { set_status(a.status, 24); goto done; }
                     tc_fence_after_sync();
                     if (part == 0) BCL_TRACE(3, it);
                     const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE), sw = smem_u32(wsm);
@@ -790,7 +790,7 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
             const int acc = it % NACC; const uint32_t acc_ph = (uint32_t)(it / NACC) & 1u;
             if (a.deps.done_ctr != nullptr && !__all_sync(0xffffffffu, epi_idle_poll(&bars->tmem_full[acc], acc_ph)) && lane == 0)
                 done_trk.flush(sig);                                 // about to idle: publish what is finished
-            if (!__all_sync(0xffffffffu, mbar_wait(&bars->tmem_full[acc], acc_ph))) { atomicExch(a.status, 25); goto done; }
+            if (!__all_sync(0xffffffffu, mbar_wait(&bars->tmem_full[acc], acc_ph))) { set_status(a.status, 25); goto done; }
             tc_fence_after_sync();
             if (warp == 2 && lane == 0) BCL_TRACE(5, it);
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * NB);

@@ -59,9 +59,9 @@ prefill_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         dft_fwd_body<B, SPLIT>(chain_smem, tmX, tmWf, tmXfS, SPLIT ? &lo.fwd : nullptr, a, b, n);
         __syncthreads();
     }
-    if (!grid_barrier(grid_ctr, n)) { if (threadIdx.x == 0) atomicExch(a1.status, 31); return; }
+    if (!grid_barrier(grid_ctr, n)) { if (threadIdx.x == 0) set_status(a1.status, 31); return; }
     freq_gemm_body<SPLIT>(chain_smem, tmXfL, tmC, tmYfS, SPLIT ? &lo.gemm : nullptr, a2, b, n);
-    if (!grid_barrier(grid_ctr, 2 * n)) { if (threadIdx.x == 0) atomicExch(a1.status, 32); return; }
+    if (!grid_barrier(grid_ctr, 2 * n)) { if (threadIdx.x == 0) set_status(a1.status, 32); return; }
     for (int h = 0; h < HALVES; ++h) {
         DftArgs a = a3;
         a.half = h;

@@ -58,6 +58,13 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* b, uint32_t parity) {
     return mbar_wait_slow(addr, parity);
 }
 
+// Pipeline-stall report.  status[0] = code of the last stall of the current call (the host clears it per call), status[1] = code of
+// the FIRST stall since the caller zeroed the workspace header (sticky: a later, healthy call does not erase the evidence).
+__device__ __forceinline__ void set_status(int* status, int code) {
+    atomicExch(status, code);
+    atomicCAS(status + 1, 0, code);
+}
+
 // ---- programmatic dependent launch ------------------------------------------------------------------------------
 // launch_dependents: the next grid of the stream may start on SMs this grid has left.  wait: block until the previous
 // grid has completed and its memory is visible -- call before the first access to anything it may have produced or still read.

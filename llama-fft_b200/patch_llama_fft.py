@@ -153,6 +153,7 @@ class BlockCirculantLinear(nn.Module):
         self._spec: Optional[torch.Tensor] = None          # STREAM layout (decode / small N)
         self._spec_gemm: Optional[torch.Tensor] = None     # GEMM layout (tcgen05 prefill path)
         self._spec_key = None
+        self._cache_spectrum = True                        # False after disable_cfft_cache(): rfft(c) is recomputed on every forward
         self._shared_group = None                          # shared_input.SharedInputGroup when fused with siblings (q/k/v, gate/up)
 
     def extra_repr(self) -> str:
@@ -170,6 +171,9 @@ class BlockCirculantLinear(nn.Module):
             layer.c.copy_(_project_weight(linear.weight.data, block_size))
             if layer.bias is not None and linear.bias is not None:
                 layer.bias.copy_(linear.bias.data)
+        # A swapped-in module must behave like the one it replaces: a model that was put in eval() before patching stays in eval
+        # (otherwise the cached spectrum and the shared-input groups would never be used: both are eval / no-grad only).
+        layer.train(linear.training)
         return layer
 
     # -- spectrum lifecycle ---------------------------------------------------------------------------------
@@ -181,7 +185,10 @@ class BlockCirculantLinear(nn.Module):
         """rfft(c) on c's device (replaces reference :256-257 / the _Cf_cache of src/bench_all_in_one.py:204-219), in the
         STREAM layout (decode kernel) or the GEMM layout (tcgen05 prefill kernels; fp32 spectra -> split bf16 pairs).  Re-used until c is
         written to (its version counter moves), moved, or re-typed -- so load_bc_params / optimizer steps invalidate
-        it, which the reference's cache key does not."""
+        it, which the reference's cache key does not.
+        Writes that bypass autograd's version counter (``layer.c.data.copy_(...)``, ``layer.c.data[j, i] = ...`` as the reference's own
+        from_linear does, :214-219) are NOT seen: call ``drop_spectrum()`` after them, or ``disable_cfft_cache(model)`` to get the
+        reference's default behaviour (rfft(c) recomputed on every forward)."""
         key = self._spectrum_key()
         if self._spec_key != key:
             self._spec, self._spec_gemm, self._spec_key = None, None, key
@@ -242,7 +249,7 @@ class BlockCirculantLinear(nn.Module):
             y_flat = bc_linear_autograd(self, x_flat)
         else:
             # reference rule (src/bench_all_in_one.py:212-219): a cached spectrum is served only in eval/no-grad
-            reuse = (not self.training) and (not torch.is_grad_enabled())
+            reuse = (not self.training) and (not torch.is_grad_enabled()) and self._cache_spectrum
             if reuse and self._shared_group is not None:
                 # siblings reading the same activation (q/k/v, gate/up): one fused forward, this layer's column slice
                 y_flat = self._shared_group.member_forward(self, x_flat)
@@ -256,17 +263,29 @@ class BlockCirculantLinear(nn.Module):
         return y_flat
 
 
-_workspaces: Dict[str, torch.Tensor] = {}
+_workspaces: Dict[tuple, torch.Tensor] = {}      # (device index, raw stream) -> staging buffer of the GEMM-layout path
+_captured_workspaces: list = []                   # buffers a CUDA graph may still point at: kept alive for the process lifetime
+WS_HEADER = 256
 
 
 def prefill_workspace(device, nbytes: int) -> torch.Tensor:
-    """Per-device staging buffer of the GEMM-layout path (Xf/Yf of one token chunk); grows, never shrinks.  Kernels of
-    one stream run in order, so one buffer per device serves every layer."""
-    key = str(device)
+    """Staging buffer of the GEMM-layout path (status words + Xf/Yf of one token chunk) for the CURRENT stream of `device`;
+    grows, never shrinks.  Kernels of one stream run in order, so one buffer per (device, stream) serves every layer; forwards on
+    different streams get different buffers and cannot race on Xf / Yf / the status words.  A buffer that was handed out while the
+    stream was capturing a CUDA graph is never freed (the graph keeps its address): growing allocates a new one next to it."""
+    dev = device if isinstance(device, torch.device) else torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (idx, _cabi.stream_ptr(dev))
+    capturing = torch.cuda.is_current_stream_capturing()
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(nbytes, device=device, dtype=torch.uint8)
+        if ws is not None and getattr(ws, "_bcl_captured", False):
+            _captured_workspaces.append(ws)
+        ws = torch.empty(max(nbytes, WS_HEADER), device=dev, dtype=torch.uint8)
+        ws[:WS_HEADER].zero_()                          # status words: [0] per call, [1] sticky (include/bclinear.h)
         _workspaces[key] = ws
+    if capturing:
+        ws._bcl_captured = True
     return ws
 
 
@@ -301,10 +320,21 @@ def bc_forward(x_flat: torch.Tensor, spec: torch.Tensor, bias: Optional[torch.Te
     return y
 
 
-def prefill_status(device) -> int:
-    """Status word of the last GEMM-layout forward on `device` (0 = the tcgen05 pipeline never stalled).  Synchronises."""
-    ws = _workspaces.get(str(device))
-    return 0 if ws is None else int(ws[:4].view(torch.int32).item())
+def prefill_status(device, *, sticky: bool = True) -> int:
+    """Pipeline status of the GEMM-layout forwards on `device` (0 = no tcgen05 pipeline wait ever timed out).  Synchronises.
+    sticky=True: the first stall recorded in ANY workspace of the device since it was allocated (a later healthy call does not
+    erase it); sticky=False: the per-call word of the most recent forward on the current stream."""
+    dev = device if isinstance(device, torch.device) else torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if not sticky:
+        ws = _workspaces.get((idx, _cabi.stream_ptr(dev)))
+        return 0 if ws is None else int(ws[:4].view(torch.int32).item())
+    for (d, _), ws in list(_workspaces.items()) + [((w.device.index, 0), w) for w in _captured_workspaces]:
+        if d == idx:
+            words = ws[:8].view(torch.int32).tolist()
+            if words[1] or words[0]:
+                return int(words[1] or words[0])
+    return 0
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -316,6 +346,7 @@ def enable_cfft_cache(model: nn.Module) -> int:
     n = 0
     for m in model.modules():
         if isinstance(m, BlockCirculantLinear):
+            m._cache_spectrum = True
             if m.c.is_cuda:
                 m.build_spectrum()
             n += 1
@@ -323,10 +354,14 @@ def enable_cfft_cache(model: nn.Module) -> int:
 
 
 def disable_cfft_cache(model: nn.Module) -> int:
+    """Reference semantics (src/bench_all_in_one.py:239-254): back to the module's own forward, which transforms c on EVERY call
+    (src/patch_llama_fft.py:256-257).  Drops the cached spectra and makes every later forward rebuild them, so that writes the
+    version counter cannot see (``c.data`` updates) are always picked up.  Returns the number of BC layers."""
     n = 0
     for m in model.modules():
         if isinstance(m, BlockCirculantLinear):
             m.drop_spectrum()
+            m._cache_spectrum = False
             n += 1
     return n
 

@@ -82,6 +82,11 @@ class ShardedBlockCirculantLinear(nn.Module):
                     loc.bias.data = full.bias.detach()[j0 * B:j1 * B].clone()
             self.local = loc.eval() if not full.training else loc
         self._symm = None       # (N, dtype) -> (symmetric y buffer, peer views) for exchange="p2p"
+        self._bias_dtype = None if full.bias is None else full.bias.dtype     # known on EVERY rank, with or without local rows
+
+    def y_dtype(self, x_dtype: torch.dtype) -> torch.dtype:
+        """Output dtype of the full layer (reference :266-271: x.dtype, promoted with the bias dtype), the same on every rank."""
+        return x_dtype if self._bias_dtype is None else torch.promote_types(x_dtype, self._bias_dtype)
 
     # -- p2p: y lives in symmetric memory; each rank's kernels write their slice into every peer's copy ------------
     def _symmetric_y(self, N: int, dtype: torch.dtype, device):
@@ -107,11 +112,11 @@ class ShardedBlockCirculantLinear(nn.Module):
         if self.exchange == "nccl":
             if self.local is not None:
                 y_loc = self.local(x)
-            else:
-                y_loc = x.new_empty(N, 0)
+            else:                                           # a rank without rows still joins the collective, in the dtype the others produce
+                y_loc = torch.empty(N, 0, device=x.device, dtype=self.y_dtype(x.dtype))
             y = gather_columns(y_loc, self.ranges, B, self.group)
         else:
-            y_dtype = x.dtype if (self.local is None or self.local.bias is None) else torch.promote_types(x.dtype, self.local.bias.dtype)
+            y_dtype = self.y_dtype(x.dtype)
             y, peers = self._symmetric_y(N, y_dtype, x.device)
             hdl = self._symm[3]
             hdl.barrier()                                   # peers finished reading the previous contents

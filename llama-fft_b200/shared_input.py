@@ -53,6 +53,7 @@ class SharedInputGroup:
         self._bias = None
         self._key = None
         self._pending = None       # (x kept alive, key, fused y, members still to read it)
+        self.fused_calls = 0       # forward_all launches (tests / the bench assert that the fused path really ran)
 
     # -- fused parameters -----------------------------------------------------------------------------------
     def _members_key(self):
@@ -92,6 +93,7 @@ class SharedInputGroup:
     def forward_all(self, x_flat: torch.Tensor) -> torch.Tensor:
         """(N, in) -> (N, sum of the members' out_features); member m owns columns offsets[m]:offsets[m+1]."""
         m0 = self.members[0]
+        self.fused_calls += 1
         layout = _cabi.LAYOUT_GEMM if m0._use_prefill_path(x_flat.shape[0]) else _cabi.LAYOUT_STREAM
         spec = self.build_spectrum(layout)
         return bc_forward(x_flat, spec, self._bias, self.out_blocks, self.in_blocks, self.block_size, layout=layout,
@@ -99,7 +101,9 @@ class SharedInputGroup:
 
     @staticmethod
     def _x_key(x_flat: torch.Tensor):
-        return (x_flat.data_ptr(), x_flat._version, tuple(x_flat.shape), tuple(x_flat.stride()), x_flat.dtype, str(x_flat.device),
+        # inference tensors (torch.inference_mode, which every eval function of the reference's bench uses) carry no version counter
+        version = None if x_flat.is_inference() else x_flat._version
+        return (x_flat.data_ptr(), version, tuple(x_flat.shape), tuple(x_flat.stride()), x_flat.dtype, str(x_flat.device),
                 torch.cuda.current_stream(x_flat.device).cuda_stream)
 
     def member_forward(self, member: BlockCirculantLinear, x_flat: torch.Tensor) -> torch.Tensor:

@@ -69,7 +69,7 @@ def main():
     valid = (torch.arange(T - 1)[None, :] < (lens - 1)[:, None])
     nll = (tok_nll * valid).sum() / valid.sum()
     out = dict(config=CFG, block_size=B, state={k: v.clone() for k, v in model.state_dict().items()}, input_ids=ids, lengths=lens,
-               logits=logits.half(), last_logits=last, nll=nll, n_bc=sum(isinstance(m, plf.BlockCirculantLinear) for m in model.modules()))
+               logits=logits, last_logits=last, nll=nll, n_bc=sum(isinstance(m, plf.BlockCirculantLinear) for m in model.modules()))
     path = os.path.join(HERE, "e2e_tiny_llama.pt")
     torch.save(out, path)
     print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB, {len(lines)} prompts, nll {nll.item():.6f}, ppl {nll.exp().item():.3f}, BC layers {out['n_bc']}")

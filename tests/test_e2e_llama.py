@@ -69,7 +69,8 @@ def test_logits_and_perplexity_match_reference(sdt, tol_logit, tol_nll):
     valid = mask.bool()
     scale = ref[valid].abs().max().item()
     err = (logits - ref)[valid].abs().max().item() / scale
-    assert err <= tol_logit + 1e-3 * (gold["logits"].dtype == torch.float16), f"logit rel err {err:.3e}"
+    assert gold["logits"].dtype == torch.float32                      # the fixture stores the reference's logits unrounded
+    assert err <= tol_logit, f"logit rel err {err:.3e}"
     last = logits[torch.arange(len(lens)), lens - 1]
     assert (last.argmax(-1) == gold["last_logits"].argmax(-1)).float().mean().item() >= (1.0 if sdt == torch.float32 else 0.9)
     logp = torch.log_softmax(logits[:, :-1], dim=-1)

@@ -23,5 +23,6 @@ def test_bench_all_in_one_cli_on_tiny_random_init_llama(tmp_path):
         assert r["bc_layers"] == 14 and r["cfft_cached_layers"] == 14 and r["last_mse"] > 0 and r["prefill_tokens_per_s"] > 0
     fused = bai.main(common + ["--fuse_shared_inputs", "1"])
     assert fused[1]["shared_input_groups"] == 4
+    assert all(r["shared_input_fused_calls"] > 0 for r in fused[1:])       # under torch.inference_mode, layers in eval mode: the group path ran
     for a, b in zip(rows[1:], fused[1:]):                 # fusion is bit-exact: identical quality metrics
         assert a["last_mse"] == b["last_mse"] and a["last_kl"] == b["last_kl"]

@@ -316,7 +316,8 @@ def test_prefill_chunking_small_workspace_and_full_size_properties():
     assert int(ws[:4].view(torch.int32).item()) == 0
     lin = (y12.float() - (y1.float() + y2.float())).abs().max().item()
     assert lin <= 2e-2 * y12.float().abs().max().item()
-    rows = torch.tensor([0, 127, 128, 895, 896, 897, 8000, 16383, 16384, N - 1])
+    rows = torch.unique(torch.cat([torch.tensor([0, 127, 128, 895, 896, 897, 8000, 16383, 16384, N - 1]),
+                                   torch.randint(0, N, (256,), generator=torch.Generator().manual_seed(N))]))      # tile / chunk edges + 256 random rows
     y_ref = O.bc_forward_torch(c, x1[rows].cpu())
     assert_close(y1[rows], y_ref, 1e-2, torch.float16)
     with torch.no_grad():
@@ -499,7 +500,8 @@ def test_split_prefill_chunked_workspace_full_size():
     _cabi.check(rc, "bcl_forward")
     torch.cuda.synchronize()
     assert int(ws[:4].view(torch.int32).item()) == 0
-    rows = torch.tensor([0, 127, 128, 895, 896, 897, 8000, 16383, 16384, N - 1])
+    rows = torch.unique(torch.cat([torch.tensor([0, 127, 128, 895, 896, 897, 8000, 16383, 16384, N - 1]),
+                                   torch.randint(0, N, (256,), generator=torch.Generator().manual_seed(N))]))      # tile / chunk edges + 256 random rows
     assert_close(y[rows], O.bc_forward_torch(c, x[rows].cpu()), 1e-4)
     with torch.no_grad():
         assert torch.equal(m(x), y)                                                        # unchunked == chunked, deterministic
@@ -562,3 +564,38 @@ torch.save(res, out)
     assert outs["launches"].keys() == outs["chain"].keys()
     for k in outs["launches"]:
         assert torch.equal(outs["launches"][k], outs["chain"][k]), k
+
+
+def test_workspace_is_per_stream_survives_capture_and_status_is_sticky():
+    """one staging buffer per (device, stream); a buffer handed out during CUDA-graph capture is kept alive when a larger
+    call regrows the workspace, so replaying the graph still writes into memory it owns; the status word pair is (per call, sticky)."""
+    import importlib
+    P = importlib.import_module("llama_fft_b200.patch_llama_fft")
+    torch.manual_seed(11)
+    m = bc.BlockCirculantLinear(512, 512, block_size=128, bias=False, spectrum_dtype=torch.bfloat16).to(DEV).eval()
+    x_small = torch.randn(256, 512, device=DEV).half()
+    x_big = torch.randn(2048, 512, device=DEV).half()
+    side = torch.cuda.Stream(DEV)
+    with torch.no_grad():
+        y_ref = m(x_small).clone()
+        with torch.cuda.stream(side):
+            m(x_small)                                                # warm-up on the side stream: its own workspace
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                y_cap = m(x_small)
+        keys = [k for k in P._workspaces if k[0] == torch.device(DEV).index]
+        assert len(keys) >= 2                                         # current stream + side stream
+        with torch.cuda.stream(side):
+            ws_before = P._workspaces[(torch.device(DEV).index, side.cuda_stream)]
+            assert getattr(ws_before, "_bcl_captured", False)
+            y_big = m(x_big)                                          # regrows the side stream's workspace
+            ws_after = P._workspaces[(torch.device(DEV).index, side.cuda_stream)]
+            assert ws_after.data_ptr() != ws_before.data_ptr() and any(w is ws_before for w in P._captured_workspaces)
+            junk = [torch.full((ws_before.numel(),), 7, device=DEV, dtype=torch.uint8) for _ in range(2)]   # would reuse a freed buffer
+            graph.replay()
+            torch.cuda.synchronize()
+        assert torch.equal(y_cap, y_ref)
+        assert all(int(j[0].item()) == 7 and int(j[-1].item()) == 7 for j in junk)
+        assert y_big.shape == (2048, 512)
+    assert prefill_status(DEV) == 0 and prefill_status(DEV, sticky=False) == 0

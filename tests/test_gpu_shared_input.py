@@ -87,12 +87,45 @@ def test_tiny_llama_logits_unchanged_by_fusion():
     bc.patch_llama_fft(model, block_size=64)
     model = model.to(DEV)
     ids = torch.randint(0, 320, (2, 9), device=DEV)
+    assert not any(m.training for m in model.modules())             # from_linear keeps the replaced module's mode (model was in eval)
     with torch.no_grad():
         ref = model(input_ids=ids).logits
         assert bc.fuse_shared_inputs(model) == 4                     # GQA: k/v are narrower than q, still one group
+        groups = list({id(m._shared_group): m._shared_group for m in model.modules() if getattr(m, "_shared_group", None) is not None}.values())
         got = model(input_ids=ids).logits
+        assert [g.fused_calls for g in groups] == [1, 1, 1, 1]       # one fused launch per group per forward: the group path really ran
         ids_long = torch.randint(0, 320, (2, 200), device=DEV)       # 400 tokens: the split (fp32-spectrum) tensor-core chain, fused
         l1 = model(input_ids=ids_long).logits
+        with torch.inference_mode():                                 # inference tensors have no version counter (the bench's eval functions)
+            l1i = model(input_ids=ids_long).logits
+        assert [g.fused_calls for g in groups] == [3, 3, 3, 3]
         bc.unfuse_shared_inputs(model)
         l2 = model(input_ids=ids_long).logits
-    assert torch.equal(ref, got) and torch.equal(l1, l2)
+    assert torch.equal(ref, got) and torch.equal(l1, l2) and torch.equal(l1i, l2)
+
+
+def test_cache_shims_and_data_writes():
+    """`.data` writes do not move c._version: the cached spectrum goes stale until drop_spectrum(); disable_cfft_cache() restores the
+    reference's rebuild-on-every-forward semantics (src/patch_llama_fft.py:256-257), enable_cfft_cache() the cached one."""
+    torch.manual_seed(5)
+    m = bc.BlockCirculantLinear(256, 256, block_size=64, bias=False).to(DEV).eval()
+    holder = torch.nn.Sequential(m)
+    x = torch.randn(3, 256, device=DEV)
+    with torch.no_grad():
+        y0 = m(x).clone()
+        m.c.data.mul_(2.0)                                           # invisible to the version-keyed cache
+        assert torch.equal(m(x), y0)
+        m.drop_spectrum()
+        assert torch.allclose(m(x), 2 * y0, rtol=1e-5, atol=1e-6)
+        assert bc.disable_cfft_cache(holder) == 1
+        m.c.data.mul_(0.5)
+        assert torch.allclose(m(x), y0, rtol=1e-5, atol=1e-6)        # rebuilt on every forward now
+        assert bc.enable_cfft_cache(holder) == 1
+        m.c.data.mul_(3.0)
+        assert torch.allclose(m(x), y0, rtol=1e-5, atol=1e-6)        # cached again
+
+
+def test_from_linear_keeps_training_mode():
+    lin = torch.nn.Linear(128, 128, bias=False).to(DEV)
+    assert bc.BlockCirculantLinear.from_linear(lin, block_size=64).training
+    assert not bc.BlockCirculantLinear.from_linear(lin.eval(), block_size=64).training

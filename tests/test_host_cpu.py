@@ -359,3 +359,22 @@ def test_work_based_switch_to_the_tensor_core_path(monkeypatch):
     assert not m._use_prefill_path(63) and m._use_prefill_path(64)
     monkeypatch.setattr(P, "PREFILL_MIN_TOKENS", 256)                      # the override is a plain token floor
     assert not m._use_prefill_path(255) and m._use_prefill_path(256)
+
+
+def test_from_linear_follows_the_replaced_modules_mode_and_disable_cache_flag():
+    """a model put in eval() before patching must end up with eval-mode BC layers (the cached spectrum and the
+    shared-input groups are eval-only); disable_cfft_cache switches to rebuild-on-every-forward."""
+    import torch.nn as nn
+    lin = nn.Linear(128, 64, bias=True)
+    assert bc.BlockCirculantLinear.from_linear(lin, block_size=32).training
+    m = bc.BlockCirculantLinear.from_linear(lin.eval(), block_size=32)
+    assert not m.training and m._cache_spectrum
+    holder = nn.Sequential(m)
+    assert bc.disable_cfft_cache(holder) == 1 and not m._cache_spectrum
+    assert bc.enable_cfft_cache(holder) == 1 and m._cache_spectrum
+
+
+def test_calibrate_default_prompts_file_exists():
+    from llama_fft_b200 import calibrate_bc
+    import os
+    assert os.path.exists(calibrate_bc.build_parser().parse_args([]).prompts_file)

@@ -166,3 +166,32 @@ def test_backward_oracle_matches_autograd_through_the_restated_forward():
 def test_unsupported_input_dim_raises():
     with pytest.raises(ValueError, match="Unsupported input dim"):
         O.bc_forward_torch(torch.zeros(1, 1, 64), torch.zeros(64))
+
+
+def test_oracle_is_bit_identical_to_the_staged_reference_modules():
+    """oracle/_ref/ holds byte-identical copies of the reference's modules (oracle/make_ref.py; sha256 manifest).  Wherever they are
+    present -- the build container and, shipped with the snapshot, the GPU box -- the oracle's restatement is compared with the
+    reference ITSELF on fresh seeded inputs: as shipped (src/patch_llama_fft.py:226-275) and with enable_cfft_cache
+    (src/bench_all_in_one.py:164-254)."""
+    import pytest
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not staged (python oracle/make_ref.py needs /root/reference)")
+    ref_loader.verify()
+    plf, bai = ref_loader.load("patch_llama_fft"), ref_loader.load("bench_all_in_one")
+    g = torch.Generator().manual_seed(123)
+    for (inf, outf, B, shape, dt, bias) in [(256, 128, 64, (3,), torch.float32, True), (512, 512, 128, (2, 5), torch.float16, False),
+                                            (512, 256, 256, (1, 1), torch.bfloat16, True)]:
+        m = plf.BlockCirculantLinear(inf, outf, block_size=B, bias=bias).eval()
+        with torch.no_grad():
+            m.c.copy_(torch.randn(outf // B, inf // B, B, generator=g) * 0.05)
+            if bias:
+                m.bias.copy_(torch.randn(outf, generator=g) * 0.1)
+        x = torch.randn(*shape, inf, generator=g).to(dt)
+        b = m.bias.detach() if bias else None
+        with torch.no_grad():
+            y_ref = m(x)
+            assert torch.equal(O.bc_forward_torch(m.c.detach(), x, b), y_ref)
+            bai.enable_cfft_cache(torch.nn.ModuleList([m]))
+            y_cached = m(x)
+            assert torch.equal(O.bc_forward_cached_torch(O.CachedSpectrum(m.c.detach()), x, b), y_cached)
