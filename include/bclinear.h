@@ -134,8 +134,16 @@ typedef struct bcl_problem {
     int64_t y_row_stride;   /* elements */
     int32_t p, q;
     int32_t x_dtype, y_dtype, bias_dtype;
-    int32_t reserved;
+    int32_t epilogue;       /* BCL_EPILOGUE_LINEAR (0), or BCL_EPILOGUE_SWIGLU for bcl_forward_chain */
 } bcl_problem;
+
+/* Epilogues.  LINEAR is the reference's (src/patch_llama_fft.py:263-271: 1/B, round to x_dtype, + bias in the promoted dtype).
+ * SWIGLU (bcl_forward_chain only) treats the problem as gate_proj and up_proj stacked along the output-block axis -- block-rows
+ * [0, p/2) gate, [p/2, p) up, as shared_input.py stacks them -- and writes what HF LlamaMLP.forward feeds down_proj
+ * (transformers LlamaMLP.forward; the reference swaps exactly those three modules, src/patch_llama_fft.py:379):
+ *     h = round(silu(round(gate)) ) * round(up),  every round() to x_dtype, y is (1, (p/2)*B), bias must be NULL. */
+#define BCL_EPILOGUE_LINEAR 0
+#define BCL_EPILOGUE_SWIGLU 1
 
 size_t bcl_group_plan_bytes(int count, int num_ctas);
 /* num_ctas: how many CTAs to partition over (e.g. 2 * SM count); returns BCL_OK and fills host_plan. */
@@ -143,6 +151,23 @@ int bcl_group_plan_encode(const bcl_problem* problems, int count, int B, int spe
                           void* host_plan, size_t host_plan_bytes);
 /* dev_plan = device copy of host_plan (same bytes).  host_plan is read for the launch geometry only. */
 int bcl_forward_grouped(const void* dev_plan, const void* host_plan, void* stream);
+
+/* ---- chain forward: DEPENDENT BC linears of one token in ONE launch (decode) -------------------------------------------------
+ * A decoder layer's projections depend on each other (down_proj(act_fn(gate_proj(x)) * up_proj(x)), HF LlamaMLP.forward over the
+ * modules the reference swaps, src/patch_llama_fft.py:379); launched one module at a time a token costs ~5 us of latency per module
+ * for ~0.2 us of HBM time.  bcl_forward_chain runs nsteps <= BCL_CHAIN_MAX_STEPS steps in one persistent kernel with a grid-wide
+ * barrier between steps; step s consists of problems [step_first[s], step_first[s+1]) (count = step_first[nsteps] <=
+ * BCL_CHAIN_MAX_PROBLEMS), which may read what earlier steps wrote.  The spectra of later steps are prefetched into shared
+ * memory while earlier steps compute.  All problems: N == 1, STREAM layout, the same B and spec_dtype; the descriptors travel as
+ * kernel parameters (no plan buffer).  With nsteps == 1 it is simply the low-latency small launch for a few independent problems.
+ *   barrier_counter  device memory, 8 bytes, 8-byte aligned, zeroed ONCE by the caller and then owned by the library (never reset:
+ *                    every launch advances it by 2^20); one counter may serve every chain launch of a stream, but not launches
+ *                    that can run concurrently.  May be NULL when nsteps == 1.
+ * Graph-capturable.  BCL_ERR_UNSUPPORTED if the device cannot hold the whole grid at once (the barrier needs co-resident CTAs). */
+#define BCL_CHAIN_MAX_PROBLEMS 8
+#define BCL_CHAIN_MAX_STEPS 8
+int bcl_forward_chain(const bcl_problem* problems, const int* step_first, int nsteps, int B, int spec_dtype,
+                      void* barrier_counter, void* stream);
 
 /* ---- end-to-end convenience with HOST buffers (what bench.py's e2e figure times) --------------------------
  * Copies x from (pinned) host memory to the caller's device staging buffers, runs bcl_forward, copies y

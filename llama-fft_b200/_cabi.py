@@ -13,6 +13,8 @@ LIB_PATH = os.environ.get("BCL_LIB_PATH") or os.path.join(_HERE, "libbclinear.so
 ABI_VERSION = 10
 F32, F16, BF16 = 0, 1, 2
 LAYOUT_STREAM, LAYOUT_GEMM = 0, 1
+EPILOGUE_LINEAR, EPILOGUE_SWIGLU = 0, 1
+CHAIN_MAX_PROBLEMS, CHAIN_MAX_STEPS = 8, 8
 
 DTYPE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
@@ -22,7 +24,7 @@ SYMBOLS = (
     "bcl_forward", "bcl_group_plan_bytes", "bcl_group_plan_encode", "bcl_forward_grouped", "bcl_forward_host", "bcl_forward_grouped_host", "bcl_forward_grouped_host_pipelined",
     "bcl_project_from_dense",
     "bcl_forward_bcast", "bcl_conj_transpose", "bcl_backward_workspace_bytes", "bcl_backward_weights", "bcl_prefill_geometry", "bcl_prefill_rfft", "bcl_prefill_gemm", "bcl_prefill_irfft",
-    "bcl_launch_noop",
+    "bcl_launch_noop", "bcl_forward_chain",
 )
 
 
@@ -36,7 +38,7 @@ class Problem(ctypes.Structure):
                 ("N", ctypes.c_int64), ("x_row_stride", ctypes.c_int64), ("y_row_stride", ctypes.c_int64),
                 ("p", ctypes.c_int32), ("q", ctypes.c_int32),
                 ("x_dtype", ctypes.c_int32), ("y_dtype", ctypes.c_int32), ("bias_dtype", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("epilogue", ctypes.c_int32)]
 
 
 _lib = None
@@ -83,6 +85,7 @@ def lib() -> ctypes.CDLL:
     L.bcl_prefill_gemm.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, vp]
     L.bcl_prefill_irfft.argtypes = [vp, i64, i32, i32, i32, vp, i32, i32, vp, i32, vp, i32, i64, vp, vp]
     L.bcl_launch_noop.argtypes = [i32, vp]
+    L.bcl_forward_chain.argtypes = [ctypes.POINTER(Problem), ctypes.POINTER(ctypes.c_int), i32, i32, i32, vp, vp]
     for name in SYMBOLS:
         getattr(L, name)
     if L.bcl_abi_version() != ABI_VERSION:

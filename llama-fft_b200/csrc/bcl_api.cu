@@ -36,13 +36,14 @@ int promote(int a, int b) {
 }
 
 int check_problem(const void* x, int x_dtype, int64_t N, int64_t xs, const void* spec, int p, int q, int B,
-                  const void* bias, int bias_dtype, const void* y, int y_dtype, int64_t ys) {
+                  const void* bias, int bias_dtype, const void* y, int y_dtype, int64_t ys, int out_blocks = -1) {
+    if (out_blocks < 0) out_blocks = p;                              // SWIGLU problems write (p/2)*B columns
     if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
     if (p <= 0 || q <= 0 || N < 0) return fail(BCL_ERR_SHAPE, "bad shape p=%d q=%d N=%lld", p, q, (long long)N);
     if (!valid_dt(x_dtype) || !valid_dt(y_dtype) || (bias && !valid_dt(bias_dtype))) return fail(BCL_ERR_DTYPE, "unknown dtype enum");
     if (N == 0) return BCL_OK;
     if (!x || !spec || !y) return fail(BCL_ERR_ARG, "NULL x/spec/y");
-    if (xs < (int64_t)q * B || ys < (int64_t)p * B) return fail(BCL_ERR_SHAPE, "row stride smaller than the feature dimension");
+    if (xs < (int64_t)q * B || ys < (int64_t)out_blocks * B) return fail(BCL_ERR_SHAPE, "row stride smaller than the feature dimension");
     const int want = bias ? promote(x_dtype, bias_dtype) : x_dtype;
     if (y_dtype != want) return fail(BCL_ERR_DTYPE, "y_dtype %d but the reference's promotion of x_dtype %d (+bias %d) gives %d", y_dtype, x_dtype, bias ? bias_dtype : -1, want);
     if (!aligned(x, 16) || !aligned(y, 16) || !aligned(spec, 16) || (bias && !aligned(bias, 16)))
@@ -312,6 +313,50 @@ int bcl_forward_grouped(const void* dev_plan, const void* host_plan, void* strea
                   : H.variant == 1 ? bcl::launch_stream_ws(H, dev_plan, (cudaStream_t)stream)
                                    : bcl::launch_stream_grouped(H, dev_plan, (cudaStream_t)stream);
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "grouped forward launch");
+}
+
+int bcl_forward_chain(const bcl_problem* problems, const int* step_first, int nsteps, int B, int spec_dtype, void* barrier_counter, void* stream) {
+    if (!problems || !step_first) return fail(BCL_ERR_ARG, "NULL problems / step_first");
+    if (nsteps < 1 || nsteps > BCL_CHAIN_MAX_STEPS) return fail(BCL_ERR_ARG, "nsteps %d not in 1..%d", nsteps, BCL_CHAIN_MAX_STEPS);
+    if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
+    if (spec_dtype != BCL_F32 && spec_dtype != BCL_BF16) return fail(BCL_ERR_DTYPE, "STREAM spectrum must be f32 or bf16");
+    const int count = step_first[nsteps];
+    if (step_first[0] != 0 || count < 1 || count > BCL_CHAIN_MAX_PROBLEMS) return fail(BCL_ERR_ARG, "step_first must run from 0 to 1..%d problems", BCL_CHAIN_MAX_PROBLEMS);
+    if (nsteps > 1 && (!barrier_counter || !aligned(barrier_counter, 8))) return fail(BCL_ERR_ARG, "a chain of several steps needs an 8-byte aligned barrier counter");
+    bcl::ChainParams prm{};
+    prm.nsteps = nsteps; prm.nproblems = count;
+    int qmax = 0, max_units = 1;
+    for (int s = 0; s < nsteps; ++s) {
+        if (step_first[s + 1] <= step_first[s]) return fail(BCL_ERR_ARG, "step %d is empty", s);
+        prm.step_first[s] = step_first[s];
+        int units = 0;
+        for (int g = step_first[s]; g < step_first[s + 1]; ++g) {
+            const bcl_problem& P = problems[g];
+            const bool swiglu = P.epilogue == BCL_EPILOGUE_SWIGLU;
+            if (P.epilogue != BCL_EPILOGUE_LINEAR && !swiglu) return fail(BCL_ERR_ARG, "problem %d: unknown epilogue %d", g, P.epilogue);
+            if (swiglu && ((P.p & 1) || P.bias)) return fail(BCL_ERR_SHAPE, "problem %d: SWIGLU needs an even number of block-rows (gate | up) and no bias", g);
+            int rc = check_problem(P.x, P.x_dtype, P.N, P.x_row_stride, P.spec, P.p, P.q, B, P.bias, P.bias_dtype, P.y, P.y_dtype, P.y_row_stride,
+                                   swiglu ? P.p / 2 : P.p);
+            if (rc != BCL_OK) return rc;
+            if (P.N != 1) return fail(BCL_ERR_SHAPE, "chain problems are single tokens (problem %d has N = %lld)", g, (long long)P.N);
+            prm.prob[g] = bcl::ProblemDev{P.x, P.spec, P.bias, P.y, P.N, P.x_row_stride, P.y_row_stride, P.p, P.q, P.x_dtype, P.y_dtype,
+                                          P.bias ? P.bias_dtype : BCL_F32, 0, {}, P.epilogue, 0};
+            if (P.q > qmax) qmax = P.q;
+            units += swiglu ? P.p / 2 : P.p;
+        }
+        if (units > max_units) max_units = units;
+    }
+    prm.step_first[nsteps] = count;
+    prm.counter = reinterpret_cast<unsigned long long*>(barrier_counter);
+    static long long* dbg = getenv("BCL_CHAIN_DBG_PTR") ? reinterpret_cast<long long*>(strtoull(getenv("BCL_CHAIN_DBG_PTR"), nullptr, 0)) : nullptr;   // tools/chain_trace.py only
+    prm.dbg = dbg;
+    if (!bcl::chain_supported(B, spec_dtype, qmax)) return fail(BCL_ERR_UNSUPPORTED, "x spectrum (q=%d, B=%d) leaves no room for the spectrum ring in shared memory", qmax, B);
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
+        return fail(BCL_ERR_CUDA, "cannot query the SM count");
+    const int grid = max_units < sms ? max_units : sms;              // one CTA per SM at most: the grid barrier needs all of them resident
+    cudaError_t e = bcl::launch_chain(prm, B, spec_dtype, qmax, grid, (cudaStream_t)stream);
+    return e == cudaSuccess ? BCL_OK : cuda_fail(e, "chain forward launch");
 }
 
 int bcl_forward_host(const void* host_x, int x_dtype, int64_t N,

@@ -19,8 +19,22 @@ struct ProblemDev {
     int32_t x_dtype, y_dtype, bias_dtype;
     int32_t n_extra;        // additional destinations of y (same shape / stride / dtype), e.g. peer GPUs' buffers
     void* y_extra[7];
+    int32_t epilogue;       // BCL_EPILOGUE_LINEAR (reference epilogue) | BCL_EPILOGUE_SWIGLU (chain kernel only: rows [0,p/2) gate, [p/2,p) up)
+    int32_t pad_;
 };
 constexpr int kMaxExtraDst = 7;
+
+// Parameters of the chain kernel (bcl_stream_chain.cu): up to kChainMaxSteps dependent steps over kChainMaxProblems problems, all N == 1.
+constexpr int kChainMaxProblems = 8;
+constexpr int kChainMaxSteps = 8;
+constexpr unsigned long long kChainQuantum = 1ull << 20;     // every launch advances the barrier counter by exactly this much
+struct ChainParams {
+    int32_t nsteps, nproblems;
+    int32_t step_first[kChainMaxSteps + 1];
+    ProblemDev prob[kChainMaxProblems];
+    unsigned long long* counter;      // device, 8 bytes, zeroed once by the caller; never reset by the library (nsteps > 1 only)
+    long long* dbg;                   // profiling builds / tools only: clock64 stamps of CTA 0 (NULL otherwise)
+};
 
 // Header of an encoded group plan (host and device copies are byte-identical).
 struct GroupPlanHeader {
@@ -44,6 +58,9 @@ bool stream_rw_supported(int B, int spec_dtype, int nt, int qmax);
 cudaError_t launch_stream_rw(const GroupPlanHeader& H, const void* dev_plan, cudaStream_t st);
 size_t stream_smem_bytes(int B, int nt, int q, int warps);
 int stream_pick_nt(int64_t N, int q, int B);
+
+bool chain_supported(int B, int spec_dtype, int qmax);
+cudaError_t launch_chain(const ChainParams& prm, int B, int spec_dtype, int qmax, int grid, cudaStream_t st);
 
 // prefill path (bcl_gemm.cu): GEMM-layout spectrum, the three stages, and the chunked forward that chains them
 // split = 1: the fp32-accurate variant (fp32 spectra): (hi, lo) bf16 pairs for Cmat / Xf / Yf, three MMAs per k-step

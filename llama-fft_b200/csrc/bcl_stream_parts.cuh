@@ -21,7 +21,12 @@ struct SegWork { int g, j0, j1, pad; };
 // the V global loads of a pass back to back (one exposed DRAM latency) whatever the activation dtype is.
 template <int V> struct XRaw { uint2 w[V]; };
 
-template <int B>
+// CG: L2-coherent loads (ld.global.cg) instead of the read-only path: inside the chain kernel x was written by OTHER SMs earlier in the
+// same launch, and an address may be reused from step to step, so neither L1 nor the non-coherent cache may serve it.
+template <bool CG> __device__ __forceinline__ uint2 ldx_u2(const uint2* p) { if constexpr (CG) return __ldcg(p); else return __ldg(p); }
+template <bool CG> __device__ __forceinline__ uint32_t ldx_u1(const uint32_t* p) { if constexpr (CG) return __ldcg(p); else return __ldg(p); }
+
+template <int B, bool CG = false>
 __device__ __forceinline__ void load_x_raw(XRaw<FftCfg<B>::V>& r, const ProblemDev& P, int64_t row_off, int i, int t, bool active) {
     using C = FftCfg<B>;
     if (!active) {
@@ -32,11 +37,11 @@ __device__ __forceinline__ void load_x_raw(XRaw<FftCfg<B>::V>& r, const ProblemD
     if (P.x_dtype == BCL_F32) {
         const float* base = reinterpret_cast<const float*>(P.x) + row_off + (int64_t)i * B + 2 * t;
 #pragma unroll
-        for (int n1 = 0; n1 < C::V; ++n1) r.w[n1] = __ldg(reinterpret_cast<const uint2*>(base + 2 * C::T * n1));
+        for (int n1 = 0; n1 < C::V; ++n1) r.w[n1] = ldx_u2<CG>(reinterpret_cast<const uint2*>(base + 2 * C::T * n1));
     } else {
         const uint16_t* base = reinterpret_cast<const uint16_t*>(P.x) + row_off + (int64_t)i * B + 2 * t;
 #pragma unroll
-        for (int n1 = 0; n1 < C::V; ++n1) r.w[n1].x = __ldg(reinterpret_cast<const uint32_t*>(base + 2 * C::T * n1));
+        for (int n1 = 0; n1 < C::V; ++n1) r.w[n1].x = ldx_u1<CG>(reinterpret_cast<const uint32_t*>(base + 2 * C::T * n1));
     }
 }
 
@@ -50,7 +55,7 @@ __device__ __forceinline__ void convert_x_raw(const XRaw<V>& r, int dt, float2 (
     }
 }
 
-template <int B, int NT, int NWARPS, int PITCH = B>
+template <int B, int NT, int NWARPS, int PITCH = B, bool CG = false>
 __device__ inline void load_x_spectrum(const ProblemDev& P, int64_t n0, float* xs, const float2* tw, float2* fscr, int lane, int warp) {
     using C = FftCfg<B>;
     const int q = P.q;
@@ -66,14 +71,14 @@ __device__ inline void load_x_spectrum(const ProblemDev& P, int64_t n0, float* x
     int base = warp * C::G;
     if (base >= nb) return;
     locate(base, idx, n, i, active);
-    load_x_raw<B>(cur, P, (n0 + n) * P.x_stride, i, t, active);
+    load_x_raw<B, CG>(cur, P, (n0 + n) * P.x_stride, i, t, active);
     while (true) {
         const int nbase = base + NWARPS * C::G;
         int idx2 = 0, n2 = 0, i2 = 0; bool act2 = false;
         const bool more = nbase < nb;
         if (more) {                                                  // next pass's global loads fly during this pass's FFT
             locate(nbase, idx2, n2, i2, act2);
-            load_x_raw<B>(nxt, P, (n0 + n2) * P.x_stride, i2, t, act2);
+            load_x_raw<B, CG>(nxt, P, (n0 + n2) * P.x_stride, i2, t, act2);
         }
         float2 a[C::V];
         convert_x_raw<C::V>(cur, P.x_dtype, a);

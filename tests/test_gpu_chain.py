@@ -1,0 +1,205 @@
+"""GPU tests (-m gpu) of the chain kernel (llama-fft_b200/csrc/bcl_stream_chain.cu, ``bcl_forward_chain``): dependent BC linears of one
+token in ONE launch with grid barriers in between, the SWIGLU epilogue and the whole-MLP fusion built on it.
+Oracle: oracle/bc_oracle.py (the reference's forward, src/patch_llama_fft.py:226-275) composed the way HF LlamaMLP.forward composes the
+three modules the reference swaps (src/patch_llama_fft.py:379): down_proj(act_fn(gate_proj(x)) * up_proj(x))."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import llama_fft_b200 as bc
+from llama_fft_b200 import _cabi
+from llama_fft_b200.patch_llama_fft import bc_forward
+from oracle import bc_oracle as O
+from tests import _golden as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def spectrum(c, sdt):
+    p, q, B = c.shape
+    cd = c.to(DEV).contiguous()
+    spec = torch.empty(p, q, B, device=DEV, dtype=sdt)
+    _cabi.check(_cabi.lib().bcl_precompute_spectrum(cd.data_ptr(), p, q, B, spec.data_ptr(), _cabi.DTYPE[sdt], _cabi.LAYOUT_STREAM,
+                                                    _cabi.stream_ptr(torch.device(DEV))), "bcl_precompute_spectrum")
+    return spec
+
+
+def assert_close(y, y_ref, tol, io_dtype, ulps=2):
+    yd, rd = y.double().cpu(), y_ref.double().cpu()
+    assert yd.shape == rd.shape
+    scale = max(rd.abs().max().item(), 1e-30)
+    bound = tol * scale + (ulps * G.ulp(io_dtype) * rd.abs() if io_dtype != torch.float32 else 0.0)
+    bad = (yd - rd).abs() > bound
+    assert not bool(torch.as_tensor(bad).any()), f"max rel err {(yd - rd).abs().max().item() / scale:.3e} (tol {tol})"
+
+
+SHAPES = [(4096, 4096, 128), (4096, 11008, 128), (11008, 4096, 128), (512, 1024, 64), (1024, 512, 256), (8192, 1024, 256)]
+
+
+@pytest.mark.parametrize("inf,outf,B", SHAPES)
+@pytest.mark.parametrize("dtype,sdt,tol", [(torch.float16, torch.float32, 1e-4), (torch.float32, torch.float32, 1e-4), (torch.bfloat16, torch.bfloat16, 1e-2)])
+def test_single_step_matches_oracle_and_the_per_module_kernel(inf, outf, B, dtype, sdt, tol):
+    g = torch.Generator().manual_seed(inf + outf + B)
+    c = torch.randn(outf // B, inf // B, B, generator=g) * 0.02
+    x = torch.randn(1, inf, generator=g).to(dtype)
+    spec = spectrum(c, sdt)
+    xd = x.to(DEV)
+    y = torch.zeros(1, outf, device=DEV, dtype=dtype)
+    bc.BCChain([[(xd, spec, y, _cabi.EPILOGUE_LINEAR)]]).run()
+    torch.cuda.synchronize()
+    assert_close(y, O.bc_forward_torch(c, x), tol, dtype)
+    y_mod = bc_forward(xd, spec, None, outf // B, inf // B, B)           # stream_single_kernel: same split-q order, same FFT core
+    assert_close(y, y_mod, 1e-6, dtype, ulps=1)
+
+
+def test_single_step_with_bias_promotion():
+    g = torch.Generator().manual_seed(5)
+    c = torch.randn(8, 8, 128, generator=g) * 0.05
+    b = torch.randn(1024, generator=g) * 0.1
+    x = torch.randn(1, 1024, generator=g).half()
+    spec = spectrum(c, torch.float32)
+    y = torch.zeros(1, 1024, device=DEV, dtype=torch.float32)              # fp16 x + fp32 bias -> fp32 y (reference :266-271)
+    bc.BCChain([[(x.to(DEV), spec, y, _cabi.EPILOGUE_LINEAR, b.to(DEV))]]).run()
+    torch.cuda.synchronize()
+    y_ref = O.bc_forward_torch(c, x, b)
+    assert y_ref.dtype == torch.float32
+    assert_close(y, y_ref, 1e-4, torch.float32)
+
+
+def test_one_layer_of_independent_projections_in_one_step():
+    """q/k/v/o + gate/up + down of a 7B layer as ONE single-step launch (the small-launch replacement of the grouped plan)."""
+    g = torch.Generator().manual_seed(9)
+    shapes = [(32, 32)] * 4 + [(86, 32)] * 2 + [(32, 86)]
+    cs = [torch.randn(p, q, 128, generator=g) * 0.02 for (p, q) in shapes]
+    xs = [torch.randn(1, q * 128, generator=g).half() for (p, q) in shapes]
+    specs = [spectrum(c, torch.float32) for c in cs]
+    ys = [torch.zeros(1, p * 128, device=DEV, dtype=torch.float16) for (p, q) in shapes]
+    chain = bc.BCChain([[(x.to(DEV), s, y, _cabi.EPILOGUE_LINEAR) for x, s, y in zip(xs, specs, ys)]])
+    chain.run()
+    torch.cuda.synchronize()
+    for c, x, y in zip(cs, xs, ys):
+        assert_close(y, O.bc_forward_torch(c, x), 1e-4, torch.float16)
+
+
+def mlp_reference(cg, cu, cd, x):
+    """HF LlamaMLP.forward over the reference's modules, on the CPU oracle: every module output is rounded to x.dtype (:266)."""
+    gate, up = O.bc_forward_torch(cg, x), O.bc_forward_torch(cu, x)
+    h = F.silu(gate) * up
+    return h, O.bc_forward_torch(cd, h)
+
+
+@pytest.mark.parametrize("hidden,inter,B", [(4096, 11008, 128), (512, 1536, 64), (1024, 2048, 256)])
+@pytest.mark.parametrize("dtype,sdt,tol", [(torch.float16, torch.float32, 2e-4), (torch.float32, torch.float32, 2e-4), (torch.bfloat16, torch.bfloat16, 2e-2)])
+def test_fused_mlp_chain_matches_the_composed_oracle(hidden, inter, B, dtype, sdt, tol):
+    g = torch.Generator().manual_seed(hidden + inter + B)
+    cg = torch.randn(inter // B, hidden // B, B, generator=g) * 0.03
+    cu = torch.randn(inter // B, hidden // B, B, generator=g) * 0.03
+    cd = torch.randn(hidden // B, inter // B, B, generator=g) * 0.03
+    x = torch.randn(1, hidden, generator=g).to(dtype)
+    h_ref, y_ref = mlp_reference(cg, cu, cd, x)
+    spec_gu = spectrum(torch.cat([cg, cu], 0), sdt)
+    spec_d = spectrum(cd, sdt)
+    h = torch.zeros(1, inter, device=DEV, dtype=dtype)
+    y = torch.zeros(1, hidden, device=DEV, dtype=dtype)
+    chain = bc.BCChain([[(x.to(DEV), spec_gu, h, _cabi.EPILOGUE_SWIGLU)], [(h, spec_d, y, _cabi.EPILOGUE_LINEAR)]])
+    chain.run()
+    torch.cuda.synchronize()
+    # h: products of two rounded values: a 1-ulp flip of gate or up moves h by ~2 ulp; absolute floor from the 1e-4 / 1e-2 class
+    assert_close(h, h_ref, tol, dtype, ulps=4)
+    assert_close(y, y_ref, tol, dtype, ulps=4)
+    # the barrier counter is shared and never reset: many launches back to back, then under CUDA-graph replay, stay bit-identical
+    y0, h0 = y.clone(), h.clone()
+    for _ in range(40):
+        chain.run()
+    torch.cuda.synchronize()
+    assert torch.equal(y, y0) and torch.equal(h, h0)
+    s = torch.cuda.Stream(DEV)
+    with torch.cuda.stream(s):
+        chain.run()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            chain.run()
+            chain.run()
+        y.zero_(); h.zero_()
+        for _ in range(5):
+            graph.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(y, y0) and torch.equal(h, h0)
+
+
+def test_long_dependent_chain_equals_step_by_step_launches():
+    """Eight dependent steps (each reads the previous step's output, buffers ping-pong so an address is re-read after it was rewritten by
+    other SMs): one launch == eight single-step launches, bit for bit; mixed grids share the one barrier counter."""
+    g = torch.Generator().manual_seed(77)
+    B, p = 128, 16
+    cs = [torch.randn(p, p, B, generator=g) * (1.0 / (p ** 0.5)) for _ in range(8)]
+    specs = [spectrum(c, torch.float32) for c in cs]
+    x = torch.randn(1, p * B, generator=g).half().to(DEV)
+    buf = [torch.zeros(1, p * B, device=DEV, dtype=torch.float16) for _ in range(2)]
+    steps, cur = [], x
+    for k, s in enumerate(specs):
+        steps.append([(cur, s, buf[k & 1], _cabi.EPILOGUE_LINEAR)])
+        cur = buf[k & 1]
+    bc.BCChain(steps).run()
+    torch.cuda.synchronize()
+    got = buf[1].clone()
+    cur = x
+    for k, s in enumerate(specs):
+        bc.BCChain([[(cur, s, buf[k & 1], _cabi.EPILOGUE_LINEAR)]]).run()
+        cur = buf[k & 1]
+    torch.cuda.synchronize()
+    assert torch.equal(got, buf[1])
+    ref = x.cpu()
+    for c in cs:
+        ref = O.bc_forward_torch(c, ref)
+    assert_close(got, ref, 5e-3, torch.float16, ulps=8)                      # eight fp16 roundings deep
+
+
+def test_chain_argument_validation():
+    L = _cabi.lib()
+    spec = torch.zeros(4, 4, 128, device=DEV)
+    x2 = torch.zeros(2, 512, device=DEV)
+    y2 = torch.zeros(2, 512, device=DEV)
+    probs = (_cabi.Problem * 1)(_cabi.Problem(x2.data_ptr(), spec.data_ptr(), None, y2.data_ptr(), 2, 512, 512, 4, 4, 0, 0, 0, 0))
+    first = (ctypes.c_int * 2)(0, 1)
+    st = _cabi.stream_ptr(torch.device(DEV))
+    assert L.bcl_forward_chain(probs, first, 1, 128, _cabi.F32, None, st) == -2          # N != 1
+    probs[0].N = 1
+    assert L.bcl_forward_chain(probs, first, 1, 128, _cabi.F32, None, st) == 0
+    spec3 = torch.zeros(3, 4, 128, device=DEV)
+    probs[0] = _cabi.Problem(x2.data_ptr(), spec3.data_ptr(), None, y2.data_ptr(), 1, 512, 512, 3, 4, 0, 0, 0, _cabi.EPILOGUE_SWIGLU)
+    assert L.bcl_forward_chain(probs, first, 1, 128, _cabi.F32, None, st) == -2          # odd number of stacked rows
+    first2 = (ctypes.c_int * 3)(0, 1, 1)
+    assert L.bcl_forward_chain(probs, first2, 2, 128, _cabi.F32, None, st) == -1         # several steps need a counter / empty step
+    torch.cuda.synchronize()
+
+
+def test_fuse_mlp_in_a_tiny_llama_decode_step():
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                      vocab_size=320, max_position_embeddings=512)
+    torch.manual_seed(0)
+    model = LlamaForCausalLM(cfg).eval()
+    bc.patch_llama_fft(model, block_size=64)
+    model = model.to(DEV)
+    ids = torch.randint(0, 320, (1, 1), device=DEV)
+    with torch.no_grad():
+        ref1 = model(input_ids=ids).logits
+        assert bc.fuse_mlp(model) == 2
+        fused = [m._bcl_fused_mlp for m in model.modules() if hasattr(m, "_bcl_fused_mlp")]
+        got1 = model(input_ids=ids).logits
+        assert [f.fused_calls for f in fused] == [1, 1]                     # one token: the chain kernel served both MLPs
+        ids9 = torch.randint(0, 320, (1, 9), device=DEV)
+        a9 = model(input_ids=ids9).logits                                    # nine tokens: the original forward
+        assert [f.fused_calls for f in fused] == [1, 1]
+        out = model.generate(input_ids=ids9, max_new_tokens=4, do_sample=False, use_cache=True, pad_token_id=0)
+        assert [f.fused_calls for f in fused] == [4, 4] and out.shape == (1, 13)   # prefill unfused, 3 + ... single-token decode steps fused
+        assert bc.unfuse_mlp(model) == 2
+        b9 = model(input_ids=ids9).logits
+        back1 = model(input_ids=ids).logits
+    assert torch.equal(a9, b9) and torch.equal(back1, ref1)
+    assert (got1 - ref1).abs().max().item() <= 2e-4 * ref1.abs().max().item()
