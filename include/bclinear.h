@@ -134,7 +134,8 @@ typedef struct bcl_problem {
     int64_t y_row_stride;   /* elements */
     int32_t p, q;
     int32_t x_dtype, y_dtype, bias_dtype;
-    int32_t epilogue;       /* BCL_EPILOGUE_LINEAR (0), or BCL_EPILOGUE_SWIGLU for bcl_forward_chain */
+    int32_t epilogue;       /* BCL_EPILOGUE_LINEAR (0); bcl_forward_chain also takes BCL_EPILOGUE_SWIGLU / BCL_EPILOGUE_EMIT_SPECTRUM bits */
+    void* y_spectrum;       /* bcl_forward_chain with BCL_EPILOGUE_EMIT_SPECTRUM: (output blocks, B) fp32, else ignored (NULL) */
 } bcl_problem;
 
 /* Epilogues.  LINEAR is the reference's (src/patch_llama_fft.py:263-271: 1/B, round to x_dtype, + bias in the promoted dtype).
@@ -144,6 +145,13 @@ typedef struct bcl_problem {
  *     h = round(silu(round(gate)) ) * round(up),  every round() to x_dtype, y is (1, (p/2)*B), bias must be NULL. */
 #define BCL_EPILOGUE_LINEAR 0
 #define BCL_EPILOGUE_SWIGLU 1
+/* EMIT_SPECTRUM (bit, bcl_forward_chain only, no bias): besides y, the finisher writes y_spectrum = the packed fp32 half-spectrum
+ * (STREAM packing) of every ROUNDED output block -- bit for bit what the next step's rfft(x) (src/patch_llama_fft.py:252) would
+ * compute from y.  A later step of the same chain may then take x = that buffer with x_dtype = BCL_X_SPECTRUM and skips its own
+ * forward transform, which every CTA would otherwise repeat for the whole input (at one token the transform of a 11008-wide
+ * input costs more than streaming the weights). */
+#define BCL_EPILOGUE_EMIT_SPECTRUM 2
+#define BCL_X_SPECTRUM 3    /* x_dtype of a chain problem whose x is a (q, B) fp32 packed spectrum; y_dtype then names the activation dtype */
 
 size_t bcl_group_plan_bytes(int count, int num_ctas);
 /* num_ctas: how many CTAs to partition over (e.g. 2 * SM count); returns BCL_OK and fills host_plan. */

@@ -13,7 +13,8 @@ LIB_PATH = os.environ.get("BCL_LIB_PATH") or os.path.join(_HERE, "libbclinear.so
 ABI_VERSION = 10
 F32, F16, BF16 = 0, 1, 2
 LAYOUT_STREAM, LAYOUT_GEMM = 0, 1
-EPILOGUE_LINEAR, EPILOGUE_SWIGLU = 0, 1
+EPILOGUE_LINEAR, EPILOGUE_SWIGLU, EPILOGUE_EMIT_SPECTRUM = 0, 1, 2
+X_SPECTRUM = 3                      # x_dtype of a chain problem that consumes an emitted spectrum
 CHAIN_MAX_PROBLEMS, CHAIN_MAX_STEPS = 8, 8
 
 DTYPE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
@@ -38,7 +39,7 @@ class Problem(ctypes.Structure):
                 ("N", ctypes.c_int64), ("x_row_stride", ctypes.c_int64), ("y_row_stride", ctypes.c_int64),
                 ("p", ctypes.c_int32), ("q", ctypes.c_int32),
                 ("x_dtype", ctypes.c_int32), ("y_dtype", ctypes.c_int32), ("bias_dtype", ctypes.c_int32),
-                ("epilogue", ctypes.c_int32)]
+                ("epilogue", ctypes.c_int32), ("y_spectrum", ctypes.c_void_p)]
 
 
 _lib = None

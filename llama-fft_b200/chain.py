@@ -42,18 +42,26 @@ def barrier_counter(device) -> torch.Tensor:
     return c
 
 
-def _problem(x: torch.Tensor, spec: torch.Tensor, y: torch.Tensor, epilogue: int, bias: Optional[torch.Tensor] = None) -> _cabi.Problem:
+def _problem(x: torch.Tensor, spec: torch.Tensor, y: torch.Tensor, epilogue: int, bias: Optional[torch.Tensor] = None,
+             y_spectrum: Optional[torch.Tensor] = None, x_is_spectrum: bool = False) -> _cabi.Problem:
+    """x_is_spectrum: x is the (1, in) float32 packed spectrum an earlier step of the chain emitted (EPILOGUE_EMIT_SPECTRUM)."""
     p, q = int(spec.shape[0]), int(spec.shape[1])
+    if y_spectrum is not None:
+        epilogue |= _cabi.EPILOGUE_EMIT_SPECTRUM
+    if x_is_spectrum and x.dtype != torch.float32:
+        raise TypeError("an emitted spectrum is float32")
     return _cabi.Problem(x.data_ptr(), spec.data_ptr(), None if bias is None else bias.data_ptr(), y.data_ptr(),
-                         1, x.stride(0), y.stride(0), p, q, _cabi.DTYPE[x.dtype], _cabi.DTYPE[y.dtype],
-                         0 if bias is None else _cabi.DTYPE[bias.dtype], epilogue)
+                         1, x.stride(0), y.stride(0), p, q, _cabi.X_SPECTRUM if x_is_spectrum else _cabi.DTYPE[x.dtype], _cabi.DTYPE[y.dtype],
+                         0 if bias is None else _cabi.DTYPE[bias.dtype], epilogue, None if y_spectrum is None else y_spectrum.data_ptr())
 
 
 class BCChain:
     """A fixed chain: plan once (buffers, spectra and step structure fixed), ``run()`` many times (CUDA-graph capturable).
 
-    steps: list of steps; a step is a list of (x, spec, y, epilogue[, bias]) with x (1, q*B), STREAM-layout spec (p, q, B) and
-    y (1, p*B) -- or (1, p*B/2) with ``_cabi.EPILOGUE_SWIGLU``.  A later step may read what an earlier one writes."""
+    steps: list of steps; a step is a list of (x, spec, y, epilogue[, bias[, y_spectrum[, x_is_spectrum]]]) with x (1, q*B), STREAM-layout
+    spec (p, q, B) and y (1, p*B) -- or (1, p*B/2) with ``_cabi.EPILOGUE_SWIGLU``.  A later step may read what an earlier one writes;
+    with y_spectrum (float32, same width as y) the step also emits rfft of its rounded output, which a later step can take as x
+    (x_is_spectrum=True) instead of transforming y again."""
 
     def __init__(self, steps: Sequence[Sequence[tuple]]):
         flat = [pr for st in steps for pr in st]
@@ -69,11 +77,13 @@ class BCChain:
         for k, pr in enumerate(flat):
             x, spec, y, epi = pr[:4]
             bias = pr[4] if len(pr) > 4 else None
+            ysp = pr[5] if len(pr) > 5 else None
+            xsp = bool(pr[6]) if len(pr) > 6 else False
             if spec.dim() != 3 or spec.shape[-1] != self.B or spec.dtype != self.spec_dtype or not spec.is_contiguous():
                 raise ValueError("all problems of a chain share the block size and the spectrum dtype (STREAM layout, contiguous)")
             if x.shape != (1, spec.shape[1] * self.B):
                 raise ValueError("chain problems are single tokens: x must be (1, in_features)")
-            self.problems[k] = _problem(x, spec, y, epi, bias)
+            self.problems[k] = _problem(x, spec, y, epi, bias, ysp, xsp)
         first = [0]
         for st in steps:
             first.append(first[-1] + len(st))
@@ -131,8 +141,11 @@ class FusedBCMLP:
         spec_d = self.down.build_spectrum(layout=_cabi.LAYOUT_STREAM)
         if self._h is None or self._h.dtype != x_flat.dtype or self._h.device != x_flat.device:
             self._h = torch.empty(1, self.down.in_features, device=x_flat.device, dtype=x_flat.dtype)
+            self._hf = torch.empty(1, self.down.in_features, device=x_flat.device, dtype=torch.float32)
         y = torch.empty(1, self.down.out_features, device=x_flat.device, dtype=x_flat.dtype)
-        probs = (_cabi.Problem * 2)(_problem(x_flat, spec_gu, self._h, _cabi.EPILOGUE_SWIGLU), _problem(self._h, spec_d, y, _cabi.EPILOGUE_LINEAR))
+        # step 0 also emits rfft(h) (of the rounded h, bit for bit what down_proj would compute): step 1 starts from the spectrum
+        probs = (_cabi.Problem * 2)(_problem(x_flat, spec_gu, self._h, _cabi.EPILOGUE_SWIGLU, None, self._hf),
+                                    _problem(self._hf, spec_d, y, _cabi.EPILOGUE_LINEAR, None, None, True))
         first = (ctypes.c_int * 3)(0, 1, 2)
         ctr = barrier_counter(x_flat.device)
         with _cabi.on_device(x_flat.device):

@@ -326,23 +326,28 @@ int bcl_forward_chain(const bcl_problem* problems, const int* step_first, int ns
     bcl::ChainParams prm{};
     prm.nsteps = nsteps; prm.nproblems = count;
     int qmax = 0, max_units = 1;
+    const long long sms_guess = 512;                                 // upper bound of the grid for the overflow check below
     for (int s = 0; s < nsteps; ++s) {
         if (step_first[s + 1] <= step_first[s]) return fail(BCL_ERR_ARG, "step %d is empty", s);
         prm.step_first[s] = step_first[s];
         int units = 0;
         for (int g = step_first[s]; g < step_first[s + 1]; ++g) {
             const bcl_problem& P = problems[g];
-            const bool swiglu = P.epilogue == BCL_EPILOGUE_SWIGLU;
-            if (P.epilogue != BCL_EPILOGUE_LINEAR && !swiglu) return fail(BCL_ERR_ARG, "problem %d: unknown epilogue %d", g, P.epilogue);
+            if (P.epilogue & ~(BCL_EPILOGUE_SWIGLU | BCL_EPILOGUE_EMIT_SPECTRUM)) return fail(BCL_ERR_ARG, "problem %d: unknown epilogue %d", g, P.epilogue);
+            const bool swiglu = (P.epilogue & BCL_EPILOGUE_SWIGLU) != 0, emit = (P.epilogue & BCL_EPILOGUE_EMIT_SPECTRUM) != 0;
             if (swiglu && ((P.p & 1) || P.bias)) return fail(BCL_ERR_SHAPE, "problem %d: SWIGLU needs an even number of block-rows (gate | up) and no bias", g);
-            int rc = check_problem(P.x, P.x_dtype, P.N, P.x_row_stride, P.spec, P.p, P.q, B, P.bias, P.bias_dtype, P.y, P.y_dtype, P.y_row_stride,
-                                   swiglu ? P.p / 2 : P.p);
+            if (emit && (P.bias || !P.y_spectrum || !aligned(P.y_spectrum, 16))) return fail(BCL_ERR_ARG, "problem %d: EMIT_SPECTRUM needs a 16-byte aligned y_spectrum and no bias", g);
+            const bool xspec = P.x_dtype == BCL_X_SPECTRUM;          // x is the fp32 packed spectrum an earlier step emitted
+            if (xspec && P.bias) return fail(BCL_ERR_DTYPE, "problem %d: a spectrum input takes no bias", g);
+            int rc = check_problem(P.x, xspec ? P.y_dtype : P.x_dtype, P.N, xspec ? (int64_t)P.q * B : P.x_row_stride, P.spec, P.p, P.q, B, P.bias, P.bias_dtype, P.y,
+                                   P.y_dtype, P.y_row_stride, swiglu ? P.p / 2 : P.p);
             if (rc != BCL_OK) return rc;
             if (P.N != 1) return fail(BCL_ERR_SHAPE, "chain problems are single tokens (problem %d has N = %lld)", g, (long long)P.N);
             prm.prob[g] = bcl::ProblemDev{P.x, P.spec, P.bias, P.y, P.N, P.x_row_stride, P.y_row_stride, P.p, P.q, P.x_dtype, P.y_dtype,
-                                          P.bias ? P.bias_dtype : BCL_F32, 0, {}, P.epilogue, 0};
+                                          P.bias ? P.bias_dtype : BCL_F32, 0, {}, P.epilogue, 0, emit ? P.y_spectrum : nullptr};
             if (P.q > qmax) qmax = P.q;
             units += swiglu ? P.p / 2 : P.p;
+            if ((long long)(swiglu ? 2 : 1) * P.q * P.p * (2 * sms_guess) > 0x7fffffffLL) return fail(BCL_ERR_SHAPE, "problem %d too large for the chain kernel's 32-bit work split", g);
         }
         if (units > max_units) max_units = units;
     }
@@ -354,7 +359,9 @@ int bcl_forward_chain(const bcl_problem* problems, const int* step_first, int ns
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
         return fail(BCL_ERR_CUDA, "cannot query the SM count");
-    const int grid = max_units < sms ? max_units : sms;              // one CTA per SM at most: the grid barrier needs all of them resident
+    // one CTA per SM at most: the grid barrier needs every CTA resident (and two CTAs per SM measured slower for single steps too)
+    const int cap = sms;
+    const int grid = max_units < cap ? max_units : cap;
     cudaError_t e = bcl::launch_chain(prm, B, spec_dtype, qmax, grid, (cudaStream_t)stream);
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "chain forward launch");
 }

@@ -112,19 +112,32 @@ __device__ __forceinline__ void group_rfft_packed(float2 (&a)[FftCfg<B>::V], flo
     }
     __syncwarp();
     // real pass: X[k] = (Zk + conj(Zm))/2 - (i/2) w^k (Zk - conj(Zm)),  X[M-k] = conj((Zk + conj(Zm))/2 + (i/2) w^k (Zk - conj(Zm)))
+    // Three phases (all loads, all arithmetic, then the predicated stores): with loads inside the per-pair predicate the compiler cannot
+    // hoist them and the NPAIR pairs run one shared-memory latency after the other -- a single warp is latency-bound here.
+    float2 zk[C::NPAIR], zm[C::NPAIR], wk[C::NPAIR];
+#pragma unroll
+    for (int it = 0; it < C::NPAIR; ++it) {
+        const int k = min(t + T * it, M / 2);                        // clamped: always a valid pair, surplus lanes recompute pair M/2
+        zk[it] = scr[k]; zm[it] = scr[(M - k) & (M - 1)]; wk[it] = tw[k];
+    }
+    float2 xa[C::NPAIR], xb[C::NPAIR];
+#pragma unroll
+    for (int it = 0; it < C::NPAIR; ++it) {
+        const float2 e = make_float2(0.5f * (zk[it].x + zm[it].x), 0.5f * (zk[it].y - zm[it].y));
+        const float2 d = make_float2(0.5f * (zk[it].x - zm[it].x), 0.5f * (zk[it].y + zm[it].y));
+        const float2 wd = cmul(wk[it], d);
+        xa[it] = make_float2(e.x + wd.y, e.y - wd.x);
+        xb[it] = make_float2(e.x - wd.y, -(e.y + wd.x));
+    }
 #pragma unroll
     for (int it = 0; it < C::NPAIR; ++it) {
         const int k = t + T * it;
         if (k <= M / 2 && active) {
-            const float2 zk = scr[k], zm = scr[(M - k) & (M - 1)];
             if (k == 0) {
-                *reinterpret_cast<float2*>(dst) = make_float2(zk.x + zk.y, zk.x - zk.y);     // (DC, Nyquist)
+                *reinterpret_cast<float2*>(dst) = make_float2(zk[it].x + zk[it].y, zk[it].x - zk[it].y);     // (DC, Nyquist)
             } else {
-                const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-                const float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
-                const float2 wd = cmul(tw[k], d);
-                *reinterpret_cast<float2*>(dst + 2 * k) = make_float2(e.x + wd.y, e.y - wd.x);
-                if (k != M - k) *reinterpret_cast<float2*>(dst + 2 * (M - k)) = make_float2(e.x - wd.y, -(e.y + wd.x));
+                *reinterpret_cast<float2*>(dst + 2 * k) = xa[it];
+                if (k != M - k) *reinterpret_cast<float2*>(dst + 2 * (M - k)) = xb[it];
             }
         }
     }
@@ -140,18 +153,31 @@ __device__ __forceinline__ void group_irfft_packed(const float* src, float2* scr
     using C = FftCfg<B>;
     constexpr int M = C::M, V = C::V, T = C::T, OPT = C::OPT, PITCH = C::PITCH;
     // E = Xk + conj(Xm);  O = conj(w^k) (Xk - conj(Xm));  Z[k] = E + i O;  Z[M-k] = conj(E) + i conj(O)
+    // (loads, arithmetic and predicated stores in three phases, as in the forward pass)
+    float2 xk[C::NPAIR], xm[C::NPAIR], wk[C::NPAIR];
+#pragma unroll
+    for (int it = 0; it < C::NPAIR; ++it) {
+        const int k = min(t + T * it, M / 2);
+        const float2 a0 = *reinterpret_cast<const float2*>(src + 2 * k), a1 = *reinterpret_cast<const float2*>(src + 2 * ((M - k) & (M - 1)));
+        xk[it] = (k == 0) ? make_float2(a0.x, 0.f) : a0;             // packed slot 0 is (DC, Nyquist), both real
+        xm[it] = (k == 0) ? make_float2(a0.y, 0.f) : a1;
+        wk[it] = tw[k];
+    }
+    float2 za[C::NPAIR], zb[C::NPAIR];
+#pragma unroll
+    for (int it = 0; it < C::NPAIR; ++it) {
+        const float2 e = make_float2(xk[it].x + xm[it].x, xk[it].y - xm[it].y);
+        const float2 d = make_float2(xk[it].x - xm[it].x, xk[it].y + xm[it].y);
+        const float2 o = cmulc(d, wk[it]);
+        za[it] = make_float2(e.x - o.y, e.y + o.x);
+        zb[it] = make_float2(e.x + o.y, -e.y + o.x);
+    }
 #pragma unroll
     for (int it = 0; it < C::NPAIR; ++it) {
         const int k = t + T * it;
         if (k <= M / 2) {
-            float2 xk, xm;
-            if (k == 0) { const float2 p = *reinterpret_cast<const float2*>(src); xk = make_float2(p.x, 0.f); xm = make_float2(p.y, 0.f); }
-            else { xk = *reinterpret_cast<const float2*>(src + 2 * k); xm = *reinterpret_cast<const float2*>(src + 2 * (M - k)); }
-            const float2 e = make_float2(xk.x + xm.x, xk.y - xm.y);
-            const float2 d = make_float2(xk.x - xm.x, xk.y + xm.y);
-            const float2 o = cmulc(d, tw[k]);
-            scr[k] = make_float2(e.x - o.y, e.y + o.x);
-            if (k != 0 && k != M - k) scr[M - k] = make_float2(e.x + o.y, -e.y + o.x);
+            scr[k] = za[it];
+            if (k != 0 && k != M - k) scr[M - k] = zb[it];
         }
     }
     __syncwarp();

@@ -19,8 +19,9 @@ struct ProblemDev {
     int32_t x_dtype, y_dtype, bias_dtype;
     int32_t n_extra;        // additional destinations of y (same shape / stride / dtype), e.g. peer GPUs' buffers
     void* y_extra[7];
-    int32_t epilogue;       // BCL_EPILOGUE_LINEAR (reference epilogue) | BCL_EPILOGUE_SWIGLU (chain kernel only: rows [0,p/2) gate, [p/2,p) up)
+    int32_t epilogue;       // chain kernel only: BCL_EPILOGUE_* bits (SWIGLU: rows [0,p/2) gate, [p/2,p) up; EMIT_SPECTRUM: also write y_spectrum)
     int32_t pad_;
+    void* y_spectrum;       // chain kernel only: packed fp32 spectrum of the rounded output, (out/B, B)
 };
 constexpr int kMaxExtraDst = 7;
 

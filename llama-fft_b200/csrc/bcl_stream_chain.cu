@@ -64,51 +64,160 @@ __device__ inline unsigned long long ld_acquire_u64(const unsigned long long* p)
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// Weak (default, L1-allocating) global loads.  Inside a chain x was written by other SMs earlier in the SAME launch, so it must not come
+// from a stale L1 line or the non-coherent path (__ldg): after the step barrier -- ld.acquire.gpu by one thread (ptxas invalidates the
+// SM's L1 for it), then bar.sync -- weak loads are ordered behind the writers' release by causality (PTX memory model), and measured
+// ~700 cycles faster than ld.global.cg on this path.
+__device__ __forceinline__ uint32_t ld_weak_u32(const void* p) { uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ uint2 ld_weak_u64(const void* p) { uint2 v; asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ float4 ld_weak_f4(const void* p) { float4 v; asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory"); return v; }
 __device__ inline uint64_t global_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 struct Barriers {
     uint64_t full[MAX_STAGES];      // ring stage filled by TMA              (1 arrival + tx bytes)
     uint64_t empty[MAX_STAGES];     // ring stage released by the compute warps (NC arrivals)
+    uint64_t xissued;               // the compute warps have issued the loads of the first step's activations (NC arrivals)
 };
 
 // This CTA's share [u0, u1) of the units of problem g of a step (unit = one output block-row, or one (gate, up) row pair).  The
 // flattened unit sequence of the step is cut by WEIGHT (spectrum blocks streamed) into gridDim.x equal intervals; a unit belongs to the
 // interval its start weight falls into.  Producer and compute warps call this with identical arguments.
 struct StepGeom {
-    long long lo, hi;               // this CTA's weight interval
-};
-__device__ inline long long unit_weight(const ProblemDev& P) { return P.epilogue == BCL_EPILOGUE_SWIGLU ? 2LL * P.q : (long long)P.q; }
-__device__ inline int unit_count(const ProblemDev& P) { return P.epilogue == BCL_EPILOGUE_SWIGLU ? P.p / 2 : P.p; }
+    unsigned lo, hi;                // this CTA's weight interval (32-bit on purpose: 64-bit integer division is ~100 instructions a piece,
+};                                  //  and this runs on the latency path of every step; the host checks that the products fit)
+__device__ inline unsigned unit_weight(const ProblemDev& P) { return (P.epilogue & BCL_EPILOGUE_SWIGLU) ? 2u * (unsigned)P.q : (unsigned)P.q; }
+__device__ inline int unit_count(const ProblemDev& P) { return (P.epilogue & BCL_EPILOGUE_SWIGLU) ? P.p / 2 : P.p; }
 __device__ inline StepGeom step_geom(const ChainParams& prm, int step) {
-    long long W = 0;
-    for (int g = prm.step_first[step]; g < prm.step_first[step + 1]; ++g) W += unit_weight(prm.prob[g]) * unit_count(prm.prob[g]);
+    unsigned W = 0;
+    for (int g = prm.step_first[step]; g < prm.step_first[step + 1]; ++g) W += unit_weight(prm.prob[g]) * (unsigned)unit_count(prm.prob[g]);
     StepGeom s;
     s.lo = (W * blockIdx.x + gridDim.x - 1) / gridDim.x;             // ceil: a unit starting exactly on a cut belongs to the later CTA
     s.hi = (W * (blockIdx.x + 1) + gridDim.x - 1) / gridDim.x;
     return s;
 }
-__device__ inline void seg_range(const ProblemDev& P, long long cum, const StepGeom& sg, int& u0, int& u1) {
-    const long long w = unit_weight(P);
-    const int n = unit_count(P);
-    long long a = sg.lo - cum, b = sg.hi - cum;                      // units u with  a <= u * w < b
-    a = a <= 0 ? 0 : (a + w - 1) / w;
-    b = b <= 0 ? 0 : (b + w - 1) / w;
+__device__ inline void seg_range(const ProblemDev& P, unsigned cum, const StepGeom& sg, int& u0, int& u1) {
+    const unsigned w = unit_weight(P);
+    const unsigned n = (unsigned)unit_count(P);
+    // units u with  lo <= cum + u * w < hi
+    const unsigned a = sg.lo <= cum ? 0u : (sg.lo - cum + w - 1) / w;
+    const unsigned b = sg.hi <= cum ? 0u : (sg.hi - cum + w - 1) / w;
     u0 = (int)(a > n ? n : a);
     u1 = (int)(b > n ? n : b);
 }
 // spectrum row of slot k of a segment that starts at unit u0
 __device__ inline int slot_row(const ProblemDev& P, int u0, int k) {
-    return P.epilogue == BCL_EPILOGUE_SWIGLU ? u0 + (k >> 1) + (k & 1) * (P.p / 2) : u0 + k;
+    return (P.epilogue & BCL_EPILOGUE_SWIGLU) ? u0 + (k >> 1) + (k & 1) * (P.p / 2) : u0 + k;
 }
 
-#define BCL_CHAIN_STAMP(slot) do { if (prm.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 32) prm.dbg[step * 8 + (slot)] = clock64(); } while (0)
+#define BCL_CHAIN_STAMP(slot) do { if (sp.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 32) sp.dbg[step * 8 + (slot)] = clock64(); } while (0)
 
-// Sum the NC partial spectra of `nslots` row slots, inverse real FFT of all of them at once (one T-lane group per slot), epilogue.
+// DT >= 0: the activation dtype of every problem is known at compile time (x_dtype == y_dtype == DT, no bias, no extra destinations):
+// the dtype switches of the loads, the rounding and the stores fold away -- at one token per launch the kernel is latency-bound and
+// every instruction on the single finishing warp's path counts.  DT < 0: the general path (any mix, bias promotion).
+template <int DT> __device__ __forceinline__ int act_dt(int runtime_dt) { if constexpr (DT >= 0) return DT; else return runtime_dt; }
+
+// rfft of the q input blocks of P.x (one token) into xs[q][B], cooperatively by the NC compute warps (this is warp m): a pass of all
+// warps covers NC * G blocks, the raw loads of up to four passes are issued before the first transform (one exposed L2 latency).
+template <int B, int DT>
+__device__ __forceinline__ void chain_load_x(const ProblemDev& P, float* xs, const float2* tw, float2* fscr, int lane, int m, long long* dbgp, uint64_t* issued) {
+    using C = FftCfg<B>;
+    constexpr int PASS = NC * C::G;
+    constexpr int MAXP = 4;
+    const int q = P.q;
+    if (P.x_dtype == BCL_X_SPECTRUM) {
+        // the producing step already transformed its rounded output (EMIT_SPECTRUM): fetch the packed fp32 spectrum, no FFT here
+        const float4* src = reinterpret_cast<const float4*>(P.x);
+        float4* dst = reinterpret_cast<float4*>(xs);
+        const int n4 = q * B / 4, tid = m * 32 + lane;
+        constexpr int U = 12;                                        // 12 x 16 B x 256 threads = 48 KB per round: q <= 96 blocks of 128 in ONE latency
+        for (int i0 = tid; i0 < n4; i0 += U * NC * 32) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) if (i0 + u * NC * 32 < n4) v[u] = ld_weak_f4(src + i0 + u * NC * 32);
+            if (issued != nullptr && i0 == tid && lane == 0) mbar_arrive(issued);        // (lane 0 has the smallest index of its warp)
+#pragma unroll
+            for (int u = 0; u < U; ++u) if (i0 + u * NC * 32 < n4) dst[i0 + u * NC * 32] = v[u];
+        }
+        return;
+    }
+    const int dt = act_dt<DT>(P.x_dtype);
+    const int g = lane / C::T, t = lane % C::T;
+    float2* scr = fscr + g * C::GROUP_F2;
+    for (int b0 = 0; b0 < q; b0 += MAXP * PASS) {
+        XRaw<C::V> raw[MAXP];
+#pragma unroll
+        for (int ps = 0; ps < MAXP; ++ps) {
+            const int i = b0 + ps * PASS + m * C::G + g;
+            if (i < q) {
+                if (dt == BCL_F32) {
+                    const float* base = reinterpret_cast<const float*>(P.x) + (int64_t)i * B + 2 * t;
+#pragma unroll
+                    for (int n1 = 0; n1 < C::V; ++n1) raw[ps].w[n1] = ld_weak_u64(base + 2 * C::T * n1);
+                } else {
+                    const uint16_t* base = reinterpret_cast<const uint16_t*>(P.x) + (int64_t)i * B + 2 * t;
+#pragma unroll
+                    for (int n1 = 0; n1 < C::V; ++n1) raw[ps].w[n1].x = ld_weak_u32(base + 2 * C::T * n1);
+                }
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < C::V; ++n1) raw[ps].w[n1] = make_uint2(0u, 0u);
+            }
+        }
+        if (issued != nullptr && b0 == 0 && lane == 0) mbar_arrive(issued);   // loads are on their way: the producer may stream
+#pragma unroll
+        for (int ps = 0; ps < MAXP; ++ps) {
+            const int i0 = b0 + ps * PASS + m * C::G;                   // warp-uniform: does this warp have a block in this pass?
+            if (i0 < q) {
+                float2 a[C::V];
+                convert_x_raw<C::V>(raw[ps], dt, a);
+                if (dbgp != nullptr && ps == 0 && b0 == 0) { float sacc = 0.f; for (int n1 = 0; n1 < C::V; ++n1) sacc += a[n1].x; if (sacc == 1.2345e30f) xs[0] = sacc; dbgp[6] = clock64(); }
+                group_rfft_packed<B>(a, scr, xs + (size_t)(i0 + g) * B, tw, t, i0 + g < q);
+                if (dbgp != nullptr && ps == 0 && b0 == 0) dbgp[7] = clock64();
+            }
+        }
+    }
+}
+
+// Partial spectra part[slot][w][B] of `ng` row slots -> part[slot][0][B] holds the sum.  With several slots the NC warps share the work
+// (warp w: slot w % ng, every (NC / ng)-th partial), then ONE warp adds the few sub-sums; the summation order is fixed -> deterministic.
 template <int B>
-__device__ inline void finish_slots(const ProblemDev& P, int u0, int slot0, float* part, int nslots, const float2* tw, float2* fscr, int lane) {
+__device__ __forceinline__ void sum_partials_stage1(float* part, int ng, int m, int lane) {
+    using LM = LaneMap<B>;
+    constexpr int CH = LM::CH, CW = LM::CW;
+    if (ng < 2) return;
+    const int cnt = NC / ng;                                         // warps per slot (ng = 2: 4, 3: 2, 4: 2, 5..8: 1)
+    if (cnt < 2 || m >= cnt * ng) return;
+    const int slot = m % ng, r = m / ng;
+    float* base = part + (size_t)slot * NC * B;
+    float sum[CH][CW];
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+        for (int e = 0; e < CW; ++e) sum[ch][e] = 0.f;
+    for (int w = r; w < NC; w += cnt) {
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+            const float* src = base + (size_t)w * B + LM::offset(lane, ch);
+            if constexpr (CW == 4) { float4 v = *reinterpret_cast<const float4*>(src); sum[ch][0] += v.x; sum[ch][1] += v.y; sum[ch][2] += v.z; sum[ch][3] += v.w; }
+            else { float2 v = *reinterpret_cast<const float2*>(src); sum[ch][0] += v.x; sum[ch][1] += v.y; }
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {                                // partial r is in this warp's own read set: overwrite it
+        float* dst = base + (size_t)r * B + LM::offset(lane, ch);
+        if constexpr (CW == 4) *reinterpret_cast<float4*>(dst) = make_float4(sum[ch][0], sum[ch][1], sum[ch][2], sum[ch][3]);
+        else *reinterpret_cast<float2*>(dst) = make_float2(sum[ch][0], sum[ch][1]);
+    }
+}
+
+// One warp: finish the sums, inverse real FFT of all slots at once (one T-lane group per slot), epilogue.
+template <int B, int DT>
+__device__ __forceinline__ void finish_slots(const ProblemDev& P, int u0, int slot0, float* part, int nslots, const float2* tw, float2* fscr, int lane, long long* dbgp) {
     using LM = LaneMap<B>;
     using C = FftCfg<B>;
     constexpr int CH = LM::CH, CW = LM::CW;
+    const int cnt = (nslots >= 2 && NC / nslots >= 2) ? NC / nslots : NC;   // sub-sums left by stage 1 (all NC partials if it did not run)
+    const int nsum = (cnt == NC) ? NC : cnt;
     for (int k = 0; k < nslots; ++k) {
         float* slot = part + (size_t)k * NC * B;
         float sum[CH][CW];
@@ -116,8 +225,7 @@ __device__ inline void finish_slots(const ProblemDev& P, int u0, int slot0, floa
         for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
             for (int e = 0; e < CW; ++e) sum[ch][e] = 0.f;
-#pragma unroll
-        for (int w = 0; w < NC; ++w) {
+        for (int w = 0; w < nsum; ++w) {
 #pragma unroll
             for (int ch = 0; ch < CH; ++ch) {
                 const float* src = slot + (size_t)w * B + LM::offset(lane, ch);
@@ -136,38 +244,96 @@ __device__ inline void finish_slots(const ProblemDev& P, int u0, int slot0, floa
     const int g = lane / C::T, t = lane % C::T;
     const int pg = min(g, nslots - 1);                               // idle groups shadow the last slot (no stores)
     float2 out[C::V];
+    if (dbgp != nullptr) dbgp[16] = clock64();
     group_irfft_packed<B>(part + (size_t)pg * NC * B, fscr + g * C::GROUP_F2, tw, t, out);
-    if (P.epilogue != BCL_EPILOGUE_SWIGLU) {
-        if (g < nslots) store_block_epilogue<B>(P, 0, u0 + slot0 + g, t, out);
+    if (dbgp != nullptr) { float sacc = 0.f; for (int v = 0; v < C::V; ++v) sacc += out[v].x; if (sacc == 1.2345e30f) part[0] = sacc; dbgp[17] = clock64(); }
+    const float inv_b = 1.0f / (float)B;
+    const int dt = act_dt<DT>(P.y_dtype);                            // (== x_dtype unless a bias promotes: then the general path below)
+    const bool swiglu = (P.epilogue & BCL_EPILOGUE_SWIGLU) != 0;
+    const bool emit = (P.epilogue & BCL_EPILOGUE_EMIT_SPECTRUM) != 0;
+    // staging for EMIT_SPECTRUM inside the slot's (now consumed) partial buffers: [B .. 2B) rounded time samples, [2B .. 3B) their spectrum
+    float* tbuf = part + (size_t)(swiglu ? (pg & ~1) : pg) * NC * B + B;
+    int out_block;                                                   // output block this lane group contributes to
+    if (!swiglu) {
+        out_block = u0 + slot0 + g;
+        if (g < nslots) {
+            if (DT >= 0 || (P.bias == nullptr && P.n_extra == 0 && (P.y_dtype == P.x_dtype || P.x_dtype == BCL_X_SPECTRUM))) {
+                // reference epilogue without a bias (src/patch_llama_fft.py:263-266): 1/B, round to x.dtype (the store's conversion)
+                const int64_t colbase = (int64_t)out_block * B;
+#pragma unroll
+                for (int jj = 0; jj < C::OPT; ++jj)
+#pragma unroll
+                    for (int k2 = 0; k2 < C::T; ++k2) {
+                        const int mm = (t * C::OPT + jj) + C::V * k2;
+                        const float2 v = make_float2(round_to(out[jj * C::T + k2].x * inv_b, dt), round_to(out[jj * C::T + k2].y * inv_b, dt));
+                        store_act2(P.y, colbase + 2 * mm, dt, v);
+                        if (emit) *reinterpret_cast<float2*>(tbuf + 2 * mm) = v;
+                    }
+            } else {
+                store_block_epilogue<B>(P, 0, out_block, t, out);
+            }
+        }
     } else {
         // slots come in (gate, up) pairs on neighbouring lane groups: HF LlamaMLP.forward computes act_fn(gate_proj(x)) * up_proj(x) on
-        // the projections' OUTPUTS, i.e. on values already rounded to x.dtype (reference :266), silu in fp32 rounded to x.dtype, product
-        // rounded to x.dtype.
-        const float inv_b = 1.0f / (float)B;
-        const int dt = P.x_dtype;
-        const int64_t colbase = (int64_t)(u0 + ((slot0 + g) >> 1)) * B;
+        // the projections' OUTPUTS, i.e. on values already rounded to x.dtype (reference :266); silu is evaluated in fp32 and rounded
+        // to x.dtype, so is the product.  Each lane holds sample pairs (2m, 2m+1) of its row; one xor exchange hands the gate lane
+        // the up row's EVEN sample and the up lane the gate row's ODD sample, so the two lanes of a pair each finish one of the two
+        // samples -- no divergence, half the transcendental work per lane -- and a second exchange reunites the pair for the store.
+        out_block = u0 + ((slot0 + g) >> 1);
+        const int64_t colbase = (int64_t)out_block * B;
+        const bool is_up = (g & 1) != 0;
+        // four phases over all V sample pairs, so that the V dependent chains (shuffle -> round -> exp -> divide -> round -> shuffle) overlap:
+        // with the predicated store inside one loop the compiler keeps the warp-synchronous shuffles in order and every pair costs a
+        // full chain latency (measured: 1.9k cycles for 8 pairs).
+        float got[C::V], hv[C::V], ho[C::V];
 #pragma unroll
-        for (int jj = 0; jj < C::OPT; ++jj) {
+        for (int v = 0; v < C::V; ++v) got[v] = __shfl_xor_sync(0xffffffffu, is_up ? out[v].x : out[v].y, C::T);   // up.x for the even sample, gate.y for the odd one
 #pragma unroll
-            for (int k2 = 0; k2 < C::T; ++k2) {
-                const float2 mine = out[jj * C::T + k2];
-                float2 other;
-                other.x = __shfl_xor_sync(0xffffffffu, mine.x, C::T);
-                other.y = __shfl_xor_sync(0xffffffffu, mine.y, C::T);
-                if (g < nslots && (g & 1) == 0) {
-                    const float g0 = round_to(mine.x * inv_b, dt), g1 = round_to(mine.y * inv_b, dt);
-                    const float u0v = round_to(other.x * inv_b, dt), u1v = round_to(other.y * inv_b, dt);
-                    const float s0 = round_to(g0 / (1.0f + expf(-g0)), dt), s1 = round_to(g1 / (1.0f + expf(-g1)), dt);
-                    const int m = (t * C::OPT + jj) + C::V * k2;
-                    store_act2(P.y, colbase + 2 * m, P.y_dtype, make_float2(s0 * u0v, s1 * u1v));
+        for (int v = 0; v < C::V; ++v) {
+            const float gv = round_to((is_up ? got[v] : out[v].x) * inv_b, dt);
+            const float uv = round_to((is_up ? out[v].y : got[v]) * inv_b, dt);
+            const float sv = round_to(__fdividef(gv, 1.0f + __expf(-gv)), dt);
+            hv[v] = round_to(sv * uv, dt);                           // gate lane: h[2m], up lane: h[2m+1]
+        }
+#pragma unroll
+        for (int v = 0; v < C::V; ++v) ho[v] = __shfl_xor_sync(0xffffffffu, hv[v], C::T);
+        if (g < nslots && !is_up) {
+#pragma unroll
+            for (int jj = 0; jj < C::OPT; ++jj)
+#pragma unroll
+                for (int k2 = 0; k2 < C::T; ++k2) {
+                    const int mm = (t * C::OPT + jj) + C::V * k2;
+                    const float2 v = make_float2(hv[jj * C::T + k2], ho[jj * C::T + k2]);
+                    store_act2(P.y, colbase + 2 * mm, dt, v);
+                    if (emit) *reinterpret_cast<float2*>(tbuf + 2 * mm) = v;
                 }
-            }
+        }
+    }
+    if (dbgp != nullptr) dbgp[18] = clock64();
+    if (emit) {
+        // rfft of the ROUNDED output block, exactly what the next step would compute from y (same FFT core, same inputs): the consumer
+        // reads it with x_dtype = BCL_X_SPECTRUM and skips its own -- per-CTA redundant -- forward transform.
+        __syncwarp();
+        const bool owner = g < nslots && (!swiglu || (g & 1) == 0);  // one lane group per output block
+        float2 a[C::V];
+#pragma unroll
+        for (int n1 = 0; n1 < C::V; ++n1) a[n1] = *reinterpret_cast<const float2*>(tbuf + 2 * (C::T * n1 + t));
+        __syncwarp();
+        group_rfft_packed<B>(a, fscr + g * C::GROUP_F2, tbuf + B, tw, t, owner);
+        float* ys = reinterpret_cast<float*>(P.y_spectrum);
+        const int nblk = swiglu ? (nslots + 1) / 2 : nslots;
+        for (int b = 0; b < nblk; ++b) {                             // coalesced write-out, one block (B floats) per iteration
+            const int gsrc = swiglu ? 2 * b : b;
+            const float* sb = part + (size_t)gsrc * NC * B + 2 * B;
+            const int ob = swiglu ? u0 + ((slot0 + gsrc) >> 1) : u0 + slot0 + gsrc;
+            for (int e = lane * 4; e < B; e += 128) *reinterpret_cast<float4*>(ys + (size_t)ob * B + e) = *reinterpret_cast<const float4*>(sb + e);
         }
     }
     __syncwarp();
+    if (dbgp != nullptr) dbgp[19] = clock64();
 }
 
-template <int B, typename SpecT>
+template <int B, typename SpecT, int DT>
 __global__ void __launch_bounds__(THREADS, 1) chain_kernel(const __grid_constant__ ChainParams prm, int S, int qmax) {
     using LM = LaneMap<B>;
     using FC = FftCfg<B>;
@@ -179,8 +345,11 @@ __global__ void __launch_bounds__(THREADS, 1) chain_kernel(const __grid_constant
     constexpr int STAGE_BYTES = CB * BLOCK_BYTES;
     constexpr int NW = CW * (int)sizeof(SpecT) / 4;
     static_assert(CB % NC == 0, "stage must split evenly over the compute warps");
+    static_assert(sizeof(ChainParams) % 4 == 0, "parameter block is copied word by word");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(16) ChainParams sp;                         // the parameter block, copied once: every later read is an LDS
+    __shared__ int2 s_seg[kChainMaxProblems];                        // this CTA's unit range [x, y) of every problem
     Barriers* bars = reinterpret_cast<Barriers*>(smem_raw);
     float2* tw = reinterpret_cast<float2*>(smem_raw + 512);
     unsigned char* ring = smem_raw + 512 + 1024;
@@ -192,26 +361,52 @@ __global__ void __launch_bounds__(THREADS, 1) chain_kernel(const __grid_constant
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], NC); }
+        mbar_init(&bars->xissued, NC);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&prm);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sp);
+        for (int i = threadIdx.x; i < (int)(sizeof(ChainParams) / 4); i += THREADS) dst[i] = src[i];
+    }
     fill_twiddles<B>(tw, threadIdx.x, THREADS);
+    __syncthreads();
+    // This CTA's share of every problem of every step, worked out once, here -- before the wait on the previous grid -- so that the
+    // path behind a step barrier starts with one shared-memory read instead of a chain of integer divisions.
+    if ((int)threadIdx.x < sp.nsteps) {
+        const int step = threadIdx.x;
+        const StepGeom sg = step_geom(sp, step);
+        unsigned cum = 0;
+        for (int g = sp.step_first[step]; g < sp.step_first[step + 1]; ++g) {
+            int u0, u1;
+            seg_range(sp.prob[g], cum, sg, u0, u1);
+            cum += unit_weight(sp.prob[g]) * (unsigned)unit_count(sp.prob[g]);
+            s_seg[g] = make_int2(u0, u1);
+        }
+    }
     __syncthreads();
     pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            // Measured (clock stamps, tools/chain_timing.py): the SM takes responses in order at ~64 B/clk, so activation loads issued
+            // while ~100 KB of bulk copies are in flight land ~1.6k cycles later than alone.  When this grid starts on an SM the moment
+            // the previous one leaves it (the usual case: one 200 KB CTA per SM), kernel start and the end of the wait on the previous
+            // grid coincide: let the first step's x loads go first.  Bounded: if the previous grid is still running after ~1k cycles
+            // there is time to prefetch, which is what the ring is for.
+            {
+                const long long t0 = clock64();
+                const uint32_t xaddr = smem_u32(&bars->xissued);
+                while (!mbar_try(xaddr, 0u) && clock64() - t0 < 1000) {}
+            }
             int stage = 0; uint32_t ph = 0;
-            for (int step = 0; step < prm.nsteps; ++step) {
-                const StepGeom sg = step_geom(prm, step);
-                long long cum = 0;
-                for (int g = prm.step_first[step]; g < prm.step_first[step + 1]; ++g) {
-                    const ProblemDev& P = prm.prob[g];
-                    int u0, u1;
-                    seg_range(P, cum, sg, u0, u1);
-                    cum += unit_weight(P) * unit_count(P);
+            for (int step = 0; step < sp.nsteps; ++step) {
+                for (int g = sp.step_first[step]; g < sp.step_first[step + 1]; ++g) {
+                    const ProblemDev& P = sp.prob[g];
+                    const int u0 = s_seg[g].x, u1 = s_seg[g].y;
                     const int q = P.q;
-                    const int nslots = (u1 - u0) * (P.epilogue == BCL_EPILOGUE_SWIGLU ? 2 : 1);
+                    const int nslots = (u1 - u0) * ((P.epilogue & BCL_EPILOGUE_SWIGLU) ? 2 : 1);
                     for (int k = 0; k < nslots; ++k) {
                         const unsigned char* rowp = reinterpret_cast<const unsigned char*>(P.spec) + (size_t)slot_row(P, u0, k) * q * BLOCK_BYTES;
                         for (int c0 = 0; c0 < q; c0 += CB) {
@@ -238,38 +433,37 @@ __global__ void __launch_bounds__(THREADS, 1) chain_kernel(const __grid_constant
     // above), so the counter started this launch at a multiple of QUANTUM; before this CTA's own first arrival fewer than QUANTUM
     // arrivals of THIS launch can have happened: rounding down recovers the base.
     unsigned long long base = 0;
-    if (prm.nsteps > 1 && m == 0 && lane == 0) base = ld_acquire_u64(prm.counter) & ~(QUANTUM - 1);
-    for (int step = 0; step < prm.nsteps; ++step) {
+    if (sp.nsteps > 1 && m == 0 && lane == 0) base = ld_acquire_u64(sp.counter) & ~(QUANTUM - 1);
+    bool first_x = true;                                             // (a CTA without work in step 0 never signals: the producer's wait is bounded)
+    for (int step = 0; step < sp.nsteps; ++step) {
         BCL_CHAIN_STAMP(0);
         if (step > 0) {
             if (m == 0 && lane == 0) {
                 const unsigned long long target = base + (unsigned long long)step * gridDim.x;
-                if (ld_acquire_u64(prm.counter) < target) {
+                if (ld_acquire_u64(sp.counter) < target) {
                     const uint64_t t0 = global_ns();
                     uint32_t spin = 0;
-                    while (ld_acquire_u64(prm.counter) < target) {
+                    while (ld_acquire_u64(sp.counter) < target) {
                         if ((++spin & 4095u) == 0u && global_ns() - t0 > 4000000000ull) __trap();   // a CTA is missing: fail, never hang the GPU
                     }
                 }
-            }
-            if (step == prm.nsteps - 1 && blockIdx.x == 0 && m == 0 && lane == 0) {   // every CTA has arrived at the last barrier: pad to QUANTUM
-                const unsigned long long pad = QUANTUM - (unsigned long long)gridDim.x * (unsigned long long)(prm.nsteps - 1);
-                asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(prm.counter), "l"(pad) : "memory");
+                if (step == sp.nsteps - 1 && blockIdx.x == 0) {       // every CTA has arrived at the last barrier: pad the launch to QUANTUM
+                    const unsigned long long pad = QUANTUM - (unsigned long long)gridDim.x * (unsigned long long)(sp.nsteps - 1);
+                    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(sp.counter), "l"(pad) : "memory");
+                }
             }
             compute_sync();
         }
         BCL_CHAIN_STAMP(1);
-        const StepGeom sg = step_geom(prm, step);
-        long long cum = 0;
-        for (int g = prm.step_first[step]; g < prm.step_first[step + 1]; ++g) {
-            const ProblemDev& P = prm.prob[g];
-            int u0, u1;
-            seg_range(P, cum, sg, u0, u1);
-            cum += unit_weight(P) * unit_count(P);
+        for (int g = sp.step_first[step]; g < sp.step_first[step + 1]; ++g) {
+            const int u0 = s_seg[g].x, u1 = s_seg[g].y;
             if (u0 >= u1) continue;
+            const ProblemDev P = sp.prob[g];                         // registers: the fields the path below uses
             const int q = P.q;
-            const int nslots = (u1 - u0) * (P.epilogue == BCL_EPILOGUE_SWIGLU ? 2 : 1);
-            load_x_spectrum<B, 1, NC, B, true>(P, 0, xs, tw, fscr, lane, m);
+            const int nslots = (u1 - u0) * ((P.epilogue & BCL_EPILOGUE_SWIGLU) ? 2 : 1);
+            chain_load_x<B, DT>(P, xs, tw, fscr, lane, m, (sp.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 32) ? sp.dbg + step * 8 : nullptr,
+                                first_x ? &bars->xissued : nullptr);
+            first_x = false;
             compute_sync();
             BCL_CHAIN_STAMP(2);
             for (int s0 = 0; s0 < nslots; s0 += RG) {
@@ -331,15 +525,17 @@ __global__ void __launch_bounds__(THREADS, 1) chain_kernel(const __grid_constant
                 }
                 compute_sync();
                 BCL_CHAIN_STAMP(3);
-                if (m == 0) finish_slots<B>(P, u0, s0, part, ng, tw, fscr, lane);
+                if (ng >= 2 && NC / ng >= 2) {
+                    sum_partials_stage1<B>(part, ng, m, lane);
+                    compute_sync();
+                }
+                if (m == 0) finish_slots<B, DT>(P, u0, s0, part, ng, tw, fscr, lane, (sp.dbg != nullptr && blockIdx.x == 0 && lane == 0) ? sp.dbg + step * 8 : nullptr);
                 compute_sync();                                      // part / xs may be overwritten; warp 1's stores are issued
                 BCL_CHAIN_STAMP(4);
             }
         }
-        if (step + 1 < prm.nsteps && m == 0 && lane == 0) {
-            __threadfence();                                         // this CTA's y (ordered before by the bar.sync above) -> visible GPU-wide
-            asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(prm.counter), "l"(1ull) : "memory");
-        }
+        if (step + 1 < sp.nsteps && m == 0 && lane == 0)             // release: this CTA's y (ordered before by the bar.sync above) is visible
+            asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(sp.counter), "l"(1ull) : "memory");   // GPU-wide before the count moves
         BCL_CHAIN_STAMP(5);
     }
 }
@@ -353,7 +549,7 @@ size_t smem_bytes(int B, int spec_bytes, int qmax, int S) {
 
 int pick_stages(int B, int spec_dtype, int qmax) {
     const int sb = spec_dtype == BCL_F32 ? 4 : 2;
-    const size_t budget = 227 * 1024;
+    const size_t budget = 227 * 1024 - 2048;                        // minus the static shared memory (parameter block)
     const size_t fixed = smem_bytes(B, sb, qmax, 0);
     const size_t stage = (size_t)stage_blocks(B) * B * sb;
     if (fixed + 2 * stage > budget) return 0;
@@ -362,13 +558,44 @@ int pick_stages(int B, int spec_dtype, int qmax) {
     return S;
 }
 
-template <int B, typename SpecT>
+// the activation dtype every problem shares (x_dtype == y_dtype, no bias, no extra destinations), or -1
+static int uniform_dt(const ChainParams& prm) {
+    const int dt = prm.prob[0].y_dtype;
+    for (int g = 0; g < prm.nproblems; ++g) {
+        const ProblemDev& P = prm.prob[g];
+        if ((P.x_dtype != dt && P.x_dtype != BCL_X_SPECTRUM) || P.y_dtype != dt || P.bias != nullptr || P.n_extra != 0) return -1;
+    }
+    return dt;
+}
+
+// Ring stages the busiest CTA can use: all the (row, stage-of-row) chunks of all its steps (the producer runs ahead across steps).
+static int stages_wanted(const ChainParams& prm, int B, int grid) {
+    const int CB = stage_blocks(B);
+    long long total = 0;
+    for (int s = 0; s < prm.nsteps; ++s) {
+        long long step_chunks = 0;
+        for (int g = prm.step_first[s]; g < prm.step_first[s + 1]; ++g) {
+            const ProblemDev& P = prm.prob[g];
+            const int units = (P.epilogue & BCL_EPILOGUE_SWIGLU) ? P.p / 2 : P.p;
+            const int rows_per_unit = (P.epilogue & BCL_EPILOGUE_SWIGLU) ? 2 : 1;
+            step_chunks += (long long)((units + grid - 1) / grid + 1) * rows_per_unit * ((P.q + CB - 1) / CB);   // + 1: a share may straddle two problems
+        }
+        total += step_chunks;
+    }
+    return (int)(total > MAX_STAGES ? MAX_STAGES : total);
+}
+
+template <int B, typename SpecT, int DT>
 static cudaError_t launch_t(const ChainParams& prm, int spec_dtype, int qmax, int grid, cudaStream_t st) {
-    auto kern = chain_kernel<B, SpecT>;
-    const int S = pick_stages(B, spec_dtype, qmax);
+    auto kern = chain_kernel<B, SpecT, DT>;
+    int S = pick_stages(B, spec_dtype, qmax);
     if (S < 2) return cudaErrorInvalidConfiguration;
+    // A small launch asks only for the stages it can fill: with ~100 KB per CTA two CTAs share an SM, so under programmatic dependent
+    // launch the NEXT kernel's CTAs start (parameters, twiddles, spectrum prefetch) while this kernel's are still finishing.
+    const int want = stages_wanted(prm, B, grid);
+    if (want < S) S = want < 2 ? 2 : want;
     const size_t smem = smem_bytes(B, (int)sizeof(SpecT), qmax, S);
-    static int granted[64] = {0};                                    // per device: largest dynamic-smem attribute set so far (a race only repeats the call)
+    static int granted[64] = {0};                                    // (one table per template instance)                                    // per device: largest dynamic-smem attribute set so far (a race only repeats the call)
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -397,9 +624,12 @@ static cudaError_t launch_t(const ChainParams& prm, int spec_dtype, int qmax, in
 bool chain_supported(int B, int spec_dtype, int qmax) { return chain::pick_stages(B, spec_dtype, qmax) >= 2; }
 
 cudaError_t launch_chain(const ChainParams& prm, int B, int spec_dtype, int qmax, int grid, cudaStream_t st) {
-#define BCL_CH(BB) (spec_dtype == BCL_F32 ? chain::launch_t<BB, float>(prm, spec_dtype, qmax, grid, st) : chain::launch_t<BB, __nv_bfloat16>(prm, spec_dtype, qmax, grid, st))
+    const int dt = chain::uniform_dt(prm);                           // 16-bit activations (the decode configuration): dtype-specialised kernels
+#define BCL_CH2(BB, TT) (dt == BCL_F16 ? chain::launch_t<BB, TT, BCL_F16>(prm, spec_dtype, qmax, grid, st) : dt == BCL_BF16 ? chain::launch_t<BB, TT, BCL_BF16>(prm, spec_dtype, qmax, grid, st) : chain::launch_t<BB, TT, -1>(prm, spec_dtype, qmax, grid, st))
+#define BCL_CH(BB) (spec_dtype == BCL_F32 ? BCL_CH2(BB, float) : BCL_CH2(BB, __nv_bfloat16))
     switch (B) { case 64: return BCL_CH(64); case 128: return BCL_CH(128); default: return BCL_CH(256); }
 #undef BCL_CH
+#undef BCL_CH2
 }
 
 }  // namespace bcl

@@ -58,6 +58,24 @@ x0 = torch.randn(1, H, device=DEV).half()
 f16 = dict(device=DEV, dtype=torch.float16)
 out = {"spectrum_dtype": str(SDT)}
 
+if "--stamps-only" in sys.argv:
+    hb, yb = torch.empty(1, I, **dict(device=DEV, dtype=torch.float16)), torch.empty(1, H, **dict(device=DEV, dtype=torch.float16))
+    hfb = torch.empty(1, I, device=DEV, dtype=torch.float32)
+    ch = bc.BCChain([[(x0, layers[0]["gu"], hb, _cabi.EPILOGUE_SWIGLU, None, hfb)], [(hfb, layers[0]["down"], yb, 0, None, None, True)]])
+    for _ in range(3):
+        ch.run()
+    torch.cuda.synchronize()
+    dbg.zero_()
+    ch.run()
+    torch.cuda.synchronize()
+    st = dbg.view(8, 8)[:2].tolist()
+    t0 = st[0][0]
+    fin = dbg[16:20].tolist()
+    print(json.dumps({"legend": "[loop top, barrier passed, x ready, parked, finished, arrived, x loads landed (warp 1), first rfft done (warp 1)]",
+                      "step0": [v - t0 if v else None for v in st[0]], "step1": [v - t0 if v else None for v in st[1]],
+                      "finish_step0 [sums done, irfft done, epilogue done, emit done]": [v - t0 for v in fin]}))
+    sys.exit(0)
+
 # ---- (a) one small projection per launch, 32 distinct weights back to back (independent) ------------------------------------------
 ys = [torch.empty(1, H, **f16) for _ in range(LAYERS)]
 def per_module_o():
@@ -81,7 +99,12 @@ def mlp_per_module():
         h = torch.nn.functional.silu(g[:, :I]) * g[:, I:]
         bc_forward(h, l["down"], None, 32, 86, B, out=y)
 mlp_chains = [bc.BCChain([[(x0, l["gu"], h, _cabi.EPILOGUE_SWIGLU)], [(h, l["down"], y, 0)]]) for l, h, y in zip(layers, hbuf, ymlp)]
-out["mlp_us_per_layer"] = {"per_module_3_launches": time_graph(mlp_per_module) / LAYERS, "fused_chain_1_launch": time_graph(lambda: [c.run() for c in mlp_chains]) / LAYERS}
+hfbuf = [torch.empty(1, I, device=DEV, dtype=torch.float32) for _ in range(LAYERS)]
+mlp_chains_hf = [bc.BCChain([[(x0, l["gu"], h, _cabi.EPILOGUE_SWIGLU, None, hf)], [(hf, l["down"], y, 0, None, None, True)]]) for l, h, hf, y in zip(layers, hbuf, hfbuf, ymlp)]
+mlp_two = [(bc.BCChain([[(x0, l["gu"], h, _cabi.EPILOGUE_SWIGLU)]]), bc.BCChain([[(h, l["down"], y, 0)]])) for l, h, y in zip(layers, hbuf, ymlp)]
+out["mlp_us_per_layer"] = {"per_module_3_launches": time_graph(mlp_per_module) / LAYERS, "fused_chain_1_launch": time_graph(lambda: [c.run() for c in mlp_chains]) / LAYERS,
+                           "fused_chain_1_launch_spectrum_handoff": time_graph(lambda: [c.run() for c in mlp_chains_hf]) / LAYERS,
+                           "chain_kernel_2_launches_swiglu_then_down": time_graph(lambda: [(a.run(), b.run()) for a, b in mlp_two]) / LAYERS}
 
 # ---- (c) 7 independent projections of a layer in one launch ----------------------------------------------------------------------
 shapes = [(32, 32)] * 4 + [(86, 32)] * 2 + [(32, 86)]
@@ -97,7 +120,7 @@ out["layer_7_independent_us_per_launch"] = {"grouped_ws_kernel": time_graph(lamb
 del grp, chn
 
 # ---- (d) the dependent layer chain: q/k/v -> o -> gate/up -> down, each launch reads the previous one's output ---------------------
-bufs = dict(qkv=torch.empty(1, 3 * H, **f16), a=torch.empty(1, H, **f16), gu=torch.empty(1, 2 * I, **f16), h=torch.empty(1, I, **f16),
+bufs = dict(qkv=torch.empty(1, 3 * H, **f16), a=torch.empty(1, H, **f16), gu=torch.empty(1, 2 * I, **f16), h=torch.empty(1, I, **f16), hf=torch.empty(1, I, device=DEV, dtype=torch.float32),
             y=[torch.empty(1, H, **f16) for _ in range(2)])
 def chain_per_module():
     cur = x0
@@ -114,9 +137,9 @@ for k, l in enumerate(layers):
     single += [bc.BCChain([[(cur, l["qkv"], bufs["qkv"], 0)]]), bc.BCChain([[(bufs["qkv"][:, :H], l["o"], bufs["a"], 0)]]),
                bc.BCChain([[(bufs["a"], l["gu"], bufs["gu"], 0)]]), bc.BCChain([[(bufs["gu"][:, :I], l["down"], y, 0)]])]
     fused3 += [bc.BCChain([[(cur, l["qkv"], bufs["qkv"], 0)]]), bc.BCChain([[(bufs["qkv"][:, :H], l["o"], bufs["a"], 0)]]),
-               bc.BCChain([[(bufs["a"], l["gu"], bufs["h"], _cabi.EPILOGUE_SWIGLU)], [(bufs["h"], l["down"], y, 0)]])]
+               bc.BCChain([[(bufs["a"], l["gu"], bufs["h"], _cabi.EPILOGUE_SWIGLU, None, bufs["hf"])], [(bufs["hf"], l["down"], y, 0, None, None, True)]])]
     whole += [bc.BCChain([[(cur, l["qkv"], bufs["qkv"], 0)], [(bufs["qkv"][:, :H], l["o"], bufs["a"], 0)],
-                          [(bufs["a"], l["gu"], bufs["h"], _cabi.EPILOGUE_SWIGLU)], [(bufs["h"], l["down"], y, 0)]])]
+                          [(bufs["a"], l["gu"], bufs["h"], _cabi.EPILOGUE_SWIGLU, None, bufs["hf"])], [(bufs["hf"], l["down"], y, 0, None, None, True)]])]
     cur = y
 out["dependent_chain_us_per_layer"] = {
     "per_module_kernel_4_launches": time_graph(chain_per_module, 10) / LAYERS,
@@ -126,10 +149,10 @@ out["dependent_chain_us_per_layer"] = {
 
 # ---- clock stamps of CTA 0 for one fused MLP launch ---------------------------------------------------------------------------------
 dbg.zero_()
-mlp_chains[0].run()
+mlp_chains_hf[0].run()
 torch.cuda.synchronize()
 st = dbg.view(8, 8)[:2].tolist()
 t0 = st[0][0]
 out["fused_mlp_stamps_cycles_cta0"] = {"legend": "per step: [loop top, barrier passed, x spectrum ready, partials parked, finished, arrived]",
-                                       "step0": [v - t0 if v else None for v in st[0][:6]], "step1": [v - t0 if v else None for v in st[1][:6]]}
+                                       "step0": [v - t0 if v else None for v in st[0][:8]], "step1": [v - t0 if v else None for v in st[1][:8]]}
 print(json.dumps(out, indent=1))
