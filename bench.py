@@ -324,6 +324,15 @@ def run_ours(args):
     barrier()
     e2e_serial_ms = ev0.elapsed_time(ev1) / 50
 
+    # ---- BASELINE.json configs[4]: Llama-2-70B shapes, output-block-row sharded over the N GPUs of this run (all ranks take part) -----
+    sharded = None
+    if world > 1 and not args.no_detail:
+        try:
+            sharded = sharded_70b_detail(bc, dev, world, rank)
+        except Exception as e:                      # noqa: BLE001 -- evidence only; never hides the headline line
+            sharded = {"error": "%s: %s" % (type(e).__name__, e)}
+        barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -331,6 +340,8 @@ def run_ours(args):
 
     # ---- extra evidence at N=1 (not part of the timed value): other launch granularities, bf16 spectra --------------
     detail = {}
+    if sharded is not None:
+        detail["sharded_70b"] = sharded
     if world == 1 and not args.no_detail:
         detail = launch_granularity_detail(bc, _cabi, groups[0], shapes, dev, args)
         try:
@@ -569,6 +580,77 @@ def dependent_chain_detail(bc, _cabi, dev, time_graph):
 
 
 PREFILL_TOKENS = 8 * 2048          # BASELINE.json configs[2]: 2048-token prefill x batch 8
+
+SHAPES_70B = [("q/o", 8192, 8192), ("k/v", 8192, 1024), ("gate/up", 8192, 28672), ("down", 28672, 8192)]
+
+
+def sharded_70b_detail(bc, dev, world, rank, B70=256, reps=10):
+    """BASELINE.json configs[4]: Llama-2-70B projection shapes, B = 256, bf16 spectra, fp16 activations, output block-rows sharded over
+    the `world` GPUs of this run (llama-fft_b200/sharded.py), at 1 token (decode) and 2048 tokens (prefill).  Per shape: the unsharded
+    layer on one GPU, the rank-local slice alone, and the complete sharded forward with each exchange -- NCCL all-gather, push (slice
+    written in place, one bcl_push_columns launch over NVLink), p2p (stores to every peer fused into the producing kernels) -- with
+    the result checked against the unsharded layer on the same GPU.  CUDA events, max over ranks.  exchange_GBps = bytes a rank
+    RECEIVES, (G-1)/G * N * out * 2, over (total - local compute)."""
+    import torch
+    import torch.distributed as dist
+
+    def ev_time(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    rows = []
+    for name, inf, outf in SHAPES_70B:
+        torch.manual_seed(0)                                        # same weights on every rank
+        full = bc.BlockCirculantLinear(inf, outf, block_size=B70, bias=False, spectrum_dtype=torch.bfloat16).to(dev).eval()
+        shards = {}
+        for mode in ("nccl", "push", "p2p"):
+            try:
+                shards[mode] = bc.shard_bc_linear(full, exchange=mode)
+            except Exception as e:                                  # noqa: BLE001
+                shards[mode] = "%s: %s" % (type(e).__name__, e)
+        for ntok in (1, 2048):
+            x = torch.randn(ntok, inf, device=dev, generator=torch.Generator(device=dev).manual_seed(1)).half()
+            row = {"shape": "%dx%d" % (inf, outf), "name": name, "tokens": ntok, "world": world,
+                   "rows_per_rank": [j1 - j0 for j0, j1 in bc.shard_rows(outf // B70, world)]}
+            with torch.no_grad():
+                y_full = full(x)
+                row["unsharded_us"] = ev_time(lambda: full(x))
+                loc = shards["nccl"].local if not isinstance(shards["nccl"], str) else None
+                row["local_compute_us"] = ev_time((lambda: loc(x)) if loc is not None else (lambda: None))
+                recv_bytes = (world - 1) / world * ntok * outf * 2
+                for mode, sh in shards.items():
+                    if isinstance(sh, str):
+                        row[mode + "_error"] = sh[:200]
+                        continue
+                    try:
+                        y = sh(x)
+                        torch.cuda.synchronize()
+                        err = (y.float() - y_full.float()).abs().max().item() / max(y_full.float().abs().max().item(), 1e-30)
+                        t = torch.tensor([err], device=dev, dtype=torch.float64)
+                        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                        row[mode + "_rel_err_vs_unsharded"] = t.item()
+                        row[mode + "_total_us"] = ev_time(lambda: sh(x))
+                        ex_us = max(row[mode + "_total_us"] - row["local_compute_us"], 1e-3)
+                        row[mode + "_exchange_us"] = ex_us
+                        row[mode + "_exchange_GBps"] = recv_bytes / (ex_us * 1e-6) / 1e9
+                    except Exception as e:                          # noqa: BLE001
+                        row[mode + "_error"] = ("%s: %s" % (type(e).__name__, e))[:200]
+            rows.append({k: (round(v, 3) if isinstance(v, float) else v) for k, v in row.items()})
+        del full, shards
+        torch.cuda.empty_cache()
+    return {"what": "Llama-2-70B projection shapes, B = 256, bf16 spectra, fp16 activations, output block-rows sharded over %d GPUs; us, max over ranks" % world,
+            "rows": rows}
 
 
 def reference_cuda_detail(dev):

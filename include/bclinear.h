@@ -225,6 +225,16 @@ int bcl_backward_weights(const void* x, int x_dtype, int64_t x_row_stride, const
 int bcl_project_from_dense(const void* W, int w_dtype, int64_t w_row_stride, int p, int q, int B,
                            float* c, void* stream);
 
+/* ---- exchange step of output-block-row sharding (BASELINE.json configs[4]; no reference counterpart: SURVEY 2a / 8e) -----------
+ * Rank g of G holds block-rows [j0, j1) of c and computes y[:, j0*B : j1*B] -- with bcl_forward and y_row_stride = out it lands in
+ * place in the rank's own (N, out) buffer.  bcl_push_columns then copies that column slice into the SAME columns of n_dst peer
+ * buffers (peer-mapped device pointers, e.g. symmetric memory; same shape and row stride): a gather straight into the final layout,
+ * one read of the slice, one NVLink store per peer, no collective and no interleave pass afterwards.  src / dsts point at ROW 0,
+ * COLUMN 0 of the (N, out) buffers; col_offset / width in elements, 16-byte aligned in bytes.  The caller orders the exchange
+ * against the peers' reads (a barrier before and after; sharded.py uses the symmetric-memory handle's). */
+int bcl_push_columns(const void* src, void* const* dsts, int n_dst, int64_t N, int64_t row_stride, int64_t col_offset, int64_t width,
+                     int dtype, void* stream);
+
 /* ---- measurement aid ----------------------------------------------------------------------------------------------
  * Launches an EMPTY kernel (1 CTA, 32 threads) on `stream`; pdl != 0 launches it with the programmatic-stream-serialization
  * attribute the forward kernels use.  bench.py replays graphs of these to print the launch floor next to every

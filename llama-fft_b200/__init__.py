@@ -21,6 +21,6 @@ from .fft_utils import circulant_matvec_fft  # noqa: F401
 from .grouped import GroupedBCForward, HostPipe  # noqa: F401
 from .shared_input import SharedInputGroup, fuse_shared_inputs, unfuse_shared_inputs  # noqa: F401
 from .chain import BCChain, FusedBCMLP, fuse_mlp, unfuse_mlp, barrier_counter  # noqa: F401
-from .sharded import ShardedBlockCirculantLinear, shard_bc_linear, shard_rows, gather_columns  # noqa: F401
+from .sharded import ShardedBlockCirculantLinear, shard_bc_linear, shard_rows, gather_columns, push_columns  # noqa: F401
 
 __version__ = "0.1.0"

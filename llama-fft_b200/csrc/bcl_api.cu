@@ -366,6 +366,24 @@ int bcl_forward_chain(const bcl_problem* problems, const int* step_first, int ns
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "chain forward launch");
 }
 
+int bcl_push_columns(const void* src, void* const* dsts, int n_dst, int64_t N, int64_t row_stride, int64_t col_offset, int64_t width, int dtype, void* stream) {
+    if (!src || !dsts || n_dst < 0 || n_dst > bcl::kMaxExtraDst) return fail(BCL_ERR_ARG, "need a source and 0..%d destinations", bcl::kMaxExtraDst);
+    if (!valid_dt(dtype)) return fail(BCL_ERR_DTYPE, "unknown dtype enum");
+    if (N < 0 || width < 0 || col_offset < 0 || row_stride < col_offset + width) return fail(BCL_ERR_SHAPE, "slice [%lld, +%lld) does not fit rows of %lld elements", (long long)col_offset, (long long)width, (long long)row_stride);
+    const int es = bcl::dtype_size(dtype);
+    if ((row_stride * es) % 16 || (col_offset * es) % 16 || (width * es) % 16 || !aligned(src, 16)) return fail(BCL_ERR_ALIGN, "rows, slice offset and width must be multiples of 16 bytes");
+    if (N == 0 || width == 0 || n_dst == 0) return BCL_OK;
+    void* d[bcl::kMaxExtraDst];
+    for (int k = 0; k < n_dst; ++k) {
+        if (!dsts[k] || !aligned(dsts[k], 16)) return fail(BCL_ERR_ALIGN, "destination %d is NULL or not 16-byte aligned", k);
+        d[k] = reinterpret_cast<unsigned char*>(dsts[k]) + col_offset * es;
+    }
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = bcl::launch_push_columns(reinterpret_cast<const unsigned char*>(src) + col_offset * es, N, width * es, row_stride * es, d, n_dst, sms, (cudaStream_t)stream);
+    return e == cudaSuccess ? BCL_OK : cuda_fail(e, "push-columns launch");
+}
+
 int bcl_forward_host(const void* host_x, int x_dtype, int64_t N,
                      const void* spec, int spec_dtype, int layout, int p, int q, int B,
                      const void* bias, int bias_dtype, void* host_y, int y_dtype,

@@ -51,6 +51,22 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_split_kernel(const 
     dft_inv_body<B, true>(dft_smem, tmYf, tmW, tmOut, &lo, a, (int)blockIdx.x, (int)gridDim.x);
 }
 
+// multi-destination variants (sharded layer, exchange="p2p"): every finished tile also goes to the peers' y
+template <int B>
+__global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_bcast_kernel(const __grid_constant__ CUtensorMap tmYf, const __grid_constant__ CUtensorMap tmW,
+                                                                           const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ DftExtraOut ex,
+                                                                           const __grid_constant__ DftArgs a) {
+    extern __shared__ __align__(1024) unsigned char dft_smem[];
+    dft_inv_body<B, false>(dft_smem, tmYf, tmW, tmOut, nullptr, a, (int)blockIdx.x, (int)gridDim.x, &ex);
+}
+template <int B>
+__global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_split_bcast_kernel(const __grid_constant__ CUtensorMap tmYf, const __grid_constant__ CUtensorMap tmW,
+                                                                                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ DftLoMaps lo,
+                                                                                 const __grid_constant__ DftExtraOut ex, const __grid_constant__ DftArgs a) {
+    extern __shared__ __align__(1024) unsigned char dft_smem[];
+    dft_inv_body<B, true>(dft_smem, tmYf, tmW, tmOut, &lo, a, (int)blockIdx.x, (int)gridDim.x, &ex);
+}
+
 // =========================================================================================================
 // host side
 // =========================================================================================================
@@ -119,7 +135,7 @@ bool prep_dft_fwd(const ProblemDev& P, const Geometry& g, const void* spec_gemm,
 }
 
 bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L,
-                  const void* Yf_lo, DftLoMaps* lo) {
+                  const void* Yf_lo, DftLoMaps* lo, DftExtraOut* ex) {
     const bool split = lo != nullptr;
     const int B = g.B;
     const bool bf = P.x_dtype == BCL_BF16;
@@ -132,6 +148,11 @@ bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm,
         const uint64_t strides[1] = {(uint64_t)P.y_stride * 2};
         const uint32_t box[2] = {KATOM, 32};
         if (!make_tensor_map(&L.tm_out, adt, 2, P.y, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
+        if (ex != nullptr) {
+            ex->n = P.n_extra;
+            for (int e = 0; e < P.n_extra; ++e)
+                if (!make_tensor_map(&ex->out[e], adt, 2, P.y_extra[e], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
+        }
     }
     DftArgs& a = L.a;
     a = DftArgs{};
@@ -180,20 +201,24 @@ cudaError_t launch_dft_fwd_tc(const ProblemDev& P, const Geometry& g, const void
 cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, const void* Yf_lo, int* status,
                               int max_ctas, cudaStream_t st) {
     StageLaunch<DftArgs> L;
+    const bool bcast = P.n_extra > 0;                               // peer destinations: the *_bcast kernels store every tile to all of them
+    DftExtraOut ex;
     if (g.split && Yf_lo != nullptr) {
         DftLoMaps lo;
-        if (!prep_dft_inv(P, g, spec_gemm, n_begin, nc, Yf, status, L, Yf_lo, &lo)) return cudaErrorNotSupported;
+        if (!prep_dft_inv(P, g, spec_gemm, n_begin, nc, Yf, status, L, Yf_lo, &lo, bcast ? &ex : nullptr)) return cudaErrorNotSupported;
+        if (bcast) return g.B == 128 ? launch_stage(dft_inv_tc_split_bcast_kernel<128>, L, max_ctas, st, lo, ex) : launch_stage(dft_inv_tc_split_bcast_kernel<64>, L, max_ctas, st, lo, ex);
         return g.B == 128 ? launch_stage(dft_inv_tc_split_kernel<128>, L, max_ctas, st, lo) : launch_stage(dft_inv_tc_split_kernel<64>, L, max_ctas, st, lo);
     }
-    if (!prep_dft_inv(P, g, spec_gemm, n_begin, nc, Yf, status, L)) return cudaErrorNotSupported;
+    if (!prep_dft_inv(P, g, spec_gemm, n_begin, nc, Yf, status, L, nullptr, nullptr, bcast ? &ex : nullptr)) return cudaErrorNotSupported;
     if (g.B == 256) {                                               // two launches: output samples [0,128) and [128,256) of every block
         for (int half = 0; half < 2; ++half) {
             L.a.half = half;
-            cudaError_t e = launch_stage(dft_inv_tc_kernel<256>, L, max_ctas, st);
+            cudaError_t e = bcast ? launch_stage(dft_inv_tc_bcast_kernel<256>, L, max_ctas, st, ex) : launch_stage(dft_inv_tc_kernel<256>, L, max_ctas, st);
             if (e != cudaSuccess) return e;
         }
         return cudaSuccess;
     }
+    if (bcast) return g.B == 128 ? launch_stage(dft_inv_tc_bcast_kernel<128>, L, max_ctas, st, ex) : launch_stage(dft_inv_tc_bcast_kernel<64>, L, max_ctas, st, ex);
     return g.B == 128 ? launch_stage(dft_inv_tc_kernel<128>, L, max_ctas, st) : launch_stage(dft_inv_tc_kernel<64>, L, max_ctas, st);
 }
 

@@ -478,7 +478,7 @@ cudaError_t launch_prefill_stage1(const ProblemDev& P, int B, const void* spec_g
 
 cudaError_t launch_prefill_stage3(const ProblemDev& P, int B, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, int impl, cudaStream_t st) {
     const gemm::Geometry g = gemm::geometry(P.p, P.q, B);
-    const bool tc_ok = gemm::dft_tc_supported(B, P.x_dtype) && P.y_dtype == P.x_dtype && spec_gemm != nullptr && P.n_extra == 0;   // peer destinations: plain stores
+    const bool tc_ok = gemm::dft_tc_supported(B, P.x_dtype) && P.y_dtype == P.x_dtype && spec_gemm != nullptr;   // (peer destinations: one TMA store per destination)
     if (impl == 2 && !tc_ok) return cudaErrorNotSupported;
     if (impl != 1 && tc_ok) return gemm::launch_dft_inv_tc(P, g, spec_gemm, n_begin, nc, Yf, nullptr, status, sm_count(), st);
     return launch_gemm_irfft(P, B, n_begin, nc, Yf, nullptr, st);
@@ -513,10 +513,10 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
         static const int impl_s = getenv("BCL_PREFILL_DFT") ? atoi(getenv("BCL_PREFILL_DFT")) : 0;   // 1: force the CUDA-core FFT stages
         // 16-bit activations, B <= 128: the DFT stages run on the tensor cores too, with (hi, lo) DFT matrices
         const bool tc1 = impl_s != 1 && B <= 128 && gemm::dft_tc_supported(B, P.x_dtype);   // B = 256: the (hi, lo) DFT matrices do not fit
-        const bool tc3 = tc1 && P.y_dtype == P.x_dtype && P.n_extra == 0;
+        const bool tc3 = tc1 && P.y_dtype == P.x_dtype;
         for (int64_t n0 = 0; n0 < P.N; n0 += ncmax) {
             const int nc = (int)((P.N - n0 < ncmax) ? (P.N - n0) : ncmax);
-            if (tc1 && tc3 && chain_enabled() && ctas >= 8) {                // all three stages on the tensor cores: one launch
+            if (tc1 && tc3 && chain_enabled() && ctas >= 8 && P.n_extra == 0) {                // all three stages on the tensor cores: one launch
                 if ((e = cudaMemsetAsync(ws + kWsHeader, 0, 256, st)) != cudaSuccess) return e;
                 if ((e = gemm::launch_prefill_chain(P, g, spec_gemm, n0, nc, Xf, Xf_lo, Yf, Yf_lo, status, reinterpret_cast<int*>(ws + kWsHeader), ctas, st)) != cudaSuccess) return e;
                 continue;
@@ -535,8 +535,8 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
     // costs what the saved HBM passes gain (profiles/r1_prefill_notes.md).  BCL_FUSED_MIN_TILES=<tiles> enables it.
     static const int fused_min_tiles = getenv("BCL_FUSED_MIN_TILES") ? atoi(getenv("BCL_FUSED_MIN_TILES")) : 0;    // <= 0: never
     const int ctas = sm_count();
-    const bool tc_ok = impl != 1 && spec_gemm != nullptr && gemm::dft_tc_supported(B, P.x_dtype) && P.y_dtype == P.x_dtype && P.n_extra == 0;
-    if (tc_ok && B <= 128 && ncmax >= P.N && fused_min_tiles > 0 && (P.N + gemm::TILE_M - 1) / gemm::TILE_M >= fused_min_tiles && ctas >= 12) {
+    const bool tc_ok = impl != 1 && spec_gemm != nullptr && gemm::dft_tc_supported(B, P.x_dtype) && P.y_dtype == P.x_dtype;
+    if (tc_ok && P.n_extra == 0 && B <= 128 && ncmax >= P.N && fused_min_tiles > 0 && (P.N + gemm::TILE_M - 1) / gemm::TILE_M >= fused_min_tiles && ctas >= 12) {
         // one launch: the three stages pipelined tile by tile over L2-resident Xf / Yf (bcl_prefill_fused.cu)
         cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int), st);                       // (status[1] is sticky: never cleared here)
         if (e == cudaSuccess) e = cudaMemsetAsync(ws + kWsHeader, 0, ctr_bytes, st);
@@ -547,7 +547,7 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
     if (e != cudaSuccess) return e;
     for (int64_t n0 = 0; n0 < P.N; n0 += ncmax) {
         const int nc = (int)((P.N - n0 < ncmax) ? (P.N - n0) : ncmax);
-        if (tc_ok && impl == 0 && chain_enabled() && ctas >= 8) {            // all three stages on the tensor cores: one launch
+        if (tc_ok && impl == 0 && chain_enabled() && ctas >= 8 && P.n_extra == 0) {            // all three stages on the tensor cores: one launch
             if ((e = cudaMemsetAsync(ws + kWsHeader, 0, 256, st)) != cudaSuccess) return e;
             if ((e = gemm::launch_prefill_chain(P, g, spec_gemm, n0, nc, Xf, nullptr, Yf, nullptr, status, reinterpret_cast<int*>(ws + kWsHeader), ctas, st)) != cudaSuccess) return e;
             continue;

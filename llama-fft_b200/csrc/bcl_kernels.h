@@ -83,6 +83,9 @@ cudaError_t launch_conj_transpose(const float* c, int p, int q, int B, float* ct
 cudaError_t launch_backward_weights(const void* x, int x_dtype, int64_t x_stride, const void* gy, int gy_dtype, int64_t gy_stride, int64_t N, int p, int q,
                                     int B, float* dc, int accumulate, void* workspace, cudaStream_t st);
 
+// exchange step of the sharded layer (bcl_exchange.cu)
+cudaError_t launch_push_columns(const void* src, int64_t rows, int64_t row_bytes, int64_t pitch_bytes, void* const* dsts, int n_dst, int sms, cudaStream_t st);
+
 cudaError_t launch_project_from_dense(const void* W, int w_dtype, int64_t w_stride, int p, int q, int B, float* c, cudaStream_t st);
 
 }  // namespace bcl

@@ -456,6 +456,9 @@ template <int B> struct DftShape {
 // forward: x -> Xf
 // =========================================================================================================
 struct DftLoMaps { CUtensorMap W, IO; };         // split layout: the lo DFT matrix, and Xf_lo (forward, store) / Yf_lo (inverse, load)
+// Sharded layer, exchange fused into the producer (sharded.py exchange="p2p"): the inverse stage's finished tile is TMA-stored into the
+// same rows / columns of every peer's y as well (peer-mapped symmetric memory: the stores travel over NVLink), so no collective follows.
+struct DftExtraOut { CUtensorMap out[kMaxExtraDst]; int n; };
 
 // SPLIT (fp32 spectra): the activations are exact in their 16-bit format; W = Whi + Wlo (same format), two MMAs per k-step;
 // the fp32 accumulators leave as (hi, lo) bf16 pairs into Xf and Xf_lo.
@@ -680,7 +683,7 @@ __device__ __forceinline__ void store_row(unsigned char* row, int lane, const ui
 // One staging buffer per epilogue warp instead of two, so that two 64 KB (hi, lo) stages fit next to the two DFT matrices.
 template <int B, bool SPLIT>
 __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUtensorMap& tmYf, const CUtensorMap& tmW, const CUtensorMap& tmOut,
-                                             const DftLoMaps* lo, const DftArgs& a, const int first, const int stride) {
+                                             const DftLoMaps* lo, const DftArgs& a, const int first, const int stride, const DftExtraOut* ex = nullptr) {
     using SH = DftShape<B>;
     constexpr int NB = SH::NB, PARTS = SH::PARTS;
     constexpr int ATOMS = SH::KATOMS;                        // K atoms of the DFT matrix (K = B packed spectrum reals)
@@ -712,6 +715,7 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmYf); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmOut);
         if constexpr (SPLIT) { tma_prefetch_desc(&lo->W); tma_prefetch_desc(&lo->IO); }
+        if (ex != nullptr) for (int e = 0; e < ex->n; ++e) tma_prefetch_desc(&ex->out[e]);
     }
     if (warp == 1) tmem_alloc(&bars->tmem_base, NACC * NB);
     tc_fence_before_sync();
@@ -827,6 +831,9 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
                 __syncwarp();
                 if (lane == 0) {
                     tma_store_2d(&tmOut, col0, (int)(a.n_begin + (int64_t)m * TILE_M + quarter * 32), stg + (size_t)buf * DFT_EPI_BUF);
+                    if (ex != nullptr)                                           // the peers' copies of y: same tile, same coordinates
+                        for (int e = 0; e < ex->n; ++e)
+                            tma_store_2d(&ex->out[e], col0, (int)(a.n_begin + (int64_t)m * TILE_M + quarter * 32), stg + (size_t)buf * DFT_EPI_BUF);
                     tma_store_commit();
                 }
                 if (++buf == NBUF) buf = 0;
@@ -865,7 +872,7 @@ bool prep_dft_fwd(const ProblemDev& P, const Geometry& g, const void* spec_gemm,
 bool prep_gemm(const void* Xf, const void* Cmat, void* Yf, int* status, const Geometry& g, int nc, StageLaunch<GemmArgs>& L, GemmLoMaps* lo = nullptr);
 bool prep_gemm_lo(const void* Xf_lo, const void* Cmat, void* Yf_lo, const Geometry& g, int nc, GemmLoMaps* lo);
 bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L,
-                  const void* Yf_lo = nullptr, DftLoMaps* lo = nullptr);
+                  const void* Yf_lo = nullptr, DftLoMaps* lo = nullptr, DftExtraOut* ex = nullptr);
 
 }  // namespace gemm
 }  // namespace bcl

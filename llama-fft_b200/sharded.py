@@ -4,9 +4,13 @@ The reference has no distributed code.  The BC forward shards natura
 c[j0_g:j1_g] (and its spectrum), sees the full x (N, in), computes y[:, j0_g*B : j1_g*B] with the same sm_100a kernels as
 the unsharded layer, and the slices meet in ONE exchange step:
 
-    exchange="nccl"   torch.distributed all_gather_into_tensor over NCCL / NVLink, then a column interleave
-    exchange="p2p"    every rank's kernels store their slice straight into EVERY peer's y buffer (symmetric memory,
-                      NVLink peer stores): the gather is fused into the producing kernels, no collective afterwards
+    exchange="nccl"   torch.distributed all_gather_into_tensor over NCCL / NVLink.  One token with an even split gathers straight into
+                      y (slices of a single row ARE the final layout); several tokens need one interleave copy (G, N, out/G) -> (N, out)
+    exchange="push"   the rank's kernels write its slice IN PLACE into its own (N, out) symmetric buffer (y_row_stride = out), then one
+                      bcl_push_columns launch stores the slice into the same columns of every peer's buffer: the gather lands in the
+                      final layout, bytes cross NVLink once, no collective and no interleave pass
+    exchange="p2p"    fully fused: the producing kernels' epilogues store every finished tile into EVERY peer's y as well (stream kernel:
+                      peer stores; tensor-core inverse DFT: one TMA store per destination); nothing runs afterwards
 
 Block-rows are split as evenly as possible; when p is not divisible by the world size the NCCL path pads the slices to the
 largest one (70B k/v: p = 4 on 8 ranks leaves ranks idle; ``shard_rows`` reports empty ranges for them).
@@ -36,23 +40,32 @@ def shard_rows(p: int, world: int) -> List[Tuple[int, int]]:
 
 def gather_columns(y_local: torch.Tensor, ranges: List[Tuple[int, int]], B: int, group=None) -> torch.Tensor:
     """All-gather column slices: y_local is (N, (j1-j0)*B) on every rank -> (N, p*B) everywhere.
-    Slices are padded to the widest one so that the collective is a plain all_gather_into_tensor."""
+    Even split, one token: the collective writes y directly (row 0's slices back to back are the final layout).  Otherwise the
+    slices (padded to the widest when the split is ragged) are gathered as (G, N, w) and ONE permuting copy lays them out."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     N = y_local.shape[0]
-    wmax = max(j1 - j0 for j0, j1 in ranges) * B
+    widths = [(j1 - j0) * B for j0, j1 in ranges]
+    wmax = max(widths)
+    p = ranges[-1][1]
+    assert widths[rank] == y_local.shape[1]
+    even = all(w == wmax for w in widths)
+    if even and N == 1:
+        y = y_local.new_empty(1, p * B)
+        dist.all_gather_into_tensor(y.view(world, wmax), y_local.contiguous(), group=group)
+        return y
     send = y_local
     if y_local.shape[1] != wmax:
         send = y_local.new_zeros(N, wmax)
         send[:, :y_local.shape[1]] = y_local
     recv = y_local.new_empty(world, N, wmax)
     dist.all_gather_into_tensor(recv.view(world * N, wmax), send.contiguous(), group=group)
-    p = ranges[-1][1]
+    if even:
+        return recv.permute(1, 0, 2).reshape(N, p * B)               # one copy kernel: (G, N, w) -> (N, G * w)
     y = y_local.new_empty(N, p * B)
     for r, (j0, j1) in enumerate(ranges):
         if j1 > j0:
             y[:, j0 * B:j1 * B] = recv[r, :, :(j1 - j0) * B]
-    assert ranges[rank][1] - ranges[rank][0] == y_local.shape[1] // B
     return y
 
 
@@ -61,8 +74,8 @@ class ShardedBlockCirculantLinear(nn.Module):
 
     def __init__(self, full: BlockCirculantLinear, group=None, *, exchange: str = "nccl"):
         super().__init__()
-        if exchange not in ("nccl", "p2p"):
-            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        if exchange not in ("nccl", "push", "p2p"):
+            raise ValueError("exchange must be 'nccl', 'push' or 'p2p'")
         self.group = group
         self.exchange = exchange
         self.world = dist.get_world_size(group)
@@ -115,13 +128,23 @@ class ShardedBlockCirculantLinear(nn.Module):
             else:                                           # a rank without rows still joins the collective, in the dtype the others produce
                 y_loc = torch.empty(N, 0, device=x.device, dtype=self.y_dtype(x.dtype))
             y = gather_columns(y_loc, self.ranges, B, self.group)
+        elif self.exchange == "push":
+            y_dtype = self.y_dtype(x.dtype)
+            y, peers = self._symmetric_y(N, y_dtype, x.device)
+            hdl = self._symm[3]
+            hdl.barrier()                                   # peers finished reading the previous contents
+            if self.local is not None:
+                bc_forward_bcast(self.local, x, [y[:, self.j0 * B:self.j1 * B]])        # in place, final layout (row stride = out)
+                push_columns(y, [pv for r, pv in enumerate(peers) if r != self.rank], self.j0 * B, (self.j1 - self.j0) * B)
+            hdl.barrier()                                   # every slice of every peer has landed
         else:
             y_dtype = self.y_dtype(x.dtype)
             y, peers = self._symmetric_y(N, y_dtype, x.device)
             hdl = self._symm[3]
             hdl.barrier()                                   # peers finished reading the previous contents
             if self.local is not None:                      # ONE forward whose epilogue stores into every rank's y
-                bc_forward_bcast(self.local, x, [pv[:, self.j0 * B:self.j1 * B] for pv in peers])
+                order = [peers[self.rank]] + [pv for r, pv in enumerate(peers) if r != self.rank]   # own copy first (plain address)
+                bc_forward_bcast(self.local, x, [pv[:, self.j0 * B:self.j1 * B] for pv in order])
             hdl.barrier()                                   # every slice of every peer has landed
         if lead is not None:
             return y.view(lead[0], lead[1], self.out_features)
@@ -155,6 +178,21 @@ def bc_forward_bcast(layer: BlockCirculantLinear, x: torch.Tensor, dsts: List[to
                                  None if bias is None else bias.data_ptr(), 0 if bias is None else _cabi.DTYPE[bias.dtype],
                                  ptrs, len(dsts), _cabi.DTYPE[d0.dtype], d0.stride(0), ws_ptr, ws_bytes, _cabi.stream_ptr(x.device))
     _cabi.check(rc, "bcl_forward_bcast")
+
+
+def push_columns(y: torch.Tensor, dsts: List[torch.Tensor], col_offset: int, width: int) -> None:
+    """``bcl_push_columns``: copy y[:, col_offset : col_offset + width] into the same columns of every tensor of `dsts` (peer-mapped
+    buffers of the same shape / strides / dtype)."""
+    import ctypes
+    from . import _cabi
+    if not dsts or width == 0 or y.shape[0] == 0:
+        return
+    assert all(d.shape == y.shape and d.stride() == y.stride() and d.dtype == y.dtype for d in dsts) and y.stride(1) == 1
+    ptrs = (ctypes.c_void_p * len(dsts))(*[d.data_ptr() for d in dsts])
+    with _cabi.on_device(y.device):
+        rc = _cabi.lib().bcl_push_columns(y.data_ptr(), ptrs, len(dsts), y.shape[0], y.stride(0), col_offset, width, _cabi.DTYPE[y.dtype],
+                                          _cabi.stream_ptr(y.device))
+    _cabi.check(rc, "bcl_push_columns")
 
 
 def shard_bc_linear(layer: BlockCirculantLinear, group=None, *, exchange: str = "nccl") -> ShardedBlockCirculantLinear:
