@@ -582,6 +582,36 @@ def dependent_chain_detail(bc, _cabi, dev, time_graph):
            "bc_us_per_layer_whole_layer_one_launch": whole_ms * 1e3 / N_LAYERS,
            "hbm_frac_of_measured_peak": layer_bytes / (three_ms * 1e-3 / N_LAYERS) / 1e9 / peak,
            "algorithmic_bytes_per_layer": layer_bytes}
+    # end to end for ONE token through that chain, moving what a real token moves: 8 KB of hidden state in (pinned host -> device),
+    # 96 launches (one CUDA-graph replay), 8 KB of hidden state out, stream synchronised -- every token
+    try:
+        hx = torch.randn(1, H).half().pin_memory()
+        hy = torch.empty(1, H, dtype=torch.float16).pin_memory()
+        s2 = torch.cuda.Stream(dev)
+        with torch.cuda.stream(s2):
+            for c in three:
+                c.run()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=s2):
+                for c in three:
+                    c.run()
+
+            def token():
+                x0.copy_(hx, non_blocking=True)
+                graph.replay()
+                hy.copy_(cur, non_blocking=True)
+                s2.synchronize()
+            for _ in range(5):
+                token()
+            t0 = time.perf_counter()
+            for _ in range(200):
+                token()
+            tok_s = 200 / (time.perf_counter() - t0)
+        res["e2e_token_path"] = {"tokens_per_s": tok_s, "us_per_token": 1e6 / tok_s, "h2d_bytes_per_token": H * 2, "d2h_bytes_per_token": H * 2,
+                                 "what": "per token: pinned hidden state -> device, one graph replay of the 96-launch chain, hidden state -> pinned host, synchronise (wall clock)"}
+    except Exception as e:                                               # noqa: BLE001
+        res["e2e_token_path"] = {"error": "%s: %s" % (type(e).__name__, e)}
     bc_ms = three_ms
     del three, whole
     del layers

@@ -149,6 +149,93 @@ def perf_generate(model, tokenized: Tokenized, device: torch.device, pad_id: int
     return {"decode_new_tokens_per_s": runs * len(tokenized) * max_new_tokens / wall, "decode_total_s": wall}
 
 
+class GraphDecoder:
+    """Greedy single-sequence decode with the per-token model step captured in ONE CUDA graph (HF StaticCache, static token / position
+    buffers; token selection and position increment are part of the graph, so a generated token costs one graph replay and no host
+    synchronisation).  Why: HF ``generate`` spends ~25 ms of Python per step on a 7B-shaped model while the GPU needs 0.7-2 ms
+     -- per-layer microseconds only reach tokens/s once the host is out of the loop.  The reference's
+    ``perf_generate`` (src/bench_all_in_one.py:393-427) times ``model.generate``; this is the same greedy decode, same metric."""
+
+    def __init__(self, model, device: torch.device, max_cache_len: int):
+        from transformers import StaticCache
+        self.model, self.device, self.max_cache_len = model, device, max_cache_len
+        self.cache = StaticCache(config=model.config, max_cache_len=max_cache_len)
+        self.tok = torch.zeros(1, 1, dtype=torch.long, device=device)
+        self.pos = torch.zeros(1, dtype=torch.long, device=device)
+        self.out = torch.zeros(1, max_cache_len, dtype=torch.long, device=device)
+        self.slot = torch.zeros(1, dtype=torch.long, device=device)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.stream = torch.cuda.Stream(device) if device.type == "cuda" else None
+
+    def _step(self) -> None:
+        logits = self.model(input_ids=self.tok, past_key_values=self.cache, cache_position=self.pos, use_cache=True).logits[:, -1]
+        self.tok.copy_(logits.argmax(-1, keepdim=True))
+        self.out.index_copy_(1, self.slot, self.tok)
+        self.pos.add_(1)
+        self.slot.add_(1)
+
+    @torch.inference_mode()
+    def generate(self, input_ids: torch.Tensor, max_new_tokens: int) -> torch.Tensor:
+        """input_ids (1, T) -> (1, max_new_tokens) greedy continuation."""
+        T = input_ids.shape[1]
+        if T + max_new_tokens > self.max_cache_len:
+            raise ValueError("prompt + new tokens exceed the static cache")
+        ctx = torch.cuda.stream(self.stream) if self.stream is not None else _nullcontext()
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with ctx:
+            self.cache.reset()
+            logits = self.model(input_ids=input_ids, past_key_values=self.cache, cache_position=torch.arange(T, device=self.device), use_cache=True).logits[:, -1]
+            self.tok.copy_(logits.argmax(-1, keepdim=True))
+            self.out.zero_()
+            self.out[:, 0:1] = self.tok
+            self.pos.fill_(T)
+            self.slot.fill_(1)
+            steps = max_new_tokens - 1
+            if self.stream is None:
+                for _ in range(steps):
+                    self._step()
+            else:
+                if self.graph is None and steps > 0:                # capture once: one eager step to warm every lazy allocation, then record
+                    self._step()
+                    steps -= 1
+                    torch.cuda.synchronize(self.device)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self.stream):
+                        self._step()
+                    self.graph = g
+                    steps -= 1                                      # the capture pass does not execute: replay it once for this token
+                    self.graph.replay()
+                for _ in range(max(steps, 0)):
+                    self.graph.replay()
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return self.out[:, :max_new_tokens].clone()
+
+
+class _nullcontext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+@torch.inference_mode()
+def perf_generate_graph(model, tokenized: Tokenized, device: torch.device, warmup: int, runs: int, max_new_tokens: int) -> Dict[str, float]:
+    """The reference's decode metric (decode_new_tokens_per_s = runs * prompts * max_new_tokens / wall, src/bench_all_in_one.py:424-426)
+    with the decode step under CUDA-graph replay, one sequence at a time (batch 1, the decode configuration of BASELINE.json)."""
+    max_len = max(int(a.sum().item()) for _, a in tokenized) + max_new_tokens
+    dec = GraphDecoder(model, device, max_len)
+    prompts = [ids[:int(a.sum().item())].unsqueeze(0).to(device) for ids, a in tokenized]
+
+    def once():
+        for ids in prompts:
+            dec.generate(ids, max_new_tokens)
+    wall, _ = _timed(device, once, warmup, runs)
+    return {"decode_graph_new_tokens_per_s": runs * len(prompts) * max_new_tokens / wall, "decode_graph_total_s": wall}
+
+
 RANDOM_INIT = {
     "tiny": dict(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=8, num_key_value_heads=8, vocab_size=320,
                  max_position_embeddings=512),
@@ -187,6 +274,8 @@ def main(argv=None):
     ap.add_argument("--targets", choices=["mlp", "all"], default="mlp", help="mlp = the reference's gate/up/down; all = + q/k/v/o")
     ap.add_argument("--spectrum", choices=["float32", "bfloat16"], default="float32")
     ap.add_argument("--fuse_shared_inputs", type=int, default=0)
+    ap.add_argument("--fuse_mlp", type=int, default=0, help="single-token MLP calls as one chain launch (gate|up + SiLU*mul + down)")
+    ap.add_argument("--graph_decode", type=int, default=0, help="also time greedy decode with the per-token step under CUDA-graph replay")
     ap.add_argument("--calib_dir", type=str, default="", help="directory with bc_calibrated_B{B}.pt (src/calibrate_bc.py:302)")
     ap.add_argument("--dtype", type=str, default="fp16")
     ap.add_argument("--device", type=str, default="cuda")
@@ -237,6 +326,9 @@ def main(argv=None):
                 from .shared_input import fuse_shared_inputs
                 row["shared_input_groups"] = fuse_shared_inputs(model)
                 groups = list({id(m._shared_group): m._shared_group for m in model.modules() if getattr(m, "_shared_group", None) is not None}.values())
+            if args.fuse_mlp:
+                from .chain import fuse_mlp
+                row["fused_mlps"] = fuse_mlp(model)
         if B == 0:
             teacher_cache = compute_teacher_last_cache(model, tokenized, device)
         else:
@@ -245,6 +337,13 @@ def main(argv=None):
         if args.do_generate:
             row.update(perf_generate(model, tokenized, device, pad_id, args.batch_size, max(1, args.warmup // 2), max(1, args.runs // 2),
                                      args.max_new_tokens))
+        if args.do_generate and args.graph_decode:
+            try:
+                row.update(perf_generate_graph(model, tokenized, device, max(1, args.warmup // 2), max(1, args.runs // 2), args.max_new_tokens))
+            except Exception as e:                                   # noqa: BLE001 -- HF internals that cannot be captured: report, keep the eager figure
+                row["decode_graph_error"] = f"{type(e).__name__}: {e}"[:300]
+        if B and args.fuse_mlp:
+            row["fused_mlp_calls"] = sum(m._bcl_fused_mlp.fused_calls for m in model.modules() if hasattr(m, "_bcl_fused_mlp"))
         if B and args.fuse_shared_inputs:
             row["shared_input_fused_calls"] = sum(g.fused_calls for g in groups)     # > 0: the fused path really served the forwards
         if B == 0:
@@ -253,6 +352,8 @@ def main(argv=None):
             row["prefill_speedup_vs_dense"] = row["prefill_tokens_per_s"] / dense_row["prefill_tokens_per_s"]
             if args.do_generate:
                 row["decode_speedup_vs_dense"] = row["decode_new_tokens_per_s"] / dense_row["decode_new_tokens_per_s"]
+                if "decode_graph_new_tokens_per_s" in row and "decode_graph_new_tokens_per_s" in dense_row:
+                    row["decode_graph_speedup_vs_dense"] = row["decode_graph_new_tokens_per_s"] / dense_row["decode_graph_new_tokens_per_s"]
         rows.append(row)
         print(json.dumps(row), flush=True)
         del model

@@ -378,3 +378,31 @@ def test_calibrate_default_prompts_file_exists():
     from llama_fft_b200 import calibrate_bc
     import os
     assert os.path.exists(calibrate_bc.build_parser().parse_args([]).prompts_file)
+
+
+def test_lm_eval_adapter_on_cpu_without_bc_layers_matches_direct_scores():
+    """num_layers=0 leaves the model dense, so the adapter's request handling (tokenisation, windowing, greedy flag) can be checked on CPU."""
+    import math
+    from llama_fft_b200.lm_eval_adapter import LlamaFftLM
+    lm = LlamaFftLM(pretrained="", random_init="tiny", dtype="float32", device="cpu", num_layers=0, max_length=16)
+    ctx, cont = "abc", "defg"
+    (ll, greedy), = lm.loglikelihood([(ctx, cont)])
+    ids = lm.tok_encode(ctx) + lm.tok_encode(cont)
+    with torch.no_grad():
+        logits = lm.model(input_ids=torch.tensor([ids[:-1]])).logits[0]
+    want = torch.log_softmax(logits[-4:], -1).gather(-1, torch.tensor(ids[-4:])[:, None]).sum().item()
+    assert math.isclose(ll, want, rel_tol=1e-5, abs_tol=1e-5)
+    long_text = "x" * 40                                              # 40 tokens through windows of 15
+    (roll,) = lm.loglikelihood_rolling([(long_text,)])
+    assert roll < 0 and lm.loglikelihood([("", "a")])[0][0] < 0
+
+
+def test_fuse_mlp_attaches_and_detaches_on_cpu():
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=2, vocab_size=64)
+    model = LlamaForCausalLM(cfg).eval()
+    bc.patch_llama_fft(model, block_size=64)
+    assert bc.fuse_mlp(model) == 2 and bc.fuse_mlp(model) == 0
+    mlp = model.model.layers[0].mlp
+    assert not mlp._bcl_fused_mlp.eligible(torch.zeros(1, 1, 128))        # CPU tensor: the original forward (which then refuses: no CPU path)
+    assert bc.unfuse_mlp(model) == 2 and "forward" not in mlp.__dict__
