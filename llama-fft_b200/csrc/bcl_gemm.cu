@@ -543,6 +543,21 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
         if (e != cudaSuccess) return e;
         return gemm::launch_prefill_fused(P, g, spec_gemm, Xf, Yf, status, reinterpret_cast<int*>(ws + kWsHeader), ctas, st);
     }
+    // Wave schedule (bcl_prefill_wave.cu): one launch, all three stages interleaved on every SM over L2-resident rings of Xf / Yf.
+    // BCL_PREFILL_WAVE=0 disables it, BCL_PREFILL_WAVE_MIN_TILES moves the switch-over (token tiles of 128).
+    // (read per call: tests and tools/wave_bench.py switch it inside one process)
+    const char* wave_env = getenv("BCL_PREFILL_WAVE");
+    const int wave_on = wave_env ? atoi(wave_env) : 0;
+    const char* wave_min_env = getenv("BCL_PREFILL_WAVE_MIN_TILES");
+    const int wave_min_tiles = wave_min_env ? atoi(wave_min_env) : 48;
+    if (wave_on && tc_ok && impl == 0 && ctas >= 8 && gemm::wave_supported(P, g) && (P.N + gemm::TILE_M - 1) / gemm::TILE_M >= wave_min_tiles &&
+        workspace_bytes > kWsHeader + ctr_bytes) {
+        cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ws + kWsHeader, 0, ctr_bytes, st);
+        if (e != cudaSuccess) return e;
+        e = gemm::launch_prefill_wave(P, g, spec_gemm, Xf, workspace_bytes - kWsHeader - ctr_bytes, status, reinterpret_cast<int*>(ws + kWsHeader), ctas, st);
+        if (e != cudaErrorInvalidValue) return e;              // (workspace too small for the rings: the three launches below)
+    }
     cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     for (int64_t n0 = 0; n0 < P.N; n0 += ncmax) {

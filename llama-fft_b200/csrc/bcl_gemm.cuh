@@ -110,5 +110,12 @@ cudaError_t launch_prefill_chain(const ProblemDev& P, const Geometry& g, const v
 cudaError_t launch_prefill_fused(const ProblemDev& P, const Geometry& g, const void* spec_gemm, void* Xf, void* Yf, int* status, int* counters, int ctas,
                                  cudaStream_t st);
 
+
+// Wave schedule (bcl_prefill_wave.cu): ONE launch, every CTA interleaves forward-DFT / GEMM / inverse-DFT items `lag` token tiles
+// apart over L2-resident rings of Xf / Yf.  area: workspace bytes for the rings; counters: 3 * ceil(N/128) ints, zeroed before.
+bool wave_supported(const ProblemDev& P, const Geometry& g);
+cudaError_t launch_prefill_wave(const ProblemDev& P, const Geometry& g, const void* spec_gemm, void* area, size_t area_bytes, int* status, int* counters,
+                                int ctas, cudaStream_t st);
+
 }  // namespace gemm
 }  // namespace bcl

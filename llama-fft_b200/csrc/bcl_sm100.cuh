@@ -97,6 +97,10 @@ __device__ __forceinline__ void tma_load_4d(void* dst_smem, const void* tmap, in
                  ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 prefetch of a 2-D tile (no shared-memory destination, no barrier): brings an HBM tile into L2 ahead of the load that needs it.
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
 // L2 eviction-priority hints (the fixed createpolicy encodings): streamed-once data must not push out what the next stage re-reads.
 constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
 constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;

@@ -420,6 +420,42 @@ def test_prefill_fused_single_launch_matches_three_launch_chain(tmp_path, inf, o
         assert_close(outs["fused"][rows], O.bc_forward_torch(c, x[rows].float()), 1e-2, dtype)
 
 
+@pytest.mark.parametrize("inf,outf,B,N,dt,has_bias,lag,ring", [(4096, 4096, 128, 6144 + 77, "f16", 0, 0, 0), (4096, 4096, 128, 4096, "bf16", 1, 6, 14),
+                                                               (4096, 11008, 128, 1500, "bf16", 1, 3, 8), (11008, 4096, 128, 1024, "f16", 0, 2, 6),
+                                                               (1024, 512, 64, 3000, "f16", 1, 4, 9)])
+def test_prefill_wave_single_launch_matches_three_launch_chain(monkeypatch, inf, outf, B, N, dt, has_bias, lag, ring):
+    """The opt-in wave-schedule kernel (bcl_prefill_wave.cu, BCL_PREFILL_WAVE=1): every CTA interleaves forward-DFT / GEMM / inverse-DFT
+    items `lag` tiles apart over rings of `ring` tiles of Xf / Yf.  Same MMAs on the same tiles as the three stage launches: the output
+    must be BIT-identical, also when ring slots are reused (ring < tiles) and with a ragged last tile.  The switch is read per call."""
+    dtype = {"f16": torch.float16, "bf16": torch.bfloat16}[dt]
+    g = torch.Generator().manual_seed(inf + outf + B + N)
+    c = torch.randn(outf // B, inf // B, B, generator=g) * 0.01
+    x = torch.randn(N, inf, generator=g).to(dtype).to(DEV)
+    m = bc.BlockCirculantLinear(inf, outf, block_size=B, bias=bool(has_bias), spectrum_dtype=torch.bfloat16)
+    with torch.no_grad():
+        m.c.copy_(c)
+        if has_bias:
+            m.bias.copy_(torch.randn(outf, generator=g) * 0.1)
+    m = m.to(DEV).eval()
+    if has_bias:
+        m.bias.data = m.bias.data.to(dtype)
+    monkeypatch.setenv("BCL_PREFILL_WAVE", "0")
+    with torch.no_grad():
+        y_chain = m(x).clone()
+    monkeypatch.setenv("BCL_PREFILL_WAVE", "1")
+    monkeypatch.setenv("BCL_PREFILL_WAVE_MIN_TILES", "1")
+    if lag:
+        monkeypatch.setenv("BCL_WAVE_LAG", str(lag))
+        monkeypatch.setenv("BCL_WAVE_RING", str(ring))
+    with torch.no_grad():
+        y_wave = m(x).clone()
+        y_wave2 = m(x).clone()
+    torch.cuda.synchronize()
+    assert prefill_status(DEV) == 0
+    assert torch.equal(y_wave, y_chain)
+    assert torch.equal(y_wave2, y_chain)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # fp32 spectra on the tensor cores: split (hi, lo) bf16 operands, three MMAs per k-step, fp32 CUDA-core FFT stages
 # (north star: max relative error <= 1e-4 for fp32 spectra)
