@@ -848,6 +848,52 @@ def time_prefill_layer_shared_input(bc, _cabi, dev, reps, n=PREFILL_TOKENS):
     return e0.elapsed_time(e1) / reps * 1e3, alg, prefill_status(dev)
 
 
+def time_prefill_mlp(bc, _cabi, dev, reps, n=PREFILL_TOKENS):
+    """The MLP of one layer at prefill: what HF's LlamaMLP.forward runs over the three BC modules (gate, up, act_fn, multiply, down),
+    the same with gate | up stacked (shared-input fusion), and the whole-MLP fusion (bcl_forward_swiglu: SWIGLU epilogue inside the
+    tensor-core inverse stage, then down_proj)."""
+    import torch
+    import torch.nn.functional as F
+    from llama_fft_b200.patch_llama_fft import prefill_status
+    torch.manual_seed(0)
+
+    def mk(inf, outf):
+        return bc.BlockCirculantLinear(inf, outf, block_size=B, bias=False, spectrum_dtype=torch.bfloat16).to(dev).eval()
+    gate, up, down = mk(4096, 11008), mk(4096, 11008), mk(11008, 4096)
+    fused = bc.FusedBCMLP(gate, up, down)
+    xs = [torch.randn(n, 4096, device=dev).half() for _ in range(2)]
+    stream = torch.cuda.current_stream(dev)
+
+    def timed(fn):
+        with torch.no_grad():
+            for i in range(2):
+                fn(i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(reps):
+                fn(i)
+            e1.record(stream)
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3
+    t_modules = timed(lambda i: down(F.silu(gate(xs[i & 1])) * up(xs[i & 1])))
+
+    def stacked(i):
+        gu = fused.group.forward_all(xs[i & 1])
+        return down(F.silu(gu[:, :11008]) * gu[:, 11008:])
+    t_stacked = timed(stacked)
+    t_fused = timed(lambda i: fused.forward_prefill(xs[i & 1]))
+    with torch.no_grad():
+        a, b = fused.forward_prefill(xs[0]).float(), stacked(0).float()
+    rel = ((a - b).abs().max() / b.abs().max()).item()
+    # bytes the fused MLP has to move: x in, h out and in again (down_proj is a separate forward), y out, + the spectra
+    alg = n * 4096 * 2 + 2 * n * 11008 * 2 + n * 4096 * 2 + 3 * 4096 * 11008 // B * 2
+    return {"what": "one layer's MLP, %d tokens, fp16, bf16 spectra: down(silu(gate(x)) * up(x))" % n,
+            "three_modules_plus_torch_silu_mul_us": t_modules, "stacked_gate_up_plus_torch_silu_mul_us": t_stacked,
+            "fused_swiglu_stage_us": t_fused, "speedup_vs_modules": t_modules / t_fused, "max_rel_diff_vs_stacked": rel,
+            "algorithmic_bytes_fused": alg, "pipeline_status": prefill_status(dev)}
+
+
 def prefill_detail(bc, _cabi, dev, reps=5):
     import torch
     us, per_shape, status = time_prefill_layer(bc, _cabi, dev, reps)
@@ -872,6 +918,11 @@ def prefill_detail(bc, _cabi, dev, reps=5):
                                       "hbm_frac_of_measured_peak": alg2 / (us2 * 1e-6) / 1e9 / peak, "pipeline_status": status2}
     except Exception as e:                                               # noqa: BLE001
         out["shared_input_fusion"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    torch.cuda.empty_cache()
+    try:
+        out["mlp_fusion"] = time_prefill_mlp(bc, _cabi, dev, reps)
+    except Exception as e:                                               # noqa: BLE001
+        out["mlp_fusion"] = {"error": "%s: %s" % (type(e).__name__, e)}
     torch.cuda.empty_cache()
     return out
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BCL_ABI_VERSION 10
+#define BCL_ABI_VERSION 11
 
 typedef enum bcl_dtype { BCL_F32 = 0, BCL_F16 = 1, BCL_BF16 = 2 } bcl_dtype;
 
@@ -90,6 +90,20 @@ int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
                 const void* bias, int bias_dtype,
                 void* y, int y_dtype, int64_t y_row_stride,
                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- gate_proj | up_proj + SWIGLU for many tokens (whole-MLP fusion at prefill) ------------------------------
+ * Replaces the first half of what HF's LlamaMLP.forward chains over the three modules the reference swaps in
+ * (src/patch_llama_fft.py:379):  act_fn(gate_proj(x)) * up_proj(x).  `spec_gemm` is the GEMM-layout bf16 spectrum of gate_proj and
+ * up_proj STACKED along the output-block axis (p = 2 * intermediate/B block-rows: [0, p/2) gate, [p/2, p) up; bcl_precompute_spectrum
+ * of the concatenated c).  One forward-DFT pass and one frequency-GEMM pass serve both members; the inverse stage transforms the two
+ * members of a block pair into a pair of TMEM accumulators and writes
+ *     h = round(silu(round(gate))) * round(up)        (every round() to x_dtype, silu in fp32: the arithmetic of the unfused modules)
+ * as (N, (p/2)*B): the two projection outputs never reach HBM and the act_fn / multiply kernels disappear.  B <= 128, 16-bit
+ * activations, no bias; BCL_ERR_UNSUPPORTED otherwise (callers then run the modules one by one).  Workspace as for bcl_forward. */
+int bcl_forward_swiglu(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
+                       const void* spec_gemm, int spec_dtype, int p, int q, int B,
+                       void* h, int h_dtype, int64_t h_row_stride,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- forward with several destinations: the fused gather of output-block-row sharding ---------------------------
  * Same as bcl_forward, but the epilogue stores y to every one of y_dsts[0 .. n_dst) (1 <= n_dst <= 8; same shape, row

@@ -10,7 +10,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BCL_LIB_PATH") or os.path.join(_HERE, "libbclinear.so")   # override: A/B builds when profiling
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 F32, F16, BF16 = 0, 1, 2
 LAYOUT_STREAM, LAYOUT_GEMM = 0, 1
 EPILOGUE_LINEAR, EPILOGUE_SWIGLU, EPILOGUE_EMIT_SPECTRUM = 0, 1, 2
@@ -25,7 +25,7 @@ SYMBOLS = (
     "bcl_forward", "bcl_group_plan_bytes", "bcl_group_plan_encode", "bcl_forward_grouped", "bcl_forward_host", "bcl_forward_grouped_host", "bcl_forward_grouped_host_pipelined",
     "bcl_project_from_dense",
     "bcl_forward_bcast", "bcl_conj_transpose", "bcl_backward_workspace_bytes", "bcl_backward_weights", "bcl_prefill_geometry", "bcl_prefill_rfft", "bcl_prefill_gemm", "bcl_prefill_irfft",
-    "bcl_launch_noop", "bcl_forward_chain", "bcl_push_columns",
+    "bcl_launch_noop", "bcl_forward_chain", "bcl_push_columns", "bcl_forward_swiglu",
 )
 
 
@@ -86,6 +86,7 @@ def lib() -> ctypes.CDLL:
     L.bcl_prefill_gemm.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, vp]
     L.bcl_prefill_irfft.argtypes = [vp, i64, i32, i32, i32, vp, i32, i32, vp, i32, vp, i32, i64, vp, vp]
     L.bcl_launch_noop.argtypes = [i32, vp]
+    L.bcl_forward_swiglu.argtypes = [vp, i32, i64, i64, vp, i32, i32, i32, i32, vp, i32, i64, vp, sz, vp]
     L.bcl_push_columns.argtypes = [vp, ctypes.POINTER(vp), i32, i64, i64, i64, i64, i32, vp]
     L.bcl_forward_chain.argtypes = [ctypes.POINTER(Problem), ctypes.POINTER(ctypes.c_int), i32, i32, i32, vp, vp]
     for name in SYMBOLS:

@@ -11,7 +11,12 @@ single-token eval / no-grad calls by one launch:
     ------   grid-wide barrier (the spectrum of down_proj is already streaming into shared memory)
     step 1   y = down_proj(h)
 
-Every other call (several tokens, grad mode, CPU tensors, a bias, another activation function) takes the original forward.
+Calls with MANY tokens (prefill: enough work for the tensor-core path, 16-bit activations, bf16 spectra, B <= 128) take
+``bcl_forward_swiglu``: gate and up stacked, one forward-DFT pass and one frequency-GEMM pass for both, and an inverse stage whose
+epilogue writes h = silu(gate) * up directly -- the two 11008-wide projection outputs never reach HBM and HF's act_fn / multiply
+kernels disappear -- followed by down_proj's own forward.
+
+Every other call (grad mode, CPU tensors, a bias, another activation function, fp32 activations) takes the original forward.
 """
 from __future__ import annotations
 
@@ -23,7 +28,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
-from .patch_llama_fft import BlockCirculantLinear
+from .patch_llama_fft import BlockCirculantLinear, prefill_workspace
 from .shared_input import SharedInputGroup
 
 _counters: Dict[Tuple[int, int], torch.Tensor] = {}
@@ -125,6 +130,7 @@ class FusedBCMLP:
                                             and gate._shared_group.members == [gate, up]) else SharedInputGroup([gate, up])
         self._h: Optional[torch.Tensor] = None
         self.fused_calls = 0
+        self.fused_prefill_calls = 0
 
     def eligible(self, x: torch.Tensor) -> bool:
         if torch.is_grad_enabled() or self.gate.training or self.up.training or self.down.training:
@@ -132,6 +138,44 @@ class FusedBCMLP:
         if not (x.is_cuda and x.dtype in _cabi.DTYPE and x.shape[-1] == self.gate.in_features and x.numel() == self.gate.in_features):
             return False
         return self.gate._cache_spectrum and self.up._cache_spectrum and self.down._cache_spectrum and self.gate.c.is_cuda
+
+    def _common_ok(self, x: torch.Tensor) -> bool:
+        if torch.is_grad_enabled() or self.gate.training or self.up.training or self.down.training:
+            return False
+        if not (x.is_cuda and x.dtype in _cabi.DTYPE and x.shape[-1] == self.gate.in_features and self.gate.c.is_cuda):
+            return False
+        return self.gate._cache_spectrum and self.up._cache_spectrum and self.down._cache_spectrum
+
+    def eligible_prefill(self, x: torch.Tensor) -> bool:
+        """Many tokens: the stacked gate | up layer would take the tensor-core path and bcl_forward_swiglu covers the configuration."""
+        if not self._common_ok(x) or x.dtype == torch.float32 or self.gate.block_size > 128 or self.gate.spectrum_dtype != torch.bfloat16:
+            return False
+        n = x.numel() // self.gate.in_features
+        return n > 1 and self._stacked_work(n)
+
+    def _stacked_work(self, n: int) -> bool:
+        from .patch_llama_fft import prefill_token_floor
+        return n >= prefill_token_floor(self.group.out_blocks, self.group.in_blocks, torch.bfloat16)
+
+    def forward_prefill(self, x: torch.Tensor) -> torch.Tensor:
+        g = self.group
+        x_flat = x.reshape(-1, self.gate.in_features)
+        if x_flat.stride(-1) != 1 or (x_flat.stride(0) * x_flat.element_size()) % 16 or x_flat.data_ptr() % 16:
+            x_flat = x_flat.contiguous()
+        n = x_flat.shape[0]
+        spec = g.build_spectrum(_cabi.LAYOUT_GEMM)
+        h = torch.empty(n, self.down.in_features, device=x_flat.device, dtype=x_flat.dtype)
+        L = _cabi.lib()
+        ws_bytes = L.bcl_workspace_bytes(n, g.out_blocks, g.in_blocks, g.block_size, _cabi.BF16, _cabi.LAYOUT_GEMM)
+        ws = prefill_workspace(x_flat.device, ws_bytes)
+        with _cabi.on_device(x_flat.device):
+            rc = L.bcl_forward_swiglu(x_flat.data_ptr(), _cabi.DTYPE[x_flat.dtype], n, x_flat.stride(0), spec.data_ptr(), _cabi.BF16,
+                                      g.out_blocks, g.in_blocks, g.block_size, h.data_ptr(), _cabi.DTYPE[h.dtype], h.stride(0),
+                                      ws.data_ptr(), ws.numel(), _cabi.stream_ptr(x_flat.device))
+        _cabi.check(rc, "bcl_forward_swiglu")
+        self.fused_prefill_calls += 1
+        y = self.down(h)
+        return y.view(*x.shape[:-1], self.down.out_features)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x_flat = x.reshape(1, -1)
@@ -175,6 +219,8 @@ def fuse_mlp(model: nn.Module) -> int:
         def forward(self, x, _fused=fused, _orig=orig):
             if _fused.eligible(x):
                 return _fused.forward(x)
+            if _fused.eligible_prefill(x):
+                return _fused.forward_prefill(x)
             return _orig(x)
         mod._bcl_fused_mlp = fused
         mod._bcl_orig_forward = orig

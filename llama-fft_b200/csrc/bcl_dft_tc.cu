@@ -67,6 +67,14 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_tc_split_bcast_kernel(
     dft_inv_body<B, true>(dft_smem, tmYf, tmW, tmOut, &lo, a, (int)blockIdx.x, (int)gridDim.x, &ex);
 }
 
+// gate | up stacked: inverse DFT of both members of a block pair + SWIGLU epilogue (dft_inv_swiglu_body)
+template <int B>
+__global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_swiglu_tc_kernel(const __grid_constant__ CUtensorMap tmYf, const __grid_constant__ CUtensorMap tmW,
+                                                                            const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ DftArgs a) {
+    extern __shared__ __align__(1024) unsigned char dft_smem[];
+    dft_inv_swiglu_body<B>(dft_smem, tmYf, tmW, tmOut, a, (int)blockIdx.x, (int)gridDim.x);
+}
+
 // =========================================================================================================
 // host side
 // =========================================================================================================
@@ -169,6 +177,32 @@ bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm,
     return true;
 }
 
+bool prep_dft_inv_swiglu(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L) {
+    const int B = g.B;
+    if ((B != 64 && B != 128) || (g.p & 1) || g.split) return false;
+    const bool bf = P.x_dtype == BCL_BF16;
+    const CUtensorMapDataType adt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    if (!make_chunk_map(&L.tm_in, Yf, nc, g.p, g.FG, TILE_M / TOK_GROUP, 1, (uint32_t)g.FG)) return false;
+    const unsigned char* sb = reinterpret_cast<const unsigned char*>(spec_gemm);
+    if (!map_w(&L.tm_w, sb + g.winv_off, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return false;
+    const uint64_t dims[2] = {(uint64_t)(g.p / 2) * B, (uint64_t)P.N};
+    const uint64_t strides[1] = {(uint64_t)P.y_stride * 2};
+    const uint32_t box[2] = {KATOM, 32};
+    if (!make_tensor_map(&L.tm_out, adt, 2, P.y, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
+    DftArgs& a = L.a;
+    a = DftArgs{};
+    a.status = status; a.bias = nullptr; a.n_begin = n_begin; a.nc = nc;
+    a.m_tiles = (nc + TILE_M - 1) / TILE_M; a.groups = g.p / 2; a.num_items = a.m_tiles * (g.p / 2); a.act_bf16 = bf ? 1 : 0;
+    const uint32_t stage_bytes = (uint32_t)g.FG * 2048;
+    a.stages = dft_pick_stages(B, stage_bytes) & ~1;                 // an item takes two stages
+    if (a.stages < 2) return false;
+    L.smem = dft_smem_bytes(B, stage_bytes, a.stages);
+    return true;
+}
+
+cudaError_t launch_dft_inv_swiglu_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status,
+                                     int max_ctas, cudaStream_t st);
+
 template <typename K, typename... Extra>
 static cudaError_t launch_stage(K kernel, const StageLaunch<DftArgs>& L, int max_ctas, cudaStream_t st, const Extra&... extra) {
     const int grid = L.a.num_items < max_ctas ? L.a.num_items : max_ctas;
@@ -220,6 +254,14 @@ cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void
     }
     if (bcast) return g.B == 128 ? launch_stage(dft_inv_tc_bcast_kernel<128>, L, max_ctas, st, ex) : launch_stage(dft_inv_tc_bcast_kernel<64>, L, max_ctas, st, ex);
     return g.B == 128 ? launch_stage(dft_inv_tc_kernel<128>, L, max_ctas, st) : launch_stage(dft_inv_tc_kernel<64>, L, max_ctas, st);
+}
+
+
+cudaError_t launch_dft_inv_swiglu_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status,
+                                     int max_ctas, cudaStream_t st) {
+    StageLaunch<DftArgs> L;
+    if (!prep_dft_inv_swiglu(P, g, spec_gemm, n_begin, nc, Yf, status, L)) return cudaErrorNotSupported;
+    return g.B == 128 ? launch_stage(dft_inv_swiglu_tc_kernel<128>, L, max_ctas, st) : launch_stage(dft_inv_swiglu_tc_kernel<64>, L, max_ctas, st);
 }
 
 }  // namespace gemm

@@ -858,6 +858,158 @@ done:
 }
 
 
+// =========================================================================================================
+// inverse + SWIGLU: Yf of the stacked (gate | up) layer -> h = round(silu(round(gate))) * round(up)
+// =========================================================================================================
+// HF LlamaMLP.forward computes down_proj(act_fn(gate_proj(x)) * up_proj(x)) (call sites src/patch_llama_fft.py:379): act_fn and the
+// product run on the projections' OUTPUTS, i.e. on values already rounded to x.dtype (:266), silu in fp32 rounded to x.dtype, the
+// product rounded again -- the same arithmetic as the decode chain kernel's SWIGLU epilogue (bcl_stream_chain.cu).  Here the inverse
+// DFT of output block j of gate (slab j of Yf) and of up (slab j + p/2) go to a PAIR of TMEM accumulators and the epilogue writes
+// one block of h: the two 11008-wide projection outputs never reach HBM, and the separate act_fn / multiply kernels disappear.
+template <bool BF16>
+__device__ __forceinline__ void store_row_swiglu(unsigned char* row, int lane, const uint32_t (&rg)[64], const uint32_t (&ru)[64]) {
+    constexpr int DT = BF16 ? BCL_BF16 : BCL_F16;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float hv[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float gv = round_to(__uint_as_float(rg[8 * c + 2 * e + k]), DT);
+                const float uv = round_to(__uint_as_float(ru[8 * c + 2 * e + k]), DT);
+                const float sv = round_to(__fdividef(gv, 1.0f + __expf(-gv)), DT);
+                hv[k] = sv * uv;
+            }
+            w[e] = pack16(hv[0], hv[1], BF16 ? 1 : 0);
+        }
+        *reinterpret_cast<uint4*>(row + ((c ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+template <int B>
+__device__ __forceinline__ void dft_inv_swiglu_body(unsigned char* dft_smem, const CUtensorMap& tmYf, const CUtensorMap& tmW, const CUtensorMap& tmOut,
+                                                    const DftArgs& a, const int first, const int stride) {
+    static_assert(B == 64 || B == 128, "SWIGLU inverse stage: B = 64 / 128");
+    constexpr int ATOMS = B / KATOM;
+    constexpr int OUT_ATOMS = B / KATOM;
+    constexpr int FG = B / 8;
+    constexpr int KSTEPS = B / 16;
+    constexpr uint32_t W_ATOM = B * 128;
+    constexpr uint32_t STAGE = FG * 2048;                    // Yf of (tile, slab): [fg][128 tokens][16 B]
+    constexpr int NPAIR = 2;                                 // accumulator pairs in flight (2 x 2 x B <= 512 columns)
+    DftBarriers* bars = reinterpret_cast<DftBarriers*>(dft_smem);
+    unsigned char* epi = dft_smem + 1024;
+    unsigned char* wsm = dft_smem + 1024 + DFT_EPI_WARPS * DFT_NBUF * DFT_EPI_BUF;
+    unsigned char* ring = wsm + ATOMS * W_ATOM;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int S = a.stages;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        for (int i = 0; i < NPAIR; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], DFT_EPI_WARPS); }
+        mbar_init(&bars->wfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmYf); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmOut); }
+    if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = bars->tmem_base;
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&bars->wfull, ATOMS * W_ATOM);
+            for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + at * W_ATOM, &tmW, at * KATOM, 0, &bars->wfull);
+            pdl_wait();                                                          // Yf comes from the previous kernel
+            int stage = 0; uint32_t ph = 0;
+            for (int item = first; item < a.num_items; item += stride) {
+                const int j = item % a.groups, m = item / a.groups;
+                for (int half = 0; half < 2; ++half) {                           // gate slab j, up slab j + p/2
+                    if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { set_status(a.status, 71); goto done; }
+                    mbar_arrive_expect_tx(&bars->full[stage], STAGE);
+                    tma_load_4d_hint(ring + (size_t)stage * STAGE, &tmYf, 0, m * (TILE_M / TOK_GROUP), j + half * a.groups, 0, &bars->full[stage], L2_EVICT_FIRST);
+                    if (++stage == S) { stage = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(TILE_M, B);
+            if (!mbar_wait(&bars->wfull, 0)) { set_status(a.status, 72); goto done; }
+            int stage = 0; uint32_t ph = 0; int it = 0;
+            for (int item = first; item < a.num_items; item += stride, ++it) {
+                const int pair = it % NPAIR; const uint32_t pair_ph = (uint32_t)(it / NPAIR) & 1u;
+                if (!mbar_wait(&bars->tmem_empty[pair], pair_ph ^ 1u)) { set_status(a.status, 73); goto done; }
+                tc_fence_after_sync();
+                for (int half = 0; half < 2; ++half) {
+                    if (!mbar_wait(&bars->full[stage], ph)) { set_status(a.status, 74); goto done; }
+                    tc_fence_after_sync();
+                    const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE), sw = smem_u32(wsm);
+#pragma unroll
+                    for (int kk = 0; kk < KSTEPS; ++kk)
+                        umma_bf16_ss(tmem_base + (uint32_t)((2 * pair + half) * B), umma_desc_k_nosw(sa + (uint32_t)kk * 4096u, 128u, 2048u),
+                                     umma_desc_k_sw128(sw + (kk / 4) * W_ATOM) + (uint64_t)(2 * (kk % 4)), idesc, kk != 0 ? 1u : 0u);
+                    umma_commit(&bars->empty[stage]);
+                    if (++stage == S) { stage = 0; ph ^= 1u; }
+                }
+                umma_commit(&bars->tmem_full[pair]);
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        unsigned char* stg = epi + (size_t)(warp - 2) * DFT_NBUF * DFT_EPI_BUF;
+        pdl_wait();                                                              // h may still be read by the previous kernel
+        int it = 0, buf = 0;
+        for (int item = first; item < a.num_items; item += stride, ++it) {
+            const int j = item % a.groups, m = item / a.groups;
+            const int pair = it % NPAIR; const uint32_t pair_ph = (uint32_t)(it / NPAIR) & 1u;
+            if (!__all_sync(0xffffffffu, mbar_wait(&bars->tmem_full[pair], pair_ph))) { set_status(a.status, 75); goto done; }
+            tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(2 * pair * B);
+            const int wh = (warp - 2) >> 2;
+            const int h0 = (OUT_ATOMS == 2) ? wh : 0, h1 = (OUT_ATOMS == 2) ? wh + 1 : (wh == 0 ? 1 : 0);
+            if (h0 >= h1) {                                                      // B = 64: the partner warp only releases
+                tc_fence_before_sync();
+                if (lane == 0) mbar_arrive(&bars->tmem_empty[pair]);
+            }
+            for (int h = h0; h < h1; ++h) {
+                uint32_t rg[64], ru[64];
+                tmem_ld_32x32b_x32(taddr + (uint32_t)(h * 64), *reinterpret_cast<uint32_t(*)[32]>(&rg[0]));
+                tmem_ld_32x32b_x32(taddr + (uint32_t)(h * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(&rg[32]));
+                tmem_ld_32x32b_x32(taddr + (uint32_t)(B + h * 64), *reinterpret_cast<uint32_t(*)[32]>(&ru[0]));
+                tmem_ld_32x32b_x32(taddr + (uint32_t)(B + h * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(&ru[32]));
+                tmem_ld_wait();
+                if (h == h1 - 1) {
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->tmem_empty[pair]);
+                }
+                if (lane == 0) tma_store_wait_read<DFT_NBUF - 1>();
+                __syncwarp();
+                unsigned char* row = stg + (size_t)buf * DFT_EPI_BUF + (size_t)lane * 128;
+                if (a.act_bf16) store_row_swiglu<true>(row, lane, rg, ru);
+                else store_row_swiglu<false>(row, lane, rg, ru);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmOut, j * B + h * 64, (int)(a.n_begin + (int64_t)m * TILE_M + quarter * 32), stg + (size_t)buf * DFT_EPI_BUF);
+                    tma_store_commit();
+                }
+                if (++buf == DFT_NBUF) buf = 0;
+            }
+        }
+        if (lane == 0) tma_store_wait<0>();
+    }
+done:
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host side: tensor maps + arguments of one stage (filled by prep_*, consumed by the stand-alone and the fused launchers)
 // ---------------------------------------------------------------------------------------------------------
@@ -873,6 +1025,8 @@ bool prep_gemm(const void* Xf, const void* Cmat, void* Yf, int* status, const Ge
 bool prep_gemm_lo(const void* Xf_lo, const void* Cmat, void* Yf_lo, const Geometry& g, int nc, GemmLoMaps* lo);
 bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L,
                   const void* Yf_lo = nullptr, DftLoMaps* lo = nullptr, DftExtraOut* ex = nullptr);
+// g: geometry of the STACKED (gate | up) layer (g.p block-rows, even); P.y = h with (g.p / 2) * B columns
+bool prep_dft_inv_swiglu(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L);
 
 }  // namespace gemm
 }  // namespace bcl

@@ -216,3 +216,100 @@ def test_fuse_mlp_in_a_tiny_llama_decode_step():
         back1 = model(input_ids=ids).logits
     assert torch.equal(a9, b9) and torch.equal(back1, ref1)
     assert (got1 - ref1).abs().max().item() <= 2e-4 * ref1.abs().max().item()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# whole-MLP fusion at prefill: bcl_forward_swiglu (gate | up stacked, SWIGLU epilogue in the tensor-core inverse stage)
+# ---------------------------------------------------------------------------------------------------------
+def _gemm_spectrum(c):
+    p, q, B = c.shape
+    L = _cabi.lib()
+    cd = c.to(DEV).contiguous()
+    spec = torch.empty(L.bcl_spectrum_bytes(p, q, B, _cabi.BF16, _cabi.LAYOUT_GEMM), device=DEV, dtype=torch.uint8)
+    _cabi.check(L.bcl_precompute_spectrum(cd.data_ptr(), p, q, B, spec.data_ptr(), _cabi.BF16, _cabi.LAYOUT_GEMM, _cabi.stream_ptr(torch.device(DEV))),
+                "bcl_precompute_spectrum")
+    return spec
+
+
+def _forward_swiglu(x, spec, p, q, B):
+    L = _cabi.lib()
+    N = x.shape[0]
+    h = torch.full((N, p // 2 * B), float("nan"), device=DEV, dtype=x.dtype)
+    ws = torch.zeros(L.bcl_workspace_bytes(N, p, q, B, _cabi.BF16, _cabi.LAYOUT_GEMM), device=DEV, dtype=torch.uint8)
+    rc = L.bcl_forward_swiglu(x.data_ptr(), _cabi.DTYPE[x.dtype], N, x.stride(0), spec.data_ptr(), _cabi.BF16, p, q, B,
+                              h.data_ptr(), _cabi.DTYPE[h.dtype], h.stride(0), ws.data_ptr(), ws.numel(), _cabi.stream_ptr(torch.device(DEV)))
+    _cabi.check(rc, "bcl_forward_swiglu")
+    torch.cuda.synchronize()
+    assert int(ws[:8].view(torch.int32)[0].item()) == 0 and int(ws[:8].view(torch.int32)[1].item()) == 0      # no pipeline stall
+    return h
+
+
+@pytest.mark.parametrize("hidden,inter,B,N,dtype", [(4096, 11008, 128, 1500, torch.float16), (4096, 11008, 128, 640, torch.bfloat16),
+                                                     (512, 1536, 64, 700, torch.float16), (1024, 2048, 128, 128 * 9 + 1, torch.bfloat16)])
+def test_prefill_swiglu_stage_matches_the_unfused_modules_and_the_oracle(hidden, inter, B, N, dtype):
+    """h = act_fn(gate_proj(x)) * up_proj(x) in one three-stage forward.  Against (a) the same two projections through the library's own
+    tensor-core path followed by torch's silu and multiply -- the stacked forward is bit-identical per member, so only the fp32 silu
+    evaluation (__expf / __fdividef vs torch) can flip a last bit of the rounded silu: h within 2 ulp everywhere, bit-equal almost
+    everywhere -- and (b) the reference's modules composed on the CPU oracle, bf16-spectrum class."""
+    g = torch.Generator().manual_seed(hidden + inter + B + N)
+    cg = torch.randn(inter // B, hidden // B, B, generator=g) * 0.03
+    cu = torch.randn(inter // B, hidden // B, B, generator=g) * 0.03
+    x = torch.randn(N, hidden, generator=g).to(dtype)
+    xd = x.to(DEV)
+    p, q = 2 * (inter // B), hidden // B
+    h = _forward_swiglu(xd, _gemm_spectrum(torch.cat([cg, cu], 0)), p, q, B)
+    assert not torch.isnan(h.float()).any()
+    gate = bc_forward(xd, _gemm_spectrum(cg), None, p // 2, q, B, layout=_cabi.LAYOUT_GEMM, spectrum_dtype=torch.bfloat16)
+    up = bc_forward(xd, _gemm_spectrum(cu), None, p // 2, q, B, layout=_cabi.LAYOUT_GEMM, spectrum_dtype=torch.bfloat16)
+    h_unfused = F.silu(gate) * up
+    diff = (h.double() - h_unfused.double()).abs()
+    assert bool((diff <= 2 * G.ulp(dtype) * h_unfused.double().abs() + 1e-30).all()), f"max diff {diff.max().item():.3e}"
+    assert (h == h_unfused).float().mean().item() >= 0.98
+    rows = torch.tensor([0, 1, 127, 128, N // 2, N - 1])
+    gate_ref, up_ref = O.bc_forward_torch(cg, x[rows].float()), O.bc_forward_torch(cu, x[rows].float())
+    h_ref = F.silu(gate_ref) * up_ref
+    assert_close(h[rows], h_ref, 2e-2, dtype, ulps=4)
+    h2 = _forward_swiglu(xd, _gemm_spectrum(torch.cat([cg, cu], 0)), p, q, B)
+    assert torch.equal(h, h2)
+
+
+def test_forward_swiglu_argument_validation():
+    L = _cabi.lib()
+    x = torch.zeros(256, 512, device=DEV, dtype=torch.float16)
+    c = torch.zeros(6, 4, 128)
+    spec = _gemm_spectrum(c)
+    h = torch.zeros(256, 384, device=DEV, dtype=torch.float16)
+    ws = torch.zeros(L.bcl_workspace_bytes(256, 6, 4, 128, _cabi.BF16, _cabi.LAYOUT_GEMM), device=DEV, dtype=torch.uint8)
+    st = _cabi.stream_ptr(torch.device(DEV))
+    args = lambda p=6, sd=_cabi.BF16, B=128, xt=x: (xt.data_ptr(), _cabi.DTYPE[xt.dtype], 256, xt.stride(0), spec.data_ptr(), sd, p, 4, B,
+                                                      h.data_ptr(), _cabi.DTYPE[xt.dtype], h.stride(0), ws.data_ptr(), ws.numel(), st)
+    assert L.bcl_forward_swiglu(*args()) == 0
+    assert L.bcl_forward_swiglu(*args(p=5)) != 0                               # odd number of block-rows
+    assert L.bcl_forward_swiglu(*args(sd=_cabi.F32)) == -8                     # fp32 spectra: unsupported, never a silent fallback
+    assert L.bcl_forward_swiglu(*args(xt=x.float()[:, :512].contiguous())) != 0
+    torch.cuda.synchronize()
+
+
+def test_fuse_mlp_prefill_path_in_a_tiny_llama(monkeypatch):
+    """fuse_mlp serves many-token eval calls with bcl_forward_swiglu + down_proj when the stacked gate | up layer has enough work for
+    the tensor-core path: logits agree with the unfused model to the bf16-spectrum class, and the counter shows the path really ran."""
+    import importlib
+    from transformers import LlamaConfig, LlamaForCausalLM
+    P = importlib.import_module("llama_fft_b200.patch_llama_fft")
+    cfg = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                      vocab_size=320, max_position_embeddings=512)
+    torch.manual_seed(0)
+    model = LlamaForCausalLM(cfg).eval()
+    bc.patch_llama_fft(model, block_size=64, spectrum_dtype=torch.bfloat16)
+    model = model.to(DEV).half()
+    ids = torch.randint(0, 320, (4, 96), device=DEV)
+    monkeypatch.setattr(P, "PREFILL_MIN_TOKENS", 256)
+    with torch.no_grad():
+        ref = model(input_ids=ids).logits.float()
+        assert bc.fuse_mlp(model) == 2
+        fused = [m._bcl_fused_mlp for m in model.modules() if hasattr(m, "_bcl_fused_mlp")]
+        got = model(input_ids=ids).logits.float()
+        assert [f.fused_prefill_calls for f in fused] == [1, 1] and [f.fused_calls for f in fused] == [0, 0]
+        bc.unfuse_mlp(model)
+    assert P.prefill_status(DEV) == 0
+    assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
