@@ -79,12 +79,13 @@ __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_swiglu_tc_kernel(const
 // host side
 // =========================================================================================================
 bool dft_tc_supported(int B, int act_dtype) { return (B == 64 || B == 128 || B == 256) && (act_dtype == BCL_F16 || act_dtype == BCL_BF16); }
-static int dft_nb(int B) { return B == 256 ? 128 : B; }         // accumulator columns per block and launch (DftShape<B>::NB)
+static int dft_nsplit(int B, bool split = false) { return B == 256 ? (split ? 4 : 2) : 1; }      // launches per stage (DftShape::NSPLIT)
+static int dft_nb(int B, bool split = false) { return B / dft_nsplit(B, split); }                // accumulator columns per block and launch (DftShape::NB)
 static int dft_parts(int B) { return B == 256 ? 2 : 1; }         // K parts = smem stages per block (DftShape<B>::PARTS)
 
 // nbuf: staging buffers per epilogue warp; wmats: resident DFT matrices (1, or 2 = hi + lo)
 static size_t dft_smem_bytes(int B, uint32_t stage_bytes, int stages, int nbuf = DFT_NBUF, int wmats = 1) {
-    return 1024 + DFT_EPI_WARPS * nbuf * DFT_EPI_BUF + (size_t)wmats * (B / KATOM) * dft_nb(B) * 128 + (size_t)stages * stage_bytes;
+    return 1024 + DFT_EPI_WARPS * nbuf * DFT_EPI_BUF + (size_t)wmats * (B / KATOM) * dft_nb(B, wmats == 2) * 128 + (size_t)stages * stage_bytes;
 }
 static int dft_pick_stages(int B, uint32_t stage_bytes, int nbuf = DFT_NBUF, int wmats = 1) {
     int s = DFT_MAX_STAGES;
@@ -92,10 +93,10 @@ static int dft_pick_stages(int B, uint32_t stage_bytes, int nbuf = DFT_NBUF, int
     return s;
 }
 
-static bool map_w(CUtensorMap* m, const void* w, int B, CUtensorMapDataType dt) {                  // [B rows][B k], box 64 x NB rows, 128-byte swizzle
+static bool map_w(CUtensorMap* m, const void* w, int B, CUtensorMapDataType dt, bool split = false) {   // [B rows][B k], box 64 x NB rows, 128-byte swizzle
     const uint64_t dims[2] = {(uint64_t)B, (uint64_t)B};
     const uint64_t strides[1] = {(uint64_t)B * 2};
-    const uint32_t box[2] = {KATOM, (uint32_t)dft_nb(B)};
+    const uint32_t box[2] = {KATOM, (uint32_t)dft_nb(B, split)};
     return make_tensor_map(m, dt, 2, w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -125,7 +126,7 @@ bool prep_dft_fwd(const ProblemDev& P, const Geometry& g, const void* spec_gemm,
         if (!make_tensor_map(&L.tm_in, adt, 2, P.x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
     }
     const unsigned char* sb = reinterpret_cast<const unsigned char*>(spec_gemm);
-    if (!map_w(&L.tm_w, sb + (bf ? g.wbf16_off : g.wf16_off), B, adt)) return false;
+    if (!map_w(&L.tm_w, sb + (bf ? g.wbf16_off : g.wf16_off), B, adt, split)) return false;
     if (!make_chunk_map(&L.tm_out, Xf, nc, g.KG, g.F, 1, 1, 8)) return false;
     DftArgs& a = L.a;
     a = DftArgs{};
@@ -136,7 +137,7 @@ bool prep_dft_fwd(const ProblemDev& P, const Geometry& g, const void* spec_gemm,
     a.stages = dft_pick_stages(B, stage_bytes, DFT_NBUF, split ? 2 : 1);
     L.smem = dft_smem_bytes(B, stage_bytes, a.stages, DFT_NBUF, split ? 2 : 1);
     if (split) {
-        if (!map_w(&lo->W, sb + (bf ? g.wbf16_lo_off : g.wf16_lo_off), B, adt)) return false;
+        if (!map_w(&lo->W, sb + (bf ? g.wbf16_lo_off : g.wf16_lo_off), B, adt, true)) return false;
         if (!make_chunk_map(&lo->IO, Xf_lo, nc, g.KG, g.F, 1, 1, 8)) return false;
     }
     return true;
@@ -150,7 +151,7 @@ bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm,
     const CUtensorMapDataType adt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     if (!make_chunk_map(&L.tm_in, Yf, nc, g.p, g.FG, TILE_M / TOK_GROUP, 1, (uint32_t)(g.FG / dft_parts(B)))) return false;
     const unsigned char* sb = reinterpret_cast<const unsigned char*>(spec_gemm);
-    if (!map_w(&L.tm_w, sb + g.winv_off, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return false;
+    if (!map_w(&L.tm_w, sb + g.winv_off, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, split)) return false;
     {
         const uint64_t dims[2] = {(uint64_t)g.p * B, (uint64_t)P.N};
         const uint64_t strides[1] = {(uint64_t)P.y_stride * 2};
@@ -171,8 +172,8 @@ bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm,
     a.stages = dft_pick_stages(B, stage_bytes, split ? 1 : DFT_NBUF, split ? 2 : 1);
     L.smem = dft_smem_bytes(B, stage_bytes, a.stages, split ? 1 : DFT_NBUF, split ? 2 : 1);
     if (split) {
-        if (!map_w(&lo->W, sb + g.winv_lo_off, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return false;
-        if (!make_chunk_map(&lo->IO, Yf_lo, nc, g.p, g.FG, TILE_M / TOK_GROUP, 1, (uint32_t)g.FG)) return false;
+        if (!map_w(&lo->W, sb + g.winv_lo_off, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, true)) return false;
+        if (!make_chunk_map(&lo->IO, Yf_lo, nc, g.p, g.FG, TILE_M / TOK_GROUP, 1, (uint32_t)(g.FG / dft_parts(B)))) return false;
     }
     return true;
 }
@@ -218,6 +219,14 @@ cudaError_t launch_dft_fwd_tc(const ProblemDev& P, const Geometry& g, const void
     if (g.split && Xf_lo != nullptr) {
         DftLoMaps lo;
         if (!prep_dft_fwd(P, g, spec_gemm, n_begin, nc, Xf, status, L, Xf_lo, &lo)) return cudaErrorNotSupported;
+        if (g.B == 256) {                                           // four launches: 64 spectrum rows each (DftShape<256, true>)
+            for (int part = 0; part < 4; ++part) {
+                L.a.half = part;
+                cudaError_t e = launch_stage(dft_fwd_tc_split_kernel<256>, L, max_ctas, st, lo);
+                if (e != cudaSuccess) return e;
+            }
+            return cudaSuccess;
+        }
         return g.B == 128 ? launch_stage(dft_fwd_tc_split_kernel<128>, L, max_ctas, st, lo) : launch_stage(dft_fwd_tc_split_kernel<64>, L, max_ctas, st, lo);
     }
     if (!prep_dft_fwd(P, g, spec_gemm, n_begin, nc, Xf, status, L)) return cudaErrorNotSupported;
@@ -240,6 +249,14 @@ cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void
     if (g.split && Yf_lo != nullptr) {
         DftLoMaps lo;
         if (!prep_dft_inv(P, g, spec_gemm, n_begin, nc, Yf, status, L, Yf_lo, &lo, bcast ? &ex : nullptr)) return cudaErrorNotSupported;
+        if (g.B == 256) {                                           // four launches: 64 output samples of every block each
+            for (int part = 0; part < 4; ++part) {
+                L.a.half = part;
+                cudaError_t e = bcast ? launch_stage(dft_inv_tc_split_bcast_kernel<256>, L, max_ctas, st, lo, ex) : launch_stage(dft_inv_tc_split_kernel<256>, L, max_ctas, st, lo);
+                if (e != cudaSuccess) return e;
+            }
+            return cudaSuccess;
+        }
         if (bcast) return g.B == 128 ? launch_stage(dft_inv_tc_split_bcast_kernel<128>, L, max_ctas, st, lo, ex) : launch_stage(dft_inv_tc_split_bcast_kernel<64>, L, max_ctas, st, lo, ex);
         return g.B == 128 ? launch_stage(dft_inv_tc_split_kernel<128>, L, max_ctas, st, lo) : launch_stage(dft_inv_tc_split_kernel<64>, L, max_ctas, st, lo);
     }

@@ -512,11 +512,11 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
         const int ctas = sm_count();
         static const int impl_s = getenv("BCL_PREFILL_DFT") ? atoi(getenv("BCL_PREFILL_DFT")) : 0;   // 1: force the CUDA-core FFT stages
         // 16-bit activations, B <= 128: the DFT stages run on the tensor cores too, with (hi, lo) DFT matrices
-        const bool tc1 = impl_s != 1 && B <= 128 && gemm::dft_tc_supported(B, P.x_dtype);   // B = 256: the (hi, lo) DFT matrices do not fit
+        const bool tc1 = impl_s != 1 && gemm::dft_tc_supported(B, P.x_dtype);               // B = 256: quarter-N launches (the (hi, lo) DFT matrices fit 64 rows at a time)
         const bool tc3 = tc1 && P.y_dtype == P.x_dtype;
         for (int64_t n0 = 0; n0 < P.N; n0 += ncmax) {
             const int nc = (int)((P.N - n0 < ncmax) ? (P.N - n0) : ncmax);
-            if (tc1 && tc3 && chain_enabled() && ctas >= 8 && P.n_extra == 0) {                // all three stages on the tensor cores: one launch
+            if (tc1 && tc3 && B <= 128 && chain_enabled() && ctas >= 8 && P.n_extra == 0) {    // all three stages on the tensor cores: one launch
                 if ((e = cudaMemsetAsync(ws + kWsHeader, 0, 256, st)) != cudaSuccess) return e;
                 if ((e = gemm::launch_prefill_chain(P, g, spec_gemm, n0, nc, Xf, Xf_lo, Yf, Yf_lo, status, reinterpret_cast<int*>(ws + kWsHeader), ctas, st)) != cudaSuccess) return e;
                 continue;

@@ -434,7 +434,7 @@ struct DftArgs {
     int64_t n_begin;         // first token of the chunk (row coordinate into x / y)
     int nc, m_tiles, groups; // groups: KG (forward) or p (inverse)
     int num_items, stages, act_bf16;
-    int half;                // B = 256 only: which 128 spectrum rows (forward) / output samples (inverse) this launch computes
+    int half;                // B = 256 only: which slice of the spectrum rows (forward) / output samples (inverse) this launch computes (DftShape::NB each)
     StageDeps deps;
     long long* trace;
 };
@@ -443,8 +443,11 @@ struct DftArgs {
 // HALF of the N dimension (128 spectrum rows / output samples, `DftArgs::half`) with the full K = 256 fed in two 128-wide parts
 // (one smem stage each), and the stage is launched twice.  The activations are read twice; the CUDA-core FFT stages this
 // replaces are instruction-bound at 3-5x the HBM time (profiles/r1_prefill_notes.md).
-template <int B> struct DftShape {
-    static constexpr int NB = B == 256 ? 128 : B;            // accumulator columns per block = MMA N
+// fp32 spectra (SPLIT): the (hi, lo) pair of DFT-matrix slices must fit as well, so a B = 256 launch computes a QUARTER of the N
+// dimension (64 rows / samples; 2 x 32 KB of matrix) and the stage is launched four times.
+template <int B, bool SPLIT = false> struct DftShape {
+    static constexpr int NSPLIT = B == 256 ? (SPLIT ? 4 : 2) : 1;   // launches per stage = slices of the N dimension
+    static constexpr int NB = B / NSPLIT;                     // accumulator columns per block = MMA N
     static constexpr int KATOMS = B / KATOM;                  // 128-byte K atoms over the whole K = B
     static constexpr int PARTS = B == 256 ? 2 : 1;            // K parts = smem stages per block
     static constexpr int APP = KATOMS / PARTS;                // atoms per part
@@ -465,13 +468,12 @@ struct DftExtraOut { CUtensorMap out[kMaxExtraDst]; int n; };
 template <int B, bool SPLIT>
 __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmXf,
                                              const DftLoMaps* lo, const DftArgs& a, const int first, const int stride) {
-    using SH = DftShape<B>;
+    using SH = DftShape<B, SPLIT>;
     constexpr int NB = SH::NB, PARTS = SH::PARTS, APP = SH::APP;
     constexpr int ATOMS = SH::KATOMS;                        // 128-byte K atoms per block (K = B time samples)
     constexpr uint32_t A_ATOM = TILE_M * 128;                // 128 tokens x 128 B
     constexpr uint32_t W_ATOM = NB * 128;                    // NB spectrum rows x 128 B
     constexpr uint32_t STAGE = APP * A_ATOM;                 // one K part of one input block of the tile
-    static_assert(!(SPLIT && B == 256), "B = 256 split: CUDA-core FFT stages");
     DftBarriers* bars = reinterpret_cast<DftBarriers*>(dft_smem);
     uint32_t* sig = reinterpret_cast<uint32_t*>(dft_smem + 512);                // signaller queue (fused launch)
     unsigned char* epi = dft_smem + 1024;                    // 4 warps x 2 x DFT_EPI_BUF
@@ -504,7 +506,7 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
             mbar_arrive_expect_tx(&bars->wfull, (SPLIT ? 2 : 1) * ATOMS * W_ATOM);   // the DFT matrix: resident for the whole kernel
             for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + at * W_ATOM, &tmW, at * KATOM, a.half * NB, &bars->wfull);
             if constexpr (SPLIT)
-                for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + (ATOMS + at) * W_ATOM, &lo->W, at * KATOM, 0, &bars->wfull);
+                for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + (ATOMS + at) * W_ATOM, &lo->W, at * KATOM, a.half * NB, &bars->wfull);
             pdl_wait();                                                          // x may come from the previous kernel
             int stage = 0; uint32_t ph = 0; int m_ready = -1, pit = 0;
             for (int blk = first * C; blk < a.num_items; blk += stride * C) for (int item = blk; item < min(blk + C, a.num_items); ++item, ++pit) {
@@ -555,7 +557,7 @@ __device__ __forceinline__ void dft_fwd_body(unsigned char* dft_smem, const CUte
                             umma_bf16_ss(tmem_base + (uint32_t)(ib * NB), adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (part | at | kk) != 0 ? 1u : 0u);
                             if constexpr (SPLIT)
                                 umma_bf16_ss(tmem_base + (uint32_t)(ib * NB), adesc + (uint64_t)(2 * kk),
-                                             umma_desc_k_sw128(sw + (ATOMS + at) * W_ATOM) + (uint64_t)(2 * kk), idesc, 1u);
+                                             umma_desc_k_sw128(sw + (ATOMS + part * APP + at) * W_ATOM) + (uint64_t)(2 * kk), idesc, 1u);
                         }
                     }
                     umma_commit(&bars->empty[stage]);
@@ -684,7 +686,7 @@ __device__ __forceinline__ void store_row(unsigned char* row, int lane, const ui
 template <int B, bool SPLIT>
 __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUtensorMap& tmYf, const CUtensorMap& tmW, const CUtensorMap& tmOut,
                                              const DftLoMaps* lo, const DftArgs& a, const int first, const int stride, const DftExtraOut* ex = nullptr) {
-    using SH = DftShape<B>;
+    using SH = DftShape<B, SPLIT>;
     constexpr int NB = SH::NB, PARTS = SH::PARTS;
     constexpr int ATOMS = SH::KATOMS;                        // K atoms of the DFT matrix (K = B packed spectrum reals)
     constexpr int OUT_ATOMS = NB / KATOM;                    // 64-column pieces of one block's output (of this launch's half)
@@ -695,7 +697,6 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
     constexpr uint32_t STAGE = (SPLIT ? 2 : 1) * STAGE_HALF; // split: [Yf hi | Yf lo]
     constexpr int NBUF = SPLIT ? 1 : DFT_NBUF;               // staging buffers per epilogue warp
     constexpr int NACC = 512 / NB > 4 ? 4 : 512 / NB;
-    static_assert(!(SPLIT && B == 256), "B = 256 split: CUDA-core FFT stages");
     DftBarriers* bars = reinterpret_cast<DftBarriers*>(dft_smem);
     uint32_t* sig = reinterpret_cast<uint32_t*>(dft_smem + 512);                // signaller queue (fused launch)
     unsigned char* epi = dft_smem + 1024;
@@ -729,7 +730,7 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
             mbar_arrive_expect_tx(&bars->wfull, (SPLIT ? 2 : 1) * ATOMS * W_ATOM);
             for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + at * W_ATOM, &tmW, at * KATOM, a.half * NB, &bars->wfull);
             if constexpr (SPLIT)
-                for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + (ATOMS + at) * W_ATOM, &lo->W, at * KATOM, 0, &bars->wfull);
+                for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + (ATOMS + at) * W_ATOM, &lo->W, at * KATOM, a.half * NB, &bars->wfull);
             pdl_wait();                                                          // Yf comes from the previous kernel
             int stage = 0; uint32_t ph = 0; int m_ready = -1, pit = 0;
             for (int blk = first * C; blk < a.num_items; blk += stride * C) for (int item = blk; item < min(blk + C, a.num_items); ++item, ++pit) {
@@ -744,7 +745,7 @@ __device__ __forceinline__ void dft_inv_body(unsigned char* dft_smem, const CUte
                     mbar_arrive_expect_tx(&bars->full[stage], STAGE);
                     tma_load_4d_hint(ring + (size_t)stage * STAGE, &tmYf, 0, m * (TILE_M / TOK_GROUP), j, part * FG, &bars->full[stage], L2_EVICT_FIRST);
                     if constexpr (SPLIT)
-                        tma_load_4d_hint(ring + (size_t)stage * STAGE + STAGE_HALF, &lo->IO, 0, m * (TILE_M / TOK_GROUP), j, 0, &bars->full[stage], L2_EVICT_FIRST);
+                        tma_load_4d_hint(ring + (size_t)stage * STAGE + STAGE_HALF, &lo->IO, 0, m * (TILE_M / TOK_GROUP), j, part * FG, &bars->full[stage], L2_EVICT_FIRST);
                     if (++stage == S) { stage = 0; ph ^= 1u; }
                 }
             }

@@ -20,7 +20,10 @@ namespace rw {
 #ifndef BCL_RW_NF
 #define BCL_RW_NF 3
 #endif
-constexpr int NM = 8, NX = 4, NF = BCL_RW_NF, RG = 4;       // NF = 4 and 6 measured slower (32.9, 34.2 us vs 31.5 us: fewer registers, smaller ring)
+#ifndef BCL_RW_NX
+#define BCL_RW_NX 4
+#endif
+constexpr int NM = 8, NX = BCL_RW_NX, NF = BCL_RW_NF, RG = 4;       // NF = 4 and 6 measured slower (32.9, 34.2 us vs 31.5 us: fewer registers, smaller ring)
 constexpr int THREADS = 32 * (1 + NM + NX + NF);
 #ifndef BCL_RW_MAX_STAGES
 #define BCL_RW_MAX_STAGES 16

@@ -543,12 +543,12 @@ def test_split_prefill_chunked_workspace_full_size():
         assert torch.equal(m(x), y)                                                        # unchunked == chunked, deterministic
 
 
-@pytest.mark.parametrize("inf,outf,B", SHAPES)
+@pytest.mark.parametrize("inf,outf,B", SHAPES + [(8192, 1024, 256), (8192, 8192, 256), (1024, 3584, 256)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_split_prefill_16bit_activations_tensor_core_dft_stages(inf, outf, B, dtype):
-    """fp32 spectra + 16-bit activations (the reference's default Llama configuration, commands.txt:22): for B <= 128 all three
-    stages run on the tensor cores with (hi, lo) operands; the result must stay in the fp32-spectrum class (1e-4 + I/O rounding)
-    and agree with the CUDA-core FFT stages (BCL_PREFILL_DFT=1 equivalent: fp32 activations)."""
+    """fp32 spectra + 16-bit activations (the reference's default Llama configuration, commands.txt:22): all three stages run on the
+    tensor cores with (hi, lo) operands (B = 256, the 70B block size: quarter-N launches of the DFT stages); the result must stay in
+    the fp32-spectrum class (1e-4 + I/O rounding) and agree with the CUDA-core FFT stages (BCL_PREFILL_DFT=1 equivalent: fp32 activations)."""
     N = 300
     g = torch.Generator().manual_seed(inf + outf + B + 3)
     c = torch.randn(outf // B, inf // B, B, generator=g) * 0.01
