@@ -16,7 +16,7 @@
  *   Every pointer is caller-owned.  Device pointers unless the name says host.  The library never allocates,
  *   frees or retains caller memory; its only mutable global state is a thread-local error string plus three mutex-guarded /
  *   write-once caches of facts about the device (dynamic-shared-memory attributes already granted per (kernel, device), the SM
- *   count per device, environment switches read once) -- nothing that depends on the data of a call.  It never syncs
+ *   count per device, profiling / A-B environment switches, most read once) -- nothing that depends on the data of a call.  It never syncs
  *   the device (except the *_host convenience calls, which say so), and every launch goes to the stream that
  *   is passed in (a cudaStream_t cast to void*; NULL = the legacy default stream).  All calls are CUDA-graph
  *   capturable except the *_host ones.  Errors never abort or print: a negative bcl_status is returned and

@@ -46,8 +46,10 @@ constexpr int THREADS = 32 * (1 + NM + NX + NF);
 #endif
 constexpr int MAX_STAGES = BCL_WS_MAX_STAGES;
 constexpr int PAIRS = 4;                     // rows per group buffer (one finisher warp inverse-transforms up to G = 32/T rows at once)
-// blocks per ring stage: 32 blocks of B=128 (16 KB fp32), 16 of B=256, 64 of B=64 -- always BPS = CB/NM blocks per MAC warp
-__host__ __device__ constexpr int stage_blocks(int B) { return 4096 / B; }
+// blocks per ring stage: 32 blocks of B=128 (16 KB fp32), 16 of B=256, 64 of B=64 -- always BPS = CB/NM blocks per MAC warp.
+// 16-bit spectra: twice the blocks, so that a stage is 16 KB for both dtypes: with 8 KB stages the MAC warps' per-stage hand-offs
+// (full wait, release) -- not HBM -- bound the kernel.  A stage then holds TWO block-rows of a q <= CB/2 segment (4096-wide inputs).
+__host__ __device__ constexpr int stage_blocks(int B, int spec_bytes = 4) { return (spec_bytes == 2 ? 8192 : 4096) / B; }
 
 __device__ inline uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ inline void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); }
@@ -95,9 +97,9 @@ struct Barriers {
     uint64_t xempty[2];             // every MAC warp copied its slice into registers      (NM arrivals)
 };
 
-// RS = ring stages per block-row = ceil(qmax / CB): compile-time so that each MAC warp's slice of the x spectrum
-// (RS * BPS blocks) can live in registers and the per-stage multiply is straight-line code.
-template <int B, typename SpecT, int RS>
+// RS = ring stages per block-row = ceil(qmax / CB), KX = x blocks per MAC warp (>= ceil(qmax / NM)): compile-time so that each MAC
+// warp's slice of the x spectrum (KX blocks) can live in registers and the per-stage multiply is straight-line code.
+template <int B, typename SpecT, int RS, int KX>
 __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev* __restrict__ problems, const int* __restrict__ cta_seg_ptr,
                                                               const SegWork* __restrict__ segs, int S, int qmax, int dbg) {
     using LM = LaneMap<B>;
@@ -106,8 +108,9 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
     constexpr int CH = LM::CH, CW = LM::CW;
     constexpr int RG = PAIRS;                                        // rows per group buffer
     constexpr int BLOCK_BYTES = B * (int)sizeof(SpecT);
-    constexpr int CB = stage_blocks(B);                              // blocks per ring stage
+    constexpr int CB = stage_blocks(B, (int)sizeof(SpecT));          // blocks per ring stage
     constexpr int BPS = CB / NM;                                     // blocks per MAC warp per stage
+    constexpr int HB = BPS / 2 > 0 ? BPS / 2 : 1;                    // ... per row when a stage holds two rows
     constexpr int STAGE_BYTES = CB * BLOCK_BYTES;
     constexpr int NW = CW * (int)sizeof(SpecT) / 4;                  // 32-bit words per lane chunk of a spectrum block
     static_assert(CB % NM == 0, "stage must split evenly over the MAC warps");
@@ -149,6 +152,17 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
                 const ProblemDev* P = problems + w.g;
                 const int q = P->q;
                 const unsigned char* rowp = reinterpret_cast<const unsigned char*>(P->spec) + (size_t)w.j0 * q * BLOCK_BYTES;
+                if (BPS >= 2 && 2 * q <= CB) {                          // narrow rows: two block-rows per stage (they are contiguous)
+                    for (int r = w.j0; r < w.j1; r += 2, rowp += (size_t)2 * q * BLOCK_BYTES) {
+                        { TSTART(w); mbar_wait(&bars->empty[stage], ph ^ 1u); TSTOP(w, t_a); }
+                        const uint32_t bytes = (uint32_t)min(2, w.j1 - r) * (uint32_t)q * BLOCK_BYTES;
+                        mbar_arrive_expect_tx(&bars->full[stage], bytes);
+                        bulk_g2s(ring + (size_t)stage * STAGE_BYTES, rowp, bytes, &bars->full[stage]);
+                        if (++stage == S) { stage = 0; ph ^= 1u; }
+                        ++n;
+                    }
+                    continue;
+                }
                 for (int r = w.j0; r < w.j1; ++r, rowp += (size_t)q * BLOCK_BYTES) {
 #pragma unroll
                     for (int cs = 0; cs < RS; ++cs) {
@@ -187,12 +201,13 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
             const int q = problems[w.g].q;
             const int rows = w.j1 - w.j0;
             // my slice of this segment's x spectrum -> registers (blocks i = cs*CB + m + NM*u), then free the X buffer at once
-            float xr[RS][BPS][CH][CW];
+            float xr[RS][BPS][CH][CW];                                // (entries cs * BPS + u >= KX are never touched: no registers)
             if (s > s0) { TSTART(x); mbar_wait(&bars->xfull[0], (uint32_t)(s - s0 - 1) & 1u); TSTOP(x, t_a); }
 #pragma unroll
             for (int cs = 0; cs < RS; ++cs)
 #pragma unroll
                 for (int u = 0; u < BPS; ++u) {
+                    if (cs * BPS + u >= KX) continue;
                     const int i = cs * CB + m + NM * u;
 #pragma unroll
                     for (int ch = 0; ch < CH; ++ch) {
@@ -208,6 +223,75 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
                 }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->xempty[0]);
+            if (BPS >= 2 && 2 * q <= CB) {
+                // ---- two block-rows per stage: rows r and r + 1 (same group: RG is even), x blocks u < HB, independent accumulators
+                for (int r = 0; r < rows; r += 2) {
+                    const bool two = r + 1 < rows;
+                    RowAcc<B, NT> acc1;
+                    acc.clear(); acc1.clear();
+                    { TSTART(f); mbar_wait(&bars->full[stage], ph); TSTOP(f, t_b); }
+                    const SpecT* cbuf = reinterpret_cast<const SpecT*>(ring + (size_t)stage * STAGE_BYTES) + (size_t)m * B;
+                    RawChunk<SpecT, CW> raw[2][HB][CH];
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int u = 0; u < HB; ++u) {
+                            if (u < KX && m + NM * u < q && (rr == 0 || two)) {
+#pragma unroll
+                                for (int ch = 0; ch < CH; ++ch) {
+                                    const uint32_t* src = reinterpret_cast<const uint32_t*>(cbuf + (size_t)(rr * q + NM * u) * B + LM::offset(lane, ch));
+                                    if constexpr (NW == 4) { uint4 t = *reinterpret_cast<const uint4*>(src); raw[rr][u][ch].w[0] = t.x; raw[rr][u][ch].w[1] = t.y; raw[rr][u][ch].w[2] = t.z; raw[rr][u][ch].w[3] = t.w; }
+                                    else if constexpr (NW == 2) { uint2 t = *reinterpret_cast<const uint2*>(src); raw[rr][u][ch].w[0] = t.x; raw[rr][u][ch].w[1] = t.y; }
+                                    else { raw[rr][u][ch].w[0] = *src; }
+                                }
+                            } else {
+#pragma unroll
+                                for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+                                    for (int e = 0; e < NW; ++e) raw[rr][u][ch].w[e] = 0u;
+                            }
+                        }
+#pragma unroll
+                    for (int u = 0; u < HB; ++u) {
+                        if (u >= KX) continue;
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            RowAcc<B, NT>& ac = rr == 0 ? acc : acc1;
+#pragma unroll
+                            for (int ch = 0; ch < CH; ++ch) {
+                                float cv[CW];
+                                decode_raw<SpecT, CW>(raw[rr][u][ch], cv);
+#pragma unroll
+                                for (int e = 0; e < CW; e += 2) {
+                                    const float cr = cv[e], ci = cv[e + 1], xre = xr[0][u][ch][e], xim = xr[0][u][ch][e + 1];
+                                    ac.a[0][ch][e] = fmaf(cr, xre, ac.a[0][ch][e]);
+                                    ac.a[0][ch][e] = fmaf(-ci, xim, ac.a[0][ch][e]);
+                                    ac.a[0][ch][e + 1] = fmaf(cr, xim, ac.a[0][ch][e + 1]);
+                                    ac.a[0][ch][e + 1] = fmaf(ci, xre, ac.a[0][ch][e + 1]);
+                                    if (ch == 0 && e == 0) {
+                                        ac.dc[0] = fmaf(cr, xre, ac.dc[0]);
+                                        ac.ny[0] = fmaf(ci, xim, ac.ny[0]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->empty[stage]);
+                    if (++stage == S) { stage = 0; ph ^= 1u; }
+                    const int slot = r % RG;
+                    const int gb = gi % NF;
+                    if (slot == 0) { TSTART(g); mbar_wait(&bars->gempty[gb], ((uint32_t)(gi / NF) & 1u) ^ 1u); TSTOP(g, t_c); }
+                    store_partial<B, NT, NM>(acc, part + (size_t)gb * PAIRS * NM * B, slot, m, lane);
+                    if (two) store_partial<B, NT, NM>(acc1, part + (size_t)gb * PAIRS * NM * B, slot + 1, m, lane);
+                    if (slot + (two ? 1 : 0) == RG - 1 || r + 2 >= rows) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->gfull[gb]);
+                        ++gi;
+                    }
+                }
+                continue;
+            }
             for (int r = 0; r < rows; ++r) {
                 acc.clear();
 #pragma unroll
@@ -218,7 +302,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
                         RawChunk<SpecT, CW> raw[BPS][CH];
 #pragma unroll
                         for (int u = 0; u < BPS; ++u) {               // all shared loads first: one latency, no branches
-                            if (cs * CB + m + NM * u < q) {
+                            if (cs * BPS + u < KX && cs * CB + m + NM * u < q) {
 #pragma unroll
                                 for (int ch = 0; ch < CH; ++ch) {
                                     const uint32_t* src = reinterpret_cast<const uint32_t*>(cbuf + (size_t)(NM * u) * B + LM::offset(lane, ch));
@@ -235,6 +319,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
                         }
 #pragma unroll
                         for (int u = 0; u < BPS; ++u) {
+                            if (cs * BPS + u >= KX) continue;
 #pragma unroll
                             for (int ch = 0; ch < CH; ++ch) {
                                 float cv[CW];
@@ -323,18 +408,18 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
 
 size_t smem_bytes(int B, int spec_bytes, int qmax, int S) {
     const size_t fscr = B == 64 ? FftCfg<64>::WARP_SCRATCH_BYTES : (B == 128 ? FftCfg<128>::WARP_SCRATCH_BYTES : FftCfg<256>::WARP_SCRATCH_BYTES);
-    const size_t stage = (size_t)stage_blocks(B) * B * spec_bytes;
+    const size_t stage = (size_t)stage_blocks(B, spec_bytes) * B * spec_bytes;
     return 512 + 1024 + (size_t)S * stage + (size_t)NF * PAIRS * NM * B * 4 + (size_t)(NX + NF) * fscr + (size_t)qmax * B * 4;
 }
 
 // Number of ring stages that fit next to the fixed buffers (0 = this shape does not fit the warp-specialised kernel).
 int pick_stages(int B, int spec_dtype, int nt, int qmax) {
     if (nt != 1) return 0;                                           // decode path: one token per problem
-    if (qmax > 4 * stage_blocks(B)) return 0;                        // x slice must fit the MAC warps' registers (RS <= 4)
     const int sb = spec_dtype == BCL_F32 ? 4 : 2;
+    if (qmax > 4 * stage_blocks(B, sb) || (qmax + NM - 1) / NM > 16) return 0;   // x slice must fit the MAC warps' registers (RS <= 4, KX <= 16)
     const size_t budget = 227 * 1024;
     const size_t fixed = smem_bytes(B, sb, qmax, 0);
-    const size_t stage = (size_t)stage_blocks(B) * B * sb;
+    const size_t stage = (size_t)stage_blocks(B, sb) * B * sb;
     if (fixed + 3 * stage > budget) return 0;
     int S = (int)((budget - fixed) / stage);
     if (S > MAX_STAGES) S = MAX_STAGES;
@@ -346,9 +431,9 @@ static bool pdl_enabled() {                                             // BCL_P
     return on;
 }
 
-template <int B, typename SpecT, int RS>
+template <int B, typename SpecT, int RS, int KX>
 static cudaError_t launch_t(const GroupPlanHeader& H, const unsigned char* d, cudaStream_t st) {
-    auto kern = stream_ws_kernel<B, SpecT, RS>;
+    auto kern = stream_ws_kernel<B, SpecT, RS, KX>;
     const int S = pick_stages(B, H.spec_dtype, H.nt, H.qmax);
     const size_t smem = smem_bytes(B, (int)sizeof(SpecT), H.qmax, S);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -375,12 +460,25 @@ static cudaError_t launch_t(const GroupPlanHeader& H, const unsigned char* d, cu
 
 template <int B, typename SpecT>
 static cudaError_t launch_b(const GroupPlanHeader& H, const unsigned char* d, cudaStream_t st) {
-    const int rs = (H.qmax + stage_blocks(B) - 1) / stage_blocks(B);
-    switch (rs) {
-        case 1: return launch_t<B, SpecT, 1>(H, d, st);
-        case 2: return launch_t<B, SpecT, 2>(H, d, st);
-        case 3: return launch_t<B, SpecT, 3>(H, d, st);
-        default: return launch_t<B, SpecT, 4>(H, d, st);
+    constexpr int CB = stage_blocks(B, (int)sizeof(SpecT)), BPS = CB / NM;
+    const int rs = (H.qmax + CB - 1) / CB;
+    const int kx = (H.qmax + NM - 1) / NM;                            // x blocks per MAC warp
+    if constexpr (BPS <= 4) {                                        // KX = RS * BPS <= 16: one instance per RS
+        switch (rs) {
+            case 1: return launch_t<B, SpecT, 1, BPS>(H, d, st);
+            case 2: return launch_t<B, SpecT, 2, 2 * BPS>(H, d, st);
+            case 3: return launch_t<B, SpecT, 3, 3 * BPS>(H, d, st);
+            default: return launch_t<B, SpecT, 4, 4 * BPS>(H, d, st);
+        }
+    } else {                                                         // wider stages: bound the register slice by the plan's qmax (KX <= 16)
+        constexpr int RSMAX = 16 / BPS > 0 ? 16 / BPS : 1;
+        if (rs > RSMAX || kx > 16) return cudaErrorInvalidValue;
+        if (rs == 1) return kx <= BPS / 2 ? launch_t<B, SpecT, 1, BPS / 2>(H, d, st) : launch_t<B, SpecT, 1, BPS>(H, d, st);
+        if constexpr (RSMAX >= 2) {
+            if (kx <= BPS + BPS / 2) return launch_t<B, SpecT, 2, BPS + BPS / 2>(H, d, st);
+            return launch_t<B, SpecT, 2, 2 * BPS>(H, d, st);
+        }
+        return cudaErrorInvalidValue;
     }
 }
 
