@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BCL_ABI_VERSION 11
+#define BCL_ABI_VERSION 12
 
 typedef enum bcl_dtype { BCL_F32 = 0, BCL_F16 = 1, BCL_BF16 = 2 } bcl_dtype;
 
@@ -46,7 +46,12 @@ typedef enum bcl_dtype { BCL_F32 = 0, BCL_F16 = 1, BCL_BF16 = 2 } bcl_dtype;
  *           spec_dtype BCL_BF16: one bf16 Cmat (parity class 1e-2).  spec_dtype BCL_F32: the SPLIT layout -- Cmat_hi then
  *           Cmat_lo, bf16 each, value = hi + lo to ~2^-17; the frequency GEMM evaluates Ahi*Bhi + Ahi*Blo + Alo*Bhi with fp32
  *           accumulation and the rfft / irfft stages run in fp32 (parity class 1e-4, the reference's complex64 contraction). */
-typedef enum bcl_layout { BCL_LAYOUT_STREAM = 0, BCL_LAYOUT_GEMM = 1 } bcl_layout;
+typedef enum bcl_layout {
+    BCL_LAYOUT_STREAM = 0,      /* [p][q][B] packed half-spectra (f32 / bf16): the CUDA-core decode kernels, bcl_forward at small N */
+    BCL_LAYOUT_GEMM = 1,        /* per-frequency K-major matrices + DFT matrices: the tcgen05 prefill path (bcl_forward at large N) */
+    BCL_LAYOUT_DECODE_TC = 2    /* bf16, [32-row quad][f][8-row group][k/8][8][8]: the UMMA operand image streamed by the tensor-core
+                                   decode kernel (grouped launches with one token per problem, B <= 128; bcl_group_plan_encode_layout) */
+} bcl_layout;
 
 typedef enum bcl_status {
     BCL_OK = 0,
@@ -171,6 +176,12 @@ size_t bcl_group_plan_bytes(int count, int num_ctas);
 /* num_ctas: how many CTAs to partition over (e.g. 2 * SM count); returns BCL_OK and fills host_plan. */
 int bcl_group_plan_encode(const bcl_problem* problems, int count, int B, int spec_dtype, int num_ctas,
                           void* host_plan, size_t host_plan_bytes);
+/* Same, for problems whose `spec` pointers are in `layout`.  BCL_LAYOUT_DECODE_TC (bf16, one token per problem, B <= 128): the plan
+ * selects the tensor-core decode kernel -- the per-frequency contraction (einsum, src/patch_llama_fft.py:260) as tcgen05 matrix-vector
+ * products, the spectrum streamed by bulk copies as the UMMA operand image -- and cuts the work at multiples of 8 block-rows.
+ * BCL_ERR_UNSUPPORTED when the configuration is not covered (callers then plan with the STREAM layout). */
+int bcl_group_plan_encode_layout(const bcl_problem* problems, int count, int B, int spec_dtype, int layout, int num_ctas,
+                                 void* host_plan, size_t host_plan_bytes);
 /* dev_plan = device copy of host_plan (same bytes).  host_plan is read for the launch geometry only. */
 int bcl_forward_grouped(const void* dev_plan, const void* host_plan, void* stream);
 

@@ -18,7 +18,7 @@ from .patch_llama_fft import (  # noqa: F401
     enable_cfft_cache, disable_cfft_cache, _detect_best_convention_for_layer, _get_submodule_by_name,
 )
 from .fft_utils import circulant_matvec_fft  # noqa: F401
-from .grouped import GroupedBCForward, HostPipe  # noqa: F401
+from .grouped import GroupedBCForward, HostPipe, decode_tc_spectrum  # noqa: F401
 from .shared_input import SharedInputGroup, fuse_shared_inputs, unfuse_shared_inputs  # noqa: F401
 from .chain import BCChain, FusedBCMLP, fuse_mlp, unfuse_mlp, barrier_counter  # noqa: F401
 from .sharded import ShardedBlockCirculantLinear, shard_bc_linear, shard_rows, gather_columns, push_columns  # noqa: F401

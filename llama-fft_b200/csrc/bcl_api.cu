@@ -88,6 +88,7 @@ size_t bcl_spectrum_bytes(int p, int q, int B, int spec_dtype, int layout) {
     }
     if (layout == BCL_LAYOUT_GEMM)                                  // f32 = the split (hi, lo) bf16 layout of the fp32-accurate tensor path
         return (spec_dtype == BCL_BF16 || spec_dtype == BCL_F32) ? bcl::gemm_spectrum_bytes(p, q, B, spec_dtype == BCL_F32) : 0;
+    if (layout == BCL_LAYOUT_DECODE_TC) return (spec_dtype == BCL_BF16 && B <= 128) ? bcl::stream_tc_spectrum_bytes(p, q, B) : 0;
     return 0;
 }
 
@@ -105,6 +106,11 @@ int bcl_precompute_spectrum(const float* c, int p, int q, int B, void* spec, int
         if (spec_dtype != BCL_BF16 && spec_dtype != BCL_F32) return fail(BCL_ERR_DTYPE, "GEMM spectrum must be bf16 or f32 (split bf16 pairs)");
         cudaError_t e = bcl::launch_spectrum_gemm(c, spec, p, q, B, spec_dtype == BCL_F32, (cudaStream_t)stream);
         return e == cudaSuccess ? BCL_OK : cuda_fail(e, "GEMM spectrum precompute launch");
+    }
+    if (layout == BCL_LAYOUT_DECODE_TC) {
+        if (spec_dtype != BCL_BF16 || B > 128) return fail(BCL_ERR_UNSUPPORTED, "DECODE_TC spectra are bf16 with B <= 128");
+        cudaError_t e = bcl::launch_spectrum_tc(c, spec, p, q, B, (cudaStream_t)stream);
+        return e == cudaSuccess ? BCL_OK : cuda_fail(e, "DECODE_TC spectrum precompute launch");
     }
     return fail(BCL_ERR_ARG, "unknown spectrum layout %d", layout);
 }
@@ -252,9 +258,16 @@ size_t bcl_group_plan_bytes(int count, int num_ctas) {
 
 int bcl_group_plan_encode(const bcl_problem* problems, int count, int B, int spec_dtype, int num_ctas,
                           void* host_plan, size_t host_plan_bytes) {
+    return bcl_group_plan_encode_layout(problems, count, B, spec_dtype, BCL_LAYOUT_STREAM, num_ctas, host_plan, host_plan_bytes);
+}
+
+int bcl_group_plan_encode_layout(const bcl_problem* problems, int count, int B, int spec_dtype, int layout, int num_ctas,
+                                 void* host_plan, size_t host_plan_bytes) {
+    if (layout != BCL_LAYOUT_STREAM && layout != BCL_LAYOUT_DECODE_TC) return fail(BCL_ERR_ARG, "grouped plans take STREAM or DECODE_TC spectra");
     if (!problems || !host_plan || count <= 0 || num_ctas <= 0) return fail(BCL_ERR_ARG, "bad plan arguments");
     if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
     if (spec_dtype != BCL_F32 && spec_dtype != BCL_BF16) return fail(BCL_ERR_DTYPE, "STREAM spectrum must be f32 or bf16");
+    if (layout == BCL_LAYOUT_DECODE_TC && spec_dtype != BCL_BF16) return fail(BCL_ERR_UNSUPPORTED, "DECODE_TC spectra are bf16");
     const size_t need = bcl_group_plan_bytes(count, num_ctas);
     if (host_plan_bytes < need) return fail(BCL_ERR_WORKSPACE, "plan buffer %zu < %zu bytes", host_plan_bytes, need);
     int64_t maxN = 0; int qmax = 0; int64_t total_w = 0;
@@ -273,6 +286,12 @@ int bcl_group_plan_encode(const bcl_problem* problems, int count, int B, int spe
     if (variant == 1 && bcl::stream_rw_supported(B, spec_dtype, nt, qmax)) variant = 2;     // bf16 spectra: row-per-warp kernel
     if (force && !strcmp(force, "plain")) variant = 0;
     if (force && !strcmp(force, "ws") && variant == 2) variant = 1;
+    const int gran = layout == BCL_LAYOUT_DECODE_TC ? 8 : 1;        // block-rows per work unit (DECODE_TC: 8-row groups of the operand image)
+    if (layout == BCL_LAYOUT_DECODE_TC) {
+        if (!bcl::stream_tc_supported(B, spec_dtype, nt, qmax))
+            return fail(BCL_ERR_UNSUPPORTED, "tensor-core decode kernel: one token per problem, B <= 128, q <= 128 (got N <= %d, B = %d, qmax = %d)", nt, B, qmax);
+        variant = 3;
+    }
     if (variant == 0 && bcl::stream_smem_bytes(B, nt, qmax, 8) > 200 * 1024)
         return fail(BCL_ERR_UNSUPPORTED, "x spectrum tile (N=%d, q=%d, B=%d) exceeds shared memory; call bcl_forward per problem", nt, qmax, B);
 
@@ -308,6 +327,7 @@ int bcl_group_plan_encode(const bcl_problem* problems, int count, int B, int spe
             int64_t room = limit - cum;
             int take = (int)((room + q - 1) / q);
             if (take < 1) take = 1;
+            take = (take + gran - 1) / gran * gran;
             if (take > p - j) take = p - j;
             segs[4 * nseg + 0] = g; segs[4 * nseg + 1] = j; segs[4 * nseg + 2] = j + take; segs[4 * nseg + 3] = 0;
             ++nseg;
@@ -327,7 +347,8 @@ int bcl_forward_grouped(const void* dev_plan, const void* host_plan, void* strea
     memcpy(&H, host_plan, sizeof(H));
     if (H.magic != bcl::kPlanMagic) return fail(BCL_ERR_ARG, "host_plan was not written by bcl_group_plan_encode");
     if (!aligned(dev_plan, 16)) return fail(BCL_ERR_ALIGN, "dev_plan must be 16-byte aligned");
-    cudaError_t e = H.variant == 2 ? bcl::launch_stream_rw(H, dev_plan, (cudaStream_t)stream)
+    cudaError_t e = H.variant == 3 ? bcl::launch_stream_tc(H, dev_plan, (cudaStream_t)stream)
+                  : H.variant == 2 ? bcl::launch_stream_rw(H, dev_plan, (cudaStream_t)stream)
                   : H.variant == 1 ? bcl::launch_stream_ws(H, dev_plan, (cudaStream_t)stream)
                                    : bcl::launch_stream_grouped(H, dev_plan, (cudaStream_t)stream);
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "grouped forward launch");

@@ -44,7 +44,8 @@ struct GroupPlanHeader {
     int32_t num_ctas;
     int32_t num_segs;
     int32_t B, spec_dtype, nt, qmax;
-    int32_t variant;      // 0 = plain CTA-cooperative kernel, 1 = warp-specialised TMA pipeline (one CTA per SM), 2 = its row-per-warp form (bf16 spectra)
+    int32_t variant;      // 0 = plain CTA-cooperative kernel, 1 = warp-specialised TMA pipeline (one CTA per SM), 2 = its row-per-warp form (bf16 spectra),
+                          // 3 = tensor-core MAC over BCL_LAYOUT_DECODE_TC spectra (bcl_stream_tc.cu)
     int32_t reserved;
     uint64_t off_problems, off_cta_ptr, off_segs, total_bytes;
 };
@@ -59,6 +60,12 @@ bool stream_rw_supported(int B, int spec_dtype, int nt, int qmax);
 cudaError_t launch_stream_rw(const GroupPlanHeader& H, const void* dev_plan, cudaStream_t st);
 size_t stream_smem_bytes(int B, int nt, int q, int warps);
 int stream_pick_nt(int64_t N, int q, int B);
+
+// grouped decode with the MAC on the tensor cores (bcl_stream_tc.cu): BCL_LAYOUT_DECODE_TC spectra (bf16), B <= 128, one token per problem
+size_t stream_tc_spectrum_bytes(int p, int q, int B);
+cudaError_t launch_spectrum_tc(const float* c, void* spec, int p, int q, int B, cudaStream_t st);
+bool stream_tc_supported(int B, int spec_dtype, int nt, int qmax);
+cudaError_t launch_stream_tc(const GroupPlanHeader& H, const void* dev_plan, cudaStream_t st);
 
 bool chain_supported(int B, int spec_dtype, int qmax);
 cudaError_t launch_chain(const ChainParams& prm, int B, int spec_dtype, int qmax, int grid, cudaStream_t st);

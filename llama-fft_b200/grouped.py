@@ -5,7 +5,7 @@ latency, so independent problems are submitted together and the launch streams a
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Sequence
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -20,13 +20,19 @@ class GroupedBCForward:
 
     def __init__(self, xs: Sequence[torch.Tensor], specs: Sequence[torch.Tensor],
                  biases: Optional[Sequence[Optional[torch.Tensor]]] = None, *, num_ctas: Optional[int] = None,
-                 _y_packed=None):
+                 _y_packed=None, layout: int = _cabi.LAYOUT_STREAM, shapes: Optional[Sequence[Tuple[int, int]]] = None,
+                 block_size: Optional[int] = None):
+        """layout = LAYOUT_DECODE_TC: `specs` are the opaque bf16 operand images of ``decode_tc_spectrum`` (uint8 buffers), `shapes`
+        = [(p, q)] and `block_size` say what they hold; the plan then runs the tensor-core decode kernel (one token per problem)."""
         assert len(xs) == len(specs) and len(xs) > 0
         biases = list(biases) if biases is not None else [None] * len(xs)
         dev = xs[0].device
         _cabi.require_cuda(xs[0], "input x")
-        B = specs[0].shape[-1]
-        spec_dtype = specs[0].dtype
+        tc = layout == _cabi.LAYOUT_DECODE_TC
+        if tc and (shapes is None or block_size is None or len(shapes) != len(specs)):
+            raise ValueError("LAYOUT_DECODE_TC needs shapes=[(p, q)] and block_size")
+        B = int(block_size) if tc else specs[0].shape[-1]
+        spec_dtype = torch.bfloat16 if tc else specs[0].dtype
         self.device, self.B = dev, B
         self.xs, self.specs, self.biases = list(xs), list(specs), biases
         self.ys = []
@@ -35,9 +41,12 @@ class GroupedBCForward:
             self.y_all = torch.empty(_y_packed[0], device=dev, dtype=xs[0].dtype)
         probs = (_cabi.Problem * len(xs))()
         for g, (x, s, b) in enumerate(zip(xs, specs, biases)):
-            assert x.device == dev and s.device == dev and x.dim() == 2 and s.dim() == 3
-            assert s.shape[-1] == B and s.dtype == spec_dtype and x.is_contiguous() and s.is_contiguous()
-            p, q = int(s.shape[0]), int(s.shape[1])
+            assert x.device == dev and s.device == dev and x.dim() == 2 and x.is_contiguous() and s.is_contiguous()
+            if tc:
+                p, q = int(shapes[g][0]), int(shapes[g][1])
+            else:
+                assert s.dim() == 3 and s.shape[-1] == B and s.dtype == spec_dtype
+                p, q = int(s.shape[0]), int(s.shape[1])
             if x.shape[1] != q * B:
                 raise ValueError("in_features mismatch")
             y_dtype = x.dtype if b is None else torch.promote_types(x.dtype, b.dtype)
@@ -57,19 +66,23 @@ class GroupedBCForward:
         self.num_ctas = int(num_ctas)
         nbytes = L.bcl_group_plan_bytes(len(xs), self.num_ctas)
         self.host_plan = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-        rc = L.bcl_group_plan_encode(probs, len(xs), B, _cabi.DTYPE[spec_dtype], self.num_ctas,
-                                     self.host_plan.data_ptr(), nbytes)
-        _cabi.check(rc, "bcl_group_plan_encode")
+        rc = L.bcl_group_plan_encode_layout(probs, len(xs), B, _cabi.DTYPE[spec_dtype], layout, self.num_ctas,
+                                            self.host_plan.data_ptr(), nbytes)
+        _cabi.check(rc, "bcl_group_plan_encode_layout")
         self.dev_plan = self.host_plan.to(dev)
-        self.algorithmic_bytes = sum(x.numel() * x.element_size() + s.numel() * s.element_size() + y.numel() * y.element_size()
+        # (DECODE_TC images pad p to 8 and 2q to 16: the algorithmic figure stays p * q * B reals)
+        self.algorithmic_bytes = sum(x.numel() * x.element_size() + (y.shape[1] * x.shape[1] // B * 2 if tc else s.numel() * s.element_size())
+                                     + y.numel() * y.element_size()
                                      + (0 if b is None else b.numel() * b.element_size())
                                      for x, s, y, b in zip(self.xs, self.specs, self.ys, self.biases))
 
     @classmethod
-    def from_packed(cls, shapes, specs, N, x_dtype, device, **kw):
+    def from_packed(cls, shapes, specs, N, x_dtype, device, block_size=None, **kw):
         """Problems whose x (and y) live back to back in ONE staging buffer each, so a host round trip is one copy
         per direction (``run_host``).  shapes[g] = (p, q); returns the instance with .x_all / .y_all set."""
-        B = specs[0].shape[-1]
+        B = int(block_size) if block_size is not None else specs[0].shape[-1]
+        if kw.get("layout", _cabi.LAYOUT_STREAM) == _cabi.LAYOUT_DECODE_TC:
+            kw.update(shapes=list(shapes), block_size=B)
         esz = torch.empty(0, dtype=x_dtype).element_size()
         align = 16 // esz
         x_off, y_off, xo, yo = [], [], 0, 0
@@ -125,6 +138,22 @@ class GroupedBCForward:
                                                  _cabi.stream_ptr(self.device))
         _cabi.check(rc, "bcl_forward_grouped")
         return self.ys
+
+
+def decode_tc_spectrum(c: torch.Tensor) -> torch.Tensor:
+    """c (p, q, B) on a CUDA device -> the bf16 operand image of the tensor-core decode kernel (BCL_LAYOUT_DECODE_TC), a uint8 buffer."""
+    _cabi.require_cuda(c, "c")
+    p, q, B = (int(v) for v in c.shape)
+    L = _cabi.lib()
+    nbytes = L.bcl_spectrum_bytes(p, q, B, _cabi.BF16, _cabi.LAYOUT_DECODE_TC)
+    if nbytes == 0:
+        raise ValueError("LAYOUT_DECODE_TC covers block sizes 64 and 128")
+    c32 = c.detach().to(torch.float32).contiguous()
+    spec = torch.empty(nbytes, device=c.device, dtype=torch.uint8)
+    with _cabi.on_device(c.device):
+        rc = L.bcl_precompute_spectrum(c32.data_ptr(), p, q, B, spec.data_ptr(), _cabi.BF16, _cabi.LAYOUT_DECODE_TC, _cabi.stream_ptr(c.device))
+    _cabi.check(rc, "bcl_precompute_spectrum")
+    return spec
 
 
 class HostPipe:

@@ -388,3 +388,35 @@ def test_grouped_decode_bf16_row_per_warp_kernel(B, shapes, reps, num_ctas, bias
             # (with a bias the flipped ulp belongs to the value before the bias was added, which |y| no longer bounds: absolute 1e-3)
             assert_close(y, m(x), 1e-3 if bias else 1e-5, torch.float16)
             assert_close(y, O.bc_forward_torch(m.c.detach().cpu(), x.cpu(), None if m.bias is None else m.bias.detach().cpu()), 1e-2, torch.float16)
+
+
+@pytest.mark.parametrize("B,shapes,reps,num_ctas,bias,dtype", [
+    (128, [(32, 32)] * 4 + [(86, 32)] * 2 + [(32, 86)], 3, None, False, torch.float16),      # Llama-2-7B layer x 3, one CTA per SM
+    (128, [(32, 32), (86, 32), (32, 86), (5, 3), (9, 1), (40, 17)], 2, 11, True, torch.float16),   # ragged rows / K padding, few CTAs
+    (128, [(32, 32)] * 2 + [(3, 64)], 1, 5, False, torch.bfloat16),
+    (64, [(64, 64), (10, 7), (172, 64)], 2, 37, False, torch.float32)])
+def test_grouped_decode_tensor_core_kernel(B, shapes, reps, num_ctas, bias, dtype):
+    """BCL_LAYOUT_DECODE_TC: the grouped batch-1 launch with the per-frequency contraction on tcgen05 (bcl_stream_tc.cu): bf16 spectrum
+    image streamed as the UMMA A operand, bf16 x spectrum as the B operand, fp32 accumulation in TMEM, inverse FFT + reference epilogue
+    on the CUDA cores.  Every problem must match the oracle in the bf16 class (the x spectrum is rounded to bf16 too, like Xf of the
+    prefill path) and its own per-module forward with bf16 spectra; a second launch of the same plan must be bit-identical."""
+    g = torch.Generator().manual_seed(B + len(shapes) + reps)
+    layers, xs, tcs = [], [], []
+    for _ in range(reps):
+        for (p, q) in shapes:
+            b = torch.randn(p * B, generator=g) * 0.1 if bias else None
+            layers.append(make_layer(torch.randn(p, q, B, generator=g) * 0.02, b, torch.bfloat16))
+            xs.append(torch.randn(1, q * B, generator=g).to(dtype).to(DEV))
+            tcs.append(bc.decode_tc_spectrum(layers[-1].c.detach()))
+    kw = {} if num_ctas is None else {"num_ctas": num_ctas}
+    grp = bc.GroupedBCForward(xs, tcs, [m.bias.detach() for m in layers] if bias else None, layout=_cabi.LAYOUT_DECODE_TC,
+                              shapes=shapes * reps, block_size=B, **kw)
+    ys = [y.clone() for y in grp.run()]
+    ys2 = grp.run()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for m, x, y, y2 in zip(layers, xs, ys, ys2):
+            assert torch.equal(y, y2)
+            assert not torch.isnan(y.float()).any()
+            assert_close(y, O.bc_forward_torch(m.c.detach().cpu(), x.cpu(), None if m.bias is None else m.bias.detach().cpu()), 1e-2, dtype)
+            assert_close(y, m(x), 1e-2, dtype)
