@@ -88,6 +88,12 @@ __device__ inline long long clk() { return 0; }
 #define TPRINT(...)
 #endif
 
+// The first packed pair of a lane chunk is (DC, Nyquist) in lane 0 -- two real x real products, Y_dc = sum C_dc X_dc and Y_ny = sum C_ny
+// X_ny -- and an ordinary complex bin (Re, Im) in every other lane.  The MAC loop keeps the two products of that pair's real part in
+// separate sums (dc = sum cr xre, ny = sum ci xim): lane 0 needs exactly those, the other lanes need their difference.  That saves the
+// two extra FMAs per block every lane used to spend on lane 0's behalf (10 -> 8 per block at B = 128) and halves the dependent chain.
+template <typename Acc> __device__ __forceinline__ void park_prepare(Acc& acc) { acc.a[0][0][0] = acc.dc[0] - acc.ny[0]; }
+
 struct Barriers {
     uint64_t full[MAX_STAGES];      // ring stage filled by TMA            (1 arrival + tx bytes)
     uint64_t empty[MAX_STAGES];     // ring stage released by the MAC warps (NM arrivals)
@@ -264,14 +270,15 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
 #pragma unroll
                                 for (int e = 0; e < CW; e += 2) {
                                     const float cr = cv[e], ci = cv[e + 1], xre = xr[0][u][ch][e], xim = xr[0][u][ch][e + 1];
-                                    ac.a[0][ch][e] = fmaf(cr, xre, ac.a[0][ch][e]);
-                                    ac.a[0][ch][e] = fmaf(-ci, xim, ac.a[0][ch][e]);
-                                    ac.a[0][ch][e + 1] = fmaf(cr, xim, ac.a[0][ch][e + 1]);
-                                    ac.a[0][ch][e + 1] = fmaf(ci, xre, ac.a[0][ch][e + 1]);
-                                    if (ch == 0 && e == 0) {
+                                    if (ch == 0 && e == 0) {         // first pair: the two products of Re kept apart (see park_prepare)
                                         ac.dc[0] = fmaf(cr, xre, ac.dc[0]);
                                         ac.ny[0] = fmaf(ci, xim, ac.ny[0]);
+                                    } else {
+                                        ac.a[0][ch][e] = fmaf(cr, xre, ac.a[0][ch][e]);
+                                        ac.a[0][ch][e] = fmaf(-ci, xim, ac.a[0][ch][e]);
                                     }
+                                    ac.a[0][ch][e + 1] = fmaf(cr, xim, ac.a[0][ch][e + 1]);
+                                    ac.a[0][ch][e + 1] = fmaf(ci, xre, ac.a[0][ch][e + 1]);
                                 }
                             }
                         }
@@ -282,6 +289,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
                     const int slot = r % RG;
                     const int gb = gi % NF;
                     if (slot == 0) { TSTART(g); mbar_wait(&bars->gempty[gb], ((uint32_t)(gi / NF) & 1u) ^ 1u); TSTOP(g, t_c); }
+                    park_prepare(acc); park_prepare(acc1);
                     store_partial<B, NT, NM>(acc, part + (size_t)gb * PAIRS * NM * B, slot, m, lane);
                     if (two) store_partial<B, NT, NM>(acc1, part + (size_t)gb * PAIRS * NM * B, slot + 1, m, lane);
                     if (slot + (two ? 1 : 0) == RG - 1 || r + 2 >= rows) {
@@ -327,14 +335,15 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
 #pragma unroll
                                 for (int e = 0; e < CW; e += 2) {
                                     const float cr = cv[e], ci = cv[e + 1], xre = xr[cs][u][ch][e], xim = xr[cs][u][ch][e + 1];
-                                    acc.a[0][ch][e] = fmaf(cr, xre, acc.a[0][ch][e]);
-                                    acc.a[0][ch][e] = fmaf(-ci, xim, acc.a[0][ch][e]);
-                                    acc.a[0][ch][e + 1] = fmaf(cr, xim, acc.a[0][ch][e + 1]);
-                                    acc.a[0][ch][e + 1] = fmaf(ci, xre, acc.a[0][ch][e + 1]);
-                                    if (ch == 0 && e == 0) {         // packed slot 0/1 of lane 0 is (DC, Nyquist)
+                                    if (ch == 0 && e == 0) {         // first pair: the two products of Re kept apart (see park_prepare)
                                         acc.dc[0] = fmaf(cr, xre, acc.dc[0]);
                                         acc.ny[0] = fmaf(ci, xim, acc.ny[0]);
+                                    } else {
+                                        acc.a[0][ch][e] = fmaf(cr, xre, acc.a[0][ch][e]);
+                                        acc.a[0][ch][e] = fmaf(-ci, xim, acc.a[0][ch][e]);
                                     }
+                                    acc.a[0][ch][e + 1] = fmaf(cr, xim, acc.a[0][ch][e + 1]);
+                                    acc.a[0][ch][e + 1] = fmaf(ci, xre, acc.a[0][ch][e + 1]);
                                 }
                             }
                         }
@@ -347,6 +356,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
                 const int slot = r % RG;
                 const int gb = gi % NF;
                 if (slot == 0) { TSTART(g); mbar_wait(&bars->gempty[gb], ((uint32_t)(gi / NF) & 1u) ^ 1u); TSTOP(g, t_c); }
+                park_prepare(acc);
                 store_partial<B, NT, NM>(acc, part + (size_t)gb * PAIRS * NM * B, slot, m, lane);
                 if (slot == RG - 1 || r == rows - 1) {
                     __syncwarp();
