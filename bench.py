@@ -763,16 +763,17 @@ def prefill_algorithmic_flops(n=PREFILL_TOKENS):
     return sum(4 * n * (outf // B) * (inf // B) * (B - 1) for _, inf, outf in LLAMA7B_LAYER)
 
 
-def time_prefill_layer(bc, _cabi, dev, reps, n=PREFILL_TOKENS, through_host=False):
+def time_prefill_layer(bc, _cabi, dev, reps, n=PREFILL_TOKENS, through_host=False, spectrum_dtype=None):
     """One decoder layer's 7 BC projections (bf16 spectra -> tcgen05 prefill path) on n tokens of synthetic fp16
     activations; inputs rotate over two buffer sets (each larger than L2).  Returns (us per layer, per-shape us, status)."""
     import torch
     from llama_fft_b200.patch_llama_fft import bc_forward, prefill_status
     torch.manual_seed(0)
+    sdt = torch.bfloat16 if spectrum_dtype is None else spectrum_dtype
     layers = {}
     for name, inf, outf in LLAMA7B_LAYER:
         if (inf, outf) not in layers:
-            m = bc.BlockCirculantLinear(inf, outf, block_size=B, bias=False, spectrum_dtype=torch.bfloat16).to(dev).eval()
+            m = bc.BlockCirculantLinear(inf, outf, block_size=B, bias=False, spectrum_dtype=sdt).to(dev).eval()
             layers[(inf, outf)] = (m, m.build_spectrum(layout=_cabi.LAYOUT_GEMM))
     xs = {d: [torch.randn(n, d, device=dev).half() for _ in range(2)] for d in (4096, 11008)}
     ys = {d: [torch.empty(n, d, device=dev, dtype=torch.float16) for _ in range(2)] for d in (4096, 11008)}
@@ -787,7 +788,7 @@ def time_prefill_layer(bc, _cabi, dev, reps, n=PREFILL_TOKENS, through_host=Fals
         x, y = xs[inf][i & 1], ys[outf][i & 1]
         if through_host:
             x.copy_(hx[inf], non_blocking=True)
-        bc_forward(x, spec, None, outf // B, inf // B, B, out=y, layout=_cabi.LAYOUT_GEMM)
+        bc_forward(x, spec, None, outf // B, inf // B, B, out=y, layout=_cabi.LAYOUT_GEMM, spectrum_dtype=sdt)
         if through_host:
             hy[outf].copy_(y, non_blocking=True)
             stream.synchronize()
@@ -918,6 +919,15 @@ def prefill_detail(bc, _cabi, dev, reps=5):
                                       "hbm_frac_of_measured_peak": alg2 / (us2 * 1e-6) / 1e9 / peak, "pipeline_status": status2}
     except Exception as e:                                               # noqa: BLE001
         out["shared_input_fusion"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    torch.cuda.empty_cache()
+    try:                                                                 # the default spectrum_dtype (fp32): split (hi, lo) operands on tcgen05, 1e-4 class
+        us3, per3, status3 = time_prefill_layer(bc, _cabi, dev, max(2, reps // 2), spectrum_dtype=torch.float32)
+        alg3 = sum(PREFILL_TOKENS * inf * 2 + inf * outf // B * 4 + PREFILL_TOKENS * outf * 2 for _, inf, outf in LLAMA7B_LAYER)
+        out["fp32_spectra"] = {"what": "same layer with fp32 spectra (the default spectrum_dtype): split (hi, lo) bf16 operands, fp32 accumulation, 1e-4 parity class",
+                               "us_per_layer": us3, "tokens_per_s": PREFILL_TOKENS / (us3 * 1e-6), "us_per_projection_shape": per3,
+                               "algorithmic_bytes_per_layer": alg3, "hbm_frac_of_measured_peak": alg3 / (us3 * 1e-6) / 1e9 / peak, "pipeline_status": status3}
+    except Exception as e:                                               # noqa: BLE001
+        out["fp32_spectra"] = {"error": "%s: %s" % (type(e).__name__, e)}
     torch.cuda.empty_cache()
     try:
         out["mlp_fusion"] = time_prefill_mlp(bc, _cabi, dev, reps)
