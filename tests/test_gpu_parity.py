@@ -420,3 +420,32 @@ def test_grouped_decode_tensor_core_kernel(B, shapes, reps, num_ctas, bias, dtyp
             assert not torch.isnan(y.float()).any()
             assert_close(y, O.bc_forward_torch(m.c.detach().cpu(), x.cpu(), None if m.bias is None else m.bias.detach().cpu()), 1e-2, dtype)
             assert_close(y, m(x), 1e-2, dtype)
+
+
+@pytest.mark.parametrize("sdt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,shapes,num_ctas", [(128, [(32, 16), (7, 3), (40, 8), (86, 32), (5, 1), (32, 86)], 9),
+                                                (64, [(64, 64), (9, 5), (33, 32), (16, 70)], None),
+                                                (256, [(16, 8), (12, 20), (5, 2), (32, 16)], 13)])
+def test_grouped_decode_split_q_kernel_two_rows_per_stage(monkeypatch, sdt, B, shapes, num_ctas):
+    """The warp-specialised split-q kernel (bcl_stream_ws.cu) puts TWO block-rows of a narrow segment (2 q <= blocks per stage) into one
+    ring stage and multiplies them with independent accumulators; 16-bit spectra use 16 KB stages (twice the blocks).  Forced for bf16
+    spectra too (BCL_GROUP_VARIANT=ws; the default there is the row-per-warp kernel).  Odd row counts, q not a multiple of the MAC
+    warps, segments cut in the middle of a row pair: every problem must match its per-module forward and the oracle."""
+    monkeypatch.setenv("BCL_GROUP_VARIANT", "ws")
+    g = torch.Generator().manual_seed(B + len(shapes))
+    layers, xs = [], []
+    for rep in range(3):
+        for (p, q) in shapes:
+            layers.append(make_layer(torch.randn(p, q, B, generator=g) * 0.02, None, sdt))
+            xs.append(torch.randn(1, q * B, generator=g).to(torch.float16).to(DEV))
+    kw = {} if num_ctas is None else {"num_ctas": num_ctas}
+    grp = bc.GroupedBCForward(xs, [m.build_spectrum() for m in layers], None, **kw)
+    ys = [y.clone() for y in grp.run()]
+    ys2 = grp.run()
+    torch.cuda.synchronize()
+    tol = 1e-4 if sdt == torch.float32 else 1e-2
+    with torch.no_grad():
+        for m, x, y, y2 in zip(layers, xs, ys, ys2):
+            assert torch.equal(y, y2)
+            assert_close(y, m(x), 1e-5, torch.float16)
+            assert_close(y, O.bc_forward_torch(m.c.detach().cpu(), x.cpu()), tol, torch.float16)
