@@ -61,6 +61,7 @@ struct WaveArgs {
     int chunk[3];            // consecutive items a CTA takes at a time
     int target[3];           // counter value of a complete tile: per_tile * epilogue warps
     long long* prof;         // profiling builds (make WAVE_PROF=1) only: per-role wait / busy cycles of the first 8 CTAs
+    int immediate;           // few tiles (latency-bound): publish every item as soon as its stores have completed
 };
 
 struct WaveBarriers {
@@ -467,7 +468,7 @@ prefill_wave_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     }
                 }
                 WPROF_END(3 + type, wp_b)
-                if (lane == 0) trk.commit(sig, type * a.m_tiles + m, groups);
+                if (lane == 0) { trk.commit(sig, type * a.m_tiles + m, groups); if (a.immediate) trk.flush(sig); }
             }
         }
         if (warp == 2 && lane == 0) { WPROF_DUMP(16) }
@@ -524,6 +525,8 @@ cudaError_t launch_prefill_wave(const ProblemDev& P, const Geometry& g, const vo
     if (ring >= a.m_tiles) ring = a.m_tiles;                 // everything fits: no slot is ever reused
     else if (ring < lag + 2) return cudaErrorInvalidValue;   // a reused slot must be consumed before its overwrite comes up in the order
     a.lag = lag; a.ring = ring;
+    a.immediate = env_int("BCL_WAVE_IMMEDIATE", 0);        // (measured at 256-2048 tokens: a hand-off costs 2.6-3.7 us -- bulk-store completion + the gpu-scope fence --
+                                                           //  as much as a kernel boundary under PDL: 32 us vs 27 us for the three launches at 256 tokens)
     a.prof = getenv("BCL_WAVE_PROF_PTR") ? reinterpret_cast<long long*>(strtoull(getenv("BCL_WAVE_PROF_PTR"), nullptr, 0)) : nullptr;
 
     CUtensorMap tmX, tmWf, tmXfS, tmXfL, tmC, tmYfS, tmYfL, tmWi, tmOut;
@@ -564,9 +567,9 @@ cudaError_t launch_prefill_wave(const ProblemDev& P, const Geometry& g, const vo
     while (stages > 2 && wave_smem_bytes(B, stages) > 227 * 1024) --stages;
     a.stages = stages;
     const size_t smem = wave_smem_bytes(B, stages);
-    int grid = ctas;
-    const int chunksA = (a.n_items[0] + a.chunk[0] - 1) / a.chunk[0];
-    if (grid > chunksA) grid = chunksA;
+    int grid = ctas, most = 0;
+    for (int t = 0; t < 3; ++t) { const int c = (a.n_items[t] + a.chunk[t] - 1) / a.chunk[t]; if (c > most) most = c; }
+    if (grid > most) grid = most;
     if (grid < 1) return cudaSuccess;
     cudaError_t e;
     if (B == 128) {
