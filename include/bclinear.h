@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BCL_ABI_VERSION 12
+#define BCL_ABI_VERSION 13
 
 typedef enum bcl_dtype { BCL_F32 = 0, BCL_F16 = 1, BCL_BF16 = 2 } bcl_dtype;
 
@@ -230,6 +230,13 @@ int bcl_forward_grouped_host_pipelined(const void* dev_plan, const void* host_pl
                                        void* host_y, const void* dev_y, size_t y_bytes,
                                        void* stream_in, void* stream_compute, void* stream_out,
                                        void* ev_in_done, void* ev_compute_done, void* ev_out_done, int slot_used_before);
+/* The same step on ONE stream, asynchronously: H2D(x) -> grouped launch -> D2H(y) are enqueued in order and the call returns at once
+ * (three API calls, no events).  With one stream per staging slot the steps of neighbouring slots overlap by themselves -- copy
+ * engines and SMs serve different streams concurrently -- which costs the host a third of the calls of the three-stream form.
+ * The caller synchronises the stream (or an event recorded on it) before it reads host_y or resubmits the slot's buffers. */
+int bcl_forward_grouped_host_async(const void* dev_plan, const void* host_plan, const void* host_x, void* dev_x, size_t x_bytes,
+                                   void* host_y, const void* dev_y, size_t y_bytes, void* stream);
+
 
 /* ---- gradients for calibration -----------------------------------------------------------------------------------
  * reference: torch autograd through BlockCirculantLinear.forward (src/patch_llama_fft.py:226-275), used by the KL

@@ -481,6 +481,18 @@ int bcl_forward_grouped_host_pipelined(const void* dev_plan, const void* host_pl
     return BCL_OK;
 }
 
+int bcl_forward_grouped_host_async(const void* dev_plan, const void* host_plan, const void* host_x, void* dev_x, size_t x_bytes,
+                                   void* host_y, const void* dev_y, size_t y_bytes, void* stream) {
+    if (!host_x || !dev_x || !host_y || !dev_y) return fail(BCL_ERR_ARG, "NULL host/device staging buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(dev_x, host_x, x_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D copy of x");
+    int rc = bcl_forward_grouped(dev_plan, host_plan, stream);
+    if (rc != BCL_OK) return rc;
+    if ((e = cudaMemcpyAsync(host_y, dev_y, y_bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H copy of y");
+    return BCL_OK;
+}
+
 int bcl_conj_transpose(const float* c, int p, int q, int B, float* ct, void* stream) {
     if (!valid_B(B)) return fail(BCL_ERR_BLOCK, "block size %d not supported (64, 128, 256)", B);
     if (p <= 0 || q <= 0) return fail(BCL_ERR_SHAPE, "bad shape p=%d q=%d", p, q);

@@ -127,6 +127,17 @@ class GroupedBCForward:
         _cabi.check(rc, "bcl_forward_grouped_host_pipelined")
         self._slot_used = True
 
+    def submit_host_stream(self, host_x: torch.Tensor, host_y: torch.Tensor, stream: "torch.cuda.Stream") -> None:
+        """One end-to-end step on `stream`, asynchronously (``bcl_forward_grouped_host_async``): H2D(x), the grouped launch and D2H(y) in
+        stream order; returns at once.  Give every staging slot its own stream and neighbouring steps overlap by themselves.
+        ``stream.synchronize()`` before reading host_y or resubmitting this group."""
+        with _cabi.on_device(self.device):
+            rc = _cabi.lib().bcl_forward_grouped_host_async(
+                self.dev_plan.data_ptr(), self.host_plan.data_ptr(),
+                host_x.data_ptr(), self.x_all.data_ptr(), self.x_all.numel() * self.x_all.element_size(),
+                host_y.data_ptr(), self.y_all.data_ptr(), self.y_all.numel() * self.y_all.element_size(), stream.cuda_stream)
+        _cabi.check(rc, "bcl_forward_grouped_host_async")
+
     def wait_host(self) -> None:
         """Block until this group's last submitted step has delivered host_y."""
         if getattr(self, "_slot_used", False):
