@@ -313,3 +313,31 @@ def test_fuse_mlp_prefill_path_in_a_tiny_llama(monkeypatch):
         bc.unfuse_mlp(model)
     assert P.prefill_status(DEV) == 0
     assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+
+
+def test_prefill_swiglu_stage_at_full_size():
+    """BASELINE configs[2] size (16384 tokens, Llama-2-7B MLP, B = 128): the fused SWIGLU stage against the unfused modules on 256 random
+    rows plus the tile edges, determinism, and linearity in x of the PRE-activation path via the down projection is not available here
+    (SWIGLU is not linear): instead gate == 0 rows must give exactly h == 0 (silu(0) * up)."""
+    hidden, inter, B, N, dtype = 4096, 11008, 128, 16384, torch.float16
+    g = torch.Generator().manual_seed(5)
+    cg = torch.randn(inter // B, hidden // B, B, generator=g) * 0.03
+    cu = torch.randn(inter // B, hidden // B, B, generator=g) * 0.03
+    x = torch.randn(N, hidden, generator=g).to(dtype)
+    x[777] = 0                                                      # a zero token: gate = up = 0 -> h = 0 exactly
+    xd = x.to(DEV)
+    p, q = 2 * (inter // B), hidden // B
+    spec = _gemm_spectrum(torch.cat([cg, cu], 0))
+    h = _forward_swiglu(xd, spec, p, q, B)
+    assert torch.equal(h, _forward_swiglu(xd, spec, p, q, B))
+    assert not torch.isnan(h.float()).any() and bool((h[777] == 0).all())
+    rows = torch.unique(torch.cat([torch.tensor([0, 127, 128, 8191, 8192, N - 1]), torch.randint(0, N, (256,), generator=g)]))
+    xr = xd[rows].contiguous()
+    gate = bc_forward(xr, _gemm_spectrum(cg), None, p // 2, q, B, layout=_cabi.LAYOUT_GEMM, spectrum_dtype=torch.bfloat16)
+    up = bc_forward(xr, _gemm_spectrum(cu), None, p // 2, q, B, layout=_cabi.LAYOUT_GEMM, spectrum_dtype=torch.bfloat16)
+    h_unfused = F.silu(gate) * up
+    diff = (h[rows].double() - h_unfused.double()).abs()
+    assert bool((diff <= 2 * G.ulp(dtype) * h_unfused.double().abs() + 1e-30).all()), f"max diff {diff.max().item():.3e}"
+    sub = rows[:24]
+    h_ref = F.silu(O.bc_forward_torch(cg, x[sub].float())) * O.bc_forward_torch(cu, x[sub].float())
+    assert_close(h[sub], h_ref, 2e-2, dtype, ulps=4)
