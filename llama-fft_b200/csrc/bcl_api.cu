@@ -278,7 +278,7 @@ int bcl_group_plan_encode_layout(const bcl_problem* problems, int count, int B, 
         if (P.N < 1 || P.N > 8) return fail(BCL_ERR_SHAPE, "grouped problems need 1 <= N <= 8 (problem %d has %lld)", g, (long long)P.N);
         if (P.N > maxN) maxN = P.N;
         if (P.q > qmax) qmax = P.q;
-        total_w += (int64_t)P.p * P.q;
+        total_w += (int64_t)P.p * P.q;                                  // (re-weighted below once the kernel variant is known)
     }
     int nt = 1; while (nt < maxN) nt *= 2;
     const char* force = getenv("BCL_GROUP_VARIANT");                 // "plain" | "ws": A/B switch for profiling only
@@ -315,23 +315,35 @@ int bcl_group_plan_encode_layout(const bcl_problem* problems, int count, int B, 
     // weight (q per row = bytes streamed) falls in [b, b+1) * total / num_ctas.
     int* cta_ptr = reinterpret_cast<int*>(base + H.off_cta_ptr);
     int* segs = reinterpret_cast<int*>(base + H.off_segs);
+    // Cost model of a CTA's share, in units of one spectrum block streamed from HBM: q blocks per row (+ `arow` per row, + `aseg` per
+    // problem start; BCL_PLAN_COST="arow,aseg").  Default: bytes only.  Measured on B200 (224 Llama-2-7B projections): per-CTA clock
+    // counts do correlate with rows and segments (+600 cycles per 4-row group and +2.1k per segment with bf16 spectra, the slowest CTA
+    // 15 % behind the median), but shifting bytes by those costs made the launch SLOWER (fp32 36.3 -> 37.6 us, bf16 29.3 -> 32.9 us):
+    // the launch is bound by the aggregate HBM stream, a CTA that finishes its bytes early leaves its bandwidth to the others, and the
+    // one with the most bytes finishes last whatever else it does.
+    int arow = 0, aseg = 0;
+    if (const char* pc = getenv("BCL_PLAN_COST")) { int a = 0, b = 0; if (sscanf(pc, "%d,%d", &a, &b) == 2 && a >= 0 && b >= 0) { arow = a; aseg = b; } }
+    total_w = 0;
+    for (int g = 0; g < count; ++g) total_w += (int64_t)problems[g].p * (problems[g].q + arow) + aseg;
     int nseg = 0, cta = 0;
     int64_t cum = 0;
     cta_ptr[0] = 0;
     for (int g = 0; g < count; ++g) {
         const int p = problems[g].p, q = problems[g].q;
+        const int wr = q + arow;                                     // weight of one row
         int j = 0;
+        cum += aseg;
         while (j < p) {
             // rows of this problem that still belong to the current CTA
             const int64_t limit = (total_w * (cta + 1) + num_ctas - 1) / num_ctas;   // ceil
             int64_t room = limit - cum;
-            int take = (int)((room + q - 1) / q);
+            int take = (int)((room + wr - 1) / wr);
             if (take < 1) take = 1;
             take = (take + gran - 1) / gran * gran;
             if (take > p - j) take = p - j;
             segs[4 * nseg + 0] = g; segs[4 * nseg + 1] = j; segs[4 * nseg + 2] = j + take; segs[4 * nseg + 3] = 0;
             ++nseg;
-            j += take; cum += (int64_t)take * q;
+            j += take; cum += (int64_t)take * wr;
             while (cta < num_ctas - 1 && cum >= (total_w * (cta + 1) + num_ctas - 1) / num_ctas) { ++cta; cta_ptr[cta] = nseg; }
         }
     }

@@ -72,10 +72,11 @@ def _decode(blob):
     return dict(count=count, num_ctas=num_ctas, num_segs=num_segs, nt=nt, qmax=qmax, variant=variant), cta_ptr, segs
 
 
-def test_group_plan_covers_every_row_once_and_balances_bytes():
+def test_group_plan_covers_every_row_once_and_balances_bytes(monkeypatch):
     # one Llama-2-7B decoder layer x 4: q,k,v,o (32x32), gate, up (86x32), down (32x86) at B=128
     layer = [(32, 32)] * 4 + [(86, 32)] * 2 + [(32, 86)]
     shapes = layer * 4
+    monkeypatch.delenv("BCL_PLAN_COST", raising=False)            # the default: bytes only
     rc, blob = _encode(shapes, 128, 296)
     assert rc == 0
     H, cta_ptr, segs = _decode(blob)
@@ -94,6 +95,29 @@ def test_group_plan_covers_every_row_once_and_balances_bytes():
     assert w.sum() == total
     assert w.max() <= total / H["num_ctas"] + 86 + 1          # within one row of the ideal share
 
+
+
+def test_group_plan_cost_model_override(monkeypatch):
+    """BCL_PLAN_COST="arow,aseg": a row weighs q + arow blocks and every problem start aseg blocks (an A/B switch: the default is bytes
+    only, which measured faster on B200, bcl_api.cu) -- CTAs with many short rows or many segments get fewer bytes.  Every row once."""
+    layer = [(32, 32)] * 4 + [(86, 32)] * 2 + [(32, 86)]
+    shapes = layer * 32
+    monkeypatch.setenv("BCL_PLAN_COST", "3,105")
+    rc, blob = _encode(shapes, 128, 148)
+    assert rc == 0
+    H, cta_ptr, segs = _decode(blob)
+    seen = {g: np.zeros(p, dtype=int) for g, (p, q) in enumerate(shapes)}
+    w, nbytes = np.zeros(H["num_ctas"]), np.zeros(H["num_ctas"])
+    for b in range(H["num_ctas"]):
+        for g, j0, j1, _ in segs[cta_ptr[b]:cta_ptr[b + 1]]:
+            seen[g][j0:j1] += 1
+            w[b] += (j1 - j0) * (shapes[g][1] + 3) + (105 if j0 == 0 else 0)
+            nbytes[b] += (j1 - j0) * shapes[g][1]
+    assert all((v == 1).all() for v in seen.values())
+    total = sum(p * (q + 3) + 105 for p, q in shapes)
+    assert abs(w.sum() - total) < 1e-6
+    assert w.max() <= total / H["num_ctas"] + (86 + 3) + 105 + 1   # within one row and one segment start of the ideal share
+    assert nbytes.max() > nbytes.min() * 1.05                      # ... and the bytes are no longer equal
 
 def test_group_plan_rejects_bad_requests():
     rc, _ = _encode([(4, 4)], 128, 8, N=9)
