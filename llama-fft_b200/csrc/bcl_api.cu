@@ -137,6 +137,21 @@ static int forward_impl(const void* x, int x_dtype, int64_t N, int64_t x_row_str
     if (layout == BCL_LAYOUT_STREAM) {
         if (spec_dtype != BCL_F32 && spec_dtype != BCL_BF16) return fail(BCL_ERR_DTYPE, "STREAM spectrum must be f32 or bf16");
         if (N > 65535LL * 8) return fail(BCL_ERR_SHAPE, "N=%lld exceeds the stream kernel's grid limit; split the batch", (long long)N);
+        // One token, one destination: the chain kernel with a single step -- the same split-q MAC, but the spectrum arrives through the
+        // TMA / mbarrier ring (1-D bulk copies that start before the wait on the previous grid) instead of ld.global.nc, and the work
+        // split needs no dependent global loads.  BCL_SINGLE_VIA_CHAIN=0: the plain kernel (A/B).
+        static const bool via_chain = !(getenv("BCL_SINGLE_VIA_CHAIN") && getenv("BCL_SINGLE_VIA_CHAIN")[0] == '0');
+        if (via_chain && N == 1 && n_dst == 1 && bcl::chain_supported(B, spec_dtype, q) && (long long)q * p * 1024 <= 0x7fffffffLL) {
+            bcl::ChainParams prm{};
+            prm.nsteps = 1; prm.nproblems = 1; prm.step_first[0] = 0; prm.step_first[1] = 1;
+            prm.prob[0] = P;
+            prm.counter = nullptr; prm.dbg = nullptr;
+            int dev = 0, sms = 0;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) {
+                cudaError_t e = bcl::launch_chain(prm, B, spec_dtype, q, p < sms ? p : sms, (cudaStream_t)stream);
+                return e == cudaSuccess ? BCL_OK : cuda_fail(e, "stream forward launch (chain kernel)");
+            }
+        }
         cudaError_t e = bcl::launch_stream_single(P, B, spec_dtype, (cudaStream_t)stream);
         return e == cudaSuccess ? BCL_OK : cuda_fail(e, "stream forward launch");
     }
