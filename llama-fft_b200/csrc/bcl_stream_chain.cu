@@ -178,14 +178,16 @@ __device__ __forceinline__ void chain_load_x(const ProblemDev& P, float* xs, con
     }
 }
 
-// Partial spectra part[slot][w][B] of `ng` row slots -> part[slot][0][B] holds the sum.  With several slots the NC warps share the work
-// (warp w: slot w % ng, every (NC / ng)-th partial), then ONE warp adds the few sub-sums; the summation order is fixed -> deterministic.
+// Partial spectra part[slot][w][B] of `ng` row slots -> part[slot][0][B] holds the sum.  The association order is the SAME however many
+// rows a CTA owns: e = ((p0 + p2) + p4) + p6, o = ((p1 + p3) + p5) + p7, sum = e + o -- so a row's bits do not depend on the grid or the
+// work split (a member of a shared-input group equals its own forward bit for bit, tests/test_gpu_shared_input.py).  With 2-4 slots
+// two warps per slot form e and o here (stage 1) and the finisher adds them; otherwise the finisher forms both itself.
 template <int B>
 __device__ __forceinline__ void sum_partials_stage1(float* part, int ng, int m, int lane) {
     using LM = LaneMap<B>;
     constexpr int CH = LM::CH, CW = LM::CW;
     if (ng < 2) return;
-    const int cnt = NC / ng;                                         // warps per slot (ng = 2: 4, 3: 2, 4: 2, 5..8: 1)
+    const int cnt = NC / ng >= 2 ? 2 : 1;                            // warps per slot: one for the even partials, one for the odd ones
     if (cnt < 2 || m >= cnt * ng) return;
     const int slot = m % ng, r = m / ng;
     float* base = part + (size_t)slot * NC * B;
@@ -216,28 +218,36 @@ __device__ __forceinline__ void finish_slots(const ProblemDev& P, int u0, int sl
     using LM = LaneMap<B>;
     using C = FftCfg<B>;
     constexpr int CH = LM::CH, CW = LM::CW;
-    const int cnt = (nslots >= 2 && NC / nslots >= 2) ? NC / nslots : NC;   // sub-sums left by stage 1 (all NC partials if it did not run)
-    const int nsum = (cnt == NC) ? NC : cnt;
+    const bool staged = nslots >= 2 && NC / nslots >= 2;             // stage 1 left e in partial 0 and o in partial 1
     for (int k = 0; k < nslots; ++k) {
         float* slot = part + (size_t)k * NC * B;
-        float sum[CH][CW];
+        float se[CH][CW], so[CH][CW];
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-            for (int e = 0; e < CW; ++e) sum[ch][e] = 0.f;
-        for (int w = 0; w < nsum; ++w) {
+            for (int e = 0; e < CW; ++e) { se[ch][e] = 0.f; so[ch][e] = 0.f; }
+        const int nper = staged ? 1 : NC / 2;                        // partials per parity to add
+        const int stride = staged ? 1 : 2;
+        for (int w = 0; w < nper; ++w) {
 #pragma unroll
             for (int ch = 0; ch < CH; ++ch) {
-                const float* src = slot + (size_t)w * B + LM::offset(lane, ch);
-                if constexpr (CW == 4) { float4 v = *reinterpret_cast<const float4*>(src); sum[ch][0] += v.x; sum[ch][1] += v.y; sum[ch][2] += v.z; sum[ch][3] += v.w; }
-                else { float2 v = *reinterpret_cast<const float2*>(src); sum[ch][0] += v.x; sum[ch][1] += v.y; }
+                const float* s0p = slot + (size_t)(stride * w) * B + LM::offset(lane, ch);
+                const float* s1p = slot + (size_t)(stride * w + 1) * B + LM::offset(lane, ch);
+                if constexpr (CW == 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(s0p), u = *reinterpret_cast<const float4*>(s1p);
+                    se[ch][0] += v.x; se[ch][1] += v.y; se[ch][2] += v.z; se[ch][3] += v.w;
+                    so[ch][0] += u.x; so[ch][1] += u.y; so[ch][2] += u.z; so[ch][3] += u.w;
+                } else {
+                    const float2 v = *reinterpret_cast<const float2*>(s0p), u = *reinterpret_cast<const float2*>(s1p);
+                    se[ch][0] += v.x; se[ch][1] += v.y; so[ch][0] += u.x; so[ch][1] += u.y;
+                }
             }
         }
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) {
             float* dst = slot + LM::offset(lane, ch);
-            if constexpr (CW == 4) *reinterpret_cast<float4*>(dst) = make_float4(sum[ch][0], sum[ch][1], sum[ch][2], sum[ch][3]);
-            else *reinterpret_cast<float2*>(dst) = make_float2(sum[ch][0], sum[ch][1]);
+            if constexpr (CW == 4) *reinterpret_cast<float4*>(dst) = make_float4(se[ch][0] + so[ch][0], se[ch][1] + so[ch][1], se[ch][2] + so[ch][2], se[ch][3] + so[ch][3]);
+            else *reinterpret_cast<float2*>(dst) = make_float2(se[ch][0] + so[ch][0], se[ch][1] + so[ch][1]);
         }
     }
     __syncwarp();
