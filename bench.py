@@ -143,7 +143,7 @@ class ClockSampler:
 # CPU reference arm / cpu_baseline: the reference's own CPU path (torch.fft.rfft -> einsum -> irfft), restated in
 # oracle/bc_oracle.py (bit-identical to the reference on the golden vectors), spectra cached like its perf runs.
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(steps, warmup, budget_s=None):
+def cpu_reference_steps(steps, warmup, budget_s=None, cached=True):
     """One decode token through all 224 projections on the host cores, the way the reference's perf runs do it: its own
     BlockCirculantLinear (src/patch_llama_fft.py:142-275) with enable_cfft_cache (src/bench_all_in_one.py:164-254), fp32, batch 1.
     The modules are the UNMODIFIED reference imported from oracle/_ref/ (kind "reference"; staged by oracle/make_ref.py); without it
@@ -166,7 +166,8 @@ def cpu_reference_steps(steps, warmup, budget_s=None):
                     m.c.copy_(torch.randn(outf // B, inf // B, B, generator=g) * 0.01)
                 holder.append(m)
         holder.eval()
-        bai.enable_cfft_cache(holder)
+        if cached:
+            bai.enable_cfft_cache(holder)                     # else: the forward as shipped, rfft(c) on every call (src/patch_llama_fft.py:256-257)
         mods = [(m, torch.randn(1, 1, m.in_features, generator=g)) for m in holder]
         call = lambda m, x: m(x)                                                        # noqa: E731
     else:
@@ -432,6 +433,10 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         sec, cores, done, kind = cpu_reference_steps(50, 1, budget_s=15.0)
         cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": kind, "sample": CPU_SAMPLE % (done, CPU_KIND_TEXT[kind])}
+        if kind == "reference":                               # also the forward as shipped (no spectrum cache), a few passes
+            sec_u, _, done_u, _ = cpu_reference_steps(8, 1, budget_s=6.0, cached=False)
+            cpu["value_as_shipped_uncached"] = 1.0 / sec_u
+            cpu["sample_as_shipped"] = "%d timed passes, rfft(c) recomputed by every forward (src/patch_llama_fft.py:256-257)" % done_u
     line = {"metric": METRIC, "value": world * 1.0 / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config(world, args.spectrum),
