@@ -403,6 +403,10 @@ def run_ours(args):
     if world == 1 and not args.no_detail:
         detail = launch_granularity_detail(bc, _cabi, groups[0], shapes, dev, args)
         try:
+            detail["decode_independent_launches"] = independent_launch_detail(bc, groups, dev, shapes, algorithmic_bytes(args.spectrum)[0])
+        except Exception as e:                                           # noqa: BLE001
+            detail["decode_independent_launches"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        try:
             detail["decode_bf16_spectra"] = bf16_decode_detail(bc, _cabi, dev, shapes, args)
         except Exception as e:                      # noqa: BLE001
             detail["decode_bf16_spectra"] = {"error": "%s: %s" % (type(e).__name__, e)}
@@ -557,6 +561,38 @@ def bf16_decode_detail(bc, _cabi, dev, shapes, args, steps=1000):
     torch.cuda.empty_cache()
     return {"ms_per_step": ms, "tokens_per_s": 1.0 / (ms * 1e-3), "algorithmic_bytes_per_launch": alg, "hbm_frac_of_measured_peak": alg / (ms * 1e-3) / 1e9 / peak,
             "note": "row-per-warp kernel (bcl_stream_rw.cu): with 8 KB rows the split-q kernel of the headline is bound by its per-row hand-offs, not by HBM; profiles/r1_prefill_notes.md"}
+
+
+def independent_launch_detail(bc, groups, dev, shapes, alg, steps=2000):
+    """Where the headline's last ~10 % go.  Every launch of the headline calls griddepcontrol.wait before it touches activations (the
+    previous launch may have produced them), so step k+1 computes only after the SLOWEST CTA of step k has finished.  The bench's
+    steps do not depend on each other (two alternating buffer sets); plans encoded with BCL_GROUP_INDEPENDENT=1 skip the wait, an SM
+    starts the next step the moment its CTA leaves, and the same kernel runs at the rate its stream sustains.  A measurement switch:
+    a decoder's consecutive tokens DO depend on each other, so the headline keeps the wait."""
+    import torch
+    os.environ["BCL_GROUP_INDEPENDENT"] = "1"
+    try:
+        ind = [bc.GroupedBCForward.from_packed(shapes, grp.specs, 1, torch.float16, dev, num_ctas=grp.num_ctas) for grp in groups]
+    finally:
+        os.environ.pop("BCL_GROUP_INDEPENDENT", None)
+    for g2, g1 in zip(ind, groups):
+        g2.x_all.copy_(g1.x_all)
+    for i in range(20):
+        ind[i % len(ind)].run()
+    torch.cuda.synchronize()
+    same = all(bool(torch.equal(g2.y_all, g1.y_all)) for g2, g1 in zip(ind, groups))
+    stream = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        ind[i % len(ind)].run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak, _ = peaks()
+    return {"what": "the headline launches without griddepcontrol.wait (BCL_GROUP_INDEPENDENT=1 plans): consecutive steps overlap on the SMs",
+            "ms_per_step": ms, "tokens_per_s": 1.0 / (ms * 1e-3), "hbm_frac_of_measured_peak": alg / (ms * 1e-3) / 1e9 / peak,
+            "outputs_bit_identical_to_headline": same}
 
 
 def dependent_chain_detail(bc, _cabi, dev, time_graph):

@@ -314,6 +314,7 @@ int bcl_group_plan_encode_layout(const bcl_problem* problems, int count, int B, 
     memset(base, 0, need);
     bcl::GroupPlanHeader H{};
     H.magic = bcl::kPlanMagic; H.count = count; H.num_ctas = num_ctas; H.B = B; H.spec_dtype = spec_dtype; H.nt = nt; H.qmax = qmax; H.variant = variant;
+    H.reserved = (getenv("BCL_GROUP_INDEPENDENT") && getenv("BCL_GROUP_INDEPENDENT")[0] == '1') ? 1 : 0;
     size_t off = sizeof(bcl::GroupPlanHeader);
     off = (off + 15) & ~(size_t)15; H.off_problems = off; off += (size_t)count * sizeof(bcl::ProblemDev);
     off = (off + 15) & ~(size_t)15; H.off_cta_ptr = off; off += ((size_t)num_ctas + 1) * sizeof(int);

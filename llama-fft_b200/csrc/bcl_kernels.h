@@ -46,7 +46,8 @@ struct GroupPlanHeader {
     int32_t B, spec_dtype, nt, qmax;
     int32_t variant;      // 0 = plain CTA-cooperative kernel, 1 = warp-specialised TMA pipeline (one CTA per SM), 2 = its row-per-warp form (bf16 spectra),
                           // 3 = tensor-core MAC over BCL_LAYOUT_DECODE_TC spectra (bcl_stream_tc.cu)
-    int32_t reserved;
+    int32_t reserved;     // plan flags.  bit 0 (BCL_GROUP_INDEPENDENT=1 at encode time, a measurement switch): the launch neither reads what the
+                          // previous launch of the stream wrote nor overwrites what it still reads, so it skips griddepcontrol.wait
     uint64_t off_problems, off_cta_ptr, off_segs, total_bytes;
 };
 constexpr uint32_t kPlanMagic = 0x474c4342u;

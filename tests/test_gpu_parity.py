@@ -449,3 +449,27 @@ def test_grouped_decode_split_q_kernel_two_rows_per_stage(monkeypatch, sdt, B, s
             assert torch.equal(y, y2)
             assert_close(y, m(x), 1e-5, torch.float16)
             assert_close(y, O.bc_forward_torch(m.c.detach().cpu(), x.cpu()), tol, torch.float16)
+
+
+def test_grouped_plans_marked_independent_skip_the_dependency_wait(monkeypatch):
+    """BCL_GROUP_INDEPENDENT=1 at plan-encode time: launches of the plan do not wait for the previous launch of the stream
+    (griddepcontrol.wait skipped), so consecutive launches that use DIFFERENT buffers overlap on the SMs.  Two alternating groups,
+    many launches back to back: every output must stay bit-identical to the ordinary plans' and to the per-module forward."""
+    g = torch.Generator().manual_seed(99)
+    shapes = [(32, 32)] * 4 + [(86, 32)] * 2 + [(32, 86)]
+    B = 128
+    layers = [make_layer(torch.randn(p, q, B, generator=g) * 0.01, None) for _ in range(2) for (p, q) in shapes]
+    xs = [torch.randn(1, q * B, generator=g).to(torch.float16).to(DEV) for _ in range(2) for (p, q) in shapes]
+    specs = [m.build_spectrum() for m in layers]
+    n = len(shapes)
+    ref = [bc.GroupedBCForward(xs[k * n:(k + 1) * n], specs[k * n:(k + 1) * n]) for k in range(2)]
+    ref_out = [[y.clone() for y in grp.run()] for grp in ref]
+    monkeypatch.setenv("BCL_GROUP_INDEPENDENT", "1")
+    ind = [bc.GroupedBCForward(xs[k * n:(k + 1) * n], specs[k * n:(k + 1) * n]) for k in range(2)]
+    monkeypatch.delenv("BCL_GROUP_INDEPENDENT")
+    for i in range(200):
+        ind[i & 1].run()
+    torch.cuda.synchronize()
+    for k in range(2):
+        for y, yr in zip(ind[k].ys, ref_out[k]):
+            assert torch.equal(y, yr)
