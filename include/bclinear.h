@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BCL_ABI_VERSION 13
+#define BCL_ABI_VERSION 14
 
 typedef enum bcl_dtype { BCL_F32 = 0, BCL_F16 = 1, BCL_BF16 = 2 } bcl_dtype;
 
@@ -173,6 +173,16 @@ typedef struct bcl_problem {
 #define BCL_X_SPECTRUM 3    /* x_dtype of a chain problem whose x is a (q, B) fp32 packed spectrum; y_dtype then names the activation dtype */
 
 size_t bcl_group_plan_bytes(int count, int num_ctas);
+/* Bytes of a plan with room for the DYNAMIC TAIL of the fp32 decode kernel (>= bcl_group_plan_bytes; size host_plan and dev_plan
+ * with it).  An opt-in experiment (BCL_GROUP_DYNAMIC="percent[,rows]" at encode time; default off = every row in a static share):
+ * equal-byte shares of 148 CTAs finish up to ~6 us apart on B200 and a dependent next launch waits for the slowest, so the encoder
+ * can leave the last `percent` of the spectrum bytes unassigned: the CTAs draw them in `rows`-row items from a ticket counter in the
+ * DEVICE copy of the plan, and rfft(x) of the problems those items belong to (src/patch_llama_fft.py:252) is computed once per launch
+ * into a cache behind the plan.  Which CTA computes a row does not change a bit of it (tests), but the tail measured SLOWER than the
+ * static plan, hence off.  With it the device copy holds a few words the kernel writes (left zero / monotonic after
+ * every launch): launches of ONE plan must then be stream-ordered, not concurrent -- they write the same y anyway.  A buffer sized
+ * by bcl_group_plan_bytes alone gets a plan without the tail whatever the environment says. */
+size_t bcl_group_plan_bytes_for(const bcl_problem* problems, int count, int B, int spec_dtype, int num_ctas);
 /* num_ctas: how many CTAs to partition over (e.g. 2 * SM count); returns BCL_OK and fills host_plan. */
 int bcl_group_plan_encode(const bcl_problem* problems, int count, int B, int spec_dtype, int num_ctas,
                           void* host_plan, size_t host_plan_bytes);

@@ -10,7 +10,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BCL_LIB_PATH") or os.path.join(_HERE, "libbclinear.so")   # override: A/B builds when profiling
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 F32, F16, BF16 = 0, 1, 2
 LAYOUT_STREAM, LAYOUT_GEMM, LAYOUT_DECODE_TC = 0, 1, 2
 EPILOGUE_LINEAR, EPILOGUE_SWIGLU, EPILOGUE_EMIT_SPECTRUM = 0, 1, 2
@@ -25,7 +25,7 @@ SYMBOLS = (
     "bcl_forward", "bcl_group_plan_bytes", "bcl_group_plan_encode", "bcl_forward_grouped", "bcl_forward_host", "bcl_forward_grouped_host", "bcl_forward_grouped_host_pipelined",
     "bcl_project_from_dense",
     "bcl_forward_bcast", "bcl_conj_transpose", "bcl_backward_workspace_bytes", "bcl_backward_weights", "bcl_prefill_geometry", "bcl_prefill_rfft", "bcl_prefill_gemm", "bcl_prefill_irfft",
-    "bcl_launch_noop", "bcl_forward_chain", "bcl_push_columns", "bcl_forward_swiglu", "bcl_group_plan_encode_layout", "bcl_forward_grouped_host_async",
+    "bcl_launch_noop", "bcl_forward_chain", "bcl_push_columns", "bcl_forward_swiglu", "bcl_group_plan_encode_layout", "bcl_forward_grouped_host_async", "bcl_group_plan_bytes_for",
 )
 
 
@@ -72,6 +72,8 @@ def lib() -> ctypes.CDLL:
     L.bcl_backward_weights.argtypes = [vp, i32, i64, vp, i32, i64, i64, i32, i32, i32, vp, i32, vp, sz, vp]
     L.bcl_group_plan_bytes.restype = sz
     L.bcl_group_plan_bytes.argtypes = [i32, i32]
+    L.bcl_group_plan_bytes_for.restype = sz
+    L.bcl_group_plan_bytes_for.argtypes = [ctypes.POINTER(Problem), i32, i32, i32, i32]
     L.bcl_group_plan_encode.argtypes = [ctypes.POINTER(Problem), i32, i32, i32, i32, vp, sz]
     L.bcl_group_plan_encode_layout.argtypes = [ctypes.POINTER(Problem), i32, i32, i32, i32, i32, vp, sz]
     L.bcl_forward_grouped.argtypes = [vp, vp, vp]

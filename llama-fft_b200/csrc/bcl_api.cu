@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstdarg>
 #include <vector>
+#include <algorithm>
 #include "bcl_common.cuh"
 #include "bcl_kernels.h"
 #include "bcl_gemm.cuh"
@@ -260,15 +261,67 @@ int bcl_prefill_irfft(const void* Yf, int64_t N, int p, int q, int B, const void
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "prefill irfft launch");
 }
 
+static constexpr int kMaxDynPerCta = 16;      // cap of dynamic-tail items per CTA (plan size)
+
 size_t bcl_group_plan_bytes(int count, int num_ctas) {
     if (count <= 0 || num_ctas <= 0) return 0;
-    // segments: every CTA boundary and every problem boundary can start one
-    size_t segs = (size_t)count + (size_t)num_ctas;
+    // segments: every CTA boundary and every problem boundary can start one; plus the items of the dynamic tail and its two counters
+    size_t segs = (size_t)count + (size_t)num_ctas + 2 * (size_t)kMaxDynPerCta * (size_t)num_ctas;      // (an item is 32 bytes)
     size_t b = sizeof(bcl::GroupPlanHeader);
     b = (b + 15) & ~(size_t)15; b += (size_t)count * sizeof(bcl::ProblemDev);
     b = (b + 15) & ~(size_t)15; b += ((size_t)num_ctas + 1) * sizeof(int);
     b = (b + 15) & ~(size_t)15; b += segs * 16;
+    b = (b + 15) & ~(size_t)15; b += 16 + 8 * (size_t)count;          // launch counters, ready marks and problem indices of the tail
     return (b + 255) & ~(size_t)255;
+}
+
+static int device_sms() {                                               // the dynamic tail needs every CTA of the grid resident at once
+    static const int sms = [] { int dev = 0, n = 0; if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; } return n; }();
+    return sms;
+}
+
+// Dynamic tail of a grouped plan (see bcl_group_plan_encode_layout): which rows [pstat[g], p) of which problems are cut into items.
+// A pure function of the shapes, shared by the encoder and by bcl_group_plan_bytes_for.
+struct DynTail { int pct = 0, rows = 4, items = 0, K = 0, xstride = 0; std::vector<int> order, pstat; };
+static DynTail select_dyn_tail(const bcl_problem* problems, int count, int B, int num_ctas, bool eligible, int arow) {
+    DynTail t;
+    t.order.resize(count); t.pstat.resize(count);
+    int64_t total_rows = 0, total_w = 0;
+    for (int g = 0; g < count; ++g) { t.order[g] = g; t.pstat[g] = problems[g].p; total_rows += problems[g].p; total_w += (int64_t)problems[g].p * (problems[g].q + arow); }
+    int pct = 0, rows = 4;                                          // off unless requested: measured slower than the static plan (see the encoder)
+    if (const char* dc = getenv("BCL_GROUP_DYNAMIC")) { int a = 0, b = 4; int n = sscanf(dc, "%d,%d", &a, &b); if (n >= 1 && a >= 0 && a <= 90) pct = a; if (n == 2 && b >= 1 && b <= 64) rows = b; }
+    if (!eligible || num_ctas > device_sms() || total_rows < (int64_t)4 * num_ctas) pct = 0;
+    if (pct == 0) return t;
+    std::stable_sort(t.order.begin(), t.order.end(), [&](int a, int b) { return problems[a].q > problems[b].q; });
+    for (;;) {
+        for (int g = 0; g < count; ++g) t.pstat[g] = problems[g].p;
+        int64_t want = total_w * pct / 100;
+        t.items = 0; t.K = 0; int qm = 0;
+        for (int o = count - 1; o >= 0 && want > 0; --o) {
+            const int g = t.order[o], p = problems[g].p, wr = problems[g].q + arow;
+            int take = (int)std::min<int64_t>(p, (want + wr - 1) / wr);
+            take = std::min(p, (take + rows - 1) / rows * rows);
+            t.pstat[g] = p - take;
+            want -= (int64_t)take * wr;
+            t.items += (take + rows - 1) / rows;
+            ++t.K; qm = std::max(qm, problems[g].q);
+        }
+        t.xstride = qm * B;
+        if (t.items <= kMaxDynPerCta * num_ctas) break;
+        rows *= 2;
+    }
+    t.pct = pct; t.rows = rows;
+    return t;
+}
+
+size_t bcl_group_plan_bytes_for(const bcl_problem* problems, int count, int B, int spec_dtype, int num_ctas) {
+    size_t b = bcl_group_plan_bytes(count, num_ctas);
+    if (!b || !problems || !valid_B(B)) return b;
+    int qmax = 0;
+    for (int g = 0; g < count; ++g) { if (problems[g].N != 1 || problems[g].p <= 0 || problems[g].q <= 0) return b; qmax = std::max(qmax, problems[g].q); }
+    const bool eligible = bcl::stream_ws_supported(B, spec_dtype, 1, qmax) && !bcl::stream_rw_supported(B, spec_dtype, 1, qmax);
+    const DynTail t = select_dyn_tail(problems, count, B, num_ctas, eligible, 0);
+    return b + (size_t)t.K * t.xstride * sizeof(float);
 }
 
 int bcl_group_plan_encode(const bcl_problem* problems, int count, int B, int spec_dtype, int num_ctas,
@@ -341,14 +394,33 @@ int bcl_group_plan_encode_layout(const bcl_problem* problems, int count, int B, 
     if (const char* pc = getenv("BCL_PLAN_COST")) { int a = 0, b = 0; if (sscanf(pc, "%d,%d", &a, &b) == 2 && a >= 0 && b >= 0) { arow = a; aseg = b; } }
     total_w = 0;
     for (int g = 0; g < count; ++g) total_w += (int64_t)problems[g].p * (problems[g].q + arow) + aseg;
+    // Dynamic tail (the warp-specialised fp32 kernel; BCL_GROUP_DYNAMIC="percent[,rows]", 0 = off): equal-byte shares finish up to
+    // ~6 us apart on B200 (the HBM system does not serve 148 streams evenly, and differently every launch), and a dependent next launch
+    // waits for the slowest.  So the last `percent` of the weight is not assigned: it is cut into items of `rows` block-rows that the
+    // CTAs draw from a ticket counter once their static share is streamed.  Every item costs its CTA an rfft of the problem's input, so
+    // the problems are walked widest input first and the tail is taken from the narrow ones.
+    // Every item switches its CTA to another problem; the rfft of that problem's input is computed once per launch into a cache behind
+    // the plan (bcl_stream_ws.cu), so the device plan must have room for it: size the buffers with bcl_group_plan_bytes_for.  A buffer
+    // sized by bcl_group_plan_bytes alone gets a plan without the tail (every row in a static share).
+    DynTail dt = select_dyn_tail(problems, count, B, num_ctas, variant == 1 && maxN == 1 && !(H.reserved & 1) && aseg == 0, arow);
+    if (dt.pct > 0 && host_plan_bytes < need + (size_t)dt.K * dt.xstride * sizeof(float))
+        dt = select_dyn_tail(problems, count, B, num_ctas, false, arow);
+    const std::vector<int>& order = dt.order;
+    const std::vector<int>& pstat = dt.pstat;
+    const int dyn_pct = dt.pct, dyn_rows = dt.rows;
+    if (dyn_pct > 0) {
+        total_w = 0;
+        for (int g = 0; g < count; ++g) total_w += (int64_t)pstat[g] * (problems[g].q + arow);
+    }
     int nseg = 0, cta = 0;
     int64_t cum = 0;
     cta_ptr[0] = 0;
-    for (int g = 0; g < count; ++g) {
-        const int p = problems[g].p, q = problems[g].q;
+    for (int o = 0; o < count; ++o) {
+        const int g = order[o];
+        const int p = pstat[g], q = problems[g].q;
         const int wr = q + arow;                                     // weight of one row
         int j = 0;
-        cum += aseg;
+        if (p) cum += aseg;
         while (j < p) {
             // rows of this problem that still belong to the current CTA
             const int64_t limit = (total_w * (cta + 1) + num_ctas - 1) / num_ctas;   // ceil
@@ -365,6 +437,24 @@ int bcl_group_plan_encode_layout(const bcl_problem* problems, int count, int B, 
     }
     while (cta < num_ctas) { ++cta; cta_ptr[cta] = nseg; }
     H.num_segs = nseg;
+    int nd = 0, K = 0;
+    off = H.off_segs + (size_t)(nseg + 2 * dt.items) * 16;
+    off = (off + 15) & ~(size_t)15; H.off_ctr = off;                 // counters: zero here; the kernel leaves them zero after every launch
+    int* pool_g = reinterpret_cast<int*>(base + H.off_ctr) + 4 + dt.K;
+    for (int o = 0; o < count && dyn_pct > 0; ++o) {                 // the tail's items, in the order the tickets hand them out
+        const int g = order[o];
+        if (pstat[g] == problems[g].p) continue;
+        for (int j = pstat[g]; j < problems[g].p; j += dyn_rows, ++nd) {
+            int* it = segs + 4 * nseg + 8 * nd;                      // bcl::ws::DynItem: g, j0, j1, pool index, q, pad, spectrum row j0
+            it[0] = g; it[1] = j; it[2] = std::min(problems[g].p, j + dyn_rows); it[3] = K; it[4] = problems[g].q; it[5] = 0;
+            const unsigned char* rowp = reinterpret_cast<const unsigned char*>(problems[g].spec) + (size_t)j * problems[g].q * B * (spec_dtype == BCL_F32 ? 4 : 2);
+            memcpy(it + 6, &rowp, 8);
+        }
+        pool_g[K++] = g;
+    }
+    H.num_dyn = nd; H.dyn_rows = dyn_rows; H.dyn_problems = K; H.dyn_xstride = dt.xstride;
+    H.off_xcache = need;                                             // behind everything bcl_group_plan_bytes counts (256-byte aligned)
+    H.total_bytes = need + (size_t)K * dt.xstride * sizeof(float);
     memcpy(base, &H, sizeof(H));
     return BCL_OK;
 }

@@ -49,6 +49,13 @@ struct GroupPlanHeader {
     int32_t reserved;     // plan flags.  bit 0 (BCL_GROUP_INDEPENDENT=1 at encode time, a measurement switch): the launch neither reads what the
                           // previous launch of the stream wrote nor overwrites what it still reads, so it skips griddepcontrol.wait
     uint64_t off_problems, off_cta_ptr, off_segs, total_bytes;
+    int32_t num_dyn;      // dynamic tail (variant 1): items segs[num_segs .. num_segs + num_dyn) that the CTAs draw from a ticket counter
+    int32_t dyn_rows;     // block-rows per item
+    uint64_t off_ctr;     // launch scratch in the DEVICE copy of the plan (ints): ticket counter, CTAs done (both zero between launches), launch
+                          // sequence number, pad, dyn_problems ready marks, then (constant) the dyn_problems problem indices
+    int32_t dyn_problems; // problems that own items of the tail
+    int32_t dyn_xstride;  // floats between their cached input spectra
+    uint64_t off_xcache;  // [dyn_problems][dyn_xstride] floats in the device copy: rfft(x) of the tail's problems, computed once per launch
 };
 constexpr uint32_t kPlanMagic = 0x474c4342u;
 

@@ -76,6 +76,13 @@ __device__ inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t b
 __device__ inline void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ inline void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+#ifdef BCL_WS_TRACE
+// Per-CTA timeline of three launches in steady state (launch 200-202 of the process): %globaltimer at CTA start, at the release of
+// griddepcontrol.wait and at the end of each finisher; read by tools/ws_trace.py.
+__device__ int g_trace_count[1024];
+__device__ inline unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ inline int smid() { int v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+#endif
 #ifdef BCL_WS_TIMING
 __device__ inline long long clk() { long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c)); return c; }
 #define TSTART(v) long long v##_t0 = clk()
@@ -101,13 +108,50 @@ struct Barriers {
     uint64_t gempty[NF];            // group buffer drained by its finisher (1 arrival)
     uint64_t xfull[2];              // x spectrum of a segment ready in shared memory     (NX arrivals; slot 0 used)
     uint64_t xempty[2];             // every MAC warp copied its slice into registers      (NM arrivals)
+    int dq_n;                       // dynamic items published by the producer so far (release / acquire)
 };
+// Dynamic tail (round 2): the last part of a plan's rows is not assigned to CTAs but cut into small items that the producers draw from
+// a ticket counter in the device plan, so a CTA that finishes its static share early takes more of them and all CTAs end together
+// (per-CTA finish times of equal-byte static shares spread over ~6 us: the HBM system does not serve 148 streams evenly).  The producer
+// thread publishes every item it draws in a small shared-memory queue that the other roles follow; g < 0 ends the CTA.
+// Every item switches its CTA to another problem, and an rfft of that problem's input per item (~3 us on the four X warps) would cost
+// more than the item's stream (4 rows ~1.8 us).  So the input spectrum of every problem of the tail is computed ONCE per launch -- by
+// the X warps of CTA (pool index mod grid), right after start-up, when they are idle -- into a cache in the device plan, marked ready
+// with the launch sequence number; an item's CTA copies it from L2 instead (16 KB, one round of loads).
+// An item carries everything its CTA's producer needs (one load, issued one item ahead: the chain ticket -> item -> problem table would
+// otherwise stall the producer for two L2 round trips per item, longer than the ring covers).
+struct DynItem { int g, j0, j1, pi; int q, pad; const void* rowp; };       // pi: pool index of the problem; rowp: spectrum row j0
+static_assert(sizeof(DynItem) == 32, "DynItem is two 16-byte loads");
+struct DynArgs {
+    const DynItem* items;           // [n]
+    int n;                          // 0: no dynamic tail
+    int K;                          // problems in the tail
+    int* ctr;                       // [0] ticket counter, [1] CTAs done, [2] launch sequence number, [4 + pi] ready marks
+    const int* pool_g;              // [K] problem index
+    float* xcache;                  // [K][xstride] packed input spectra
+    int xstride;                    // floats
+};
+__device__ inline int ld_acquire_gpu(const int* p) { int v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ inline void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+constexpr int DQ = 32;              // queue slots: > ring stages + group buffers + 2 items can be in flight between producer and finishers
+constexpr int HEADER_BYTES = 1536;  // Barriers (512) + queue (DQ * 32)
+__device__ inline void st_release_shared(int* p, int v) { asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
+__device__ inline int ld_acquire_shared(const int* p) { int v; asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory"); return v; }
 
 // RS = ring stages per block-row = ceil(qmax / CB), KX = x blocks per MAC warp (>= ceil(qmax / NM)): compile-time so that each MAC
 // warp's slice of the x spectrum (KX blocks) can live in registers and the per-stage multiply is straight-line code.
-template <int B, typename SpecT, int RS, int KX>
+// rfft(x) of a problem by the NX x-spectrum warps, out of line: the dynamic-tail kernel calls it from two places, and a third inlined
+// copy of the transform pushes the kernel past what the instruction cache holds.
+template <int B>
+__device__ __noinline__ void x_warps_rfft(const ProblemDev* P, float* dst, const float2* tw, float2* fscr, int lane, int xw) {
+    load_x_spectrum<B, 1, NX>(*P, 0, dst, tw, fscr, lane, xw);
+}
+
+// DYN: the plan has a dynamic tail.  A separate instantiation, so that plans without one run exactly the code they ran before (the
+// tail's paths make the kernel 60 % larger, and measurably slower even when they are never taken).
+template <int B, typename SpecT, int RS, int KX, bool DYN>
 __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev* __restrict__ problems, const int* __restrict__ cta_seg_ptr,
-                                                              const SegWork* __restrict__ segs, int S, int qmax, int dbg) {
+                                                              const SegWork* __restrict__ segs, int S, int qmax, int dbg, const DynArgs dyn) {
     using LM = LaneMap<B>;
     using FC = FftCfg<B>;
     constexpr int NT = 1;
@@ -123,8 +167,9 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Barriers* bars = reinterpret_cast<Barriers*>(smem_raw);
-    float2* tw = reinterpret_cast<float2*>(smem_raw + 512);
-    unsigned char* ring = smem_raw + 512 + 1024;                     // tw needs B/2*8 <= 1024 bytes
+    int4* dq = reinterpret_cast<int4*>(smem_raw + 512);
+    float2* tw = reinterpret_cast<float2*>(smem_raw + HEADER_BYTES);
+    unsigned char* ring = smem_raw + HEADER_BYTES + 1024;            // tw needs B/2*8 <= 1024 bytes
     float* part = reinterpret_cast<float*>(ring + (size_t)S * STAGE_BYTES);                         // [NF][PAIRS][NM][B]
     float2* fscr_all = reinterpret_cast<float2*>(part + NF * PAIRS * NM * B);                       // FFT scratch of the NX + NF warps
     float* xs = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(fscr_all) + (size_t)(NX + NF) * FC::WARP_SCRATCH_BYTES);   // [qmax][B]
@@ -134,6 +179,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
         for (int s = 0; s < S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], NM); }
         for (int g = 0; g < NF; ++g) { mbar_init(&bars->gfull[g], NM); mbar_init(&bars->gempty[g], 1); }
         mbar_init(&bars->xfull[0], NX); mbar_init(&bars->xempty[0], NM);
+        bars->dq_n = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fill_twiddles<B>(tw, threadIdx.x, THREADS);
@@ -145,6 +191,20 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
     pdl_launch_dependents();
 
     const int s0 = cta_seg_ptr[blockIdx.x], s1 = cta_seg_ptr[blockIdx.x + 1];
+    const int ns = s1 - s0;
+    const int n_dyn = DYN ? dyn.n : 0;
+    int* __restrict__ dyn_ctr = dyn.ctr;
+    // segment k of this CTA: its static share first, then the dynamic items its producer drew (false: no more work)
+    auto fetch = [&](int k, SegWork& w, int& q) -> bool {
+        if (k < ns) { w = segs[s0 + k]; q = problems[w.g].q; return true; }
+        if (n_dyn == 0) return false;
+        const int d = k - ns;
+        while (ld_acquire_shared(&bars->dq_n) <= d) __nanosleep(32);
+        const int4 e = dq[2 * (d % DQ)];
+        w.g = e.x; w.j0 = e.y; w.j1 = e.z; w.pad = e.w;
+        q = dq[2 * (d % DQ) + 1].x;
+        return e.x >= 0;
+    };
     long long t_a = 0, t_b = 0, t_c = 0;
     const long long t_all0 = clk();
     (void)t_a; (void)t_b; (void)t_c; (void)t_all0; (void)dbg; (void)qmax;
@@ -153,23 +213,24 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
         // ===================== TMA producer: one bulk copy per (row, stage-of-row) =====================
         if (lane == 0) {
             int stage = 0; uint32_t ph = 0; int n = 0;
-            for (int s = s0; s < s1; ++s) {
-                const SegWork w = segs[s];
-                const ProblemDev* P = problems + w.g;
-                const int q = P->q;
-                const unsigned char* rowp = reinterpret_cast<const unsigned char*>(P->spec) + (size_t)w.j0 * q * BLOCK_BYTES;
+            bool have_t = false; int t = 0;
+            // first ticket of the dynamic tail: drawn once the ring has gone round (the MAC warps have consumed a stage, so the previous
+            // grid is complete and has reset the counter -- the wait returns at once), its latency hidden behind the static share
+            auto first_ticket = [&]() { pdl_wait(); t = atomicAdd(dyn_ctr, 1); have_t = true; };
+            auto stream_rows = [&](const int q, const unsigned char* rowp, const int j0, const int j1) {
                 if (BPS >= 2 && 2 * q <= CB) {                          // narrow rows: two block-rows per stage (they are contiguous)
-                    for (int r = w.j0; r < w.j1; r += 2, rowp += (size_t)2 * q * BLOCK_BYTES) {
+                    for (int r = j0; r < j1; r += 2, rowp += (size_t)2 * q * BLOCK_BYTES) {
                         { TSTART(w); mbar_wait(&bars->empty[stage], ph ^ 1u); TSTOP(w, t_a); }
-                        const uint32_t bytes = (uint32_t)min(2, w.j1 - r) * (uint32_t)q * BLOCK_BYTES;
+                        const uint32_t bytes = (uint32_t)min(2, j1 - r) * (uint32_t)q * BLOCK_BYTES;
                         mbar_arrive_expect_tx(&bars->full[stage], bytes);
                         bulk_g2s(ring + (size_t)stage * STAGE_BYTES, rowp, bytes, &bars->full[stage]);
                         if (++stage == S) { stage = 0; ph ^= 1u; }
                         ++n;
+                        if (n_dyn > 0 && !have_t && n > S) first_ticket();
                     }
-                    continue;
+                    return;
                 }
-                for (int r = w.j0; r < w.j1; ++r, rowp += (size_t)q * BLOCK_BYTES) {
+                for (int r = j0; r < j1; ++r, rowp += (size_t)q * BLOCK_BYTES) {
 #pragma unroll
                     for (int cs = 0; cs < RS; ++cs) {
                         if (cs * CB < q) {
@@ -181,6 +242,61 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
                             ++n;
                         }
                     }
+                    if (n_dyn > 0 && !have_t && n > S) first_ticket();
+                }
+            };
+            if constexpr (!DYN) {
+                for (int s = s0; s < s1; ++s) {
+                    const SegWork w = segs[s];
+                    const ProblemDev* P = problems + w.g;
+                    const int q = P->q;
+                    stream_rows(q, reinterpret_cast<const unsigned char*>(P->spec) + (size_t)w.j0 * q * BLOCK_BYTES, w.j0, w.j1);
+                }
+            } else {
+                // Software pipeline over the tickets: while item d streams, the load of item d + 1 and the draw of ticket d + 2 are in
+                // flight.  Every CTA draws exactly one ticket past the end; the X warps, who follow the queue to that entry, count the
+                // CTA as done.
+                auto load_item = [&](int tk) {
+                    const int4* p = reinterpret_cast<const int4*>(dyn.items + tk);
+                    const int4 a = __ldg(p), b = __ldg(p + 1);
+                    DynItem it;
+                    it.g = a.x; it.j0 = a.y; it.j1 = a.z; it.pi = a.w; it.q = b.x; it.pad = 0;
+                    it.rowp = reinterpret_cast<const void*>(((unsigned long long)(unsigned)b.w << 32) | (unsigned)b.z);
+                    return it;
+                };
+                // (one loop -- one copy of the streaming code -- over the static segments, k < ns, and then the tickets)
+                bool live = false;
+                DynItem it{};
+                int tn = 0;
+                for (int k = 0;; ++k) {
+                    if (k < ns) {
+                        const SegWork w = segs[s0 + k];
+                        const ProblemDev* P = problems + w.g;
+                        it.q = P->q; it.j0 = w.j0; it.j1 = w.j1;
+                        it.rowp = reinterpret_cast<const unsigned char*>(P->spec) + (size_t)w.j0 * it.q * BLOCK_BYTES;
+                    } else {
+                        if (k == ns) {
+                            if (!have_t) first_ticket();
+                            live = t < n_dyn;
+                            if (live) it = load_item(t);
+                            tn = live ? atomicAdd(dyn_ctr, 1) : 0;
+                        }
+                        const int d = k - ns;
+                        dq[2 * (d % DQ)] = live ? make_int4(it.g, it.j0, it.j1, it.pi) : make_int4(-1, 0, 0, 0);
+                        dq[2 * (d % DQ) + 1] = make_int4(it.q, 0, 0, 0);
+                        st_release_shared(&bars->dq_n, d + 1);
+                        if (!live) break;
+                    }
+                    DynItem itn{};
+                    bool live_n = false;
+                    int tnn = 0;
+                    if (k >= ns) {
+                        live_n = tn < n_dyn;
+                        if (live_n) itn = load_item(tn);
+                        tnn = live_n ? atomicAdd(dyn_ctr, 1) : 0;
+                    }
+                    stream_rows(it.q, reinterpret_cast<const unsigned char*>(it.rowp), it.j0, it.j1);
+                    if (k >= ns) { it = itn; live = live_n; tn = tnn; }
                 }
             }
             if (blockIdx.x == 3) TPRINT("producer: total %lld wait_empty %lld chunks %d\n", clk() - t_all0, t_a, n);
@@ -191,24 +307,24 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
         int stage = 0; uint32_t ph = 0;
         int gi = 0;
         RowAcc<B, NT> acc;
-        if (s0 < s1) {
+        SegWork w; int q = 0;
+        const bool any = fetch(0, w, q);                                 // (no static share: waits for the producer's first ticket)
+        if (any) {
             // First segment: nothing to multiply yet, so the MAC warps help the X warps with rfft(x) (all NM + NX warps, one
             // pass for q <= 48 instead of three): the start-up latency during which the ring is full and HBM idles.
             // Scratch: the (still unused) group buffers.
-            const ProblemDev P0 = problems[segs[s0].g];                  // plan data: constant, fetched while the previous grid drains
+            const ProblemDev P0 = problems[w.g];                         // plan data: constant, fetched while the previous grid drains
             if (!(dbg & 1)) pdl_wait();                                  // x may have been written by the previous grid (bit 0 of the plan flags: it was not)
             TSTART(x0);
             load_x_spectrum<B, NT, NM + NX>(P0, 0, xs, tw, reinterpret_cast<float2*>(part) + (size_t)m * (FC::WARP_SCRATCH_BYTES / 8), lane, m);
             asm volatile("bar.sync 1, %0;" ::"r"(32 * (NM + NX)) : "memory");
             TSTOP(x0, t_a);
         }
-        for (int s = s0; s < s1; ++s) {
-            const SegWork w = segs[s];
-            const int q = problems[w.g].q;
+        for (int k = 0; any && fetch(k, w, q); ++k) {
             const int rows = w.j1 - w.j0;
             // my slice of this segment's x spectrum -> registers (blocks i = cs*CB + m + NM*u), then free the X buffer at once
             float xr[RS][BPS][CH][CW];                                // (entries cs * BPS + u >= KX are never touched: no registers)
-            if (s > s0) { TSTART(x); mbar_wait(&bars->xfull[0], (uint32_t)(s - s0 - 1) & 1u); TSTOP(x, t_a); }
+            if (k > 0) { TSTART(x); mbar_wait(&bars->xfull[0], (uint32_t)(k - 1) & 1u); TSTOP(x, t_a); }
 #pragma unroll
             for (int cs = 0; cs < RS; ++cs)
 #pragma unroll
@@ -372,30 +488,98 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
         const int xw = warp - 1 - NM;
         float2* fscr = fscr_all + (size_t)xw * (FC::WARP_SCRATCH_BYTES / 8);
         ProblemDev P0{};
-        if (s0 < s1) P0 = problems[segs[s0].g];                          // plan data: constant, fetched while the previous grid drains
+        SegWork w; int qk = 0;
+        const bool any = fetch(0, w, qk);
+        if (any) P0 = problems[w.g];                                     // plan data: constant, fetched while the previous grid drains
         if (!(dbg & 1)) pdl_wait();                                      // x may have been written by the previous grid
-        if (s0 < s1) {                                                   // first segment: together with the MAC warps (see there)
+        // dynamic tail: this launch's mark = the sequence number the last CTA of the previous launch left + 1.  Read before anything of
+        // this CTA can count as done (below), so no CTA can see the number this launch will leave.
+        int mark = 0;
+        if (n_dyn > 0) mark = __ldcg(dyn_ctr + 2) + 1;
+        if (any) {                                                       // first segment: together with the MAC warps (see there)
             TSTART(y0);
             load_x_spectrum<B, NT, NM + NX>(P0, 0, xs, tw, fscr, lane, NM + xw);
             asm volatile("bar.sync 1, %0;" ::"r"(32 * (NM + NX)) : "memory");
             TSTOP(y0, t_b);
         }
-        for (int s = s0 + 1; s < s1; ++s) {
-            const ProblemDev P = problems[segs[s].g];
-            { TSTART(x); mbar_wait(&bars->xempty[0], ((uint32_t)(s - s0) & 1u) ^ 1u); TSTOP(x, t_a); }   // MAC warps copied the previous X out
-            { TSTART(y); load_x_spectrum<B, NT, NX>(P, 0, xs, tw, fscr, lane, xw); TSTOP(y, t_b); }
+        // dynamic tail: this CTA's share of the tail's input spectra (computed when the X warps have nothing else to do: at once if the
+        // static share is a single segment, else behind the second segment's transform)
+        auto publish = [&]() {
+            for (int pi = blockIdx.x; pi < dyn.K; pi += gridDim.x) {
+                x_warps_rfft<B>(problems + dyn.pool_g[pi], dyn.xcache + (size_t)pi * dyn.xstride, tw, fscr, lane, xw);
+                __threadfence();
+                asm volatile("bar.sync 2, %0;" ::"r"(32 * NX) : "memory");
+                if (xw == 0 && lane == 0) st_release_gpu(dyn_ctr + 4 + pi, mark);
+            }
+        };
+        bool published = n_dyn == 0, all_ready = false;
+        if (!published && ns <= 1) { publish(); published = true; }
+        for (int k = 1; any && fetch(k, w, qk); ++k) {
+            // An item of the tail: its input spectrum is in the cache.  The first 8 x 16 bytes per lane (all of a 4096-wide input) are
+            // loaded BEFORE waiting for the X buffer, so that behind the wait only the shared-memory stores remain: the item before it
+            // lasts ~1.5 us, an L2 round trip behind the wait would not fit.
+            float4 pre[8];
+            const float4* csrc = nullptr;
+            int n4 = 0;
+            if (DYN && k >= ns) {
+                if (!all_ready) {                                        // first item: every spectrum of the tail was marked ready long ago
+                    for (int pi = lane; pi < dyn.K; pi += 32)
+                        while (ld_acquire_gpu(dyn_ctr + 4 + pi) != mark) __nanosleep(64);
+                    __syncwarp();
+                    all_ready = true;
+                }
+                csrc = reinterpret_cast<const float4*>(dyn.xcache + (size_t)w.pad * dyn.xstride);
+                n4 = qk * (B / 4);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int i = xw * 32 + lane + u * 32 * NX; if (i < n4) pre[u] = __ldcg(csrc + i); }
+            }
+            { TSTART(x); mbar_wait(&bars->xempty[0], ((uint32_t)k & 1u) ^ 1u); TSTOP(x, t_a); }   // MAC warps copied the previous X out
+            if (k < ns) {
+                TSTART(y);
+                if constexpr (DYN) x_warps_rfft<B>(problems + w.g, xs, tw, fscr, lane, xw);
+                else { const ProblemDev P = problems[w.g]; load_x_spectrum<B, NT, NX>(P, 0, xs, tw, fscr, lane, xw); }
+                TSTOP(y, t_b);
+            } else if (DYN) {
+                float4* dst = reinterpret_cast<float4*>(xs);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int i = xw * 32 + lane + u * 32 * NX; if (i < n4) dst[i] = pre[u]; }
+                for (int i0 = xw * 32 + lane + 8 * 32 * NX; i0 < n4; i0 += 8 * 32 * NX) {      // (wider inputs: the rest, behind the wait)
+                    float4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (i0 + u * 32 * NX < n4) v[u] = __ldcg(csrc + i0 + u * 32 * NX);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (i0 + u * 32 * NX < n4) dst[i0 + u * 32 * NX] = v[u];
+                }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->xfull[0]);
+            if (!published) { publish(); published = true; }
+        }
+        if (!published) publish();
+        if (n_dyn > 0) {
+            // This CTA has drawn its one ticket past the end (the X warps followed the queue to that entry), read its mark and published
+            // its spectra.  The last CTA of the grid to get here re-arms the counters for the next launch, which touches them only after
+            // griddepcontrol.wait, i.e. after this grid has completed.
+            asm volatile("bar.sync 2, %0;" ::"r"(32 * NX) : "memory");
+            if (xw == 0 && lane == 0 && atomicAdd(dyn_ctr + 1, 1) == (int)gridDim.x - 1) { atomicExch(dyn_ctr, 0); atomicExch(dyn_ctr + 1, 0); atomicAdd(dyn_ctr + 2, 1); }
         }
         if (blockIdx.x == 3 && lane == 0) TPRINT("xw %d: total %lld wait_xempty %lld fft %lld\n", xw, clk() - t_all0, t_a, t_b);
     } else {
         // ===================== finishers: one warp per group, alternating =====================
         const int f = warp - 1 - NM - NX;
         float2* fscr = fscr_all + (size_t)(NX + f) * (FC::WARP_SCRATCH_BYTES / 8);
+#ifdef BCL_WS_TRACE
+        const unsigned long long tr0 = gtime();
+#endif
         if (!(dbg & 1)) pdl_wait();                                      // y may still be read by the previous grid
+#ifdef BCL_WS_TRACE
+        const unsigned long long tr1 = gtime();
+        int trn = 0;
+        if (lane == 0) { trn = g_trace_count[blockIdx.x * NF + f]; g_trace_count[blockIdx.x * NF + f] = trn + 1; }
+#endif
         int gi = 0;
-        for (int s = s0; s < s1; ++s) {
-            const SegWork w = segs[s];
+        SegWork w; int qf = 0;
+        for (int k = 0; fetch(k, w, qf); ++k) {
             const ProblemDev P = problems[w.g];
             const int rows = w.j1 - w.j0;
             for (int g0 = 0; g0 < rows; g0 += RG, ++gi) {
@@ -413,13 +597,17 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
             }
         }
         if (blockIdx.x == 3 && lane == 0) TPRINT("fin %d: total %lld wait_gfull %lld finish %lld groups %d\n", f, clk() - t_all0, t_a, t_b, gi);
+#ifdef BCL_WS_TRACE
+        if (lane == 0 && trn >= 200 && trn < 203)
+            printf("TL %d %d %d %d %llu %llu %llu %d\n", trn, (int)blockIdx.x, smid(), f, tr0, tr1, gtime(), s1 - s0);
+#endif
     }
 }
 
 size_t smem_bytes(int B, int spec_bytes, int qmax, int S) {
     const size_t fscr = B == 64 ? FftCfg<64>::WARP_SCRATCH_BYTES : (B == 128 ? FftCfg<128>::WARP_SCRATCH_BYTES : FftCfg<256>::WARP_SCRATCH_BYTES);
     const size_t stage = (size_t)stage_blocks(B, spec_bytes) * B * spec_bytes;
-    return 512 + 1024 + (size_t)S * stage + (size_t)NF * PAIRS * NM * B * 4 + (size_t)(NX + NF) * fscr + (size_t)qmax * B * 4;
+    return HEADER_BYTES + 1024 + (size_t)S * stage + (size_t)NF * PAIRS * NM * B * 4 + (size_t)(NX + NF) * fscr + (size_t)qmax * B * 4;
 }
 
 // Number of ring stages that fit next to the fixed buffers (0 = this shape does not fit the warp-specialised kernel).
@@ -443,7 +631,8 @@ static bool pdl_enabled() {                                             // BCL_P
 
 template <int B, typename SpecT, int RS, int KX>
 static cudaError_t launch_t(const GroupPlanHeader& H, const unsigned char* d, cudaStream_t st) {
-    auto kern = stream_ws_kernel<B, SpecT, RS, KX>;
+    const bool with_tail = H.num_dyn > 0 && !(H.reserved & 1);
+    auto kern = with_tail ? stream_ws_kernel<B, SpecT, RS, KX, true> : stream_ws_kernel<B, SpecT, RS, KX, false>;
     const int S = pick_stages(B, H.spec_dtype, H.nt, H.qmax);
     const size_t smem = smem_bytes(B, (int)sizeof(SpecT), H.qmax, S);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -462,7 +651,16 @@ static cudaError_t launch_t(const GroupPlanHeader& H, const unsigned char* d, cu
     const int* cta_ptr = reinterpret_cast<const int*>(d + H.off_cta_ptr);
     const SegWork* segs = reinterpret_cast<const SegWork*>(d + H.off_segs);
     int qmax = H.qmax, dbg = H.reserved, S_ = S;          // `reserved` = plan flags (bit 0: launches of this plan do not depend on the launch before them)
-    void* args[] = {(void*)&probs, (void*)&cta_ptr, (void*)&segs, (void*)&S_, (void*)&qmax, (void*)&dbg};
+    // dynamic tail: items behind the static segments, ticket + completion counters in the device plan (the one part of it the kernel writes)
+    DynArgs dyn{};
+    dyn.items = reinterpret_cast<const DynItem*>(segs + H.num_segs);
+    dyn.n = (dbg & 1) ? 0 : H.num_dyn;
+    dyn.K = H.dyn_problems;
+    dyn.ctr = reinterpret_cast<int*>(const_cast<unsigned char*>(d) + H.off_ctr);
+    dyn.pool_g = reinterpret_cast<const int*>(d + H.off_ctr) + 4 + H.dyn_problems;
+    dyn.xcache = reinterpret_cast<float*>(const_cast<unsigned char*>(d) + H.off_xcache);
+    dyn.xstride = H.dyn_xstride;
+    void* args[] = {(void*)&probs, (void*)&cta_ptr, (void*)&segs, (void*)&S_, (void*)&qmax, (void*)&dbg, (void*)&dyn};
     e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kern), args);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();

@@ -64,7 +64,7 @@ class GroupedBCForward:
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
             num_ctas = sms           # the warp-specialised kernel runs one persistent CTA per SM
         self.num_ctas = int(num_ctas)
-        nbytes = L.bcl_group_plan_bytes(len(xs), self.num_ctas)
+        nbytes = L.bcl_group_plan_bytes_for(probs, len(xs), B, _cabi.DTYPE[spec_dtype], self.num_ctas)   # with room for the dynamic tail
         self.host_plan = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         rc = L.bcl_group_plan_encode_layout(probs, len(xs), B, _cabi.DTYPE[spec_dtype], layout, self.num_ctas,
                                             self.host_plan.data_ptr(), nbytes)

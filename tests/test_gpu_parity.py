@@ -473,3 +473,31 @@ def test_grouped_plans_marked_independent_skip_the_dependency_wait(monkeypatch):
     for k in range(2):
         for y, yr in zip(ind[k].ys, ref_out[k]):
             assert torch.equal(y, yr)
+
+
+@pytest.mark.parametrize("spec", ["10,1", "40,2", "25,4", "90,3"])
+def test_grouped_decode_dynamic_tail_is_bit_identical_and_rearms_its_counters(monkeypatch, spec):
+    """Dynamic tail of the fp32 decode kernel (bcl_api.cu / bcl_stream_ws.cu): part of the rows is drawn by the CTAs from a ticket
+    counter in the device plan.  Which CTA computes a row must not change a bit of it; the counters must be back at zero after every
+    launch (200 launches back to back, two plans alternating, also with a small grid so that every CTA draws many items); and a CTA
+    without a static share (more CTAs than static rows) must work from tickets alone."""
+    g = torch.Generator().manual_seed(1234)
+    shapes = ([(32, 32)] * 4 + [(86, 32)] * 2 + [(32, 86)]) * 2 + [(5, 3), (1, 40)]
+    B = 128
+    layers = [make_layer(torch.randn(p, q, B, generator=g) * 0.01, None) for (p, q) in shapes]
+    xs = [[torch.randn(1, q * B, generator=g).to(torch.float16).to(DEV) for (p, q) in shapes] for _ in range(2)]
+    specs = [m.build_spectrum() for m in layers]
+    monkeypatch.setenv("BCL_GROUP_DYNAMIC", "0")
+    ref_out = [[y.clone() for y in bc.GroupedBCForward(xs[k], specs).run()] for k in range(2)]
+    monkeypatch.setenv("BCL_GROUP_DYNAMIC", spec)
+    for num_ctas in (None, 8, 40):
+        grp = [bc.GroupedBCForward(xs[k], specs, num_ctas=num_ctas) for k in range(2)]
+        for i in range(200):
+            grp[i & 1].run()
+        torch.cuda.synchronize()
+        for k in range(2):
+            for y, yr in zip(grp[k].ys, ref_out[k]):
+                assert torch.equal(y, yr)
+    # the oracle, once
+    for m, x, y in zip(layers[:3], xs[0][:3], ref_out[0][:3]):
+        assert_close(y, O.bc_forward_torch(m.c.detach().cpu(), x.cpu()), 2e-3, torch.float16)
