@@ -920,7 +920,7 @@ def time_prefill_layer_shared_input(bc, _cabi, dev, reps, n=PREFILL_TOKENS):
     return e0.elapsed_time(e1) / reps * 1e3, alg, prefill_status(dev)
 
 
-def time_prefill_mlp(bc, _cabi, dev, reps, n=PREFILL_TOKENS):
+def time_prefill_mlp(bc, _cabi, dev, reps, n=PREFILL_TOKENS, spectrum_dtype=None):
     """The MLP of one layer at prefill: what HF's LlamaMLP.forward runs over the three BC modules (gate, up, act_fn, multiply, down),
     the same with gate | up stacked (shared-input fusion), and the whole-MLP fusion (bcl_forward_swiglu: SWIGLU epilogue inside the
     tensor-core inverse stage, then down_proj)."""
@@ -928,9 +928,10 @@ def time_prefill_mlp(bc, _cabi, dev, reps, n=PREFILL_TOKENS):
     import torch.nn.functional as F
     from llama_fft_b200.patch_llama_fft import prefill_status
     torch.manual_seed(0)
+    sdt = spectrum_dtype or torch.bfloat16
 
     def mk(inf, outf):
-        return bc.BlockCirculantLinear(inf, outf, block_size=B, bias=False, spectrum_dtype=torch.bfloat16).to(dev).eval()
+        return bc.BlockCirculantLinear(inf, outf, block_size=B, bias=False, spectrum_dtype=sdt).to(dev).eval()
     gate, up, down = mk(4096, 11008), mk(4096, 11008), mk(11008, 4096)
     fused = bc.FusedBCMLP(gate, up, down)
     xs = [torch.randn(n, 4096, device=dev).half() for _ in range(2)]
@@ -960,7 +961,7 @@ def time_prefill_mlp(bc, _cabi, dev, reps, n=PREFILL_TOKENS):
     rel = ((a - b).abs().max() / b.abs().max()).item()
     # bytes the fused MLP has to move: x in, h out and in again (down_proj is a separate forward), y out, + the spectra
     alg = n * 4096 * 2 + 2 * n * 11008 * 2 + n * 4096 * 2 + 3 * 4096 * 11008 // B * 2
-    return {"what": "one layer's MLP, %d tokens, fp16, bf16 spectra: down(silu(gate(x)) * up(x))" % n,
+    return {"what": "one layer's MLP, %d tokens, fp16, %s spectra: down(silu(gate(x)) * up(x))" % (n, "bf16" if sdt == torch.bfloat16 else "fp32 (split hi/lo)"),
             "three_modules_plus_torch_silu_mul_us": t_modules, "stacked_gate_up_plus_torch_silu_mul_us": t_stacked,
             "fused_swiglu_stage_us": t_fused, "speedup_vs_modules": t_modules / t_fused, "max_rel_diff_vs_stacked": rel,
             "algorithmic_bytes_fused": alg, "pipeline_status": prefill_status(dev)}
@@ -1004,6 +1005,10 @@ def prefill_detail(bc, _cabi, dev, reps=5):
         out["mlp_fusion"] = time_prefill_mlp(bc, _cabi, dev, reps)
     except Exception as e:                                               # noqa: BLE001
         out["mlp_fusion"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    try:                                                                 # the same fusion at the default precision (fp32 spectra)
+        out["mlp_fusion_fp32_spectra"] = time_prefill_mlp(bc, _cabi, dev, max(2, reps // 2), spectrum_dtype=torch.float32)
+    except Exception as e:
+        out["mlp_fusion_fp32_spectra"] = {"error": "%s: %s" % (type(e).__name__, e)}
     torch.cuda.empty_cache()
     return out
 

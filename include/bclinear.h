@@ -98,8 +98,8 @@ int bcl_forward(const void* x, int x_dtype, int64_t N, int64_t x_row_stride,
 
 /* ---- gate_proj | up_proj + SWIGLU for many tokens (whole-MLP fusion at prefill) ------------------------------
  * Replaces the first half of what HF's LlamaMLP.forward chains over the three modules the reference swaps in
- * (src/patch_llama_fft.py:379):  act_fn(gate_proj(x)) * up_proj(x).  `spec_gemm` is the GEMM-layout bf16 spectrum of gate_proj and
- * up_proj STACKED along the output-block axis (p = 2 * intermediate/B block-rows: [0, p/2) gate, [p/2, p) up; bcl_precompute_spectrum
+ * (src/patch_llama_fft.py:379):  act_fn(gate_proj(x)) * up_proj(x).  `spec_gemm` is the GEMM-layout spectrum (spec_dtype BCL_BF16, or
+ * BCL_F32 = the (hi, lo) bf16 pairs of the fp32-accurate path: three MMAs per k-step in every stage) of gate_proj and up_proj STACKED along the output-block axis (p = 2 * intermediate/B block-rows: [0, p/2) gate, [p/2, p) up; bcl_precompute_spectrum
  * of the concatenated c).  One forward-DFT pass and one frequency-GEMM pass serve both members; the inverse stage transforms the two
  * members of a block pair into a pair of TMEM accumulators and writes
  *     h = round(silu(round(gate))) * round(up)        (every round() to x_dtype, silu in fp32: the arithmetic of the unfused modules)

@@ -148,14 +148,14 @@ class FusedBCMLP:
 
     def eligible_prefill(self, x: torch.Tensor) -> bool:
         """Many tokens: the stacked gate | up layer would take the tensor-core path and bcl_forward_swiglu covers the configuration."""
-        if not self._common_ok(x) or x.dtype == torch.float32 or self.gate.block_size > 128 or self.gate.spectrum_dtype != torch.bfloat16:
+        if not self._common_ok(x) or x.dtype == torch.float32 or self.gate.block_size > 128 or self.gate.spectrum_dtype not in (torch.bfloat16, torch.float32):
             return False
         n = x.numel() // self.gate.in_features
         return n > 1 and self._stacked_work(n)
 
     def _stacked_work(self, n: int) -> bool:
         from .patch_llama_fft import prefill_token_floor
-        return n >= prefill_token_floor(self.group.out_blocks, self.group.in_blocks, torch.bfloat16)
+        return n >= prefill_token_floor(self.group.out_blocks, self.group.in_blocks, self.gate.spectrum_dtype)
 
     def forward_prefill(self, x: torch.Tensor) -> torch.Tensor:
         g = self.group
@@ -166,10 +166,11 @@ class FusedBCMLP:
         spec = g.build_spectrum(_cabi.LAYOUT_GEMM)
         h = torch.empty(n, self.down.in_features, device=x_flat.device, dtype=x_flat.dtype)
         L = _cabi.lib()
-        ws_bytes = L.bcl_workspace_bytes(n, g.out_blocks, g.in_blocks, g.block_size, _cabi.BF16, _cabi.LAYOUT_GEMM)
+        sd = _cabi.DTYPE[self.gate.spectrum_dtype]                       # bf16, or f32 = the (hi, lo) split stages
+        ws_bytes = L.bcl_workspace_bytes(n, g.out_blocks, g.in_blocks, g.block_size, sd, _cabi.LAYOUT_GEMM)
         ws = prefill_workspace(x_flat.device, ws_bytes)
         with _cabi.on_device(x_flat.device):
-            rc = L.bcl_forward_swiglu(x_flat.data_ptr(), _cabi.DTYPE[x_flat.dtype], n, x_flat.stride(0), spec.data_ptr(), _cabi.BF16,
+            rc = L.bcl_forward_swiglu(x_flat.data_ptr(), _cabi.DTYPE[x_flat.dtype], n, x_flat.stride(0), spec.data_ptr(), sd,
                                       g.out_blocks, g.in_blocks, g.block_size, h.data_ptr(), _cabi.DTYPE[h.dtype], h.stride(0),
                                       ws.data_ptr(), ws.numel(), _cabi.stream_ptr(x_flat.device))
         _cabi.check(rc, "bcl_forward_swiglu")

@@ -192,15 +192,16 @@ int bcl_forward_swiglu(const void* x, int x_dtype, int64_t N, int64_t x_row_stri
     if (p <= 0 || (p & 1)) return fail(BCL_ERR_SHAPE, "SWIGLU needs an even number of block-rows (gate | up stacked), got p=%d", p);
     int rc = check_problem(x, x_dtype, N, x_row_stride, spec_gemm, p, q, B, nullptr, 0, h, h_dtype, h_row_stride, p / 2);
     if (rc != BCL_OK || N == 0) return rc;
-    if (spec_dtype != BCL_BF16) return fail(BCL_ERR_UNSUPPORTED, "bcl_forward_swiglu: bf16 GEMM-layout spectra only (fp32 spectra: run the projections one by one)");
+    if (spec_dtype != BCL_BF16 && spec_dtype != BCL_F32) return fail(BCL_ERR_DTYPE, "GEMM spectrum must be bf16 or f32 (split bf16 pairs)");
+    const int split = spec_dtype == BCL_F32;
     if (B > 128 || x_dtype == BCL_F32) return fail(BCL_ERR_UNSUPPORTED, "bcl_forward_swiglu: B <= 128 and 16-bit activations");
     if (N > (int64_t)1 << 30) return fail(BCL_ERR_SHAPE, "N=%lld too large; split the batch", (long long)N);
     if (!workspace || !aligned(workspace, 256)) return fail(BCL_ERR_WORKSPACE, "GEMM layout needs a 256-byte aligned workspace");
-    if (bcl::gemm_chunk_tokens(N, p, q, B, workspace_bytes, 0) < (N < 128 ? N : 128))
+    if (bcl::gemm_chunk_tokens(N, p, q, B, workspace_bytes, split) < (N < 128 ? N : 128))
         return fail(BCL_ERR_WORKSPACE, "workspace %zu bytes cannot stage one 128-token chunk (bcl_workspace_bytes gives %zu)", workspace_bytes,
-                    bcl::gemm_workspace_bytes(N, p, q, B, 0));
+                    bcl::gemm_workspace_bytes(N, p, q, B, split));
     bcl::ProblemDev P{x, spec_gemm, nullptr, h, N, x_row_stride, h_row_stride, p, q, x_dtype, h_dtype, BCL_F32, 0, {}};
-    cudaError_t e = bcl::launch_gemm_forward_swiglu(P, B, spec_gemm, workspace, workspace_bytes, (cudaStream_t)stream);
+    cudaError_t e = bcl::launch_gemm_forward_swiglu(P, B, spec_gemm, workspace, workspace_bytes, split, (cudaStream_t)stream);
     if (e == cudaErrorNotSupported) return fail(BCL_ERR_UNSUPPORTED, "bcl_forward_swiglu: configuration not covered by the tensor-core SWIGLU stage");
     return e == cudaSuccess ? BCL_OK : cuda_fail(e, "SWIGLU forward launch");
 }

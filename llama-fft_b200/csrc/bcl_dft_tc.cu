@@ -72,7 +72,15 @@ template <int B>
 __global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_swiglu_tc_kernel(const __grid_constant__ CUtensorMap tmYf, const __grid_constant__ CUtensorMap tmW,
                                                                             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ DftArgs a) {
     extern __shared__ __align__(1024) unsigned char dft_smem[];
-    dft_inv_swiglu_body<B>(dft_smem, tmYf, tmW, tmOut, a, (int)blockIdx.x, (int)gridDim.x);
+    dft_inv_swiglu_body<B, false>(dft_smem, tmYf, tmW, tmOut, nullptr, a, (int)blockIdx.x, (int)gridDim.x);
+}
+// fp32 spectra: (hi, lo) Yf and inverse DFT matrices
+template <int B>
+__global__ void __launch_bounds__(DFT_THREADS, 1) dft_inv_swiglu_tc_split_kernel(const __grid_constant__ CUtensorMap tmYf, const __grid_constant__ CUtensorMap tmW,
+                                                                                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ DftLoMaps lo,
+                                                                                  const __grid_constant__ DftArgs a) {
+    extern __shared__ __align__(1024) unsigned char dft_smem[];
+    dft_inv_swiglu_body<B, true>(dft_smem, tmYf, tmW, tmOut, &lo, a, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // =========================================================================================================
@@ -178,14 +186,16 @@ bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm,
     return true;
 }
 
-bool prep_dft_inv_swiglu(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L) {
+bool prep_dft_inv_swiglu(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L,
+                         const void* Yf_lo, DftLoMaps* lo) {
     const int B = g.B;
-    if ((B != 64 && B != 128) || (g.p & 1) || g.split) return false;
+    const bool split = lo != nullptr;
+    if ((B != 64 && B != 128) || (g.p & 1) || (g.split != 0) != split || (split && Yf_lo == nullptr)) return false;
     const bool bf = P.x_dtype == BCL_BF16;
     const CUtensorMapDataType adt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     if (!make_chunk_map(&L.tm_in, Yf, nc, g.p, g.FG, TILE_M / TOK_GROUP, 1, (uint32_t)g.FG)) return false;
     const unsigned char* sb = reinterpret_cast<const unsigned char*>(spec_gemm);
-    if (!map_w(&L.tm_w, sb + g.winv_off, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return false;
+    if (!map_w(&L.tm_w, sb + g.winv_off, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, split)) return false;
     const uint64_t dims[2] = {(uint64_t)(g.p / 2) * B, (uint64_t)P.N};
     const uint64_t strides[1] = {(uint64_t)P.y_stride * 2};
     const uint32_t box[2] = {KATOM, 32};
@@ -194,15 +204,19 @@ bool prep_dft_inv_swiglu(const ProblemDev& P, const Geometry& g, const void* spe
     a = DftArgs{};
     a.status = status; a.bias = nullptr; a.n_begin = n_begin; a.nc = nc;
     a.m_tiles = (nc + TILE_M - 1) / TILE_M; a.groups = g.p / 2; a.num_items = a.m_tiles * (g.p / 2); a.act_bf16 = bf ? 1 : 0;
-    const uint32_t stage_bytes = (uint32_t)g.FG * 2048;
-    a.stages = dft_pick_stages(B, stage_bytes) & ~1;                 // an item takes two stages
+    const uint32_t stage_bytes = (uint32_t)g.FG * 2048 * (split ? 2 : 1);
+    a.stages = dft_pick_stages(B, stage_bytes, split ? 1 : DFT_NBUF, split ? 2 : 1) & ~1;   // an item takes two stages
     if (a.stages < 2) return false;
-    L.smem = dft_smem_bytes(B, stage_bytes, a.stages);
+    L.smem = dft_smem_bytes(B, stage_bytes, a.stages, split ? 1 : DFT_NBUF, split ? 2 : 1);
+    if (split) {
+        if (!map_w(&lo->W, sb + g.winv_lo_off, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, true)) return false;
+        if (!make_chunk_map(&lo->IO, Yf_lo, nc, g.p, g.FG, TILE_M / TOK_GROUP, 1, (uint32_t)g.FG)) return false;
+    }
     return true;
 }
 
-cudaError_t launch_dft_inv_swiglu_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status,
-                                     int max_ctas, cudaStream_t st);
+cudaError_t launch_dft_inv_swiglu_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, const void* Yf_lo,
+                                     int* status, int max_ctas, cudaStream_t st);
 
 template <typename K, typename... Extra>
 static cudaError_t launch_stage(K kernel, const StageLaunch<DftArgs>& L, int max_ctas, cudaStream_t st, const Extra&... extra) {
@@ -274,9 +288,14 @@ cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void
 }
 
 
-cudaError_t launch_dft_inv_swiglu_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status,
-                                     int max_ctas, cudaStream_t st) {
+cudaError_t launch_dft_inv_swiglu_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, const void* Yf_lo,
+                                     int* status, int max_ctas, cudaStream_t st) {
     StageLaunch<DftArgs> L;
+    if (g.split) {
+        DftLoMaps lo;
+        if (!prep_dft_inv_swiglu(P, g, spec_gemm, n_begin, nc, Yf, status, L, Yf_lo, &lo)) return cudaErrorNotSupported;
+        return g.B == 128 ? launch_stage(dft_inv_swiglu_tc_split_kernel<128>, L, max_ctas, st, lo) : launch_stage(dft_inv_swiglu_tc_split_kernel<64>, L, max_ctas, st, lo);
+    }
     if (!prep_dft_inv_swiglu(P, g, spec_gemm, n_begin, nc, Yf, status, L)) return cudaErrorNotSupported;
     return g.B == 128 ? launch_stage(dft_inv_swiglu_tc_kernel<128>, L, max_ctas, st) : launch_stage(dft_inv_swiglu_tc_kernel<64>, L, max_ctas, st);
 }

@@ -575,29 +575,32 @@ cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* spec_gem
 }
 
 
-// gate | up stacked along the output-block axis (P.p = 2 x the MLP's intermediate block count), GEMM-layout bf16 spectrum: the
-// forward-DFT and frequency-GEMM stages of the chain, then the SWIGLU inverse stage: P.y = h = round(silu(round(gate))) * round(up).
+// gate | up stacked along the output-block axis (P.p = 2 x the MLP's intermediate block count), GEMM-layout spectrum (bf16, or the
+// (hi, lo) pairs of fp32 spectra with split = 1): the forward-DFT and frequency-GEMM stages of the chain, then the SWIGLU inverse
+// stage: P.y = h = round(silu(round(gate))) * round(up).
 // Chunked like launch_gemm_forward.  cudaErrorNotSupported: the caller runs the three modules one by one.
-cudaError_t launch_gemm_forward_swiglu(const ProblemDev& P, int B, const void* spec_gemm, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    const gemm::Geometry g = gemm::geometry(P.p, P.q, B, 0);
+cudaError_t launch_gemm_forward_swiglu(const ProblemDev& P, int B, const void* spec_gemm, void* workspace, size_t workspace_bytes, int split, cudaStream_t st) {
+    const gemm::Geometry g = gemm::geometry(P.p, P.q, B, split);
     if (B > 128 || (P.p & 1) || !gemm::dft_tc_supported(B, P.x_dtype) || P.y_dtype != P.x_dtype || P.bias != nullptr || P.n_extra != 0 || spec_gemm == nullptr)
         return cudaErrorNotSupported;
-    const int64_t ncmax = gemm_chunk_tokens(P.N, P.p, P.q, B, workspace_bytes, 0);
+    const int64_t ncmax = gemm_chunk_tokens(P.N, P.p, P.q, B, workspace_bytes, split);
     if (ncmax < 1) return cudaErrorInvalidValue;
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     int* status = reinterpret_cast<int*>(ws);
     const size_t ctr_bytes = gemm::fused_counter_bytes(P.N);
-    const size_t xfb = (gemm::xf_bytes(g, ncmax) + 255) & ~(size_t)255;
-    unsigned char* Xf = ws + kWsHeader + ctr_bytes;
-    unsigned char* Yf = Xf + xfb;
+    const size_t xfb = (gemm::xf_bytes(g, ncmax) + 255) & ~(size_t)255, yfb = (gemm::yf_bytes(g, ncmax) + 255) & ~(size_t)255;
+    unsigned char* Xf = ws + kWsHeader + ctr_bytes;                 // same layout as launch_gemm_forward: Xf [| Xf_lo] | Yf [| Yf_lo]
+    unsigned char* Yf = Xf + xfb * (split ? 2 : 1);
+    unsigned char* Xf_lo = split ? Xf + xfb : nullptr;
+    unsigned char* Yf_lo = split ? Yf + yfb : nullptr;
     const int ctas = sm_count();
     cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     for (int64_t n0 = 0; n0 < P.N; n0 += ncmax) {
         const int nc = (int)((P.N - n0 < ncmax) ? (P.N - n0) : ncmax);
-        if ((e = gemm::launch_dft_fwd_tc(P, g, spec_gemm, n0, nc, Xf, nullptr, status, ctas, st)) != cudaSuccess) return e;
-        if ((e = launch_gemm_mma(Xf, nullptr, spec_gemm, Yf, nullptr, status, P.p, P.q, B, nc, ctas, st)) != cudaSuccess) return e;
-        if ((e = gemm::launch_dft_inv_swiglu_tc(P, g, spec_gemm, n0, nc, Yf, status, ctas, st)) != cudaSuccess) return e;
+        if ((e = gemm::launch_dft_fwd_tc(P, g, spec_gemm, n0, nc, Xf, Xf_lo, status, ctas, st)) != cudaSuccess) return e;
+        if ((e = launch_gemm_mma(Xf, Xf_lo, spec_gemm, Yf, Yf_lo, status, P.p, P.q, B, nc, ctas, st)) != cudaSuccess) return e;
+        if ((e = gemm::launch_dft_inv_swiglu_tc(P, g, spec_gemm, n0, nc, Yf, Yf_lo, status, ctas, st)) != cudaSuccess) return e;
     }
     return cudaSuccess;
 }

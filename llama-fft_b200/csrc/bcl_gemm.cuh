@@ -102,8 +102,8 @@ cudaError_t launch_dft_inv_tc(const ProblemDev& P, const Geometry& g, const void
                               int max_ctas, cudaStream_t st);
 
 // gate | up stacked along the output-block axis: inverse DFT + SWIGLU epilogue, P.y = h with (g.p / 2) * B columns (B <= 128, bf16 spectra)
-cudaError_t launch_dft_inv_swiglu_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status,
-                                     int max_ctas, cudaStream_t st);
+cudaError_t launch_dft_inv_swiglu_tc(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, const void* Yf_lo,
+                                     int* status, int max_ctas, cudaStream_t st);
 
 // Single-launch pipeline of the three tensor-core stages over L2-resident intermediates (bcl_prefill_fused.cu).
 // counters: 3 * ceil(N/128) ints, zeroed in stream order before the launch; Xf / Yf sized for all N tokens.

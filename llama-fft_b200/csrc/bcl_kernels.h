@@ -91,7 +91,7 @@ cudaError_t launch_gemm_irfft(const ProblemDev& P, int B, int64_t n_begin, int n
 cudaError_t launch_prefill_stage1(const ProblemDev& P, int B, const void* spec_gemm, int64_t n_begin, int nc, void* Xf, int* status, int impl, cudaStream_t st);
 cudaError_t launch_prefill_stage3(const ProblemDev& P, int B, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, int impl, cudaStream_t st);
 cudaError_t launch_gemm_forward(const ProblemDev& P, int B, const void* Cmat, void* workspace, size_t workspace_bytes, int split, cudaStream_t st);
-cudaError_t launch_gemm_forward_swiglu(const ProblemDev& P, int B, const void* spec_gemm, void* workspace, size_t workspace_bytes, cudaStream_t st);
+cudaError_t launch_gemm_forward_swiglu(const ProblemDev& P, int B, const void* spec_gemm, void* workspace, size_t workspace_bytes, int split, cudaStream_t st);
 
 // calibration gradients (bcl_backward.cu)
 size_t backward_workspace_bytes(int64_t N, int p, int q, int B);

@@ -889,21 +889,25 @@ __device__ __forceinline__ void store_row_swiglu(unsigned char* row, int lane, c
     }
 }
 
-template <int B>
+// SPLIT (fp32 spectra): Yf = Yhi + Ylo, Winv = Whi + Wlo (bf16 pairs), three MMAs per k-step as in dft_inv_body<B, true>; a stage holds
+// [Yf hi | Yf lo] of one slab and every epilogue warp has one staging buffer, so two 64 KB stages fit next to the two DFT matrices.
+template <int B, bool SPLIT>
 __device__ __forceinline__ void dft_inv_swiglu_body(unsigned char* dft_smem, const CUtensorMap& tmYf, const CUtensorMap& tmW, const CUtensorMap& tmOut,
-                                                    const DftArgs& a, const int first, const int stride) {
+                                                    const DftLoMaps* lo, const DftArgs& a, const int first, const int stride) {
     static_assert(B == 64 || B == 128, "SWIGLU inverse stage: B = 64 / 128");
     constexpr int ATOMS = B / KATOM;
     constexpr int OUT_ATOMS = B / KATOM;
     constexpr int FG = B / 8;
     constexpr int KSTEPS = B / 16;
     constexpr uint32_t W_ATOM = B * 128;
-    constexpr uint32_t STAGE = FG * 2048;                    // Yf of (tile, slab): [fg][128 tokens][16 B]
+    constexpr uint32_t STAGE_HALF = FG * 2048;               // Yf of (tile, slab): [fg][128 tokens][16 B]
+    constexpr uint32_t STAGE = (SPLIT ? 2 : 1) * STAGE_HALF; // split: [Yf hi | Yf lo]
+    constexpr int NBUF = SPLIT ? 1 : DFT_NBUF;               // staging buffers per epilogue warp
     constexpr int NPAIR = 2;                                 // accumulator pairs in flight (2 x 2 x B <= 512 columns)
     DftBarriers* bars = reinterpret_cast<DftBarriers*>(dft_smem);
     unsigned char* epi = dft_smem + 1024;
-    unsigned char* wsm = dft_smem + 1024 + DFT_EPI_WARPS * DFT_NBUF * DFT_EPI_BUF;
-    unsigned char* ring = wsm + ATOMS * W_ATOM;
+    unsigned char* wsm = dft_smem + 1024 + DFT_EPI_WARPS * NBUF * DFT_EPI_BUF;
+    unsigned char* ring = wsm + (SPLIT ? 2 : 1) * ATOMS * W_ATOM;           // split: [W hi | W lo]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int S = a.stages;
 
@@ -913,7 +917,10 @@ __device__ __forceinline__ void dft_inv_swiglu_body(unsigned char* dft_smem, con
         mbar_init(&bars->wfull, 1);
         fence_barrier_init();
     }
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmYf); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmOut); }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmYf); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmOut);
+        if constexpr (SPLIT) { tma_prefetch_desc(&lo->W); tma_prefetch_desc(&lo->IO); }
+    }
     if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
     tc_fence_before_sync();
     __syncthreads();
@@ -923,8 +930,10 @@ __device__ __forceinline__ void dft_inv_swiglu_body(unsigned char* dft_smem, con
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(&bars->wfull, ATOMS * W_ATOM);
+            mbar_arrive_expect_tx(&bars->wfull, (SPLIT ? 2 : 1) * ATOMS * W_ATOM);
             for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + at * W_ATOM, &tmW, at * KATOM, 0, &bars->wfull);
+            if constexpr (SPLIT)
+                for (int at = 0; at < ATOMS; ++at) tma_load_2d(wsm + (ATOMS + at) * W_ATOM, &lo->W, at * KATOM, 0, &bars->wfull);
             pdl_wait();                                                          // Yf comes from the previous kernel
             int stage = 0; uint32_t ph = 0;
             for (int item = first; item < a.num_items; item += stride) {
@@ -933,6 +942,9 @@ __device__ __forceinline__ void dft_inv_swiglu_body(unsigned char* dft_smem, con
                     if (!mbar_wait(&bars->empty[stage], ph ^ 1u)) { set_status(a.status, 71); goto done; }
                     mbar_arrive_expect_tx(&bars->full[stage], STAGE);
                     tma_load_4d_hint(ring + (size_t)stage * STAGE, &tmYf, 0, m * (TILE_M / TOK_GROUP), j + half * a.groups, 0, &bars->full[stage], L2_EVICT_FIRST);
+                    if constexpr (SPLIT)
+                        tma_load_4d_hint(ring + (size_t)stage * STAGE + STAGE_HALF, &lo->IO, 0, m * (TILE_M / TOK_GROUP), j + half * a.groups, 0, &bars->full[stage],
+                                         L2_EVICT_FIRST);
                     if (++stage == S) { stage = 0; ph ^= 1u; }
                 }
             }
@@ -950,10 +962,17 @@ __device__ __forceinline__ void dft_inv_swiglu_body(unsigned char* dft_smem, con
                     if (!mbar_wait(&bars->full[stage], ph)) { set_status(a.status, 74); goto done; }
                     tc_fence_after_sync();
                     const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE), sw = smem_u32(wsm);
+                    const uint32_t acc = tmem_base + (uint32_t)((2 * pair + half) * B);
 #pragma unroll
-                    for (int kk = 0; kk < KSTEPS; ++kk)
-                        umma_bf16_ss(tmem_base + (uint32_t)((2 * pair + half) * B), umma_desc_k_nosw(sa + (uint32_t)kk * 4096u, 128u, 2048u),
-                                     umma_desc_k_sw128(sw + (kk / 4) * W_ATOM) + (uint64_t)(2 * (kk % 4)), idesc, kk != 0 ? 1u : 0u);
+                    for (int kk = 0; kk < KSTEPS; ++kk) {
+                        const uint64_t adesc = umma_desc_k_nosw(sa + (uint32_t)kk * 4096u, 128u, 2048u);
+                        const uint64_t bdesc = umma_desc_k_sw128(sw + (kk / 4) * W_ATOM) + (uint64_t)(2 * (kk % 4));
+                        umma_bf16_ss(acc, adesc, bdesc, idesc, kk != 0 ? 1u : 0u);
+                        if constexpr (SPLIT) {
+                            umma_bf16_ss(acc, adesc, umma_desc_k_sw128(sw + (ATOMS + kk / 4) * W_ATOM) + (uint64_t)(2 * (kk % 4)), idesc, 1u);
+                            umma_bf16_ss(acc, umma_desc_k_nosw(sa + STAGE_HALF + (uint32_t)kk * 4096u, 128u, 2048u), bdesc, idesc, 1u);
+                        }
+                    }
                     umma_commit(&bars->empty[stage]);
                     if (++stage == S) { stage = 0; ph ^= 1u; }
                 }
@@ -962,7 +981,7 @@ __device__ __forceinline__ void dft_inv_swiglu_body(unsigned char* dft_smem, con
         }
     } else {
         const int quarter = warp & 3;
-        unsigned char* stg = epi + (size_t)(warp - 2) * DFT_NBUF * DFT_EPI_BUF;
+        unsigned char* stg = epi + (size_t)(warp - 2) * NBUF * DFT_EPI_BUF;
         pdl_wait();                                                              // h may still be read by the previous kernel
         int it = 0, buf = 0;
         for (int item = first; item < a.num_items; item += stride, ++it) {
@@ -989,7 +1008,7 @@ __device__ __forceinline__ void dft_inv_swiglu_body(unsigned char* dft_smem, con
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->tmem_empty[pair]);
                 }
-                if (lane == 0) tma_store_wait_read<DFT_NBUF - 1>();
+                if (lane == 0) tma_store_wait_read<NBUF - 1>();
                 __syncwarp();
                 unsigned char* row = stg + (size_t)buf * DFT_EPI_BUF + (size_t)lane * 128;
                 if (a.act_bf16) store_row_swiglu<true>(row, lane, rg, ru);
@@ -1000,7 +1019,7 @@ __device__ __forceinline__ void dft_inv_swiglu_body(unsigned char* dft_smem, con
                     tma_store_2d(&tmOut, j * B + h * 64, (int)(a.n_begin + (int64_t)m * TILE_M + quarter * 32), stg + (size_t)buf * DFT_EPI_BUF);
                     tma_store_commit();
                 }
-                if (++buf == DFT_NBUF) buf = 0;
+                if (++buf == NBUF) buf = 0;
             }
         }
         if (lane == 0) tma_store_wait<0>();
@@ -1027,7 +1046,8 @@ bool prep_gemm_lo(const void* Xf_lo, const void* Cmat, void* Yf_lo, const Geomet
 bool prep_dft_inv(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L,
                   const void* Yf_lo = nullptr, DftLoMaps* lo = nullptr, DftExtraOut* ex = nullptr);
 // g: geometry of the STACKED (gate | up) layer (g.p block-rows, even); P.y = h with (g.p / 2) * B columns
-bool prep_dft_inv_swiglu(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L);
+bool prep_dft_inv_swiglu(const ProblemDev& P, const Geometry& g, const void* spec_gemm, int64_t n_begin, int nc, const void* Yf, int* status, StageLaunch<DftArgs>& L,
+                         const void* Yf_lo = nullptr, DftLoMaps* lo = nullptr);
 
 }  // namespace gemm
 }  // namespace bcl

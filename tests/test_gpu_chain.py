@@ -221,22 +221,22 @@ def test_fuse_mlp_in_a_tiny_llama_decode_step():
 # ---------------------------------------------------------------------------------------------------------
 # whole-MLP fusion at prefill: bcl_forward_swiglu (gate | up stacked, SWIGLU epilogue in the tensor-core inverse stage)
 # ---------------------------------------------------------------------------------------------------------
-def _gemm_spectrum(c):
+def _gemm_spectrum(c, sd=_cabi.BF16):
     p, q, B = c.shape
     L = _cabi.lib()
     cd = c.to(DEV).contiguous()
-    spec = torch.empty(L.bcl_spectrum_bytes(p, q, B, _cabi.BF16, _cabi.LAYOUT_GEMM), device=DEV, dtype=torch.uint8)
-    _cabi.check(L.bcl_precompute_spectrum(cd.data_ptr(), p, q, B, spec.data_ptr(), _cabi.BF16, _cabi.LAYOUT_GEMM, _cabi.stream_ptr(torch.device(DEV))),
+    spec = torch.empty(L.bcl_spectrum_bytes(p, q, B, sd, _cabi.LAYOUT_GEMM), device=DEV, dtype=torch.uint8)
+    _cabi.check(L.bcl_precompute_spectrum(cd.data_ptr(), p, q, B, spec.data_ptr(), sd, _cabi.LAYOUT_GEMM, _cabi.stream_ptr(torch.device(DEV))),
                 "bcl_precompute_spectrum")
     return spec
 
 
-def _forward_swiglu(x, spec, p, q, B):
+def _forward_swiglu(x, spec, p, q, B, sd=_cabi.BF16, ws_bytes=None):
     L = _cabi.lib()
     N = x.shape[0]
     h = torch.full((N, p // 2 * B), float("nan"), device=DEV, dtype=x.dtype)
-    ws = torch.zeros(L.bcl_workspace_bytes(N, p, q, B, _cabi.BF16, _cabi.LAYOUT_GEMM), device=DEV, dtype=torch.uint8)
-    rc = L.bcl_forward_swiglu(x.data_ptr(), _cabi.DTYPE[x.dtype], N, x.stride(0), spec.data_ptr(), _cabi.BF16, p, q, B,
+    ws = torch.zeros(ws_bytes or L.bcl_workspace_bytes(N, p, q, B, sd, _cabi.LAYOUT_GEMM), device=DEV, dtype=torch.uint8)
+    rc = L.bcl_forward_swiglu(x.data_ptr(), _cabi.DTYPE[x.dtype], N, x.stride(0), spec.data_ptr(), sd, p, q, B,
                               h.data_ptr(), _cabi.DTYPE[h.dtype], h.stride(0), ws.data_ptr(), ws.numel(), _cabi.stream_ptr(torch.device(DEV)))
     _cabi.check(rc, "bcl_forward_swiglu")
     torch.cuda.synchronize()
@@ -273,6 +273,38 @@ def test_prefill_swiglu_stage_matches_the_unfused_modules_and_the_oracle(hidden,
     assert torch.equal(h, h2)
 
 
+@pytest.mark.parametrize("hidden,inter,B,N,dtype", [(4096, 11008, 128, 1500, torch.float16), (4096, 11008, 128, 640, torch.bfloat16),
+                                                     (512, 1536, 64, 700, torch.float16), (1024, 2048, 128, 128 * 9 + 1, torch.bfloat16)])
+def test_prefill_swiglu_stage_with_fp32_spectra(hidden, inter, B, N, dtype):
+    """The same fusion for the default precision (fp32 spectra = (hi, lo) bf16 pairs, split stages; dft_inv_swiglu_tc_split_kernel):
+    (a) within 2 ulp of the two unfused projections through the library's own split tensor-core path followed by torch's silu and
+    multiply, (b) against the reference's modules composed on the CPU oracle in the fp32-spectrum class (1e-4 on gate and up; h is a
+    product of two rounded 16-bit values, hence the ulps), (c) forced chunking (a workspace of two 128-token tiles) changes nothing."""
+    g = torch.Generator().manual_seed(hidden + inter + B + N + 1)
+    cg = torch.randn(inter // B, hidden // B, B, generator=g) * 0.03
+    cu = torch.randn(inter // B, hidden // B, B, generator=g) * 0.03
+    x = torch.randn(N, hidden, generator=g).to(dtype)
+    xd = x.to(DEV)
+    p, q = 2 * (inter // B), hidden // B
+    spec = _gemm_spectrum(torch.cat([cg, cu], 0), _cabi.F32)
+    h = _forward_swiglu(xd, spec, p, q, B, _cabi.F32)
+    assert not torch.isnan(h.float()).any()
+    gate = bc_forward(xd, _gemm_spectrum(cg, _cabi.F32), None, p // 2, q, B, layout=_cabi.LAYOUT_GEMM, spectrum_dtype=torch.float32)
+    up = bc_forward(xd, _gemm_spectrum(cu, _cabi.F32), None, p // 2, q, B, layout=_cabi.LAYOUT_GEMM, spectrum_dtype=torch.float32)
+    h_unfused = F.silu(gate) * up
+    diff = (h.double() - h_unfused.double()).abs()
+    assert bool((diff <= 2 * G.ulp(dtype) * h_unfused.double().abs() + 1e-30).all()), f"max diff {diff.max().item():.3e}"
+    assert (h == h_unfused).float().mean().item() >= 0.98
+    rows = torch.tensor([0, 1, 127, 128, N // 2, N - 1])
+    gate_ref, up_ref = O.bc_forward_torch(cg, x[rows].float()), O.bc_forward_torch(cu, x[rows].float())
+    h_ref = F.silu(gate_ref) * up_ref
+    assert_close(h[rows], h_ref, 5e-4, dtype, ulps=4)
+    L = _cabi.lib()
+    small = L.bcl_workspace_bytes(256, p, q, B, _cabi.F32, _cabi.LAYOUT_GEMM)
+    if N > 256:
+        assert torch.equal(h, _forward_swiglu(xd, spec, p, q, B, _cabi.F32, ws_bytes=small))
+
+
 def test_forward_swiglu_argument_validation():
     L = _cabi.lib()
     x = torch.zeros(256, 512, device=DEV, dtype=torch.float16)
@@ -285,14 +317,17 @@ def test_forward_swiglu_argument_validation():
                                                       h.data_ptr(), _cabi.DTYPE[xt.dtype], h.stride(0), ws.data_ptr(), ws.numel(), st)
     assert L.bcl_forward_swiglu(*args()) == 0
     assert L.bcl_forward_swiglu(*args(p=5)) != 0                               # odd number of block-rows
-    assert L.bcl_forward_swiglu(*args(sd=_cabi.F32)) == -8                     # fp32 spectra: unsupported, never a silent fallback
+    assert L.bcl_forward_swiglu(*args(sd=_cabi.F16)) != 0                      # spectra are bf16 or f32 (split pairs)
+    assert L.bcl_forward_swiglu(*args(B=256)) != 0                             # B <= 128
     assert L.bcl_forward_swiglu(*args(xt=x.float()[:, :512].contiguous())) != 0
     torch.cuda.synchronize()
 
 
-def test_fuse_mlp_prefill_path_in_a_tiny_llama(monkeypatch):
+@pytest.mark.parametrize("sdt,tol", [(torch.bfloat16, 1e-2), (torch.float32, 2e-3)])
+def test_fuse_mlp_prefill_path_in_a_tiny_llama(monkeypatch, sdt, tol):
     """fuse_mlp serves many-token eval calls with bcl_forward_swiglu + down_proj when the stacked gate | up layer has enough work for
-    the tensor-core path: logits agree with the unfused model to the bf16-spectrum class, and the counter shows the path really ran."""
+    the tensor-core path: logits agree with the unfused model to the spectrum class (fp16 model: the fp32-spectrum arm is bounded by
+    the 16-bit activations between the layers), and the counter shows the path really ran."""
     import importlib
     from transformers import LlamaConfig, LlamaForCausalLM
     P = importlib.import_module("llama_fft_b200.patch_llama_fft")
@@ -300,10 +335,11 @@ def test_fuse_mlp_prefill_path_in_a_tiny_llama(monkeypatch):
                       vocab_size=320, max_position_embeddings=512)
     torch.manual_seed(0)
     model = LlamaForCausalLM(cfg).eval()
-    bc.patch_llama_fft(model, block_size=64, spectrum_dtype=torch.bfloat16)
+    bc.patch_llama_fft(model, block_size=64, spectrum_dtype=sdt)
     model = model.to(DEV).half()
     ids = torch.randint(0, 320, (4, 96), device=DEV)
     monkeypatch.setattr(P, "PREFILL_MIN_TOKENS", 256)
+    monkeypatch.setattr(P, "PREFILL_MIN_TOKENS_F32", 256)
     with torch.no_grad():
         ref = model(input_ids=ids).logits.float()
         assert bc.fuse_mlp(model) == 2
@@ -312,7 +348,7 @@ def test_fuse_mlp_prefill_path_in_a_tiny_llama(monkeypatch):
         assert [f.fused_prefill_calls for f in fused] == [1, 1] and [f.fused_calls for f in fused] == [0, 0]
         bc.unfuse_mlp(model)
     assert P.prefill_status(DEV) == 0
-    assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= tol * ref.abs().max().item()
 
 
 def test_prefill_swiglu_stage_at_full_size():
