@@ -123,4 +123,11 @@ __device__ inline void fill_twiddles(float2* tw, int tid, int nthreads) {
 __device__ inline float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ inline float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a * conj(b)
 
+// Packed fp32 arithmetic (PTX fma.rn.f32x2 -> SASS FFMA2, sm_100): two independent IEEE fma.rn per issue slot.  pack2 / unpack2 are
+// register-pair moves that ptxas folds into the instruction's operand modifiers (R.F32 = broadcast of one register, .LO_HI = swapped
+// pair), so pack2(c, c) and pack2(x.y, x.x) cost nothing.  Each half rounds exactly like the scalar fmaf.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void ffma2(uint64_t& acc, uint64_t a, uint64_t b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+
 }  // namespace bcl

@@ -170,13 +170,17 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                 // Independent accumulator chains: the two products of every complex MAC go to separate sums (pos / neg) and even / odd
                 // blocks to separate sets, so consecutive FMAs never depend on each other (a single chain per packed real made the
                 // row warp issue one FMA per ~4-5 cycles: 2.3k cycles per row, clock stamps).
-                float sp[2][CH][CW], sn[2][CH][CW];
+                // Packed fp32 FMAs (fma.rn.f32x2 -> FFMA2, sm_100): p1 = (Σ cr xre, Σ cr xim), p2 = (Σ ci xim, Σ ci xre) per complex bin; the
+                // broadcast of cr / ci and the (xim, xre) swap are operand modifiers of the SASS instruction (.F32, .LO_HI), so a complex MAC
+                // is 2 issue slots instead of 4 -- this kernel is issue-bound (ncu: ALU 42 %, issue 51 %, HBM 34 %), and every lane of the
+                // packed FMA rounds like the scalar one: the sums are bit-identical to the four-FMA form.
+                uint64_t p1[2][CH][CW / 2], p2[2][CH][CW / 2];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
 #pragma unroll
                     for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-                        for (int e = 0; e < CW; ++e) { sp[h][ch][e] = 0.f; sn[h][ch][e] = 0.f; }
+                        for (int e = 0; e < CW / 2; ++e) { p1[h][ch][e] = 0ull; p2[h][ch][e] = 0ull; }
                 }
                 for (int cs = 0; cs < nst; ++cs, ++idx) {
                     while (bars->chunk_in[stage] != idx) __nanosleep(128);   // my chunk's turn in this stage (see Barriers)
@@ -218,19 +222,27 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
 #pragma unroll
                                 for (int e = 0; e < CW; e += 2) {
                                     const float cr = cv[e], ci = cv[e + 1], xre = xv[u][ch][e], xim = xv[u][ch][e + 1];
-                                    sp[h][ch][e] = fmaf(cr, xre, sp[h][ch][e]);             // Re: cr xre - ci xim
-                                    sn[h][ch][e] = fmaf(ci, xim, sn[h][ch][e]);
-                                    sp[h][ch][e + 1] = fmaf(cr, xim, sp[h][ch][e + 1]);     // Im: cr xim + ci xre
-                                    sn[h][ch][e + 1] = fmaf(ci, xre, sn[h][ch][e + 1]);
+                                    ffma2(p1[h][ch][e / 2], pack2(cr, cr), pack2(xre, xim));    // (cr xre, cr xim)
+                                    ffma2(p2[h][ch][e / 2], pack2(ci, ci), pack2(xim, xre));    // (ci xim, ci xre)
                                 }
                             }
-                            // packed slot 0/1 of lane 0 is (DC, Nyquist): real x real products, already in sp[..][0][0] and sn[..][0][0]
+                            // packed slot 0/1 of lane 0 is (DC, Nyquist): real x real products, already in p1[..][0][0].lo and p2[..][0][0].lo
                         }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->empty[stage]);   // the producer may refill this stage
                     if (++stage == S) { stage = 0; ph ^= 1u; }
                 }
+                float sp[2][CH][CW], sn[2][CH][CW];
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+                        for (int e = 0; e < CW; e += 2) {
+                            unpack2(p1[h][ch][e / 2], sp[h][ch][e], sp[h][ch][e + 1]);
+                            unpack2(p2[h][ch][e / 2], sn[h][ch][e], sn[h][ch][e + 1]);
+                        }
                 RowAcc<B, NT> acc;
 #pragma unroll
                 for (int ch = 0; ch < CH; ++ch)
