@@ -35,6 +35,43 @@ __host__ __device__ constexpr int brev_n(int k, int n) {            // bit rever
     return r;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Packed complex arithmetic (BCL_FFT_PACKED=1, an A/B build switch, default OFF): a complex value is an aligned register pair and every
+// complex add / sub / scale is ONE instruction (add / mul / fma .f32x2 -> FADD2 / FMUL2 / FFMA2 on sm_100), a complex multiply two.
+// The sign flips, the (re, im) swaps and the scalar broadcasts below are written as pack2() of plain floats: ptxas folds them into
+// the instruction's operand modifiers (.F32 broadcast, .LO_HI swap, .NP / .PN per-half negation), they are not instructions.
+// MEASURED (round 2, B200): parity green (426 GPU tests), 2.7x fewer floating-point instructions in the transforms -- and SLOWER:
+// fp32 decode step 36.9 -> 39.0 us, bf16 28.4 -> 29.2 us.  The transforms are dependent chains in single warps (latency-bound, DESIGN
+// 3.3), and a packed operation occupies the fp32 pipe for two passes with a longer dependent-issue latency than the scalar one, so
+// halving the instruction count lengthens the critical path.  Packed FMAs pay where the work is throughput-bound and independent:
+// the MAC loop of bcl_stream_rw.cu (29.4 -> 28.4 us).
+// ---------------------------------------------------------------------------------------------------------
+#ifndef BCL_FFT_PACKED
+#define BCL_FFT_PACKED 0
+#endif
+__device__ __forceinline__ uint64_t p2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t p2_sub(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t p2_mul(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t p2_fma(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float2 p2_out(uint64_t v) { float2 r; unpack2(v, r.x, r.y); return r; }
+__device__ __forceinline__ uint64_t p2_in(float2 a) { return pack2(a.x, a.y); }
+#if BCL_FFT_PACKED
+__device__ __forceinline__ float2 c_add(float2 a, float2 b) { return p2_out(p2_add(p2_in(a), p2_in(b))); }
+__device__ __forceinline__ float2 c_sub(float2 a, float2 b) { return p2_out(p2_sub(p2_in(a), p2_in(b))); }
+__device__ __forceinline__ float2 c_scale(float2 a, float s) { return p2_out(p2_mul(p2_in(a), pack2(s, s))); }
+// a * w = (ax wr - ay wi, ax wi + ay wr)
+__device__ __forceinline__ float2 c_mul(float2 a, float2 w) { return p2_out(p2_fma(pack2(a.y, a.y), pack2(-w.y, w.x), p2_mul(pack2(a.x, a.x), p2_in(w)))); }
+// a * conj(w) = (ax wr + ay wi, -ax wi + ay wr)
+__device__ __forceinline__ float2 c_mulc(float2 a, float2 w) { return p2_out(p2_fma(pack2(a.y, a.y), pack2(w.y, w.x), p2_mul(pack2(a.x, a.x), pack2(w.x, -w.y)))); }
+#else
+__device__ __forceinline__ float2 c_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 c_scale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float2 c_mul(float2 a, float2 w) { return cmul(a, w); }
+__device__ __forceinline__ float2 c_mulc(float2 a, float2 w) { return cmulc(a, w); }
+#endif
+
 // exp(-2 pi i k / 16), k = 0..7 (compile-time: every use is in a fully unrolled loop)
 __device__ __forceinline__ constexpr float tw16_re(int k) {
     constexpr float t[8] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f, 0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
@@ -56,13 +93,23 @@ __device__ __forceinline__ void fft_reg(float2 (&a)[N]) {
             const int i0 = (b / half) * 2 * half + pos, i1 = i0 + half;
             const int k16 = pos * (8 / half);                       // w_{2 half}^{pos} = w_16^{k16}
             const float2 u = a[i0], v = a[i1];
-            a[i0] = make_float2(u.x + v.x, u.y + v.y);
-            const float dx = u.x - v.x, dy = u.y - v.y;
-            if (k16 == 0) a[i1] = make_float2(dx, dy);
+            a[i0] = c_add(u, v);
+            const float2 d = c_sub(u, v);
+            const float dx = d.x, dy = d.y;
+            if (k16 == 0) a[i1] = d;
             else if (k16 == 4) a[i1] = INV ? make_float2(-dy, dx) : make_float2(dy, -dx);        // * (-i)  /  * (+i)
+#if BCL_FFT_PACKED
+            else if (k16 == 2) {                                     // w = s (1 -+ i): one packed add of the rotated pair, one scale
+                constexpr float sq = 0.70710678118654752f;
+                a[i1] = INV ? c_scale(c_add(d, make_float2(-dy, dx)), sq) : c_scale(c_add(d, make_float2(dy, -dx)), sq);
+            } else if (k16 == 6) {                                   // w = -s (1 +- i)
+                constexpr float sq = 0.70710678118654752f;
+                a[i1] = INV ? c_scale(c_sub(make_float2(-dy, dx), d), sq) : c_scale(c_sub(make_float2(dy, -dx), d), sq);
+            }
+#endif
             else {
                 const float wr = tw16_re(k16), wi = INV ? -tw16_im(k16) : tw16_im(k16);
-                a[i1] = make_float2(dx * wr - dy * wi, dx * wi + dy * wr);
+                a[i1] = c_mul(d, make_float2(wr, wi));
             }
         }
     }
@@ -91,7 +138,7 @@ __device__ __forceinline__ void group_rfft_packed(float2 (&a)[FftCfg<B>::V], flo
 #pragma unroll
     for (int k1 = 0; k1 < V; ++k1) {
         float2 A = a[brev_n(k1, V)];
-        if (k1 > 0) A = cmul(A, twiddle_m<B>(tw, t * k1));
+        if (k1 > 0) A = c_mul(A, twiddle_m<B>(tw, t * k1));
         scr[k1 * PITCH + t] = A;
     }
     __syncwarp();
@@ -123,11 +170,12 @@ __device__ __forceinline__ void group_rfft_packed(float2 (&a)[FftCfg<B>::V], flo
     float2 xa[C::NPAIR], xb[C::NPAIR];
 #pragma unroll
     for (int it = 0; it < C::NPAIR; ++it) {
-        const float2 e = make_float2(0.5f * (zk[it].x + zm[it].x), 0.5f * (zk[it].y - zm[it].y));
-        const float2 d = make_float2(0.5f * (zk[it].x - zm[it].x), 0.5f * (zk[it].y + zm[it].y));
-        const float2 wd = cmul(wk[it], d);
-        xa[it] = make_float2(e.x + wd.y, e.y - wd.x);
-        xb[it] = make_float2(e.x - wd.y, -(e.y + wd.x));
+        const float2 cz = make_float2(zm[it].x, -zm[it].y);          // conj(Zm)
+        const float2 e = c_scale(c_add(zk[it], cz), 0.5f);
+        const float2 d = c_scale(c_sub(zk[it], cz), 0.5f);
+        const float2 wd = c_mul(wk[it], d);
+        xa[it] = c_add(e, make_float2(wd.y, -wd.x));
+        xb[it] = c_sub(make_float2(e.x, -e.y), make_float2(wd.y, wd.x));
     }
 #pragma unroll
     for (int it = 0; it < C::NPAIR; ++it) {
@@ -166,11 +214,12 @@ __device__ __forceinline__ void group_irfft_packed(const float* src, float2* scr
     float2 za[C::NPAIR], zb[C::NPAIR];
 #pragma unroll
     for (int it = 0; it < C::NPAIR; ++it) {
-        const float2 e = make_float2(xk[it].x + xm[it].x, xk[it].y - xm[it].y);
-        const float2 d = make_float2(xk[it].x - xm[it].x, xk[it].y + xm[it].y);
-        const float2 o = cmulc(d, wk[it]);
-        za[it] = make_float2(e.x - o.y, e.y + o.x);
-        zb[it] = make_float2(e.x + o.y, -e.y + o.x);
+        const float2 cx = make_float2(xm[it].x, -xm[it].y);          // conj(Xm)
+        const float2 e = c_add(xk[it], cx);
+        const float2 d = c_sub(xk[it], cx);
+        const float2 o = c_mulc(d, wk[it]);
+        za[it] = c_add(e, make_float2(-o.y, o.x));
+        zb[it] = c_add(make_float2(e.x, -e.y), make_float2(o.y, o.x));
     }
 #pragma unroll
     for (int it = 0; it < C::NPAIR; ++it) {
@@ -189,7 +238,7 @@ __device__ __forceinline__ void group_irfft_packed(const float* src, float2* scr
 #pragma unroll
     for (int k1 = 0; k1 < V; ++k1) {
         float2 A = a[brev_n(k1, V)];
-        if (k1 > 0) A = cmulc(A, twiddle_m<B>(tw, t * k1));
+        if (k1 > 0) A = c_mulc(A, twiddle_m<B>(tw, t * k1));
         scr[k1 * PITCH + t] = A;
     }
     __syncwarp();
