@@ -12,6 +12,7 @@
 //   warps 9..12      X warps: rfft(x) of the next segment into the other half of a double-buffered X buffer
 //   warps 13..15     finishers: inverse real FFT of 4 rows at once, 1/B, round to x.dtype, + bias, store y
 #include <cstdlib>
+#include <cstdio>
 #include "bcl_stream_parts.cuh"
 
 namespace bcl {
@@ -30,6 +31,20 @@ constexpr int THREADS = 32 * (1 + NM + NX + NF);
 #endif
 constexpr int MAX_STAGES = BCL_RW_MAX_STAGES;
 __host__ __device__ constexpr int stage_blocks(int B) { return 4096 / B; }       // same chunking as bcl_stream_ws.cu
+
+// -DBCL_RW_TIMING: per-role cycle counters of CTA 3 (printf at the end of the launch; read with tools/small_launch_timing.py or any bench run
+// against a library built with the flag).  Off by default: the macros expand to nothing.
+#ifdef BCL_RW_TIMING
+__device__ inline long long clk() { long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c)); return c; }
+#define TSTART(v) long long v##_t0 = clk()
+#define TSTOP(v, acc) acc += clk() - v##_t0
+#define TPRINT(...) printf(__VA_ARGS__)
+#else
+__device__ inline long long clk() { return 0; }
+#define TSTART(v)
+#define TSTOP(v, acc)
+#define TPRINT(...)
+#endif
 
 // The row warps drift apart (a warp's consecutive rows are NM rows = up to NM * nst ring chunks and two groups apart), so a warp
 // can be MORE than one phase ahead of a barrier -- and a parity wait cannot tell phase n+2 from phase n.  Wherever that can happen
@@ -122,6 +137,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t ph = 0; int idx = 0;
+            long long t_all0 = clk(), t_e = 0; (void)t_all0; (void)t_e;
             for (int s = s0; s < s1; ++s) {
                 const SegWork w = segs[s];
                 const ProblemDev* P = problems + w.g;
@@ -130,7 +146,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                 const unsigned char* rowp = reinterpret_cast<const unsigned char*>(P->spec) + (size_t)w.j0 * q * BLOCK_BYTES;
                 for (int r = w.j0; r < w.j1; ++r, rowp += (size_t)q * BLOCK_BYTES) {
                     for (int cs = 0; cs < nst; ++cs, ++idx) {
-                        mbar_wait(&bars->empty[stage], ph ^ 1u);          // in order and one phase at a time: parity is enough here
+                        { TSTART(e); mbar_wait(&bars->empty[stage], ph ^ 1u); TSTOP(e, t_e); }   // in order and one phase at a time: parity is enough here
                         bars->chunk_in[stage] = idx;                     // from now on full[stage] is in this chunk's phase (the store cannot pass the
                                                                          // acquiring wait above; nothing else is ordered by it: no fence, the producer
                                                                          // thread's ~300 cycles per copy are the scarce resource here)
@@ -141,15 +157,19 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                     }
                 }
             }
+            if (blockIdx.x == 3) TPRINT("producer: total %lld wait_empty %lld chunks %d\n", clk() - t_all0, t_e, idx);
         }
     } else if (warp <= NM) {
         // ===================== row warps =====================
         const int m = warp - 1;
+        long long t_all0 = clk(), t_x = 0, t_f = 0, t_g = 0, t_mac = 0, t_first = 0; int nrows = 0;
+        (void)t_all0; (void)t_x; (void)t_f; (void)t_g; (void)t_mac; (void)t_first; (void)nrows;
         if (s0 < s1) {                                               // first segment: help with rfft(x) (start-up latency, HBM idles)
             const ProblemDev P0 = problems[segs[s0].g];              // plan data: constant, fetched while the previous grid drains
             pdl_wait();
             load_x_spectrum<B, NT, NM + NX>(P0, 0, xs_all, tw, row_scr + (size_t)m * (FC::WARP_SCRATCH_BYTES / 8), lane, m);
             asm volatile("bar.sync 1, %0;" ::"r"(32 * (NM + NX)) : "memory");
+            t_first = clk() - t_all0;
         }
         int chunk0 = 0;                                              // ring chunk index of the segment's first chunk (CTA-wide sequence)
         int row0 = 0;                                                // running row index of the segment's first row
@@ -161,7 +181,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
             const int nst = (q + CB - 1) / CB;
             const int k = s - s0;
             const float* xs = xs_all + (size_t)(k & 1) * xs_stride;
-            if (k > 0) mbar_wait(&bars->xfull[k & 1], (uint32_t)((k - 1) >> 1) & 1u);      // buffer 1: segments 1,3,..; buffer 0: 2,4,.. (0 was cooperative)
+            if (k > 0) { TSTART(x); mbar_wait(&bars->xfull[k & 1], (uint32_t)((k - 1) >> 1) & 1u); TSTOP(x, t_x); }      // buffer 1: segments 1,3,..; buffer 0: 2,4,.. (0 was cooperative)
             // my rows of this segment: (row0 + r) % NM == m
             int r = (m - (row0 % NM) + NM) % NM;
             for (; r < rows; r += NM) {
@@ -183,8 +203,11 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                         for (int e = 0; e < CW / 2; ++e) { p1[h][ch][e] = 0ull; p2[h][ch][e] = 0ull; }
                 }
                 for (int cs = 0; cs < nst; ++cs, ++idx) {
+                    { TSTART(f);
                     while (bars->chunk_in[stage] != idx) __nanosleep(128);   // my chunk's turn in this stage (see Barriers)
                     mbar_wait(&bars->full[stage], ph);
+                    TSTOP(f, t_f); }
+                    TSTART(mac);
                     const SpecT* cbuf = reinterpret_cast<const SpecT*>(ring + (size_t)stage * STAGE_BYTES);
                     const int nblk = min(CB, q - cs * CB);
                     const float* xrow = xs + (size_t)cs * CB * B;
@@ -232,7 +255,9 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->empty[stage]);   // the producer may refill this stage
                     if (++stage == S) { stage = 0; ph ^= 1u; }
+                    TSTOP(mac, t_mac);
                 }
+                ++nrows;
                 float sp[2][CH][CW], sn[2][CH][CW];
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
@@ -256,7 +281,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                 // park the finished row spectrum; the group's finisher starts when all its rows have arrived
                 const int gi = grp0 + r / RG;
                 const int gb = gi % NF;
-                while (bars->accepts[gb] != gi) __nanosleep(128);      // the finisher has drained the buffer's previous group
+                { TSTART(g); while (bars->accepts[gb] != gi) __nanosleep(128); TSTOP(g, t_g); }     // the finisher has drained the buffer's previous group
                 __threadfence_block();
                 store_partial<B, NT, 1>(acc, part + (size_t)gb * RG * B, r % RG, 0, lane);
                 __syncwarp();
@@ -271,6 +296,9 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
             row0 += rows;
             grp0 += (rows + RG - 1) / RG;
         }
+        if (blockIdx.x == 3 && lane == 0 && (m == 0 || m == NM - 1))
+            TPRINT("row warp %d: total %lld first_x %lld wait_x %lld wait_chunk %lld mac %lld wait_group %lld rows %d segs %d\n", m, clk() - t_all0, t_first, t_x, t_f, t_mac, t_g,
+                   nrows, s1 - s0);
     } else if (warp <= NM + NX) {
         // ===================== X warps: rfft(x) of each segment into the other X buffer, one segment ahead of the row warps ======
         const int xw = warp - 1 - NM;
@@ -296,21 +324,25 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
         float2* fscr = fscr_all + (size_t)(NX + f) * (FC::WARP_SCRATCH_BYTES / 8);
         pdl_wait();                                                      // y may still be read by the previous grid
         int gi = 0;
+        long long t_all0 = clk(), t_w = 0, t_b = 0; int ngr = 0; (void)t_all0; (void)t_w; (void)t_b; (void)ngr;
         for (int s = s0; s < s1; ++s) {
             const SegWork w = segs[s];
             const ProblemDev P = problems[w.g];
             const int rows = w.j1 - w.j0;
             for (int g0 = 0; g0 < rows; g0 += RG, ++gi) {
                 if (gi % NF != f) continue;
-                mbar_wait(&bars->gfull[f], (uint32_t)(gi / NF) & 1u);
+                { TSTART(w); mbar_wait(&bars->gfull[f], (uint32_t)(gi / NF) & 1u); TSTOP(w, t_w); }
+                TSTART(b); ++ngr;
                 const int nr = min(RG, rows - g0);
                 float* gpart = part + (size_t)f * RG * B;
                 for (int p0 = 0; p0 < nr; p0 += FC::G)
                     finish_pairs<B, NT, 1>(P, w.j0 + g0, 0, gpart + (size_t)p0 * B, p0, min(FC::G, nr - p0), tw, fscr, lane);
                 __syncwarp();
                 if (lane == 0) { __threadfence_block(); bars->accepts[f] = gi + NF; }     // the buffer takes group gi + NF next
+                TSTOP(b, t_b);
             }
         }
+        if (blockIdx.x == 3 && lane == 0) TPRINT("finisher %d: total %lld wait_gfull %lld busy %lld groups %d\n", f, clk() - t_all0, t_w, t_b, ngr);
     }
 }
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Per-kernel counts of the Blackwell-specific SASS instructions in libbclinear.so (cuobjdump -sass):
 UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG / UTMASTG (TMA tensor load / store), UBLKCP (1-D bulk copy), UTCBAR (tcgen05.commit),
-SYNCS (mbarrier), plus FFMA as the CUDA-core reference.  Writes a table to stdout; `> profiles/rN_sass_summary.txt`."""
+SYNCS (mbarrier), FFMA2 (packed fp32 FMA, sm_100), plus FFMA as the CUDA-core reference.  Writes a table to stdout; `> profiles/rN_sass_summary.txt`."""
 import collections
 import os
 import re
@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "llama-fft_b200", "libbclinear.so")
-OPS = ["UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "UTMAPF", "SYNCS", "FFMA", "REDG", "LDG", "STG"]
+OPS = ["UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "UTMAPF", "SYNCS", "FFMA2", "FFMA", "REDG", "LDG", "STG"]   # (FFMA2 = packed fma.rn.f32x2, before its prefix FFMA)
 
 
 def demangle(names):
