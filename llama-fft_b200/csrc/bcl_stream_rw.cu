@@ -7,10 +7,10 @@
 // the kernel (clock stamps: profiles/r1_prefill_notes.md).  Here a MAC warp multiplies a WHOLE row: lane l accumulates its
 // packed reals of all q blocks of C_f[row] (ring) times X_f (shared memory) in registers, parks ONE finished spectrum per row,
 // and the finisher only inverse-transforms.  Eight rows are in flight per CTA; the hand-offs per row drop eightfold.
-//   warp 0           TMA producer (identical ring protocol: one bulk copy per (row, stage-of-row))
-//   warps 1..8       row warps: rows r = m, m + 8, ... of the CTA's running row sequence
-//   warps 9..12      X warps: rfft(x) of the next segment into the other half of a double-buffered X buffer
-//   warps 13..15     finishers: inverse real FFT of 4 rows at once, 1/B, round to x.dtype, + bias, store y
+//   NP = 3 warps     TMA producers (identical ring protocol: one bulk copy per (row, stage-of-row); producer w takes chunks w mod NP)
+//   next 8 warps     row warps: rows r = m, m + 8, ... of the CTA's running row sequence
+//   next 4 warps     X warps: rfft(x) of the next segment into the other half of a double-buffered X buffer
+//   last 3 warps     finishers: inverse real FFT of 4 rows at once, 1/B, round to x.dtype, + bias, store y
 #include <cstdlib>
 #include <cstdio>
 #include "bcl_stream_parts.cuh"
@@ -24,8 +24,29 @@ namespace rw {
 #ifndef BCL_RW_NX
 #define BCL_RW_NX 4
 #endif
+#ifndef BCL_RW_NG
+#define BCL_RW_NG 3
+#endif
+// NG group buffers for NF finishers (NG a multiple of NF, so a buffer always belongs to the same finisher).  With one buffer per
+// finisher a row warp whose group's buffer is still being transformed stalls 4-5k cycles per step (-DBCL_RW_TIMING); with NG = 6
+// that wait disappears (0.8k) -- and reappears as a wait for ring chunks: measured 28.6 (NG = 3) / 29.0 (6) / 29.0 (9) / 29.2 us (12).
+// The default stays one buffer per finisher.
+constexpr int NG = BCL_RW_NG;
+static_assert(NG % BCL_RW_NF == 0, "group buffers: a multiple of the finisher count");
+#ifndef BCL_RW_NP
+#define BCL_RW_NP 3
+#endif
+// NP producer warps: producer w issues the ring chunks idx = w (mod NP).  One thread needs ~370 cycles per bulk copy (~40 dependent
+// instructions: wait, sequence number, expect_tx, the elect / R2UR sequence around UBLKCP; -DBCL_RW_TIMING: 32k busy cycles for 88
+// chunks), i.e. 8 KB per 370 cycles = 22 B/clk, just the HBM share of an SM -- and it waits in order, so one late stage holds up the
+// copies behind it.  The number of stages is a multiple of NP, so a stage always belongs to the same producer and the parity waits
+// stay valid.  Measured (bf16, 224 projections): NP = 1: 28.6 us, 2: 28.4, 3: 27.2, 4: 28.0 (every extra warp costs the others: above 16
+// warps an SM sub-partition holds five and the register cap drops from 128 to 96).  ONE producer warp whose lane l owns stage l and polls
+// its empty barrier (copies of all free stages issued in one pass, built and measured): 29.9 us -- a pass costs the same ~40
+// instructions whether one lane or ten issue, and the lanes that are not ready make the warp sleep.
+constexpr int NP = BCL_RW_NP;
 constexpr int NM = 8, NX = BCL_RW_NX, NF = BCL_RW_NF, RG = 4;       // NF = 4 and 6 measured slower (32.9, 34.2 us vs 31.5 us: fewer registers, smaller ring)
-constexpr int THREADS = 32 * (1 + NM + NX + NF);
+constexpr int THREADS = 32 * (NP + NM + NX + NF);
 #ifndef BCL_RW_MAX_STAGES
 #define BCL_RW_MAX_STAGES 16
 #endif
@@ -53,11 +74,11 @@ __device__ inline long long clk() { return 0; }
 struct Barriers {
     uint64_t full[MAX_STAGES];      // ring stage filled by TMA                      (1 arrival + tx bytes)
     uint64_t empty[MAX_STAGES];     // ring stage released by the ONE row warp that owns it
-    uint64_t gfull[NF];             // group buffer complete                          (RG arrivals: one per row)
+    uint64_t gfull[NG];             // group buffer complete                          (RG arrivals: one per row)
     uint64_t xfull[2];              // x spectrum of a segment ready in X buffer k    (NX arrivals)
     uint64_t xempty[2];             // every row warp is done with X buffer k          (NM arrivals)
     volatile int chunk_in[MAX_STAGES];
-    volatile int accepts[NF];
+    volatile int accepts[NG];
 };
 static_assert(sizeof(Barriers) <= 512, "barrier block");
 
@@ -109,12 +130,12 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
     Barriers* bars = reinterpret_cast<Barriers*>(smem_raw);
     float2* tw = reinterpret_cast<float2*>(smem_raw + 512);
     unsigned char* ring = smem_raw + 512 + 1024;
-    float* part = reinterpret_cast<float*>(ring + (size_t)S * STAGE_BYTES);                         // [NF][RG][B]: finished row spectra
+    float* part = reinterpret_cast<float*>(ring + (size_t)S * STAGE_BYTES);                         // [NG][RG][B]: finished row spectra
     // FFT scratch: the X warps and the finishers own theirs; the row warps only transform during the cooperative first segment, when X
     // buffer 1 is still unused (the X warps write it after the bar.sync that ends that phase) -- so their scratch aliases it when it
     // is large enough, which buys two more ring stages for Llama shapes (9 -> 12 stages was worth 3 us of 34: the ring is what
     // bounds this kernel).
-    float2* fscr_all = reinterpret_cast<float2*>(part + NF * RG * B);                               // scratch of NX + NF warps (+ NM if not aliased)
+    float2* fscr_all = reinterpret_cast<float2*>(part + NG * RG * B);                               // scratch of NX + NF warps (+ NM if not aliased)
     const bool alias_scr = scratch_aliases_x(B, qmax);
     float* xs_all = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(fscr_all) + (size_t)(NX + NF + (alias_scr ? 0 : NM)) * FC::WARP_SCRATCH_BYTES);   // [2][qmax][B]
     const size_t xs_stride = (size_t)qmax * B;
@@ -123,7 +144,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); bars->chunk_in[s] = -1; }
-        for (int g = 0; g < NF; ++g) { mbar_init(&bars->gfull[g], RG); bars->accepts[g] = g; }
+        for (int g = 0; g < NG; ++g) { mbar_init(&bars->gfull[g], RG); bars->accepts[g] = g; }
         for (int k = 0; k < 2; ++k) { mbar_init(&bars->xfull[k], NX); mbar_init(&bars->xempty[k], NM); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -133,8 +154,8 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
 
     const int s0 = cta_seg_ptr[blockIdx.x], s1 = cta_seg_ptr[blockIdx.x + 1];
 
-    if (warp == 0) {
-        // ===================== TMA producer =====================
+    if (warp < NP) {
+        // ===================== TMA producers =====================
         if (lane == 0) {
             int stage = 0; uint32_t ph = 0; int idx = 0;
             long long t_all0 = clk(), t_e = 0; (void)t_all0; (void)t_e;
@@ -146,6 +167,10 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                 const unsigned char* rowp = reinterpret_cast<const unsigned char*>(P->spec) + (size_t)w.j0 * q * BLOCK_BYTES;
                 for (int r = w.j0; r < w.j1; ++r, rowp += (size_t)q * BLOCK_BYTES) {
                     for (int cs = 0; cs < nst; ++cs, ++idx) {
+                        if (NP > 1 && idx % NP != warp) {                 // another producer's chunk
+                            if (++stage == S) { stage = 0; ph ^= 1u; }
+                            continue;
+                        }
                         { TSTART(e); mbar_wait(&bars->empty[stage], ph ^ 1u); TSTOP(e, t_e); }   // in order and one phase at a time: parity is enough here
                         bars->chunk_in[stage] = idx;                     // from now on full[stage] is in this chunk's phase (the store cannot pass the
                                                                          // acquiring wait above; nothing else is ordered by it: no fence, the producer
@@ -157,11 +182,11 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                     }
                 }
             }
-            if (blockIdx.x == 3) TPRINT("producer: total %lld wait_empty %lld chunks %d\n", clk() - t_all0, t_e, idx);
+            if (blockIdx.x == 3) TPRINT("producer %d: total %lld wait_empty %lld chunks %d\n", warp, clk() - t_all0, t_e, idx);
         }
-    } else if (warp <= NM) {
+    } else if (warp < NP + NM) {
         // ===================== row warps =====================
-        const int m = warp - 1;
+        const int m = warp - NP;
         long long t_all0 = clk(), t_x = 0, t_f = 0, t_g = 0, t_mac = 0, t_first = 0; int nrows = 0;
         (void)t_all0; (void)t_x; (void)t_f; (void)t_g; (void)t_mac; (void)t_first; (void)nrows;
         if (s0 < s1) {                                               // first segment: help with rfft(x) (start-up latency, HBM idles)
@@ -280,7 +305,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
                 acc.ny[0] = sn[0][0][0] + sn[1][0][0];               //         Nyquist = sum C_ny X_ny (= the ci*xim sum of slot 0)
                 // park the finished row spectrum; the group's finisher starts when all its rows have arrived
                 const int gi = grp0 + r / RG;
-                const int gb = gi % NF;
+                const int gb = gi % NG;
                 { TSTART(g); while (bars->accepts[gb] != gi) __nanosleep(128); TSTOP(g, t_g); }     // the finisher has drained the buffer's previous group
                 __threadfence_block();
                 store_partial<B, NT, 1>(acc, part + (size_t)gb * RG * B, r % RG, 0, lane);
@@ -299,9 +324,9 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
         if (blockIdx.x == 3 && lane == 0 && (m == 0 || m == NM - 1))
             TPRINT("row warp %d: total %lld first_x %lld wait_x %lld wait_chunk %lld mac %lld wait_group %lld rows %d segs %d\n", m, clk() - t_all0, t_first, t_x, t_f, t_mac, t_g,
                    nrows, s1 - s0);
-    } else if (warp <= NM + NX) {
+    } else if (warp < NP + NM + NX) {
         // ===================== X warps: rfft(x) of each segment into the other X buffer, one segment ahead of the row warps ======
-        const int xw = warp - 1 - NM;
+        const int xw = warp - NP - NM;
         float2* fscr = fscr_all + (size_t)xw * (FC::WARP_SCRATCH_BYTES / 8);
         ProblemDev P0{};
         if (s0 < s1) P0 = problems[segs[s0].g];                          // plan data: constant, fetched while the previous grid drains
@@ -320,7 +345,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
         }
     } else {
         // ===================== finishers =====================
-        const int f = warp - 1 - NM - NX;
+        const int f = warp - NP - NM - NX;
         float2* fscr = fscr_all + (size_t)(NX + f) * (FC::WARP_SCRATCH_BYTES / 8);
         pdl_wait();                                                      // y may still be read by the previous grid
         int gi = 0;
@@ -331,14 +356,15 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
             const int rows = w.j1 - w.j0;
             for (int g0 = 0; g0 < rows; g0 += RG, ++gi) {
                 if (gi % NF != f) continue;
-                { TSTART(w); mbar_wait(&bars->gfull[f], (uint32_t)(gi / NF) & 1u); TSTOP(w, t_w); }
+                const int gb = gi % NG;
+                { TSTART(w); mbar_wait(&bars->gfull[gb], (uint32_t)(gi / NG) & 1u); TSTOP(w, t_w); }
                 TSTART(b); ++ngr;
                 const int nr = min(RG, rows - g0);
-                float* gpart = part + (size_t)f * RG * B;
+                float* gpart = part + (size_t)gb * RG * B;
                 for (int p0 = 0; p0 < nr; p0 += FC::G)
                     finish_pairs<B, NT, 1>(P, w.j0 + g0, 0, gpart + (size_t)p0 * B, p0, min(FC::G, nr - p0), tw, fscr, lane);
                 __syncwarp();
-                if (lane == 0) { __threadfence_block(); bars->accepts[f] = gi + NF; }     // the buffer takes group gi + NF next
+                if (lane == 0) { __threadfence_block(); bars->accepts[gb] = gi + NG; }    // the buffer takes group gi + NG next
                 TSTOP(b, t_b);
             }
         }
@@ -350,7 +376,7 @@ size_t smem_bytes(int B, int spec_bytes, int qmax, int S) {
     const size_t fscr = warp_scratch_bytes(B);
     const size_t stage = (size_t)stage_blocks(B) * B * spec_bytes;
     const int scr_warps = NX + NF + (scratch_aliases_x(B, qmax) ? 0 : NM);
-    return 512 + 1024 + (size_t)S * stage + (size_t)NF * RG * B * 4 + (size_t)scr_warps * fscr + (size_t)2 * qmax * B * 4;
+    return 512 + 1024 + (size_t)S * stage + (size_t)NG * RG * B * 4 + (size_t)scr_warps * fscr + (size_t)2 * qmax * B * 4;
 }
 
 int pick_stages(int B, int spec_dtype, int nt, int qmax) {
@@ -360,7 +386,8 @@ int pick_stages(int B, int spec_dtype, int nt, int qmax) {
     const size_t stage = (size_t)stage_blocks(B) * B * 2;
     if (fixed + (size_t)(NM + 1) * stage > budget) return 0;          // eight rows in flight + one stage of prefetch at least
     int S = (int)((budget - fixed) / stage);
-    return S > MAX_STAGES ? MAX_STAGES : S;
+    if (S > MAX_STAGES) S = MAX_STAGES;
+    return S / NP * NP;                                               // a stage always belongs to the same producer
 }
 
 template <int B>
