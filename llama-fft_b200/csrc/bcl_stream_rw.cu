@@ -9,8 +9,8 @@
 // and the finisher only inverse-transforms.  Eight rows are in flight per CTA; the hand-offs per row drop eightfold.
 //   NP = 3 warps     TMA producers (identical ring protocol: one bulk copy per (row, stage-of-row); producer w takes chunks w mod NP)
 //   next 8 warps     row warps: rows r = m, m + 8, ... of the CTA's running row sequence
-//   next 4 warps     X warps: rfft(x) of the next segment into the other half of a double-buffered X buffer
-//   last 3 warps     finishers: inverse real FFT of 4 rows at once, 1/B, round to x.dtype, + bias, store y
+//   next 5 warps     X warps: rfft(x) of the next segment into the other half of a double-buffered X buffer
+//   last 4 warps     finishers: inverse real FFT of 4 rows at once, 1/B, round to x.dtype, + bias, store y
 #include <cstdlib>
 #include <cstdio>
 #include "bcl_stream_parts.cuh"
@@ -18,21 +18,23 @@
 namespace bcl {
 namespace rw {
 
+// Warp mix.  17 to 20 warps put five warps on an SM sub-partition, which caps a thread at 96 registers (16 warps: 128); B = 64 / 128 need
+// 92-93, so once the third producer is there two more warps are free.  Measured at 20 warps, bf16, 224 projections (NP / NX / NF):
+// 3/5/4: 26.1 us, 3/4/4 (19 warps): 26.4, 3/4/5: 26.7, 2/6/4: 27.1, 3/4/3 (18): 27.2, 3/6/3: 27.5, 4/4/4: 28.6, 4/5/3: 28.8, 2/5/5: 28.9.
 #ifndef BCL_RW_NF
-#define BCL_RW_NF 3
+#define BCL_RW_NF 4
 #endif
 #ifndef BCL_RW_NX
-#define BCL_RW_NX 4
+#define BCL_RW_NX 5
 #endif
 #ifndef BCL_RW_NG
-#define BCL_RW_NG 3
+#define BCL_RW_NG BCL_RW_NF
 #endif
 // NG group buffers for NF finishers (NG a multiple of NF, so a buffer always belongs to the same finisher).  With one buffer per
 // finisher a row warp whose group's buffer is still being transformed stalls 4-5k cycles per step (-DBCL_RW_TIMING); with NG = 6
 // that wait disappears (0.8k) -- and reappears as a wait for ring chunks: measured 28.6 (NG = 3) / 29.0 (6) / 29.0 (9) / 29.2 us (12).
 // The default stays one buffer per finisher.
-constexpr int NG = BCL_RW_NG;
-static_assert(NG % BCL_RW_NF == 0, "group buffers: a multiple of the finisher count");
+static_assert(BCL_RW_NG % BCL_RW_NF == 0, "group buffers: a multiple of the finisher count");
 #ifndef BCL_RW_NP
 #define BCL_RW_NP 3
 #endif
@@ -44,9 +46,15 @@ static_assert(NG % BCL_RW_NF == 0, "group buffers: a multiple of the finisher co
 // warps an SM sub-partition holds five and the register cap drops from 128 to 96).  ONE producer warp whose lane l owns stage l and polls
 // its empty barrier (copies of all free stages issued in one pass, built and measured): 29.9 us -- a pass costs the same ~40
 // instructions whether one lane or ten issue, and the lanes that are not ready make the warp sleep.
-constexpr int NP = BCL_RW_NP;
-constexpr int NM = 8, NX = BCL_RW_NX, NF = BCL_RW_NF, RG = 4;       // NF = 4 and 6 measured slower (32.9, 34.2 us vs 31.5 us: fewer registers, smaller ring)
-constexpr int THREADS = 32 * (NP + NM + NX + NF);
+constexpr int NM = 8, RG = 4;
+// B = 256 keeps the 16-warp mix (one producer, 4 X warps, 3 finishers, 128 registers): its transforms need more than the 96
+// registers of the 20-warp tier and the spills cost more than the extra warps bring (11008^2, B = 256: 26.7 us -> 40.3 us with 3/5/4).
+__host__ __device__ constexpr int mix_np(int B) { return B == 256 ? 1 : BCL_RW_NP; }
+__host__ __device__ constexpr int mix_nx(int B) { return B == 256 ? 4 : BCL_RW_NX; }
+__host__ __device__ constexpr int mix_nf(int B) { return B == 256 ? 3 : BCL_RW_NF; }
+__host__ __device__ constexpr int mix_ng(int B) { return B == 256 ? 3 : BCL_RW_NG; }
+__host__ __device__ constexpr int mix_threads(int B) { return 32 * (mix_np(B) + NM + mix_nx(B) + mix_nf(B)); }
+constexpr int NG_MAX = BCL_RW_NG > 3 ? BCL_RW_NG : 3;
 #ifndef BCL_RW_MAX_STAGES
 #define BCL_RW_MAX_STAGES 16
 #endif
@@ -74,11 +82,11 @@ __device__ inline long long clk() { return 0; }
 struct Barriers {
     uint64_t full[MAX_STAGES];      // ring stage filled by TMA                      (1 arrival + tx bytes)
     uint64_t empty[MAX_STAGES];     // ring stage released by the ONE row warp that owns it
-    uint64_t gfull[NG];             // group buffer complete                          (RG arrivals: one per row)
+    uint64_t gfull[NG_MAX];           // group buffer complete                          (RG arrivals: one per row)
     uint64_t xfull[2];              // x spectrum of a segment ready in X buffer k    (NX arrivals)
     uint64_t xempty[2];             // every row warp is done with X buffer k          (NM arrivals)
     volatile int chunk_in[MAX_STAGES];
-    volatile int accepts[NG];
+    volatile int accepts[NG_MAX];
 };
 static_assert(sizeof(Barriers) <= 512, "barrier block");
 
@@ -114,11 +122,12 @@ __host__ __device__ inline size_t warp_scratch_bytes(int B) {
 __host__ __device__ inline bool scratch_aliases_x(int B, int qmax) { return (size_t)qmax * B * 4 >= (size_t)NM * warp_scratch_bytes(B); }
 
 template <int B, typename SpecT>
-__global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev* __restrict__ problems, const int* __restrict__ cta_seg_ptr,
+__global__ void __launch_bounds__(mix_threads(B), 1) stream_rw_kernel(const ProblemDev* __restrict__ problems, const int* __restrict__ cta_seg_ptr,
                                                               const SegWork* __restrict__ segs, int S, int qmax) {
     using LM = LaneMap<B>;
     using FC = FftCfg<B>;
     constexpr int NT = 1;
+    constexpr int NP = mix_np(B), NX = mix_nx(B), NF = mix_nf(B), NG = mix_ng(B), THREADS = mix_threads(B);
     constexpr int CH = LM::CH, CW = LM::CW;
     constexpr int BLOCK_BYTES = B * (int)sizeof(SpecT);
     constexpr int CB = stage_blocks(B);                              // blocks per ring stage
@@ -375,8 +384,8 @@ __global__ void __launch_bounds__(THREADS, 1) stream_rw_kernel(const ProblemDev*
 size_t smem_bytes(int B, int spec_bytes, int qmax, int S) {
     const size_t fscr = warp_scratch_bytes(B);
     const size_t stage = (size_t)stage_blocks(B) * B * spec_bytes;
-    const int scr_warps = NX + NF + (scratch_aliases_x(B, qmax) ? 0 : NM);
-    return 512 + 1024 + (size_t)S * stage + (size_t)NG * RG * B * 4 + (size_t)scr_warps * fscr + (size_t)2 * qmax * B * 4;
+    const int scr_warps = mix_nx(B) + mix_nf(B) + (scratch_aliases_x(B, qmax) ? 0 : NM);
+    return 512 + 1024 + (size_t)S * stage + (size_t)mix_ng(B) * RG * B * 4 + (size_t)scr_warps * fscr + (size_t)2 * qmax * B * 4;
 }
 
 int pick_stages(int B, int spec_dtype, int nt, int qmax) {
@@ -387,7 +396,7 @@ int pick_stages(int B, int spec_dtype, int nt, int qmax) {
     if (fixed + (size_t)(NM + 1) * stage > budget) return 0;          // eight rows in flight + one stage of prefetch at least
     int S = (int)((budget - fixed) / stage);
     if (S > MAX_STAGES) S = MAX_STAGES;
-    return S / NP * NP;                                               // a stage always belongs to the same producer
+    return S / mix_np(B) * mix_np(B);                                 // a stage always belongs to the same producer
 }
 
 template <int B>
@@ -399,7 +408,7 @@ static cudaError_t launch_t(const GroupPlanHeader& H, const unsigned char* d, cu
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)H.num_ctas);
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3(mix_threads(B));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
