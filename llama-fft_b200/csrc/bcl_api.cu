@@ -352,9 +352,9 @@ int bcl_group_plan_encode_layout(const bcl_problem* problems, int count, int B, 
     int nt = 1; while (nt < maxN) nt *= 2;
     const char* force = getenv("BCL_GROUP_VARIANT");                 // "plain" | "ws": A/B switch for profiling only
     int variant = bcl::stream_ws_supported(B, spec_dtype, nt, qmax) ? 1 : 0;
-    if (variant == 1 && bcl::stream_rw_supported(B, spec_dtype, nt, qmax)) variant = 2;     // bf16 spectra: row-per-warp kernel
+    if (bcl::stream_rw_supported(B, spec_dtype, nt, qmax)) variant = 2;                      // bf16 spectra: row-per-warp kernel (its own shape limits)
     if (force && !strcmp(force, "plain")) variant = 0;
-    if (force && !strcmp(force, "ws") && variant == 2) variant = 1;
+    if (force && !strcmp(force, "ws") && variant == 2 && bcl::stream_ws_supported(B, spec_dtype, nt, qmax)) variant = 1;
     const int gran = layout == BCL_LAYOUT_DECODE_TC ? 8 : 1;        // block-rows per work unit (DECODE_TC: 8-row groups of the operand image)
     if (layout == BCL_LAYOUT_DECODE_TC) {
         if (!bcl::stream_tc_supported(B, spec_dtype, nt, qmax))

@@ -614,7 +614,14 @@ size_t smem_bytes(int B, int spec_bytes, int qmax, int S) {
 int pick_stages(int B, int spec_dtype, int nt, int qmax) {
     if (nt != 1) return 0;                                           // decode path: one token per problem
     const int sb = spec_dtype == BCL_F32 ? 4 : 2;
-    if (qmax > 4 * stage_blocks(B, sb) || (qmax + NM - 1) / NM > 16) return 0;   // x slice must fit the MAC warps' registers (RS <= 4, KX <= 16)
+    // x slice must fit the MAC warps' registers: RS <= 4 and KX <= 16 blocks of 4 (B = 128) or 8 (B = 256) reals per lane; a block of
+    // B = 64 is 2 reals per lane, so 32 of them are the same 64 registers (11008-wide inputs at B = 64: q = 172, KX = 22)
+    if (qmax > 4 * stage_blocks(B, sb) || (qmax + NM - 1) / NM > (B == 64 ? 32 : 16)) return 0;
+    if (stage_blocks(B, sb) / NM > 4) {                              // wider stages: the instances launch_b has (RS <= min(3, KXMAX / BPS))
+        const int bps = stage_blocks(B, sb) / NM, kxmax = B == 64 ? 32 : 16;
+        const int rsmax = kxmax / bps > 0 ? (kxmax / bps > 3 ? 3 : kxmax / bps) : 1;
+        if ((qmax + stage_blocks(B, sb) - 1) / stage_blocks(B, sb) > rsmax) return 0;
+    }
     const size_t budget = 227 * 1024;
     const size_t fixed = smem_bytes(B, sb, qmax, 0);
     const size_t stage = (size_t)stage_blocks(B, sb) * B * sb;
@@ -678,14 +685,18 @@ static cudaError_t launch_b(const GroupPlanHeader& H, const unsigned char* d, cu
             case 3: return launch_t<B, SpecT, 3, 3 * BPS>(H, d, st);
             default: return launch_t<B, SpecT, 4, 4 * BPS>(H, d, st);
         }
-    } else {                                                         // wider stages: bound the register slice by the plan's qmax (KX <= 16)
-        constexpr int RSMAX = 16 / BPS > 0 ? 16 / BPS : 1;
-        if (rs > RSMAX || kx > 16) return cudaErrorInvalidValue;
+    } else {                                                         // wider stages: bound the register slice by the plan's qmax (KX <= KXMAX)
+        constexpr int KXMAX = B == 64 ? 32 : 16;                     // (pick_stages: the same 64 registers per lane)
+        constexpr int RSMAX = KXMAX / BPS > 0 ? (KXMAX / BPS > 3 ? 3 : KXMAX / BPS) : 1;
+        if (rs > RSMAX || kx > KXMAX) return cudaErrorInvalidValue;
         if (rs == 1) return kx <= BPS / 2 ? launch_t<B, SpecT, 1, BPS / 2>(H, d, st) : launch_t<B, SpecT, 1, BPS>(H, d, st);
         if constexpr (RSMAX >= 2) {
-            if (kx <= BPS + BPS / 2) return launch_t<B, SpecT, 2, BPS + BPS / 2>(H, d, st);
-            return launch_t<B, SpecT, 2, 2 * BPS>(H, d, st);
+            if (rs == 2) {
+                if (kx <= BPS + BPS / 2) return launch_t<B, SpecT, 2, BPS + BPS / 2>(H, d, st);
+                return launch_t<B, SpecT, 2, 2 * BPS>(H, d, st);
+            }
         }
+        if constexpr (RSMAX >= 3) return launch_t<B, SpecT, 3, 3 * BPS>(H, d, st);      // B = 64, fp32 spectra, 128 < q <= 192
         return cudaErrorInvalidValue;
     }
 }

@@ -77,6 +77,34 @@ def _decode(blob):
                 off_ctr=off_ctr, dyn=dyn, total=int(total)), cta_ptr, segs
 
 
+def _variant(shape, B, sdt):
+    L = _cabi.lib()
+    p, q = shape
+    probs = (_cabi.Problem * 32)()
+    for g in range(32):
+        probs[g] = _cabi.Problem(0x1000, 0x2000, None, 0x3000, 1, q * B, p * B, p, q, _cabi.F16, _cabi.F16, 0, 0)
+    n = L.bcl_group_plan_bytes_for(probs, 32, B, sdt, 148)
+    buf = (ctypes.c_uint8 * n)()
+    assert L.bcl_group_plan_encode(probs, 32, B, sdt, 148, ctypes.addressof(buf), n) == 0
+    return _decode(bytes(buf))[0]["variant"]
+
+
+def test_group_plan_selects_the_pipelined_kernels_for_every_sweep_shape(monkeypatch):
+    """BASELINE configs[3] (block-size sweep: in = out in {4096, 11008}, B in {64, 128, 256}) and the Llama shapes: the grouped decode
+    launch must run the warp-specialised TMA kernels (variant 1 = split-q, fp32 spectra; 2 = row-per-warp, bf16 spectra), never the plain
+    fallback (variant 0) -- 11008 at B = 64 (q = 172) silently fell back once (144 us against 42 us per 32-layer launch)."""
+    monkeypatch.delenv("BCL_GROUP_VARIANT", raising=False)
+    for dim in (4096, 11008):
+        for B in (64, 128, 256):
+            q = dim // B
+            assert _variant((q, q), B, _cabi.F32) == 1, (dim, B)
+            assert _variant((q, q), B, _cabi.BF16) == 2, (dim, B)
+    # (70B down_proj, 28672 -> 8192 at B = 256, is refused by the grouped call -- its 112 KB x spectrum leaves no room for a ring -- and
+    #  goes through bcl_forward per module)
+    for shape, B in (((32, 86), 128), ((86, 32), 128), ((32, 32), 256), ((112, 32), 256), ((4, 32), 256)):
+        assert _variant(shape, B, _cabi.F32) == 1 and _variant(shape, B, _cabi.BF16) == 2, (shape, B)
+
+
 def test_group_plan_covers_every_row_once_and_balances_bytes(monkeypatch):
     # one Llama-2-7B decoder layer x 4: q,k,v,o (32x32), gate, up (86x32), down (32x86) at B=128
     layer = [(32, 32)] * 4 + [(86, 32)] * 2 + [(32, 86)]
