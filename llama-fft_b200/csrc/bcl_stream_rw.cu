@@ -13,6 +13,7 @@
 //   last 4 warps     finishers: inverse real FFT of 4 rows at once, 1/B, round to x.dtype, + bias, store y
 #include <cstdlib>
 #include <cstdio>
+#include <type_traits>
 #include "bcl_stream_parts.cuh"
 
 namespace bcl {
@@ -245,12 +246,14 @@ __global__ void __launch_bounds__(mix_threads(B), 1) stream_rw_kernel(const Prob
                     const SpecT* cbuf = reinterpret_cast<const SpecT*>(ring + (size_t)stage * STAGE_BYTES);
                     const int nblk = min(CB, q - cs * CB);
                     const float* xrow = xs + (size_t)cs * CB * B;
-                    for (int u0 = 0; u0 < nblk; u0 += UB) {
+                    // one batch of UB blocks; FULL: all of them exist (the common case: no per-block predicate, no zero fill)
+                    auto batch = [&](int u0, auto fullc) {
+                        constexpr bool FULL = decltype(fullc)::value;
                         RawChunk<SpecT, CW> raw[UB][CH];
                         float xv[UB][CH][CW];
 #pragma unroll
                         for (int u = 0; u < UB; ++u) {                // all shared loads first: one latency per batch
-                            const bool on = u0 + u < nblk;
+                            const bool on = FULL || u0 + u < nblk;
 #pragma unroll
                             for (int ch = 0; ch < CH; ++ch) {
                                 if (on) {
@@ -285,6 +288,11 @@ __global__ void __launch_bounds__(mix_threads(B), 1) stream_rw_kernel(const Prob
                             }
                             // packed slot 0/1 of lane 0 is (DC, Nyquist): real x real products, already in p1[..][0][0].lo and p2[..][0][0].lo
                         }
+                    
+                    };
+                    for (int u0 = 0; u0 < nblk; u0 += UB) {
+                        if (u0 + UB <= nblk) batch(u0, std::true_type{});
+                        else batch(u0, std::false_type{});
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->empty[stage]);   // the producer may refill this stage
