@@ -236,6 +236,7 @@ __device__ inline void finish_pairs(const ProblemDev& P, int j_first, int64_t n0
     using LM = LaneMap<B>;
     using C = FftCfg<B>;
     constexpr int CH = LM::CH, CW = LM::CW;
+    if constexpr (NPART > 1)                                            // (one partial per pair: it already is the spectrum)
     for (int p = 0; p < npairs; ++p) {
         float* slot = part + (size_t)p * NPART * B;
         float sum[CH][CW];
