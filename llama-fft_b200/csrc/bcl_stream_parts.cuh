@@ -207,6 +207,26 @@ __device__ __forceinline__ void store_block_epilogue(const ProblemDev& P, int64_
     using C = FftCfg<B>;
     const float inv_b = 1.0f / (float)B;
     const int64_t colbase = (int64_t)j * B;
+    if (P.bias == nullptr && P.n_extra == 0 && P.y_dtype == P.x_dtype && P.x_dtype != BCL_F32) {
+        // the common decode case (16-bit activations, no bias, one destination): the store's round-to-nearest-even conversion IS the
+        // reference's y32.to(x.dtype) (:266) -- one address computation, one convert-and-pack and one store per sample pair instead
+        // of round / reconvert / promote / dtype switches; every instruction counts on the single finishing warp's path.
+        uint16_t* yb = reinterpret_cast<uint16_t*>(P.y) + n * P.y_stride + colbase;
+        const bool bf = P.x_dtype == BCL_BF16;
+#pragma unroll
+        for (int jj = 0; jj < C::OPT; ++jj) {
+#pragma unroll
+            for (int k2 = 0; k2 < C::T; ++k2) {
+                const int m = (t * C::OPT + jj) + C::V * k2;
+                const float2 v = out[jj * C::T + k2];
+                uint32_t w;
+                if (bf) { __nv_bfloat162 h = __floats2bfloat162_rn(v.x * inv_b, v.y * inv_b); w = *reinterpret_cast<uint32_t*>(&h); }
+                else { __half2 h = __floats2half2_rn(v.x * inv_b, v.y * inv_b); w = *reinterpret_cast<uint32_t*>(&h); }
+                *reinterpret_cast<uint32_t*>(yb + 2 * m) = w;
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int jj = 0; jj < C::OPT; ++jj) {
 #pragma unroll
