@@ -125,6 +125,22 @@ __device__ __forceinline__ float2 twiddle_m(const float2* tw, int e) {
     return w;
 }
 
+// Per-lane twiddles of the two-level transform, fetched once: w1[k1] = w_M^{t k1} (level-1 twiddle of point k1) and wk[it] = w_B^k of
+// the lane's (k, M-k) pairs.  A warp that transforms group after group (the decode kernels' finishers) keeps them in registers
+// instead of 12 dependent shared-memory lookups (index arithmetic + load + sign fix) on every transform's critical path.
+template <int B> struct FftTw {
+    float2 w1[FftCfg<B>::V];
+    float2 wk[FftCfg<B>::NPAIR];
+};
+template <int B>
+__device__ __forceinline__ void fft_tw_init(FftTw<B>& f, const float2* tw, int t) {
+    using C = FftCfg<B>;
+#pragma unroll
+    for (int k1 = 0; k1 < C::V; ++k1) f.w1[k1] = twiddle_m<B>(tw, t * k1);
+#pragma unroll
+    for (int it = 0; it < C::NPAIR; ++it) f.wk[it] = tw[min(t + C::T * it, C::M / 2)];
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Forward.  Lane t (0..T-1) of a block's group passes a[n1] = z[T*n1 + t] = (x[2(T n1 + t)], x[2(T n1 + t)+1]).
 // Writes the packed half-spectrum {Re X0, Re X_{B/2}, Re X1, Im X1, ...} to dst[0..B) (shared, linear) if active.
@@ -196,8 +212,8 @@ __device__ __forceinline__ void group_rfft_packed(float2 (&a)[FftCfg<B>::V], flo
 // Inverse.  src[0..B): packed half-spectrum (shared, linear).  Returns, UNSCALED (caller multiplies by 1/B), for
 // j < OPT, k2 < T:   out[j*T + k2] = ( y[2m], y[2m+1] )  with  m = (t*OPT + j) + V*k2.
 // ---------------------------------------------------------------------------------------------------------
-template <int B>
-__device__ __forceinline__ void group_irfft_packed(const float* src, float2* scr, const float2* tw, int t, float2 (&out)[FftCfg<B>::V]) {
+template <int B, bool PRE>
+__device__ __forceinline__ void group_irfft_packed_impl(const float* src, float2* scr, const float2* tw, const FftTw<B>* pre, int t, float2 (&out)[FftCfg<B>::V]) {
     using C = FftCfg<B>;
     constexpr int M = C::M, V = C::V, T = C::T, OPT = C::OPT, PITCH = C::PITCH;
     // E = Xk + conj(Xm);  O = conj(w^k) (Xk - conj(Xm));  Z[k] = E + i O;  Z[M-k] = conj(E) + i conj(O)
@@ -209,7 +225,7 @@ __device__ __forceinline__ void group_irfft_packed(const float* src, float2* scr
         const float2 a0 = *reinterpret_cast<const float2*>(src + 2 * k), a1 = *reinterpret_cast<const float2*>(src + 2 * ((M - k) & (M - 1)));
         xk[it] = (k == 0) ? make_float2(a0.x, 0.f) : a0;             // packed slot 0 is (DC, Nyquist), both real
         xm[it] = (k == 0) ? make_float2(a0.y, 0.f) : a1;
-        wk[it] = tw[k];
+        if constexpr (PRE) wk[it] = pre->wk[it]; else wk[it] = tw[k];
     }
     float2 za[C::NPAIR], zb[C::NPAIR];
 #pragma unroll
@@ -238,7 +254,7 @@ __device__ __forceinline__ void group_irfft_packed(const float* src, float2* scr
 #pragma unroll
     for (int k1 = 0; k1 < V; ++k1) {
         float2 A = a[brev_n(k1, V)];
-        if (k1 > 0) A = c_mulc(A, twiddle_m<B>(tw, t * k1));
+        if (k1 > 0) { if constexpr (PRE) A = c_mulc(A, pre->w1[k1]); else A = c_mulc(A, twiddle_m<B>(tw, t * k1)); }
         scr[k1 * PITCH + t] = A;
     }
     __syncwarp();
@@ -253,6 +269,15 @@ __device__ __forceinline__ void group_irfft_packed(const float* src, float2* scr
         for (int k2 = 0; k2 < T; ++k2) out[j * T + k2] = b[brev_n(k2, T)];
     }
     __syncwarp();
+}
+
+template <int B>
+__device__ __forceinline__ void group_irfft_packed(const float* src, float2* scr, const float2* tw, int t, float2 (&out)[FftCfg<B>::V]) {
+    group_irfft_packed_impl<B, false>(src, scr, tw, nullptr, t, out);
+}
+template <int B>
+__device__ __forceinline__ void group_irfft_packed(const float* src, float2* scr, const FftTw<B>& pre, int t, float2 (&out)[FftCfg<B>::V]) {
+    group_irfft_packed_impl<B, true>(src, scr, nullptr, &pre, t, out);
 }
 
 // time-domain element pair (2m, 2m+1) -> activation dtype helpers -------------------------------------------------

@@ -252,7 +252,8 @@ __device__ __forceinline__ void store_block_epilogue(const ProblemDev& P, int64_
 //   part : [pair][NPART][B] floats, already offset to this warp's first pair; absolute pair pair0 + p is
 //          row (j_first + (pair0+p) / NT), token (n0 + (pair0+p) % NT)
 template <int B, int NT, int NPART>
-__device__ inline void finish_pairs(const ProblemDev& P, int j_first, int64_t n0, float* part, int pair0, int npairs, const float2* tw, float2* fscr, int lane) {
+__device__ __forceinline__ void finish_pairs(const ProblemDev& P, int j_first, int64_t n0, float* part, int pair0, int npairs, const float2* tw, float2* fscr, int lane,
+                                    const FftTw<B>* pre = nullptr) {
     using LM = LaneMap<B>;
     using C = FftCfg<B>;
     constexpr int CH = LM::CH, CW = LM::CW;
@@ -284,7 +285,8 @@ __device__ inline void finish_pairs(const ProblemDev& P, int j_first, int64_t n0
     const int g = lane / C::T, t = lane % C::T;
     const int pg = min(g, npairs - 1);                              // idle groups shadow the last pair (no stores)
     float2 out[C::V];
-    group_irfft_packed<B>(part + (size_t)pg * NPART * B, fscr + g * C::GROUP_F2, tw, t, out);
+    if (pre != nullptr) group_irfft_packed<B>(part + (size_t)pg * NPART * B, fscr + g * C::GROUP_F2, *pre, t, out);   // (resolved at compile time after inlining)
+    else group_irfft_packed<B>(part + (size_t)pg * NPART * B, fscr + g * C::GROUP_F2, tw, t, out);
     const int slot_row = (pair0 + pg) / NT, n = (pair0 + pg) - slot_row * NT;
     if (g < npairs && n0 + n < P.N) store_block_epilogue<B>(P, n0 + n, j_first + slot_row, t, out);
     __syncwarp();

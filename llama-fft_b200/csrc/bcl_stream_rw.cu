@@ -364,6 +364,8 @@ __global__ void __launch_bounds__(mix_threads(B), 1) stream_rw_kernel(const Prob
         // ===================== finishers =====================
         const int f = warp - NP - NM - NX;
         float2* fscr = fscr_all + (size_t)(NX + f) * (FC::WARP_SCRATCH_BYTES / 8);
+        FftTw<B> ftw;                                                    // this lane's twiddles, once (B = 256: 25 pairs are too many registers)
+        if constexpr (B <= 128) fft_tw_init<B>(ftw, tw, lane % FC::T);
         pdl_wait();                                                      // y may still be read by the previous grid
         int gi = 0;
         long long t_all0 = clk(), t_w = 0, t_b = 0; int ngr = 0; (void)t_all0; (void)t_w; (void)t_b; (void)ngr;
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(mix_threads(B), 1) stream_rw_kernel(const Prob
                 const int nr = min(RG, rows - g0);
                 float* gpart = part + (size_t)gb * RG * B;
                 for (int p0 = 0; p0 < nr; p0 += FC::G)
-                    finish_pairs<B, NT, 1>(P, w.j0 + g0, 0, gpart + (size_t)p0 * B, p0, min(FC::G, nr - p0), tw, fscr, lane);
+                    finish_pairs<B, NT, 1>(P, w.j0 + g0, 0, gpart + (size_t)p0 * B, p0, min(FC::G, nr - p0), tw, fscr, lane, B <= 128 ? &ftw : nullptr);
                 __syncwarp();
                 if (lane == 0) { __threadfence_block(); bars->accepts[gb] = gi + NG; }    // the buffer takes group gi + NG next
                 TSTOP(b, t_b);
