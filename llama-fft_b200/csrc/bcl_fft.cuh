@@ -146,15 +146,15 @@ __device__ __forceinline__ void fft_tw_init(FftTw<B>& f, const float2* tw, int t
 // Writes the packed half-spectrum {Re X0, Re X_{B/2}, Re X1, Im X1, ...} to dst[0..B) (shared, linear) if active.
 // scr: this block's scratch (GROUP_F2 float2).  All 32 lanes must call (warp-level syncs inside).
 // ---------------------------------------------------------------------------------------------------------
-template <int B>
-__device__ __forceinline__ void group_rfft_packed(float2 (&a)[FftCfg<B>::V], float2* scr, float* dst, const float2* tw, int t, bool active) {
+template <int B, bool PRE>
+__device__ __forceinline__ void group_rfft_packed_impl(float2 (&a)[FftCfg<B>::V], float2* scr, float* dst, const float2* tw, const FftTw<B>* pre, int t, bool active) {
     using C = FftCfg<B>;
     constexpr int M = C::M, V = C::V, T = C::T, OPT = C::OPT, PITCH = C::PITCH;
     fft_reg<V, false>(a);
 #pragma unroll
     for (int k1 = 0; k1 < V; ++k1) {
         float2 A = a[brev_n(k1, V)];
-        if (k1 > 0) A = c_mul(A, twiddle_m<B>(tw, t * k1));
+        if (k1 > 0) { if constexpr (PRE) A = c_mul(A, pre->w1[k1]); else A = c_mul(A, twiddle_m<B>(tw, t * k1)); }
         scr[k1 * PITCH + t] = A;
     }
     __syncwarp();
@@ -181,7 +181,8 @@ __device__ __forceinline__ void group_rfft_packed(float2 (&a)[FftCfg<B>::V], flo
 #pragma unroll
     for (int it = 0; it < C::NPAIR; ++it) {
         const int k = min(t + T * it, M / 2);                        // clamped: always a valid pair, surplus lanes recompute pair M/2
-        zk[it] = scr[k]; zm[it] = scr[(M - k) & (M - 1)]; wk[it] = tw[k];
+        zk[it] = scr[k]; zm[it] = scr[(M - k) & (M - 1)];
+        if constexpr (PRE) wk[it] = pre->wk[it]; else wk[it] = tw[k];
     }
     float2 xa[C::NPAIR], xb[C::NPAIR];
 #pragma unroll
@@ -206,6 +207,15 @@ __device__ __forceinline__ void group_rfft_packed(float2 (&a)[FftCfg<B>::V], flo
         }
     }
     __syncwarp();
+}
+
+template <int B>
+__device__ __forceinline__ void group_rfft_packed(float2 (&a)[FftCfg<B>::V], float2* scr, float* dst, const float2* tw, int t, bool active) {
+    group_rfft_packed_impl<B, false>(a, scr, dst, tw, nullptr, t, active);
+}
+template <int B>
+__device__ __forceinline__ void group_rfft_packed(float2 (&a)[FftCfg<B>::V], float2* scr, float* dst, const FftTw<B>& pre, int t, bool active) {
+    group_rfft_packed_impl<B, true>(a, scr, dst, nullptr, &pre, t, active);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -56,7 +56,8 @@ __device__ __forceinline__ void convert_x_raw(const XRaw<V>& r, int dt, float2 (
 }
 
 template <int B, int NT, int NWARPS, int PITCH = B, bool CG = false>
-__device__ inline void load_x_spectrum(const ProblemDev& P, int64_t n0, float* xs, const float2* tw, float2* fscr, int lane, int warp) {
+__device__ __forceinline__ void load_x_spectrum(const ProblemDev& P, int64_t n0, float* xs, const float2* tw, float2* fscr, int lane, int warp,
+                                                const FftTw<B>* pre = nullptr) {
     using C = FftCfg<B>;
     const int q = P.q;
     const int nb = NT * q;
@@ -82,7 +83,8 @@ __device__ inline void load_x_spectrum(const ProblemDev& P, int64_t n0, float* x
         }
         float2 a[C::V];
         convert_x_raw<C::V>(cur, P.x_dtype, a);
-        group_rfft_packed<B>(a, scr, xs + (size_t)idx * PITCH, tw, t, active);
+        if (pre != nullptr) group_rfft_packed<B>(a, scr, xs + (size_t)idx * PITCH, *pre, t, active);   // (resolved at compile time after inlining)
+        else group_rfft_packed<B>(a, scr, xs + (size_t)idx * PITCH, tw, t, active);
         if (!more) break;
         cur = nxt; base = nbase; idx = idx2; n = n2; i = i2; active = act2;
     }

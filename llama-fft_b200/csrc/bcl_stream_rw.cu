@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(mix_threads(B), 1) stream_rw_kernel(const Prob
         float2* fscr = fscr_all + (size_t)xw * (FC::WARP_SCRATCH_BYTES / 8);
         ProblemDev P0{};
         if (s0 < s1) P0 = problems[segs[s0].g];                          // plan data: constant, fetched while the previous grid drains
+        // (keeping the lane's twiddles in registers here, as the finishers do, pushes the kernel over its 96 registers: measured slower)
         pdl_wait();                                                      // x may have been written by the previous grid
         if (s0 < s1) {
             load_x_spectrum<B, NT, NM + NX>(P0, 0, xs_all, tw, fscr, lane, NM + xw);

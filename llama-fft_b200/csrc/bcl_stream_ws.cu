@@ -496,9 +496,12 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
         // this CTA can count as done (below), so no CTA can see the number this launch will leave.
         int mark = 0;
         if (n_dyn > 0) mark = __ldcg(dyn_ctr + 2) + 1;
+        FftTw<B> xtw;                                                    // this lane's twiddles, once (static plans, B <= 128)
+        if constexpr (B <= 128 && !DYN) fft_tw_init<B>(xtw, tw, lane % FC::T);
+        const FftTw<B>* xtwp = (B <= 128 && !DYN) ? &xtw : nullptr;
         if (any) {                                                       // first segment: together with the MAC warps (see there)
             TSTART(y0);
-            load_x_spectrum<B, NT, NM + NX>(P0, 0, xs, tw, fscr, lane, NM + xw);
+            load_x_spectrum<B, NT, NM + NX>(P0, 0, xs, tw, fscr, lane, NM + xw, xtwp);
             asm volatile("bar.sync 1, %0;" ::"r"(32 * (NM + NX)) : "memory");
             TSTOP(y0, t_b);
         }
@@ -537,7 +540,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
             if (k < ns) {
                 TSTART(y);
                 if constexpr (DYN) x_warps_rfft<B>(problems + w.g, xs, tw, fscr, lane, xw);
-                else { const ProblemDev P = problems[w.g]; load_x_spectrum<B, NT, NX>(P, 0, xs, tw, fscr, lane, xw); }
+                else { const ProblemDev P = problems[w.g]; load_x_spectrum<B, NT, NX>(P, 0, xs, tw, fscr, lane, xw, xtwp); }
                 TSTOP(y, t_b);
             } else if (DYN) {
                 float4* dst = reinterpret_cast<float4*>(xs);
@@ -579,6 +582,8 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
 #endif
         int gi = 0;
         SegWork w; int qf = 0;
+        FftTw<B> ftw;                                                    // this lane's twiddles, once (B = 256: too many registers)
+        if constexpr (B <= 128) fft_tw_init<B>(ftw, tw, lane % FC::T);
         for (int k = 0; fetch(k, w, qf); ++k) {
             const ProblemDev P = problems[w.g];
             const int rows = w.j1 - w.j0;
@@ -590,7 +595,7 @@ __global__ void __launch_bounds__(THREADS, 1) stream_ws_kernel(const ProblemDev*
                 TSTART(fin);
                 float* gpart = part + (size_t)gb * PAIRS * NM * B;
                 for (int p0 = 0; p0 < nr; p0 += FC::G)
-                    finish_pairs<B, NT, NM>(P, w.j0 + g0, 0, gpart + (size_t)p0 * NM * B, p0, min(FC::G, nr - p0), tw, fscr, lane);
+                    finish_pairs<B, NT, NM>(P, w.j0 + g0, 0, gpart + (size_t)p0 * NM * B, p0, min(FC::G, nr - p0), tw, fscr, lane, B <= 128 ? &ftw : nullptr);
                 TSTOP(fin, t_b);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->gempty[gb]);
