@@ -119,7 +119,8 @@ template <int DT> __device__ __forceinline__ int act_dt(int runtime_dt) { if con
 // rfft of the q input blocks of P.x (one token) into xs[q][B], cooperatively by the NC compute warps (this is warp m): a pass of all
 // warps covers NC * G blocks, the raw loads of up to four passes are issued before the first transform (one exposed L2 latency).
 template <int B, int DT>
-__device__ __forceinline__ void chain_load_x(const ProblemDev& P, float* xs, const float2* tw, float2* fscr, int lane, int m, long long* dbgp, uint64_t* issued) {
+__device__ __forceinline__ void chain_load_x(const ProblemDev& P, float* xs, const float2* tw, float2* fscr, int lane, int m, long long* dbgp, uint64_t* issued,
+                                             const FftTw<B>* pre) {
     using C = FftCfg<B>;
     constexpr int PASS = NC * C::G;
     constexpr int MAXP = 4;
@@ -171,7 +172,8 @@ __device__ __forceinline__ void chain_load_x(const ProblemDev& P, float* xs, con
                 float2 a[C::V];
                 convert_x_raw<C::V>(raw[ps], dt, a);
                 if (dbgp != nullptr && ps == 0 && b0 == 0) { float sacc = 0.f; for (int n1 = 0; n1 < C::V; ++n1) sacc += a[n1].x; if (sacc == 1.2345e30f) xs[0] = sacc; dbgp[6] = clock64(); }
-                group_rfft_packed<B>(a, scr, xs + (size_t)(i0 + g) * B, tw, t, i0 + g < q);
+                if (pre != nullptr) group_rfft_packed<B>(a, scr, xs + (size_t)(i0 + g) * B, *pre, t, i0 + g < q);   // lane twiddles in registers
+                else group_rfft_packed<B>(a, scr, xs + (size_t)(i0 + g) * B, tw, t, i0 + g < q);
                 if (dbgp != nullptr && ps == 0 && b0 == 0) dbgp[7] = clock64();
             }
         }
@@ -214,7 +216,8 @@ __device__ __forceinline__ void sum_partials_stage1(float* part, int ng, int m, 
 
 // One warp: finish the sums, inverse real FFT of all slots at once (one T-lane group per slot), epilogue.
 template <int B, int DT>
-__device__ __forceinline__ void finish_slots(const ProblemDev& P, int u0, int slot0, float* part, int nslots, const float2* tw, float2* fscr, int lane, long long* dbgp) {
+__device__ __forceinline__ void finish_slots(const ProblemDev& P, int u0, int slot0, float* part, int nslots, const float2* tw, float2* fscr, int lane, long long* dbgp,
+                                             const FftTw<B>* pre) {
     using LM = LaneMap<B>;
     using C = FftCfg<B>;
     constexpr int CH = LM::CH, CW = LM::CW;
@@ -255,7 +258,8 @@ __device__ __forceinline__ void finish_slots(const ProblemDev& P, int u0, int sl
     const int pg = min(g, nslots - 1);                               // idle groups shadow the last slot (no stores)
     float2 out[C::V];
     if (dbgp != nullptr) dbgp[16] = clock64();
-    group_irfft_packed<B>(part + (size_t)pg * NC * B, fscr + g * C::GROUP_F2, tw, t, out);
+    if (pre != nullptr) group_irfft_packed<B>(part + (size_t)pg * NC * B, fscr + g * C::GROUP_F2, *pre, t, out);
+    else group_irfft_packed<B>(part + (size_t)pg * NC * B, fscr + g * C::GROUP_F2, tw, t, out);
     if (dbgp != nullptr) { float sacc = 0.f; for (int v = 0; v < C::V; ++v) sacc += out[v].x; if (sacc == 1.2345e30f) part[0] = sacc; dbgp[17] = clock64(); }
     const float inv_b = 1.0f / (float)B;
     const int dt = act_dt<DT>(P.y_dtype);                            // (== x_dtype unless a bias promotes: then the general path below)
@@ -329,7 +333,8 @@ __device__ __forceinline__ void finish_slots(const ProblemDev& P, int u0, int sl
 #pragma unroll
         for (int n1 = 0; n1 < C::V; ++n1) a[n1] = *reinterpret_cast<const float2*>(tbuf + 2 * (C::T * n1 + t));
         __syncwarp();
-        group_rfft_packed<B>(a, fscr + g * C::GROUP_F2, tbuf + B, tw, t, owner);
+        if (pre != nullptr) group_rfft_packed<B>(a, fscr + g * C::GROUP_F2, tbuf + B, *pre, t, owner);
+        else group_rfft_packed<B>(a, fscr + g * C::GROUP_F2, tbuf + B, tw, t, owner);
         float* ys = reinterpret_cast<float*>(P.y_spectrum);
         const int nblk = swiglu ? (nslots + 1) / 2 : nslots;
         for (int b = 0; b < nblk; ++b) {                             // coalesced write-out, one block (B floats) per iteration
@@ -445,6 +450,9 @@ __global__ void __launch_bounds__(THREADS, 1) chain_kernel(const __grid_constant
     unsigned long long base = 0;
     if (sp.nsteps > 1 && m == 0 && lane == 0) base = ld_acquire_u64(sp.counter) & ~(QUANTUM - 1);
     bool first_x = true;                                             // (a CTA without work in step 0 never signals: the producer's wait is bounded)
+    FftTw<B> ftw;                                                    // this lane's FFT twiddles, fetched once: every transform of every step sits on
+    if constexpr (B <= 128) fft_tw_init<B>(ftw, tw, lane % FftCfg<B>::T);   // the latency path (B = 256: 25 pairs are too many registers)
+    const FftTw<B>* pre = B <= 128 ? &ftw : nullptr;
     for (int step = 0; step < sp.nsteps; ++step) {
         BCL_CHAIN_STAMP(0);
         if (step > 0) {
@@ -472,7 +480,7 @@ __global__ void __launch_bounds__(THREADS, 1) chain_kernel(const __grid_constant
             const int q = P.q;
             const int nslots = (u1 - u0) * ((P.epilogue & BCL_EPILOGUE_SWIGLU) ? 2 : 1);
             chain_load_x<B, DT>(P, xs, tw, fscr, lane, m, (sp.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 32) ? sp.dbg + step * 8 : nullptr,
-                                first_x ? &bars->xissued : nullptr);
+                                first_x ? &bars->xissued : nullptr, pre);
             first_x = false;
             compute_sync();
             BCL_CHAIN_STAMP(2);
@@ -539,7 +547,7 @@ __global__ void __launch_bounds__(THREADS, 1) chain_kernel(const __grid_constant
                     sum_partials_stage1<B>(part, ng, m, lane);
                     compute_sync();
                 }
-                if (m == 0) finish_slots<B, DT>(P, u0, s0, part, ng, tw, fscr, lane, (sp.dbg != nullptr && blockIdx.x == 0 && lane == 0) ? sp.dbg + step * 8 : nullptr);
+                if (m == 0) finish_slots<B, DT>(P, u0, s0, part, ng, tw, fscr, lane, (sp.dbg != nullptr && blockIdx.x == 0 && lane == 0) ? sp.dbg + step * 8 : nullptr, pre);
                 compute_sync();                                      // part / xs may be overwritten; warp 1's stores are issued
                 BCL_CHAIN_STAMP(4);
             }
