@@ -560,7 +560,7 @@ def bf16_decode_detail(bc, _cabi, dev, shapes, args, steps=1000):
     del groups
     torch.cuda.empty_cache()
     return {"ms_per_step": ms, "tokens_per_s": 1.0 / (ms * 1e-3), "algorithmic_bytes_per_launch": alg, "hbm_frac_of_measured_peak": alg / (ms * 1e-3) / 1e9 / peak,
-            "note": "row-per-warp kernel (bcl_stream_rw.cu): with 8 KB rows the split-q kernel of the headline is bound by its per-row hand-offs, not by HBM; profiles/r1_prefill_notes.md"}
+            "note": "row-per-warp kernel (bcl_stream_rw.cu: packed FFMA2 MAC loop, 3 TMA producer warps, 20-warp CTA): with 8 KB rows the split-q kernel of the headline is bound by its per-row hand-offs, not by HBM; DESIGN 3.3b"}
 
 
 def independent_launch_detail(bc, groups, dev, shapes, alg, steps=2000):
