@@ -9,8 +9,8 @@
 // and the finisher only inverse-transforms.  Eight rows are in flight per CTA; the hand-offs per row drop eightfold.
 //   NP = 3 warps     TMA producers (identical ring protocol: one bulk copy per (row, stage-of-row); producer w takes chunks w mod NP)
 //   next 8 warps     row warps: rows r = m, m + 8, ... of the CTA's running row sequence
-//   next 5 warps     X warps: rfft(x) of the next segment into the other half of a double-buffered X buffer
-//   last 4 warps     finishers: inverse real FFT of 4 rows at once, 1/B, round to x.dtype, + bias, store y
+//   next 6 warps     X warps: rfft(x) of the next segment into the other half of a double-buffered X buffer
+//   last 3 warps     finishers: inverse real FFT of 4 rows at once, 1/B, round to x.dtype, + bias, store y
 #include <cstdlib>
 #include <cstdio>
 #include <type_traits>
@@ -22,11 +22,14 @@ namespace rw {
 // Warp mix.  17 to 20 warps put five warps on an SM sub-partition, which caps a thread at 96 registers (16 warps: 128); B = 64 / 128 need
 // 92-93, so once the third producer is there two more warps are free.  Measured at 20 warps, bf16, 224 projections (NP / NX / NF):
 // 3/5/4: 26.1 us, 3/4/4 (19 warps): 26.4, 3/4/5: 26.7, 2/6/4: 27.1, 3/4/3 (18): 27.2, 3/6/3: 27.5, 4/4/4: 28.6, 4/5/3: 28.8, 2/5/5: 28.9.
+// Measured again after the finisher path was shortened (no partial-sum pass, convert-and-pack epilogue, lane twiddles in registers):
+// three finishers are enough and the sixth X warp pays -- 3/6/3: 23.1 us (70.2 %), 3/6/3 with 6 group buffers: 23.2, 3/7/2: 23.4,
+// 3/5/4: 23.9, 3/5/3: 24.0, 3/4/4: 24.2, 4/5/3: 26.1.
 #ifndef BCL_RW_NF
-#define BCL_RW_NF 4
+#define BCL_RW_NF 3
 #endif
 #ifndef BCL_RW_NX
-#define BCL_RW_NX 5
+#define BCL_RW_NX 6
 #endif
 #ifndef BCL_RW_NG
 #define BCL_RW_NG BCL_RW_NF
